@@ -1,0 +1,914 @@
+/*
+ * oracle_global.c -- TEST INFRASTRUCTURE ONLY (see phasta_oracle.h).
+ *
+ * Restatement of the global-level routines of the hot path: ElmGMRe, qpbc,
+ * bc3LHS/bc3Res/bc3BDg/bc3per, commu (in-process over all parts), sumgat,
+ * i3LU, i3pre, Au1GMR/AsAuGMR, SolGMRe.  Fortran layouts throughout.
+ */
+#include "oracle_internal.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+int orc_sizeof_part(void) { return (int)sizeof(orc_part); }
+int orc_sizeof_common(void) { return (int)sizeof(orc_common); }
+
+/* ---------------- tables ---------------- */
+/* genint.f:30-75 (symtet 1/4-pt, symtet.c rstw1/rstw4, Qwt*4/3) and
+ * genshp.f:34-37 (shptet, TetShapeAndDrv p=1 uniformP.c:8-35, shgl/2).
+ * Pinned against the reference's own C generators by tests/golden. */
+void orc_tet_tables(int rule, int *nint, double *Qwt, double *shp,
+                    double *shgl) {
+  const double a4 = 0.5854101966249685, b4 = 0.1381966011250150;
+  double pts[4][4];
+  double w[4];
+  int n;
+  if (rule == 1) {
+    n = 1;
+    for (int j = 0; j < 4; j++) pts[0][j] = 0.25;
+    w[0] = 1.0;
+  } else if (rule == 2) {
+    n = 4;
+    for (int i = 0; i < 4; i++) {
+      for (int j = 0; j < 4; j++) pts[i][j] = (i == j) ? a4 : b4;
+      w[i] = 0.25;
+    }
+  } else {
+    fprintf(stderr, "orc_tet_tables: rule %d not restated\n", rule);
+    abort();
+  }
+  nint[0] = n;
+  for (int i = 0; i < n; i++) {
+    Qwt[0 + ORC_MAXTOP * i] = (4.0 / 3.0) * w[i];
+    double L[4] = {pts[i][0], pts[i][1], pts[i][2],
+                   1.0 - pts[i][0] - pts[i][1] - pts[i][2]};
+    for (int a = 0; a < 4; a++) {
+      shp[0 + ORC_MAXTOP * (a + ORC_MAXSH * i)] = L[a];
+      for (int j = 0; j < 3; j++) {
+        double dN = (a == 3) ? -1.0 : ((a == j) ? 1.0 : 0.0);
+        shgl[0 + ORC_MAXTOP * (j + 3 * (a + ORC_MAXSH * i))] = dN / 2.0;
+      }
+    }
+  }
+}
+
+/* ---------------- commu (common/commu.f:131-295) ---------------- */
+static const int *find_task(const orc_part *q, int itag, int iother,
+                            int want_iacc) {
+  const int *il = q->ilwork;
+  int numtask = il[0], itk = 1;
+  for (int t = 0; t < numtask; t++) {
+    if (il[itk] == itag && il[itk + 2] == iother && il[itk + 1] == want_iacc)
+      return il + itk;
+    itk += 4 + 2 * il[itk + 3];
+  }
+  return NULL;
+}
+
+void orc_commu(int nparts, orc_part *parts, double **global, int n, int code) {
+  if (nparts <= 1) return;
+  for (int m = 0; m < nparts; m++) {
+    const orc_part *pm = &parts[m];
+    const int *il = pm->ilwork;
+    int numtask = il[0], itk = 1;
+    int nshg_m = pm->c.nshg;
+    for (int t = 0; t < numtask; t++) {
+      int itag = il[itk], iacc = il[itk + 1], iother = il[itk + 2],
+          numseg = il[itk + 3];
+      if (iacc == 1) {
+        /* master task: partner is the slave part's matching send task */
+        const orc_part *ps = &parts[iother];
+        const int *ts = find_task(ps, itag, m, 0);
+        if (!ts) {
+          fprintf(stderr, "orc_commu: no partner for tag %d\n", itag);
+          abort();
+        }
+        int nshg_s = ps->c.nshg;
+        /* flatten the slave's segment list */
+        int snum = ts[3];
+        for (int idof = 0; idof < n; idof++) {
+          int sseg = 0, spos = 0; /* cursor in the slave's segments */
+          for (int is = 0; is < numseg; is++) {
+            int isgbeg = il[itk + 4 + 2 * is], lenseg = il[itk + 5 + 2 * is];
+            for (int k = 0; k < lenseg; k++) {
+              while (sseg < snum && spos >= ts[5 + 2 * sseg]) {
+                sseg++;
+                spos = 0;
+              }
+              int snode = ts[4 + 2 * sseg] + spos - 1;
+              int mnode = isgbeg + k - 1;
+              spos++;
+              if (code == 0)
+                global[m][mnode + (size_t)nshg_m * idof] +=
+                    global[iother][snode + (size_t)nshg_s * idof];
+              else
+                global[iother][snode + (size_t)nshg_s * idof] =
+                    global[m][mnode + (size_t)nshg_m * idof];
+            }
+          }
+        }
+      }
+      itk += 4 + 2 * numseg;
+    }
+  }
+}
+
+/* zero (or identity for BDiag) the rows owned by another part
+ * (bc3res.f:177-196, au1gmr.f:81-100, bc3bdg.f:364-386) */
+static void zero_slaves(const orc_part *p, double *r, int n, int identity) {
+  if (p->c.numpe <= 1) return;
+  const int *il = p->ilwork;
+  int numtask = il[0], itk = 1, nshg = p->c.nshg;
+  for (int t = 0; t < numtask; t++) {
+    int iacc = il[itk + 1], numseg = il[itk + 3];
+    if (iacc == 0)
+      for (int is = 0; is < numseg; is++) {
+        int isgbeg = il[itk + 4 + 2 * is], lenseg = il[itk + 5 + 2 * is];
+        for (int k = 0; k < lenseg; k++) {
+          int A = isgbeg + k - 1;
+          for (int j = 0; j < n; j++) r[A + (size_t)nshg * j] = 0.0;
+          if (identity)
+            for (int j = 0; j < 5; j++) r[A + (size_t)nshg * (j + 5 * j)] = 1.0;
+        }
+      }
+    itk += 4 + 2 * numseg;
+  }
+}
+
+/* sumgat (common/mpitools.f:107-137) */
+double orc_sumgat(int nparts, orc_part *parts, double **u, int n) {
+  double summed = 0.0;
+  for (int m = 0; m < nparts; m++) {
+    double s = 0.0;
+    size_t len = (size_t)parts[m].c.nshg * n;
+    for (size_t i = 0; i < len; i++) s += u[m][i];
+    summed += s;
+  }
+  return summed;
+}
+
+/* ---------------- qpbc (common/qpbc.f:1-115) ---------------- */
+void orc_qpbc(int nparts, orc_part *parts) {
+  double **q = malloc(sizeof(double *) * nparts),
+         **rm = malloc(sizeof(double *) * nparts);
+  for (int m = 0; m < nparts; m++) {
+    q[m] = parts[m].qres;
+    rm[m] = parts[m].rmass;
+  }
+  orc_commu(nparts, parts, q, 12, 0);
+  orc_commu(nparts, parts, rm, 1, 0);
+  for (int m = 0; m < nparts; m++) {
+    orc_part *p = &parts[m];
+    int nshg = p->c.nshg;
+    for (int j = 0; j < nshg; j++)
+      if (p->iBC[j] & (1 << 10)) {
+        int i = p->iper[j] - 1;
+        p->rmass[i] += p->rmass[j];
+        for (int k = 0; k < 12; k++)
+          p->qres[i + (size_t)nshg * k] += p->qres[j + (size_t)nshg * k];
+      }
+    for (int j = 0; j < nshg; j++)
+      if (p->iBC[j] & (1 << 10)) {
+        int i = p->iper[j] - 1;
+        p->rmass[j] = p->rmass[i];
+        for (int k = 0; k < 12; k++)
+          p->qres[j + (size_t)nshg * k] = p->qres[i + (size_t)nshg * k];
+      }
+    for (int j = 0; j < nshg; j++) p->rmass[j] = 1.0 / p->rmass[j];
+    for (int k = 0; k < 12; k++)
+      for (int j = 0; j < nshg; j++)
+        p->qres[j + (size_t)nshg * k] = p->rmass[j] * p->qres[j + (size_t)nshg * k];
+  }
+  orc_commu(nparts, parts, q, 12, 1);
+  free(q);
+  free(rm);
+}
+
+/* ---------------- bc3LHS (compressible/bc3lhs.f:1-290) ---------------- */
+void orc_bc3lhs_block(const orc_part *p, int iblk, double *EGmass) {
+  const orc_common *c = &p->c;
+  const int *lc = p->lcblk + 10 * iblk;
+  int iel0 = lc[0], nshl = lc[9];
+  int npro = lc[10] - iel0;
+  const int *ien = p->ien + p->ien_off[iblk];
+  int nedof = c->nedof, nshg = c->nshg;
+  size_t numel = (size_t)c->numel;
+  int nd = 5 * nshl; /* the reference loops 1..nedof; rows beyond 5*nshl are
+                        zero for this block */
+  (void)nd;
+#define EGm(r, cc) \
+  EGmass[(size_t)(iel0 - 1 + iel) + numel * (((r)-1) + (size_t)nedof * ((cc)-1))]
+#define BCv(in, k) p->BC[(in) + (size_t)nshg * ((k)-1)]
+  for (int iel = 0; iel < npro; iel++)
+    for (int inod = 1; inod <= nshl; inod++) {
+      int in = abs(ien[iel + (size_t)npro * (inod - 1)]) - 1;
+      int ibc = p->iBC[in];
+      if (ibc == 0) continue;
+      int ioff = (inod - 1) * 5;
+      int i1 = ioff + 1, i2 = ioff + 2, i3 = ioff + 3, i4 = ioff + 4,
+          i5 = ioff + 5;
+      if (ibc & (1 << 2)) { /* pressure */
+        for (int i = 1; i <= nedof; i++) {
+          EGm(i, i1) = 0.0;
+          EGm(i1, i) = 0.0;
+        }
+        EGm(i1, i1) = 1.0;
+      }
+      int vcode = (ibc >> 3) & 7;
+      /* one-velocity codes 1,2,4: (ia eliminated; ib, ic get BC4, BC5) */
+      if (vcode == 1 || vcode == 2 || vcode == 4) {
+        int ia, ib, ic;
+        if (vcode == 1) { ia = i2; ib = i3; ic = i4; }
+        else if (vcode == 2) { ia = i3; ib = i2; ic = i4; }
+        else { ia = i4; ib = i2; ic = i3; }
+        for (int i = 1; i <= nedof; i++) {
+          EGm(ib, i) = EGm(ib, i) - BCv(in, 4) * EGm(ia, i);
+          EGm(ic, i) = EGm(ic, i) - BCv(in, 5) * EGm(ia, i);
+        }
+        for (int i = 1; i <= nedof; i++) {
+          EGm(i, ib) = EGm(i, ib) - BCv(in, 4) * EGm(i, ia);
+          EGm(i, ic) = EGm(i, ic) - BCv(in, 5) * EGm(i, ia);
+        }
+        for (int i = 1; i <= nedof; i++) {
+          EGm(i, ia) = 0.0;
+          EGm(ia, i) = 0.0;
+        }
+        EGm(ia, ia) = 1.0;
+      }
+      /* two-velocity codes 3,5,6: (ia, ib eliminated; ic gets BC4, BC6) */
+      if (vcode == 3 || vcode == 5 || vcode == 6) {
+        int ia, ib, ic;
+        if (vcode == 3) { ia = i2; ib = i3; ic = i4; }
+        else if (vcode == 5) { ia = i2; ib = i4; ic = i3; }
+        else { ia = i3; ib = i4; ic = i2; }
+        for (int i = 1; i <= nedof; i++)
+          EGm(ic, i) = EGm(ic, i) - BCv(in, 4) * EGm(ia, i) -
+                       BCv(in, 6) * EGm(ib, i);
+        for (int i = 1; i <= nedof; i++)
+          EGm(i, ic) = EGm(i, ic) - BCv(in, 4) * EGm(i, ia) -
+                       BCv(in, 6) * EGm(i, ib);
+        for (int i = 1; i <= nedof; i++) {
+          EGm(i, ia) = 0.0;
+          EGm(ia, i) = 0.0;
+          EGm(i, ib) = 0.0;
+          EGm(ib, i) = 0.0;
+        }
+        EGm(ia, ia) = 1.0;
+        EGm(ib, ib) = 1.0;
+      }
+      if (vcode == 7) {
+        for (int i = 1; i <= nedof; i++) {
+          EGm(i, i2) = 0.0;
+          EGm(i2, i) = 0.0;
+          EGm(i, i3) = 0.0;
+          EGm(i3, i) = 0.0;
+          EGm(i, i4) = 0.0;
+          EGm(i4, i) = 0.0;
+        }
+        EGm(i2, i2) = 1.0;
+        EGm(i3, i3) = 1.0;
+        EGm(i4, i4) = 1.0;
+      }
+      if (ibc & (1 << 1)) { /* temperature */
+        for (int i = 1; i <= nedof; i++) {
+          EGm(i, i5) = 0.0;
+          EGm(i5, i) = 0.0;
+        }
+        EGm(i5, i5) = 1.0;
+      }
+      if (ibc & (1 << 11)) {
+        fprintf(stderr, "oracle bc3LHS: SPEBC (bit 11) not restated\n");
+        abort();
+      }
+    }
+#undef EGm
+}
+
+/* ---------------- bc3Res (compressible/bc3res.f:30-196) ---------------- */
+void orc_bc3res(const orc_part *p, double *res) {
+  const orc_common *c = &p->c;
+  int nshg = c->nshg;
+#define R(i, k) res[(i) + (size_t)nshg * ((k)-1)]
+  for (int i = 0; i < nshg; i++) {
+    int ibc = p->iBC[i];
+    if (ibc & 1) { /* density (:30-33) */
+      R(i, 5) = R(i, 5) + BCv(i, 1) * c->Rgas * R(i, 1);
+      R(i, 1) = 0.0;
+    }
+  }
+  if (c->EntropyPressure == 1) {
+    fprintf(stderr, "oracle bc3Res: EntropyPressure=1 not restated\n");
+    abort();
+  }
+  for (int i = 0; i < nshg; i++)
+    if (p->iBC[i] & (1 << 2)) R(i, 1) = 0.0;
+  for (int i = 0; i < nshg; i++) {
+    int v = (p->iBC[i] >> 3) & 7;
+    switch (v) {
+      case 1:
+        R(i, 3) = R(i, 3) - BCv(i, 4) * R(i, 2);
+        R(i, 4) = R(i, 4) - BCv(i, 5) * R(i, 2);
+        R(i, 2) = 0.0;
+        break;
+      case 2:
+        R(i, 2) = R(i, 2) - BCv(i, 4) * R(i, 3);
+        R(i, 4) = R(i, 4) - BCv(i, 5) * R(i, 3);
+        R(i, 3) = 0.0;
+        break;
+      case 3:
+        R(i, 4) = R(i, 4) - BCv(i, 4) * R(i, 2) - BCv(i, 6) * R(i, 3);
+        R(i, 2) = 0.0;
+        R(i, 3) = 0.0;
+        break;
+      case 4:
+        R(i, 2) = R(i, 2) - BCv(i, 4) * R(i, 4);
+        R(i, 3) = R(i, 3) - BCv(i, 5) * R(i, 4);
+        R(i, 4) = 0.0;
+        break;
+      case 5:
+        R(i, 3) = R(i, 3) - BCv(i, 4) * R(i, 2) - BCv(i, 6) * R(i, 4);
+        R(i, 2) = 0.0;
+        R(i, 4) = 0.0;
+        break;
+      case 6:
+        R(i, 2) = R(i, 2) - BCv(i, 4) * R(i, 3) - BCv(i, 6) * R(i, 4);
+        R(i, 3) = 0.0;
+        R(i, 4) = 0.0;
+        break;
+      case 7:
+        R(i, 2) = 0.0;
+        R(i, 3) = 0.0;
+        R(i, 4) = 0.0;
+        break;
+      default:
+        break;
+    }
+  }
+  for (int i = 0; i < nshg; i++)
+    if (p->iBC[i] & (1 << 11)) {
+      fprintf(stderr, "oracle bc3Res: SPEBC (bit 11) not restated\n");
+      abort();
+    }
+  for (int i = 0; i < nshg; i++)
+    if (p->iBC[i] & (1 << 1)) R(i, 5) = 0.0;
+  /* local periodicity (:157-163) */
+  for (int j = 0; j < nshg; j++)
+    if (p->iBC[j] & (1 << 10)) {
+      int i = p->iper[j] - 1;
+      for (int k = 1; k <= 5; k++) {
+        R(i, k) = R(i, k) + R(j, k);
+        R(j, k) = 0.0;
+      }
+    }
+  zero_slaves(p, res, 5, 0);
+#undef R
+}
+
+/* bc3per (compressible/bc3per.f:28-34) */
+void orc_bc3per(const orc_part *p, double *r, int nQs) {
+  int nshg = p->c.nshg;
+  for (int j = 0; j < nshg; j++)
+    if (p->iBC[j] & (1 << 10)) {
+      int i = p->iper[j] - 1;
+      for (int k = 0; k < nQs; k++) {
+        r[i + (size_t)nshg * k] += r[j + (size_t)nshg * k];
+        r[j + (size_t)nshg * k] = 0.0;
+      }
+    }
+}
+
+/* ---------------- bc3BDg (compressible/bc3bdg.f:39-388) ---------------- */
+void orc_bc3bdg(const orc_part *p, double *BDiag) {
+  const orc_common *c = &p->c;
+  int nshg = c->nshg;
+#define B(i, r, cc) BDiag[(i) + (size_t)nshg * (((r)-1) + 5 * ((cc)-1))]
+  for (int i = 0; i < nshg; i++) {
+    int ibc = p->iBC[i];
+    if (ibc & 1) { /* density (:49-70) */
+      double a5 = -p->y[i + (size_t)nshg * 4] * (c->Rgas * c->gamma / c->gamma1);
+      B(i, 5, 5) = B(i, 5, 5) + a5 * a5 * B(i, 1, 1) + a5 * B(i, 1, 5) +
+                   a5 * B(i, 5, 1);
+      B(i, 4, 5) = B(i, 4, 5) + a5 * B(i, 4, 1);
+      B(i, 3, 5) = B(i, 3, 5) + a5 * B(i, 3, 1);
+      B(i, 2, 5) = B(i, 2, 5) + a5 * B(i, 2, 1);
+      B(i, 5, 4) = B(i, 5, 4) + a5 * B(i, 1, 4);
+      B(i, 5, 3) = B(i, 5, 3) + a5 * B(i, 1, 3);
+      B(i, 5, 2) = B(i, 5, 2) + a5 * B(i, 1, 2);
+      for (int k = 2; k <= 5; k++) {
+        B(i, 1, k) = 0.0;
+        B(i, k, 1) = 0.0;
+      }
+      B(i, 1, 1) = 1.0;
+    }
+  }
+  for (int i = 0; i < nshg; i++)
+    if (p->iBC[i] & (1 << 2)) { /* pressure (:72-82) */
+      for (int k = 2; k <= 5; k++) {
+        B(i, 1, k) = 0.0;
+        B(i, k, 1) = 0.0;
+      }
+      B(i, 1, 1) = 1.0;
+    }
+  for (int i = 0; i < nshg; i++) {
+    int v = (p->iBC[i] >> 3) & 7;
+    double b4 = BCv(i, 4), b5 = BCv(i, 5), b6 = BCv(i, 6);
+    if (v == 1 || v == 2 || v == 4) {
+      /* (:86-118,120-152,186-218): a eliminated; b gets b4, cdof gets b5 */
+      int a, b, d;
+      if (v == 1) { a = 2; b = 3; d = 4; }
+      else if (v == 2) { a = 3; b = 2; d = 4; }
+      else { a = 4; b = 2; d = 3; }
+      B(i, 5, d) = B(i, 5, d) - b5 * B(i, 5, a);
+      B(i, 5, b) = B(i, 5, b) - b4 * B(i, 5, a);
+      B(i, d, 5) = B(i, d, 5) - b5 * B(i, a, 5);
+      B(i, b, 5) = B(i, b, 5) - b4 * B(i, a, 5);
+      B(i, d, 1) = B(i, d, 1) - b5 * B(i, a, 1);
+      B(i, b, 1) = B(i, b, 1) - b4 * B(i, a, 1);
+      B(i, 1, d) = B(i, 1, d) - b5 * B(i, 1, a);
+      B(i, 1, b) = B(i, 1, b) - b4 * B(i, 1, a);
+      B(i, d, d) = B(i, d, d) + b5 * b5 * B(i, a, a) - b5 * B(i, a, d) -
+                   b5 * B(i, d, a);
+      B(i, b, d) = B(i, b, d) + b4 * b5 * B(i, a, a) - b5 * B(i, b, a) -
+                   b4 * B(i, a, d);
+      B(i, d, b) = B(i, d, b) + b4 * b5 * B(i, a, a) - b5 * B(i, a, b) -
+                   b4 * B(i, d, a);
+      B(i, b, b) = B(i, b, b) + b4 * b4 * B(i, a, a) - b4 * B(i, a, b) -
+                   b4 * B(i, b, a);
+      for (int k = 1; k <= 5; k++)
+        if (k != a) {
+          B(i, a, k) = 0.0;
+          B(i, k, a) = 0.0;
+        }
+      B(i, a, a) = 1.0;
+    } else if (v == 3) {
+      /* (:154-184) NOTE the reference multiplies the cross terms
+       * (BDiag(2,3)*BDiag(3,2) etc.) where v=5,6 add them; kept verbatim */
+      B(i, 4, 4) = B(i, 4, 4) + b4 * b4 * B(i, 2, 2) + b6 * b6 * B(i, 3, 3) +
+                   b4 * b6 * (B(i, 2, 3) * B(i, 3, 2)) -
+                   b6 * (B(i, 4, 3) * B(i, 3, 4)) -
+                   b4 * (B(i, 4, 2) * B(i, 2, 4));
+      B(i, 1, 4) = B(i, 1, 4) - b4 * B(i, 1, 2) - b6 * B(i, 1, 3);
+      B(i, 4, 1) = B(i, 4, 1) - b4 * B(i, 2, 1) - b6 * B(i, 3, 1);
+      B(i, 5, 4) = B(i, 5, 4) - b4 * B(i, 5, 2) - b6 * B(i, 5, 3);
+      B(i, 4, 5) = B(i, 4, 5) - b4 * B(i, 2, 5) - b6 * B(i, 3, 5);
+      for (int k = 1; k <= 5; k++) {
+        if (k != 2) { B(i, 2, k) = 0.0; B(i, k, 2) = 0.0; }
+        if (k != 3) { B(i, 3, k) = 0.0; B(i, k, 3) = 0.0; }
+      }
+      B(i, 3, 3) = 1.0;
+      B(i, 2, 2) = 1.0;
+    } else if (v == 5 || v == 6) {
+      /* (:220-252,254-286): a,b eliminated; d kept (gets b4 from a, b6 from b) */
+      int a, b, d;
+      if (v == 5) { a = 2; b = 4; d = 3; }
+      else { a = 3; b = 4; d = 2; }
+      B(i, d, d) = B(i, d, d) + b4 * b4 * B(i, a, a) + b6 * b6 * B(i, b, b) +
+                   b4 * b6 * (B(i, a, b) + B(i, b, a)) -
+                   b4 * (B(i, a, d) + B(i, d, a)) -
+                   b6 * (B(i, b, d) + B(i, d, b));
+      B(i, 1, d) = B(i, 1, d) - b4 * B(i, 1, a) - b6 * B(i, 1, b);
+      B(i, d, 1) = B(i, d, 1) - b4 * B(i, a, 1) - b6 * B(i, b, 1);
+      B(i, 5, d) = B(i, 5, d) - b4 * B(i, 5, a) - b6 * B(i, 5, b);
+      B(i, d, 5) = B(i, d, 5) - b4 * B(i, a, 5) - b6 * B(i, b, 5);
+      /* the reference's v=5 zero list (:236-249) names BDiag(4,2) twice and
+       * never BDiag(3,2): that entry survives.  Kept verbatim. */
+      double keep32 = B(i, 3, 2);
+      for (int k = 1; k <= 5; k++) {
+        if (k != a) { B(i, a, k) = 0.0; B(i, k, a) = 0.0; }
+        if (k != b) { B(i, b, k) = 0.0; B(i, k, b) = 0.0; }
+      }
+      if (v == 5) B(i, 3, 2) = keep32;
+      B(i, b, b) = 1.0;
+      B(i, a, a) = 1.0;
+    } else if (v == 7) {
+      for (int a = 2; a <= 4; a++) {
+        for (int k = 1; k <= 5; k++)
+          if (k != a) {
+            B(i, a, k) = 0.0;
+            B(i, k, a) = 0.0;
+          }
+        B(i, a, a) = 1.0;
+      }
+    }
+  }
+  for (int i = 0; i < nshg; i++)
+    if (p->iBC[i] & (1 << 1)) { /* temperature (:322-332) */
+      B(i, 5, 5) = 1.0;
+      for (int k = 1; k <= 4; k++) {
+        B(i, k, 5) = 0.0;
+        B(i, 5, k) = 0.0;
+      }
+    }
+  /* periodicity (:337-352) */
+  for (int j = 0; j < nshg; j++)
+    if (p->iBC[j] & (1 << 10)) {
+      int i = p->iper[j] - 1;
+      for (int k = 0; k < 25; k++)
+        BDiag[i + (size_t)nshg * k] += BDiag[j + (size_t)nshg * k];
+    }
+  for (int j = 0; j < nshg; j++)
+    if (p->iBC[j] & (1 << 10)) {
+      int i = p->iper[j] - 1;
+      for (int k = 0; k < 25; k++)
+        BDiag[j + (size_t)nshg * k] = BDiag[i + (size_t)nshg * k];
+    }
+  zero_slaves(p, BDiag, 25, 1);
+#undef B
+}
+#undef BCv
+
+/* ---------------- ElmGMRe (compressible/elmgmr.f:1-274) ---------------- */
+void orc_elmgmre(int nparts, orc_part *parts) {
+  for (int m = 0; m < nparts; m++) {
+    orc_part *p = &parts[m];
+    p->c.ires = 1; /* elmgmr.f:56 */
+  }
+  if (parts[0].c.idiff == 1 || parts[0].c.idiff == 3) {
+    for (int m = 0; m < nparts; m++) {
+      orc_part *p = &parts[m];
+      size_t nshg = (size_t)p->c.nshg;
+      memset(p->qres, 0, sizeof(double) * nshg * 12);
+      memset(p->rmass, 0, sizeof(double) * nshg);
+      for (int iblk = 0; iblk < p->c.nelblk; iblk++)
+        orc_asiq(p, iblk, p->qres, p->rmass);
+    }
+    orc_qpbc(nparts, parts);
+  }
+  for (int m = 0; m < nparts; m++) {
+    orc_part *p = &parts[m];
+    const orc_common *c = &p->c;
+    size_t nshg = (size_t)c->nshg;
+    memset(p->res, 0, sizeof(double) * nshg * 5);
+    if (p->rmes) memset(p->rmes, 0, sizeof(double) * nshg * 5);
+    if (c->lhs == 1)
+      memset(p->EGmass, 0,
+             sizeof(double) * (size_t)c->numel * c->nedof * c->nedof);
+    if (c->iprec != 0) memset(p->BDiag, 0, sizeof(double) * nshg * 25);
+    for (int iblk = 0; iblk < c->nelblk; iblk++) {
+      orc_asigmr(p, iblk, p->qres, p->res, p->BDiag,
+                 c->lhs == 1 ? p->EGmass : NULL);
+      if (c->lhs == 1) orc_bc3lhs_block(p, iblk, p->EGmass);
+    }
+    for (int iblk = 0; iblk < c->nelblb; iblk++) orc_asbmfg(p, iblk, p->res);
+  }
+  if (nparts > 1) {
+    double **g = malloc(sizeof(double *) * nparts);
+    for (int m = 0; m < nparts; m++) g[m] = parts[m].res;
+    orc_commu(nparts, parts, g, 5, 0);
+    if (parts[0].c.iprec != 0) {
+      for (int m = 0; m < nparts; m++) g[m] = parts[m].BDiag;
+      orc_commu(nparts, parts, g, 25, 0);
+    }
+    free(g);
+  }
+  for (int m = 0; m < nparts; m++) {
+    orc_part *p = &parts[m];
+    orc_bc3res(p, p->res);
+    if (p->c.iprec != 0) orc_bc3bdg(p, p->BDiag);
+  }
+}
+
+/* ---------------- i3LU (compressible/i3lu.f:41-165) ---------------- */
+void orc_i3lu(const orc_common *c, double *Diag, double *r, int code) {
+  int nshg = c->nshg;
+#define D(i, a, b) Diag[(i) + (size_t)nshg * (((a)-1) + 5 * ((b)-1))]
+#define Rr(i, a) r[(i) + (size_t)nshg * ((a)-1)]
+  for (int i = 0; i < nshg; i++) {
+    if (code == 0) {
+      D(i, 1, 1) = 1.0 / D(i, 1, 1);
+      D(i, 2, 1) = D(i, 1, 1) * D(i, 2, 1);
+      D(i, 3, 1) = D(i, 1, 1) * D(i, 3, 1);
+      D(i, 4, 1) = D(i, 1, 1) * D(i, 4, 1);
+      D(i, 5, 1) = D(i, 1, 1) * D(i, 5, 1);
+      D(i, 2, 2) = D(i, 2, 2) - D(i, 2, 1) * D(i, 1, 2);
+      D(i, 2, 3) = D(i, 2, 3) - D(i, 2, 1) * D(i, 1, 3);
+      D(i, 2, 4) = D(i, 2, 4) - D(i, 2, 1) * D(i, 1, 4);
+      D(i, 2, 5) = D(i, 2, 5) - D(i, 2, 1) * D(i, 1, 5);
+      D(i, 2, 2) = 1.0 / D(i, 2, 2);
+      D(i, 3, 2) = D(i, 2, 2) * (D(i, 3, 2) - D(i, 3, 1) * D(i, 1, 2));
+      D(i, 4, 2) = D(i, 2, 2) * (D(i, 4, 2) - D(i, 4, 1) * D(i, 1, 2));
+      D(i, 5, 2) = D(i, 2, 2) * (D(i, 5, 2) - D(i, 5, 1) * D(i, 1, 2));
+      D(i, 3, 3) = D(i, 3, 3) - D(i, 3, 1) * D(i, 1, 3) - D(i, 3, 2) * D(i, 2, 3);
+      D(i, 3, 4) = D(i, 3, 4) - D(i, 3, 1) * D(i, 1, 4) - D(i, 3, 2) * D(i, 2, 4);
+      D(i, 3, 5) = D(i, 3, 5) - D(i, 3, 1) * D(i, 1, 5) - D(i, 3, 2) * D(i, 2, 5);
+      D(i, 3, 3) = 1.0 / D(i, 3, 3);
+      D(i, 4, 3) = D(i, 3, 3) * (D(i, 4, 3) - D(i, 4, 1) * D(i, 1, 3) -
+                                 D(i, 4, 2) * D(i, 2, 3));
+      D(i, 5, 3) = D(i, 3, 3) * (D(i, 5, 3) - D(i, 5, 1) * D(i, 1, 3) -
+                                 D(i, 5, 2) * D(i, 2, 3));
+      D(i, 4, 4) = D(i, 4, 4) - D(i, 4, 1) * D(i, 1, 4) -
+                   D(i, 4, 2) * D(i, 2, 4) - D(i, 4, 3) * D(i, 3, 4);
+      D(i, 4, 4) = 1.0 / D(i, 4, 4);
+      D(i, 5, 4) = D(i, 4, 4) * (D(i, 5, 4) - D(i, 5, 1) * D(i, 1, 4) -
+                                 D(i, 5, 2) * D(i, 2, 4) - D(i, 5, 3) * D(i, 3, 4));
+      D(i, 5, 5) = D(i, 5, 5) - D(i, 5, 1) * D(i, 1, 5) -
+                   D(i, 5, 2) * D(i, 2, 5) - D(i, 5, 3) * D(i, 3, 5) -
+                   D(i, 5, 4) * D(i, 4, 5);
+      D(i, 5, 5) = 1.0 / D(i, 5, 5);
+    } else if (code == 1) {
+      Rr(i, 2) = Rr(i, 2) - D(i, 2, 1) * Rr(i, 1);
+      Rr(i, 3) = Rr(i, 3) - D(i, 3, 1) * Rr(i, 1) - D(i, 3, 2) * Rr(i, 2);
+      Rr(i, 4) = Rr(i, 4) - D(i, 4, 1) * Rr(i, 1) - D(i, 4, 2) * Rr(i, 2) -
+                 D(i, 4, 3) * Rr(i, 3);
+      Rr(i, 5) = Rr(i, 5) - D(i, 5, 1) * Rr(i, 1) - D(i, 5, 2) * Rr(i, 2) -
+                 D(i, 5, 3) * Rr(i, 3) - D(i, 5, 4) * Rr(i, 4);
+    } else if (code == 2) {
+      Rr(i, 5) = D(i, 5, 5) * Rr(i, 5);
+      Rr(i, 4) = D(i, 4, 4) * (Rr(i, 4) - Rr(i, 5) * D(i, 4, 5));
+      Rr(i, 3) = D(i, 3, 3) *
+                 (Rr(i, 3) - Rr(i, 5) * D(i, 3, 5) - Rr(i, 4) * D(i, 3, 4));
+      Rr(i, 2) = D(i, 2, 2) * (Rr(i, 2) - Rr(i, 5) * D(i, 2, 5) -
+                               Rr(i, 4) * D(i, 2, 4) - Rr(i, 3) * D(i, 2, 3));
+      Rr(i, 1) = D(i, 1, 1) *
+                 (Rr(i, 1) - Rr(i, 5) * D(i, 1, 5) - Rr(i, 4) * D(i, 1, 4) -
+                  Rr(i, 3) * D(i, 1, 3) - Rr(i, 2) * D(i, 1, 2));
+    } else if (code == 3) {
+      Rr(i, 1) = Rr(i, 1) / D(i, 1, 1) + Rr(i, 2) * D(i, 1, 2) +
+                 Rr(i, 3) * D(i, 1, 3) + Rr(i, 4) * D(i, 1, 4) +
+                 Rr(i, 5) * D(i, 1, 5);
+      Rr(i, 2) = Rr(i, 2) / D(i, 2, 2) + Rr(i, 3) * D(i, 2, 3) +
+                 Rr(i, 4) * D(i, 2, 4) + Rr(i, 5) * D(i, 2, 5);
+      Rr(i, 3) = Rr(i, 3) / D(i, 3, 3) + Rr(i, 4) * D(i, 3, 4) +
+                 Rr(i, 5) * D(i, 3, 5);
+      Rr(i, 4) = Rr(i, 4) / D(i, 4, 4) + Rr(i, 5) * D(i, 4, 5);
+      Rr(i, 5) = Rr(i, 5) / D(i, 5, 5);
+    }
+  }
+#undef D
+#undef Rr
+}
+
+/* ---------------- i3pre (compressible/i3pre.f:27-133) ---------------- */
+void orc_i3pre(int nparts, orc_part *parts) {
+  double **tmp = malloc(sizeof(double *) * nparts);
+  for (int m = 0; m < nparts; m++) {
+    size_t n = (size_t)parts[m].c.nshg * 25;
+    tmp[m] = malloc(sizeof(double) * n);
+    memcpy(tmp[m], parts[m].BDiag, sizeof(double) * n); /* BDiag = BDtmp */
+  }
+  orc_commu(nparts, parts, tmp, 25, 1);
+  for (int m = 0; m < nparts; m++) {
+    orc_part *p = &parts[m];
+    const orc_common *c = &p->c;
+    int nshg = c->nshg, nedof = c->nedof;
+    size_t numel = (size_t)c->numel;
+    const double *BD = tmp[m];
+    for (int iblk = 0; iblk < c->nelblk; iblk++) {
+      const int *lc = p->lcblk + 10 * iblk;
+      int iel0 = lc[0], nshl = lc[9];
+      int npro = lc[10] - iel0;
+      const int *ien = p->ien + p->ien_off[iblk];
+#define EGm(r, cc) \
+  p->EGmass[(size_t)(iel0 - 1 + iv) + numel * (((r)-1) + (size_t)nedof * ((cc)-1))]
+#define BDl(a, b) BD[A + (size_t)nshg * (((a)-1) + 5 * ((b)-1))]
+      for (int inode = 1; inode <= nshl; inode++) {
+        int i = (inode - 1) * 5;
+        for (int j = 1; j <= nedof; j++)
+          for (int iv = 0; iv < npro; iv++) {
+            int A = abs(ien[iv + (size_t)npro * (inode - 1)]) - 1;
+            EGm(i + 2, j) = EGm(i + 2, j) - BDl(2, 1) * EGm(i + 1, j);
+            EGm(i + 3, j) = EGm(i + 3, j) - BDl(3, 1) * EGm(i + 1, j) -
+                            BDl(3, 2) * EGm(i + 2, j);
+            EGm(i + 4, j) = EGm(i + 4, j) - BDl(4, 1) * EGm(i + 1, j) -
+                            BDl(4, 2) * EGm(i + 2, j) - BDl(4, 3) * EGm(i + 3, j);
+            EGm(i + 5, j) = EGm(i + 5, j) - BDl(5, 1) * EGm(i + 1, j) -
+                            BDl(5, 2) * EGm(i + 2, j) - BDl(5, 3) * EGm(i + 3, j) -
+                            BDl(5, 4) * EGm(i + 4, j);
+          }
+      }
+      for (int inode = 1; inode <= nshl; inode++) {
+        int i = (inode - 1) * 5;
+        for (int j = 1; j <= nedof; j++)
+          for (int iv = 0; iv < npro; iv++) {
+            int A = abs(ien[iv + (size_t)npro * (inode - 1)]) - 1;
+            EGm(j, i + 1) = BDl(1, 1) * EGm(j, i + 1);
+            EGm(j, i + 2) = BDl(2, 2) * (EGm(j, i + 2) - BDl(1, 2) * EGm(j, i + 1));
+            EGm(j, i + 3) = BDl(3, 3) * (EGm(j, i + 3) - BDl(1, 3) * EGm(j, i + 1) -
+                                         BDl(2, 3) * EGm(j, i + 2));
+            EGm(j, i + 4) = BDl(4, 4) * (EGm(j, i + 4) - BDl(1, 4) * EGm(j, i + 1) -
+                                         BDl(2, 4) * EGm(j, i + 2) -
+                                         BDl(3, 4) * EGm(j, i + 3));
+            EGm(j, i + 5) = BDl(5, 5) * (EGm(j, i + 5) - BDl(1, 5) * EGm(j, i + 1) -
+                                         BDl(2, 5) * EGm(j, i + 2) -
+                                         BDl(3, 5) * EGm(j, i + 3) -
+                                         BDl(4, 5) * EGm(j, i + 4));
+          }
+      }
+#undef EGm
+#undef BDl
+    }
+    free(tmp[m]);
+  }
+  free(tmp);
+}
+
+/* ---------------- Au1GMR + AsAuGMR (au1gmr.f:29-101, asaugmr.f:26-74) ---- */
+void orc_au1gmr(int nparts, orc_part *parts, double **u) {
+  orc_commu(nparts, parts, u, 5, 1);
+  for (int m = 0; m < nparts; m++) {
+    orc_part *p = &parts[m];
+    const orc_common *c = &p->c;
+    int nshg = c->nshg, nedof = c->nedof;
+    size_t numel = (size_t)c->numel;
+    double *ub = u[m];
+    /* uBrg(:,j)=uBrg(iper(:),j) (:35-37) */
+    for (int j = 0; j < 5; j++)
+      for (int i = 0; i < nshg; i++)
+        ub[i + (size_t)nshg * j] = ub[(p->iper[i] - 1) + (size_t)nshg * j];
+    double *uBtmp = calloc((size_t)nshg * 5, sizeof(double));
+    for (int iblk = 0; iblk < c->nelblk; iblk++) {
+      const int *lc = p->lcblk + 10 * iblk;
+      int iel0 = lc[0], nshl = lc[9];
+      int npro = lc[10] - iel0;
+      const int *ien = p->ien + p->ien_off[iblk];
+      int nd = 5 * nshl;
+      double *ubBgl = calloc((size_t)npro * nd, sizeof(double));
+      for (int e = 0; e < npro; e++) {
+        double ul[5 * ORC_MAXSH];
+        for (int jn = 0; jn < nshl; jn++) {
+          int A = abs(ien[e + (size_t)npro * jn]) - 1;
+          for (int i = 0; i < 5; i++) ul[5 * jn + i] = ub[A + (size_t)nshg * i];
+        }
+        for (int i = 0; i < nd; i += 5)
+          for (int j = 0; j < nd; j += 5)
+            for (int ii = 0; ii < 5; ii++) {
+              double acc = ubBgl[e + (size_t)npro * (i + ii)];
+              for (int jj = 0; jj < 5; jj++)
+                acc += p->EGmass[(size_t)(iel0 - 1 + e) +
+                                 numel * ((i + ii) + (size_t)nedof * (j + jj))] *
+                       ul[j + jj];
+              ubBgl[e + (size_t)npro * (i + ii)] = acc;
+            }
+      }
+      /* localt scatter (localt.f:62-70): node, dof, element */
+      for (int jn = 0; jn < nshl; jn++)
+        for (int i = 0; i < 5; i++)
+          for (int e = 0; e < npro; e++) {
+            int A = abs(ien[e + (size_t)npro * jn]) - 1;
+            uBtmp[A + (size_t)nshg * i] += ubBgl[e + (size_t)npro * (5 * jn + i)];
+          }
+      free(ubBgl);
+    }
+    memcpy(ub, uBtmp, sizeof(double) * (size_t)nshg * 5);
+    free(uBtmp);
+  }
+  orc_commu(nparts, parts, u, 5, 0);
+  for (int m = 0; m < nparts; m++) zero_slaves(&parts[m], u[m], 5, 0);
+}
+
+/* ---------------- GMRES shared by SolGMRe / SolGMRs ---------------- */
+typedef void (*ap_fn)(int, orc_part *, double **);
+
+static void gmres_core(int nparts, orc_part *parts, ap_fn Ap, int minIters,
+                       double *HBrg, double *eBrg, double *yBrg, double *Rcos,
+                       double *Rsin, int *iKs_out, int *lGMRES_out,
+                       int *ntotGM) {
+  const orc_common *c = &parts[0].c;
+  int Kspace = c->Kspace, nGMRES = c->nGMRES;
+  double **v = malloc(sizeof(double *) * nparts);
+  double **t = malloc(sizeof(double *) * nparts);
+#define UB(m, k) (parts[m].uBrg + (size_t)parts[m].c.nshg * 5 * ((k)-1))
+#define H(a, b) HBrg[((a)-1) + (size_t)(Kspace + 1) * ((b)-1)]
+  /* uBrg(:,:,1) = res; unorm (solgmr.f:120-127) */
+  for (int m = 0; m < nparts; m++) {
+    size_t n = (size_t)parts[m].c.nshg * 5;
+    memcpy(UB(m, 1), parts[m].res, sizeof(double) * n);
+    for (size_t i = 0; i < n; i++) parts[m].temp[i] = parts[m].res[i] * parts[m].res[i];
+    t[m] = parts[m].temp;
+  }
+  double unorm = sqrt(orc_sumgat(nparts, parts, t, 5));
+  int iKs = 0, lGMRES = 0;
+  if (unorm < 100.0 * c->epsM * c->epsM) goto done; /* :136 */
+  double epsnrm = c->etol * unorm;
+  for (int mGMRES = 1; mGMRES <= nGMRES; mGMRES++) {
+    lGMRES = mGMRES - 1;
+    if (lGMRES > 0) { /* restart: R - A x (:149-178) */
+      for (int m = 0; m < nparts; m++) {
+        size_t n = (size_t)parts[m].c.nshg * 5;
+        memcpy(parts[m].temp, parts[m].Dy, sizeof(double) * n);
+        t[m] = parts[m].temp;
+      }
+      Ap(nparts, parts, t);
+      for (int m = 0; m < nparts; m++) {
+        size_t n = (size_t)parts[m].c.nshg * 5;
+        orc_bc3per(&parts[m], parts[m].temp, 5);
+        for (size_t i = 0; i < n; i++) {
+          parts[m].temp[i] = parts[m].res[i] - parts[m].temp[i];
+          UB(m, 1)[i] = parts[m].temp[i];
+          parts[m].temp[i] = parts[m].temp[i] * parts[m].temp[i];
+        }
+      }
+      unorm = sqrt(orc_sumgat(nparts, parts, t, 5));
+    }
+    for (int k = 0; k < Kspace + 1; k++) eBrg[k] = 0.0;
+    eBrg[0] = unorm;
+    for (int m = 0; m < nparts; m++) {
+      size_t n = (size_t)parts[m].c.nshg * 5;
+      for (size_t i = 0; i < n; i++) UB(m, 1)[i] = UB(m, 1)[i] / unorm;
+    }
+    for (int iK = 1; iK <= Kspace; iK++) {
+      iKs = iK;
+      for (int m = 0; m < nparts; m++) {
+        size_t n = (size_t)parts[m].c.nshg * 5;
+        memcpy(UB(m, iKs + 1), UB(m, iKs), sizeof(double) * n);
+        v[m] = UB(m, iKs + 1);
+      }
+      Ap(nparts, parts, v);
+      for (int m = 0; m < nparts; m++) orc_bc3per(&parts[m], v[m], 5);
+      /* modified Gram-Schmidt (:224-252) */
+      double beta = 0.0;
+      for (int jK = 1; jK <= iKs + 1; jK++) {
+        for (int m = 0; m < nparts; m++) {
+          size_t n = (size_t)parts[m].c.nshg * 5;
+          double *w = UB(m, iKs + 1), *uj = UB(m, jK);
+          if (jK == 1) {
+            for (size_t i = 0; i < n; i++) parts[m].temp[i] = w[i] * uj[i];
+          } else {
+            double *ujm = UB(m, jK - 1);
+            for (size_t i = 0; i < n; i++) w[i] = w[i] - beta * ujm[i];
+            for (size_t i = 0; i < n; i++) parts[m].temp[i] = w[i] * uj[i];
+          }
+          t[m] = parts[m].temp;
+        }
+        beta = orc_sumgat(nparts, parts, t, 5);
+        H(jK, iKs) = beta;
+      }
+      unorm = sqrt(beta);
+      H(iKs + 1, iKs) = unorm;
+      for (int m = 0; m < nparts; m++) {
+        size_t n = (size_t)parts[m].c.nshg * 5;
+        double *w = UB(m, iKs + 1);
+        for (size_t i = 0; i < n; i++) w[i] = w[i] / unorm;
+      }
+      /* Givens (:270-288) */
+      for (int jK = 1; jK <= iKs - 1; jK++) {
+        double tmp = Rcos[jK - 1] * H(jK, iKs) + Rsin[jK - 1] * H(jK + 1, iKs);
+        H(jK + 1, iKs) =
+            -Rsin[jK - 1] * H(jK, iKs) + Rcos[jK - 1] * H(jK + 1, iKs);
+        H(jK, iKs) = tmp;
+      }
+      double tmp = sqrt(H(iKs, iKs) * H(iKs, iKs) + H(iKs + 1, iKs) * H(iKs + 1, iKs));
+      Rcos[iKs - 1] = H(iKs, iKs) / tmp;
+      Rsin[iKs - 1] = H(iKs + 1, iKs) / tmp;
+      H(iKs, iKs) = tmp;
+      H(iKs + 1, iKs) = 0.0;
+      tmp = Rcos[iKs - 1] * eBrg[iKs - 1] + Rsin[iKs - 1] * eBrg[iKs];
+      eBrg[iKs] = -Rsin[iKs - 1] * eBrg[iKs - 1] + Rcos[iKs - 1] * eBrg[iKs];
+      eBrg[iKs - 1] = tmp;
+      *ntotGM += 1;
+      double echeck = fabs(eBrg[iKs]);
+      if (echeck <= epsnrm && iKs >= minIters) break; /* :293-294 / :669 */
+    }
+    /* back substitution (:306-311) and update (:315-317) */
+    for (int jK = iKs; jK >= 1; jK--) {
+      yBrg[jK - 1] = eBrg[jK - 1] / H(jK, jK);
+      for (int lK = 1; lK <= jK - 1; lK++)
+        eBrg[lK - 1] = eBrg[lK - 1] - yBrg[jK - 1] * H(lK, jK);
+    }
+    for (int jK = 1; jK <= iKs; jK++)
+      for (int m = 0; m < nparts; m++) {
+        size_t n = (size_t)parts[m].c.nshg * 5;
+        double *uj = UB(m, jK);
+        for (size_t i = 0; i < n; i++) parts[m].Dy[i] = parts[m].Dy[i] + yBrg[jK - 1] * uj[i];
+      }
+    double echeck = fabs(eBrg[iKs]);
+    if (echeck <= epsnrm) break;
+  }
+done:
+  *iKs_out = iKs;
+  *lGMRES_out = lGMRES;
+  free(v);
+  free(t);
+#undef UB
+#undef H
+}
+
+/* ---------------- SolGMRe (compressible/solgmr.f:66-362) ---------------- */
+void orc_solgmre(int nparts, orc_part *parts, double *HBrg, double *eBrg,
+                 double *yBrg, double *Rcos, double *Rsin, int *iKs,
+                 int *lGMRES, int *ntotGM) {
+  orc_elmgmre(nparts, parts);
+  for (int m = 0; m < nparts; m++) {
+    orc_part *p = &parts[m];
+    size_t n = (size_t)p->c.nshg * 5;
+    if (p->rmes) memcpy(p->rmes, p->res, sizeof(double) * n); /* :83 */
+    if (p->c.iprec != 0) orc_i3lu(&p->c, p->BDiag, p->res, 0);
+    orc_i3lu(&p->c, p->BDiag, p->res, 1);
+    memset(p->Dy, 0, sizeof(double) * n);
+  }
+  orc_i3pre(nparts, parts);
+  gmres_core(nparts, parts, orc_au1gmr, 0, HBrg, eBrg, yBrg, Rcos, Rsin, iKs,
+             lGMRES, ntotGM);
+  for (int m = 0; m < nparts; m++)
+    orc_i3lu(&parts[m].c, parts[m].BDiag, parts[m].Dy, 2); /* :347 */
+}
+
+/* exported so oracle_sparse.c can reuse the same Krylov loop */
+void orc_gmres_core(int nparts, orc_part *parts,
+                    void (*Ap)(int, orc_part *, double **), int minIters,
+                    double *HBrg, double *eBrg, double *yBrg, double *Rcos,
+                    double *Rsin, int *iKs, int *lGMRES, int *ntotGM) {
+  gmres_core(nparts, parts, Ap, minIters, HBrg, eBrg, yBrg, Rcos, Rsin, iKs,
+             lGMRES, ntotGM);
+}

@@ -1,0 +1,198 @@
+"""ctypes binding of the CPU oracle (TEST INFRASTRUCTURE ONLY -- see
+oracle/phasta_oracle.h).  Importable only from tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+MAXTOP, MAXQPT = 6, 125
+
+
+class OrcCommon(C.Structure):
+    _fields_ = [
+        *[(n, C.c_int) for n in (
+            "nshg", "numnp", "numel", "numelb", "nflow", "ndof", "ndofBC", "nshape", "nedof",
+            "nelblk", "nelblb", "nlwork", "numpe", "myrank",
+            "ipord", "idiff", "itau", "iprec", "lhs", "ires", "iremoveStabTimeTerm",
+            "EntropyPressure",
+            "iDC", "Navier", "Kspace", "nGMRES", "minIters",
+            "matflg2", "matflg3", "pad0")],
+        *[(n, C.c_double) for n in (
+            "Rgas", "gamma", "gamma1", "pr", "datmat121", "datmat221", "datmat321", "datmat131",
+            "epsM", "dtsfct", "taucfct", "temper",
+            "Dtgl", "almi", "alfi", "gami", "etol")],
+        ("nint", C.c_int * MAXTOP), ("nintb", C.c_int * MAXTOP),
+        ("Qwt", C.c_double * (MAXTOP * MAXQPT)), ("Qwtb", C.c_double * (MAXTOP * MAXQPT)),
+    ]
+
+
+_PTRS = ["lcblk", "ien", "ien_off", "lcblkb", "ienb", "ienb_off", "iBCB", "iBCB_off", "BCB",
+         "BCB_off", "x", "iBC", "BC", "iper", "ilwork", "shp", "shgl", "shpb", "shglb",
+         "y", "ac", "res", "rmes", "BDiag", "EGmass", "qres", "rmass", "Dy", "uBrg", "temp",
+         "lhsK", "colm", "rowp"]
+
+
+class OrcPart(C.Structure):
+    _fields_ = [("c", OrcCommon)] + [(n, C.c_void_p) for n in _PTRS]
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libphasta_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "libphasta_oracle.so"], stdout=subprocess.DEVNULL)
+    if os.path.isdir("/root/reference/phSolver/common") and \
+            not os.path.exists(os.path.join(_HERE, "_ref", "libref_tables.so")):
+        subprocess.check_call(["make", "-C", _HERE, "ref"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        assert _LIB.orc_sizeof_part() == C.sizeof(OrcPart), "orc_part layout mismatch"
+        assert _LIB.orc_sizeof_common() == C.sizeof(OrcCommon)
+        _LIB.orc_sumgat.restype = C.c_double
+    return _LIB
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class OraclePart:
+    """Owns every array of one part in the reference layouts."""
+
+    def __init__(self, mp, params, tables, y, ac, nedof=None):
+        self.mp, self.params, self.tables = mp, params, tables
+        nshg, numel = mp.nshg, mp.numel
+        nshape = max(int(b.shape[1]) for b in mp.mien)
+        self.nedof = nedof or 5 * nshape
+        self.keep = {}
+        k = self.keep
+        k["lcblk"] = np.asfortranarray(mp.lcblk, dtype=np.int32)
+        k["ien"] = np.concatenate([np.asfortranarray(b, dtype=np.int32).ravel(order="F") for b in mp.mien])
+        off = np.zeros(len(mp.mien), dtype=np.int64)
+        off[1:] = np.cumsum([b.size for b in mp.mien])[:-1]
+        k["ien_off"] = off
+        if mp.nelblb:
+            k["lcblkb"] = np.asfortranarray(mp.lcblkb, dtype=np.int32)
+            for nm, lst, dt in (("ienb", mp.mienb, np.int32), ("iBCB", mp.miBCB, np.int32),
+                                ("BCB", mp.mBCB, np.float64)):
+                k[nm] = np.concatenate([np.asfortranarray(b, dtype=dt).ravel(order="F") for b in lst])
+                o = np.zeros(len(lst), dtype=np.int64)
+                o[1:] = np.cumsum([b.size for b in lst])[:-1]
+                k[nm + "_off"] = o
+        k["x"] = np.asfortranarray(mp.x, dtype=np.float64)
+        k["iBC"] = np.ascontiguousarray(mp.iBC, dtype=np.int32)
+        k["BC"] = np.asfortranarray(mp.BC, dtype=np.float64)
+        k["iper"] = np.ascontiguousarray(mp.iper, dtype=np.int32)
+        k["ilwork"] = np.ascontiguousarray(mp.ilwork, dtype=np.int32)
+        for nm in ("shp", "shgl", "shpb", "shglb"):
+            k[nm] = np.asfortranarray(tables[nm], dtype=np.float64)
+        k["y"] = np.asfortranarray(y, dtype=np.float64).copy(order="F")
+        k["ac"] = np.asfortranarray(ac, dtype=np.float64).copy(order="F")
+        K = params.Kspace
+        self.res = k["res"] = np.zeros((nshg, 5), order="F")
+        self.rmes = k["rmes"] = np.zeros((nshg, 5), order="F")
+        self.BDiag = k["BDiag"] = np.zeros((nshg, 5, 5), order="F")
+        self.EGmass = k["EGmass"] = np.zeros((numel, self.nedof, self.nedof), order="F")
+        self.qres = k["qres"] = np.zeros((nshg, 12), order="F")
+        self.rmass = k["rmass"] = np.zeros(nshg)
+        self.Dy = k["Dy"] = np.zeros((nshg, 5), order="F")
+        self.uBrg = k["uBrg"] = np.zeros((nshg, 5, K + 1), order="F")
+        k["temp"] = np.zeros((nshg, 5), order="F")
+
+    def fill(self, s: OrcPart):
+        mp, P, T = self.mp, self.params, self.tables
+        c = s.c
+        c.nshg, c.numnp, c.numel, c.numelb = mp.nshg, mp.numnp, mp.numel, 0
+        c.nflow, c.ndof, c.ndofBC = 5, 5, 6
+        c.nshape, c.nedof = self.nedof // 5, self.nedof
+        c.nelblk, c.nelblb, c.nlwork = mp.nelblk, mp.nelblb, mp.nlwork
+        c.numpe, c.myrank = mp.numpe, mp.rank
+        for nm in ("ipord", "idiff", "itau", "iprec", "lhs", "iremoveStabTimeTerm", "EntropyPressure",
+                   "iDC", "Navier", "Kspace", "nGMRES", "minIters", "matflg2", "matflg3"):
+            setattr(c, nm, int(getattr(P, nm)))
+        c.ires = 1
+        for nm in ("Rgas", "gamma", "gamma1", "pr", "datmat121", "datmat221", "datmat321", "datmat131",
+                   "epsM", "dtsfct", "taucfct", "temper", "Dtgl", "almi", "alfi", "gami", "etol"):
+            setattr(c, nm, float(getattr(P, nm)))
+        for i in range(MAXTOP):
+            c.nint[i] = int(T["nint"][i])
+            c.nintb[i] = int(T["nintb"][i])
+        q = np.asfortranarray(T["Qwt"]).ravel(order="F")
+        qb = np.asfortranarray(T["Qwtb"]).ravel(order="F")
+        for i in range(MAXTOP * MAXQPT):
+            c.Qwt[i] = q[i]
+            c.Qwtb[i] = qb[i]
+        for nm in _PTRS:
+            setattr(s, nm, _ptr(self.keep.get(nm)))
+
+
+class Oracle:
+    """All parts of one case; methods mirror the reference routine names."""
+
+    def __init__(self, parts, params, tables, states):
+        self.L = lib()
+        self.parts = [OraclePart(mp, params, tables, y, ac) for mp, (y, ac) in zip(parts, states)]
+        self.n = len(self.parts)
+        self.arr = (OrcPart * self.n)()
+        for p, s in zip(self.parts, self.arr):
+            p.fill(s)
+        K = params.Kspace
+        self.HBrg = np.zeros((K + 1, K), order="F")
+        self.eBrg = np.zeros(K + 1)
+        self.yBrg = np.zeros(K + 1)
+        self.Rcos = np.zeros(K + 1)
+        self.Rsin = np.zeros(K + 1)
+        self.ntotGM = C.c_int(0)
+
+    def set_flags(self, **kw):
+        for s in self.arr:
+            for k, v in kw.items():
+                setattr(s.c, k, v)
+
+    def _vecs(self, arrs):
+        pp = (C.POINTER(C.c_double) * self.n)()
+        for i, a in enumerate(arrs):
+            pp[i] = a.ctypes.data_as(C.POINTER(C.c_double))
+        return pp
+
+    def ElmGMRe(self):
+        self.L.orc_elmgmre(self.n, self.arr)
+
+    def i3LU(self, code, vecs=None):
+        for i, p in enumerate(self.parts):
+            r = p.res if vecs is None else vecs[i]
+            self.L.orc_i3lu(C.byref(self.arr[i].c), _ptr(p.BDiag), _ptr(r), code)
+
+    def i3pre(self):
+        self.L.orc_i3pre(self.n, self.arr)
+
+    def Au1GMR(self, vecs):
+        self.L.orc_au1gmr(self.n, self.arr, self._vecs(vecs))
+
+    def bc3per(self, vecs):
+        for i, v in enumerate(vecs):
+            self.L.orc_bc3per(C.byref(self.arr[i]), _ptr(v), 5)
+
+    def commu(self, vecs, n, code):
+        self.L.orc_commu(self.n, self.arr, self._vecs(vecs), n, {"in": 0, "out": 1}[code])
+
+    def sumgat(self, vecs, n):
+        return self.L.orc_sumgat(self.n, self.arr, self._vecs(vecs), n)
+
+    def SolGMRe(self):
+        iKs, lG = C.c_int(0), C.c_int(0)
+        self.L.orc_solgmre(self.n, self.arr, _ptr(self.HBrg), _ptr(self.eBrg), _ptr(self.yBrg),
+                           _ptr(self.Rcos), _ptr(self.Rsin), C.byref(iKs), C.byref(lG),
+                           C.byref(self.ntotGM))
+        return iKs.value, lG.value

@@ -1,0 +1,246 @@
+"""Synthetic PHASTA mesh parts: structured box, 6 Kuhn tets
+per hex, slab partition along x with ilwork master/slave lists.
+
+Every array uses the reference's in-memory layout (column-major, 1-based node
+ids) so the same buffers feed the oracle, the C-ABI and a phastaIO writer:
+  x(numnp,3), ien per block (npro,nshl), lcblk(10,nelblk+1)
+  (phSolver/common/genblkPosix.f:62-72), iBC bits (compressible/bc3res.f:30-153),
+  BC(nshg,ndofBC=ndof+1) (common/readnblk.f:171), iper (au1gmr.f:35-37),
+  ilwork (common/commu.f:131-143, iother 0-based as after ctypes.f:47).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from itertools import permutations
+
+import numpy as np
+
+NFLOW = 5
+NDOF = 5
+NDOFBC = NDOF + 1
+
+
+@dataclass
+class MeshPart:
+    """One partition (= one MPI rank of the reference / one GPU here)."""
+    rank: int
+    numpe: int
+    nshg: int
+    numnp: int
+    numel: int
+    x: np.ndarray                 # (numnp,3) F
+    lcblk: np.ndarray             # (10, nelblk+1) F int32
+    mien: list                    # per block (npro,nshl) F int32, 1-based
+    iBC: np.ndarray               # (nshg,) int32
+    BC: np.ndarray                # (nshg, NDOFBC) F
+    iper: np.ndarray              # (nshg,) int32 1-based
+    ilwork: np.ndarray            # (nlwork,) int32
+    lcblkb: np.ndarray = None     # (10, nelblb+1)
+    mienb: list = field(default_factory=list)
+    miBCB: list = field(default_factory=list)
+    mBCB: list = field(default_factory=list)
+    gnode: np.ndarray = None      # local -> global node id (0-based), tests only
+    gelem: np.ndarray = None      # local -> global element id (0-based)
+
+    @property
+    def nelblk(self):
+        return self.lcblk.shape[1] - 1
+
+    @property
+    def nelblb(self):
+        return 0 if self.lcblkb is None else self.lcblkb.shape[1] - 1
+
+    @property
+    def nlwork(self):
+        return int(self.ilwork.size)
+
+    def ien_all(self):
+        """(numel, nshl) connectivity, 1-based, file order."""
+        return np.concatenate([np.asarray(b) for b in self.mien], axis=0)
+
+
+_KUHN = list(permutations(range(3)))
+
+
+def _box_tets(nx, ny, nz, node_id):
+    """Connectivity (6*nx*ny*nz, 4) of the Kuhn split, hex-major order.
+    node_id(i,j,k) -> 0-based id (vectorised)."""
+    I, J, K = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    I, J, K = I.ravel(), J.ravel(), K.ravel()
+    nh = I.size
+    ien = np.empty((nh, 6, 4), dtype=np.int64)
+    for t, perm in enumerate(_KUHN):
+        d = np.zeros((4, 3), dtype=np.int64)
+        for s, ax in enumerate(perm):
+            d[s + 1:, ax] += 1
+        # parity of the permutation decides orientation; keep det>0 for
+        # x = x4 + r(x1-x4) + s(x2-x4) + t(x3-x4)  (uniformP.c:18-35)
+        verts = [node_id(I + d[v, 0], J + d[v, 1], K + d[v, 2]) for v in range(4)]
+        e = np.array([d[0] - d[3], d[1] - d[3], d[2] - d[3]], dtype=float)
+        if np.linalg.det(e) < 0:
+            verts[0], verts[1] = verts[1], verts[0]
+        for v in range(4):
+            ien[:, t, v] = verts[v]
+    return ien.reshape(nh * 6, 4)
+
+
+def _blocks(numel, ibksiz, lcsyst=1, ipord=1, nenl=4, nshl=4, nfacel=4):
+    """genblkPosix.f:52-96: consecutive runs of <= ibksiz elements."""
+    starts = np.arange(0, numel, ibksiz)
+    nb = starts.size
+    lcblk = np.zeros((10, nb + 1), dtype=np.int32, order="F")
+    lcblk[0, :nb] = starts + 1
+    lcblk[0, nb] = numel + 1
+    lcblk[2, :nb] = lcsyst
+    lcblk[3, :nb] = ipord
+    lcblk[4, :nb] = nenl
+    lcblk[5, :nb] = nfacel
+    lcblk[6, :nb] = 0          # mattyp
+    lcblk[7, :nb] = NDOF       # ndofl
+    lcblk[8, :nb] = 0          # nsymdl
+    lcblk[9, :nb] = nshl
+    return lcblk
+
+
+def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15,
+             bc="channel", periodic_z=True, seed=1234, max_seg=0):
+    """Build `nparts` MeshPart objects for an nx*ny*nz-hex box (6 tets/hex).
+
+    bc: "channel"  x-min inflow (velocity code 7 + T), x-max pressure,
+                   y walls no-slip isothermal, z periodic (or free)
+        "none"     no essential BCs (iBC=0)
+        "mixed"    channel + a few nodes with every velocity code 1..6 and
+                   density BC, random slopes (exercises bc3* branches)
+    max_seg: if >0 split ilwork segments to at most this length.
+    """
+    assert nx % nparts == 0 or nparts == 1, "nx must be divisible by nparts"
+    rng = np.random.default_rng(seed)
+    parts = []
+    hx, hy, hz = L[0] / nx, L[1] / ny, L[2] / nz
+    nyp, nzp = ny + 1, nz + 1
+
+    def gid(i, j, k):
+        return (i * nyp + j) * nzp + k
+
+    # global iBC/BC pattern as functions of (i,j,k) so parts agree
+    nxs = nx // nparts
+    for p in range(nparts):
+        i0, i1 = p * nxs, (p + 1) * nxs
+        nxl = i1 - i0
+
+        def lid(i, j, k, i0=i0):
+            return ((i - i0) * nyp + j) * nzp + k
+
+        I, J, K = np.meshgrid(np.arange(i0, i1 + 1), np.arange(nyp), np.arange(nzp),
+                              indexing="ij")
+        I, J, K = I.ravel(), J.ravel(), K.ravel()
+        nn = I.size
+        x = np.empty((nn, 3), order="F")
+        X, Y, Z = I * hx, J * hy, K * hz
+        if perturb:
+            # interior-only smooth perturbation; vanishes on all faces so the
+            # box stays a box and periodic planes stay congruent
+            s = (np.sin(np.pi * X / L[0]) * np.sin(np.pi * Y / L[1]) *
+                 np.sin(np.pi * Z / L[2]))
+            X = X + perturb * hx * s * np.sin(7.0 * Y / L[1] + 3.0 * Z / L[2])
+            Y = Y + perturb * hy * s * np.sin(5.0 * X / L[0] + 2.0 * Z / L[2])
+            Z = Z + perturb * hz * s * np.sin(4.0 * X / L[0] + 6.0 * Y / L[1])
+        x[:, 0], x[:, 1], x[:, 2] = X, Y, Z
+        gnode = gid(I, J, K)
+
+        ien0 = _box_tets(nxl, ny, nz, lambda a, b, c: lid(a + i0, b, c))
+        numel = ien0.shape[0]
+        ien1 = (ien0 + 1).astype(np.int32)
+        lcblk = _blocks(numel, ibksiz)
+        mien = [np.asfortranarray(ien1[lcblk[0, b] - 1: lcblk[0, b + 1] - 1])
+                for b in range(lcblk.shape[1] - 1)]
+        hexid = (np.arange(nxl)[:, None, None] + i0) * ny * nz + \
+            np.arange(ny)[None, :, None] * nz + np.arange(nz)[None, None, :]
+        gelem = (hexid.ravel()[:, None] * 6 + np.arange(6)[None, :]).ravel()
+
+        iBC = np.zeros(nn, dtype=np.int32)
+        BC = np.zeros((nn, NDOFBC), order="F")
+        iper = np.arange(1, nn + 1, dtype=np.int32)
+        if bc in ("channel", "mixed"):
+            inflow = I == 0
+            outflow = I == nx
+            wall = (J == 0) | (J == ny)
+            iBC[inflow] |= (7 << 3) | (1 << 1)
+            iBC[outflow & ~wall] |= (1 << 2)
+            iBC[wall] |= (7 << 3) | (1 << 1)
+            if periodic_z:
+                slave = K == nz
+                iBC[slave] |= (1 << 10)
+                iper[slave] = lid(I[slave], J[slave], 0) + 1
+        if bc == "mixed":
+            # sprinkle the remaining velocity codes / density BC on interior
+            # nodes, deterministic in the GLOBAL node id
+            interior = (I > 0) & (I < nx) & (J > 0) & (J < ny) & (K > 0) & (K < nz)
+            h = (gnode * 2654435761) % 97
+            for code in range(1, 7):
+                sel = interior & (h == code)
+                iBC[sel] |= (code << 3)
+            iBC[interior & (h == 7)] |= 1          # density
+            iBC[interior & (h == 8)] |= (1 << 2) | (1 << 1)
+            r = np.random.default_rng(seed + 7)
+            slopes = r.uniform(-0.5, 0.5, size=((nx + 1) * nyp * nzp, NDOFBC))
+            BC[:, :] = slopes[gnode]
+            BC[:, 0] = 1.1 + 0.1 * slopes[gnode, 0]
+
+        # ilwork: slab neighbours; lower rank is master
+        tasks = []
+        plane = nyp * nzp
+
+        def segs(first):
+            if max_seg and max_seg < plane:
+                out = []
+                a = first
+                while a < first + plane:
+                    ln = min(max_seg, first + plane - a)
+                    out.append((a, ln))
+                    a += ln
+                return out
+            return [(first, plane)]
+
+        if nparts > 1:
+            if p > 0:      # my left plane is owned by p-1: I am slave, send
+                tasks.append((1000 + p - 1, 0, p - 1, segs(1)))
+            if p < nparts - 1:   # my right plane: I am master, receive from p+1
+                tasks.append((1000 + p, 1, p + 1, segs(nxl * plane + 1)))
+        il = [len(tasks)]
+        for tag, iacc, iother, sg in tasks:
+            il += [tag, iacc, iother, len(sg)]
+            for a, ln in sg:
+                il += [a, ln]
+        ilwork = np.array(il, dtype=np.int32)
+
+        parts.append(MeshPart(rank=p, numpe=nparts, nshg=nn, numnp=nn, numel=numel,
+                              x=x, lcblk=lcblk, mien=mien, iBC=iBC, BC=BC, iper=iper,
+                              ilwork=ilwork, gnode=gnode, gelem=gelem))
+    return parts
+
+
+def make_state(part: MeshPart, nglobal_nodes: int, seed=1234):
+    """SURVEY 8(d) synthetic state, deterministic in the GLOBAL node id so
+    partitioned and serial runs see identical fields.
+    y = {u1,u2,u3,p,T} (nshg,5) F; ac same layout."""
+    rng = np.random.default_rng(seed)
+    r = rng.uniform(-1.0, 1.0, size=(nglobal_nodes, 10))
+    g = part.gnode
+    y = np.empty((part.nshg, NDOF), order="F")
+    ac = np.empty((part.nshg, NDOF), order="F")
+    y[:, 0] = 30.0 * 1.0 + 3.0 * r[g, 0]
+    y[:, 1] = 30.0 * 0.1 + 3.0 * r[g, 1]
+    y[:, 2] = 30.0 * 0.05 + 3.0 * r[g, 2]
+    y[:, 3] = 1.0e5 * (1.0 + 0.01 * r[g, 3])
+    y[:, 4] = 300.0 * (1.0 + 0.01 * r[g, 4])
+    ac[:, :] = 1.0e2 * r[g, 5:10]
+    # periodic slaves carry the master's state (itrbc.f:170-178)
+    m = part.iper - 1
+    y[:, :] = y[m, :]
+    ac[:, :] = ac[m, :]
+    return y, ac
+
+
+def global_node_count(nx, ny, nz):
+    return (nx + 1) * (ny + 1) * (nz + 1)
