@@ -1,0 +1,157 @@
+/*
+ * phb200.h -- C ABI of libphb200.so: the B200-native drop-in for PHASTA's
+ * compressible implicit-step hot path (element assembly + EBE GMRES).
+ *
+ * The boundary is the SolGMRe call in phSolver/compressible/itrdrv.f:515-524;
+ * the precedent for a C function behind that call site is SolGMRp
+ * (phSolver/compressible/solgmrpetsc.c:59-65).  All arguments are plain
+ * pointers to caller-owned arrays in the reference's in-memory (Fortran,
+ * column-major, 1-based ids) layouts; the hidden COMMON-block inputs
+ * (phSolver/common/common.h:35-268) travel in phb200_common / phb200_step.
+ * INTEGRATION.md shows the ISO_C_BINDING shim that binds these entry points.
+ *
+ * Every function returns 0 on success; on failure it prints
+ * "phb200: <routine>: <what>" to stderr (the reference's error() convention,
+ * phSolver/common/error.f) and returns non-zero so the Fortran shim can call
+ * error()/MPI_ABORT.  There is no CPU fallback: without a CUDA device
+ * phb200_init fails.
+ */
+#ifndef PHB200_H
+#define PHB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PHB200_MAXTOP 6   /* common.h:17-20 MAXTOP */
+#define PHB200_MAXSH 32   /* MAXSH  */
+#define PHB200_MAXQPT 125 /* MAXQPT */
+
+/* Scalars fixed for a run: /conpar/ /blkdat/ /fronts/ /workfc/ /genpar/
+ * /solpar/ /incomp/ /mmatpar/ /matdat/ /precis/ /outpar/ /intpt/
+ * (common.h:92-96,111,121-125,184-189,220-231,247). */
+typedef struct phb200_common {
+  int nshg, numnp, numel, numelb, nflow, ndof, ndofBC, nshape, nedof;
+  int nelblk, nelblb, nlwork, numpe, myrank;
+  int ipord, idiff, itau, iremoveStabTimeTerm, EntropyPressure;
+  int iDC, Navier, Kspace, nGMRES, minIters;
+  int matflg2, matflg3; /* matflg(2,1) viscosity model, matflg(3,1) */
+  double Rgas, gamma, gamma1, pr;
+  double datmat121, datmat221, datmat321, datmat131;
+  double epsM, dtsfct, taucfct, temper;
+  int nint[PHB200_MAXTOP], nintb[PHB200_MAXTOP];
+  double Qwt[PHB200_MAXTOP * PHB200_MAXQPT];  /* Qwt(MAXTOP,MAXQPT)  */
+  double Qwtb[PHB200_MAXTOP * PHB200_MAXQPT]; /* Qwtb(MAXTOP,MAXQPT) */
+} phb200_common;
+
+/* Scalars that change per call: /timdat/ (common.h:252-255; itrPC.f:18-47)
+ * and the per-solve switches itrdrv sets (itrdrv.f:456-457,511-512). */
+typedef struct phb200_step {
+  int lhs, iprec, iter, nitr, lstep, pad;
+  double Dtgl, almi, alfi, gami, etol;
+} phb200_step;
+
+typedef struct phb200_ctx phb200_ctx;
+
+/* One-time setup, called after genadj in itrdrv (itrdrv.f:169).  Replaces the
+ * mesh/BC/table arguments SolGMRe receives on every call (solgmr.f:1-8):
+ * x, iBC, BC, iper, ilwork, shp, shgl, shpb, shglb, plus lcblk/lcblkb
+ * (common.h:111) and the pointer_data block arrays mien/mienb/miBCB/mBCB
+ * (pointer.f:42-47) -- mien[iblk] points at mien(iblk)%p (npro,nshl).
+ * ilwork is the in-memory array after ctypes (iother 0-based, ctypes.f:47).
+ * device: CUDA ordinal (one process per GPU). */
+int phb200_init(phb200_ctx **ctx, const phb200_common *c, const int *lcblk,
+                const int *const *mien, const int *lcblkb,
+                const int *const *mienb, const int *const *miBCB,
+                const double *const *mBCB, const double *x, const int *iBC,
+                const double *BC, const int *iper, const int *ilwork,
+                const double *shp, const double *shgl, const double *shpb,
+                const double *shglb, int device);
+void phb200_finalize(phb200_ctx *ctx);
+
+/* Multi-GPU plumbing: replaces MPI_COMM_WORLD of commu.f / mpitools.f with an
+ * NCCL communicator over NVLink.  Rank 0 creates the 128-byte id, the host
+ * broadcasts it (MPI_Bcast in the Fortran shim, torch.distributed here). */
+int phb200_nccl_unique_id(void *id128);
+int phb200_comm_init(phb200_ctx *ctx, const void *id128);
+
+/* SolGMRe (solgmr.f:1-362).  y, ac: (nshg,ndof) {u1,u2,u3,p,T}.  Outputs:
+ * res (nshg,nflow) block-diagonal-preconditioned residual, rmes un-
+ * preconditioned b (solgmr.f:83) (nullable), Dy (nshg,nflow) {p,u,v,w,T}
+ * (= solinc), HBrg(Kspace+1,Kspace)/eBrg/yBrg/Rcos/Rsin (nullable), and the
+ * /itrpar/ counters iKs, lGMRES, ntotGM (+= iterations).  EGmass and BDiag
+ * stay device-resident (nothing outside SolGMRe reads them);
+ * BDiag (LU factors) is copied back only if the pointer is non-null. */
+int phb200_solgmre(phb200_ctx *ctx, const double *y, const double *ac,
+                   const phb200_step *step, double *res, double *rmes,
+                   double *BDiag, double *Dy, double *HBrg, double *eBrg,
+                   double *yBrg, double *Rcos, double *Rsin, int *iKs,
+                   int *lGMRES, int *ntotGM);
+
+/* ElmGMRe (elmgmr.f:1-274): res, BDiag(nshg,5,5), EGmass(numel,nedof,nedof)
+ * (any output pointer may be null).  qres(nshg,12) nullable (debug seam). */
+int phb200_elmgmre(phb200_ctx *ctx, const double *y, const double *ac,
+                   const phb200_step *step, double *res, double *BDiag,
+                   double *EGmass, double *qres);
+
+/* Finer seams, all on host arrays: */
+/* i3LU (i3lu.f:1-181) code 0 LU_Fact / 1 forward / 2 backward / 3 product */
+int phb200_i3lu(phb200_ctx *ctx, double *Diag, double *r, int code);
+/* i3pre (i3pre.f:1-146) on the device-resident EGmass/BDiag of the last
+ * elmgmre; EGmass out nullable */
+int phb200_i3pre(phb200_ctx *ctx, double *EGmass);
+/* Au1GMR (au1gmr.f:1-106) with the resident EGmass: u(nshg,5) in/out */
+int phb200_au1gmr(phb200_ctx *ctx, double *u);
+/* bc3per (bc3per.f:1-46) */
+int phb200_bc3per(phb200_ctx *ctx, double *r);
+/* commu (commu.f:1-297): code 0 'in ', 1 'out'; global(nshg,n) */
+int phb200_commu(phb200_ctx *ctx, double *global, int n, int code);
+/* sumgat (mpitools.f:98-137) */
+int phb200_sumgat(phb200_ctx *ctx, const double *u, int n, double *summed);
+
+/* HBM-resident path (what bench.py's `value` times: inputs already on the
+ * device).  set_state uploads y/ac once; the dev_* calls run on them. */
+int phb200_set_state(phb200_ctx *ctx, const double *y, const double *ac);
+int phb200_dev_elmgmre(phb200_ctx *ctx, const phb200_step *step);
+/* i3LU + i3pre + GMRES + back-substitution on the resident system */
+int phb200_dev_solve(phb200_ctx *ctx, const phb200_step *step, int *iKs,
+                     int *lGMRES, int *ntotGM);
+/* one Au1GMR + bc3per on Krylov slot `slot` -> slot+1 (for Ap/s timing) */
+int phb200_dev_ap(phb200_ctx *ctx, int slot);
+int phb200_get_res(phb200_ctx *ctx, double *res);
+int phb200_get_dy(phb200_ctx *ctx, double *Dy);
+int phb200_get_bdiag(phb200_ctx *ctx, double *BDiag);
+int phb200_get_egmass(phb200_ctx *ctx, double *EGmass);
+
+/* Timing on the library's own stream (bench.py): record event `slot`
+ * (0..15), elapsed ms between two recorded events, full sync, and the number
+ * of kernel launches issued so far. */
+int phb200_event_record(phb200_ctx *ctx, int slot);
+int phb200_event_elapsed_ms(phb200_ctx *ctx, int a, int b, float *ms);
+int phb200_sync(phb200_ctx *ctx);
+long long phb200_launch_count(phb200_ctx *ctx);
+/* accumulated device time (ms) and launch count of kernel class k since the
+ * last reset: 0 assembly(AsIGMR), 1 AsIq, 2 Ap(EBE), 3 i3pre, 4 Krylov BLAS-1,
+ * 5 node-wise BC/LU, 6 halo pack/unpack.  Timed with CUDA events only when
+ * profiling is switched on (phb200_profile(ctx,1)). */
+int phb200_profile(phb200_ctx *ctx, int on);
+int phb200_profile_get(phb200_ctx *ctx, int k, float *ms, long long *launches);
+int phb200_profile_reset(phb200_ctx *ctx);
+/* FP64 FMA peak microbenchmark (MEASURED_PEAKS.json has no FP64 number):
+ * returns achieved TFLOP/s of a register-resident DFMA chain kernel. */
+int phb200_fp64_peak(phb200_ctx *ctx, double *tflops);
+/* flush L2 by writing a >126 MB scratch buffer (bench hygiene) */
+int phb200_flush_l2(phb200_ctx *ctx);
+
+const char *phb200_version(void);
+/* struct sizes, so a binding can verify its mirror of the two structs */
+int phb200_sizeof_common(void);
+int phb200_sizeof_step(void);
+/* test transport: several parts on ONE GPU, one host thread per part (see
+ * csrc/comm.cu); stands in for phb200_comm_init on a single-GPU box */
+int phb200_local_group_join(phb200_ctx *ctx, int nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,395 @@
+// api.cu -- the extern "C" boundary declared in include/phb200.h.
+#include "ctx.h"
+#include <cstring>
+#include <new>
+
+static int fail(const char *routine, const char *what) {
+  fprintf(stderr, "phb200: %s: %s\n", routine, what);
+  return 1;
+}
+
+template <class T>
+static int dev_alloc(T **p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  PHB_CHECK(cudaMalloc((void **)p, sizeof(T) * n));
+  return 0;
+}
+
+extern "C" const char *phb200_version(void) { return "phb200 0.1 (sm_100a)"; }
+extern "C" int phb200_sizeof_common(void) { return (int)sizeof(phb200_common); }
+extern "C" int phb200_sizeof_step(void) { return (int)sizeof(phb200_step); }
+
+extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *lcblk, const int *const *mien,
+                           const int *lcblkb, const int *const *mienb, const int *const *miBCB,
+                           const double *const *mBCB, const double *x, const int *iBC, const double *BC,
+                           const int *iper, const int *ilwork, const double *shp, const double *shgl,
+                           const double *shpb, const double *shglb, int device) {
+  (void)lcblkb; (void)mienb; (void)miBCB; (void)mBCB; (void)shpb; (void)shglb;
+  if (!out || !c) return fail("init", "null argument");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("init", "no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("init", "bad device ordinal");
+  if (c->nflow != 5 || c->ndof != 5) return fail("init", "only nflow=ndof=5 (no scalars) supported");
+  if (c->ipord != 1) return fail("init", "only ipord=1 supported");
+  if (c->itau != 0) return fail("init", "only itau=0 (Shakib diagonal tau) supported");
+  if (c->iDC != 0) return fail("init", "iDC!=0 (discontinuity capturing) not supported");
+  if (c->Navier != 1) return fail("init", "Navier must be 1");
+  if (c->EntropyPressure != 0) return fail("init", "EntropyPressure=1 not supported");
+  if (c->nelblb != 0) return fail("init", "boundary element blocks not supported yet");
+  PHB_CHECK(cudaSetDevice(device));
+  phb200_ctx *ctx = new (std::nothrow) phb200_ctx();
+  if (!ctx) return fail("init", "out of host memory");
+  ctx->c = *c;
+  ctx->device = device;
+  ctx->nccl = nullptr;
+  ctx->local_group = false;
+  ctx->launches = 0;
+  ctx->profiling = false;
+  ctx->have_lhs = false;
+  memset(ctx->kc_ms, 0, sizeof ctx->kc_ms);
+  memset(ctx->kc_n, 0, sizeof ctx->kc_n);
+  PHB_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 16; i++) PHB_CHECK(cudaEventCreate(&ctx->ev[i]));
+  PHB_CHECK(cudaEventCreate(&ctx->pev0));
+  PHB_CHECK(cudaEventCreate(&ctx->pev1));
+  const int nshg = c->nshg, numnp = c->numnp;
+  // ---- connectivity: concatenate tet blocks in file order (genblkPosix.f:52-96)
+  int numel = 0;
+  for (int b = 0; b < c->nelblk; b++) {
+    const int *lc = lcblk + 10 * b;
+    int npro = lc[10] - lc[0];
+    if (lc[2] != 1 || lc[9] != 4) return fail("init", "only linear tet blocks (lcsyst=1,nshl=4) supported yet");
+    numel += npro;
+  }
+  if (numel != c->numel) return fail("init", "lcblk does not add up to numel");
+  ctx->numel_tet = numel;
+  ctx->numel_pad = ((size_t)numel + 63) / 64 * 64;
+  if (ctx->numel_pad == 0) ctx->numel_pad = 64;
+  {
+    std::vector<int> ien((size_t)4 * ctx->numel_pad, 0);
+    size_t e0 = 0;
+    for (int b = 0; b < c->nelblk; b++) {
+      const int *lc = lcblk + 10 * b;
+      int npro = lc[10] - lc[0];
+      const int *ib = mien[b];
+      for (int a = 0; a < 4; a++)
+        for (int e = 0; e < npro; e++) {
+          int v = ib[e + (size_t)npro * a];
+          if (v < 0) v = -v;
+          if (v < 1 || v > nshg) return fail("init", "ien entry out of range");
+          ien[(size_t)a * ctx->numel_pad + e0 + e] = v - 1;
+        }
+      e0 += npro;
+    }
+    PHB_TRY(dev_alloc(&ctx->d_ien, ien.size()));
+    PHB_CHECK(cudaMemcpy(ctx->d_ien, ien.data(), sizeof(int) * ien.size(), cudaMemcpyHostToDevice));
+  }
+  // ---- nodal data
+  PHB_TRY(dev_alloc(&ctx->d_x, (size_t)3 * numnp));
+  PHB_CHECK(cudaMemcpy(ctx->d_x, x, sizeof(double) * 3 * (size_t)numnp, cudaMemcpyHostToDevice));
+  PHB_TRY(dev_alloc(&ctx->d_iBC, (size_t)nshg));
+  PHB_CHECK(cudaMemcpy(ctx->d_iBC, iBC, sizeof(int) * (size_t)nshg, cudaMemcpyHostToDevice));
+  PHB_TRY(dev_alloc(&ctx->d_BC, (size_t)c->ndofBC * nshg));
+  PHB_CHECK(cudaMemcpy(ctx->d_BC, BC, sizeof(double) * (size_t)c->ndofBC * nshg, cudaMemcpyHostToDevice));
+  {
+    std::vector<int> ip(nshg), sl;
+    for (int i = 0; i < nshg; i++) {
+      ip[i] = iper[i] - 1;
+      if (ip[i] < 0 || ip[i] >= nshg) return fail("init", "iper entry out of range");
+      if (iBC[i] & (1 << 10)) sl.push_back(i);
+      if (iBC[i] & (1 << 11)) return fail("init", "SPEBC (iBC bit 11) not supported");
+    }
+    for (int j : sl)
+      if (iBC[ip[j]] & (1 << 10)) return fail("init", "chained periodic masters not supported");
+    PHB_TRY(dev_alloc(&ctx->d_iper, (size_t)nshg));
+    PHB_CHECK(cudaMemcpy(ctx->d_iper, ip.data(), sizeof(int) * (size_t)nshg, cudaMemcpyHostToDevice));
+    ctx->n_perslave = (int)sl.size();
+    PHB_TRY(dev_alloc(&ctx->d_perslave, sl.size()));
+    if (!sl.empty())
+      PHB_CHECK(cudaMemcpy(ctx->d_perslave, sl.data(), sizeof(int) * sl.size(), cudaMemcpyHostToDevice));
+  }
+  PHB_TRY(phb_halo_setup(ctx, ilwork));
+  PHB_TRY(phb_upload_tables(ctx, shp, shgl));
+  // ---- state and work arrays
+  const size_t n5 = (size_t)5 * nshg;
+  PHB_TRY(dev_alloc(&ctx->d_y, n5));
+  PHB_TRY(dev_alloc(&ctx->d_ac, n5));
+  PHB_TRY(dev_alloc(&ctx->d_qres, (size_t)12 * nshg));
+  PHB_TRY(dev_alloc(&ctx->d_rmass, (size_t)nshg));
+  PHB_TRY(dev_alloc(&ctx->d_res, n5));
+  PHB_TRY(dev_alloc(&ctx->d_rmes, n5));
+  PHB_TRY(dev_alloc(&ctx->d_Dy, n5));
+  PHB_TRY(dev_alloc(&ctx->d_temp, n5));
+  PHB_TRY(dev_alloc(&ctx->d_BDiag, (size_t)25 * nshg));
+  ctx->d_BDtmp = nullptr;
+  if (c->numpe > 1) PHB_TRY(dev_alloc(&ctx->d_BDtmp, (size_t)25 * nshg));
+  PHB_TRY(dev_alloc(&ctx->d_EG, ctx->numel_pad * 400));
+  PHB_CHECK(cudaMemset(ctx->d_EG, 0, sizeof(double) * ctx->numel_pad * 400));
+  PHB_TRY(dev_alloc(&ctx->d_uBrg, n5 * (size_t)(c->Kspace + 1)));
+  PHB_TRY(dev_alloc(&ctx->d_dots, (size_t)c->Kspace + 8));
+  PHB_CHECK(cudaMallocHost(&ctx->h_dots, sizeof(double) * ((size_t)c->Kspace + 8)));
+  ctx->scratch_bytes = (size_t)256 << 20;
+  PHB_TRY(dev_alloc((char **)&ctx->d_scratch, ctx->scratch_bytes));
+  PHB_CHECK(cudaMemset(ctx->d_qres, 0, sizeof(double) * 12 * (size_t)nshg));
+  const int K = c->Kspace;
+  ctx->HBrg.assign((size_t)(K + 1) * K, 0.0);
+  ctx->eBrg.assign(K + 1, 0.0);
+  ctx->yBrg.assign(K + 1, 0.0);
+  ctx->Rcos.assign(K + 1, 0.0);
+  ctx->Rsin.assign(K + 1, 0.0);
+  PHB_CHECK(cudaDeviceSynchronize());
+  *out = ctx;
+  return 0;
+}
+
+extern "C" void phb200_finalize(phb200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  phb_comm_free(ctx);
+  void *ptrs[] = {ctx->d_ien, ctx->d_iBC, ctx->d_BC, ctx->d_iper, ctx->d_x, ctx->d_perslave, ctx->d_halo_nodes,
+                  ctx->d_slave_nodes, ctx->d_sendbuf, ctx->d_recvbuf, ctx->d_y, ctx->d_ac, ctx->d_qres,
+                  ctx->d_rmass, ctx->d_res, ctx->d_rmes, ctx->d_Dy, ctx->d_temp, ctx->d_BDiag, ctx->d_BDtmp,
+                  ctx->d_EG, ctx->d_uBrg, ctx->d_dots, ctx->d_scratch};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (ctx->h_dots) cudaFreeHost(ctx->h_dots);
+  for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
+  cudaEventDestroy(ctx->pev0);
+  cudaEventDestroy(ctx->pev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" int phb200_nccl_unique_id(void *id128) { return phb_comm_unique_id(id128); }
+extern "C" int phb200_comm_init(phb200_ctx *ctx, const void *id128) { return phb_comm_init(ctx, id128); }
+
+#define ENTER(ctx)                                  \
+  if (!(ctx)) return fail(__func__, "null context"); \
+  PHB_CHECK(cudaSetDevice((ctx)->device));
+
+static int h2d(phb200_ctx *ctx, double *d, const double *h, size_t n) {
+  PHB_CHECK(cudaMemcpyAsync(d, h, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+static int d2h(phb200_ctx *ctx, double *h, const double *d, size_t n) {
+  PHB_CHECK(cudaMemcpyAsync(h, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+// device tiles -> EGmass(numel,nedof,nedof)
+__global__ void k_eg_to_ref(int numel, int nedof, const double *__restrict__ EG, double *__restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t tot = (size_t)numel * 400;
+  if (t >= tot) return;
+  size_t e = t % numel;
+  int k = (int)(t / numel), r = k % 20, c = k / 20;
+  out[e + (size_t)numel * (r + (size_t)nedof * c)] =
+      EG[((e / EG_TILE) * 400 + (size_t)(r + 20 * c)) * EG_TILE + (e % EG_TILE)];
+}
+
+extern "C" int phb200_set_state(phb200_ctx *ctx, const double *y, const double *ac) {
+  ENTER(ctx);
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  PHB_TRY(h2d(ctx, ctx->d_y, y, n5));
+  PHB_TRY(h2d(ctx, ctx->d_ac, ac, n5));
+  return 0;
+}
+extern "C" int phb200_dev_elmgmre(phb200_ctx *ctx, const phb200_step *st) {
+  ENTER(ctx);
+  return phb_elmgmre(ctx, st);
+}
+extern "C" int phb200_dev_solve(phb200_ctx *ctx, const phb200_step *st, int *iKs, int *lGMRES, int *ntotGM) {
+  ENTER(ctx);
+  return phb_solve(ctx, st, iKs, lGMRES, ntotGM);
+}
+extern "C" int phb200_dev_ap(phb200_ctx *ctx, int slot) {
+  ENTER(ctx);
+  if (slot < 0 || slot >= ctx->c.Kspace) return fail("dev_ap", "slot out of range");
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  double *src = ctx->d_uBrg + (size_t)slot * n5, *dst = src + n5;
+  PHB_CHECK(cudaMemcpyAsync(dst, src, sizeof(double) * n5, cudaMemcpyDeviceToDevice, ctx->stream));
+  PHB_TRY(phb_au1gmr(ctx, dst));
+  return phb_bc3per(ctx, dst, 5);
+}
+extern "C" int phb200_get_res(phb200_ctx *ctx, double *res) {
+  ENTER(ctx);
+  PHB_TRY(d2h(ctx, res, ctx->d_res, (size_t)5 * ctx->c.nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_get_dy(phb200_ctx *ctx, double *Dy) {
+  ENTER(ctx);
+  PHB_TRY(d2h(ctx, Dy, ctx->d_Dy, (size_t)5 * ctx->c.nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_get_bdiag(phb200_ctx *ctx, double *BD) {
+  ENTER(ctx);
+  PHB_TRY(d2h(ctx, BD, ctx->d_BDiag, (size_t)25 * ctx->c.nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_get_egmass(phb200_ctx *ctx, double *EGmass) {
+  ENTER(ctx);
+  const int numel = ctx->c.numel, nedof = ctx->c.nedof;
+  if (numel == 0) return 0;
+  double *d_out = nullptr;
+  size_t tot = (size_t)numel * nedof * nedof;
+  PHB_CHECK(cudaMalloc(&d_out, sizeof(double) * tot));
+  PHB_CHECK(cudaMemsetAsync(d_out, 0, sizeof(double) * tot, ctx->stream));
+  size_t nthr = (size_t)numel * 400;
+  k_eg_to_ref<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(numel, nedof, ctx->d_EG, d_out);
+  ctx->launches++;
+  PHB_CHECK(cudaGetLastError());
+  PHB_TRY(d2h(ctx, EGmass, d_out, tot));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_out);
+  return 0;
+}
+
+extern "C" int phb200_elmgmre(phb200_ctx *ctx, const double *y, const double *ac, const phb200_step *st, double *res,
+                              double *BDiag, double *EGmass, double *qres) {
+  ENTER(ctx);
+  if (!y || !ac || !st) return fail("elmgmre", "null argument");
+  PHB_TRY(phb200_set_state(ctx, y, ac));
+  PHB_TRY(phb_elmgmre(ctx, st));
+  if (res) PHB_TRY(d2h(ctx, res, ctx->d_res, (size_t)5 * ctx->c.nshg));
+  if (BDiag && st->iprec) PHB_TRY(d2h(ctx, BDiag, ctx->d_BDiag, (size_t)25 * ctx->c.nshg));
+  if (qres) PHB_TRY(d2h(ctx, qres, ctx->d_qres, (size_t)12 * ctx->c.nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (EGmass && st->lhs == 1) PHB_TRY(phb200_get_egmass(ctx, EGmass));
+  return 0;
+}
+
+extern "C" int phb200_solgmre(phb200_ctx *ctx, const double *y, const double *ac, const phb200_step *st, double *res,
+                              double *rmes, double *BDiag, double *Dy, double *HBrg, double *eBrg, double *yBrg,
+                              double *Rcos, double *Rsin, int *iKs, int *lGMRES, int *ntotGM) {
+  ENTER(ctx);
+  if (!y || !ac || !st || !Dy || !iKs || !lGMRES || !ntotGM) return fail("solgmre", "null argument");
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  PHB_TRY(phb200_set_state(ctx, y, ac));
+  PHB_TRY(phb_elmgmre(ctx, st));
+  PHB_TRY(phb_solve(ctx, st, iKs, lGMRES, ntotGM));
+  PHB_TRY(d2h(ctx, Dy, ctx->d_Dy, n5));
+  if (res) PHB_TRY(d2h(ctx, res, ctx->d_res, n5));
+  if (rmes) PHB_TRY(d2h(ctx, rmes, ctx->d_rmes, n5));
+  if (BDiag) PHB_TRY(d2h(ctx, BDiag, ctx->d_BDiag, (size_t)25 * ctx->c.nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  const int K = ctx->c.Kspace;
+  if (HBrg) memcpy(HBrg, ctx->HBrg.data(), sizeof(double) * (size_t)(K + 1) * K);
+  if (eBrg) memcpy(eBrg, ctx->eBrg.data(), sizeof(double) * (K + 1));
+  if (yBrg) memcpy(yBrg, ctx->yBrg.data(), sizeof(double) * (K + 1));
+  if (Rcos) memcpy(Rcos, ctx->Rcos.data(), sizeof(double) * (K + 1));
+  if (Rsin) memcpy(Rsin, ctx->Rsin.data(), sizeof(double) * (K + 1));
+  return 0;
+}
+
+// ---- finer seams on host arrays: stage through d_temp / d_BDiag ------------
+extern "C" int phb200_i3lu(phb200_ctx *ctx, double *Diag, double *r, int code) {
+  ENTER(ctx);
+  const size_t nshg = ctx->c.nshg;
+  if (Diag) PHB_TRY(h2d(ctx, ctx->d_BDiag, Diag, 25 * nshg));
+  double *d_r = ctx->d_uBrg;  // slot 1 as staging
+  if (code != 0) {
+    if (!r) return fail("i3lu", "null r");
+    PHB_TRY(h2d(ctx, d_r, r, 5 * nshg));
+  }
+  PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, d_r, code));
+  if (code == 0 && Diag) PHB_TRY(d2h(ctx, Diag, ctx->d_BDiag, 25 * nshg));
+  if (code != 0) PHB_TRY(d2h(ctx, r, d_r, 5 * nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_i3pre(phb200_ctx *ctx, double *EGmass) {
+  ENTER(ctx);
+  PHB_TRY(phb_i3pre(ctx));
+  if (EGmass) PHB_TRY(phb200_get_egmass(ctx, EGmass));
+  return 0;
+}
+extern "C" int phb200_au1gmr(phb200_ctx *ctx, double *u) {
+  ENTER(ctx);
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  double *d_u = ctx->d_uBrg;
+  PHB_TRY(h2d(ctx, d_u, u, n5));
+  PHB_TRY(phb_au1gmr(ctx, d_u));
+  PHB_TRY(d2h(ctx, u, d_u, n5));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_bc3per(phb200_ctx *ctx, double *r) {
+  ENTER(ctx);
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  double *d_u = ctx->d_uBrg;
+  PHB_TRY(h2d(ctx, d_u, r, n5));
+  PHB_TRY(phb_bc3per(ctx, d_u, 5));
+  PHB_TRY(d2h(ctx, r, d_u, n5));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_commu(phb200_ctx *ctx, double *global, int n, int code) {
+  ENTER(ctx);
+  if (n < 1 || n > 25) return fail("commu", "n must be 1..25");
+  const size_t len = (size_t)n * ctx->c.nshg;
+  double *d = (n <= 5) ? ctx->d_uBrg : ctx->d_scratch;
+  PHB_TRY(h2d(ctx, d, global, len));
+  PHB_TRY(phb_commu(ctx, d, n, code));
+  PHB_TRY(d2h(ctx, global, d, len));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_sumgat(phb200_ctx *ctx, const double *u, int n, double *summed) {
+  ENTER(ctx);
+  const size_t len = (size_t)n * ctx->c.nshg;
+  if (len * sizeof(double) > ctx->scratch_bytes) return fail("sumgat", "vector too long");
+  PHB_TRY(h2d(ctx, ctx->d_scratch, u, len));
+  return phb_sumgat_dev(ctx, ctx->d_scratch, len, summed);
+}
+
+// ---- instrumentation ---------------------------------------------------------
+extern "C" int phb200_event_record(phb200_ctx *ctx, int slot) {
+  ENTER(ctx);
+  if (slot < 0 || slot >= 16) return fail("event_record", "slot 0..15");
+  PHB_CHECK(cudaEventRecord(ctx->ev[slot], ctx->stream));
+  return 0;
+}
+extern "C" int phb200_event_elapsed_ms(phb200_ctx *ctx, int a, int b, float *ms) {
+  ENTER(ctx);
+  PHB_CHECK(cudaEventSynchronize(ctx->ev[b]));
+  PHB_CHECK(cudaEventElapsedTime(ms, ctx->ev[a], ctx->ev[b]));
+  return 0;
+}
+extern "C" int phb200_sync(phb200_ctx *ctx) {
+  ENTER(ctx);
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" long long phb200_launch_count(phb200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int phb200_profile(phb200_ctx *ctx, int on) {
+  ENTER(ctx);
+  ctx->profiling = on != 0;
+  return 0;
+}
+extern "C" int phb200_profile_get(phb200_ctx *ctx, int k, float *ms, long long *launches) {
+  if (!ctx || k < 0 || k >= KC_N) return 1;
+  if (ms) *ms = ctx->kc_ms[k];
+  if (launches) *launches = ctx->kc_n[k];
+  return 0;
+}
+extern "C" int phb200_profile_reset(phb200_ctx *ctx) {
+  if (!ctx) return 1;
+  memset(ctx->kc_ms, 0, sizeof ctx->kc_ms);
+  memset(ctx->kc_n, 0, sizeof ctx->kc_n);
+  return 0;
+}
+extern "C" int phb200_fp64_peak(phb200_ctx *ctx, double *tflops) {
+  ENTER(ctx);
+  return phb_fp64_peak(ctx, tflops);
+}
+extern "C" int phb200_flush_l2(phb200_ctx *ctx) {
+  ENTER(ctx);
+  PHB_CHECK(cudaMemsetAsync(ctx->d_scratch, 0, ctx->scratch_bytes, ctx->stream));
+  return 0;
+}

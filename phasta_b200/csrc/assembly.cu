@@ -1,0 +1,1010 @@
+// assembly.cu -- ElmGMRe on the device: AsIq/qpbc diffusive-flux projection,
+// the fused AsIGMR/e3/bc3LHS element kernel for linear tets, and the node-wise
+// bc3Res / bc3BDg post-processing.
+//
+// Reference path (all under phSolver/): compressible/elmgmr.f:1-274 ->
+// asiq.f/e3q.f/common/qpbc.f, asigmr.f:1-119 -> e3.f:106-299 (e3ivar, getthm,
+// getdiff, e3metric, e3mtrx, e3conv, e3visc, e3ls, e3tau, e3massr, e3massl,
+// e3wmlt), bc3lhs.f, bc3res.f, bc3bdg.f.
+//
+// B200 design (DESIGN.md "assembly kernel"):
+//  * one CTA works on a tile of TILE_E elements.  Phase A: one thread per
+//    (element, quadrature point) gathers nodal data and evaluates the
+//    point-wise state (thermodynamics, tau, fluxes) into shared memory.
+//    Phase B: one warp per (row node a, column node b) pair, lane = element,
+//    accumulates the 5x5 block of EGmass over the quadrature points in
+//    registers, extracts BDiag, applies bc3LHS in registers and stores the
+//    block with fully coalesced 256 B stores into the 32-element-tile layout.
+//  * algebra: with Y={p,u,T}, A_i = u_i A0 + w e_{i+1}^T + (e_{i+1} + u_i e_5) e_1^T
+//    (w = {rho, rho u, rho(h+k)}), so sum_i N_a,i A_i is a rank-2 update of A0
+//    and all LHS terms except the viscous one collapse to ONE 5x5x5 product
+//    per (a,b,qp):  W (At_a tau + N_a I) (At_b + c N_b A0).
+#include "ctx.h"
+#include <cstring>
+
+struct TetTables {
+  int nq;
+  double N[4][4];      // N[q][a]       shp(1,a,q)
+  double dN[4][4][3];  // dN[q][a][i]   shgl(1,i,a,q)
+  double Qwt[4];       // Qwt(1,q)
+};
+struct PhysParams {
+  double Rgas, gamma, gamma1, pr, mu0, Tref, Ssuth, dat131;
+  double dtsfct, taucfct, temper, Dtgl, fct1;  // fct1 = almi/gami/alfi*Dtgl
+  int matflg2, matflg3, idiff, iremove, ipord, lhs, iprec, pad;
+};
+__constant__ TetTables c_tet;
+__constant__ PhysParams c_ph;
+
+int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl) {
+  TetTables t;
+  memset(&t, 0, sizeof t);
+  const phb200_common &c = ctx->c;
+  t.nq = c.nint[0];
+  if (t.nq != 1 && t.nq != 4) {
+    fprintf(stderr, "phb200: init: tet rule with %d points not supported\n", t.nq);
+    return 1;
+  }
+  for (int q = 0; q < t.nq; q++) {
+    t.Qwt[q] = c.Qwt[0 + PHB200_MAXTOP * q];
+    for (int a = 0; a < 4; a++) {
+      t.N[q][a] = shp[0 + PHB200_MAXTOP * (a + PHB200_MAXSH * q)];
+      for (int i = 0; i < 3; i++)
+        t.dN[q][a][i] = shgl[0 + PHB200_MAXTOP * (i + 3 * (a + PHB200_MAXSH * q))];
+    }
+  }
+  PHB_CHECK(cudaMemcpyToSymbol(c_tet, &t, sizeof t));
+  return 0;
+}
+
+static int upload_phys(phb200_ctx *ctx, const phb200_step *st) {
+  const phb200_common &c = ctx->c;
+  PhysParams p;
+  p.Rgas = c.Rgas; p.gamma = c.gamma; p.gamma1 = c.gamma1; p.pr = c.pr;
+  p.mu0 = c.datmat121; p.Tref = c.datmat221; p.Ssuth = c.datmat321; p.dat131 = c.datmat131;
+  p.dtsfct = c.dtsfct; p.taucfct = c.taucfct; p.temper = c.temper;
+  p.Dtgl = st->Dtgl;
+  p.fct1 = st->almi / st->gami / st->alfi * st->Dtgl;
+  p.matflg2 = c.matflg2; p.matflg3 = c.matflg3; p.idiff = c.idiff;
+  p.iremove = c.iremoveStabTimeTerm; p.ipord = c.ipord;
+  p.lhs = st->lhs; p.iprec = st->iprec; p.pad = 0;
+  PHB_CHECK(cudaMemcpyToSymbolAsync(c_ph, &p, sizeof p, 0, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// point-wise helpers
+// ---------------------------------------------------------------------------
+struct Metric {
+  double shg[4][3];
+  double dxidx[3][3];
+  double W;
+};
+
+// e3metric (common/e3metric.f:22-77): xl[a][i], dN[a][i]
+__device__ __forceinline__ void tet_metric(const double xl[4][3], const double (*dN)[3], double Qw, Metric &g) {
+  double d[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int n = 0; n < 4; n++) s += xl[n][i] * dN[n][j];
+      d[i][j] = s;
+    }
+  double (*x)[3] = g.dxidx;
+  x[0][0] = d[1][1] * d[2][2] - d[2][1] * d[1][2];
+  x[0][1] = d[2][1] * d[0][2] - d[0][1] * d[2][2];
+  x[0][2] = d[0][1] * d[1][2] - d[0][2] * d[1][1];
+  double tmp = 1.0 / (x[0][0] * d[0][0] + x[0][1] * d[1][0] + x[0][2] * d[2][0]);
+  x[0][0] *= tmp; x[0][1] *= tmp; x[0][2] *= tmp;
+  x[1][0] = (d[1][2] * d[2][0] - d[1][0] * d[2][2]) * tmp;
+  x[1][1] = (d[0][0] * d[2][2] - d[2][0] * d[0][2]) * tmp;
+  x[1][2] = (d[1][0] * d[0][2] - d[0][0] * d[1][2]) * tmp;
+  x[2][0] = (d[1][0] * d[2][1] - d[1][1] * d[2][0]) * tmp;
+  x[2][1] = (d[2][0] * d[0][1] - d[0][0] * d[2][1]) * tmp;
+  x[2][2] = (d[0][0] * d[1][1] - d[0][1] * d[1][0]) * tmp;
+  g.W = Qw / tmp;
+#pragma unroll
+  for (int n = 0; n < 4; n++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      g.shg[n][i] = dN[n][0] * x[0][i] + dN[n][1] * x[1][i] + dN[n][2] * x[2][i];
+}
+
+// getDiff (compressible/getdiff.f:127,156-171), DNS
+__device__ __forceinline__ void diffusivities(double T, double cp, double &mu, double &lam, double &con) {
+  const double pt66 = 0.6666666666666666666666666666667;
+  if (c_ph.matflg2 == 0)
+    mu = c_ph.mu0;
+  else
+    mu = c_ph.mu0 * (T / c_ph.Tref) * sqrt(T / c_ph.Tref) * (c_ph.Tref + c_ph.Ssuth) / (T + c_ph.Ssuth);
+  lam = (c_ph.matflg3 == 0) ? (-pt66 * mu) : ((c_ph.dat131 - pt66) * mu);
+  con = mu * cp / c_ph.pr;
+}
+
+// viscous + heat flux (e3visc.f:278-343 == e3q.f:103-146), f[i][m], m=1..4
+// (momentum 1-3, energy); g[i][m] = dY_m/dx_i with m: 0 p,1..3 u,4 T
+__device__ __forceinline__ void diff_flux(const double g[3][5], double u1, double u2, double u3, double mu,
+                                          double lam, double con, double f[3][4]) {
+  double l2m = lam + 2.0 * mu;
+  const double *g1 = g[0], *g2 = g[1], *g3 = g[2];
+  f[0][0] = l2m * g1[1] + lam * g2[2] + lam * g3[3];
+  f[0][1] = mu * g1[2] + mu * g2[1];
+  f[0][2] = mu * g1[3] + mu * g3[1];
+  f[0][3] = l2m * u1 * g1[1] + mu * u2 * g1[2] + mu * u3 * g1[3] + mu * u2 * g2[1] + lam * u1 * g2[2] +
+            mu * u3 * g3[1] + lam * u1 * g3[3] + con * g1[4];
+  f[1][0] = mu * g1[2] + mu * g2[1];
+  f[1][1] = lam * g1[1] + l2m * g2[2] + lam * g3[3];
+  f[1][2] = mu * g2[3] + mu * g3[2];
+  f[1][3] = lam * u2 * g1[1] + mu * u1 * g1[2] + mu * u1 * g2[1] + l2m * u2 * g2[2] + mu * u3 * g2[3] +
+            mu * u3 * g3[2] + lam * u2 * g3[3] + con * g2[4];
+  f[2][0] = mu * g1[3] + mu * g3[1];
+  f[2][1] = mu * g2[3] + mu * g3[2];
+  f[2][2] = lam * g1[1] + lam * g2[2] + l2m * g3[3];
+  f[2][3] = lam * u3 * g1[1] + mu * u1 * g1[3] + lam * u3 * g2[2] + mu * u2 * g2[3] + mu * u1 * g3[1] +
+            mu * u2 * g3[2] + l2m * u3 * g3[3] + con * g3[4];
+}
+
+// gather the 4 nodes' coordinates
+__device__ __forceinline__ void gather_x(const double *__restrict__ x, int numnp, const int nd[4], double xl[4][3]) {
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) xl[a][i] = __ldg(x + (size_t)numnp * i + nd[a]);
+}
+
+// localy (common/localy.f:47-72): global {u,v,w,p,T} -> local {p,u,v,w,T}
+__device__ __forceinline__ void gather_y(const double *__restrict__ y, int nshg, int node, double yl[5]) {
+  yl[0] = __ldg(y + (size_t)nshg * 3 + node);
+  yl[1] = __ldg(y + node);
+  yl[2] = __ldg(y + (size_t)nshg * 1 + node);
+  yl[3] = __ldg(y + (size_t)nshg * 2 + node);
+  yl[4] = __ldg(y + (size_t)nshg * 4 + node);
+}
+
+// ---------------------------------------------------------------------------
+// AsIq + e3q (asiq.f:1-71, e3q.f:1-246): thread per element
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_asiq_tet(int numel, size_t numel_pad, int nshg, int numnp,
+                                                   const int *__restrict__ ien, const double *__restrict__ x,
+                                                   const double *__restrict__ y, double *__restrict__ qres,
+                                                   double *__restrict__ rmass) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= numel) return;
+  int nd[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) nd[a] = ien[(size_t)a * numel_pad + e];
+  double xl[4][3], yl[4][5];
+  gather_x(x, numnp, nd, xl);
+#pragma unroll
+  for (int a = 0; a < 4; a++) gather_y(y, nshg, nd[a], yl[a]);
+  double ql[4][12];
+  double rm[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    rm[a] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 12; k++) ql[a][k] = 0.0;
+  }
+  const int nq = c_tet.nq;
+  for (int q = 0; q < nq; q++) {
+    Metric g;
+    tet_metric(xl, c_tet.dN[q], c_tet.Qwt[q], g);
+    double Y[5] = {0, 0, 0, 0, 0};
+    double gr[3][5];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int m = 0; m < 5; m++) gr[i][m] = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      double Na = c_tet.N[q][a];
+#pragma unroll
+      for (int m = 0; m < 5; m++) {
+        Y[m] += Na * yl[a][m];
+#pragma unroll
+        for (int i = 0; i < 3; i++) gr[i][m] += g.shg[a][i] * yl[a][m];
+      }
+    }
+    double cp = c_ph.Rgas * c_ph.gamma / c_ph.gamma1;
+    double mu, lam, con;
+    diffusivities(Y[4], cp, mu, lam, con);
+    double f[3][4];
+    diff_flux(gr, Y[1], Y[2], Y[3], mu, lam, con, f);
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      double nw = c_tet.N[q][a] * g.W;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) ql[a][4 * i + m] += nw * f[i][m];
+      rm[a] += nw;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+#pragma unroll
+    for (int k = 0; k < 12; k++) atomicAdd(qres + (size_t)nshg * k + nd[a], ql[a][k]);
+    atomicAdd(rmass + nd[a], rm[a]);
+  }
+}
+
+// qpbc (common/qpbc.f:42-66): periodic accumulate / copy / divide
+__global__ void k_qpbc_peradd(int n, const int *__restrict__ slaves, const int *__restrict__ iper, int nshg,
+                              double *qres, double *rmass) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int j = slaves[t], i = iper[j];
+  atomicAdd(rmass + i, rmass[j]);
+  for (int k = 0; k < 12; k++) atomicAdd(qres + (size_t)nshg * k + i, qres[(size_t)nshg * k + j]);
+}
+__global__ void k_qpbc_percopy(int n, const int *__restrict__ slaves, const int *__restrict__ iper, int nshg,
+                               double *qres, double *rmass) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  int j = slaves[t], i = iper[j];
+  rmass[j] = rmass[i];
+  for (int k = 0; k < 12; k++) qres[(size_t)nshg * k + j] = qres[(size_t)nshg * k + i];
+}
+__global__ void k_qpbc_divide(int nshg, double *qres, double *rmass) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nshg) return;
+  double r = 1.0 / rmass[i];
+  rmass[i] = r;
+#pragma unroll
+  for (int k = 0; k < 12; k++) qres[(size_t)nshg * k + i] *= r;
+}
+
+// ---------------------------------------------------------------------------
+// fused AsIGMR + e3 + BDiag extraction + bc3LHS for linear tets
+// ---------------------------------------------------------------------------
+// per-(qp,element) state in shared memory
+enum { S_RHO = 0, S_U1, S_U2, S_U3, S_DRDP, S_DRDT, S_E1P, S_E3P, S_E4P, S_TAU1, S_TAU2, S_TAU3, S_MU, S_LAM, S_CON, S_NVAR };
+
+template <int TILE_E, int NQ>
+struct AsmSmem {
+  double st[NQ][S_NVAR][TILE_E];
+  double ri[NQ][20][TILE_E];
+  double shg[12][TILE_E];
+  double W[TILE_E];
+  int nd[4][TILE_E];
+};
+
+// bc3LHS velocity-code tables (bc3lhs.f:47-213): for one-velocity codes the
+// eliminated dof ia and the two that receive BC4, BC5; for two-velocity codes
+// the eliminated ia, ib and the survivor ic (BC4, BC6).  dofs are 1..3 = u1..u3
+template <int ia, int ib, int ic>
+__device__ __forceinline__ void bc_rows1(const double bc[3], double B[5][5]) {
+#pragma unroll
+  for (int n = 0; n < 5; n++) {
+    B[ib][n] -= bc[0] * B[ia][n];
+    B[ic][n] -= bc[1] * B[ia][n];
+  }
+}
+template <int ia, int ib, int ic>
+__device__ __forceinline__ void bc_rows2(const double bc[3], double B[5][5]) {
+#pragma unroll
+  for (int n = 0; n < 5; n++) B[ic][n] = B[ic][n] - bc[0] * B[ia][n] - bc[2] * B[ib][n];
+}
+template <int ia, int ib, int ic>
+__device__ __forceinline__ void bc_cols1(const double bc[3], double B[5][5]) {
+#pragma unroll
+  for (int m = 0; m < 5; m++) {
+    B[m][ib] -= bc[0] * B[m][ia];
+    B[m][ic] -= bc[1] * B[m][ia];
+  }
+}
+template <int ia, int ib, int ic>
+__device__ __forceinline__ void bc_cols2(const double bc[3], double B[5][5]) {
+#pragma unroll
+  for (int m = 0; m < 5; m++) B[m][ic] = B[m][ic] - bc[0] * B[m][ia] - bc[2] * B[m][ib];
+}
+// all register indices are compile-time so the 5x5 block stays in registers
+__device__ __forceinline__ void bc_rows(int code, const double bc[3], double B[5][5]) {
+  switch (code) {  // bc = {BC(:,4), BC(:,5), BC(:,6)}
+    case 1: bc_rows1<1, 2, 3>(bc, B); break;
+    case 2: bc_rows1<2, 1, 3>(bc, B); break;
+    case 4: bc_rows1<3, 1, 2>(bc, B); break;
+    case 3: bc_rows2<1, 2, 3>(bc, B); break;
+    case 5: bc_rows2<1, 3, 2>(bc, B); break;
+    case 6: bc_rows2<2, 3, 1>(bc, B); break;
+    default: break;
+  }
+}
+__device__ __forceinline__ void bc_cols(int code, const double bc[3], double B[5][5]) {
+  switch (code) {
+    case 1: bc_cols1<1, 2, 3>(bc, B); break;
+    case 2: bc_cols1<2, 1, 3>(bc, B); break;
+    case 4: bc_cols1<3, 1, 2>(bc, B); break;
+    case 3: bc_cols2<1, 2, 3>(bc, B); break;
+    case 5: bc_cols2<1, 3, 2>(bc, B); break;
+    case 6: bc_cols2<2, 3, 1>(bc, B); break;
+    default: break;
+  }
+}
+// bit mask of eliminated local dofs {p,u1,u2,u3,T} for an iBC word
+__device__ __forceinline__ int bc_elim_mask(int ibc) {
+  int m = 0;
+  if (ibc & (1 << 2)) m |= 1;
+  int code = (ibc >> 3) & 7;
+  // code bit0 -> u1 fixed, bit1 -> u2, bit2 -> u3 (bc3lhs.f:47-213)
+  m |= (code & 7) << 1;
+  if (ibc & (1 << 1)) m |= 1 << 4;
+  return m;
+}
+
+template <int TILE_E, int NQ, bool LHS>
+__global__ void __launch_bounds__(TILE_E * 4) k_asigmr_tet(
+    int numel, size_t numel_pad, int nshg, int numnp, int ntiles, const int *__restrict__ ien,
+    const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ ac,
+    const double *__restrict__ qres, const int *__restrict__ iBC, const double *__restrict__ BC,
+    double *__restrict__ res, double *__restrict__ BDiag, double *__restrict__ EG) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AsmSmem<TILE_E, NQ> &sm = *reinterpret_cast<AsmSmem<TILE_E, NQ> *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int el = tid % TILE_E;  // element within tile
+  const int sub = tid / TILE_E; // 0..3: quadrature point (phase A) / node (phase B')
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e = tile * TILE_E + el;
+    const bool live = e < numel;
+    // ------------------------------ phase A ------------------------------
+    if (sub < NQ) {
+      const int q = sub;
+      int nd[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) nd[a] = live ? ien[(size_t)a * numel_pad + e] : 0;
+      double xl[4][3];
+      gather_x(x, numnp, nd, xl);
+      Metric g;
+      tet_metric(xl, c_tet.dN[q], c_tet.Qwt[q], g);
+      if (q == 0) {
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          sm.nd[a][el] = nd[a];
+#pragma unroll
+          for (int i = 0; i < 3; i++) sm.shg[3 * a + i][el] = g.shg[a][i];
+        }
+        sm.W[el] = g.W;
+      }
+      // interpolate Y, Y,t, grad Y (e3ivar.f:147-356)
+      double Y[5] = {0, 0, 0, 0, 0}, At[5] = {0, 0, 0, 0, 0};
+      double gr[3][5];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int m = 0; m < 5; m++) gr[i][m] = 0.0;
+      double divq[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        double yl[5], al[5];
+        gather_y(y, nshg, nd[a], yl);
+        gather_y(ac, nshg, nd[a], al);
+        double Na = c_tet.N[q][a];
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+          Y[m] += Na * yl[m];
+          At[m] += Na * al[m];
+#pragma unroll
+          for (int i = 0; i < 3; i++) gr[i][m] += g.shg[a][i] * yl[m];
+        }
+        if (c_ph.idiff >= 1) {  // div q (e3ivar.f:374-395)
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int m = 0; m < 4; m++)
+              divq[m] += g.shg[a][i] * __ldg(qres + (size_t)nshg * (4 * i + m) + nd[a]);
+        }
+      }
+      const double pres = Y[0], u1 = Y[1], u2 = Y[2], u3 = Y[3], T = Y[4];
+      // getthm ithm=7 (getthm.f:111,148,163-169)
+      const double rho = pres / (c_ph.Rgas * T);
+      const double ei = T * (c_ph.Rgas / c_ph.gamma1);
+      const double h = T * (c_ph.Rgas * c_ph.gamma / c_ph.gamma1);
+      const double cv = c_ph.Rgas / c_ph.gamma1;
+      const double cp = c_ph.Rgas * c_ph.gamma / c_ph.gamma1;
+      const double alfap = 1.0 / T, betaT = 1.0 / pres;
+      const double rk = 0.5 * (u1 * u1 + u2 * u2 + u3 * u3);
+      double mu, lam, con;
+      diffusivities(T, cp, mu, lam, con);
+      // e3mtrx scalars (e3mtrx.f:87-97)
+      const double drdp = rho * betaT, drdT = -rho * alfap;
+      const double e1p = drdp * (h + rk) - alfap * T;
+      const double e3p = rho * (h + rk);
+      const double e4p = drdT * (h + rk) + rho * cp;
+      const double u[3] = {u1, u2, u3};
+      const double w[5] = {rho, rho * u1, rho * u2, rho * u3, e3p};
+      // A0 * v
+      auto A0v = [&](const double v[5], double o[5]) {
+        double c1 = drdp * v[0] + drdT * v[4];
+        o[0] = c1;
+        o[1] = u1 * c1 + rho * v[1];
+        o[2] = u2 * c1 + rho * v[2];
+        o[3] = u3 * c1 + rho * v[3];
+        o[4] = e1p * v[0] + rho * (u1 * v[1] + u2 * v[2] + u3 * v[3]) + e4p * v[4];
+      };
+      double ri[20];
+      // Galerkin Euler flux (e3conv.f:76-92)
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        ri[5 * i + 0] = (-u[i]) * rho;
+        ri[5 * i + 1] = (-u[i]) * rho * u1;
+        ri[5 * i + 2] = (-u[i]) * rho * u2;
+        ri[5 * i + 3] = (-u[i]) * rho * u3;
+        ri[5 * i + 4] = (-u[i]) * rho * (ei + rk) - u[i] * pres;
+        ri[5 * i + 1 + i] -= pres;
+      }
+      // strong residual L = A_i Y,i + A0 Y,t - div q (e3conv.f:100-179, e3ls.f:108-154)
+      double adv[5], L[5];
+#pragma unroll
+      for (int m = 0; m < 5; m++) adv[m] = u1 * gr[0][m] + u2 * gr[1][m] + u3 * gr[2][m];
+      const double divu = gr[0][1] + gr[1][2] + gr[2][3];
+      double tmpv[5];
+      A0v(adv, tmpv);
+      L[0] = tmpv[0] + w[0] * divu;
+      L[1] = tmpv[1] + w[1] * divu + gr[0][0];
+      L[2] = tmpv[2] + w[2] * divu + gr[1][0];
+      L[3] = tmpv[3] + w[3] * divu + gr[2][0];
+      L[4] = tmpv[4] + w[4] * divu + adv[0];
+      double massr[5];
+      A0v(At, massr);  // e3massr (e3massr.f:33-66): ri(16:20) = A0 Y,t
+#pragma unroll
+      for (int m = 0; m < 5; m++) L[m] += massr[m];
+      if (c_ph.idiff >= 1) {
+        L[1] -= divq[0]; L[2] -= divq[1]; L[3] -= divq[2]; L[4] -= divq[3];
+      }
+      // viscous flux (e3visc.f:278-343)
+      double f[3][4];
+      diff_flux(gr, u1, u2, u3, mu, lam, con, f);
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) ri[5 * i + 1 + m] += f[i][m];
+      // e3gijd for tets (e3tau.f:1438-1474) and Shakib tau (e3tau.f:140-176)
+      double gij[6];
+      {
+        const double c1 = 1.259921049894873e+00, c2 = 6.299605249474365e-01;
+        const double (*d)[3] = g.dxidx;
+        double t1, t2, t3;
+        t1 = c1 * d[0][0] + c2 * (d[1][0] + d[2][0]);
+        t2 = c1 * d[1][0] + c2 * (d[0][0] + d[2][0]);
+        t3 = c1 * d[2][0] + c2 * (d[0][0] + d[1][0]);
+        gij[0] = d[0][0] * t1 + d[1][0] * t2 + d[2][0] * t3;
+        t1 = c1 * d[0][1] + c2 * (d[1][1] + d[2][1]);
+        t2 = c1 * d[1][1] + c2 * (d[0][1] + d[2][1]);
+        t3 = c1 * d[2][1] + c2 * (d[0][1] + d[1][1]);
+        gij[1] = d[0][0] * t1 + d[1][0] * t2 + d[2][0] * t3;
+        gij[2] = d[0][1] * t1 + d[1][1] * t2 + d[2][1] * t3;
+        t1 = c1 * d[0][2] + c2 * (d[1][2] + d[2][2]);
+        t2 = c1 * d[1][2] + c2 * (d[0][2] + d[2][2]);
+        t3 = c1 * d[2][2] + c2 * (d[0][2] + d[1][2]);
+        gij[3] = d[0][0] * t1 + d[1][0] * t2 + d[2][0] * t3;
+        gij[4] = d[0][1] * t1 + d[1][1] * t2 + d[2][1] * t3;
+        gij[5] = d[0][2] * t1 + d[1][2] * t2 + d[2][2] * t3;
+      }
+      const double fff = (c_ph.ipord == 1) ? 36.0 : (c_ph.ipord == 2 ? 60.0 : 128.0);
+      const double dts = c_ph.iremove ? 0.0 : c_ph.dtsfct * c_ph.Dtgl;
+      double tau2 = rho * rho * ((2.0 * dts) * (2.0 * dts) +
+                                 (u1 * (u1 * gij[0] + 2.0 * (u2 * gij[1] + u3 * gij[3])) +
+                                  u2 * (u2 * gij[2] + 2.0 * u3 * gij[4]) + u3 * u3 * gij[5])) +
+                    fff * mu * mu * (gij[0] * gij[0] + gij[2] * gij[2] + gij[5] * gij[5] +
+                                     2.0 * (gij[1] * gij[1] + gij[3] * gij[3] + gij[4] * gij[4]));
+      const double fact = sqrt(tau2);
+      const double tau1 = 0.125 * fact / (rho * (gij[0] + gij[2] + gij[5])) * c_ph.taucfct;
+      tau2 = 1.0 / fact;
+      const double tau3 = tau2 / cv * c_ph.temper;
+      L[0] *= tau1; L[1] *= tau2; L[2] *= tau2; L[3] *= tau2; L[4] *= tau3;
+      // ri += A_i tau L (e3ls.f:352-457): A_i v = u_i A0 v + w v[i+1] + e_{i+1} v[0] + e_5 u_i v[0]
+      A0v(L, tmpv);
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+#pragma unroll
+        for (int m = 0; m < 5; m++) ri[5 * i + m] += u[i] * tmpv[m] + w[m] * L[1 + i];
+        ri[5 * i + 1 + i] += L[0];
+        ri[5 * i + 4] += u[i] * L[0];
+      }
+      if (NQ == 1) {
+        // e3juel (e3juel.f:50,98-151): exact tet mass, rl_a += A0 (W/(15 Qwt)) (ac_a + sum_b ac_b)
+        double al[4][5], ub[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          gather_y(ac, nshg, nd[a], al[a]);
+#pragma unroll
+          for (int m = 0; m < 5; m++) ub[m] += al[a][m];
+        }
+        const double fj = g.W / (c_tet.Qwt[q] * 15.0);
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          double v[5], o[5];
+#pragma unroll
+          for (int m = 0; m < 5; m++) v[m] = fj * (al[a][m] + ub[m]);
+          A0v(v, o);
+          if (live) {
+#pragma unroll
+            for (int m = 0; m < 5; m++) atomicAdd(res + (size_t)nshg * m + nd[a], o[m]);
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 5; m++) ri[15 + m] = massr[m];
+#pragma unroll
+      for (int k = 0; k < 20; k++) sm.ri[q][k][el] = ri[k];
+      if (LHS) {
+        sm.st[q][S_RHO][el] = rho;
+        sm.st[q][S_U1][el] = u1;
+        sm.st[q][S_U2][el] = u2;
+        sm.st[q][S_U3][el] = u3;
+        sm.st[q][S_DRDP][el] = drdp;
+        sm.st[q][S_DRDT][el] = drdT;
+        sm.st[q][S_E1P][el] = e1p;
+        sm.st[q][S_E3P][el] = e3p;
+        sm.st[q][S_E4P][el] = e4p;
+        sm.st[q][S_TAU1][el] = tau1;
+        sm.st[q][S_TAU2][el] = tau2;
+        sm.st[q][S_TAU3][el] = tau3;
+        sm.st[q][S_MU][el] = mu;
+        sm.st[q][S_LAM][el] = lam;
+        sm.st[q][S_CON][el] = con;
+      }
+    }
+    __syncthreads();
+    // ------------------ phase B': residual (e3wmlt.f:74-145) -------------
+    {
+      const int a = sub;  // 4 subs == 4 nodes
+      const double W = sm.W[el];
+      const double s0 = sm.shg[3 * a + 0][el], s1 = sm.shg[3 * a + 1][el], s2 = sm.shg[3 * a + 2][el];
+      double rl[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const double Na = c_tet.N[q][a];
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+          rl[m] += W * (s0 * sm.ri[q][m][el] + s1 * sm.ri[q][5 + m][el] + s2 * sm.ri[q][10 + m][el]);
+          if (NQ != 1) rl[m] += Na * W * sm.ri[q][15 + m][el];
+        }
+      }
+      if (live) {
+        const int node = sm.nd[a][el];
+#pragma unroll
+        for (int m = 0; m < 5; m++) atomicAdd(res + (size_t)nshg * m + node, rl[m]);
+      }
+    }
+    // ------------------ phase B: LHS blocks ------------------------------
+    if (LHS) {
+      const int warp = tid >> 5, lane = tid & 31;
+      constexpr int NWARP = TILE_E * 4 / 32;
+      constexpr int NHALF = TILE_E / 32;
+      for (int task = warp; task < 16 * NHALF; task += NWARP) {
+        const int pair = task / NHALF, half = task % NHALF;
+        const int a = pair >> 2, b = pair & 3;
+        const int le = half * 32 + lane;
+        const int ge = tile * TILE_E + le;
+        const double W = sm.W[le];
+        const double ga[3] = {sm.shg[3 * a][le], sm.shg[3 * a + 1][le], sm.shg[3 * a + 2][le]};
+        const double gb[3] = {sm.shg[3 * b][le], sm.shg[3 * b + 1][le], sm.shg[3 * b + 2][le]};
+        const double gagb = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+        double acc[5][5];
+#pragma unroll
+        for (int m = 0; m < 5; m++)
+#pragma unroll
+          for (int n = 0; n < 5; n++) acc[m][n] = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < NQ; q++) {
+          const double rho = sm.st[q][S_RHO][le];
+          const double u[3] = {sm.st[q][S_U1][le], sm.st[q][S_U2][le], sm.st[q][S_U3][le]};
+          const double drdp = sm.st[q][S_DRDP][le], drdT = sm.st[q][S_DRDT][le];
+          const double e1p = sm.st[q][S_E1P][le], e3p = sm.st[q][S_E3P][le], e4p = sm.st[q][S_E4P][le];
+          const double tau[5] = {sm.st[q][S_TAU1][le], sm.st[q][S_TAU2][le], sm.st[q][S_TAU2][le],
+                                 sm.st[q][S_TAU2][le], sm.st[q][S_TAU3][le]};
+          const double mu = sm.st[q][S_MU][le], lam = sm.st[q][S_LAM][le], con = sm.st[q][S_CON][le];
+          const double Na = c_tet.N[q][a], Nb = c_tet.N[q][b];
+          const double w[5] = {rho, rho * u[0], rho * u[1], rho * u[2], e3p};
+          const double al_a = u[0] * ga[0] + u[1] * ga[1] + u[2] * ga[2];
+          const double al_b = u[0] * gb[0] + u[1] * gb[1] + u[2] * gb[2];
+          // Tm = W (At_a tau + Na I),  At_a = al_a A0 + w ghat_a^T + hhat_a e1^T
+          double Tm[5][5];
+          {
+            const double c1 = al_a * drdp, c5 = al_a * drdT;
+            // column 1 (pressure)
+            Tm[0][0] = c1;
+            Tm[1][0] = c1 * u[0] + ga[0];
+            Tm[2][0] = c1 * u[1] + ga[1];
+            Tm[3][0] = c1 * u[2] + ga[2];
+            Tm[4][0] = al_a * e1p + al_a;
+            // columns 2..4 (velocities)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+#pragma unroll
+              for (int m = 0; m < 5; m++) Tm[m][1 + j] = w[m] * ga[j];
+              Tm[1 + j][1 + j] += al_a * rho;
+              Tm[4][1 + j] += al_a * rho * u[j];
+            }
+            // column 5 (temperature)
+            Tm[0][4] = c5;
+            Tm[1][4] = c5 * u[0];
+            Tm[2][4] = c5 * u[1];
+            Tm[3][4] = c5 * u[2];
+            Tm[4][4] = al_a * e4p;
+#pragma unroll
+            for (int m = 0; m < 5; m++) {
+#pragma unroll
+              for (int n = 0; n < 5; n++) Tm[m][n] *= tau[n];
+              Tm[m][m] += Na;
+            }
+#pragma unroll
+            for (int m = 0; m < 5; m++)
+#pragma unroll
+              for (int n = 0; n < 5; n++) Tm[m][n] *= W;
+          }
+          // Bm = At_b + c Nb A0 = (al_b + c Nb) A0 + w ghat_b^T + hhat_b e1^T
+          double Bm[5][5];
+          {
+            const double alp = al_b + c_ph.fct1 * Nb;
+            const double c1 = alp * drdp, c5 = alp * drdT;
+            Bm[0][0] = c1;
+            Bm[1][0] = c1 * u[0] + gb[0];
+            Bm[2][0] = c1 * u[1] + gb[1];
+            Bm[3][0] = c1 * u[2] + gb[2];
+            Bm[4][0] = alp * e1p + al_b;
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+#pragma unroll
+              for (int m = 0; m < 5; m++) Bm[m][1 + j] = w[m] * gb[j];
+              Bm[1 + j][1 + j] += alp * rho;
+              Bm[4][1 + j] += alp * rho * u[j];
+            }
+            Bm[0][4] = c5;
+            Bm[1][4] = c5 * u[0];
+            Bm[2][4] = c5 * u[1];
+            Bm[3][4] = c5 * u[2];
+            Bm[4][4] = alp * e4p;
+          }
+#pragma unroll
+          for (int m = 0; m < 5; m++)
+#pragma unroll
+            for (int n = 0; n < 5; n++) {
+              double s = acc[m][n];
+#pragma unroll
+              for (int k = 0; k < 5; k++) s += Tm[m][k] * Bm[k][n];
+              acc[m][n] = s;
+            }
+          // viscous block N_a,i K_ij N_b,j W (e3visc.f:69-139, e3wmlt.f:154-223)
+          {
+            double V[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+              for (int s = 0; s < 3; s++) V[r][s] = W * (mu * ga[s] * gb[r] + lam * ga[r] * gb[s]);
+            const double d0 = W * mu * gagb;
+            V[0][0] += d0; V[1][1] += d0; V[2][2] += d0;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+              for (int s = 0; s < 3; s++) acc[1 + r][1 + s] += V[r][s];
+#pragma unroll
+            for (int s = 0; s < 3; s++) acc[4][1 + s] += u[0] * V[0][s] + u[1] * V[1][s] + u[2] * V[2][s];
+            acc[4][4] += W * con * gagb;
+          }
+        }
+        if (ge < numel) {
+          const int na = sm.nd[a][le], nb = sm.nd[b][le];
+          // BDiag extraction BEFORE bc3LHS (asigmr.f:92-102)
+          if (a == b && c_ph.iprec != 0) {
+#pragma unroll
+            for (int m = 0; m < 5; m++)
+#pragma unroll
+              for (int n = 0; n < 5; n++) atomicAdd(BDiag + (size_t)nshg * (m + 5 * n) + na, acc[m][n]);
+          }
+          // bc3LHS (bc3lhs.f:1-290) on this block: rows by node a, columns by node b
+          const int ibca = __ldg(iBC + na), ibcb = __ldg(iBC + nb);
+          if (ibca | ibcb) {
+            // local view with dofs {p,u1,u2,u3,T} = indices 0..4; bc_rows/cols use 1..3 for velocities
+            const int codea = (ibca >> 3) & 7, codeb = (ibcb >> 3) & 7;
+            if (codea != 0 && codea != 7) {
+              const double bc[3] = {__ldg(BC + (size_t)nshg * 3 + na), __ldg(BC + (size_t)nshg * 4 + na),
+                                    __ldg(BC + (size_t)nshg * 5 + na)};
+              bc_rows(codea, bc, acc);
+            }
+            if (codeb != 0 && codeb != 7) {
+              const double bc[3] = {__ldg(BC + (size_t)nshg * 3 + nb), __ldg(BC + (size_t)nshg * 4 + nb),
+                                    __ldg(BC + (size_t)nshg * 5 + nb)};
+              bc_cols(codeb, bc, acc);
+            }
+            const int ma = bc_elim_mask(ibca), mb = bc_elim_mask(ibcb);
+#pragma unroll
+            for (int m = 0; m < 5; m++)
+#pragma unroll
+              for (int n = 0; n < 5; n++) {
+                if (((ma >> m) & 1) | ((mb >> n) & 1)) acc[m][n] = 0.0;
+              }
+            if (a == b) {
+#pragma unroll
+              for (int m = 0; m < 5; m++)
+                if ((ma >> m) & 1) acc[m][m] = 1.0;
+            }
+          }
+        }
+        // coalesced store of the block (also for padding lanes: zeros)
+        {
+          const size_t gtile = (size_t)ge / EG_TILE;
+          const int gl = ge % EG_TILE;
+          double *base = EG + gtile * (size_t)(400 * EG_TILE) + gl;
+          const bool ok = ge < numel;
+#pragma unroll
+          for (int n = 0; n < 5; n++)
+#pragma unroll
+            for (int m = 0; m < 5; m++)
+              base[(size_t)((5 * a + m) + 20 * (5 * b + n)) * EG_TILE] = ok ? acc[m][n] : 0.0;
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// node-wise BC kernels
+// ---------------------------------------------------------------------------
+// bc3Res (bc3res.f:30-153) without the periodic / slave parts
+__global__ void k_bc3res(int nshg, const int *__restrict__ iBC, const double *__restrict__ BC, double Rgas,
+                         double *res) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nshg) return;
+  int ibc = iBC[i];
+  if (ibc == 0) return;
+  double r[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) r[k] = res[(size_t)nshg * k + i];
+  const double b1 = BC[i], b4 = BC[(size_t)nshg * 3 + i], b5 = BC[(size_t)nshg * 4 + i],
+               b6 = BC[(size_t)nshg * 5 + i];
+  if (ibc & 1) {
+    r[4] = r[4] + b1 * Rgas * r[0];
+    r[0] = 0.0;
+  }
+  if (ibc & (1 << 2)) r[0] = 0.0;
+  switch ((ibc >> 3) & 7) {
+    case 1: r[2] -= b4 * r[1]; r[3] -= b5 * r[1]; r[1] = 0.0; break;
+    case 2: r[1] -= b4 * r[2]; r[3] -= b5 * r[2]; r[2] = 0.0; break;
+    case 3: r[3] = r[3] - b4 * r[1] - b6 * r[2]; r[1] = 0.0; r[2] = 0.0; break;
+    case 4: r[1] -= b4 * r[3]; r[2] -= b5 * r[3]; r[3] = 0.0; break;
+    case 5: r[2] = r[2] - b4 * r[1] - b6 * r[3]; r[1] = 0.0; r[3] = 0.0; break;
+    case 6: r[1] = r[1] - b4 * r[2] - b6 * r[3]; r[2] = 0.0; r[3] = 0.0; break;
+    case 7: r[1] = 0.0; r[2] = 0.0; r[3] = 0.0; break;
+    default: break;
+  }
+  if (ibc & (1 << 1)) r[4] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 5; k++) res[(size_t)nshg * k + i] = r[k];
+}
+
+// bc3BDg (bc3bdg.f:39-332), faithful including the v=3 product terms and the
+// v=5 surviving BDiag(3,2) (see oracle/oracle_global.c for the line notes)
+__global__ void k_bc3bdg(int nshg, const int *__restrict__ iBC, const double *__restrict__ BC,
+                         const double *__restrict__ y, double Rgas, double gamma, double gamma1, double *BD) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nshg) return;
+  int ibc = iBC[i];
+  if ((ibc & ((1 << 6) - 1)) == 0) return;
+  double B[6][6];
+#pragma unroll
+  for (int r = 1; r <= 5; r++)
+#pragma unroll
+    for (int c = 1; c <= 5; c++) B[r][c] = BD[(size_t)nshg * ((r - 1) + 5 * (c - 1)) + i];
+  const double b4 = BC[(size_t)nshg * 3 + i], b5 = BC[(size_t)nshg * 4 + i], b6 = BC[(size_t)nshg * 5 + i];
+  if (ibc & 1) {
+    double a5 = -y[(size_t)nshg * 4 + i] * (Rgas * gamma / gamma1);
+    B[5][5] = B[5][5] + a5 * a5 * B[1][1] + a5 * B[1][5] + a5 * B[5][1];
+    B[4][5] += a5 * B[4][1];
+    B[3][5] += a5 * B[3][1];
+    B[2][5] += a5 * B[2][1];
+    B[5][4] += a5 * B[1][4];
+    B[5][3] += a5 * B[1][3];
+    B[5][2] += a5 * B[1][2];
+    for (int k = 2; k <= 5; k++) { B[1][k] = 0.0; B[k][1] = 0.0; }
+    B[1][1] = 1.0;
+  }
+  if (ibc & (1 << 2)) {
+    for (int k = 2; k <= 5; k++) { B[1][k] = 0.0; B[k][1] = 0.0; }
+    B[1][1] = 1.0;
+  }
+  const int v = (ibc >> 3) & 7;
+  if (v == 1 || v == 2 || v == 4) {
+    int a, b, d;
+    if (v == 1) { a = 2; b = 3; d = 4; } else if (v == 2) { a = 3; b = 2; d = 4; } else { a = 4; b = 2; d = 3; }
+    B[5][d] -= b5 * B[5][a];
+    B[5][b] -= b4 * B[5][a];
+    B[d][5] -= b5 * B[a][5];
+    B[b][5] -= b4 * B[a][5];
+    B[d][1] -= b5 * B[a][1];
+    B[b][1] -= b4 * B[a][1];
+    B[1][d] -= b5 * B[1][a];
+    B[1][b] -= b4 * B[1][a];
+    B[d][d] = B[d][d] + b5 * b5 * B[a][a] - b5 * B[a][d] - b5 * B[d][a];
+    B[b][d] = B[b][d] + b4 * b5 * B[a][a] - b5 * B[b][a] - b4 * B[a][d];
+    B[d][b] = B[d][b] + b4 * b5 * B[a][a] - b5 * B[a][b] - b4 * B[d][a];
+    B[b][b] = B[b][b] + b4 * b4 * B[a][a] - b4 * B[a][b] - b4 * B[b][a];
+    for (int k = 1; k <= 5; k++)
+      if (k != a) { B[a][k] = 0.0; B[k][a] = 0.0; }
+    B[a][a] = 1.0;
+  } else if (v == 3) {
+    B[4][4] = B[4][4] + b4 * b4 * B[2][2] + b6 * b6 * B[3][3] + b4 * b6 * (B[2][3] * B[3][2]) -
+              b6 * (B[4][3] * B[3][4]) - b4 * (B[4][2] * B[2][4]);
+    B[1][4] = B[1][4] - b4 * B[1][2] - b6 * B[1][3];
+    B[4][1] = B[4][1] - b4 * B[2][1] - b6 * B[3][1];
+    B[5][4] = B[5][4] - b4 * B[5][2] - b6 * B[5][3];
+    B[4][5] = B[4][5] - b4 * B[2][5] - b6 * B[3][5];
+    for (int k = 1; k <= 5; k++) {
+      if (k != 2) { B[2][k] = 0.0; B[k][2] = 0.0; }
+      if (k != 3) { B[3][k] = 0.0; B[k][3] = 0.0; }
+    }
+    B[3][3] = 1.0;
+    B[2][2] = 1.0;
+  } else if (v == 5 || v == 6) {
+    int a, b, d;
+    if (v == 5) { a = 2; b = 4; d = 3; } else { a = 3; b = 4; d = 2; }
+    B[d][d] = B[d][d] + b4 * b4 * B[a][a] + b6 * b6 * B[b][b] + b4 * b6 * (B[a][b] + B[b][a]) -
+              b4 * (B[a][d] + B[d][a]) - b6 * (B[b][d] + B[d][b]);
+    B[1][d] = B[1][d] - b4 * B[1][a] - b6 * B[1][b];
+    B[d][1] = B[d][1] - b4 * B[a][1] - b6 * B[b][1];
+    B[5][d] = B[5][d] - b4 * B[5][a] - b6 * B[5][b];
+    B[d][5] = B[d][5] - b4 * B[a][5] - b6 * B[b][5];
+    double keep32 = B[3][2];
+    for (int k = 1; k <= 5; k++) {
+      if (k != a) { B[a][k] = 0.0; B[k][a] = 0.0; }
+      if (k != b) { B[b][k] = 0.0; B[k][b] = 0.0; }
+    }
+    if (v == 5) B[3][2] = keep32;
+    B[b][b] = 1.0;
+    B[a][a] = 1.0;
+  } else if (v == 7) {
+    for (int a = 2; a <= 4; a++) {
+      for (int k = 1; k <= 5; k++)
+        if (k != a) { B[a][k] = 0.0; B[k][a] = 0.0; }
+      B[a][a] = 1.0;
+    }
+  }
+  if (ibc & (1 << 1)) {
+    B[5][5] = 1.0;
+    for (int k = 1; k <= 4; k++) { B[k][5] = 0.0; B[5][k] = 0.0; }
+  }
+#pragma unroll
+  for (int r = 1; r <= 5; r++)
+#pragma unroll
+    for (int c = 1; c <= 5; c++) BD[(size_t)nshg * ((r - 1) + 5 * (c - 1)) + i] = B[r][c];
+}
+
+// periodic master += slave (bc3res.f:157-163, bc3bdg.f:337-343, bc3per.f:28-34)
+__global__ void k_per_add(int n, const int *__restrict__ slaves, const int *__restrict__ iper, int nshg, int ncol,
+                          double *v, int zero_slave) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * ncol) return;
+  int j = slaves[t % n], k = t / n, i = iper[j];
+  double *col = v + (size_t)nshg * k;
+  atomicAdd(col + i, col[j]);
+  if (zero_slave) col[j] = 0.0;
+}
+__global__ void k_per_copy(int n, const int *__restrict__ slaves, const int *__restrict__ iper, int nshg, int ncol,
+                           double *v) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * ncol) return;
+  int j = slaves[t % n], k = t / n, i = iper[j];
+  v[(size_t)nshg * k + j] = v[(size_t)nshg * k + i];
+}
+
+int phb_bc3per(phb200_ctx *ctx, double *d_r, int n) {
+  if (ctx->n_perslave == 0) return 0;
+  KScope ks(ctx, KC_NODE);
+  int tot = ctx->n_perslave * n;
+  k_per_add<<<(tot + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, ctx->c.nshg,
+                                                        n, d_r, 1);
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
+
+template <int TILE_E, int NQ, bool LHS>
+static int launch_asigmr(phb200_ctx *ctx) {
+  const phb200_common &c = ctx->c;
+  size_t smem = sizeof(AsmSmem<TILE_E, NQ>);
+  auto kern = k_asigmr_tet<TILE_E, NQ, LHS>;
+  static bool configured = false;
+  if (!configured) {
+    PHB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int ntiles = (ctx->numel_tet + TILE_E - 1) / TILE_E;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TILE_E * 4, smem);
+  if (occ < 1) occ = 1;
+  int grid = nsm * occ;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  KScope ks(ctx, KC_ASM);
+  kern<<<grid, TILE_E * 4, smem, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, c.nshg, c.numnp, ntiles, ctx->d_ien,
+                                                ctx->d_x, ctx->d_y, ctx->d_ac, ctx->d_qres, ctx->d_iBC, ctx->d_BC,
+                                                ctx->d_res, ctx->d_BDiag, ctx->d_EG);
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ElmGMRe (elmgmr.f:1-274) on the resident state
+int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st) {
+  const phb200_common &c = ctx->c;
+  const int nshg = c.nshg;
+  cudaStream_t s = ctx->stream;
+  PHB_TRY(upload_phys(ctx, st));
+  const int nq = c.nint[0];
+  if (c.idiff == 1) {
+    PHB_CHECK(cudaMemsetAsync(ctx->d_qres, 0, sizeof(double) * 12 * (size_t)nshg, s));
+    PHB_CHECK(cudaMemsetAsync(ctx->d_rmass, 0, sizeof(double) * (size_t)nshg, s));
+    if (ctx->numel_tet > 0) {
+      KScope ks(ctx, KC_ASIQ);
+      k_asiq_tet<<<(ctx->numel_tet + 127) / 128, 128, 0, s>>>(ctx->numel_tet, ctx->numel_pad, nshg, c.numnp,
+                                                              ctx->d_ien, ctx->d_x, ctx->d_y, ctx->d_qres,
+                                                              ctx->d_rmass);
+      PHB_CHECK(cudaGetLastError());
+    }
+    // qpbc (qpbc.f:37-95)
+    PHB_TRY(phb_commu(ctx, ctx->d_qres, 12, 0));
+    PHB_TRY(phb_commu(ctx, ctx->d_rmass, 1, 0));
+    {
+      KScope ks(ctx, KC_NODE);
+      if (ctx->n_perslave) {
+        int nb = (ctx->n_perslave + 127) / 128;
+        k_qpbc_peradd<<<nb, 128, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, ctx->d_qres,
+                                         ctx->d_rmass);
+        k_qpbc_percopy<<<nb, 128, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, ctx->d_qres,
+                                          ctx->d_rmass);
+        ctx->launches++;
+      }
+      k_qpbc_divide<<<(nshg + 255) / 256, 256, 0, s>>>(nshg, ctx->d_qres, ctx->d_rmass);
+      ctx->launches++;
+      PHB_CHECK(cudaGetLastError());
+    }
+    PHB_TRY(phb_commu(ctx, ctx->d_qres, 12, 1));
+  } else if (c.idiff != 0) {
+    fprintf(stderr, "phb200: elmgmre: idiff=%d not supported (0 or 1)\n", c.idiff);
+    return 1;
+  }
+  PHB_CHECK(cudaMemsetAsync(ctx->d_res, 0, sizeof(double) * 5 * (size_t)nshg, s));
+  if (st->iprec != 0) PHB_CHECK(cudaMemsetAsync(ctx->d_BDiag, 0, sizeof(double) * 25 * (size_t)nshg, s));
+  if (ctx->numel_tet > 0) {
+    if (nq == 4) {
+      if (st->lhs == 1) PHB_TRY((launch_asigmr<32, 4, true>(ctx)));
+      else PHB_TRY((launch_asigmr<32, 4, false>(ctx)));
+    } else {
+      if (st->lhs == 1) PHB_TRY((launch_asigmr<32, 1, true>(ctx)));
+      else PHB_TRY((launch_asigmr<32, 1, false>(ctx)));
+    }
+  }
+  if (st->lhs == 1) ctx->have_lhs = true;
+  // halo + BC post-processing (elmgmr.f:249-268)
+  PHB_TRY(phb_commu(ctx, ctx->d_res, 5, 0));
+  if (st->iprec != 0) PHB_TRY(phb_commu(ctx, ctx->d_BDiag, 25, 0));
+  {
+    KScope ks(ctx, KC_NODE);
+    k_bc3res<<<(nshg + 255) / 256, 256, 0, s>>>(nshg, ctx->d_iBC, ctx->d_BC, c.Rgas, ctx->d_res);
+    PHB_CHECK(cudaGetLastError());
+  }
+  PHB_TRY(phb_bc3per(ctx, ctx->d_res, 5));
+  PHB_TRY(phb_zero_slaves(ctx, ctx->d_res, 5, 0));
+  if (st->iprec != 0) {
+    KScope ks(ctx, KC_NODE);
+    k_bc3bdg<<<(nshg + 255) / 256, 256, 0, s>>>(nshg, ctx->d_iBC, ctx->d_BC, ctx->d_y, c.Rgas, c.gamma, c.gamma1,
+                                                ctx->d_BDiag);
+    if (ctx->n_perslave) {
+      int tot = ctx->n_perslave * 25;
+      k_per_add<<<(tot + 255) / 256, 256, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, 25,
+                                                  ctx->d_BDiag, 0);
+      k_per_copy<<<(tot + 255) / 256, 256, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, 25,
+                                                   ctx->d_BDiag);
+      ctx->launches += 2;
+    }
+    PHB_CHECK(cudaGetLastError());
+  }
+  if (st->iprec != 0) PHB_TRY(phb_zero_slaves(ctx, ctx->d_BDiag, 25, 1));
+  return 0;
+}

@@ -1,0 +1,271 @@
+// comm.cu -- commu (phSolver/common/commu.f:1-297) and the sumgat allreduce
+// (common/mpitools.f:107-137) on the device.
+//
+// ilwork keeps its reference meaning (commu.f:131-143): per task
+// {itag, iacc (0 = slave/send on 'in', 1 = master/recv on 'in'), iother,
+// numseg, (isgbeg,lenseg)*}.  Each task's segments are flattened once into a
+// node list; 'in' = slaves pack -> send, masters recv -> add (dof-outer,
+// node-inner, tasks in ilwork order: commu.f:268-294); 'out' = masters pack
+// -> send, slaves recv -> overwrite.  Transport is NCCL point-to-point over
+// NVLink (one process per GPU), resolved with dlopen so a single-GPU run
+// needs no NCCL at all.  A second transport, the in-process "local group"
+// (several parts on ONE GPU, one host thread each, pthread barrier), exists
+// so the partitioned path can be parity-tested on a single-GPU box.
+#include "ctx.h"
+#include <dlfcn.h>
+#include <pthread.h>
+#include <cstring>
+#include <mutex>
+
+// ---- minimal NCCL surface (nccl.h 2.27), resolved at run time -------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat64 = 8, ncclSum = 0 };
+static struct {
+  void *h;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char *(*GetErrorString)(ncclResult_t);
+} N;
+
+static int nccl_load() {
+  if (N.h) return 0;
+  const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+  for (int i = 0; names[i] && !N.h; i++) N.h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+  if (!N.h) {
+    fprintf(stderr, "phb200: comm_init: cannot dlopen libnccl.so.2: %s\n", dlerror());
+    return 1;
+  }
+#define SYM(f)                                                    \
+  *(void **)(&N.f) = dlsym(N.h, "nccl" #f);                       \
+  if (!N.f) {                                                     \
+    fprintf(stderr, "phb200: comm_init: missing nccl" #f "\n");   \
+    return 1;                                                     \
+  }
+  SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(GroupStart)
+  SYM(GroupEnd) SYM(GetErrorString)
+#undef SYM
+  return 0;
+}
+#define NCCL_CHECK(call)                                                                   \
+  do {                                                                                     \
+    ncclResult_t r_ = (call);                                                              \
+    if (r_ != 0) {                                                                         \
+      fprintf(stderr, "phb200: nccl %s:%d: %s\n", __FILE__, __LINE__, N.GetErrorString(r_)); \
+      return 1;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+// ---- in-process local group ------------------------------------------------
+struct LocalGroup {
+  int n = 0;
+  pthread_barrier_t bar;
+  bool bar_init = false;
+  phb200_ctx *members[64] = {};
+  double red[64] = {};
+};
+static LocalGroup g_local;
+static std::mutex g_local_mu;
+
+extern "C" int phb200_local_group_join(phb200_ctx *ctx, int nranks) {
+  std::lock_guard<std::mutex> lk(g_local_mu);
+  if (nranks > 64) return 1;
+  if (!g_local.bar_init || g_local.n != nranks) {
+    if (g_local.bar_init) pthread_barrier_destroy(&g_local.bar);
+    pthread_barrier_init(&g_local.bar, nullptr, nranks);
+    g_local.bar_init = true;
+    g_local.n = nranks;
+  }
+  g_local.members[ctx->c.myrank] = ctx;
+  ctx->nccl = nullptr;
+  ctx->local_group = true;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+int phb_halo_setup(phb200_ctx *ctx, const int *il) {
+  ctx->tasks.clear();
+  ctx->d_halo_nodes = nullptr;
+  ctx->d_slave_nodes = nullptr;
+  ctx->n_slave_nodes = 0;
+  ctx->d_sendbuf = ctx->d_recvbuf = nullptr;
+  ctx->halo_cap = 0;
+  if (ctx->c.numpe <= 1 || !il || ctx->c.nlwork < 1) return 0;
+  std::vector<int> nodes, slaves;
+  int numtask = il[0], itk = 1;
+  for (int t = 0; t < numtask; t++) {
+    HaloTask h;
+    h.tag = il[itk];
+    h.iacc = il[itk + 1];
+    h.peer = il[itk + 2];
+    int numseg = il[itk + 3];
+    h.offset = (int)nodes.size();
+    for (int s = 0; s < numseg; s++) {
+      int beg = il[itk + 4 + 2 * s], len = il[itk + 5 + 2 * s];
+      for (int k = 0; k < len; k++) {
+        nodes.push_back(beg + k - 1);
+        if (h.iacc == 0) slaves.push_back(beg + k - 1);
+      }
+    }
+    h.count = (int)nodes.size() - h.offset;
+    ctx->tasks.push_back(h);
+    itk += 4 + 2 * numseg;
+  }
+  if (nodes.empty()) return 0;
+  PHB_CHECK(cudaMalloc(&ctx->d_halo_nodes, sizeof(int) * nodes.size()));
+  PHB_CHECK(cudaMemcpy(ctx->d_halo_nodes, nodes.data(), sizeof(int) * nodes.size(), cudaMemcpyHostToDevice));
+  if (!slaves.empty()) {
+    PHB_CHECK(cudaMalloc(&ctx->d_slave_nodes, sizeof(int) * slaves.size()));
+    PHB_CHECK(cudaMemcpy(ctx->d_slave_nodes, slaves.data(), sizeof(int) * slaves.size(), cudaMemcpyHostToDevice));
+    ctx->n_slave_nodes = (int)slaves.size();
+  }
+  ctx->halo_cap = nodes.size() * 25;
+  PHB_CHECK(cudaMalloc(&ctx->d_sendbuf, sizeof(double) * ctx->halo_cap));
+  PHB_CHECK(cudaMalloc(&ctx->d_recvbuf, sizeof(double) * ctx->halo_cap));
+  return 0;
+}
+
+// buf[(k*count + t)] <-> global[node_t + nshg*k]
+__global__ void k_halo_pack(int count, const int *__restrict__ nodes, int nshg, int n, const double *__restrict__ g,
+                            double *__restrict__ buf) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * n) return;
+  int k = t / count, i = t % count;
+  buf[t] = g[(size_t)nshg * k + nodes[i]];
+}
+__global__ void k_halo_unpack(int count, const int *__restrict__ nodes, int nshg, int n, double *__restrict__ g,
+                              const double *__restrict__ buf, int add) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count * n) return;
+  int k = t / count, i = t % count;
+  double *p = g + (size_t)nshg * k + nodes[i];
+  *p = add ? (*p + buf[t]) : buf[t];
+}
+
+int phb_commu(phb200_ctx *ctx, double *g, int n, int code) {
+  if (ctx->c.numpe <= 1 || ctx->tasks.empty()) return 0;
+  if (!ctx->nccl && !ctx->local_group) {
+    fprintf(stderr, "phb200: commu: numpe=%d but no communicator (call phb200_comm_init)\n", ctx->c.numpe);
+    return 1;
+  }
+  if (n > 25) {
+    fprintf(stderr, "phb200: commu: n=%d > 25 unsupported\n", n);
+    return 1;
+  }
+  cudaStream_t s = ctx->stream;
+  const int nshg = ctx->c.nshg;
+  // sender role: iacc==0 on 'in', iacc==1 on 'out'
+  const int send_role = (code == 0) ? 0 : 1;
+  {
+    KScope ks(ctx, KC_HALO);
+    for (auto &h : ctx->tasks)
+      if (h.iacc == send_role) {
+        int tot = h.count * n;
+        k_halo_pack<<<(tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g,
+                                                      ctx->d_sendbuf + (size_t)h.offset * 25);
+      }
+    PHB_CHECK(cudaGetLastError());
+  }
+  if (ctx->nccl) {
+    ncclComm_t comm = (ncclComm_t)ctx->nccl;
+    NCCL_CHECK(N.GroupStart());
+    for (auto &h : ctx->tasks) {
+      size_t cnt = (size_t)h.count * n;
+      if (h.iacc == send_role)
+        NCCL_CHECK(N.Send(ctx->d_sendbuf + (size_t)h.offset * 25, cnt, ncclFloat64, h.peer, comm, s));
+      else
+        NCCL_CHECK(N.Recv(ctx->d_recvbuf + (size_t)h.offset * 25, cnt, ncclFloat64, h.peer, comm, s));
+    }
+    NCCL_CHECK(N.GroupEnd());
+  } else {
+    // local group: every rank's packed data must be complete before peers read it
+    PHB_CHECK(cudaStreamSynchronize(s));
+    pthread_barrier_wait(&g_local.bar);
+    for (auto &h : ctx->tasks)
+      if (h.iacc != send_role) {
+        phb200_ctx *peer = g_local.members[h.peer];
+        const HaloTask *ph = nullptr;
+        for (auto &t : peer->tasks)
+          if (t.tag == h.tag && t.peer == ctx->c.myrank && t.iacc == send_role) ph = &t;
+        if (!ph || ph->count != h.count) {
+          fprintf(stderr, "phb200: commu: unmatched task tag %d\n", h.tag);
+          return 1;
+        }
+        PHB_CHECK(cudaMemcpyAsync(ctx->d_recvbuf + (size_t)h.offset * 25, peer->d_sendbuf + (size_t)ph->offset * 25,
+                                  sizeof(double) * h.count * n, cudaMemcpyDeviceToDevice, s));
+      }
+    PHB_CHECK(cudaStreamSynchronize(s));
+    pthread_barrier_wait(&g_local.bar);
+  }
+  {
+    KScope ks(ctx, KC_HALO);
+    for (auto &h : ctx->tasks)
+      if (h.iacc != send_role) {
+        int tot = h.count * n;
+        k_halo_unpack<<<(tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g,
+                                                        ctx->d_recvbuf + (size_t)h.offset * 25, code == 0);
+      }
+    PHB_CHECK(cudaGetLastError());
+  }
+  return 0;
+}
+
+int phb_allreduce_sum(phb200_ctx *ctx, double *d_vals, int n) {
+  if (ctx->c.numpe <= 1) return 0;
+  if (ctx->nccl) {
+    NCCL_CHECK(N.AllReduce(d_vals, d_vals, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+    return 0;
+  }
+  if (ctx->local_group) {
+    if (n != 1) return 1;
+    double v;
+    PHB_CHECK(cudaMemcpyAsync(&v, d_vals, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+    g_local.red[ctx->c.myrank] = v;
+    pthread_barrier_wait(&g_local.bar);
+    double s = 0.0;
+    for (int r = 0; r < g_local.n; r++) s += g_local.red[r];
+    pthread_barrier_wait(&g_local.bar);
+    PHB_CHECK(cudaMemcpyAsync(d_vals, &s, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  }
+  fprintf(stderr, "phb200: allreduce: numpe=%d but no communicator\n", ctx->c.numpe);
+  return 1;
+}
+
+int phb_comm_unique_id(void *id128) {
+  PHB_TRY(nccl_load());
+  ncclUniqueId id;
+  NCCL_CHECK(N.GetUniqueId(&id));
+  memcpy(id128, &id, 128);
+  return 0;
+}
+
+int phb_comm_init(phb200_ctx *ctx, const void *id128) {
+  PHB_TRY(nccl_load());
+  ncclUniqueId id;
+  memcpy(&id, id128, 128);
+  ncclComm_t comm;
+  PHB_CHECK(cudaSetDevice(ctx->device));
+  NCCL_CHECK(N.CommInitRank(&comm, ctx->c.numpe, id, ctx->c.myrank));
+  ctx->nccl = comm;
+  ctx->local_group = false;
+  return 0;
+}
+
+void phb_comm_free(phb200_ctx *ctx) {
+  if (ctx->nccl && N.CommDestroy) N.CommDestroy((ncclComm_t)ctx->nccl);
+  ctx->nccl = nullptr;
+  if (ctx->local_group) {
+    std::lock_guard<std::mutex> lk(g_local_mu);
+    g_local.members[ctx->c.myrank] = nullptr;
+  }
+}

@@ -1,0 +1,125 @@
+// ctx.h -- device-resident state of one mesh part (one GPU) and shared helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "../../include/phb200.h"
+
+#define PHB_CHECK(call)                                                        \
+  do {                                                                         \
+    cudaError_t e_ = (call);                                                   \
+    if (e_ != cudaSuccess) {                                                   \
+      fprintf(stderr, "phb200: %s:%d: %s\n", __FILE__, __LINE__,               \
+              cudaGetErrorString(e_));                                         \
+      return 1;                                                                \
+    }                                                                          \
+  } while (0)
+
+#define PHB_TRY(expr)            \
+  do {                           \
+    int r_ = (expr);             \
+    if (r_) return r_;           \
+  } while (0)
+
+// kernel classes for the built-in profile (phb200_profile_get)
+enum { KC_ASM = 0, KC_ASIQ = 1, KC_AP = 2, KC_I3PRE = 3, KC_BLAS = 4, KC_NODE = 5, KC_HALO = 6, KC_N = 7 };
+
+// EGmass device layout: 32-element tiles, each tile is the reference's block
+// layout EGmass(npro=32,nedof,nedof) (asigmr.f:36): EG[tile][c][r][lane].
+#define EG_TILE 32
+__host__ __device__ inline size_t eg_index(size_t e, int r, int c, int nedof) {
+  return ((e / EG_TILE) * (size_t)(nedof * nedof) + (size_t)(r + nedof * c)) * EG_TILE + (e % EG_TILE);
+}
+
+struct HaloTask {
+  int peer, iacc, tag, count;  // count = number of nodes (all segments)
+  int offset;                  // into d_halo_nodes
+};
+
+struct phb200_ctx {
+  phb200_common c;
+  int device;
+  cudaStream_t stream;
+  // ---- mesh (tets only for now: lcsyst==1 blocks concatenated in file order)
+  int numel_tet;       // elements in tet blocks
+  size_t numel_pad;    // padded to EG_TILE
+  int *d_ien;          // [4][numel_pad] 0-based, padding repeats node 0 (masked)
+  int *d_iBC;          // [nshg]
+  double *d_BC;        // [ndofBC][nshg]
+  int *d_iper;         // [nshg] 0-based
+  double *d_x;         // [3][numnp]
+  int n_perslave;      // periodic slave nodes (iBC bit 10)
+  int *d_perslave;     // their ids
+  // ---- halo (ilwork)
+  std::vector<HaloTask> tasks;
+  int *d_halo_nodes;   // concatenated node lists of all tasks
+  int n_slave_nodes;   // nodes owned by another part (iacc==0 tasks)
+  int *d_slave_nodes;
+  double *d_sendbuf, *d_recvbuf;
+  size_t halo_cap;     // doubles per buffer
+  void *nccl;          // ncclComm_t
+  bool local_group;    // in-process multi-part transport (tests)
+  // ---- state / results
+  double *d_y, *d_ac;            // [5][nshg] {u,v,w,p,T}
+  double *d_qres, *d_rmass;      // [12][nshg], [nshg]
+  double *d_res, *d_rmes, *d_Dy, *d_temp;  // [5][nshg]
+  double *d_BDiag;               // [25][nshg]  BDiag(nshg,5,5)
+  double *d_BDtmp;               // scratch copy for i3pre's commu 'out'
+  double *d_EG;                  // tiles, see eg_index
+  double *d_uBrg;                // [Kspace+1][5][nshg]
+  double *d_dots;                // device scalars for fused MGS
+  double *h_dots;                // pinned
+  double *d_scratch;             // L2 flush / fp64 peak
+  size_t scratch_bytes;
+  bool have_lhs;                 // EGmass/BDiag hold a (preconditioned) system
+  // host-side Hessenberg work (solgmr.f:46-49)
+  std::vector<double> HBrg, eBrg, yBrg, Rcos, Rsin;
+  // ---- instrumentation
+  long long launches;
+  cudaEvent_t ev[16];
+  bool profiling;
+  cudaEvent_t pev0, pev1;
+  float kc_ms[KC_N];
+  long long kc_n[KC_N];
+};
+
+// launch bookkeeping: counts launches, optionally brackets with events
+struct KScope {
+  phb200_ctx *c;
+  int k;
+  KScope(phb200_ctx *c_, int k_) : c(c_), k(k_) {
+    c->launches++;
+    c->kc_n[k]++;
+    if (c->profiling) cudaEventRecord(c->pev0, c->stream);
+  }
+  ~KScope() {
+    if (c->profiling) {
+      cudaEventRecord(c->pev1, c->stream);
+      cudaEventSynchronize(c->pev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->pev0, c->pev1);
+      c->kc_ms[k] += ms;
+    }
+  }
+};
+
+// assembly.cu
+int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl);
+int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st);
+// solver.cu
+int phb_i3lu(phb200_ctx *ctx, double *d_Diag, double *d_r, int code);
+int phb_i3pre(phb200_ctx *ctx);
+int phb_au1gmr(phb200_ctx *ctx, double *d_u);
+int phb_bc3per(phb200_ctx *ctx, double *d_r, int n);
+int phb_zero_slaves(phb200_ctx *ctx, double *d_r, int n, int identity);
+int phb_sumgat_dev(phb200_ctx *ctx, const double *d_u, size_t len, double *out);
+int phb_solve(phb200_ctx *ctx, const phb200_step *st, int *iKs, int *lGMRES, int *ntotGM);
+int phb_fp64_peak(phb200_ctx *ctx, double *tflops);
+// comm.cu
+int phb_halo_setup(phb200_ctx *ctx, const int *ilwork);
+int phb_commu(phb200_ctx *ctx, double *d_global, int n, int code);
+int phb_allreduce_sum(phb200_ctx *ctx, double *d_vals, int n);
+int phb_comm_init(phb200_ctx *ctx, const void *id128);
+int phb_comm_unique_id(void *id128);
+void phb_comm_free(phb200_ctx *ctx);

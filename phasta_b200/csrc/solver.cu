@@ -1,0 +1,518 @@
+// solver.cu -- the Krylov side of SolGMRe on the device: i3LU, i3pre, the EBE
+// mat-vec Au1GMR/AsAuGMR, modified Gram-Schmidt with fused AXPY+dot kernels,
+// Givens/Hessenberg on the host (Kspace <= 50 scalars), solution update.
+//
+// Reference: phSolver/compressible/solgmr.f:83-347, i3lu.f:41-147,
+// i3pre.f:27-133, au1gmr.f:29-101, asaugmr.f:26-74, bc3per.f:28-34,
+// common/mpitools.f:107-137 (sumgat).
+#include "ctx.h"
+#include <cmath>
+#include <cstring>
+
+// ---------------------------------------------------------------------------
+// i3LU (i3lu.f:41-147): node-wise 5x5 LU without pivoting, inverted diagonal
+// ---------------------------------------------------------------------------
+__global__ void k_i3lu_fact(int nshg, double *Dg) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nshg) return;
+  double D[6][6];
+#pragma unroll
+  for (int a = 1; a <= 5; a++)
+#pragma unroll
+    for (int b = 1; b <= 5; b++) D[a][b] = Dg[(size_t)nshg * ((a - 1) + 5 * (b - 1)) + i];
+  D[1][1] = 1.0 / D[1][1];
+  D[2][1] = D[1][1] * D[2][1];
+  D[3][1] = D[1][1] * D[3][1];
+  D[4][1] = D[1][1] * D[4][1];
+  D[5][1] = D[1][1] * D[5][1];
+  D[2][2] = D[2][2] - D[2][1] * D[1][2];
+  D[2][3] = D[2][3] - D[2][1] * D[1][3];
+  D[2][4] = D[2][4] - D[2][1] * D[1][4];
+  D[2][5] = D[2][5] - D[2][1] * D[1][5];
+  D[2][2] = 1.0 / D[2][2];
+  D[3][2] = D[2][2] * (D[3][2] - D[3][1] * D[1][2]);
+  D[4][2] = D[2][2] * (D[4][2] - D[4][1] * D[1][2]);
+  D[5][2] = D[2][2] * (D[5][2] - D[5][1] * D[1][2]);
+  D[3][3] = D[3][3] - D[3][1] * D[1][3] - D[3][2] * D[2][3];
+  D[3][4] = D[3][4] - D[3][1] * D[1][4] - D[3][2] * D[2][4];
+  D[3][5] = D[3][5] - D[3][1] * D[1][5] - D[3][2] * D[2][5];
+  D[3][3] = 1.0 / D[3][3];
+  D[4][3] = D[3][3] * (D[4][3] - D[4][1] * D[1][3] - D[4][2] * D[2][3]);
+  D[5][3] = D[3][3] * (D[5][3] - D[5][1] * D[1][3] - D[5][2] * D[2][3]);
+  D[4][4] = D[4][4] - D[4][1] * D[1][4] - D[4][2] * D[2][4] - D[4][3] * D[3][4];
+  D[4][4] = 1.0 / D[4][4];
+  D[5][4] = D[4][4] * (D[5][4] - D[5][1] * D[1][4] - D[5][2] * D[2][4] - D[5][3] * D[3][4]);
+  D[5][5] = D[5][5] - D[5][1] * D[1][5] - D[5][2] * D[2][5] - D[5][3] * D[3][5] - D[5][4] * D[4][5];
+  D[5][5] = 1.0 / D[5][5];
+#pragma unroll
+  for (int a = 1; a <= 5; a++)
+#pragma unroll
+    for (int b = 1; b <= 5; b++) Dg[(size_t)nshg * ((a - 1) + 5 * (b - 1)) + i] = D[a][b];
+}
+
+#define DG(a, b) Dg[(size_t)nshg * (((a)-1) + 5 * ((b)-1)) + i]
+__global__ void k_i3lu_apply(int nshg, const double *__restrict__ Dg, double *r, int code) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nshg) return;
+  double r1 = r[i], r2 = r[(size_t)nshg + i], r3 = r[(size_t)nshg * 2 + i], r4 = r[(size_t)nshg * 3 + i],
+         r5 = r[(size_t)nshg * 4 + i];
+  if (code == 1) {  // forward (i3lu.f:102-117)
+    r2 = r2 - DG(2, 1) * r1;
+    r3 = r3 - DG(3, 1) * r1 - DG(3, 2) * r2;
+    r4 = r4 - DG(4, 1) * r1 - DG(4, 2) * r2 - DG(4, 3) * r3;
+    r5 = r5 - DG(5, 1) * r1 - DG(5, 2) * r2 - DG(5, 3) * r3 - DG(5, 4) * r4;
+  } else if (code == 2) {  // backward (i3lu.f:122-147)
+    r5 = DG(5, 5) * r5;
+    r4 = DG(4, 4) * (r4 - r5 * DG(4, 5));
+    r3 = DG(3, 3) * (r3 - r5 * DG(3, 5) - r4 * DG(3, 4));
+    r2 = DG(2, 2) * (r2 - r5 * DG(2, 5) - r4 * DG(2, 4) - r3 * DG(2, 3));
+    r1 = DG(1, 1) * (r1 - r5 * DG(1, 5) - r4 * DG(1, 4) - r3 * DG(1, 3) - r2 * DG(1, 2));
+  } else {  // product U.r (i3lu.f:152-165)
+    r1 = r1 / DG(1, 1) + r2 * DG(1, 2) + r3 * DG(1, 3) + r4 * DG(1, 4) + r5 * DG(1, 5);
+    r2 = r2 / DG(2, 2) + r3 * DG(2, 3) + r4 * DG(2, 4) + r5 * DG(2, 5);
+    r3 = r3 / DG(3, 3) + r4 * DG(3, 4) + r5 * DG(3, 5);
+    r4 = r4 / DG(4, 4) + r5 * DG(4, 5);
+    r5 = r5 / DG(5, 5);
+  }
+  r[i] = r1;
+  r[(size_t)nshg + i] = r2;
+  r[(size_t)nshg * 2 + i] = r3;
+  r[(size_t)nshg * 3 + i] = r4;
+  r[(size_t)nshg * 4 + i] = r5;
+}
+#undef DG
+
+int phb_i3lu(phb200_ctx *ctx, double *d_Diag, double *d_r, int code) {
+  int nshg = ctx->c.nshg;
+  KScope ks(ctx, KC_NODE);
+  if (code == 0)
+    k_i3lu_fact<<<(nshg + 127) / 128, 128, 0, ctx->stream>>>(nshg, d_Diag);
+  else
+    k_i3lu_apply<<<(nshg + 127) / 128, 128, 0, ctx->stream>>>(nshg, d_Diag, d_r, code);
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// i3pre (i3pre.f:43-133): EGmass <- L^-1 EGmass U^-1, block (a,b) at a time.
+// grid.y = pair (a,b); thread = element; loads/stores are 256 B coalesced.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_i3pre_tet(int numel, size_t numel_pad, int nshg,
+                                                    const int *__restrict__ ien, const double *__restrict__ BD,
+                                                    double *EG) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= numel) return;
+  const int a = blockIdx.y >> 2, b = blockIdx.y & 3;
+  const int na = ien[(size_t)a * numel_pad + e], nb = ien[(size_t)b * numel_pad + e];
+  double *base = EG + ((size_t)e / EG_TILE) * (size_t)(400 * EG_TILE) + (e % EG_TILE);
+  double B[5][5];
+#pragma unroll
+  for (int n = 0; n < 5; n++)
+#pragma unroll
+    for (int m = 0; m < 5; m++) B[m][n] = base[(size_t)((5 * a + m) + 20 * (5 * b + n)) * EG_TILE];
+  // rows: forward substitution with node a's L (i3pre.f:60-83)
+#define LA(r, c) __ldg(BD + (size_t)nshg * (((r)-1) + 5 * ((c)-1)) + na)
+  {
+    const double l21 = LA(2, 1), l31 = LA(3, 1), l32 = LA(3, 2), l41 = LA(4, 1), l42 = LA(4, 2), l43 = LA(4, 3),
+                 l51 = LA(5, 1), l52 = LA(5, 2), l53 = LA(5, 3), l54 = LA(5, 4);
+#pragma unroll
+    for (int n = 0; n < 5; n++) {
+      B[1][n] = B[1][n] - l21 * B[0][n];
+      B[2][n] = B[2][n] - l31 * B[0][n] - l32 * B[1][n];
+      B[3][n] = B[3][n] - l41 * B[0][n] - l42 * B[1][n] - l43 * B[2][n];
+      B[4][n] = B[4][n] - l51 * B[0][n] - l52 * B[1][n] - l53 * B[2][n] - l54 * B[3][n];
+    }
+  }
+#undef LA
+  // columns: right multiply by node b's U^-1 (i3pre.f:92-121)
+#define UB(r, c) __ldg(BD + (size_t)nshg * (((r)-1) + 5 * ((c)-1)) + nb)
+  {
+    const double u11 = UB(1, 1), u22 = UB(2, 2), u33 = UB(3, 3), u44 = UB(4, 4), u55 = UB(5, 5);
+    const double u12 = UB(1, 2), u13 = UB(1, 3), u14 = UB(1, 4), u15 = UB(1, 5), u23 = UB(2, 3), u24 = UB(2, 4),
+                 u25 = UB(2, 5), u34 = UB(3, 4), u35 = UB(3, 5), u45 = UB(4, 5);
+#pragma unroll
+    for (int m = 0; m < 5; m++) {
+      B[m][0] = u11 * B[m][0];
+      B[m][1] = u22 * (B[m][1] - u12 * B[m][0]);
+      B[m][2] = u33 * (B[m][2] - u13 * B[m][0] - u23 * B[m][1]);
+      B[m][3] = u44 * (B[m][3] - u14 * B[m][0] - u24 * B[m][1] - u34 * B[m][2]);
+      B[m][4] = u55 * (B[m][4] - u15 * B[m][0] - u25 * B[m][1] - u35 * B[m][2] - u45 * B[m][3]);
+    }
+  }
+#undef UB
+#pragma unroll
+  for (int n = 0; n < 5; n++)
+#pragma unroll
+    for (int m = 0; m < 5; m++) base[(size_t)((5 * a + m) + 20 * (5 * b + n)) * EG_TILE] = B[m][n];
+}
+
+int phb_i3pre(phb200_ctx *ctx) {
+  const int nshg = ctx->c.nshg;
+  const double *BD = ctx->d_BDiag;
+  if (ctx->c.numpe > 1) {
+    // BDiag = BDtmp; commu(BDiag,'out') (i3pre.f:31-36): slaves need the master's LU
+    PHB_CHECK(cudaMemcpyAsync(ctx->d_BDtmp, ctx->d_BDiag, sizeof(double) * 25 * (size_t)nshg,
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+    PHB_TRY(phb_commu(ctx, ctx->d_BDtmp, 25, 1));
+    BD = ctx->d_BDtmp;
+  }
+  if (ctx->numel_tet > 0) {
+    KScope ks(ctx, KC_I3PRE);
+    dim3 grid((ctx->numel_tet + 127) / 128, 16);
+    k_i3pre_tet<<<grid, 128, 0, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, nshg, ctx->d_ien, BD, ctx->d_EG);
+    PHB_CHECK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Au1GMR / AsAuGMR (au1gmr.f:29-101, asaugmr.f:26-74): thread per element,
+// 400 coalesced 8-byte loads each; HBM-bound (3200 B/element).
+// ---------------------------------------------------------------------------
+__global__ void k_iper_copy(int n, const int *__restrict__ slaves, const int *__restrict__ iper, int nshg,
+                            double *u) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 5) return;
+  int j = slaves[t % n], k = t / n;
+  u[(size_t)nshg * k + j] = u[(size_t)nshg * k + iper[j]];
+}
+
+__global__ void __launch_bounds__(128) k_ap_ebe_tet(int numel, size_t numel_pad, int nshg,
+                                                     const int *__restrict__ ien, const double *__restrict__ EG,
+                                                     const double *__restrict__ u, double *__restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= numel) return;
+  int nd[4];
+  double p[20], q[20];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    nd[a] = ien[(size_t)a * numel_pad + e];
+#pragma unroll
+    for (int m = 0; m < 5; m++) {
+      p[5 * a + m] = __ldg(u + (size_t)nshg * m + nd[a]);
+      q[5 * a + m] = 0.0;
+    }
+  }
+  const double *base = EG + ((size_t)e / EG_TILE) * (size_t)(400 * EG_TILE) + (e % EG_TILE);
+#pragma unroll
+  for (int c = 0; c < 20; c++) {
+    const double pc = p[c];
+#pragma unroll
+    for (int r = 0; r < 20; r++) q[r] += __ldcs(base + (size_t)(r + 20 * c) * EG_TILE) * pc;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int m = 0; m < 5; m++) atomicAdd(out + (size_t)nshg * m + nd[a], q[5 * a + m]);
+}
+
+__global__ void k_zero_nodes(int n, const int *__restrict__ nodes, int nshg, int ncol, double *v, int identity) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * ncol) return;
+  int A = nodes[t % n], k = t / n;
+  double val = 0.0;
+  if (identity && (k % 6 == 0)) val = 1.0;  // (j,j) of a 5x5 col-major block: k = j + 5 j
+  v[(size_t)nshg * k + A] = val;
+}
+
+int phb_zero_slaves(phb200_ctx *ctx, double *d_r, int n, int identity) {
+  if (ctx->n_slave_nodes == 0) return 0;
+  KScope ks(ctx, KC_NODE);
+  int tot = ctx->n_slave_nodes * n;
+  k_zero_nodes<<<(tot + 255) / 256, 256, 0, ctx->stream>>>(ctx->n_slave_nodes, ctx->d_slave_nodes, ctx->c.nshg, n,
+                                                           d_r, identity);
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// u <- A u (in place, like the reference; uses d_temp as uBtmp)
+int phb_au1gmr(phb200_ctx *ctx, double *d_u) {
+  const int nshg = ctx->c.nshg;
+  cudaStream_t s = ctx->stream;
+  if (!ctx->have_lhs) {
+    fprintf(stderr, "phb200: au1gmr: no LHS has been assembled (lhs=1 call needed first)\n");
+    return 1;
+  }
+  PHB_TRY(phb_commu(ctx, d_u, 5, 1));
+  if (ctx->n_perslave) {
+    KScope ks(ctx, KC_NODE);
+    int tot = ctx->n_perslave * 5;
+    k_iper_copy<<<(tot + 255) / 256, 256, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, d_u);
+    PHB_CHECK(cudaGetLastError());
+  }
+  PHB_CHECK(cudaMemsetAsync(ctx->d_temp, 0, sizeof(double) * 5 * (size_t)nshg, s));
+  if (ctx->numel_tet > 0) {
+    KScope ks(ctx, KC_AP);
+    k_ap_ebe_tet<<<(ctx->numel_tet + 127) / 128, 128, 0, s>>>(ctx->numel_tet, ctx->numel_pad, nshg, ctx->d_ien,
+                                                              ctx->d_EG, d_u, ctx->d_temp);
+    PHB_CHECK(cudaGetLastError());
+  }
+  PHB_CHECK(cudaMemcpyAsync(d_u, ctx->d_temp, sizeof(double) * 5 * (size_t)nshg, cudaMemcpyDeviceToDevice, s));
+  PHB_TRY(phb_commu(ctx, d_u, 5, 0));
+  PHB_TRY(phb_zero_slaves(ctx, d_u, 5, 0));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// BLAS-1 with device-resident scalars (no host round trip inside MGS)
+// ---------------------------------------------------------------------------
+#define RED_BLOCK 256
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[RED_BLOCK / 32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  v = (threadIdx.x < RED_BLOCK / 32) ? sh[threadIdx.x] : 0.0;
+  if (w == 0) {
+#pragma unroll
+    for (int o = RED_BLOCK / 64; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v;
+}
+
+// MGS step (solgmr.f:224-244): w -= beta_prev * uprev (if uprev); out = (w, uj)
+// beta_prev is read from device memory; *out must be zero on entry.
+__global__ void __launch_bounds__(RED_BLOCK) k_mgs_step(size_t n, double *__restrict__ w,
+                                                         const double *__restrict__ uprev,
+                                                         const double *__restrict__ beta_prev,
+                                                         const double *__restrict__ uj, double *out) {
+  double s = 0.0;
+  const double beta = uprev ? *beta_prev : 0.0;
+  const bool self = (uj == w);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double wi = w[i];
+    if (uprev) {
+      wi = wi - beta * uprev[i];
+      w[i] = wi;
+    }
+    s += wi * (self ? wi : uj[i]);
+  }
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+// v <- v / sqrt(*nrm2) (solgmr.f:251-256) or v <- v * alpha
+__global__ void k_scale_dev(size_t n, double *v, const double *nrm2) {
+  const double f = sqrt(*nrm2);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    v[i] = v[i] / f;
+}
+__global__ void k_scale(size_t n, double *v, double divisor) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    v[i] = v[i] / divisor;
+}
+__global__ void k_axpy(size_t n, double *y, double a, const double *__restrict__ x) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    y[i] = y[i] + a * x[i];
+}
+// Dy += sum_j yBrg(j) uBrg(:,:,j) in one pass (solgmr.f:315-317)
+__global__ void k_update(size_t n, double *Dy, const double *__restrict__ U, int nvec, const double *__restrict__ yb) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double s = Dy[i];
+    for (int j = 0; j < nvec; j++) s = s + yb[j] * U[(size_t)j * n + i];
+    Dy[i] = s;
+  }
+}
+__global__ void k_sub(size_t n, double *out, const double *__restrict__ a, const double *__restrict__ b) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = a[i] - b[i];
+}
+__global__ void __launch_bounds__(RED_BLOCK) k_sum(size_t n, const double *__restrict__ u, double *out) {
+  double s = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s += u[i];
+  s = block_sum(s);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+static inline int vec_grid(size_t n) {
+  size_t g = (n + RED_BLOCK - 1) / RED_BLOCK;
+  if (g > 148 * 8) g = 148 * 8;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// sumgat (mpitools.f:107-137): local sum + allreduce
+int phb_sumgat_dev(phb200_ctx *ctx, const double *d_u, size_t len, double *out) {
+  cudaStream_t s = ctx->stream;
+  PHB_CHECK(cudaMemsetAsync(ctx->d_dots, 0, sizeof(double), s));
+  {
+    KScope ks(ctx, KC_BLAS);
+    k_sum<<<vec_grid(len), RED_BLOCK, 0, s>>>(len, d_u, ctx->d_dots);
+    PHB_CHECK(cudaGetLastError());
+  }
+  PHB_TRY(phb_allreduce_sum(ctx, ctx->d_dots, 1));
+  PHB_CHECK(cudaMemcpyAsync(ctx->h_dots, ctx->d_dots, sizeof(double), cudaMemcpyDeviceToHost, s));
+  PHB_CHECK(cudaStreamSynchronize(s));
+  *out = ctx->h_dots[0];
+  return 0;
+}
+
+// dot(a,b) with allreduce, result on host
+static int dot_host(phb200_ctx *ctx, size_t n, double *a, const double *b, double *out) {
+  cudaStream_t s = ctx->stream;
+  PHB_CHECK(cudaMemsetAsync(ctx->d_dots, 0, sizeof(double), s));
+  {
+    KScope ks(ctx, KC_BLAS);
+    k_mgs_step<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, a, nullptr, nullptr, b, ctx->d_dots);
+    PHB_CHECK(cudaGetLastError());
+  }
+  PHB_TRY(phb_allreduce_sum(ctx, ctx->d_dots, 1));
+  PHB_CHECK(cudaMemcpyAsync(ctx->h_dots, ctx->d_dots, sizeof(double), cudaMemcpyDeviceToHost, s));
+  PHB_CHECK(cudaStreamSynchronize(s));
+  *out = ctx->h_dots[0];
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// SolGMRe after ElmGMRe (solgmr.f:83-347)
+// ---------------------------------------------------------------------------
+int phb_solve(phb200_ctx *ctx, const phb200_step *st, int *iKs_out, int *lGMRES_out, int *ntotGM) {
+  const phb200_common &c = ctx->c;
+  const int nshg = c.nshg, Kspace = c.Kspace, nGMRES = c.nGMRES;
+  const size_t n = (size_t)5 * nshg;
+  cudaStream_t s = ctx->stream;
+  double *U = ctx->d_uBrg;
+  auto Uk = [&](int k) { return U + (size_t)(k - 1) * n; };  // 1-based slot
+  double *HBrg = ctx->HBrg.data(), *eBrg = ctx->eBrg.data(), *yBrg = ctx->yBrg.data(), *Rcos = ctx->Rcos.data(),
+         *Rsin = ctx->Rsin.data();
+#define H(a, b) HBrg[((a)-1) + (size_t)(Kspace + 1) * ((b)-1)]
+  // rmes = res (solgmr.f:83)
+  PHB_CHECK(cudaMemcpyAsync(ctx->d_rmes, ctx->d_res, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  if (st->iprec != 0) PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, nullptr, 0));
+  PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, ctx->d_res, 1));
+  PHB_CHECK(cudaMemsetAsync(ctx->d_Dy, 0, sizeof(double) * n, s));
+  PHB_TRY(phb_i3pre(ctx));  // unconditional in SolGMRe (solgmr.f:112)
+  PHB_CHECK(cudaMemcpyAsync(Uk(1), ctx->d_res, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  double summed = 0.0;
+  PHB_TRY(dot_host(ctx, n, ctx->d_res, ctx->d_res, &summed));
+  double unorm = sqrt(summed);
+  int iKs = 0, lGMRES = 0;
+  std::fill(ctx->HBrg.begin(), ctx->HBrg.end(), 0.0);
+  if (!(unorm < 100.0 * c.epsM * c.epsM)) {
+    const double epsnrm = st->etol * unorm;
+    for (int mGMRES = 1; mGMRES <= nGMRES; mGMRES++) {
+      lGMRES = mGMRES - 1;
+      if (lGMRES > 0) {  // restart: R - A x (solgmr.f:149-178)
+        double *tmp = Uk(Kspace + 1);  // free slot at restart time
+        PHB_CHECK(cudaMemcpyAsync(tmp, ctx->d_Dy, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        PHB_TRY(phb_au1gmr(ctx, tmp));
+        PHB_TRY(phb_bc3per(ctx, tmp, 5));
+        {
+          KScope ks(ctx, KC_BLAS);
+          k_sub<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, Uk(1), ctx->d_res, tmp);
+          PHB_CHECK(cudaGetLastError());
+        }
+        PHB_TRY(dot_host(ctx, n, Uk(1), Uk(1), &summed));
+        unorm = sqrt(summed);
+      }
+      for (int k = 0; k < Kspace + 1; k++) eBrg[k] = 0.0;
+      eBrg[0] = unorm;
+      {
+        KScope ks(ctx, KC_BLAS);
+        k_scale<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, Uk(1), unorm);
+        PHB_CHECK(cudaGetLastError());
+      }
+      for (int iK = 1; iK <= Kspace; iK++) {
+        iKs = iK;
+        double *w = Uk(iKs + 1);
+        PHB_CHECK(cudaMemcpyAsync(w, Uk(iKs), sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+        PHB_TRY(phb_au1gmr(ctx, w));
+        PHB_TRY(phb_bc3per(ctx, w, 5));
+        // modified Gram-Schmidt, beta_j stay on the device (d_dots[j]) unless
+        // an allreduce is needed between steps
+        PHB_CHECK(cudaMemsetAsync(ctx->d_dots, 0, sizeof(double) * (iKs + 2), s));
+        for (int jK = 1; jK <= iKs + 1; jK++) {
+          {
+            KScope ks(ctx, KC_BLAS);
+            k_mgs_step<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, w, jK == 1 ? nullptr : Uk(jK - 1),
+                                                         ctx->d_dots + (jK - 1), Uk(jK), ctx->d_dots + jK);
+            PHB_CHECK(cudaGetLastError());
+          }
+          PHB_TRY(phb_allreduce_sum(ctx, ctx->d_dots + jK, 1));
+        }
+        {
+          KScope ks(ctx, KC_BLAS);
+          k_scale_dev<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, w, ctx->d_dots + iKs + 1);
+          PHB_CHECK(cudaGetLastError());
+        }
+        PHB_CHECK(cudaMemcpyAsync(ctx->h_dots, ctx->d_dots + 1, sizeof(double) * (iKs + 1), cudaMemcpyDeviceToHost, s));
+        PHB_CHECK(cudaStreamSynchronize(s));
+        for (int jK = 1; jK <= iKs + 1; jK++) H(jK, iKs) = ctx->h_dots[jK - 1];
+        unorm = sqrt(ctx->h_dots[iKs]);
+        H(iKs + 1, iKs) = unorm;
+        // Givens (solgmr.f:270-288)
+        for (int jK = 1; jK <= iKs - 1; jK++) {
+          double tmp = Rcos[jK - 1] * H(jK, iKs) + Rsin[jK - 1] * H(jK + 1, iKs);
+          H(jK + 1, iKs) = -Rsin[jK - 1] * H(jK, iKs) + Rcos[jK - 1] * H(jK + 1, iKs);
+          H(jK, iKs) = tmp;
+        }
+        double tmp = sqrt(H(iKs, iKs) * H(iKs, iKs) + H(iKs + 1, iKs) * H(iKs + 1, iKs));
+        Rcos[iKs - 1] = H(iKs, iKs) / tmp;
+        Rsin[iKs - 1] = H(iKs + 1, iKs) / tmp;
+        H(iKs, iKs) = tmp;
+        H(iKs + 1, iKs) = 0.0;
+        tmp = Rcos[iKs - 1] * eBrg[iKs - 1] + Rsin[iKs - 1] * eBrg[iKs];
+        eBrg[iKs] = -Rsin[iKs - 1] * eBrg[iKs - 1] + Rcos[iKs - 1] * eBrg[iKs];
+        eBrg[iKs - 1] = tmp;
+        *ntotGM += 1;
+        if (fabs(eBrg[iKs]) <= epsnrm) break;
+      }
+      for (int jK = iKs; jK >= 1; jK--) {
+        yBrg[jK - 1] = eBrg[jK - 1] / H(jK, jK);
+        for (int lK = 1; lK <= jK - 1; lK++) eBrg[lK - 1] = eBrg[lK - 1] - yBrg[jK - 1] * H(lK, jK);
+      }
+      PHB_CHECK(cudaMemcpyAsync(ctx->d_dots, yBrg, sizeof(double) * iKs, cudaMemcpyHostToDevice, s));
+      {
+        KScope ks(ctx, KC_BLAS);
+        k_update<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, ctx->d_Dy, U, iKs, ctx->d_dots);
+        PHB_CHECK(cudaGetLastError());
+      }
+      PHB_CHECK(cudaStreamSynchronize(s));  // yBrg is reused by the host next cycle
+      if (fabs(eBrg[iKs]) <= epsnrm) break;
+    }
+  }
+#undef H
+  PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, ctx->d_Dy, 2));  // solgmr.f:347
+  *iKs_out = iKs;
+  *lGMRES_out = lGMRES;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// FP64 FMA peak microbenchmark: 8 independent register chains per thread
+// ---------------------------------------------------------------------------
+__global__ void k_dfma_peak(double *out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+int phb_fp64_peak(phb200_ctx *ctx, double *tflops) {
+  const int blocks = 148 * 8, threads = 256, iters = 20000;
+  if (ctx->scratch_bytes < sizeof(double) * blocks * threads) return 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_dfma_peak<<<blocks, threads, 0, ctx->stream>>>(ctx->d_scratch, 1000, 0.999999, 1e-7);
+  float best = 1e30f;
+  for (int r = 0; r < 3; r++) {
+    cudaEventRecord(e0, ctx->stream);
+    k_dfma_peak<<<blocks, threads, 0, ctx->stream>>>(ctx->d_scratch, iters, 0.999999, 1e-7);
+    cudaEventRecord(e1, ctx->stream);
+    PHB_CHECK(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  ctx->launches += 4;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return 0;
+}

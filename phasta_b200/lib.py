@@ -1,0 +1,77 @@
+"""ctypes binding of libphb200.so (include/phb200.h).
+
+This is the same binding surface the Fortran ISO_C_BINDING shim uses
+(INTEGRATION.md).  The library is CUDA-only: if it is missing or no GPU is
+visible the product path raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+MAXTOP, MAXSH, MAXQPT = 6, 32, 125
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphb200.so")
+
+
+class PhbCommon(C.Structure):
+    """struct phb200_common (include/phb200.h)."""
+    _fields_ = [
+        *[(n, C.c_int) for n in (
+            "nshg", "numnp", "numel", "numelb", "nflow", "ndof", "ndofBC", "nshape", "nedof",
+            "nelblk", "nelblb", "nlwork", "numpe", "myrank",
+            "ipord", "idiff", "itau", "iremoveStabTimeTerm", "EntropyPressure",
+            "iDC", "Navier", "Kspace", "nGMRES", "minIters",
+            "matflg2", "matflg3")],
+        *[(n, C.c_double) for n in (
+            "Rgas", "gamma", "gamma1", "pr", "datmat121", "datmat221", "datmat321", "datmat131",
+            "epsM", "dtsfct", "taucfct", "temper")],
+        ("nint", C.c_int * MAXTOP), ("nintb", C.c_int * MAXTOP),
+        ("Qwt", C.c_double * (MAXTOP * MAXQPT)), ("Qwtb", C.c_double * (MAXTOP * MAXQPT)),
+    ]
+
+
+class PhbStep(C.Structure):
+    """struct phb200_step."""
+    _fields_ = [*[(n, C.c_int) for n in ("lhs", "iprec", "iter", "nitr", "lstep", "pad")],
+                *[(n, C.c_double) for n in ("Dtgl", "almi", "alfi", "gami", "etol")]]
+
+
+# every symbol include/phb200.h declares (tests/test_abi.py checks the .so exports them all)
+SYMBOLS = [
+    "phb200_init", "phb200_finalize", "phb200_nccl_unique_id", "phb200_comm_init",
+    "phb200_solgmre", "phb200_elmgmre", "phb200_i3lu", "phb200_i3pre", "phb200_au1gmr",
+    "phb200_bc3per", "phb200_commu", "phb200_sumgat", "phb200_set_state", "phb200_dev_elmgmre",
+    "phb200_dev_solve", "phb200_dev_ap", "phb200_get_res", "phb200_get_dy", "phb200_get_bdiag",
+    "phb200_get_egmass", "phb200_event_record", "phb200_event_elapsed_ms", "phb200_sync",
+    "phb200_launch_count", "phb200_profile", "phb200_profile_get", "phb200_profile_reset",
+    "phb200_fp64_peak", "phb200_flush_l2", "phb200_version", "phb200_sizeof_common",
+    "phb200_sizeof_step", "phb200_local_group_join",
+]
+
+_LIB = None
+
+
+def build(verbose=False):
+    """Compile libphb200.so in-tree for sm_100a (nvcc cross-compiles on CPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", os.path.join(_HERE, "csrc")], stdout=out)
+    return LIB_PATH
+
+
+def load():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "libphb200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
+                "phasta_b200 has no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        lib.phb200_version.restype = C.c_char_p
+        lib.phb200_launch_count.restype = C.c_longlong
+        lib.phb200_finalize.restype = None
+        if lib.phb200_sizeof_common() != C.sizeof(PhbCommon) or lib.phb200_sizeof_step() != C.sizeof(PhbStep):
+            raise RuntimeError('phb200 struct layout mismatch between include/phb200.h and lib.py')
+        _LIB = lib
+    return _LIB

@@ -1,0 +1,261 @@
+"""Host-side mirror of the reference's solver interface for the hot path.
+
+`PhastaGPU` plays the role of the Fortran caller (itrdrv.f:427-525): it owns
+the mesh part, hands it once to `phb200_init`, and then calls `SolGMRe` /
+`ElmGMRe` / `Au1GMR` / `i3LU` / `commu` / `sumgat` with the reference's
+argument meaning (solgmr.f:1-8, elmgmr.f:1-6, au1gmr.f:1, i3lu.f:1,
+commu.f:1, mpitools.f:107).  All numerics run in libphb200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import lib as _lib
+from .lib import PhbCommon, PhbStep, MAXTOP, MAXQPT
+from .mesh import MeshPart
+from .params import SolverParams
+
+KCLASS = {"assembly": 0, "asiq": 1, "ap": 2, "i3pre": 3, "blas1": 4, "node": 5, "halo": 6}
+
+
+def _p(a, t=C.c_double):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+class PhastaError(RuntimeError):
+    pass
+
+
+def _chk(rc, what):
+    if rc != 0:
+        raise PhastaError("phb200 %s failed (rc=%d); see stderr" % (what, rc))
+
+
+class PhastaGPU:
+    def __init__(self, part: MeshPart, params: SolverParams, tables: dict, device: int = 0):
+        self.L = _lib.load()
+        self.part, self.params, self.tables = part, params, tables
+        nshape = max(int(b.shape[1]) for b in part.mien)
+        self.nedof = 5 * nshape
+        c = PhbCommon()
+        c.nshg, c.numnp, c.numel, c.numelb = part.nshg, part.numnp, part.numel, 0
+        c.nflow, c.ndof, c.ndofBC, c.nshape, c.nedof = 5, 5, 6, nshape, self.nedof
+        c.nelblk, c.nelblb, c.nlwork = part.nelblk, part.nelblb, part.nlwork
+        c.numpe, c.myrank = part.numpe, part.rank
+        for nm in ("ipord", "idiff", "itau", "iremoveStabTimeTerm", "EntropyPressure", "iDC", "Navier",
+                   "Kspace", "nGMRES", "minIters", "matflg2", "matflg3"):
+            setattr(c, nm, int(getattr(params, nm)))
+        for nm in ("Rgas", "gamma", "gamma1", "pr", "datmat121", "datmat221", "datmat321", "datmat131",
+                   "epsM", "dtsfct", "taucfct", "temper"):
+            setattr(c, nm, float(getattr(params, nm)))
+        for i in range(MAXTOP):
+            c.nint[i] = int(tables["nint"][i])
+            c.nintb[i] = int(tables["nintb"][i])
+        q = np.asfortranarray(tables["Qwt"]).ravel(order="F")
+        qb = np.asfortranarray(tables["Qwtb"]).ravel(order="F")
+        C.memmove(c.Qwt, q.ctypes.data, q.nbytes)
+        C.memmove(c.Qwtb, qb.ctypes.data, qb.nbytes)
+        self.common = c
+        k = self._keep = {}
+        k["lcblk"] = np.asfortranarray(part.lcblk, dtype=np.int32)
+        k["mien"] = [np.asfortranarray(b, dtype=np.int32) for b in part.mien]
+        mien_ptrs = (C.POINTER(C.c_int) * len(k["mien"]))(*[_p(b, C.c_int) for b in k["mien"]])
+        k["x"] = np.asfortranarray(part.x, dtype=np.float64)
+        k["iBC"] = np.ascontiguousarray(part.iBC, dtype=np.int32)
+        k["BC"] = np.asfortranarray(part.BC, dtype=np.float64)
+        k["iper"] = np.ascontiguousarray(part.iper, dtype=np.int32)
+        k["ilwork"] = np.ascontiguousarray(part.ilwork, dtype=np.int32)
+        for nm in ("shp", "shgl", "shpb", "shglb"):
+            k[nm] = np.asfortranarray(tables[nm], dtype=np.float64)
+        self.ctx = C.c_void_p()
+        _chk(self.L.phb200_init(C.byref(self.ctx), C.byref(c), _p(k["lcblk"], C.c_int), mien_ptrs,
+                                None, None, None, None, _p(k["x"]), _p(k["iBC"], C.c_int), _p(k["BC"]),
+                                _p(k["iper"], C.c_int), _p(k["ilwork"], C.c_int), _p(k["shp"]), _p(k["shgl"]),
+                                _p(k["shpb"]), _p(k["shglb"]), int(device)), "init")
+        K = params.Kspace
+        self.HBrg = np.zeros((K + 1, K), order="F")
+        self.eBrg = np.zeros(K + 1)
+        self.yBrg = np.zeros(K + 1)
+        self.Rcos = np.zeros(K + 1)
+        self.Rsin = np.zeros(K + 1)
+        self.ntotGM = 0
+        self.iKs = 0
+        self.lGMRES = 0
+
+    # ------------------------------------------------------------------ util
+    def close(self):
+        if self.ctx:
+            self.L.phb200_finalize(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def step(self, **over) -> PhbStep:
+        P = self.params
+        s = PhbStep()
+        s.lhs, s.iprec, s.iter, s.nitr, s.lstep = P.lhs, P.iprec, 1, 1, 0
+        s.Dtgl, s.almi, s.alfi, s.gami, s.etol = P.Dtgl, P.almi, P.alfi, P.gami, P.etol
+        for k, v in over.items():
+            setattr(s, k, v)
+        return s
+
+    def _vec(self, n=5):
+        return np.zeros((self.part.nshg, n), order="F")
+
+    # ------------------------------------------------- reference-named calls
+    def SolGMRe(self, y, ac, yold=None, acold=None, *, step=None, want_bdiag=False):
+        """solgmr.f:1-362.  Returns (res, Dy); res is the preconditioned
+        residual, self.rmes the saved right-hand side (solgmr.f:83)."""
+        st = step or self.step()
+        y = np.asfortranarray(y, dtype=np.float64)
+        ac = np.asfortranarray(ac, dtype=np.float64)
+        res, rmes, Dy = self._vec(), self._vec(), self._vec()
+        BD = np.zeros((self.part.nshg, 5, 5), order="F") if want_bdiag else None
+        iKs, lG, ntot = C.c_int(0), C.c_int(0), C.c_int(self.ntotGM)
+        _chk(self.L.phb200_solgmre(self.ctx, _p(y), _p(ac), C.byref(st), _p(res), _p(rmes), _p(BD), _p(Dy),
+                                   _p(self.HBrg), _p(self.eBrg), _p(self.yBrg), _p(self.Rcos), _p(self.Rsin),
+                                   C.byref(iKs), C.byref(lG), C.byref(ntot)), "solgmre")
+        self.iKs, self.lGMRES, self.ntotGM = iKs.value, lG.value, ntot.value
+        self.rmes, self.BDiag = rmes, BD
+        return res, Dy
+
+    def ElmGMRe(self, y, ac, *, step=None, want_egmass=False, want_qres=False):
+        """elmgmr.f:1-274.  Returns dict(res, BDiag, EGmass?, qres?)."""
+        st = step or self.step()
+        y = np.asfortranarray(y, dtype=np.float64)
+        ac = np.asfortranarray(ac, dtype=np.float64)
+        res = self._vec()
+        BD = np.zeros((self.part.nshg, 5, 5), order="F") if st.iprec else None
+        EG = (np.zeros((self.part.numel, self.nedof, self.nedof), order="F")
+              if (want_egmass and st.lhs == 1) else None)
+        qres = self._vec(12) if want_qres else None
+        _chk(self.L.phb200_elmgmre(self.ctx, _p(y), _p(ac), C.byref(st), _p(res), _p(BD), _p(EG), _p(qres)),
+             "elmgmre")
+        return dict(res=res, BDiag=BD, EGmass=EG, qres=qres)
+
+    def i3LU(self, Diag, r, code):
+        """i3lu.f:1-181; code 'LU_Fact'|'forward'|'backward'|'product'."""
+        ic = {"LU_Fact": 0, "forward": 1, "backward": 2, "product": 3}[code.strip()]
+        _chk(self.L.phb200_i3lu(self.ctx, _p(Diag), _p(r), ic), "i3lu")
+
+    def i3pre(self, want_egmass=False):
+        EG = np.zeros((self.part.numel, self.nedof, self.nedof), order="F") if want_egmass else None
+        _chk(self.L.phb200_i3pre(self.ctx, _p(EG)), "i3pre")
+        return EG
+
+    def Au1GMR(self, uBrg):
+        """au1gmr.f:1-106, in place on uBrg(nshg,5)."""
+        assert uBrg.flags.f_contiguous and uBrg.shape == (self.part.nshg, 5)
+        _chk(self.L.phb200_au1gmr(self.ctx, _p(uBrg)), "au1gmr")
+        return uBrg
+
+    def bc3per(self, r):
+        _chk(self.L.phb200_bc3per(self.ctx, _p(r)), "bc3per")
+        return r
+
+    def commu(self, global_, n, code):
+        """commu.f:1-297; code 'in ' | 'out'."""
+        ic = {"in": 0, "out": 1}[code.strip()]
+        _chk(self.L.phb200_commu(self.ctx, _p(global_), int(n), ic), "commu")
+        return global_
+
+    def sumgat(self, u, n):
+        out = C.c_double(0.0)
+        _chk(self.L.phb200_sumgat(self.ctx, _p(np.asfortranarray(u)), int(n), C.byref(out)), "sumgat")
+        return out.value
+
+    # --------------------------------------------------- HBM-resident path
+    def set_state(self, y, ac):
+        self._y = np.asfortranarray(y, dtype=np.float64)
+        self._ac = np.asfortranarray(ac, dtype=np.float64)
+        _chk(self.L.phb200_set_state(self.ctx, _p(self._y), _p(self._ac)), "set_state")
+
+    def dev_elmgmre(self, step=None):
+        st = step or self.step()
+        _chk(self.L.phb200_dev_elmgmre(self.ctx, C.byref(st)), "dev_elmgmre")
+
+    def dev_solve(self, step=None):
+        st = step or self.step()
+        iKs, lG, ntot = C.c_int(0), C.c_int(0), C.c_int(self.ntotGM)
+        _chk(self.L.phb200_dev_solve(self.ctx, C.byref(st), C.byref(iKs), C.byref(lG), C.byref(ntot)), "dev_solve")
+        self.iKs, self.lGMRES, self.ntotGM = iKs.value, lG.value, ntot.value
+        return self.iKs
+
+    def dev_ap(self, slot=0):
+        _chk(self.L.phb200_dev_ap(self.ctx, int(slot)), "dev_ap")
+
+    def get(self, what):
+        nshg = self.part.nshg
+        if what == "res":
+            a = self._vec()
+            _chk(self.L.phb200_get_res(self.ctx, _p(a)), "get_res")
+        elif what == "Dy":
+            a = self._vec()
+            _chk(self.L.phb200_get_dy(self.ctx, _p(a)), "get_dy")
+        elif what == "BDiag":
+            a = np.zeros((nshg, 5, 5), order="F")
+            _chk(self.L.phb200_get_bdiag(self.ctx, _p(a)), "get_bdiag")
+        elif what == "EGmass":
+            a = np.zeros((self.part.numel, self.nedof, self.nedof), order="F")
+            _chk(self.L.phb200_get_egmass(self.ctx, _p(a)), "get_egmass")
+        else:
+            raise KeyError(what)
+        return a
+
+    # ------------------------------------------------------ instrumentation
+    def sync(self):
+        _chk(self.L.phb200_sync(self.ctx), "sync")
+
+    def event(self, slot):
+        _chk(self.L.phb200_event_record(self.ctx, slot), "event_record")
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_float(0)
+        _chk(self.L.phb200_event_elapsed_ms(self.ctx, a, b, C.byref(ms)), "event_elapsed")
+        return ms.value
+
+    def launches(self):
+        return int(self.L.phb200_launch_count(self.ctx))
+
+    def profile(self, on):
+        _chk(self.L.phb200_profile(self.ctx, int(on)), "profile")
+
+    def profile_get(self):
+        out = {}
+        for name, k in KCLASS.items():
+            ms, n = C.c_float(0), C.c_longlong(0)
+            self.L.phb200_profile_get(self.ctx, k, C.byref(ms), C.byref(n))
+            out[name] = (ms.value, n.value)
+        return out
+
+    def profile_reset(self):
+        self.L.phb200_profile_reset(self.ctx)
+
+    def fp64_peak(self):
+        t = C.c_double(0)
+        _chk(self.L.phb200_fp64_peak(self.ctx, C.byref(t)), "fp64_peak")
+        return t.value
+
+    def flush_l2(self):
+        _chk(self.L.phb200_flush_l2(self.ctx), "flush_l2")
+
+    # multi-GPU
+    def comm_init(self, id128: bytes):
+        buf = C.create_string_buffer(id128, 128)
+        _chk(self.L.phb200_comm_init(self.ctx, buf), "comm_init")
+
+    def local_group_join(self, nranks):
+        _chk(self.L.phb200_local_group_join(self.ctx, int(nranks)), "local_group_join")
+
+
+def nccl_unique_id() -> bytes:
+    L = _lib.load()
+    buf = C.create_string_buffer(128)
+    _chk(L.phb200_nccl_unique_id(buf), "nccl_unique_id")
+    return buf.raw
