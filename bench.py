@@ -1,0 +1,386 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on B200: FP64 elements assembled / s
+(ElmGMRe, lhs=1) with GMRES Ap / s and the full implicit solve beside it.
+
+  python bench.py --gpus N --steps K --warmup W            (our arm)
+  python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
+
+A "step" is one ElmGMRe pass (AsIq + qpbc + AsIGMR/e3/bc3LHS + halo + bc3Res/
+bc3BDg, lhs=1, iprec=1) over the whole synthetic mesh, state resident in HBM.
+At N=1 the workload is BASELINE.json configs[1]: compressible channel,
+128x64x82 hexes x 6 = 4 030 464 linear tets; at N>1 each GPU
+gets a slab of the same per-GPU size (weak scaling, ilwork halo over NCCL).
+The same JSON line carries Ap/s (EBE Au1GMR + bc3per) and the whole SolGMRe
+(assembly + BDiag-preconditioned GMRES), the roofline of the dominant kernel,
+the end-to-end number through the C-ABI with host buffers, and the CPU
+baseline (oracle port, -O3 -march=native, one replica per host core).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_ELEM_LHS = 52000.0     # hand count, 4-pt rule, lhs=1, incl. AsIq
+BYTES_PER_ELEM_LHS = 3310.0     # EGmass 3200 + ien 16 + node data/6
+BYTES_PER_ELEM_AP = 3215.0      # EBE Ap
+FP64_NOMINAL_TF = 40.0          # BASELINE.json north_star
+
+WORKLOADS = {
+    # name: (nx_per_gpu, ny, nz)
+    "c2_channel_4M": (128, 64, 82),
+    "c1_cube_50k": (20, 20, 21),
+    "small": (32, 24, 24),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_evt = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_evt.wait(0.2)
+
+    def summary(self):
+        self.stop_evt.set()
+        self.join(timeout=3)
+        sm, smax, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                smax = max(smax, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_part(workload, rank, world):
+    from phasta_b200 import make_box, make_state, global_node_count
+    nxg, ny, nz = WORKLOADS[workload]
+    nx = nxg * world
+    L = (1.0 * world, 0.5, 0.64)
+    parts = make_box(nx, ny, nz, L=L, nparts=world, bc="channel", periodic_z=True, ibksiz=1024,
+                     only_rank=rank)
+    part = parts[0]
+    y, ac = make_state(part, global_node_count(nx, ny, nz))
+    return part, y, ac
+
+
+def cpu_baseline(workload_name, cores, seconds_target=12.0):
+    """Oracle port (-O3 -march=native), one independent replica per host core
+    (the reference is flat MPI, one rank per core)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from phasta_b200 import SolverParams, make_box, make_state, make_tables, global_node_count
+    from oracle import oracle_py
+    oracle_py.use_fast_build(True)
+    params = SolverParams(ibksiz=1024)
+    tables = make_tables(2, 2)
+    nx, ny, nz = 16, 16, 16     # 24 576 tets per replica per pass
+    objs = []
+    for r in range(cores):
+        parts = make_box(nx, ny, nz, bc="channel", periodic_z=True, ibksiz=1024, seed=1234 + r)
+        st = make_state(parts[0], global_node_count(nx, ny, nz), seed=1234 + r)
+        objs.append(oracle_py.Oracle(parts, params, tables, [st]))
+    numel = objs[0].parts[0].mp.numel
+
+    def run(o, reps):
+        for _ in range(reps):
+            o.ElmGMRe()
+
+    run(objs[0], 1)
+    t0 = time.perf_counter()
+    run(objs[0], 1)
+    t1 = time.perf_counter() - t0
+    reps = max(1, int(seconds_target / max(t1, 1e-3)))
+    with ThreadPoolExecutor(cores) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(lambda o: run(o, reps), objs))
+        dt = time.perf_counter() - t0
+    asm = cores * reps * numel / dt
+    # Ap on the same replicas
+    for o in objs:
+        o.i3LU(0)
+        o.i3LU(1)
+    objs[0].i3pre()
+    vec = [np.asfortranarray(np.random.default_rng(0).standard_normal((objs[0].parts[0].mp.nshg, 5)))]
+    t0 = time.perf_counter()
+    nap = 20
+    for _ in range(nap):
+        objs[0].Au1GMR(vec)
+    ap_elem_s_1core = nap * numel / (time.perf_counter() - t0)
+    return {"value": asm, "unit": "elements/s", "cores": cores, "kind": "port",
+            "sample": "%d replicas x %d passes of ElmGMRe(lhs=1) on a %dx%dx%dx6=%d-tet channel box "
+                      "(oracle/ C port of the reference, gcc -O3 -march=native; no Fortran toolchain on the box)"
+                      % (cores, reps, nx, ny, nz, numel),
+            "ap_elements_per_s_1core": ap_elem_s_1core}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    vals = []
+    cb = None
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(args.workload, cores, seconds_target=max(2.0, 40.0 / max(1, args.warmup + args.steps)))
+        if i >= args.warmup:
+            vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = v
+    nxg, ny, nz = WORKLOADS[args.workload]
+    numel = nxg * ny * nz * 6 * args.gpus
+    line = {"impl": "reference", "metric": "fp64_elements_assembled_per_s", "value": v, "unit": "elements/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * numel / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "elements": numel,
+                       "note": "CPU arm: bounded sample per step, ms_per_step extrapolated to the full mesh"},
+            "cpu_baseline": cb,
+            "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_channel_4M", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-solve", action="store_true", help="skip the Ap / SolGMRe legs (profiling runs)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        print("bench.py: WORLD_SIZE=%d but --gpus %d" % (world, args.gpus), file=sys.stderr)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; phasta_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from phasta_b200 import SolverParams, make_tables
+    from phasta_b200.solver import PhastaGPU, nccl_unique_id
+
+    params = SolverParams(ibksiz=1024, etol=1e-3, Kspace=50)
+    tables = make_tables(2, 2)
+    part, y, ac = build_part(args.workload, rank, world)
+    g = PhastaGPU(part, params, tables, device=local_rank)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(idt, 0)
+        g.comm_init(bytes(idt.cpu().tolist()))
+
+    def barrier():
+        g.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxrank(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    numel_total = part.numel * world
+    st = g.step()
+    g.set_state(y, ac)
+    fp64_peak = g.fp64_peak() if rank == 0 else 0.0
+
+    # ------------------------------------------------ timed: K assemblies
+    for _ in range(args.warmup):
+        g.dev_elmgmre(st)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = g.launches()
+    g.profile_reset()
+    g.event(0)
+    for _ in range(args.steps):
+        g.dev_elmgmre(st)
+    g.event(1)
+    barrier()
+    asm_ms = maxrank(g.elapsed_ms(0, 1)) / args.steps
+    launches = g.launches() - l0
+    clocks = sampler.summary() if rank == 0 else {}
+    value = numel_total / (asm_ms * 1e-3)
+
+    # per-kernel-class share (events around every launch; separate pass)
+    g.profile(True)
+    g.profile_reset()
+    for _ in range(2):
+        g.dev_elmgmre(st)
+    prof = g.profile_get()
+    g.profile(False)
+    kern_ms = prof["assembly"][0] / max(1, prof["assembly"][1])
+    asiq_ms = prof["asiq"][0] / max(1, prof["asiq"][1])
+
+    # residual-only assembly (lhs=0)
+    st0 = g.step(lhs=0, iprec=0)
+    for _ in range(2):
+        g.dev_elmgmre(st0)
+    barrier()
+    g.event(2)
+    for _ in range(args.steps):
+        g.dev_elmgmre(st0)
+    g.event(3)
+    barrier()
+    res_ms = maxrank(g.elapsed_ms(2, 3)) / args.steps
+    g.dev_elmgmre(st)   # restore the LHS
+
+    extra = {}
+    if not args.no_solve:
+        # ------------------------------------------------ full SolGMRe, then Ap/s on its basis
+        g.dev_elmgmre(st)
+        g.dev_solve(st)
+        barrier()
+        solve_ms = []
+        its = []
+        for _ in range(3):
+            g.dev_elmgmre(st)
+            barrier()
+            g.event(4)
+            its.append(g.dev_solve(st))
+            g.event(5)
+            barrier()
+            solve_ms.append(maxrank(g.elapsed_ms(4, 5)))
+        nap = max(20, args.steps)
+        for _ in range(3):
+            g.dev_ap(0)
+        barrier()
+        g.event(6)
+        for i in range(nap):
+            g.dev_ap(i % 8)
+        g.event(7)
+        barrier()
+        ap_ms = maxrank(g.elapsed_ms(6, 7)) / nap
+        g.profile(True)
+        g.profile_reset()
+        for i in range(4):
+            g.dev_ap(i)
+        ap_k_ms = g.profile_get()["ap"][0] / 4
+        g.profile(False)
+        extra = {
+            "ap": {"value": 1e3 / ap_ms, "unit": "Ap/s", "ms_per_ap": ap_ms, "kernel_ms": ap_k_ms,
+                   "elements_per_s": numel_total / (ap_ms * 1e-3)},
+            "solgmre": {"solve_ms": float(np.mean(solve_ms)), "gmres_iterations": int(its[-1]),
+                        "implicit_solve_ms": float(np.mean(solve_ms)) + asm_ms,
+                        "krylov_its_per_s": its[-1] / (np.mean(solve_ms) * 1e-3), "etol": params.etol},
+        }
+
+    # ------------------------------------------------ e2e through the C-ABI with host buffers
+    import ctypes as C
+    yp = torch.from_numpy(np.ascontiguousarray(y.T)).pin_memory()      # (5,nshg) C == (nshg,5) F
+    acp = torch.from_numpy(np.ascontiguousarray(ac.T)).pin_memory()
+    resp = torch.empty_like(yp).pin_memory()
+    yv, acv, resv = (t.numpy().T for t in (yp, acp, resp))
+    from phasta_b200.solver import _p, _chk
+    for _ in range(2):
+        _chk(g.L.phb200_elmgmre(g.ctx, _p(yv), _p(acv), C.byref(st), _p(resv), None, None, None), "elmgmre")
+    barrier()
+    t0 = time.perf_counter()
+    g.event(8)
+    ne2e = max(3, args.steps // 2)
+    for _ in range(ne2e):
+        _chk(g.L.phb200_elmgmre(g.ctx, _p(yv), _p(acv), C.byref(st), _p(resv), None, None, None), "elmgmre")
+    g.event(9)
+    barrier()
+    e2e_ms = maxrank(g.elapsed_ms(8, 9)) / ne2e
+    e2e = {"value": numel_total / (e2e_ms * 1e-3), "unit": "elements/s",
+           "h2d_bytes_per_step": int(2 * y.nbytes), "d2h_bytes_per_step": int(y.nbytes), "ms_per_step": e2e_ms,
+           "api": "phb200_elmgmre (host y, ac in; host res out; EGmass/BDiag stay in HBM)"}
+
+    if rank == 0:
+        hbm, src = peaks()
+        elem_per_launch = part.numel
+        tf = elem_per_launch * FLOP_PER_ELEM_LHS / (kern_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "k_asigmr_tet<32,4,true>",
+                "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
+                "traffic": None, "peak_source": "FP64 DFMA-chain microbenchmark run in this process "
+                                                "(MEASURED_PEAKS.json has no FP64 entry); nominal %.0f TF" % FP64_NOMINAL_TF,
+                "frac_of_nominal": tf / FP64_NOMINAL_TF,
+                "flop_per_element": FLOP_PER_ELEM_LHS, "kernel_ms": kern_ms, "asiq_kernel_ms": asiq_ms,
+                "hbm_GBps_algorithmic": elem_per_launch * BYTES_PER_ELEM_LHS / (kern_ms * 1e-3) / 1e9,
+                "hbm_peak_GBps": hbm, "hbm_peak_source": src}
+        if extra:
+            gbs = elem_per_launch * BYTES_PER_ELEM_AP / (extra["ap"]["kernel_ms"] * 1e-3) / 1e9
+            extra["roofline_ap"] = {"bound": "hbm", "kernel": "k_ap_ebe_tet", "achieved": gbs, "peak": hbm,
+                                    "unit": "GB/s", "frac": gbs / hbm, "traffic": None, "peak_source": src}
+        cb = None
+        if not args.no_cpu:
+            cb = cpu_baseline(args.workload, os.cpu_count() or 1)
+        line = {"metric": "fp64_elements_assembled_per_s", "value": value, "unit": "elements/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": asm_ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "elements": numel_total, "nodes_per_gpu": part.nshg,
+                           "elements_per_gpu": part.numel, "quadrature": "4-pt tets", "lhs": 1, "idiff": 1,
+                           "l2": "inputs larger than L2 (EGmass %.1f GB per GPU)" % (part.numel * 3200 / 1e9),
+                           "partition": "x-slabs, ilwork halo over NCCL" if world > 1 else "single part"},
+                "residual_only": {"value": numel_total / (res_ms * 1e-3), "unit": "elements/s", "ms": res_ms},
+                "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": clocks, "kernel_class_ms": {k: v[0] / 2 for k, v in prof.items()}}
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -720,9 +720,20 @@ void orc_asigmr(const orc_part *p, int iblk, const double *qres, double *res,
       for (int k = 1; k <= idflx; k++)
         ql[n][k] = qres[A + (size_t)nshg * (k - 1)];
     }
-    double *EG = EGmass ? EGmass + (size_t)(iel - 1 + e) : NULL;
-    e3_element(p, lcsyst, nshl, nenl, ngauss, ycl, acl, xl, ql, rl[e], EG,
-               numel, nedof);
+    /* the reference passes the strided section EGmass(iel:inum,:,:)
+     * (elmgmr.f:160); gfortran packs it into a contiguous temporary.  Here the
+     * element's nedof x nedof slab is accumulated contiguously and copied out. */
+    double EGl[900]; /* nedof <= 30 (wedges) */
+    if (EGmass) {
+      if (nedof * nedof > 900) { fprintf(stderr, "orc_asigmr: nedof>30\n"); abort(); }
+      memset(EGl, 0, sizeof(double) * (size_t)nedof * nedof);
+    }
+    e3_element(p, lcsyst, nshl, nenl, ngauss, ycl, acl, xl, ql, rl[e],
+               EGmass ? EGl : NULL, 1, nedof);
+    if (EGmass) {
+      double *EG = EGmass + (size_t)(iel - 1 + e);
+      for (int k = 0; k < nedof * nedof; k++) EG[numel * (size_t)k] += EGl[k];
+    }
   }
   /* local(res, rl, 'scatter') (common/local.f:67-74): dof, node, element */
   for (int j = 1; j <= 5; j++)

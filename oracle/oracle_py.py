@@ -53,10 +53,29 @@ def build(force=False):
     return so
 
 
+_FAST = False
+
+
+def use_fast_build(on=True):
+    """bench.py's CPU baseline: load the -O3 -march=native build instead."""
+    global _FAST, _LIB
+    _FAST, _LIB = bool(on), None
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
+        so = build()
+        if _FAST:
+            fast = os.path.join(_HERE, "libphasta_oracle_fast.so")
+            try:
+                subprocess.check_call(["make", "-B", "-C", _HERE, "libphasta_oracle_fast.so"],
+                                      stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            except Exception:
+                pass
+            if os.path.exists(fast):
+                so = fast
+        _LIB = C.CDLL(so)
         assert _LIB.orc_sizeof_part() == C.sizeof(OrcPart), "orc_part layout mismatch"
         assert _LIB.orc_sizeof_common() == C.sizeof(OrcCommon)
         _LIB.orc_sumgat.restype = C.c_double

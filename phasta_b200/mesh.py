@@ -103,7 +103,7 @@ def _blocks(numel, ibksiz, lcsyst=1, ipord=1, nenl=4, nshl=4, nfacel=4):
 
 
 def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15,
-             bc="channel", periodic_z=True, seed=1234, max_seg=0):
+             bc="channel", periodic_z=True, seed=1234, max_seg=0, only_rank=None):
     """Build `nparts` MeshPart objects for an nx*ny*nz-hex box (6 tets/hex).
 
     bc: "channel"  x-min inflow (velocity code 7 + T), x-max pressure,
@@ -112,6 +112,7 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
         "mixed"    channel + a few nodes with every velocity code 1..6 and
                    density BC, random slopes (exercises bc3* branches)
     max_seg: if >0 split ilwork segments to at most this length.
+    only_rank: build (and return a 1-list with) just that rank's part.
     """
     assert nx % nparts == 0 or nparts == 1, "nx must be divisible by nparts"
     rng = np.random.default_rng(seed)
@@ -125,6 +126,8 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
     # global iBC/BC pattern as functions of (i,j,k) so parts agree
     nxs = nx // nparts
     for p in range(nparts):
+        if only_rank is not None and p != only_rank:
+            continue
         i0, i1 = p * nxs, (p + 1) * nxs
         nxl = i1 - i0
 
