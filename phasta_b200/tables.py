@@ -28,7 +28,7 @@ def tet_points(rule):
 def tri_points(rule):
     """symtri 1/3-pt rules (phSolver/common/symtri.c)."""
     if rule == 1:
-        return np.array([[1 / 3, 1 / 3, 1 / 3, 0.0]]), np.array([1.0])
+        return np.array([[0.333333333333333, 0.333333333333333, 0.333333333333333, 0.0]]), np.array([1.0])
     if rule == 2:
         a, b = 0.666666666666667, 0.166666666666667
         pts = np.array([[a, b, b, 0.0], [b, a, b, 0.0], [b, b, a, 0.0]])

@@ -1,0 +1,172 @@
+"""Oracle acceptance (SURVEY.md 8(c) self-checks): the reference ships no
+golden vectors for this path, so the restatement is pinned by internal
+consistency: patch test, LHS = d(RHS)/dY at a uniform state, EBE Ap = dense
+assembled Ap, i3LU vs LAPACK, P-way partition = serial, GMRES reduces the
+true residual."""
+import numpy as np
+import pytest
+
+from common import make_case, make_oracle, rel_l2
+from phasta_b200 import make_box, make_tables, SolverParams
+from oracle.oracle_py import Oracle
+
+
+def uniform_state(mp):
+    y = np.zeros((mp.nshg, 5), order="F")
+    y[:, 0], y[:, 1], y[:, 2], y[:, 3], y[:, 4] = 30.0, 3.0, 1.5, 1.0e5, 300.0
+    return y, np.zeros_like(y)
+
+
+def interior_mask(mp, L=(1.0, 0.5, 0.5)):
+    m = np.ones(mp.nshg, bool)
+    for d, Ld in enumerate(L):
+        m &= (mp.x[:, d] > 1e-9) & (mp.x[:, d] < Ld - 1e-9)
+    return m
+
+
+@pytest.mark.parametrize("rule", [1, 2])
+def test_patch_test_uniform_state_has_zero_interior_residual(rule):
+    parts = make_box(6, 5, 4, bc="none", periodic_z=False)
+    y, ac = uniform_state(parts[0])
+    o = Oracle(parts, SolverParams(intg=rule), make_tables(rule, 2), [(y, ac)])
+    o.ElmGMRe()
+    res = o.parts[0].res
+    m = interior_mask(parts[0])
+    assert np.abs(res[m]).max() < 1e-12 * np.abs(res[~m]).max()
+
+
+def test_lhs_is_the_derivative_of_the_rhs_at_a_uniform_state():
+    P = SolverParams(idiff=0)
+    T = make_tables(2, 2)
+    parts = make_box(5, 4, 4, bc="none", periodic_z=False)
+    mp = parts[0]
+    y, ac = uniform_state(mp)
+    d = np.random.default_rng(0).uniform(-1, 1, size=y.shape) * np.array([1, 1, 1, 100.0, 1.0])
+    eps = 1e-4
+    c = P.almi / (P.gami * P.alfi) * P.Dtgl
+    o0 = Oracle(parts, P, T, [(y, ac)])
+    o0.ElmGMRe()
+    o1 = Oracle(parts, P, T, [(y + eps * d, ac + c * eps * d)])
+    o1.set_flags(lhs=0, iprec=0)
+    o1.ElmGMRe()
+    fd = (o1.parts[0].res - o0.parts[0].res) / eps
+    dl = np.asfortranarray(np.stack([d[:, 3], d[:, 0], d[:, 1], d[:, 2], d[:, 4]], axis=1))
+    o0.Au1GMR([dl])
+    m = interior_mask(mp)
+    for k in range(5):
+        assert rel_l2(dl[m, k], fd[m, k]) < 5e-6
+
+
+def test_ebe_ap_equals_dense_assembled_ap():
+    case = make_case(4, 3, 3, bc="channel")
+    o = make_oracle(case)
+    o.ElmGMRe()
+    op = o.parts[0]
+    mp = case[2][0]
+    n = mp.nshg
+    A = np.zeros((5 * n, 5 * n))
+    ien = mp.ien_all() - 1
+    for e in range(mp.numel):
+        dofs = (ien[e][:, None] * 5 + np.arange(5)[None, :]).ravel()
+        A[np.ix_(dofs, dofs)] += op.EGmass[e]
+    rng = np.random.default_rng(1)
+    u = rng.standard_normal((n, 5))
+    u = u[mp.iper - 1]                      # periodic slaves see the master value
+    v = np.asfortranarray(u.copy())
+    o.Au1GMR([v])
+    ref = (A @ u.ravel()).reshape(n, 5)
+    assert rel_l2(v, ref) < 1e-13
+
+
+def test_i3lu_is_the_reference_factorisation():
+    """i3LU (i3lu.f:41-97) never reduces Diag(4,5) (there is no update between
+    the (4,4) and (5,4) statements), so L*U reproduces BDiag everywhere except
+    entries (4,5) and (5,5).  The restatement must keep that, and forward/
+    backward/product must be exact triangular solves with those factors."""
+    case = make_case(6, 5, 4, bc="channel")
+    o = make_oracle(case)
+    o.ElmGMRe()
+    op = o.parts[0]
+    B0 = op.BDiag.copy()
+    o.i3LU(0)
+    F = op.BDiag
+    n = B0.shape[0]
+    eye = np.eye(5)[None]
+    Lm = np.tril(F, -1) + eye
+    Um = np.triu(F, 1) + eye / np.diagonal(F, axis1=1, axis2=2)[:, :, None]
+    err = np.abs(Lm @ Um - B0) / np.abs(B0).max(axis=(1, 2))[:, None, None]
+    mask = np.ones((5, 5), bool)
+    mask[3, 4] = mask[4, 4] = False
+    assert err[:, mask].max() < 1e-12
+    assert np.array_equal(F[:, 3, 4], B0[:, 3, 4])          # Diag(4,5) untouched
+    r = np.asfortranarray(np.random.default_rng(2).standard_normal((n, 5)))
+    x = r.copy(order="F")
+    o.i3LU(1, [x])
+    fwd = np.linalg.solve(Lm, r[:, :, None])[:, :, 0]
+    assert rel_l2(x, fwd) < 1e-9
+    o.i3LU(2, [x])
+    bwd = np.linalg.solve(Um, fwd[:, :, None])[:, :, 0]
+    assert rel_l2(x, bwd) < 1e-9
+    z = x.copy(order="F")
+    o.i3LU(3, [z])                                            # 'product' U.r
+    assert rel_l2(z, np.einsum("nij,nj->ni", Um, x)) < 1e-9
+
+
+@pytest.mark.parametrize("nparts,max_seg", [(2, 0), (4, 7)])
+def test_partitioned_equals_serial(nparts, max_seg):
+    kw = dict(bc="channel", etol=1e-8, Kspace=30)
+    ser = make_case(8, 4, 3, **kw)
+    par = make_case(8, 4, 3, nparts=nparts, max_seg=max_seg, **kw)
+    os_, op_ = make_oracle(ser), make_oracle(par)
+    iks_s, _ = os_.SolGMRe()
+    iks_p, _ = op_.SolGMRe()
+    assert iks_s == iks_p
+    gs = ser[2][0].gnode
+    for name, tol in (("rmes", 1e-12), ("Dy", 1e-9)):
+        glob = np.zeros((gs.max() + 1, 5))
+        glob[gs] = getattr(os_.parts[0], name)
+        for pp, mp in zip(op_.parts, par[2]):
+            own = np.ones(mp.nshg, bool)            # skip rows owned by another part (zeroed there)
+            il = mp.ilwork
+            itk = 1
+            for _ in range(il[0]):
+                if il[itk + 1] == 0:
+                    for s in range(il[itk + 3]):
+                        b, ln = il[itk + 4 + 2 * s], il[itk + 5 + 2 * s]
+                        own[b - 1:b - 1 + ln] = False
+                itk += 4 + 2 * il[itk + 3]
+            if name == "rmes":
+                assert rel_l2(getattr(pp, name)[own], glob[mp.gnode[own]]) < tol
+            else:
+                # Dy on slave rows is U^-1 of a zero row with identity LU = 0; compare owned rows
+                assert rel_l2(getattr(pp, name)[own], glob[mp.gnode[own]]) < tol
+
+
+def test_solgmre_reduces_the_true_residual():
+    case = make_case(6, 5, 4, bc="channel", etol=1e-6, Kspace=50)
+    o = make_oracle(case)
+    iKs, _ = o.SolGMRe()
+    op = o.parts[0]
+    assert 0 < iKs <= 50
+    # preconditioned system: Atilde ytilde = rtilde, Dy = U^-1 ytilde; check ||r - A U Dy|| <= etol ||r||
+    yt = op.Dy.copy(order="F")
+    o.i3LU(3, [yt])                 # ytilde = U Dy
+    o.Au1GMR([yt])
+    o.bc3per([yt])
+    assert np.linalg.norm(op.res - yt) <= 1.01e-6 * np.linalg.norm(op.res)
+
+
+def test_commu_in_then_out_roundtrip():
+    case = make_case(6, 3, 3, nparts=3, bc="none", periodic_z=False, max_seg=5)
+    o = make_oracle(case)
+    rng = np.random.default_rng(5)
+    vecs = [np.asfortranarray(rng.standard_normal((mp.nshg, 3))) for mp in case[2]]
+    before = [v.copy() for v in vecs]
+    o.commu(vecs, 3, "in")
+    o.commu(vecs, 3, "out")
+    # after in+out every copy of a shared node holds the sum of all copies
+    glob = np.zeros((max(mp.gnode.max() for mp in case[2]) + 1, 3))
+    for mp, b in zip(case[2], before):
+        np.add.at(glob, mp.gnode, b)
+    for mp, v in zip(case[2], vecs):
+        assert rel_l2(v, glob[mp.gnode]) < 1e-14

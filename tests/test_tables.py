@@ -1,0 +1,62 @@
+"""Quadrature / shape tables: bit-exact against the reference's own C
+generators (golden fixture made by tests/golden/make_golden.py; and live
+against oracle/_ref when it was built in this container)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from phasta_b200.tables import make_tables, tet_points, tri_points, MAXTOP, MAXSH, MAXQPT
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = np.load(os.path.join(HERE, "golden", "tables_ref.npz"))
+
+
+@pytest.mark.parametrize("rule,n", [(1, 1), (2, 4)])
+def test_tet_rule_bit_exact(rule, n):
+    pts, w = tet_points(rule)
+    assert np.array_equal(pts, GOLD["tet%d_pt" % n])
+    assert np.array_equal(w, GOLD["tet%d_wt" % n])
+    T = make_tables(rule, 2)
+    assert T["nint"][0] == n
+    # genint.f:74 Qwt*4/3 ; genshp.f:34-37 shgl/2
+    assert np.array_equal(T["Qwt"][0, :n], (4.0 / 3.0) * GOLD["tet%d_wt" % n])
+    assert np.array_equal(T["shp"][0, :4, :n], GOLD["tet%d_N" % n].T)
+    for i in range(n):
+        assert np.array_equal(T["shgl"][0, :, :4, i], GOLD["tet%d_dN" % n][i].T / 2.0)
+    assert T["shp"].shape == (MAXTOP, MAXSH, MAXQPT) and T["shgl"].shape == (MAXTOP, 3, MAXSH, MAXQPT)
+
+
+@pytest.mark.parametrize("rule,n", [(1, 1), (2, 3)])
+def test_tri_rule_bit_exact(rule, n):
+    pts, w = tri_points(rule)
+    assert np.array_equal(pts, GOLD["tri%d_pt" % n])
+    assert np.array_equal(w, GOLD["tri%d_wt" % n])
+
+
+def test_oracle_tables_match_python_tables():
+    from oracle.oracle_py import lib
+    L = lib()
+    for rule in (1, 2):
+        T = make_tables(rule, 2)
+        nint = (C.c_int * MAXTOP)()
+        Qwt = np.zeros((MAXTOP, MAXQPT), order="F")
+        shp = np.zeros((MAXTOP, MAXSH, MAXQPT), order="F")
+        shgl = np.zeros((MAXTOP, 3, MAXSH, MAXQPT), order="F")
+        L.orc_tet_tables(rule, nint, Qwt.ctypes.data_as(C.c_void_p), shp.ctypes.data_as(C.c_void_p),
+                         shgl.ctypes.data_as(C.c_void_p))
+        assert nint[0] == T["nint"][0]
+        assert np.array_equal(Qwt, T["Qwt"]) and np.array_equal(shp, T["shp"]) and np.array_equal(shgl, T["shgl"])
+
+
+def test_live_reference_generators_if_present():
+    so = os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libref_tables.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref not built here (reference sources absent)")
+    L = C.CDLL(so)
+    pt = np.zeros((4, 4))
+    wt = np.zeros(4)
+    err = C.c_int(0)
+    L.symtet_(C.byref(C.c_int(4)), pt.ctypes.data_as(C.c_void_p), wt.ctypes.data_as(C.c_void_p), C.byref(err))
+    assert np.array_equal(pt, GOLD["tet4_pt"]) and np.array_equal(wt, GOLD["tet4_wt"])
