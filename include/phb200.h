@@ -109,6 +109,14 @@ int phb200_commu(phb200_ctx *ctx, double *global, int n, int code);
 /* sumgat (mpitools.f:98-137) */
 int phb200_sumgat(phb200_ctx *ctx, const double *u, int n, double *summed);
 
+/* COMMON /aerfrc/ (common.h:106) integrated by the boundary elements
+ * (e3b.f:305-345): Force(3) and HFlux accumulate over calls made with
+ * step.iter==step.nitr (zero=1 resets them, as itrdrv.f:437-442 does each
+ * step); flxID(10,0:MAXSURF) holds the last ElmGMRe's per-surface fluxes.
+ * Any pointer may be null. */
+int phb200_get_aerfrc(phb200_ctx *ctx, double *Force, double *HFlux,
+                      double *flxID, int zero);
+
 /* HBM-resident path (what bench.py's `value` times: inputs already on the
  * device).  set_state uploads y/ac once; the dev_* calls run on them. */
 int phb200_set_state(phb200_ctx *ctx, const double *y, const double *ac);

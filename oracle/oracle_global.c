@@ -550,6 +550,7 @@ void orc_elmgmre(int nparts, orc_part *parts) {
                  c->lhs == 1 ? p->EGmass : NULL);
       if (c->lhs == 1) orc_bc3lhs_block(p, iblk, p->EGmass);
     }
+    if (p->aerfrc) memset(p->aerfrc + 4, 0, sizeof(double) * 10 * 1001); /* flxID = zero (elmgmr.f:122) */
     for (int iblk = 0; iblk < c->nelblb; iblk++) orc_asbmfg(p, iblk, p->res);
   }
   if (nparts > 1) {

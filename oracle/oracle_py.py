@@ -35,7 +35,7 @@ class OrcCommon(C.Structure):
 _PTRS = ["lcblk", "ien", "ien_off", "lcblkb", "ienb", "ienb_off", "iBCB", "iBCB_off", "BCB",
          "BCB_off", "x", "iBC", "BC", "iper", "ilwork", "shp", "shgl", "shpb", "shglb",
          "y", "ac", "res", "rmes", "BDiag", "EGmass", "qres", "rmass", "Dy", "uBrg", "temp",
-         "lhsK", "colm", "rowp"]
+         "lhsK", "colm", "rowp", "aerfrc"]
 
 
 class OrcPart(C.Structure):
@@ -128,11 +128,13 @@ class OraclePart:
         self.Dy = k["Dy"] = np.zeros((nshg, 5), order="F")
         self.uBrg = k["uBrg"] = np.zeros((nshg, 5, K + 1), order="F")
         k["temp"] = np.zeros((nshg, 5), order="F")
+        self.aerfrc = k["aerfrc"] = np.zeros(4 + 10 * 1001)
 
     def fill(self, s: OrcPart):
         mp, P, T = self.mp, self.params, self.tables
         c = s.c
-        c.nshg, c.numnp, c.numel, c.numelb = mp.nshg, mp.numnp, mp.numel, 0
+        c.nshg, c.numnp, c.numel = mp.nshg, mp.numnp, mp.numel
+        c.numelb = int(sum(b.shape[0] for b in mp.mienb)) if mp.nelblb else 0
         c.nflow, c.ndof, c.ndofBC = 5, 5, 6
         c.nshape, c.nedof = self.nedof // 5, self.nedof
         c.nelblk, c.nelblb, c.nlwork = mp.nelblk, mp.nelblb, mp.nlwork

@@ -83,6 +83,7 @@ typedef struct orc_part {
   double *lhsK;     /* lhsK(nflow*nflow,nnz_tot) (sparse path)                 */
   const int *colm;  /* colm(nshg+1)                                            */
   const int *rowp;  /* rowp(nnz_tot)                                           */
+  double *aerfrc;   /* Force(3), HFlux, flxID(10,0:1000) (common.h:106); nullable  */
 } orc_part;
 
 #ifdef __cplusplus

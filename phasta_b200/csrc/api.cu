@@ -25,7 +25,6 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
                            const double *const *mBCB, const double *x, const int *iBC, const double *BC,
                            const int *iper, const int *ilwork, const double *shp, const double *shgl,
                            const double *shpb, const double *shglb, int device) {
-  (void)lcblkb; (void)mienb; (void)miBCB; (void)mBCB; (void)shpb; (void)shglb;
   if (!out || !c) return fail("init", "null argument");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -37,7 +36,6 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   if (c->iDC != 0) return fail("init", "iDC!=0 (discontinuity capturing) not supported");
   if (c->Navier != 1) return fail("init", "Navier must be 1");
   if (c->EntropyPressure != 0) return fail("init", "EntropyPressure=1 not supported");
-  if (c->nelblb != 0) return fail("init", "boundary element blocks not supported yet");
   PHB_CHECK(cudaSetDevice(device));
   phb200_ctx *ctx = new (std::nothrow) phb200_ctx();
   if (!ctx) return fail("init", "out of host memory");
@@ -110,8 +108,51 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
     if (!sl.empty())
       PHB_CHECK(cudaMemcpy(ctx->d_perslave, sl.data(), sizeof(int) * sl.size(), cudaMemcpyHostToDevice));
   }
+  // ---- boundary elements (genbkbPosix.f:113-123 lcblkb rows; asbmfg.f)
+  ctx->numelb = 0;
+  ctx->d_ienb = nullptr; ctx->d_iBCB = nullptr; ctx->d_BCB = nullptr;
+  if (c->nelblb > 0) {
+    if (!lcblkb || !mienb || !miBCB || !mBCB || !shpb || !shglb) return fail("init", "null boundary arrays");
+    int nb = 0;
+    for (int b = 0; b < c->nelblb; b++) {
+      const int *lc = lcblkb + 10 * b;
+      if (lc[2] != 1 || lc[8] != 4 || lc[9] != 3 || lc[5] != 3)
+        return fail("init", "only tet boundary blocks with triangular faces supported yet");
+      nb += lc[10] - lc[0];
+    }
+    ctx->numelb = nb;
+    std::vector<int> ienb((size_t)4 * nb), ib((size_t)2 * nb);
+    std::vector<double> bcb((size_t)18 * nb);
+    size_t e0 = 0;
+    for (int b = 0; b < c->nelblb; b++) {
+      const int *lc = lcblkb + 10 * b;
+      int npro = lc[10] - lc[0];
+      for (int e = 0; e < npro; e++) {
+        for (int a = 0; a < 4; a++) {
+          int v = mienb[b][e + (size_t)npro * a];
+          if (v < 0) v = -v;
+          if (v < 1 || v > nshg) return fail("init", "ienb entry out of range");
+          ienb[(size_t)a * nb + e0 + e] = v - 1;
+        }
+        ib[e0 + e] = miBCB[b][e];
+        ib[(size_t)nb + e0 + e] = miBCB[b][e + (size_t)npro];
+        for (int k = 0; k < 6; k++)
+          for (int n = 0; n < 3; n++)
+            bcb[(size_t)(k * 3 + n) * nb + e0 + e] = mBCB[b][e + (size_t)npro * (n + 3 * k)];
+      }
+      e0 += npro;
+    }
+    PHB_TRY(dev_alloc(&ctx->d_ienb, ienb.size()));
+    PHB_CHECK(cudaMemcpy(ctx->d_ienb, ienb.data(), sizeof(int) * ienb.size(), cudaMemcpyHostToDevice));
+    PHB_TRY(dev_alloc(&ctx->d_iBCB, ib.size()));
+    PHB_CHECK(cudaMemcpy(ctx->d_iBCB, ib.data(), sizeof(int) * ib.size(), cudaMemcpyHostToDevice));
+    PHB_TRY(dev_alloc(&ctx->d_BCB, bcb.size()));
+    PHB_CHECK(cudaMemcpy(ctx->d_BCB, bcb.data(), sizeof(double) * bcb.size(), cudaMemcpyHostToDevice));
+  }
+  PHB_TRY(dev_alloc(&ctx->d_aerfrc, (size_t)4 + 10 * 1001));
+  PHB_CHECK(cudaMemset(ctx->d_aerfrc, 0, sizeof(double) * (4 + 10 * 1001)));
   PHB_TRY(phb_halo_setup(ctx, ilwork));
-  PHB_TRY(phb_upload_tables(ctx, shp, shgl));
+  PHB_TRY(phb_upload_tables(ctx, shp, shgl, shpb, shglb));
   // ---- state and work arrays
   const size_t n5 = (size_t)5 * nshg;
   PHB_TRY(dev_alloc(&ctx->d_y, n5));
@@ -152,7 +193,8 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
   void *ptrs[] = {ctx->d_ien, ctx->d_iBC, ctx->d_BC, ctx->d_iper, ctx->d_x, ctx->d_perslave, ctx->d_halo_nodes,
                   ctx->d_slave_nodes, ctx->d_sendbuf, ctx->d_recvbuf, ctx->d_y, ctx->d_ac, ctx->d_qres,
                   ctx->d_rmass, ctx->d_res, ctx->d_rmes, ctx->d_Dy, ctx->d_temp, ctx->d_BDiag, ctx->d_BDtmp,
-                  ctx->d_EG, ctx->d_uBrg, ctx->d_dots, ctx->d_scratch};
+                  ctx->d_EG, ctx->d_uBrg, ctx->d_dots, ctx->d_scratch, ctx->d_ienb, ctx->d_iBCB,
+                  ctx->d_BCB, ctx->d_aerfrc};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_dots) cudaFreeHost(ctx->h_dots);
@@ -346,6 +388,21 @@ extern "C" int phb200_sumgat(phb200_ctx *ctx, const double *u, int n, double *su
   if (len * sizeof(double) > ctx->scratch_bytes) return fail("sumgat", "vector too long");
   PHB_TRY(h2d(ctx, ctx->d_scratch, u, len));
   return phb_sumgat_dev(ctx, ctx->d_scratch, len, summed);
+}
+
+// /aerfrc/ (common.h:106): Force(3), HFlux accumulate over calls with iter==nitr
+// (e3b.f:325-345; itrdrv zeroes them per step, itrdrv.f:437-442 -> zero=1);
+// flxID(10,0:MAXSURF) is per ElmGMRe call (elmgmr.f:122).
+extern "C" int phb200_get_aerfrc(phb200_ctx *ctx, double *Force, double *HFlux, double *flxID, int zero) {
+  ENTER(ctx);
+  std::vector<double> h((size_t)4 + 10 * 1001);
+  PHB_CHECK(cudaMemcpyAsync(h.data(), ctx->d_aerfrc, sizeof(double) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (Force) memcpy(Force, h.data(), sizeof(double) * 3);
+  if (HFlux) *HFlux = h[3];
+  if (flxID) memcpy(flxID, h.data() + 4, sizeof(double) * 10 * 1001);
+  if (zero) PHB_CHECK(cudaMemsetAsync(ctx->d_aerfrc, 0, sizeof(double) * 4, ctx->stream));
+  return 0;
 }
 
 // ---- instrumentation ---------------------------------------------------------

@@ -33,10 +33,18 @@ struct PhysParams {
   double dtsfct, taucfct, temper, Dtgl, fct1;  // fct1 = almi/gami/alfi*Dtgl
   int matflg2, matflg3, idiff, iremove, ipord, lhs, iprec, pad;
 };
+struct TriTables {
+  int nq;
+  double N[3][4];      // shpb(1,a,q): volume shape functions on the face points
+  double dN[3][4][3];  // shglb(1,i,a,q)
+  double Qwt[3];       // Qwtb(1,q)
+};
 __constant__ TetTables c_tet;
+__constant__ TriTables c_tri;
 __constant__ PhysParams c_ph;
 
-int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl) {
+int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, const double *shpb,
+                      const double *shglb) {
   TetTables t;
   memset(&t, 0, sizeof t);
   const phb200_common &c = ctx->c;
@@ -54,6 +62,24 @@ int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl) {
     }
   }
   PHB_CHECK(cudaMemcpyToSymbol(c_tet, &t, sizeof t));
+  if (ctx->numelb > 0) {
+    TriTables b;
+    memset(&b, 0, sizeof b);
+    b.nq = c.nintb[0];
+    if (b.nq != 1 && b.nq != 3) {
+      fprintf(stderr, "phb200: init: tri rule with %d points not supported\n", b.nq);
+      return 1;
+    }
+    for (int q = 0; q < b.nq; q++) {
+      b.Qwt[q] = c.Qwtb[0 + PHB200_MAXTOP * q];
+      for (int a = 0; a < 4; a++) {
+        b.N[q][a] = shpb[0 + PHB200_MAXTOP * (a + PHB200_MAXSH * q)];
+        for (int i = 0; i < 3; i++)
+          b.dN[q][a][i] = shglb[0 + PHB200_MAXTOP * (i + 3 * (a + PHB200_MAXSH * q))];
+      }
+    }
+    PHB_CHECK(cudaMemcpyToSymbol(c_tri, &b, sizeof b));
+  }
   return 0;
 }
 
@@ -744,6 +770,137 @@ __global__ void __launch_bounds__(TILE_E * 4) k_asigmr_tet(
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// AsBMFG + e3b + e3bvar (asbmfg.f:1-66, e3b.f:98-283, e3bvar.f:78-356):
+// boundary flux of tets with a triangular face; thread = boundary element.
+// aer[0..2] Force, aer[3] HFlux, aer[4 + 10*surf + k] flxID(k+1,surf)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_asbmfg_tet(int numelb, int nshg, int numnp, const int *__restrict__ ienb,
+                                                     const int *__restrict__ iBCB, const double *__restrict__ BCB,
+                                                     const double *__restrict__ x, const double *__restrict__ y,
+                                                     double *__restrict__ res, double *__restrict__ aer,
+                                                     int do_force) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= numelb) return;
+  int nd[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) nd[a] = ienb[(size_t)a * numelb + e];
+  double xl[4][3], yl[4][5];
+  gather_x(x, numnp, nd, xl);
+#pragma unroll
+  for (int a = 0; a < 4; a++) gather_y(y, nshg, nd[a], yl[a]);
+  const int ibcb = iBCB[e], surf = abs(iBCB[numelb + e]);
+  // normal and face Jacobian (e3bvar.f:120-152): v1 x v2, WdetJb = Qwtb |v1 x v2| / 4
+  double v1[3], v2[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    v1[i] = xl[1][i] - xl[0][i];
+    v2[i] = xl[2][i] - xl[0][i];
+  }
+  const double t1 = v1[1] * v2[2] - v2[1] * v1[2];
+  const double t2 = v2[0] * v1[2] - v1[0] * v2[2];
+  const double t3 = v1[0] * v2[1] - v2[0] * v1[1];
+  const double tinv = 1.0 / sqrt(t1 * t1 + t2 * t2 + t3 * t3);
+  const double bn[3] = {t1 * tinv, t2 * tinv, t3 * tinv};
+  double rl[3][5];
+#pragma unroll
+  for (int n = 0; n < 3; n++)
+#pragma unroll
+    for (int m = 0; m < 5; m++) rl[n][m] = 0.0;
+  double frc[4] = {0, 0, 0, 0}, flx[5] = {0, 0, 0, 0, 0};
+  const int nq = c_tri.nq;
+  for (int q = 0; q < nq; q++) {
+    const double WdetJb = c_tri.Qwt[q] / (4.0 * tinv);
+    Metric g;  // volume metric for grad Y (e3bvar.f:157-262); W unused
+    tet_metric(xl, c_tri.dN[q], 1.0, g);
+    double Y[5] = {0, 0, 0, 0, 0};
+    double gr[3][5];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int m = 0; m < 5; m++) gr[i][m] = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+#pragma unroll
+      for (int m = 0; m < 5; m++) {
+        if (a < 3) Y[m] += c_tri.N[q][a] * yl[a][m];  // only the nshlb face nodes (e3bvar.f:84-92)
+#pragma unroll
+        for (int i = 0; i < 3; i++) gr[i][m] += g.shg[a][i] * yl[a][m];
+      }
+    }
+    const double pres = Y[0], u1 = Y[1], u2 = Y[2], u3 = Y[3], T = Y[4];
+    const double rk = 0.5 * (u1 * u1 + u2 * u2 + u3 * u3);
+    const double rho = pres / (c_ph.Rgas * T);
+    const double ei = T * (c_ph.Rgas / c_ph.gamma1);
+    const double cp = c_ph.Rgas * c_ph.gamma / c_ph.gamma1;
+    // natural BC values interpolated on the face (e3bvar.f:330-356)
+    double bv[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int n = 0; n < 3; n++)
+#pragma unroll
+      for (int k = 0; k < 6; k++) bv[k] += c_tri.N[q][n] * __ldg(BCB + (size_t)(k * 3 + n) * numelb + e);
+    double rou, un, pb = bv[1];
+    if (!(ibcb & 1)) {
+      un = bn[0] * u1 + bn[1] * u2 + bn[2] * u3;
+      rou = rho * un;
+    } else {
+      rou = bv[0];
+      un = rou / rho;
+    }
+    if (!(ibcb & 2)) pb = pres;
+    double F[5];
+    F[0] = rou;
+    F[1] = rou * u1 + bn[0] * pb;
+    F[2] = rou * u2 + bn[1] * pb;
+    F[3] = rou * u3 + bn[2] * pb;
+    F[4] = rou * (ei + rk) + un * pb;
+    double mu, lam, con;
+    diffusivities(T, cp, mu, lam, con);
+    const double l2m = lam + 2.0 * mu;
+    const double *g1 = gr[0], *g2 = gr[1], *g3 = gr[2];
+    const double tau1n = bn[0] * (l2m * g1[1] + lam * g2[2] + lam * g3[3]) + bn[1] * (mu * (g2[1] + g1[2])) +
+                         bn[2] * (mu * (g3[1] + g1[3]));
+    const double tau2n = bn[0] * (mu * (g2[1] + g1[2])) + bn[1] * (lam * g1[1] + l2m * g2[2] + lam * g3[3]) +
+                         bn[2] * (mu * (g3[2] + g2[3]));
+    const double tau3n = bn[0] * (mu * (g3[1] + g1[3])) + bn[1] * (mu * (g3[2] + g2[3])) +
+                         bn[2] * (lam * g1[1] + lam * g2[2] + l2m * g3[3]);
+    double Fv2 = bv[2], Fv3 = bv[3], Fv4 = bv[4], Fh5 = bv[5];
+    if (!(ibcb & 4)) { Fv2 = tau1n; Fv3 = tau2n; Fv4 = tau3n; }
+    const double Fv5 = u1 * Fv2 + u2 * Fv3 + u3 * Fv4;
+    const double heat = -con * (bn[0] * g1[4] + bn[1] * g2[4] + bn[2] * g3[4]);
+    if (!(ibcb & 8)) Fh5 = heat;
+    F[1] -= Fv2; F[2] -= Fv3; F[3] -= Fv4;
+    F[4] = F[4] - Fv5 + Fh5;
+#pragma unroll
+    for (int n = 0; n < 3; n++) {
+      const double wn = WdetJb * c_tri.N[q][n];
+#pragma unroll
+      for (int m = 0; m < 5; m++) rl[n][m] += wn * F[m];
+    }
+    // flxID (e3b.f:305-321) and aerodynamic forces (e3b.f:325-345)
+    flx[0] += WdetJb;
+    flx[1] -= WdetJb * rou;
+    flx[2] -= (tau1n - bn[0] * pres) * WdetJb;
+    flx[3] -= (tau2n - bn[1] * pres) * WdetJb;
+    flx[4] -= (tau3n - bn[2] * pres) * WdetJb;
+    if (!(ibcb & 1)) {
+      frc[0] += (pres * bn[0] - tau1n) * WdetJb;
+      frc[1] += (pres * bn[1] - tau2n) * WdetJb;
+      frc[2] += (pres * bn[2] - tau3n) * WdetJb;
+      frc[3] += -heat * WdetJb;
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 3; n++)
+#pragma unroll
+    for (int m = 0; m < 5; m++) atomicAdd(res + (size_t)nshg * m + nd[n], rl[n][m]);
+  if (surf != 0 && surf <= 1000)
+    for (int k = 0; k < 5; k++) atomicAdd(aer + 4 + 10 * surf + k, flx[k]);
+  if (do_force)
+    for (int k = 0; k < 4; k++) atomicAdd(aer + k, frc[k]);
+}
+
 // ---------------------------------------------------------------------------
 // node-wise BC kernels
 // ---------------------------------------------------------------------------
@@ -981,6 +1138,14 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st) {
     }
   }
   if (st->lhs == 1) ctx->have_lhs = true;
+  if (ctx->numelb > 0) {  // boundary blocks (elmgmr.f:180-222); flxID = 0 first (elmgmr.f:122)
+    PHB_CHECK(cudaMemsetAsync(ctx->d_aerfrc + 4, 0, sizeof(double) * 10 * 1001, s));
+    KScope ks(ctx, KC_ASM);
+    k_asbmfg_tet<<<(ctx->numelb + 127) / 128, 128, 0, s>>>(ctx->numelb, nshg, c.numnp, ctx->d_ienb, ctx->d_iBCB,
+                                                           ctx->d_BCB, ctx->d_x, ctx->d_y, ctx->d_res, ctx->d_aerfrc,
+                                                           st->iter == st->nitr);
+    PHB_CHECK(cudaGetLastError());
+  }
   // halo + BC post-processing (elmgmr.f:249-268)
   PHB_TRY(phb_commu(ctx, ctx->d_res, 5, 0));
   if (st->iprec != 0) PHB_TRY(phb_commu(ctx, ctx->d_BDiag, 25, 0));

@@ -51,6 +51,12 @@ struct phb200_ctx {
   double *d_x;         // [3][numnp]
   int n_perslave;      // periodic slave nodes (iBC bit 10)
   int *d_perslave;     // their ids
+  // ---- boundary elements (tet volume element, tri face = local nodes 1..3)
+  int numelb;          // boundary elements in all blocks
+  int *d_ienb;         // [4][numelb] 0-based
+  int *d_iBCB;         // [2][numelb]  iBCB(:,1) flux codes, iBCB(:,2) surfID
+  double *d_BCB;       // [6][3][numelb]  BCB(e,n,k) -> [(k*3+n)*numelb + e]
+  double *d_aerfrc;    // Force(3), HFlux, then flxID(10,0:MAXSURF)
   // ---- halo (ilwork)
   std::vector<HaloTask> tasks;
   int *d_halo_nodes;   // concatenated node lists of all tasks
@@ -105,7 +111,8 @@ struct KScope {
 };
 
 // assembly.cu
-int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl);
+int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, const double *shpb,
+                      const double *shglb);
 int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st);
 // solver.cu
 int phb_i3lu(phb200_ctx *ctx, double *d_Diag, double *d_r, int code);

@@ -102,8 +102,71 @@ def _blocks(numel, ibksiz, lcsyst=1, ipord=1, nenl=4, nshl=4, nfacel=4):
     return lcblk
 
 
+def _boundary_elements(ien0, x, on_boundary_planes, gnode, ibksiz, natural, seed):
+    """Boundary elements of a tet part (genbkbPosix.f:47-123): each is the
+    volume tet re-ordered so that local nodes 1..3 are the boundary triangle
+    with outward normal (v1 x v2, e3bvar.f:120-140) and node 4 is interior.
+    on_boundary_planes: list of boolean node masks, one per selected plane.
+    natural: "none" -> iBCB=0 (all fluxes floating); "mixed" -> deterministic
+    sprinkle of mass-flux / pressure / traction / heat-flux codes + values."""
+    faces_of = ((1, 2, 3), (0, 3, 2), (0, 1, 3), (0, 2, 1))   # face opposite node k
+    out = []
+    for mask in on_boundary_planes:
+        m = mask[ien0]                                         # (numel,4)
+        for k in range(4):
+            f = faces_of[k]
+            sel = m[:, f[0]] & m[:, f[1]] & m[:, f[2]] & ~m[:, k]
+            if not sel.any():
+                continue
+            t = ien0[sel]
+            out.append(np.stack([t[:, f[0]], t[:, f[1]], t[:, f[2]], t[:, k]], axis=1))
+    if not out:
+        return None, [], [], []
+    b = np.concatenate(out, axis=0)
+    # orient: normal (b-a)x(c-a) must point away from d
+    a_, b_, c_, d_ = (x[b[:, i]] for i in range(4))
+    nrm = np.cross(b_ - a_, c_ - a_)
+    flip = np.einsum("ij,ij->i", nrm, d_ - a_) > 0
+    b[flip, 1], b[flip, 2] = b[flip, 2].copy(), b[flip, 1].copy()
+    nb = b.shape[0]
+    ienb = (b + 1).astype(np.int32)
+    iBCB = np.zeros((nb, 2), dtype=np.int32)
+    BCB = np.zeros((nb, 3, NDOF + 1))
+    if natural == "mixed":
+        gkey = np.sort(gnode[b[:, :3]], axis=1)
+        h = (gkey[:, 0] * 73856093 ^ gkey[:, 1] * 19349663 ^ gkey[:, 2] * 83492791) % 11
+        r = np.random.default_rng(seed + 11)
+        vals = r.uniform(0.5, 1.5, size=(11, 6)) * np.array([30.0, 1.0e5, 2.0, 2.0, 2.0, 50.0])
+        for code, bit in ((1, 1), (2, 2), (3, 4), (4, 8), (5, 1 | 2), (6, 4 | 8)):
+            s_ = h == code
+            iBCB[s_, 0] = bit
+            iBCB[s_, 1] = code
+            BCB[s_, :, :] = vals[code][None, None, :]
+        # genbkbPosix.f:86-100: values of unset codes are zeroed on read
+        BCB[(iBCB[:, 0] & 1) == 0, :, 0] = 0.0
+        BCB[(iBCB[:, 0] & 2) == 0, :, 1] = 0.0
+        BCB[(iBCB[:, 0] & 4) == 0, :, 2:5] = 0.0
+        BCB[(iBCB[:, 0] & 8) == 0, :, 5] = 0.0
+    starts = np.arange(0, nb, ibksiz)
+    nblk = starts.size
+    lcblkb = np.zeros((10, nblk + 1), dtype=np.int32, order="F")
+    lcblkb[0, :nblk] = starts + 1
+    lcblkb[0, nblk] = nb + 1
+    lcblkb[2, :nblk] = 1       # lcsyst
+    lcblkb[3, :nblk] = 1       # ipord
+    lcblkb[4, :nblk] = 4       # nenl
+    lcblkb[5, :nblk] = 3       # nenbl
+    lcblkb[6, :nblk] = 0       # mattyp
+    lcblkb[7, :nblk] = NDOF    # ndofl
+    lcblkb[8, :nblk] = 4       # nshl
+    lcblkb[9, :nblk] = 3       # nshlb
+    sl = [slice(lcblkb[0, i] - 1, lcblkb[0, i + 1] - 1) for i in range(nblk)]
+    return (lcblkb, [np.asfortranarray(ienb[q]) for q in sl], [np.asfortranarray(iBCB[q]) for q in sl],
+            [np.asfortranarray(BCB[q]) for q in sl])
+
+
 def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15,
-             bc="channel", periodic_z=True, seed=1234, max_seg=0, only_rank=None):
+             bc="channel", periodic_z=True, seed=1234, max_seg=0, only_rank=None, boundary=False, natural="none"):
     """Build `nparts` MeshPart objects for an nx*ny*nz-hex box (6 tets/hex).
 
     bc: "channel"  x-min inflow (velocity code 7 + T), x-max pressure,
@@ -113,6 +176,8 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
                    density BC, random slopes (exercises bc3* branches)
     max_seg: if >0 split ilwork segments to at most this length.
     only_rank: build (and return a 1-list with) just that rank's part.
+    boundary: also generate boundary elements (x-min, x-max, y walls; z faces
+              unless periodic) with natural-BC codes per `natural`.
     """
     assert nx % nparts == 0 or nparts == 1, "nx must be divisible by nparts"
     rng = np.random.default_rng(seed)
@@ -217,9 +282,21 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
                 il += [a, ln]
         ilwork = np.array(il, dtype=np.int32)
 
-        parts.append(MeshPart(rank=p, numpe=nparts, nshg=nn, numnp=nn, numel=numel,
-                              x=x, lcblk=lcblk, mien=mien, iBC=iBC, BC=BC, iper=iper,
-                              ilwork=ilwork, gnode=gnode, gelem=gelem))
+        mp = MeshPart(rank=p, numpe=nparts, nshg=nn, numnp=nn, numel=numel,
+                      x=x, lcblk=lcblk, mien=mien, iBC=iBC, BC=BC, iper=iper,
+                      ilwork=ilwork, gnode=gnode, gelem=gelem)
+        if boundary:
+            planes = [J == 0, J == ny]
+            if i0 == 0:
+                planes.append(I == 0)
+            if i1 == nx:
+                planes.append(I == nx)
+            if not (periodic_z and bc in ("channel", "mixed")):
+                planes += [K == 0, K == nz]
+            lcb, ienb, ibcb, bcb = _boundary_elements(ien0, x, planes, gnode, ibksiz, natural, seed)
+            if lcb is not None:
+                mp.lcblkb, mp.mienb, mp.miBCB, mp.mBCB = lcb, ienb, ibcb, bcb
+        parts.append(mp)
     return parts
 
 

@@ -40,7 +40,8 @@ class PhastaGPU:
         nshape = max(int(b.shape[1]) for b in part.mien)
         self.nedof = 5 * nshape
         c = PhbCommon()
-        c.nshg, c.numnp, c.numel, c.numelb = part.nshg, part.numnp, part.numel, 0
+        c.nshg, c.numnp, c.numel = part.nshg, part.numnp, part.numel
+        c.numelb = int(sum(b.shape[0] for b in part.mienb)) if part.nelblb else 0
         c.nflow, c.ndof, c.ndofBC, c.nshape, c.nedof = 5, 5, 6, nshape, self.nedof
         c.nelblk, c.nelblb, c.nlwork = part.nelblk, part.nelblb, part.nlwork
         c.numpe, c.myrank = part.numpe, part.rank
@@ -69,9 +70,20 @@ class PhastaGPU:
         k["ilwork"] = np.ascontiguousarray(part.ilwork, dtype=np.int32)
         for nm in ("shp", "shgl", "shpb", "shglb"):
             k[nm] = np.asfortranarray(tables[nm], dtype=np.float64)
+        lcblkb = ienb_ptrs = ibcb_ptrs = bcb_ptrs = None
+        if part.nelblb:
+            k["lcblkb"] = np.asfortranarray(part.lcblkb, dtype=np.int32)
+            k["mienb"] = [np.asfortranarray(b, dtype=np.int32) for b in part.mienb]
+            k["miBCB"] = [np.asfortranarray(b, dtype=np.int32) for b in part.miBCB]
+            k["mBCB"] = [np.asfortranarray(b, dtype=np.float64) for b in part.mBCB]
+            nb = len(k["mienb"])
+            lcblkb = _p(k["lcblkb"], C.c_int)
+            ienb_ptrs = (C.POINTER(C.c_int) * nb)(*[_p(b, C.c_int) for b in k["mienb"]])
+            ibcb_ptrs = (C.POINTER(C.c_int) * nb)(*[_p(b, C.c_int) for b in k["miBCB"]])
+            bcb_ptrs = (C.POINTER(C.c_double) * nb)(*[_p(b) for b in k["mBCB"]])
         self.ctx = C.c_void_p()
         _chk(self.L.phb200_init(C.byref(self.ctx), C.byref(c), _p(k["lcblk"], C.c_int), mien_ptrs,
-                                None, None, None, None, _p(k["x"]), _p(k["iBC"], C.c_int), _p(k["BC"]),
+                                lcblkb, ienb_ptrs, ibcb_ptrs, bcb_ptrs, _p(k["x"]), _p(k["iBC"], C.c_int), _p(k["BC"]),
                                 _p(k["iper"], C.c_int), _p(k["ilwork"], C.c_int), _p(k["shp"]), _p(k["shgl"]),
                                 _p(k["shpb"]), _p(k["shglb"]), int(device)), "init")
         K = params.Kspace
@@ -169,6 +181,14 @@ class PhastaGPU:
         out = C.c_double(0.0)
         _chk(self.L.phb200_sumgat(self.ctx, _p(np.asfortranarray(u)), int(n), C.byref(out)), "sumgat")
         return out.value
+
+    def aerfrc(self, zero=False):
+        """COMMON /aerfrc/: (Force(3), HFlux, flxID(10,0:MAXSURF))."""
+        F = np.zeros(3)
+        H = C.c_double(0)
+        fl = np.zeros((10, 1001), order="F")
+        _chk(self.L.phb200_get_aerfrc(self.ctx, _p(F), C.byref(H), _p(fl), int(zero)), "get_aerfrc")
+        return F, H.value, fl
 
     # --------------------------------------------------- HBM-resident path
     def set_state(self, y, ac):

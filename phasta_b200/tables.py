@@ -60,7 +60,7 @@ def make_tables(rule=2, ruleb=2):
     nintb[0] = nb
     Qwtb[0, :nb] = 2.0 * wb
     for i in range(nb):
-        r, s, t = ptsb[i, 0], ptsb[i, 1], ptsb[i, 3]   # Qptb(1,1:3,i)
+        r, s, t = ptsb[i, 0], ptsb[i, 1], ptsb[i, 2]   # Qptb(1,1:3,i) (genshpb.f:24)
         shpb[0, :4, i] = [r, s, t, 1.0 - r - s - t]
         shglb[0, :, :4, i] = dN.T / 2.0
     return dict(nint=nint, nintb=nintb, Qwt=Qwt, Qwtb=Qwtb, shp=shp, shgl=shgl,

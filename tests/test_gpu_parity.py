@@ -141,3 +141,41 @@ def test_sumgat_and_fp64_peak():
     assert g.fp64_peak() > 1.0
     assert g.launches() > 0
     g.close()
+
+
+@pytest.mark.parametrize("natural,bc", [("none", "channel"), ("mixed", "channel"), ("mixed", "none")])
+def test_boundary_elements_parity(natural, bc):
+    """AsBMFG/e3b boundary flux (asbmfg.f, e3b.f, e3bvar.f) incl. /aerfrc/."""
+    case = make_case(6, 5, 4, bc=bc, periodic_z=(bc != "none"), boundary=True, natural=natural)
+    assert case[2][0].nelblb > 0
+    o = make_oracle(case)
+    o.ElmGMRe()
+    g = gpu(case)
+    y, ac = case[3][0]
+    out = g.ElmGMRe(y, ac, want_egmass=True)
+    op = o.parts[0]
+    assert rel_l2(out["res"], op.res) < TOL_ASM
+    assert rel_l2(out["EGmass"], op.EGmass) < TOL_ASM
+    F, H, fl = g.aerfrc()
+    assert rel_l2(F, op.aerfrc[:3]) < 1e-10 and abs(H - op.aerfrc[3]) <= 1e-10 * abs(op.aerfrc[3])
+    assert rel_l2(fl.ravel(order="F"), op.aerfrc[4:]) < 1e-10
+    # the boundary flux really contributes
+    case0 = make_case(6, 5, 4, bc=bc, periodic_z=(bc != "none"))
+    g0 = gpu(case0)
+    r0 = g0.ElmGMRe(y, ac)["res"]
+    assert rel_l2(r0, out["res"]) > 1e-3 or bc == "channel"
+    g.close()
+    g0.close()
+
+
+def test_solgmre_with_boundary_elements():
+    case = make_case(8, 6, 5, bc="channel", boundary=True, natural="mixed", etol=1e-6, Kspace=40)
+    o = make_oracle(case)
+    iKs_o, _ = o.SolGMRe()
+    g = gpu(case)
+    y, ac = case[3][0]
+    res, Dy = g.SolGMRe(y, ac)
+    assert g.iKs == iKs_o
+    assert rel_l2(g.rmes, o.parts[0].rmes) < TOL_ASM
+    assert rel_l2(Dy, o.parts[0].Dy) < TOL_SOL
+    g.close()

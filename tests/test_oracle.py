@@ -170,3 +170,16 @@ def test_commu_in_then_out_roundtrip():
         np.add.at(glob, mp.gnode, b)
     for mp, v in zip(case[2], vecs):
         assert rel_l2(v, glob[mp.gnode]) < 1e-14
+
+
+def test_boundary_flux_closes_the_patch_test():
+    """With boundary elements on every face, a uniform flow gives zero residual
+    at EVERY node (interior Galerkin flux and e3b boundary flux cancel)."""
+    parts = make_box(5, 4, 3, bc="none", periodic_z=False, boundary=True)
+    y, ac = uniform_state(parts[0])
+    o = Oracle(parts, SolverParams(), make_tables(2, 2), [(y, ac)])
+    o.ElmGMRe()
+    scale = np.array([30.0 * 1.2, 1.0e5, 1.0e5, 1.0e5, 1.0e5 * 30.0])    # rho u, p, p, p, rho h u
+    assert (np.abs(o.parts[0].res).max(axis=0) / scale).max() < 1e-13
+    nb = sum(b.shape[0] for b in parts[0].mienb)
+    assert nb == 2 * 2 * (5 * 4 + 5 * 3 + 4 * 3)
