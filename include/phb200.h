@@ -94,6 +94,34 @@ int phb200_elmgmre(phb200_ctx *ctx, const double *y, const double *ac,
                    const phb200_step *step, double *res, double *BDiag,
                    double *EGmass, double *qres);
 
+/* ---- block-CSR flavour: SolGMRs (solgmr.f:368-744, itrdrv.f:477-487) ----
+ * genadj (common/genadj.f:1-82): colm(nshg+1) 1-based row pointers, rowp
+ * ascending 1-based column ids incl. the diagonal, nnz_tot; rowp has capacity
+ * nnz*nshg like the reference (input.f:151).  (The reference calls these
+ * `colm`/`rowp` at the call site and `col`/`row` inside sparseap.f:18-20.) */
+int phb200_genadj(phb200_ctx *ctx, int nnz, int *colm, int *rowp, int *nnz_tot);
+/* hand the CSR structure itrdrv owns (itrdrv.f:167-169) to the device once */
+int phb200_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp,
+                      int nnz_tot);
+/* ElmGMRs + fillsparseC (elmgmr.f:280-612, fillsparse.f:66-126); lhsK
+ * (25,nnz_tot) out, nullable */
+int phb200_elmgmrs(phb200_ctx *ctx, const double *y, const double *ac,
+                   const phb200_step *step, double *res, double *BDiag,
+                   double *lhsK);
+/* Spsi3pre (spsi3pre.f:41-221), SparseAp (sparseap.f:26-135) */
+int phb200_spsi3pre(phb200_ctx *ctx, double *lhsK);
+int phb200_sparseap(phb200_ctx *ctx, double *p);
+/* SolGMRs: same outputs as phb200_solgmre; lhsK stays device-resident */
+int phb200_solgmrs(phb200_ctx *ctx, const double *y, const double *ac,
+                   const phb200_step *step, double *res, double *rmes,
+                   double *BDiag, double *Dy, double *HBrg, double *eBrg,
+                   double *yBrg, double *Rcos, double *Rsin, int *iKs,
+                   int *lGMRESs, int *ntotGM);
+int phb200_dev_elmgmrs(phb200_ctx *ctx, const phb200_step *step);
+int phb200_dev_solve_sparse(phb200_ctx *ctx, const phb200_step *step, int *iKs,
+                            int *lGMRESs, int *ntotGM);
+int phb200_dev_sparseap(phb200_ctx *ctx, int slot);
+
 /* Finer seams, all on host arrays: */
 /* i3LU (i3lu.f:1-181) code 0 LU_Fact / 1 forward / 2 backward / 3 product */
 int phb200_i3lu(phb200_ctx *ctx, double *Diag, double *r, int code);

@@ -762,7 +762,7 @@ void orc_au1gmr(int nparts, orc_part *parts, double **u) {
 typedef void (*ap_fn)(int, orc_part *, double **);
 
 static void gmres_core(int nparts, orc_part *parts, ap_fn Ap, int minIters,
-                       double *HBrg, double *eBrg, double *yBrg, double *Rcos,
+                       int restart_recompute, double *HBrg, double *eBrg, double *yBrg, double *Rcos,
                        double *Rsin, int *iKs_out, int *lGMRES_out,
                        int *ntotGM) {
   const orc_common *c = &parts[0].c;
@@ -784,7 +784,7 @@ static void gmres_core(int nparts, orc_part *parts, ap_fn Ap, int minIters,
   double epsnrm = c->etol * unorm;
   for (int mGMRES = 1; mGMRES <= nGMRES; mGMRES++) {
     lGMRES = mGMRES - 1;
-    if (lGMRES > 0) { /* restart: R - A x (:149-178) */
+    if (lGMRES > 0 && restart_recompute) { /* restart: R - A x (:149-178) */
       for (int m = 0; m < nparts; m++) {
         size_t n = (size_t)parts[m].c.nshg * 5;
         memcpy(parts[m].temp, parts[m].Dy, sizeof(double) * n);
@@ -899,7 +899,7 @@ void orc_solgmre(int nparts, orc_part *parts, double *HBrg, double *eBrg,
     memset(p->Dy, 0, sizeof(double) * n);
   }
   orc_i3pre(nparts, parts);
-  gmres_core(nparts, parts, orc_au1gmr, 0, HBrg, eBrg, yBrg, Rcos, Rsin, iKs,
+  gmres_core(nparts, parts, orc_au1gmr, 0, 1, HBrg, eBrg, yBrg, Rcos, Rsin, iKs,
              lGMRES, ntotGM);
   for (int m = 0; m < nparts; m++)
     orc_i3lu(&parts[m].c, parts[m].BDiag, parts[m].Dy, 2); /* :347 */
@@ -908,8 +908,9 @@ void orc_solgmre(int nparts, orc_part *parts, double *HBrg, double *eBrg,
 /* exported so oracle_sparse.c can reuse the same Krylov loop */
 void orc_gmres_core(int nparts, orc_part *parts,
                     void (*Ap)(int, orc_part *, double **), int minIters,
-                    double *HBrg, double *eBrg, double *yBrg, double *Rcos,
-                    double *Rsin, int *iKs, int *lGMRES, int *ntotGM) {
-  gmres_core(nparts, parts, Ap, minIters, HBrg, eBrg, yBrg, Rcos, Rsin, iKs,
-             lGMRES, ntotGM);
+                    int restart_recompute, double *HBrg, double *eBrg,
+                    double *yBrg, double *Rcos, double *Rsin, int *iKs,
+                    int *lGMRES, int *ntotGM) {
+  gmres_core(nparts, parts, Ap, minIters, restart_recompute, HBrg, eBrg, yBrg,
+             Rcos, Rsin, iKs, lGMRES, ntotGM);
 }

@@ -211,6 +211,38 @@ class Oracle:
     def sumgat(self, vecs, n):
         return self.L.orc_sumgat(self.n, self.arr, self._vecs(vecs), n)
 
+    # ---- block-CSR flavour ------------------------------------------------
+    def genadj(self, nnz=35):
+        """genadj.f: fills colm/rowp of every part; returns [nnz_tot]."""
+        out = []
+        for i, p in enumerate(self.parts):
+            nshg = p.mp.nshg
+            p.colm = p.keep["colm"] = np.zeros(nshg + 1, dtype=np.int32)
+            rowp = np.zeros(nnz * nshg, dtype=np.int32)
+            ntot = self.L.orc_genadj(C.byref(self.arr[i]), nnz, _ptr(p.colm), _ptr(rowp))
+            p.rowp = p.keep["rowp"] = rowp[:ntot].copy()
+            p.lhsK = p.keep["lhsK"] = np.zeros((25, ntot), order="F")
+            for nm in ("colm", "rowp", "lhsK"):
+                setattr(self.arr[i], nm, _ptr(p.keep[nm]))
+            out.append(ntot)
+        return out
+
+    def ElmGMRs(self):
+        self.L.orc_elmgmrs(self.n, self.arr)
+
+    def Spsi3pre(self):
+        self.L.orc_spsi3pre(self.n, self.arr)
+
+    def SparseAp(self, vecs):
+        self.L.orc_sparseap(self.n, self.arr, self._vecs(vecs))
+
+    def SolGMRs(self):
+        iKs, lG = C.c_int(0), C.c_int(0)
+        self.L.orc_solgmrs(self.n, self.arr, _ptr(self.HBrg), _ptr(self.eBrg), _ptr(self.yBrg),
+                           _ptr(self.Rcos), _ptr(self.Rsin), C.byref(iKs), C.byref(lG),
+                           C.byref(self.ntotGM))
+        return iKs.value, lG.value
+
     def SolGMRe(self):
         iKs, lG = C.c_int(0), C.c_int(0)
         self.L.orc_solgmre(self.n, self.arr, _ptr(self.HBrg), _ptr(self.eBrg), _ptr(self.yBrg),

@@ -166,8 +166,14 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   PHB_TRY(dev_alloc(&ctx->d_BDiag, (size_t)25 * nshg));
   ctx->d_BDtmp = nullptr;
   if (c->numpe > 1) PHB_TRY(dev_alloc(&ctx->d_BDtmp, (size_t)25 * nshg));
-  PHB_TRY(dev_alloc(&ctx->d_EG, ctx->numel_pad * 400));
-  PHB_CHECK(cudaMemset(ctx->d_EG, 0, sizeof(double) * ctx->numel_pad * 400));
+  ctx->d_EG = nullptr;  // allocated by the first EBE lhs=1 assembly
+  ctx->nnz_tot = 0;
+  ctx->d_colm = ctx->d_rowp = ctx->d_rowofblk = ctx->d_eloc = nullptr;
+  ctx->d_lhsK = nullptr;
+  ctx->have_lhs_sparse = false;
+  // keep the host block structure for genadj
+  ctx->h_lcblk.assign(lcblk, lcblk + 10 * (c->nelblk + 1));
+  ctx->h_mien.assign(mien, mien + c->nelblk);
   PHB_TRY(dev_alloc(&ctx->d_uBrg, n5 * (size_t)(c->Kspace + 1)));
   PHB_TRY(dev_alloc(&ctx->d_dots, (size_t)c->Kspace + 8));
   PHB_CHECK(cudaMallocHost(&ctx->h_dots, sizeof(double) * ((size_t)c->Kspace + 8)));
@@ -194,7 +200,7 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
                   ctx->d_slave_nodes, ctx->d_sendbuf, ctx->d_recvbuf, ctx->d_y, ctx->d_ac, ctx->d_qres,
                   ctx->d_rmass, ctx->d_res, ctx->d_rmes, ctx->d_Dy, ctx->d_temp, ctx->d_BDiag, ctx->d_BDtmp,
                   ctx->d_EG, ctx->d_uBrg, ctx->d_dots, ctx->d_scratch, ctx->d_ienb, ctx->d_iBCB,
-                  ctx->d_BCB, ctx->d_aerfrc};
+                  ctx->d_BCB, ctx->d_aerfrc, ctx->d_colm, ctx->d_rowp, ctx->d_rowofblk, ctx->d_eloc, ctx->d_lhsK};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_dots) cudaFreeHost(ctx->h_dots);
@@ -245,7 +251,7 @@ extern "C" int phb200_dev_elmgmre(phb200_ctx *ctx, const phb200_step *st) {
 }
 extern "C" int phb200_dev_solve(phb200_ctx *ctx, const phb200_step *st, int *iKs, int *lGMRES, int *ntotGM) {
   ENTER(ctx);
-  return phb_solve(ctx, st, iKs, lGMRES, ntotGM);
+  return phb_solve(ctx, st, 0, iKs, lGMRES, ntotGM);
 }
 extern "C" int phb200_dev_ap(phb200_ctx *ctx, int slot) {
   ENTER(ctx);
@@ -278,6 +284,7 @@ extern "C" int phb200_get_egmass(phb200_ctx *ctx, double *EGmass) {
   ENTER(ctx);
   const int numel = ctx->c.numel, nedof = ctx->c.nedof;
   if (numel == 0) return 0;
+  if (!ctx->d_EG) return fail("get_egmass", "no EBE LHS has been assembled");
   double *d_out = nullptr;
   size_t tot = (size_t)numel * nedof * nedof;
   PHB_CHECK(cudaMalloc(&d_out, sizeof(double) * tot));
@@ -314,7 +321,7 @@ extern "C" int phb200_solgmre(phb200_ctx *ctx, const double *y, const double *ac
   const size_t n5 = (size_t)5 * ctx->c.nshg;
   PHB_TRY(phb200_set_state(ctx, y, ac));
   PHB_TRY(phb_elmgmre(ctx, st));
-  PHB_TRY(phb_solve(ctx, st, iKs, lGMRES, ntotGM));
+  PHB_TRY(phb_solve(ctx, st, 0, iKs, lGMRES, ntotGM));
   PHB_TRY(d2h(ctx, Dy, ctx->d_Dy, n5));
   if (res) PHB_TRY(d2h(ctx, res, ctx->d_res, n5));
   if (rmes) PHB_TRY(d2h(ctx, rmes, ctx->d_rmes, n5));
@@ -327,6 +334,95 @@ extern "C" int phb200_solgmre(phb200_ctx *ctx, const double *y, const double *ac
   if (Rcos) memcpy(Rcos, ctx->Rcos.data(), sizeof(double) * (K + 1));
   if (Rsin) memcpy(Rsin, ctx->Rsin.data(), sizeof(double) * (K + 1));
   return 0;
+}
+
+
+// ---- block-CSR flavour -------------------------------------------------------
+extern "C" int phb200_genadj(phb200_ctx *ctx, int nnz, int *colm, int *rowp, int *nnz_tot) {
+  ENTER(ctx);
+  if (!colm || !rowp || !nnz_tot) return fail("genadj", "null argument");
+  return phb_genadj_host(ctx->c.nshg, ctx->c.nelblk, ctx->h_lcblk.data(), ctx->h_mien.data(), nnz, colm, rowp,
+                         nnz_tot);
+}
+extern "C" int phb200_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_tot) {
+  ENTER(ctx);
+  if (!colm || !rowp) return fail("set_sparse", "null argument");
+  return phb_set_sparse(ctx, colm, rowp, nnz_tot);
+}
+static int get_lhsk(phb200_ctx *ctx, double *lhsK) {
+  PHB_CHECK(cudaMemcpyAsync(lhsK, ctx->d_lhsK, sizeof(double) * 25 * (size_t)ctx->nnz_tot, cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_elmgmrs(phb200_ctx *ctx, const double *y, const double *ac, const phb200_step *st, double *res,
+                              double *BDiag, double *lhsK) {
+  ENTER(ctx);
+  if (!y || !ac || !st) return fail("elmgmrs", "null argument");
+  PHB_TRY(phb200_set_state(ctx, y, ac));
+  PHB_TRY(phb_elmgmre(ctx, st, 1));
+  if (res) PHB_TRY(d2h(ctx, res, ctx->d_res, (size_t)5 * ctx->c.nshg));
+  if (BDiag && st->iprec) PHB_TRY(d2h(ctx, BDiag, ctx->d_BDiag, (size_t)25 * ctx->c.nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (lhsK && st->lhs == 1) PHB_TRY(get_lhsk(ctx, lhsK));
+  return 0;
+}
+extern "C" int phb200_spsi3pre(phb200_ctx *ctx, double *lhsK) {
+  ENTER(ctx);
+  if (!ctx->have_lhs_sparse) return fail("spsi3pre", "no sparse LHS has been assembled");
+  PHB_TRY(phb_spsi3pre(ctx));
+  if (lhsK) PHB_TRY(get_lhsk(ctx, lhsK));
+  return 0;
+}
+extern "C" int phb200_sparseap(phb200_ctx *ctx, double *p) {
+  ENTER(ctx);
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  double *d_u = ctx->d_uBrg;
+  PHB_TRY(h2d(ctx, d_u, p, n5));
+  PHB_TRY(phb_sparseap(ctx, d_u));
+  PHB_TRY(d2h(ctx, p, d_u, n5));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_solgmrs(phb200_ctx *ctx, const double *y, const double *ac, const phb200_step *st, double *res,
+                              double *rmes, double *BDiag, double *Dy, double *HBrg, double *eBrg, double *yBrg,
+                              double *Rcos, double *Rsin, int *iKs, int *lGMRESs, int *ntotGM) {
+  ENTER(ctx);
+  if (!y || !ac || !st || !Dy || !iKs || !lGMRESs || !ntotGM) return fail("solgmrs", "null argument");
+  if (!ctx->d_lhsK) return fail("solgmrs", "no CSR structure (call phb200_set_sparse with colm/rowp first)");
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  PHB_TRY(phb200_set_state(ctx, y, ac));
+  PHB_TRY(phb_elmgmre(ctx, st, 1));
+  PHB_TRY(phb_solve(ctx, st, 1, iKs, lGMRESs, ntotGM));
+  PHB_TRY(d2h(ctx, Dy, ctx->d_Dy, n5));
+  if (res) PHB_TRY(d2h(ctx, res, ctx->d_res, n5));
+  if (rmes) PHB_TRY(d2h(ctx, rmes, ctx->d_rmes, n5));
+  if (BDiag) PHB_TRY(d2h(ctx, BDiag, ctx->d_BDiag, (size_t)25 * ctx->c.nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  const int K = ctx->c.Kspace;
+  if (HBrg) memcpy(HBrg, ctx->HBrg.data(), sizeof(double) * (size_t)(K + 1) * K);
+  if (eBrg) memcpy(eBrg, ctx->eBrg.data(), sizeof(double) * (K + 1));
+  if (yBrg) memcpy(yBrg, ctx->yBrg.data(), sizeof(double) * (K + 1));
+  if (Rcos) memcpy(Rcos, ctx->Rcos.data(), sizeof(double) * (K + 1));
+  if (Rsin) memcpy(Rsin, ctx->Rsin.data(), sizeof(double) * (K + 1));
+  return 0;
+}
+extern "C" int phb200_dev_elmgmrs(phb200_ctx *ctx, const phb200_step *st) {
+  ENTER(ctx);
+  return phb_elmgmre(ctx, st, 1);
+}
+extern "C" int phb200_dev_solve_sparse(phb200_ctx *ctx, const phb200_step *st, int *iKs, int *lGMRESs, int *ntotGM) {
+  ENTER(ctx);
+  return phb_solve(ctx, st, 1, iKs, lGMRESs, ntotGM);
+}
+extern "C" int phb200_dev_sparseap(phb200_ctx *ctx, int slot) {
+  ENTER(ctx);
+  if (slot < 0 || slot >= ctx->c.Kspace) return fail("dev_sparseap", "slot out of range");
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  double *src = ctx->d_uBrg + (size_t)slot * n5, *dst = src + n5;
+  PHB_CHECK(cudaMemcpyAsync(dst, src, sizeof(double) * n5, cudaMemcpyDeviceToDevice, ctx->stream));
+  PHB_TRY(phb_sparseap(ctx, dst));
+  return phb_bc3per(ctx, dst, 5);
 }
 
 // ---- finer seams on host arrays: stage through d_temp / d_BDiag ------------

@@ -361,12 +361,14 @@ __device__ __forceinline__ int bc_elim_mask(int ibc) {
   return m;
 }
 
-template <int TILE_E, int NQ, bool LHS>
+// LHS: 0 residual only, 1 EBE tiles (ElmGMRe), 2 scatter into lhsK (ElmGMRs + fillsparseC)
+template <int TILE_E, int NQ, int LHS>
 __global__ void __launch_bounds__(TILE_E * 4) k_asigmr_tet(
     int numel, size_t numel_pad, int nshg, int numnp, int ntiles, const int *__restrict__ ien,
     const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ ac,
     const double *__restrict__ qres, const int *__restrict__ iBC, const double *__restrict__ BC,
-    double *__restrict__ res, double *__restrict__ BDiag, double *__restrict__ EG) {
+    double *__restrict__ res, double *__restrict__ BDiag, double *__restrict__ EG, const int *__restrict__ eloc,
+    double *__restrict__ lhsK) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AsmSmem<TILE_E, NQ> &sm = *reinterpret_cast<AsmSmem<TILE_E, NQ> *>(smem_raw);
   const int tid = threadIdx.x;
@@ -752,8 +754,19 @@ __global__ void __launch_bounds__(TILE_E * 4) k_asigmr_tet(
             }
           }
         }
-        // coalesced store of the block (also for padding lanes: zeros)
-        {
+        if (LHS == 2) {
+          // fillsparseC (fillsparse.f:66-126): lhsK(f+5g, k) += EGmass(e, r+f, s+g); the block index k
+          // comes from the precomputed sparseloc map
+          if (ge < numel) {
+            const int k = eloc[(size_t)(4 * a + b) * numel_pad + ge];
+            double *blk = lhsK + (size_t)25 * k;
+#pragma unroll
+            for (int n = 0; n < 5; n++)
+#pragma unroll
+              for (int m = 0; m < 5; m++) atomicAdd(blk + m + 5 * n, acc[m][n]);
+          }
+        } else {
+          // coalesced store of the block (also for padding lanes: zeros)
           const size_t gtile = (size_t)ge / EG_TILE;
           const int gl = ge % EG_TILE;
           double *base = EG + gtile * (size_t)(400 * EG_TILE) + gl;
@@ -1060,7 +1073,7 @@ int phb_bc3per(phb200_ctx *ctx, double *d_r, int n) {
   return 0;
 }
 
-template <int TILE_E, int NQ, bool LHS>
+template <int TILE_E, int NQ, int LHS>
 static int launch_asigmr(phb200_ctx *ctx) {
   const phb200_common &c = ctx->c;
   size_t smem = sizeof(AsmSmem<TILE_E, NQ>);
@@ -1082,13 +1095,13 @@ static int launch_asigmr(phb200_ctx *ctx) {
   KScope ks(ctx, KC_ASM);
   kern<<<grid, TILE_E * 4, smem, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, c.nshg, c.numnp, ntiles, ctx->d_ien,
                                                 ctx->d_x, ctx->d_y, ctx->d_ac, ctx->d_qres, ctx->d_iBC, ctx->d_BC,
-                                                ctx->d_res, ctx->d_BDiag, ctx->d_EG);
+                                                ctx->d_res, ctx->d_BDiag, ctx->d_EG, ctx->d_eloc, ctx->d_lhsK);
   PHB_CHECK(cudaGetLastError());
   return 0;
 }
 
 // ElmGMRe (elmgmr.f:1-274) on the resident state
-int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st) {
+int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   const phb200_common &c = ctx->c;
   const int nshg = c.nshg;
   cudaStream_t s = ctx->stream;
@@ -1128,16 +1141,32 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st) {
   }
   PHB_CHECK(cudaMemsetAsync(ctx->d_res, 0, sizeof(double) * 5 * (size_t)nshg, s));
   if (st->iprec != 0) PHB_CHECK(cudaMemsetAsync(ctx->d_BDiag, 0, sizeof(double) * 25 * (size_t)nshg, s));
+  if (st->lhs == 1 && sparse) {
+    if (!ctx->d_lhsK) {
+      fprintf(stderr, "phb200: elmgmrs: no CSR structure (call phb200_set_sparse first)\n");
+      return 1;
+    }
+    PHB_CHECK(cudaMemsetAsync(ctx->d_lhsK, 0, sizeof(double) * 25 * (size_t)ctx->nnz_tot, s));
+  }
+  if (st->lhs == 1 && !sparse && !ctx->d_EG) {  // EBE storage on first use (3200 B/element)
+    PHB_CHECK(cudaMalloc(&ctx->d_EG, sizeof(double) * ctx->numel_pad * 400));
+    PHB_CHECK(cudaMemsetAsync(ctx->d_EG, 0, sizeof(double) * ctx->numel_pad * 400, s));
+  }
   if (ctx->numel_tet > 0) {
+    const int mode = (st->lhs == 1) ? (sparse ? 2 : 1) : 0;
     if (nq == 4) {
-      if (st->lhs == 1) PHB_TRY((launch_asigmr<32, 4, true>(ctx)));
-      else PHB_TRY((launch_asigmr<32, 4, false>(ctx)));
+      if (mode == 1) PHB_TRY((launch_asigmr<32, 4, 1>(ctx)));
+      else if (mode == 2) PHB_TRY((launch_asigmr<32, 4, 2>(ctx)));
+      else PHB_TRY((launch_asigmr<32, 4, 0>(ctx)));
     } else {
-      if (st->lhs == 1) PHB_TRY((launch_asigmr<32, 1, true>(ctx)));
-      else PHB_TRY((launch_asigmr<32, 1, false>(ctx)));
+      if (mode == 1) PHB_TRY((launch_asigmr<32, 1, 1>(ctx)));
+      else if (mode == 2) PHB_TRY((launch_asigmr<32, 1, 2>(ctx)));
+      else PHB_TRY((launch_asigmr<32, 1, 0>(ctx)));
     }
   }
-  if (st->lhs == 1) ctx->have_lhs = true;
+  if (st->lhs == 1) {
+    if (sparse) ctx->have_lhs_sparse = true; else ctx->have_lhs = true;
+  }
   if (ctx->numelb > 0) {  // boundary blocks (elmgmr.f:180-222); flxID = 0 first (elmgmr.f:122)
     PHB_CHECK(cudaMemsetAsync(ctx->d_aerfrc + 4, 0, sizeof(double) * 10 * 1001, s));
     KScope ks(ctx, KC_ASM);

@@ -72,13 +72,23 @@ struct phb200_ctx {
   double *d_res, *d_rmes, *d_Dy, *d_temp;  // [5][nshg]
   double *d_BDiag;               // [25][nshg]  BDiag(nshg,5,5)
   double *d_BDtmp;               // scratch copy for i3pre's commu 'out'
-  double *d_EG;                  // tiles, see eg_index
+  double *d_EG;                  // tiles, see eg_index (allocated on first EBE lhs=1 call)
+  // ---- block-CSR flavour (SolGMRs)
+  int nnz_tot;
+  int *d_colm, *d_rowp;          // 0-based CSR: colm[nshg+1] row pointers, rowp[nnz_tot] column ids
+  int *d_rowofblk;               // row of every block
+  int *d_eloc;                   // [16][numel_pad] CSR block of element block (a,b)
+  double *d_lhsK;                // [nnz_tot][25]  lhsK(25,nnz_tot)
+  bool have_lhs_sparse;
   double *d_uBrg;                // [Kspace+1][5][nshg]
   double *d_dots;                // device scalars for fused MGS
   double *h_dots;                // pinned
   double *d_scratch;             // L2 flush / fp64 peak
   size_t scratch_bytes;
   bool have_lhs;                 // EGmass/BDiag hold a (preconditioned) system
+  // host copies of the block structure (pointers stay caller-owned, as mien(iblk)%p does)
+  std::vector<int> h_lcblk;
+  std::vector<const int *> h_mien;
   // host-side Hessenberg work (solgmr.f:46-49)
   std::vector<double> HBrg, eBrg, yBrg, Rcos, Rsin;
   // ---- instrumentation
@@ -113,7 +123,7 @@ struct KScope {
 // assembly.cu
 int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, const double *shpb,
                       const double *shglb);
-int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st);
+int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse = 0);
 // solver.cu
 int phb_i3lu(phb200_ctx *ctx, double *d_Diag, double *d_r, int code);
 int phb_i3pre(phb200_ctx *ctx);
@@ -121,8 +131,14 @@ int phb_au1gmr(phb200_ctx *ctx, double *d_u);
 int phb_bc3per(phb200_ctx *ctx, double *d_r, int n);
 int phb_zero_slaves(phb200_ctx *ctx, double *d_r, int n, int identity);
 int phb_sumgat_dev(phb200_ctx *ctx, const double *d_u, size_t len, double *out);
-int phb_solve(phb200_ctx *ctx, const phb200_step *st, int *iKs, int *lGMRES, int *ntotGM);
+int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs, int *lGMRES, int *ntotGM);
 int phb_fp64_peak(phb200_ctx *ctx, double *tflops);
+// sparse.cu
+int phb_genadj_host(int nshg, int nelblk, const int *lcblk, const int *const *mien, int nnz, int *colm, int *rowp,
+                    int *nnz_tot);
+int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_tot);
+int phb_spsi3pre(phb200_ctx *ctx);
+int phb_sparseap(phb200_ctx *ctx, double *d_u);
 // comm.cu
 int phb_halo_setup(phb200_ctx *ctx, const int *ilwork);
 int phb_commu(phb200_ctx *ctx, double *d_global, int n, int code);

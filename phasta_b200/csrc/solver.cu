@@ -149,6 +149,10 @@ __global__ void __launch_bounds__(128) k_i3pre_tet(int numel, size_t numel_pad, 
 int phb_i3pre(phb200_ctx *ctx) {
   const int nshg = ctx->c.nshg;
   const double *BD = ctx->d_BDiag;
+  if (!ctx->d_EG) {
+    fprintf(stderr, "phb200: i3pre: no EBE LHS has been assembled (lhs=1 call needed first)\n");
+    return 1;
+  }
   if (ctx->c.numpe > 1) {
     // BDiag = BDtmp; commu(BDiag,'out') (i3pre.f:31-36): slaves need the master's LU
     PHB_CHECK(cudaMemcpyAsync(ctx->d_BDtmp, ctx->d_BDiag, sizeof(double) * 25 * (size_t)nshg,
@@ -368,7 +372,10 @@ static int dot_host(phb200_ctx *ctx, size_t n, double *a, const double *b, doubl
 // ---------------------------------------------------------------------------
 // SolGMRe after ElmGMRe (solgmr.f:83-347)
 // ---------------------------------------------------------------------------
-int phb_solve(phb200_ctx *ctx, const phb200_step *st, int *iKs_out, int *lGMRES_out, int *ntotGM) {
+// sparse=1: SolGMRs (solgmr.f:440-744): commu(BDiag,'out') after LU_Fact (:473-475), Spsi3pre only when
+// lhs=1 (:495), SparseAp, convergence also needs iKs >= minIters (:669), and the restart recomputation is
+// keyed on the stale EBE counter so it never runs (:526).
+int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, int *lGMRES_out, int *ntotGM) {
   const phb200_common &c = ctx->c;
   const int nshg = c.nshg, Kspace = c.Kspace, nGMRES = c.nGMRES;
   const size_t n = (size_t)5 * nshg;
@@ -380,10 +387,19 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int *iKs_out, int *lGMRES_
 #define H(a, b) HBrg[((a)-1) + (size_t)(Kspace + 1) * ((b)-1)]
   // rmes = res (solgmr.f:83)
   PHB_CHECK(cudaMemcpyAsync(ctx->d_rmes, ctx->d_res, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-  if (st->iprec != 0) PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, nullptr, 0));
+  auto Ap = [&](double *v) { return sparse ? phb_sparseap(ctx, v) : phb_au1gmr(ctx, v); };
+  const int minIters = sparse ? c.minIters : 0;
+  if (st->iprec != 0) {
+    PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, nullptr, 0));
+    if (sparse) PHB_TRY(phb_commu(ctx, ctx->d_BDiag, 25, 1));
+  }
   PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, ctx->d_res, 1));
   PHB_CHECK(cudaMemsetAsync(ctx->d_Dy, 0, sizeof(double) * n, s));
-  PHB_TRY(phb_i3pre(ctx));  // unconditional in SolGMRe (solgmr.f:112)
+  if (sparse) {
+    if (st->lhs == 1) PHB_TRY(phb_spsi3pre(ctx));
+  } else {
+    PHB_TRY(phb_i3pre(ctx));  // unconditional in SolGMRe (solgmr.f:112)
+  }
   PHB_CHECK(cudaMemcpyAsync(Uk(1), ctx->d_res, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
   double summed = 0.0;
   PHB_TRY(dot_host(ctx, n, ctx->d_res, ctx->d_res, &summed));
@@ -394,10 +410,10 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int *iKs_out, int *lGMRES_
     const double epsnrm = st->etol * unorm;
     for (int mGMRES = 1; mGMRES <= nGMRES; mGMRES++) {
       lGMRES = mGMRES - 1;
-      if (lGMRES > 0) {  // restart: R - A x (solgmr.f:149-178)
+      if (lGMRES > 0 && !sparse) {  // restart: R - A x (solgmr.f:149-178)
         double *tmp = Uk(Kspace + 1);  // free slot at restart time
         PHB_CHECK(cudaMemcpyAsync(tmp, ctx->d_Dy, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-        PHB_TRY(phb_au1gmr(ctx, tmp));
+        PHB_TRY(Ap(tmp));
         PHB_TRY(phb_bc3per(ctx, tmp, 5));
         {
           KScope ks(ctx, KC_BLAS);
@@ -418,7 +434,7 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int *iKs_out, int *lGMRES_
         iKs = iK;
         double *w = Uk(iKs + 1);
         PHB_CHECK(cudaMemcpyAsync(w, Uk(iKs), sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-        PHB_TRY(phb_au1gmr(ctx, w));
+        PHB_TRY(Ap(w));
         PHB_TRY(phb_bc3per(ctx, w, 5));
         // modified Gram-Schmidt, beta_j stay on the device (d_dots[j]) unless
         // an allreduce is needed between steps
@@ -457,7 +473,7 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int *iKs_out, int *lGMRES_
         eBrg[iKs] = -Rsin[iKs - 1] * eBrg[iKs - 1] + Rcos[iKs - 1] * eBrg[iKs];
         eBrg[iKs - 1] = tmp;
         *ntotGM += 1;
-        if (fabs(eBrg[iKs]) <= epsnrm) break;
+        if (fabs(eBrg[iKs]) <= epsnrm && iKs >= minIters) break;
       }
       for (int jK = iKs; jK >= 1; jK--) {
         yBrg[jK - 1] = eBrg[jK - 1] / H(jK, jK);

@@ -1,0 +1,269 @@
+// sparse.cu -- the block-CSR flavour of the path (SolGMRs): CSR structure
+// (genadj), element -> CSR block map (sparseloc once, not per assembly),
+// Spsi3pre and SparseAp.
+//
+// Reference: phSolver/common/genadj.f:1-82, asadj.f:1-59,
+// common/fillsparse.f:66-126,236-271, compressible/spsi3pre.f:41-221,
+// compressible/sparseap.f:26-135.
+#include "ctx.h"
+#include <algorithm>
+#include <cstring>
+
+// ---------------------------------------------------------------------------
+// genadj: colm(nshg+1) 1-based row pointers, rowp ascending unique neighbour
+// ids incl. self.  The reference grows per-node lists with an O(deg^2) search
+// and selection-sorts them (asadj.f:24-50, genadj.f:50-62); the result is the
+// sorted unique adjacency, built here from a node->element map in O(N deg log deg).
+// ---------------------------------------------------------------------------
+int phb_genadj_host(int nshg, int nelblk, const int *lcblk, const int *const *mien, int nnz, int *colm, int *rowp,
+                    int *nnz_tot) {
+  std::vector<int> cnt((size_t)nshg + 1, 0);
+  for (int b = 0; b < nelblk; b++) {
+    const int *lc = lcblk + 10 * b;
+    int npro = lc[10] - lc[0], nshl = lc[9];
+    for (int a = 0; a < nshl; a++)
+      for (int e = 0; e < npro; e++) {
+        int v = std::abs(mien[b][e + (size_t)npro * a]);
+        if (v < 1 || v > nshg) return 1;
+        cnt[v]++;
+      }
+  }
+  std::vector<size_t> start((size_t)nshg + 2, 0);
+  for (int i = 1; i <= nshg; i++) start[i + 1] = start[i] + cnt[i];
+  // node -> (block, element) incidence
+  std::vector<int> inc_b(start[nshg + 1]), inc_e(start[nshg + 1]);
+  std::vector<size_t> fill(start.begin(), start.end());
+  for (int b = 0; b < nelblk; b++) {
+    const int *lc = lcblk + 10 * b;
+    int npro = lc[10] - lc[0], nshl = lc[9];
+    for (int a = 0; a < nshl; a++)
+      for (int e = 0; e < npro; e++) {
+        int v = std::abs(mien[b][e + (size_t)npro * a]);
+        inc_b[fill[v]] = b;
+        inc_e[fill[v]] = e;
+        fill[v]++;
+      }
+  }
+  colm[0] = 1;
+  size_t icnt = 0;
+  std::vector<int> tmp;
+  for (int i = 1; i <= nshg; i++) {
+    tmp.clear();
+    for (size_t t = start[i]; t < start[i + 1]; t++) {
+      int b = inc_b[t], e = inc_e[t];
+      const int *lc = lcblk + 10 * b;
+      int npro = lc[10] - lc[0], nshl = lc[9];
+      for (int a = 0; a < nshl; a++) tmp.push_back(std::abs(mien[b][e + (size_t)npro * a]));
+    }
+    std::sort(tmp.begin(), tmp.end());
+    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+    if (icnt + tmp.size() > (size_t)nnz * nshg) {
+      fprintf(stderr, "phb200: genadj: increase nnz (needs more than %d per node)\n", nnz);
+      return 1;
+    }
+    for (int v : tmp) rowp[icnt++] = v;
+    colm[i] = (int)icnt + 1;
+  }
+  *nnz_tot = (int)icnt;
+  return 0;
+}
+
+// sparseloc (fillsparse.f:236-271) for every (element, a, b): CSR block index
+__global__ void k_eloc(int numel, size_t numel_pad, const int *__restrict__ ien, const int *__restrict__ colm,
+                       const int *__restrict__ rowp, int *__restrict__ eloc) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= numel) return;
+  int nd[4];
+  for (int a = 0; a < 4; a++) nd[a] = ien[(size_t)a * numel_pad + e];
+  for (int a = 0; a < 4; a++) {
+    const int c0 = colm[nd[a]], n = colm[nd[a] + 1] - c0;
+    for (int b = 0; b < 4; b++) {
+      const int target = nd[b];
+      int lo = 0, hi = n;  // rowp[c0+lo] <= target < rowp[c0+hi]
+      while (hi - lo > 1) {
+        int mid = (hi + lo) >> 1;
+        if (rowp[c0 + mid] > target) hi = mid; else lo = mid;
+      }
+      eloc[(size_t)(4 * a + b) * numel_pad + e] = c0 + lo;
+    }
+  }
+}
+
+int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_tot) {
+  const int nshg = ctx->c.nshg;
+  if (colm[0] != 1 || colm[nshg] - 1 != nnz_tot) {
+    fprintf(stderr, "phb200: set_sparse: colm is not a 1-based row pointer array ending at nnz_tot+1\n");
+    return 1;
+  }
+  std::vector<int> c0((size_t)nshg + 1), r0((size_t)nnz_tot), rob((size_t)nnz_tot);
+  for (int i = 0; i <= nshg; i++) c0[i] = colm[i] - 1;
+  for (int i = 0; i < nshg; i++)
+    for (int k = c0[i]; k < c0[i + 1]; k++) {
+      r0[k] = rowp[k] - 1;
+      rob[k] = i;
+      if (r0[k] < 0 || r0[k] >= nshg) {
+        fprintf(stderr, "phb200: set_sparse: rowp entry out of range\n");
+        return 1;
+      }
+    }
+  auto F = [](void *p) { if (p) cudaFree(p); };
+  F(ctx->d_colm); F(ctx->d_rowp); F(ctx->d_rowofblk); F(ctx->d_lhsK); F(ctx->d_eloc);
+  ctx->nnz_tot = nnz_tot;
+  PHB_CHECK(cudaMalloc(&ctx->d_colm, sizeof(int) * ((size_t)nshg + 1)));
+  PHB_CHECK(cudaMalloc(&ctx->d_rowp, sizeof(int) * (size_t)std::max(nnz_tot, 1)));
+  PHB_CHECK(cudaMalloc(&ctx->d_rowofblk, sizeof(int) * (size_t)std::max(nnz_tot, 1)));
+  PHB_CHECK(cudaMalloc(&ctx->d_lhsK, sizeof(double) * 25 * (size_t)std::max(nnz_tot, 1)));
+  PHB_CHECK(cudaMalloc(&ctx->d_eloc, sizeof(int) * 16 * ctx->numel_pad));
+  PHB_CHECK(cudaMemcpy(ctx->d_colm, c0.data(), sizeof(int) * c0.size(), cudaMemcpyHostToDevice));
+  PHB_CHECK(cudaMemcpy(ctx->d_rowp, r0.data(), sizeof(int) * r0.size(), cudaMemcpyHostToDevice));
+  PHB_CHECK(cudaMemcpy(ctx->d_rowofblk, rob.data(), sizeof(int) * rob.size(), cudaMemcpyHostToDevice));
+  PHB_CHECK(cudaMemset(ctx->d_eloc, 0, sizeof(int) * 16 * ctx->numel_pad));
+  if (ctx->numel_tet > 0) {
+    k_eloc<<<(ctx->numel_tet + 127) / 128, 128, 0, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, ctx->d_ien,
+                                                                  ctx->d_colm, ctx->d_rowp, ctx->d_eloc);
+    ctx->launches++;
+    PHB_CHECK(cudaGetLastError());
+  }
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_lhs_sparse = false;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Spsi3pre (spsi3pre.f:41-221): thread per CSR block, lhsK(25,k) column-major
+// block (entry (f,g) at f + 5 g), L from the row node, U from the column node
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_spsi3pre(int nnz_tot, int nshg, const int *__restrict__ rowofblk,
+                                                   const int *__restrict__ rowp, const double *__restrict__ BD,
+                                                   double *lhsK) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz_tot) return;
+  const int i = rowofblk[k], j = rowp[k];
+  double *blk = lhsK + (size_t)25 * k;
+  double B[5][5];  // B[f][g]
+#pragma unroll
+  for (int g = 0; g < 5; g++)
+#pragma unroll
+    for (int f = 0; f < 5; f++) B[f][g] = blk[f + 5 * g];
+#define LI(r, c) __ldg(BD + (size_t)nshg * (((r)-1) + 5 * ((c)-1)) + i)
+  {
+    const double l21 = LI(2, 1), l31 = LI(3, 1), l32 = LI(3, 2), l41 = LI(4, 1), l42 = LI(4, 2), l43 = LI(4, 3),
+                 l51 = LI(5, 1), l52 = LI(5, 2), l53 = LI(5, 3), l54 = LI(5, 4);
+#pragma unroll
+    for (int g = 0; g < 5; g++) {
+      B[1][g] = B[1][g] - l21 * B[0][g];
+      B[2][g] = B[2][g] - l31 * B[0][g] - l32 * B[1][g];
+      B[3][g] = B[3][g] - l41 * B[0][g] - l42 * B[1][g] - l43 * B[2][g];
+      B[4][g] = B[4][g] - l51 * B[0][g] - l52 * B[1][g] - l53 * B[2][g] - l54 * B[3][g];
+    }
+  }
+#undef LI
+#define UJ(r, c) __ldg(BD + (size_t)nshg * (((r)-1) + 5 * ((c)-1)) + j)
+  {
+    const double u11 = UJ(1, 1), u22 = UJ(2, 2), u33 = UJ(3, 3), u44 = UJ(4, 4), u55 = UJ(5, 5);
+    const double u12 = UJ(1, 2), u13 = UJ(1, 3), u14 = UJ(1, 4), u15 = UJ(1, 5), u23 = UJ(2, 3), u24 = UJ(2, 4),
+                 u25 = UJ(2, 5), u34 = UJ(3, 4), u35 = UJ(3, 5), u45 = UJ(4, 5);
+#pragma unroll
+    for (int f = 0; f < 5; f++) {
+      B[f][0] = u11 * B[f][0];
+      B[f][1] = u22 * (B[f][1] - u12 * B[f][0]);
+      B[f][2] = u33 * (B[f][2] - u13 * B[f][0] - u23 * B[f][1]);
+      B[f][3] = u44 * (B[f][3] - u14 * B[f][0] - u24 * B[f][1] - u34 * B[f][2]);
+      B[f][4] = u55 * (B[f][4] - u15 * B[f][0] - u25 * B[f][1] - u35 * B[f][2] - u45 * B[f][3]);
+    }
+  }
+#undef UJ
+#pragma unroll
+  for (int g = 0; g < 5; g++)
+#pragma unroll
+    for (int f = 0; f < 5; f++) blk[f + 5 * g] = B[f][g];
+}
+
+int phb_spsi3pre(phb200_ctx *ctx) {
+  if (ctx->nnz_tot <= 0) return 0;
+  KScope ks(ctx, KC_I3PRE);
+  k_spsi3pre<<<(ctx->nnz_tot + 127) / 128, 128, 0, ctx->stream>>>(ctx->nnz_tot, ctx->c.nshg, ctx->d_rowofblk,
+                                                                   ctx->d_rowp, ctx->d_BDiag, ctx->d_lhsK);
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// SparseAp (sparseap.f:45-101): one warp per row; the row's blocks are one
+// contiguous run of 25*nblk doubles, streamed with fully coalesced loads
+// (lane t reads flat entries t, t+32, ...); entry f+5g of block k multiplies
+// p(row(k), g) and lands in q(i, f).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sparseap(int nshg, const int *__restrict__ colm,
+                                                   const int *__restrict__ rowp, const double *__restrict__ lhsK,
+                                                   const double *__restrict__ p, double *__restrict__ q) {
+  const int lane = threadIdx.x & 31;
+  const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (row >= nshg) return;
+  const int k0 = colm[row], k1 = colm[row + 1];
+  const size_t base = (size_t)25 * k0;
+  const int total = 25 * (k1 - k0);
+  double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0;
+  for (int t = lane; t < total; t += 32) {
+    const int kb = t / 25, l = t - 25 * kb;
+    const int g = l / 5, f = l - 5 * g;
+    const int j = __ldg(rowp + k0 + kb);
+    const double v = __ldcs(lhsK + base + t) * __ldg(p + (size_t)nshg * g + j);
+    acc0 += (f == 0) ? v : 0.0;
+    acc1 += (f == 1) ? v : 0.0;
+    acc2 += (f == 2) ? v : 0.0;
+    acc3 += (f == 3) ? v : 0.0;
+    acc4 += (f == 4) ? v : 0.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    acc0 += __shfl_down_sync(0xffffffffu, acc0, o);
+    acc1 += __shfl_down_sync(0xffffffffu, acc1, o);
+    acc2 += __shfl_down_sync(0xffffffffu, acc2, o);
+    acc3 += __shfl_down_sync(0xffffffffu, acc3, o);
+    acc4 += __shfl_down_sync(0xffffffffu, acc4, o);
+  }
+  if (lane == 0) {
+    q[row] = acc0;
+    q[(size_t)nshg + row] = acc1;
+    q[(size_t)nshg * 2 + row] = acc2;
+    q[(size_t)nshg * 3 + row] = acc3;
+    q[(size_t)nshg * 4 + row] = acc4;
+  }
+}
+
+__global__ void k_iper_copy5(int n, const int *__restrict__ slaves, const int *__restrict__ iper, int nshg,
+                             double *u) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n * 5) return;
+  int j = slaves[t % n], k = t / n;
+  u[(size_t)nshg * k + j] = u[(size_t)nshg * k + iper[j]];
+}
+
+// p <- A p in place (uses d_temp as q)
+int phb_sparseap(phb200_ctx *ctx, double *d_u) {
+  const int nshg = ctx->c.nshg;
+  cudaStream_t s = ctx->stream;
+  if (!ctx->have_lhs_sparse) {
+    fprintf(stderr, "phb200: sparseap: no sparse LHS has been assembled (elmgmrs with lhs=1 first)\n");
+    return 1;
+  }
+  PHB_TRY(phb_commu(ctx, d_u, 5, 1));
+  if (ctx->n_perslave) {
+    KScope ks(ctx, KC_NODE);
+    int tot = ctx->n_perslave * 5;
+    k_iper_copy5<<<(tot + 255) / 256, 256, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, d_u);
+    PHB_CHECK(cudaGetLastError());
+  }
+  {
+    KScope ks(ctx, KC_AP);
+    size_t threads = (size_t)nshg * 32;
+    k_sparseap<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(nshg, ctx->d_colm, ctx->d_rowp, ctx->d_lhsK, d_u,
+                                                                 ctx->d_temp);
+    PHB_CHECK(cudaGetLastError());
+  }
+  PHB_CHECK(cudaMemcpyAsync(d_u, ctx->d_temp, sizeof(double) * 5 * (size_t)nshg, cudaMemcpyDeviceToDevice, s));
+  PHB_TRY(phb_commu(ctx, d_u, 5, 0));
+  PHB_TRY(phb_zero_slaves(ctx, d_u, 5, 0));
+  return 0;
+}

@@ -151,6 +151,77 @@ class PhastaGPU:
              "elmgmre")
         return dict(res=res, BDiag=BD, EGmass=EG, qres=qres)
 
+    # ------------------------------------------------------ block-CSR flavour
+    def genadj(self, nnz=35):
+        """common/genadj.f: returns (colm, rowp, nnz_tot) with the reference's
+        1-based conventions and hands them to the device (set_sparse)."""
+        nshg = self.part.nshg
+        colm = np.zeros(nshg + 1, dtype=np.int32)
+        rowp = np.zeros(nnz * nshg, dtype=np.int32)
+        ntot = C.c_int(0)
+        _chk(self.L.phb200_genadj(self.ctx, int(nnz), _p(colm, C.c_int), _p(rowp, C.c_int), C.byref(ntot)),
+             "genadj")
+        self.colm, self.rowp, self.nnz_tot = colm, rowp, ntot.value
+        self.set_sparse(colm, rowp, ntot.value)
+        return colm, rowp[:ntot.value], ntot.value
+
+    def set_sparse(self, colm, rowp, nnz_tot):
+        colm = np.ascontiguousarray(colm, dtype=np.int32)
+        rowp = np.ascontiguousarray(rowp, dtype=np.int32)
+        self.nnz_tot = int(nnz_tot)
+        _chk(self.L.phb200_set_sparse(self.ctx, _p(colm, C.c_int), _p(rowp, C.c_int), int(nnz_tot)), "set_sparse")
+
+    def ElmGMRs(self, y, ac, *, step=None, want_lhsk=False):
+        """elmgmr.f:280-612 (+ fillsparseC).  Returns dict(res, BDiag, lhsK?)."""
+        st = step or self.step()
+        y = np.asfortranarray(y, dtype=np.float64)
+        ac = np.asfortranarray(ac, dtype=np.float64)
+        res = self._vec()
+        BD = np.zeros((self.part.nshg, 5, 5), order="F") if st.iprec else None
+        K = np.zeros((25, self.nnz_tot), order="F") if (want_lhsk and st.lhs == 1) else None
+        _chk(self.L.phb200_elmgmrs(self.ctx, _p(y), _p(ac), C.byref(st), _p(res), _p(BD), _p(K)), "elmgmrs")
+        return dict(res=res, BDiag=BD, lhsK=K)
+
+    def Spsi3pre(self, want_lhsk=False):
+        K = np.zeros((25, self.nnz_tot), order="F") if want_lhsk else None
+        _chk(self.L.phb200_spsi3pre(self.ctx, _p(K)), "spsi3pre")
+        return K
+
+    def SparseAp(self, p):
+        """sparseap.f:1-138, in place on p(nshg,5)."""
+        assert p.flags.f_contiguous and p.shape == (self.part.nshg, 5)
+        _chk(self.L.phb200_sparseap(self.ctx, _p(p)), "sparseap")
+        return p
+
+    def SolGMRs(self, y, ac, yold=None, acold=None, *, step=None):
+        """solgmr.f:368-744 with the CSR structure given to set_sparse/genadj."""
+        st = step or self.step()
+        y = np.asfortranarray(y, dtype=np.float64)
+        ac = np.asfortranarray(ac, dtype=np.float64)
+        res, rmes, Dy = self._vec(), self._vec(), self._vec()
+        iKs, lG, ntot = C.c_int(0), C.c_int(0), C.c_int(self.ntotGM)
+        _chk(self.L.phb200_solgmrs(self.ctx, _p(y), _p(ac), C.byref(st), _p(res), _p(rmes), None, _p(Dy),
+                                   _p(self.HBrg), _p(self.eBrg), _p(self.yBrg), _p(self.Rcos), _p(self.Rsin),
+                                   C.byref(iKs), C.byref(lG), C.byref(ntot)), "solgmrs")
+        self.iKs, self.lGMRES, self.ntotGM = iKs.value, lG.value, ntot.value
+        self.rmes = rmes
+        return res, Dy
+
+    def dev_elmgmrs(self, step=None):
+        st = step or self.step()
+        _chk(self.L.phb200_dev_elmgmrs(self.ctx, C.byref(st)), "dev_elmgmrs")
+
+    def dev_solve_sparse(self, step=None):
+        st = step or self.step()
+        iKs, lG, ntot = C.c_int(0), C.c_int(0), C.c_int(self.ntotGM)
+        _chk(self.L.phb200_dev_solve_sparse(self.ctx, C.byref(st), C.byref(iKs), C.byref(lG), C.byref(ntot)),
+             "dev_solve_sparse")
+        self.iKs, self.lGMRES, self.ntotGM = iKs.value, lG.value, ntot.value
+        return self.iKs
+
+    def dev_sparseap(self, slot=0):
+        _chk(self.L.phb200_dev_sparseap(self.ctx, int(slot)), "dev_sparseap")
+
     def i3LU(self, Diag, r, code):
         """i3lu.f:1-181; code 'LU_Fact'|'forward'|'backward'|'product'."""
         ic = {"LU_Fact": 0, "forward": 1, "backward": 2, "product": 3}[code.strip()]

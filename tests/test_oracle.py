@@ -183,3 +183,28 @@ def test_boundary_flux_closes_the_patch_test():
     assert (np.abs(o.parts[0].res).max(axis=0) / scale).max() < 1e-13
     nb = sum(b.shape[0] for b in parts[0].mienb)
     assert nb == 2 * 2 * (5 * 4 + 5 * 3 + 4 * 3)
+
+
+def test_genadj_equals_scipy_csr_and_sparse_equals_ebe():
+    import scipy.sparse as sp
+    case = make_case(6, 5, 4, bc="channel", etol=1e-6, Kspace=40, minIters=0)
+    o = make_oracle(case)
+    (ntot,) = o.genadj()
+    mp = case[2][0]
+    ien = mp.ien_all() - 1
+    r = np.repeat(ien, 4, axis=1).ravel()
+    c = np.tile(ien, (1, 4)).ravel()
+    A = sp.coo_matrix((np.ones(r.size), (r, c)), shape=(mp.nshg, mp.nshg)).tocsr()
+    A.sort_indices()
+    assert np.array_equal(A.indptr + 1, o.parts[0].colm)
+    assert np.array_equal(A.indices + 1, o.parts[0].rowp) and ntot == A.nnz
+    iks_s, _ = o.SolGMRs()
+    o2 = make_oracle(case)
+    iks_e, _ = o2.SolGMRe()
+    assert iks_s == iks_e
+    assert rel_l2(o.parts[0].Dy, o2.parts[0].Dy) < 1e-12
+    u = np.asfortranarray(np.random.default_rng(0).standard_normal((mp.nshg, 5))[mp.iper - 1])
+    a, b = u.copy(order="F"), u.copy(order="F")
+    o.SparseAp([a])
+    o2.Au1GMR([b])
+    assert rel_l2(a, b) < 1e-13
