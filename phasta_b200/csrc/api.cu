@@ -159,6 +159,7 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   PHB_TRY(dev_alloc(&ctx->d_ac, n5));
   PHB_TRY(dev_alloc(&ctx->d_qres, (size_t)12 * nshg));
   PHB_TRY(dev_alloc(&ctx->d_rmass, (size_t)nshg));
+  PHB_TRY(dev_alloc(&ctx->d_nodeaos, (size_t)26 * nshg));
   PHB_TRY(dev_alloc(&ctx->d_res, n5));
   PHB_TRY(dev_alloc(&ctx->d_rmes, n5));
   PHB_TRY(dev_alloc(&ctx->d_Dy, n5));
@@ -200,7 +201,8 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
                   ctx->d_slave_nodes, ctx->d_sendbuf, ctx->d_recvbuf, ctx->d_y, ctx->d_ac, ctx->d_qres,
                   ctx->d_rmass, ctx->d_res, ctx->d_rmes, ctx->d_Dy, ctx->d_temp, ctx->d_BDiag, ctx->d_BDtmp,
                   ctx->d_EG, ctx->d_uBrg, ctx->d_dots, ctx->d_scratch, ctx->d_ienb, ctx->d_iBCB,
-                  ctx->d_BCB, ctx->d_aerfrc, ctx->d_colm, ctx->d_rowp, ctx->d_rowofblk, ctx->d_eloc, ctx->d_lhsK};
+                  ctx->d_BCB, ctx->d_aerfrc, ctx->d_colm, ctx->d_rowp, ctx->d_rowofblk, ctx->d_eloc, ctx->d_lhsK,
+                  ctx->d_nodeaos};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (ctx->h_dots) cudaFreeHost(ctx->h_dots);

@@ -283,6 +283,31 @@ __global__ void k_qpbc_divide(int nshg, double *qres, double *rmass) {
   for (int k = 0; k < 12; k++) qres[(size_t)nshg * k + i] *= r;
 }
 
+// node records for the element gathers: [node][NREC] = x(3), Y{p,u1,u2,u3,T}(5), Y,t(5), q(12), pad.
+// One 208-byte contiguous record per node (13 16-byte loads) instead of 25 strided 8-byte gathers.
+#define NREC 26
+__global__ void k_pack_nodes(int nshg, int numnp, const double *__restrict__ x, const double *__restrict__ y,
+                             const double *__restrict__ ac, const double *__restrict__ qres, int with_q,
+                             double *__restrict__ aos) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int node = t / NREC, f = t - node * NREC;
+  if (node >= nshg) return;
+  double v = 0.0;
+  if (f < 3) v = x[(size_t)numnp * f + node];
+  else if (f < 8) {  // localy order {p,u1,u2,u3,T} (localy.f:47-72)
+    const int m = f - 3;
+    const int src = (m == 0) ? 3 : (m == 4 ? 4 : m - 1);
+    v = y[(size_t)nshg * src + node];
+  } else if (f < 13) {
+    const int m = f - 8;
+    const int src = (m == 0) ? 3 : (m == 4 ? 4 : m - 1);
+    v = ac[(size_t)nshg * src + node];
+  } else if (f < 25) {
+    v = with_q ? qres[(size_t)nshg * (f - 13) + node] : 0.0;
+  }
+  aos[(size_t)node * NREC + f] = v;
+}
+
 // ---------------------------------------------------------------------------
 // fused AsIGMR + e3 + BDiag extraction + bc3LHS for linear tets
 // ---------------------------------------------------------------------------
@@ -363,10 +388,9 @@ __device__ __forceinline__ int bc_elim_mask(int ibc) {
 
 // LHS: 0 residual only, 1 EBE tiles (ElmGMRe), 2 scatter into lhsK (ElmGMRs + fillsparseC)
 template <int TILE_E, int NQ, int LHS>
-__global__ void __launch_bounds__(TILE_E * 4) k_asigmr_tet(
+__global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
     int numel, size_t numel_pad, int nshg, int numnp, int ntiles, const int *__restrict__ ien,
-    const double *__restrict__ x, const double *__restrict__ y, const double *__restrict__ ac,
-    const double *__restrict__ qres, const int *__restrict__ iBC, const double *__restrict__ BC,
+    const double *__restrict__ aos, const int *__restrict__ iBC, const double *__restrict__ BC,
     double *__restrict__ res, double *__restrict__ BDiag, double *__restrict__ EG, const int *__restrict__ eloc,
     double *__restrict__ lhsK) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -384,8 +408,16 @@ __global__ void __launch_bounds__(TILE_E * 4) k_asigmr_tet(
       int nd[4];
 #pragma unroll
       for (int a = 0; a < 4; a++) nd[a] = live ? ien[(size_t)a * numel_pad + e] : 0;
-      double xl[4][3];
-      gather_x(x, numnp, nd, xl);
+      // node records: 13 x 16-byte loads per node
+      const double2 *rec[4];
+      double xl[4][3], pn[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        rec[a] = reinterpret_cast<const double2 *>(aos + (size_t)nd[a] * NREC);
+        const double2 v0 = __ldg(rec[a]), v1 = __ldg(rec[a] + 1);
+        xl[a][0] = v0.x; xl[a][1] = v0.y; xl[a][2] = v1.x;
+        pn[a] = v1.y;
+      }
       Metric g;
       tet_metric(xl, c_tet.dN[q], c_tet.Qwt[q], g);
       if (q == 0) {
@@ -407,9 +439,10 @@ __global__ void __launch_bounds__(TILE_E * 4) k_asigmr_tet(
       double divq[4] = {0, 0, 0, 0};
 #pragma unroll
       for (int a = 0; a < 4; a++) {
-        double yl[5], al[5];
-        gather_y(y, nshg, nd[a], yl);
-        gather_y(ac, nshg, nd[a], al);
+        const double2 v2 = __ldg(rec[a] + 2), v3 = __ldg(rec[a] + 3), v4 = __ldg(rec[a] + 4),
+                      v5 = __ldg(rec[a] + 5), v6 = __ldg(rec[a] + 6);
+        const double yl[5] = {pn[a], v2.x, v2.y, v3.x, v3.y};
+        const double al[5] = {v4.x, v4.y, v5.x, v5.y, v6.x};
         double Na = c_tet.N[q][a];
 #pragma unroll
         for (int m = 0; m < 5; m++) {
@@ -418,12 +451,14 @@ __global__ void __launch_bounds__(TILE_E * 4) k_asigmr_tet(
 #pragma unroll
           for (int i = 0; i < 3; i++) gr[i][m] += g.shg[a][i] * yl[m];
         }
-        if (c_ph.idiff >= 1) {  // div q (e3ivar.f:374-395)
+        if (c_ph.idiff >= 1) {  // div q (e3ivar.f:374-395): q(4 i + m) at record slot 13 + 4 i + m
+          const double2 v7 = __ldg(rec[a] + 7), v8 = __ldg(rec[a] + 8), v9 = __ldg(rec[a] + 9),
+                        v10 = __ldg(rec[a] + 10), v11 = __ldg(rec[a] + 11), v12 = __ldg(rec[a] + 12);
+          const double ql[12] = {v6.y, v7.x, v7.y, v8.x, v8.y, v9.x, v9.y, v10.x, v10.y, v11.x, v11.y, v12.x};
 #pragma unroll
           for (int i = 0; i < 3; i++)
 #pragma unroll
-            for (int m = 0; m < 4; m++)
-              divq[m] += g.shg[a][i] * __ldg(qres + (size_t)nshg * (4 * i + m) + nd[a]);
+            for (int m = 0; m < 4; m++) divq[m] += g.shg[a][i] * ql[4 * i + m];
         }
       }
       const double pres = Y[0], u1 = Y[1], u2 = Y[2], u3 = Y[3], T = Y[4];
@@ -538,7 +573,10 @@ __global__ void __launch_bounds__(TILE_E * 4) k_asigmr_tet(
         double al[4][5], ub[5] = {0, 0, 0, 0, 0};
 #pragma unroll
         for (int a = 0; a < 4; a++) {
-          gather_y(ac, nshg, nd[a], al[a]);
+          {
+            const double2 v4 = __ldg(rec[a] + 4), v5 = __ldg(rec[a] + 5), v6 = __ldg(rec[a] + 6);
+            al[a][0] = v4.x; al[a][1] = v4.y; al[a][2] = v5.x; al[a][3] = v5.y; al[a][4] = v6.x;
+          }
 #pragma unroll
           for (int m = 0; m < 5; m++) ub[m] += al[a][m];
         }
@@ -618,103 +656,124 @@ __global__ void __launch_bounds__(TILE_E * 4) k_asigmr_tet(
         for (int m = 0; m < 5; m++)
 #pragma unroll
           for (int n = 0; n < 5; n++) acc[m][n] = 0.0;
+        // sums over the quadrature points that feed the viscous block (N_a,i is constant on a
+        // linear tet, so N_a,i K_ij N_b,j W only needs sum_q of mu, lambda, kappa, mu u, lambda u)
+        double smu = 0.0, slam = 0.0, scon = 0.0, smuu[3] = {0, 0, 0}, slamu[3] = {0, 0, 0};
 #pragma unroll 1
         for (int q = 0; q < NQ; q++) {
           const double rho = sm.st[q][S_RHO][le];
           const double u[3] = {sm.st[q][S_U1][le], sm.st[q][S_U2][le], sm.st[q][S_U3][le]};
           const double drdp = sm.st[q][S_DRDP][le], drdT = sm.st[q][S_DRDT][le];
           const double e1p = sm.st[q][S_E1P][le], e3p = sm.st[q][S_E3P][le], e4p = sm.st[q][S_E4P][le];
-          const double tau[5] = {sm.st[q][S_TAU1][le], sm.st[q][S_TAU2][le], sm.st[q][S_TAU2][le],
-                                 sm.st[q][S_TAU2][le], sm.st[q][S_TAU3][le]};
-          const double mu = sm.st[q][S_MU][le], lam = sm.st[q][S_LAM][le], con = sm.st[q][S_CON][le];
+          const double tw1 = W * sm.st[q][S_TAU1][le], tw2 = W * sm.st[q][S_TAU2][le],
+                       tw3 = W * sm.st[q][S_TAU3][le];
+          const double mu = sm.st[q][S_MU][le], lam = sm.st[q][S_LAM][le];
+          smu += mu;
+          slam += lam;
+          scon += sm.st[q][S_CON][le];
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            smuu[r] += mu * u[r];
+            slamu[r] += lam * u[r];
+          }
           const double Na = c_tet.N[q][a], Nb = c_tet.N[q][b];
           const double w[5] = {rho, rho * u[0], rho * u[1], rho * u[2], e3p};
           const double al_a = u[0] * ga[0] + u[1] * ga[1] + u[2] * ga[2];
           const double al_b = u[0] * gb[0] + u[1] * gb[1] + u[2] * gb[2];
-          // Tm = W (At_a tau + Na I),  At_a = al_a A0 + w ghat_a^T + hhat_a e1^T
+          // Tm = W (At_a tau + Na I),  At_a = al_a A0 + w ghat_a^T + hhat_a e1^T; W tau folded per column
           double Tm[5][5];
           {
-            const double c1 = al_a * drdp, c5 = al_a * drdT;
-            // column 1 (pressure)
+            const double c1 = al_a * drdp * tw1, c5 = al_a * drdT * tw3, aR = al_a * rho * tw2;
             Tm[0][0] = c1;
-            Tm[1][0] = c1 * u[0] + ga[0];
-            Tm[2][0] = c1 * u[1] + ga[1];
-            Tm[3][0] = c1 * u[2] + ga[2];
-            Tm[4][0] = al_a * e1p + al_a;
-            // columns 2..4 (velocities)
+            Tm[1][0] = c1 * u[0] + ga[0] * tw1;
+            Tm[2][0] = c1 * u[1] + ga[1] * tw1;
+            Tm[3][0] = c1 * u[2] + ga[2] * tw1;
+            Tm[4][0] = al_a * tw1 * (e1p + 1.0);
 #pragma unroll
             for (int j = 0; j < 3; j++) {
+              const double gj = ga[j] * tw2;
 #pragma unroll
-              for (int m = 0; m < 5; m++) Tm[m][1 + j] = w[m] * ga[j];
-              Tm[1 + j][1 + j] += al_a * rho;
-              Tm[4][1 + j] += al_a * rho * u[j];
+              for (int m = 0; m < 5; m++) Tm[m][1 + j] = w[m] * gj;
+              Tm[1 + j][1 + j] += aR;
+              Tm[4][1 + j] += aR * u[j];
             }
-            // column 5 (temperature)
             Tm[0][4] = c5;
             Tm[1][4] = c5 * u[0];
             Tm[2][4] = c5 * u[1];
             Tm[3][4] = c5 * u[2];
-            Tm[4][4] = al_a * e4p;
+            Tm[4][4] = al_a * e4p * tw3;
+            const double WNa = W * Na;
 #pragma unroll
-            for (int m = 0; m < 5; m++) {
-#pragma unroll
-              for (int n = 0; n < 5; n++) Tm[m][n] *= tau[n];
-              Tm[m][m] += Na;
-            }
-#pragma unroll
-            for (int m = 0; m < 5; m++)
-#pragma unroll
-              for (int n = 0; n < 5; n++) Tm[m][n] *= W;
+            for (int m = 0; m < 5; m++) Tm[m][m] += WNa;
           }
-          // Bm = At_b + c Nb A0 = (al_b + c Nb) A0 + w ghat_b^T + hhat_b e1^T
-          double Bm[5][5];
+          // acc += Tm * Bm,  Bm = At_b + c Nb A0 = (al_b + c Nb) A0 + w ghat_b^T + hhat_b e1^T,
+          // one column of Bm at a time
           {
             const double alp = al_b + c_ph.fct1 * Nb;
-            const double c1 = alp * drdp, c5 = alp * drdT;
-            Bm[0][0] = c1;
-            Bm[1][0] = c1 * u[0] + gb[0];
-            Bm[2][0] = c1 * u[1] + gb[1];
-            Bm[3][0] = c1 * u[2] + gb[2];
-            Bm[4][0] = alp * e1p + al_b;
+            const double c1 = alp * drdp, c5 = alp * drdT, aR = alp * rho;
+            double bc[5];
+            // column 1 (pressure)
+            bc[0] = c1;
+            bc[1] = c1 * u[0] + gb[0];
+            bc[2] = c1 * u[1] + gb[1];
+            bc[3] = c1 * u[2] + gb[2];
+            bc[4] = alp * e1p + al_b;
+#pragma unroll
+            for (int m = 0; m < 5; m++) {
+              double sacc = acc[m][0];
+#pragma unroll
+              for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
+              acc[m][0] = sacc;
+            }
+            // columns 2..4 (velocities)
 #pragma unroll
             for (int j = 0; j < 3; j++) {
 #pragma unroll
-              for (int m = 0; m < 5; m++) Bm[m][1 + j] = w[m] * gb[j];
-              Bm[1 + j][1 + j] += alp * rho;
-              Bm[4][1 + j] += alp * rho * u[j];
+              for (int k = 0; k < 5; k++) bc[k] = w[k] * gb[j];
+              bc[1 + j] += aR;
+              bc[4] += aR * u[j];
+#pragma unroll
+              for (int m = 0; m < 5; m++) {
+                double sacc = acc[m][1 + j];
+#pragma unroll
+                for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
+                acc[m][1 + j] = sacc;
+              }
             }
-            Bm[0][4] = c5;
-            Bm[1][4] = c5 * u[0];
-            Bm[2][4] = c5 * u[1];
-            Bm[3][4] = c5 * u[2];
-            Bm[4][4] = alp * e4p;
-          }
+            // column 5 (temperature)
+            bc[0] = c5;
+            bc[1] = c5 * u[0];
+            bc[2] = c5 * u[1];
+            bc[3] = c5 * u[2];
+            bc[4] = alp * e4p;
 #pragma unroll
-          for (int m = 0; m < 5; m++)
+            for (int m = 0; m < 5; m++) {
+              double sacc = acc[m][4];
 #pragma unroll
-            for (int n = 0; n < 5; n++) {
-              double s = acc[m][n];
-#pragma unroll
-              for (int k = 0; k < 5; k++) s += Tm[m][k] * Bm[k][n];
-              acc[m][n] = s;
+              for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
+              acc[m][4] = sacc;
             }
-          // viscous block N_a,i K_ij N_b,j W (e3visc.f:69-139, e3wmlt.f:154-223)
-          {
-            double V[3][3];
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-              for (int s = 0; s < 3; s++) V[r][s] = W * (mu * ga[s] * gb[r] + lam * ga[r] * gb[s]);
-            const double d0 = W * mu * gagb;
-            V[0][0] += d0; V[1][1] += d0; V[2][2] += d0;
-#pragma unroll
-            for (int r = 0; r < 3; r++)
-#pragma unroll
-              for (int s = 0; s < 3; s++) acc[1 + r][1 + s] += V[r][s];
-#pragma unroll
-            for (int s = 0; s < 3; s++) acc[4][1 + s] += u[0] * V[0][s] + u[1] * V[1][s] + u[2] * V[2][s];
-            acc[4][4] += W * con * gagb;
           }
+        }
+        // viscous block N_a,i K_ij N_b,j W (e3visc.f:69-139, e3wmlt.f:154-223), summed over q in closed form
+        {
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int sdx = 0; sdx < 3; sdx++)
+              acc[1 + r][1 + sdx] += W * (smu * ga[sdx] * gb[r] + slam * ga[r] * gb[sdx]);
+          const double d0 = W * smu * gagb;
+          acc[1][1] += d0;
+          acc[2][2] += d0;
+          acc[3][3] += d0;
+#pragma unroll
+          for (int sdx = 0; sdx < 3; sdx++) {
+            double e = smuu[sdx] * gagb;  // delta_rs part
+#pragma unroll
+            for (int r = 0; r < 3; r++) e += smuu[r] * ga[sdx] * gb[r] + slamu[r] * ga[r] * gb[sdx];
+            acc[4][1 + sdx] += W * e;
+          }
+          acc[4][4] += W * scon * gagb;
         }
         if (ge < numel) {
           const int na = sm.nd[a][le], nb = sm.nd[b][le];
@@ -1094,7 +1153,7 @@ static int launch_asigmr(phb200_ctx *ctx) {
   if (grid < 1) grid = 1;
   KScope ks(ctx, KC_ASM);
   kern<<<grid, TILE_E * 4, smem, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, c.nshg, c.numnp, ntiles, ctx->d_ien,
-                                                ctx->d_x, ctx->d_y, ctx->d_ac, ctx->d_qres, ctx->d_iBC, ctx->d_BC,
+                                                ctx->d_nodeaos, ctx->d_iBC, ctx->d_BC,
                                                 ctx->d_res, ctx->d_BDiag, ctx->d_EG, ctx->d_eloc, ctx->d_lhsK);
   PHB_CHECK(cudaGetLastError());
   return 0;
@@ -1138,6 +1197,13 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   } else if (c.idiff != 0) {
     fprintf(stderr, "phb200: elmgmre: idiff=%d not supported (0 or 1)\n", c.idiff);
     return 1;
+  }
+  {
+    KScope ks(ctx, KC_NODE);
+    const size_t tot = (size_t)nshg * NREC;
+    k_pack_nodes<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(nshg, c.numnp, ctx->d_x, ctx->d_y, ctx->d_ac, ctx->d_qres,
+                                                               c.idiff >= 1, ctx->d_nodeaos);
+    PHB_CHECK(cudaGetLastError());
   }
   PHB_CHECK(cudaMemsetAsync(ctx->d_res, 0, sizeof(double) * 5 * (size_t)nshg, s));
   if (st->iprec != 0) PHB_CHECK(cudaMemsetAsync(ctx->d_BDiag, 0, sizeof(double) * 25 * (size_t)nshg, s));

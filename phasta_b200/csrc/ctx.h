@@ -69,6 +69,7 @@ struct phb200_ctx {
   // ---- state / results
   double *d_y, *d_ac;            // [5][nshg] {u,v,w,p,T}
   double *d_qres, *d_rmass;      // [12][nshg], [nshg]
+  double *d_nodeaos;             // [nshg][26] node records for the element gathers (assembly.cu)
   double *d_res, *d_rmes, *d_Dy, *d_temp;  // [5][nshg]
   double *d_BDiag;               // [25][nshg]  BDiag(nshg,5,5)
   double *d_BDtmp;               // scratch copy for i3pre's commu 'out'
