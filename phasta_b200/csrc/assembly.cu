@@ -61,6 +61,19 @@ int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, co
         t.dN[q][a][i] = shgl[0 + PHB200_MAXTOP * (i + 3 * (a + PHB200_MAXSH * q))];
     }
   }
+  // the warp-specialised kernel and the closed-form viscous block rely on what holds for linear tets with
+  // the reference's rules: identical N_a,xi and weight at every point
+  ctx->tet_uniform_rule = true;
+  for (int q = 1; q < t.nq; q++) {
+    if (t.Qwt[q] != t.Qwt[0]) ctx->tet_uniform_rule = false;
+    for (int a = 0; a < 4; a++)
+      for (int i = 0; i < 3; i++)
+        if (t.dN[q][a][i] != t.dN[0][a][i]) ctx->tet_uniform_rule = false;
+  }
+  if (!ctx->tet_uniform_rule) {
+    fprintf(stderr, "phb200: init: tet tables are not those of a linear tet (N_a,xi / Qwt vary between points)\n");
+    return 1;
+  }
   PHB_CHECK(cudaMemcpyToSymbol(c_tet, &t, sizeof t));
   if (ctx->numelb > 0) {
     TriTables b;
@@ -321,6 +334,7 @@ struct AsmSmem {
   double shg[12][TILE_E];
   double W[TILE_E];
   int nd[4][TILE_E];
+  int ibc[4][TILE_E];  // iBC of the 4 nodes, prefetched so phase B never waits on a global load
 };
 
 // bc3LHS velocity-code tables (bc3lhs.f:47-213): for one-velocity codes the
@@ -386,6 +400,479 @@ __device__ __forceinline__ int bc_elim_mask(int ibc) {
   return m;
 }
 
+// phase B' (e3wmlt.f:74-145): rl = W (N_a,i ri_i) + N_a W ri(16:20), one thread per (element, node)
+template <int TILE_E, int NQ>
+__device__ __forceinline__ void phase_bprime(const AsmSmem<TILE_E, NQ> &sm, int el, int sub, bool live, int nshg,
+                                             double *__restrict__ res) {
+      const int a = sub;  // 4 subs == 4 nodes
+      const double W = sm.W[el];
+      const double s0 = sm.shg[3 * a + 0][el], s1 = sm.shg[3 * a + 1][el], s2 = sm.shg[3 * a + 2][el];
+      double rl[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        const double Na = c_tet.N[q][a];
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+          rl[m] += W * (s0 * sm.ri[q][m][el] + s1 * sm.ri[q][5 + m][el] + s2 * sm.ri[q][10 + m][el]);
+          if (NQ != 1) rl[m] += Na * W * sm.ri[q][15 + m][el];
+        }
+      }
+      if (live) {
+        const int node = sm.nd[a][el];
+#pragma unroll
+        for (int m = 0; m < 5; m++) atomicAdd(res + (size_t)nshg * m + node, rl[m]);
+      }
+}
+
+// phase B: the 5x5 blocks of EGmass; one warp-task per (a,b) pair and 32-element half tile
+template <int TILE_E, int NQ, int LHS, int NWARP>
+__device__ __forceinline__ void phase_b(const AsmSmem<TILE_E, NQ> &sm, int warp, int lane, int tile, int numel,
+                                        size_t numel_pad, int nshg, const int *__restrict__ iBC,
+                                        const double *__restrict__ BC, double *__restrict__ BDiag,
+                                        double *__restrict__ EG, const int *__restrict__ eloc,
+                                        double *__restrict__ lhsK) {
+      constexpr int NHALF = TILE_E / 32;
+      for (int task = warp; task < 16 * NHALF; task += NWARP) {
+        const int pair = task / NHALF, half = task % NHALF;
+        const int a = pair >> 2, b = pair & 3;
+        const int le = half * 32 + lane;
+        const int ge = tile * TILE_E + le;
+        const double W = sm.W[le];
+        const double ga[3] = {sm.shg[3 * a][le], sm.shg[3 * a + 1][le], sm.shg[3 * a + 2][le]};
+        const double gb[3] = {sm.shg[3 * b][le], sm.shg[3 * b + 1][le], sm.shg[3 * b + 2][le]};
+        const double gagb = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+        double acc[5][5];
+#pragma unroll
+        for (int m = 0; m < 5; m++)
+#pragma unroll
+          for (int n = 0; n < 5; n++) acc[m][n] = 0.0;
+        // sums over the quadrature points that feed the viscous block (N_a,i is constant on a
+        // linear tet, so N_a,i K_ij N_b,j W only needs sum_q of mu, lambda, kappa, mu u, lambda u)
+        double smu = 0.0, slam = 0.0, scon = 0.0, smuu[3] = {0, 0, 0}, slamu[3] = {0, 0, 0};
+#pragma unroll 1
+        for (int q = 0; q < NQ; q++) {
+          const double rho = sm.st[q][S_RHO][le];
+          const double u[3] = {sm.st[q][S_U1][le], sm.st[q][S_U2][le], sm.st[q][S_U3][le]};
+          const double drdp = sm.st[q][S_DRDP][le], drdT = sm.st[q][S_DRDT][le];
+          const double e1p = sm.st[q][S_E1P][le], e3p = sm.st[q][S_E3P][le], e4p = sm.st[q][S_E4P][le];
+          const double tw1 = W * sm.st[q][S_TAU1][le], tw2 = W * sm.st[q][S_TAU2][le],
+                       tw3 = W * sm.st[q][S_TAU3][le];
+          const double mu = sm.st[q][S_MU][le], lam = sm.st[q][S_LAM][le];
+          smu += mu;
+          slam += lam;
+          scon += sm.st[q][S_CON][le];
+#pragma unroll
+          for (int r = 0; r < 3; r++) {
+            smuu[r] += mu * u[r];
+            slamu[r] += lam * u[r];
+          }
+          const double Na = c_tet.N[q][a], Nb = c_tet.N[q][b];
+          const double w[5] = {rho, rho * u[0], rho * u[1], rho * u[2], e3p};
+          const double al_a = u[0] * ga[0] + u[1] * ga[1] + u[2] * ga[2];
+          const double al_b = u[0] * gb[0] + u[1] * gb[1] + u[2] * gb[2];
+          // Tm = W (At_a tau + Na I),  At_a = al_a A0 + w ghat_a^T + hhat_a e1^T; W tau folded per column
+          double Tm[5][5];
+          {
+            const double c1 = al_a * drdp * tw1, c5 = al_a * drdT * tw3, aR = al_a * rho * tw2;
+            Tm[0][0] = c1;
+            Tm[1][0] = c1 * u[0] + ga[0] * tw1;
+            Tm[2][0] = c1 * u[1] + ga[1] * tw1;
+            Tm[3][0] = c1 * u[2] + ga[2] * tw1;
+            Tm[4][0] = al_a * tw1 * (e1p + 1.0);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              const double gj = ga[j] * tw2;
+#pragma unroll
+              for (int m = 0; m < 5; m++) Tm[m][1 + j] = w[m] * gj;
+              Tm[1 + j][1 + j] += aR;
+              Tm[4][1 + j] += aR * u[j];
+            }
+            Tm[0][4] = c5;
+            Tm[1][4] = c5 * u[0];
+            Tm[2][4] = c5 * u[1];
+            Tm[3][4] = c5 * u[2];
+            Tm[4][4] = al_a * e4p * tw3;
+            const double WNa = W * Na;
+#pragma unroll
+            for (int m = 0; m < 5; m++) Tm[m][m] += WNa;
+          }
+          // acc += Tm * Bm,  Bm = At_b + c Nb A0 = (al_b + c Nb) A0 + w ghat_b^T + hhat_b e1^T,
+          // one column of Bm at a time
+          {
+            const double alp = al_b + c_ph.fct1 * Nb;
+            const double c1 = alp * drdp, c5 = alp * drdT, aR = alp * rho;
+            double bc[5];
+            // column 1 (pressure)
+            bc[0] = c1;
+            bc[1] = c1 * u[0] + gb[0];
+            bc[2] = c1 * u[1] + gb[1];
+            bc[3] = c1 * u[2] + gb[2];
+            bc[4] = alp * e1p + al_b;
+#pragma unroll
+            for (int m = 0; m < 5; m++) {
+              double sacc = acc[m][0];
+#pragma unroll
+              for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
+              acc[m][0] = sacc;
+            }
+            // columns 2..4 (velocities)
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+#pragma unroll
+              for (int k = 0; k < 5; k++) bc[k] = w[k] * gb[j];
+              bc[1 + j] += aR;
+              bc[4] += aR * u[j];
+#pragma unroll
+              for (int m = 0; m < 5; m++) {
+                double sacc = acc[m][1 + j];
+#pragma unroll
+                for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
+                acc[m][1 + j] = sacc;
+              }
+            }
+            // column 5 (temperature)
+            bc[0] = c5;
+            bc[1] = c5 * u[0];
+            bc[2] = c5 * u[1];
+            bc[3] = c5 * u[2];
+            bc[4] = alp * e4p;
+#pragma unroll
+            for (int m = 0; m < 5; m++) {
+              double sacc = acc[m][4];
+#pragma unroll
+              for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
+              acc[m][4] = sacc;
+            }
+          }
+        }
+        // viscous block N_a,i K_ij N_b,j W (e3visc.f:69-139, e3wmlt.f:154-223), summed over q in closed form
+        {
+#pragma unroll
+          for (int r = 0; r < 3; r++)
+#pragma unroll
+            for (int sdx = 0; sdx < 3; sdx++)
+              acc[1 + r][1 + sdx] += W * (smu * ga[sdx] * gb[r] + slam * ga[r] * gb[sdx]);
+          const double d0 = W * smu * gagb;
+          acc[1][1] += d0;
+          acc[2][2] += d0;
+          acc[3][3] += d0;
+#pragma unroll
+          for (int sdx = 0; sdx < 3; sdx++) {
+            double e = smuu[sdx] * gagb;  // delta_rs part
+#pragma unroll
+            for (int r = 0; r < 3; r++) e += smuu[r] * ga[sdx] * gb[r] + slamu[r] * ga[r] * gb[sdx];
+            acc[4][1 + sdx] += W * e;
+          }
+          acc[4][4] += W * scon * gagb;
+        }
+        if (ge < numel) {
+          const int na = sm.nd[a][le], nb = sm.nd[b][le];
+          // BDiag extraction BEFORE bc3LHS (asigmr.f:92-102, SURVEY B3)
+          if (a == b && c_ph.iprec != 0) {
+#pragma unroll
+            for (int m = 0; m < 5; m++)
+#pragma unroll
+              for (int n = 0; n < 5; n++) atomicAdd(BDiag + (size_t)nshg * (m + 5 * n) + na, acc[m][n]);
+          }
+          // bc3LHS (bc3lhs.f:1-290) on this block: rows by node a, columns by node b
+          const int ibca = sm.ibc[a][le], ibcb = sm.ibc[b][le];
+          if (ibca | ibcb) {
+            // local view with dofs {p,u1,u2,u3,T} = indices 0..4; bc_rows/cols use 1..3 for velocities
+            const int codea = (ibca >> 3) & 7, codeb = (ibcb >> 3) & 7;
+            if (codea != 0 && codea != 7) {
+              const double bc[3] = {__ldg(BC + (size_t)nshg * 3 + na), __ldg(BC + (size_t)nshg * 4 + na),
+                                    __ldg(BC + (size_t)nshg * 5 + na)};
+              bc_rows(codea, bc, acc);
+            }
+            if (codeb != 0 && codeb != 7) {
+              const double bc[3] = {__ldg(BC + (size_t)nshg * 3 + nb), __ldg(BC + (size_t)nshg * 4 + nb),
+                                    __ldg(BC + (size_t)nshg * 5 + nb)};
+              bc_cols(codeb, bc, acc);
+            }
+            const int ma = bc_elim_mask(ibca), mb = bc_elim_mask(ibcb);
+#pragma unroll
+            for (int m = 0; m < 5; m++)
+#pragma unroll
+              for (int n = 0; n < 5; n++) {
+                if (((ma >> m) & 1) | ((mb >> n) & 1)) acc[m][n] = 0.0;
+              }
+            if (a == b) {
+#pragma unroll
+              for (int m = 0; m < 5; m++)
+                if ((ma >> m) & 1) acc[m][m] = 1.0;
+            }
+          }
+        }
+        if (LHS == 2) {
+          // fillsparseC (fillsparse.f:66-126): lhsK(f+5g, k) += EGmass(e, r+f, s+g); the block index k
+          // comes from the precomputed sparseloc map
+          if (ge < numel) {
+            const int k = eloc[(size_t)(4 * a + b) * numel_pad + ge];
+            double *blk = lhsK + (size_t)25 * k;
+#pragma unroll
+            for (int n = 0; n < 5; n++)
+#pragma unroll
+              for (int m = 0; m < 5; m++) atomicAdd(blk + m + 5 * n, acc[m][n]);
+          }
+        } else {
+          // coalesced store of the block (also for padding lanes: zeros)
+          const size_t gtile = (size_t)ge / EG_TILE;
+          const int gl = ge % EG_TILE;
+          double *base = EG + gtile * (size_t)(400 * EG_TILE) + gl;
+          const bool ok = ge < numel;
+#pragma unroll
+          for (int n = 0; n < 5; n++)
+#pragma unroll
+            for (int m = 0; m < 5; m++)
+              base[(size_t)((5 * a + m) + 20 * (5 * b + n)) * EG_TILE] = ok ? acc[m][n] : 0.0;
+        }
+      }
+}
+
+// ---------------------------------------------------------------------------
+// point-wise state of e3 at one quadrature point from interpolated values:
+// thermodynamics, tau, fluxes ri(1:20) and the 15 scalars phase B needs.
+// Same formulas as phase A of k_asigmr_tet (see the citations there).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void tet_gij(const double d[3][3], double gij[6]) {
+  // e3gijd for tets (e3tau.f:1438-1474)
+  const double c1 = 1.259921049894873e+00, c2 = 6.299605249474365e-01;
+  double t1, t2, t3;
+  t1 = c1 * d[0][0] + c2 * (d[1][0] + d[2][0]);
+  t2 = c1 * d[1][0] + c2 * (d[0][0] + d[2][0]);
+  t3 = c1 * d[2][0] + c2 * (d[0][0] + d[1][0]);
+  gij[0] = d[0][0] * t1 + d[1][0] * t2 + d[2][0] * t3;
+  t1 = c1 * d[0][1] + c2 * (d[1][1] + d[2][1]);
+  t2 = c1 * d[1][1] + c2 * (d[0][1] + d[2][1]);
+  t3 = c1 * d[2][1] + c2 * (d[0][1] + d[1][1]);
+  gij[1] = d[0][0] * t1 + d[1][0] * t2 + d[2][0] * t3;
+  gij[2] = d[0][1] * t1 + d[1][1] * t2 + d[2][1] * t3;
+  t1 = c1 * d[0][2] + c2 * (d[1][2] + d[2][2]);
+  t2 = c1 * d[1][2] + c2 * (d[0][2] + d[2][2]);
+  t3 = c1 * d[2][2] + c2 * (d[0][2] + d[1][2]);
+  gij[3] = d[0][0] * t1 + d[1][0] * t2 + d[2][0] * t3;
+  gij[4] = d[0][1] * t1 + d[1][1] * t2 + d[2][1] * t3;
+  gij[5] = d[0][2] * t1 + d[1][2] * t2 + d[2][2] * t3;
+}
+
+__device__ __forceinline__ void point_math(const double Y[5], const double At[5], const double gr[3][5],
+                                           const double divq[4], const double gij[6], double ri[20],
+                                           double st[S_NVAR]) {
+  const double pres = Y[0], u1 = Y[1], u2 = Y[2], u3 = Y[3], T = Y[4];
+  const double rho = pres / (c_ph.Rgas * T);                       // getthm.f:111
+  const double ei = T * (c_ph.Rgas / c_ph.gamma1);                 // getthm.f:148
+  const double h = T * (c_ph.Rgas * c_ph.gamma / c_ph.gamma1);     // getthm.f:163-169
+  const double cv = c_ph.Rgas / c_ph.gamma1;
+  const double cp = c_ph.Rgas * c_ph.gamma / c_ph.gamma1;
+  const double alfap = 1.0 / T, betaT = 1.0 / pres;
+  const double rk = 0.5 * (u1 * u1 + u2 * u2 + u3 * u3);
+  double mu, lam, con;
+  diffusivities(T, cp, mu, lam, con);
+  const double drdp = rho * betaT, drdT = -rho * alfap;            // e3mtrx.f:87-97
+  const double e1p = drdp * (h + rk) - alfap * T;
+  const double e3p = rho * (h + rk);
+  const double e4p = drdT * (h + rk) + rho * cp;
+  const double u[3] = {u1, u2, u3};
+  const double w[5] = {rho, rho * u1, rho * u2, rho * u3, e3p};
+  auto A0v = [&](const double v[5], double o[5]) {
+    double c1 = drdp * v[0] + drdT * v[4];
+    o[0] = c1;
+    o[1] = u1 * c1 + rho * v[1];
+    o[2] = u2 * c1 + rho * v[2];
+    o[3] = u3 * c1 + rho * v[3];
+    o[4] = e1p * v[0] + rho * (u1 * v[1] + u2 * v[2] + u3 * v[3]) + e4p * v[4];
+  };
+#pragma unroll
+  for (int i = 0; i < 3; i++) {                                    // e3conv.f:76-92
+    ri[5 * i + 0] = (-u[i]) * rho;
+    ri[5 * i + 1] = (-u[i]) * rho * u1;
+    ri[5 * i + 2] = (-u[i]) * rho * u2;
+    ri[5 * i + 3] = (-u[i]) * rho * u3;
+    ri[5 * i + 4] = (-u[i]) * rho * (ei + rk) - u[i] * pres;
+    ri[5 * i + 1 + i] -= pres;
+  }
+  double adv[5], L[5], tmpv[5], massr[5];                          // e3conv.f:100-179, e3ls.f:108-154
+#pragma unroll
+  for (int m = 0; m < 5; m++) adv[m] = u1 * gr[0][m] + u2 * gr[1][m] + u3 * gr[2][m];
+  const double divu = gr[0][1] + gr[1][2] + gr[2][3];
+  A0v(adv, tmpv);
+  L[0] = tmpv[0] + w[0] * divu;
+  L[1] = tmpv[1] + w[1] * divu + gr[0][0];
+  L[2] = tmpv[2] + w[2] * divu + gr[1][0];
+  L[3] = tmpv[3] + w[3] * divu + gr[2][0];
+  L[4] = tmpv[4] + w[4] * divu + adv[0];
+  A0v(At, massr);                                                  // e3massr.f:33-66
+#pragma unroll
+  for (int m = 0; m < 5; m++) L[m] += massr[m];
+  if (c_ph.idiff >= 1) {
+    L[1] -= divq[0]; L[2] -= divq[1]; L[3] -= divq[2]; L[4] -= divq[3];
+  }
+  double f[3][4];                                                  // e3visc.f:278-343
+  diff_flux(gr, u1, u2, u3, mu, lam, con, f);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int m = 0; m < 4; m++) ri[5 * i + 1 + m] += f[i][m];
+  const double fff = (c_ph.ipord == 1) ? 36.0 : (c_ph.ipord == 2 ? 60.0 : 128.0);   // e3tau.f:140-176
+  const double dts = c_ph.iremove ? 0.0 : c_ph.dtsfct * c_ph.Dtgl;
+  double tau2 = rho * rho * ((2.0 * dts) * (2.0 * dts) +
+                             (u1 * (u1 * gij[0] + 2.0 * (u2 * gij[1] + u3 * gij[3])) +
+                              u2 * (u2 * gij[2] + 2.0 * u3 * gij[4]) + u3 * u3 * gij[5])) +
+                fff * mu * mu * (gij[0] * gij[0] + gij[2] * gij[2] + gij[5] * gij[5] +
+                                 2.0 * (gij[1] * gij[1] + gij[3] * gij[3] + gij[4] * gij[4]));
+  const double fact = sqrt(tau2);
+  const double tau1 = 0.125 * fact / (rho * (gij[0] + gij[2] + gij[5])) * c_ph.taucfct;
+  tau2 = 1.0 / fact;
+  const double tau3 = tau2 / cv * c_ph.temper;
+  L[0] *= tau1; L[1] *= tau2; L[2] *= tau2; L[3] *= tau2; L[4] *= tau3;
+  A0v(L, tmpv);                                                    // e3ls.f:352-457
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+#pragma unroll
+    for (int m = 0; m < 5; m++) ri[5 * i + m] += u[i] * tmpv[m] + w[m] * L[1 + i];
+    ri[5 * i + 1 + i] += L[0];
+    ri[5 * i + 4] += u[i] * L[0];
+  }
+#pragma unroll
+  for (int m = 0; m < 5; m++) ri[15 + m] = massr[m];
+  st[S_RHO] = rho; st[S_U1] = u1; st[S_U2] = u2; st[S_U3] = u3;
+  st[S_DRDP] = drdp; st[S_DRDT] = drdT; st[S_E1P] = e1p; st[S_E3P] = e3p; st[S_E4P] = e4p;
+  st[S_TAU1] = tau1; st[S_TAU2] = tau2; st[S_TAU3] = tau3;
+  st[S_MU] = mu; st[S_LAM] = lam; st[S_CON] = con;
+}
+
+__device__ __forceinline__ void bar_sync_named(int id, int n) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_named(int id, int n) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
+// ---------------------------------------------------------------------------
+// Warp-specialised AsIGMR for the 4-point rule: CTA = 4 consumer warps + 1
+// producer warp over a double-buffered 32-element tile.  The producer (lane =
+// element) does the gathers and the point-wise state of all 4 quadrature
+// points (metric, gradients, div q, g_ij once per element since they are
+// constant on a linear tet) while the consumers run phases B'/B of the
+// previous tile, so the gather latency hides under the FP64 block products.
+// Named barriers: 1+buf "full" (producer arrives, consumers sync),
+//                 3+buf "empty" (consumers arrive, producer syncs).
+// ---------------------------------------------------------------------------
+template <int LHS>
+__global__ void __launch_bounds__(192, 2) k_asigmr_tet_ws(
+    int numel, size_t numel_pad, int nshg, int numnp, int ntiles, const int *__restrict__ ien,
+    const double *__restrict__ aos, const int *__restrict__ iBC, const double *__restrict__ BC,
+    double *__restrict__ res, double *__restrict__ BDiag, double *__restrict__ EG, const int *__restrict__ eloc,
+    double *__restrict__ lhsK) {
+  constexpr int NQ = 4, TILE_E = 32, NTHR = 192;  // 4 consumer + 2 producer warps
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  AsmSmem<TILE_E, NQ> *smb = reinterpret_cast<AsmSmem<TILE_E, NQ> *>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp >= 4) {
+    // ------------------------------ producers: warp 4 does points 0,1; warp 5 points 2,3 ----------
+    const int qbeg = (warp - 4) * 2, qend = qbeg + 2;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      const int buf = it & 1;
+      AsmSmem<TILE_E, NQ> &sm = smb[buf];
+      const int e = tile * TILE_E + lane;
+      const bool live = e < numel;
+      int nd[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) nd[a] = live ? ien[(size_t)a * numel_pad + e] : 0;
+      const double2 *rec[4];
+      double xl[4][3];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        rec[a] = reinterpret_cast<const double2 *>(aos + (size_t)nd[a] * NREC);
+        const double2 v0 = __ldg(rec[a]), v1 = __ldg(rec[a] + 1);
+        xl[a][0] = v0.x; xl[a][1] = v0.y; xl[a][2] = v1.x;
+      }
+      int ibcn[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) ibcn[a] = __ldg(iBC + nd[a]);
+      Metric g;
+      tet_metric(xl, c_tet.dN[0], c_tet.Qwt[0], g);
+      double gij[6];
+      tet_gij(g.dxidx, gij);
+      // gradients and div q are constant on the element (e3ivar.f:259-395)
+      double gr[3][5], divq[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int m = 0; m < 5; m++) gr[i][m] = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const double2 v1 = __ldg(rec[a] + 1), v2 = __ldg(rec[a] + 2), v3 = __ldg(rec[a] + 3);
+        const double yl[5] = {v1.y, v2.x, v2.y, v3.x, v3.y};
+#pragma unroll
+        for (int m = 0; m < 5; m++)
+#pragma unroll
+          for (int i = 0; i < 3; i++) gr[i][m] += g.shg[a][i] * yl[m];
+        if (c_ph.idiff >= 1) {
+          const double2 v6 = __ldg(rec[a] + 6), v7 = __ldg(rec[a] + 7), v8 = __ldg(rec[a] + 8),
+                        v9 = __ldg(rec[a] + 9), v10 = __ldg(rec[a] + 10), v11 = __ldg(rec[a] + 11),
+                        v12 = __ldg(rec[a] + 12);
+          const double ql[12] = {v6.y, v7.x, v7.y, v8.x, v8.y, v9.x, v9.y, v10.x, v10.y, v11.x, v11.y, v12.x};
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int m = 0; m < 4; m++) divq[m] += g.shg[a][i] * ql[4 * i + m];
+        }
+      }
+      if (it >= 2) bar_sync_named(3 + buf, NTHR);  // consumers are done with this buffer
+      if (warp == 4) {
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          sm.nd[a][lane] = nd[a];
+          sm.ibc[a][lane] = ibcn[a];
+#pragma unroll
+          for (int i = 0; i < 3; i++) sm.shg[3 * a + i][lane] = g.shg[a][i];
+        }
+        sm.W[lane] = g.W;
+      }
+#pragma unroll 1
+      for (int q = qbeg; q < qend; q++) {
+        double Y[5] = {0, 0, 0, 0, 0}, At[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          const double2 v1 = __ldg(rec[a] + 1), v2 = __ldg(rec[a] + 2), v3 = __ldg(rec[a] + 3),
+                        v4 = __ldg(rec[a] + 4), v5 = __ldg(rec[a] + 5), v6 = __ldg(rec[a] + 6);
+          const double yl[5] = {v1.y, v2.x, v2.y, v3.x, v3.y};
+          const double al[5] = {v4.x, v4.y, v5.x, v5.y, v6.x};
+          const double Na = c_tet.N[q][a];
+#pragma unroll
+          for (int m = 0; m < 5; m++) {
+            Y[m] += Na * yl[m];
+            At[m] += Na * al[m];
+          }
+        }
+        double ri[20], st[S_NVAR];
+        point_math(Y, At, gr, divq, gij, ri, st);
+#pragma unroll
+        for (int k = 0; k < 20; k++) sm.ri[q][k][lane] = ri[k];
+        if (LHS) {
+#pragma unroll
+          for (int k = 0; k < S_NVAR; k++) sm.st[q][k][lane] = st[k];
+        }
+      }
+      bar_arrive_named(1 + buf, NTHR);
+    }
+  } else {
+    // ------------------------------ consumers -----------------------------
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      const int buf = it & 1;
+      const AsmSmem<TILE_E, NQ> &sm = smb[buf];
+      bar_sync_named(1 + buf, NTHR);
+      const bool live = (tile * TILE_E + lane) < numel;
+      phase_bprime<TILE_E, NQ>(sm, lane, warp, live, nshg, res);
+      if (LHS) phase_b<TILE_E, NQ, LHS, 4>(sm, warp, lane, tile, numel, numel_pad, nshg, iBC, BC, BDiag, EG, eloc, lhsK);
+      if (tile + 2 * (int)gridDim.x < ntiles) bar_arrive_named(3 + buf, NTHR);
+    }
+  }
+}
+
 // LHS: 0 residual only, 1 EBE tiles (ElmGMRe), 2 scatter into lhsK (ElmGMRs + fillsparseC)
 template <int TILE_E, int NQ, int LHS>
 __global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
@@ -424,6 +911,7 @@ __global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
 #pragma unroll
         for (int a = 0; a < 4; a++) {
           sm.nd[a][el] = nd[a];
+          sm.ibc[a][el] = __ldg(iBC + nd[a]);
 #pragma unroll
           for (int i = 0; i < 3; i++) sm.shg[3 * a + i][el] = g.shg[a][i];
         }
@@ -616,228 +1104,8 @@ __global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
       }
     }
     __syncthreads();
-    // ------------------ phase B': residual (e3wmlt.f:74-145) -------------
-    {
-      const int a = sub;  // 4 subs == 4 nodes
-      const double W = sm.W[el];
-      const double s0 = sm.shg[3 * a + 0][el], s1 = sm.shg[3 * a + 1][el], s2 = sm.shg[3 * a + 2][el];
-      double rl[5] = {0, 0, 0, 0, 0};
-#pragma unroll
-      for (int q = 0; q < NQ; q++) {
-        const double Na = c_tet.N[q][a];
-#pragma unroll
-        for (int m = 0; m < 5; m++) {
-          rl[m] += W * (s0 * sm.ri[q][m][el] + s1 * sm.ri[q][5 + m][el] + s2 * sm.ri[q][10 + m][el]);
-          if (NQ != 1) rl[m] += Na * W * sm.ri[q][15 + m][el];
-        }
-      }
-      if (live) {
-        const int node = sm.nd[a][el];
-#pragma unroll
-        for (int m = 0; m < 5; m++) atomicAdd(res + (size_t)nshg * m + node, rl[m]);
-      }
-    }
-    // ------------------ phase B: LHS blocks ------------------------------
-    if (LHS) {
-      const int warp = tid >> 5, lane = tid & 31;
-      constexpr int NWARP = TILE_E * 4 / 32;
-      constexpr int NHALF = TILE_E / 32;
-      for (int task = warp; task < 16 * NHALF; task += NWARP) {
-        const int pair = task / NHALF, half = task % NHALF;
-        const int a = pair >> 2, b = pair & 3;
-        const int le = half * 32 + lane;
-        const int ge = tile * TILE_E + le;
-        const double W = sm.W[le];
-        const double ga[3] = {sm.shg[3 * a][le], sm.shg[3 * a + 1][le], sm.shg[3 * a + 2][le]};
-        const double gb[3] = {sm.shg[3 * b][le], sm.shg[3 * b + 1][le], sm.shg[3 * b + 2][le]};
-        const double gagb = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
-        double acc[5][5];
-#pragma unroll
-        for (int m = 0; m < 5; m++)
-#pragma unroll
-          for (int n = 0; n < 5; n++) acc[m][n] = 0.0;
-        // sums over the quadrature points that feed the viscous block (N_a,i is constant on a
-        // linear tet, so N_a,i K_ij N_b,j W only needs sum_q of mu, lambda, kappa, mu u, lambda u)
-        double smu = 0.0, slam = 0.0, scon = 0.0, smuu[3] = {0, 0, 0}, slamu[3] = {0, 0, 0};
-#pragma unroll 1
-        for (int q = 0; q < NQ; q++) {
-          const double rho = sm.st[q][S_RHO][le];
-          const double u[3] = {sm.st[q][S_U1][le], sm.st[q][S_U2][le], sm.st[q][S_U3][le]};
-          const double drdp = sm.st[q][S_DRDP][le], drdT = sm.st[q][S_DRDT][le];
-          const double e1p = sm.st[q][S_E1P][le], e3p = sm.st[q][S_E3P][le], e4p = sm.st[q][S_E4P][le];
-          const double tw1 = W * sm.st[q][S_TAU1][le], tw2 = W * sm.st[q][S_TAU2][le],
-                       tw3 = W * sm.st[q][S_TAU3][le];
-          const double mu = sm.st[q][S_MU][le], lam = sm.st[q][S_LAM][le];
-          smu += mu;
-          slam += lam;
-          scon += sm.st[q][S_CON][le];
-#pragma unroll
-          for (int r = 0; r < 3; r++) {
-            smuu[r] += mu * u[r];
-            slamu[r] += lam * u[r];
-          }
-          const double Na = c_tet.N[q][a], Nb = c_tet.N[q][b];
-          const double w[5] = {rho, rho * u[0], rho * u[1], rho * u[2], e3p};
-          const double al_a = u[0] * ga[0] + u[1] * ga[1] + u[2] * ga[2];
-          const double al_b = u[0] * gb[0] + u[1] * gb[1] + u[2] * gb[2];
-          // Tm = W (At_a tau + Na I),  At_a = al_a A0 + w ghat_a^T + hhat_a e1^T; W tau folded per column
-          double Tm[5][5];
-          {
-            const double c1 = al_a * drdp * tw1, c5 = al_a * drdT * tw3, aR = al_a * rho * tw2;
-            Tm[0][0] = c1;
-            Tm[1][0] = c1 * u[0] + ga[0] * tw1;
-            Tm[2][0] = c1 * u[1] + ga[1] * tw1;
-            Tm[3][0] = c1 * u[2] + ga[2] * tw1;
-            Tm[4][0] = al_a * tw1 * (e1p + 1.0);
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-              const double gj = ga[j] * tw2;
-#pragma unroll
-              for (int m = 0; m < 5; m++) Tm[m][1 + j] = w[m] * gj;
-              Tm[1 + j][1 + j] += aR;
-              Tm[4][1 + j] += aR * u[j];
-            }
-            Tm[0][4] = c5;
-            Tm[1][4] = c5 * u[0];
-            Tm[2][4] = c5 * u[1];
-            Tm[3][4] = c5 * u[2];
-            Tm[4][4] = al_a * e4p * tw3;
-            const double WNa = W * Na;
-#pragma unroll
-            for (int m = 0; m < 5; m++) Tm[m][m] += WNa;
-          }
-          // acc += Tm * Bm,  Bm = At_b + c Nb A0 = (al_b + c Nb) A0 + w ghat_b^T + hhat_b e1^T,
-          // one column of Bm at a time
-          {
-            const double alp = al_b + c_ph.fct1 * Nb;
-            const double c1 = alp * drdp, c5 = alp * drdT, aR = alp * rho;
-            double bc[5];
-            // column 1 (pressure)
-            bc[0] = c1;
-            bc[1] = c1 * u[0] + gb[0];
-            bc[2] = c1 * u[1] + gb[1];
-            bc[3] = c1 * u[2] + gb[2];
-            bc[4] = alp * e1p + al_b;
-#pragma unroll
-            for (int m = 0; m < 5; m++) {
-              double sacc = acc[m][0];
-#pragma unroll
-              for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
-              acc[m][0] = sacc;
-            }
-            // columns 2..4 (velocities)
-#pragma unroll
-            for (int j = 0; j < 3; j++) {
-#pragma unroll
-              for (int k = 0; k < 5; k++) bc[k] = w[k] * gb[j];
-              bc[1 + j] += aR;
-              bc[4] += aR * u[j];
-#pragma unroll
-              for (int m = 0; m < 5; m++) {
-                double sacc = acc[m][1 + j];
-#pragma unroll
-                for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
-                acc[m][1 + j] = sacc;
-              }
-            }
-            // column 5 (temperature)
-            bc[0] = c5;
-            bc[1] = c5 * u[0];
-            bc[2] = c5 * u[1];
-            bc[3] = c5 * u[2];
-            bc[4] = alp * e4p;
-#pragma unroll
-            for (int m = 0; m < 5; m++) {
-              double sacc = acc[m][4];
-#pragma unroll
-              for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
-              acc[m][4] = sacc;
-            }
-          }
-        }
-        // viscous block N_a,i K_ij N_b,j W (e3visc.f:69-139, e3wmlt.f:154-223), summed over q in closed form
-        {
-#pragma unroll
-          for (int r = 0; r < 3; r++)
-#pragma unroll
-            for (int sdx = 0; sdx < 3; sdx++)
-              acc[1 + r][1 + sdx] += W * (smu * ga[sdx] * gb[r] + slam * ga[r] * gb[sdx]);
-          const double d0 = W * smu * gagb;
-          acc[1][1] += d0;
-          acc[2][2] += d0;
-          acc[3][3] += d0;
-#pragma unroll
-          for (int sdx = 0; sdx < 3; sdx++) {
-            double e = smuu[sdx] * gagb;  // delta_rs part
-#pragma unroll
-            for (int r = 0; r < 3; r++) e += smuu[r] * ga[sdx] * gb[r] + slamu[r] * ga[r] * gb[sdx];
-            acc[4][1 + sdx] += W * e;
-          }
-          acc[4][4] += W * scon * gagb;
-        }
-        if (ge < numel) {
-          const int na = sm.nd[a][le], nb = sm.nd[b][le];
-          // BDiag extraction BEFORE bc3LHS (asigmr.f:92-102, SURVEY B3)
-          if (a == b && c_ph.iprec != 0) {
-#pragma unroll
-            for (int m = 0; m < 5; m++)
-#pragma unroll
-              for (int n = 0; n < 5; n++) atomicAdd(BDiag + (size_t)nshg * (m + 5 * n) + na, acc[m][n]);
-          }
-          // bc3LHS (bc3lhs.f:1-290) on this block: rows by node a, columns by node b
-          const int ibca = __ldg(iBC + na), ibcb = __ldg(iBC + nb);
-          if (ibca | ibcb) {
-            // local view with dofs {p,u1,u2,u3,T} = indices 0..4; bc_rows/cols use 1..3 for velocities
-            const int codea = (ibca >> 3) & 7, codeb = (ibcb >> 3) & 7;
-            if (codea != 0 && codea != 7) {
-              const double bc[3] = {__ldg(BC + (size_t)nshg * 3 + na), __ldg(BC + (size_t)nshg * 4 + na),
-                                    __ldg(BC + (size_t)nshg * 5 + na)};
-              bc_rows(codea, bc, acc);
-            }
-            if (codeb != 0 && codeb != 7) {
-              const double bc[3] = {__ldg(BC + (size_t)nshg * 3 + nb), __ldg(BC + (size_t)nshg * 4 + nb),
-                                    __ldg(BC + (size_t)nshg * 5 + nb)};
-              bc_cols(codeb, bc, acc);
-            }
-            const int ma = bc_elim_mask(ibca), mb = bc_elim_mask(ibcb);
-#pragma unroll
-            for (int m = 0; m < 5; m++)
-#pragma unroll
-              for (int n = 0; n < 5; n++) {
-                if (((ma >> m) & 1) | ((mb >> n) & 1)) acc[m][n] = 0.0;
-              }
-            if (a == b) {
-#pragma unroll
-              for (int m = 0; m < 5; m++)
-                if ((ma >> m) & 1) acc[m][m] = 1.0;
-            }
-          }
-        }
-        if (LHS == 2) {
-          // fillsparseC (fillsparse.f:66-126): lhsK(f+5g, k) += EGmass(e, r+f, s+g); the block index k
-          // comes from the precomputed sparseloc map
-          if (ge < numel) {
-            const int k = eloc[(size_t)(4 * a + b) * numel_pad + ge];
-            double *blk = lhsK + (size_t)25 * k;
-#pragma unroll
-            for (int n = 0; n < 5; n++)
-#pragma unroll
-              for (int m = 0; m < 5; m++) atomicAdd(blk + m + 5 * n, acc[m][n]);
-          }
-        } else {
-          // coalesced store of the block (also for padding lanes: zeros)
-          const size_t gtile = (size_t)ge / EG_TILE;
-          const int gl = ge % EG_TILE;
-          double *base = EG + gtile * (size_t)(400 * EG_TILE) + gl;
-          const bool ok = ge < numel;
-#pragma unroll
-          for (int n = 0; n < 5; n++)
-#pragma unroll
-            for (int m = 0; m < 5; m++)
-              base[(size_t)((5 * a + m) + 20 * (5 * b + n)) * EG_TILE] = ok ? acc[m][n] : 0.0;
-        }
-      }
-    }
+    phase_bprime<TILE_E, NQ>(sm, el, sub, live, nshg, res);
+    if (LHS) phase_b<TILE_E, NQ, LHS, TILE_E * 4 / 32>(sm, tid >> 5, tid & 31, tile, numel, numel_pad, nshg, iBC, BC, BDiag, EG, eloc, lhsK);
     __syncthreads();
   }
 }
@@ -1159,6 +1427,33 @@ static int launch_asigmr(phb200_ctx *ctx) {
   return 0;
 }
 
+template <int LHS>
+static int launch_asigmr_ws(phb200_ctx *ctx) {
+  const phb200_common &c = ctx->c;
+  size_t smem = 2 * sizeof(AsmSmem<32, 4>);
+  auto kern = k_asigmr_tet_ws<LHS>;
+  static bool configured = false;
+  if (!configured) {
+    PHB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  int ntiles = (ctx->numel_tet + 31) / 32;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 192, smem);
+  if (occ < 1) occ = 1;
+  int grid = nsm * occ;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  KScope ks(ctx, KC_ASM);
+  kern<<<grid, 192, smem, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, c.nshg, c.numnp, ntiles, ctx->d_ien,
+                                         ctx->d_nodeaos, ctx->d_iBC, ctx->d_BC, ctx->d_res, ctx->d_BDiag, ctx->d_EG,
+                                         ctx->d_eloc, ctx->d_lhsK);
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // ElmGMRe (elmgmr.f:1-274) on the resident state
 int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   const phb200_common &c = ctx->c;
@@ -1220,7 +1515,12 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   }
   if (ctx->numel_tet > 0) {
     const int mode = (st->lhs == 1) ? (sparse ? 2 : 1) : 0;
-    if (nq == 4) {
+    static const bool use_ws = !(getenv("PHB200_ASM_WS") && atoi(getenv("PHB200_ASM_WS")) == 0);
+    if (nq == 4 && use_ws && ctx->tet_uniform_rule) {
+      if (mode == 1) PHB_TRY((launch_asigmr_ws<1>(ctx)));
+      else if (mode == 2) PHB_TRY((launch_asigmr_ws<2>(ctx)));
+      else PHB_TRY((launch_asigmr<32, 4, 0>(ctx)));  // residual only: phase A dominates, no producer split
+    } else if (nq == 4) {
       if (mode == 1) PHB_TRY((launch_asigmr<32, 4, 1>(ctx)));
       else if (mode == 2) PHB_TRY((launch_asigmr<32, 4, 2>(ctx)));
       else PHB_TRY((launch_asigmr<32, 4, 0>(ctx)));

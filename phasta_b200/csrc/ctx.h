@@ -87,6 +87,7 @@ struct phb200_ctx {
   double *d_scratch;             // L2 flush / fp64 peak
   size_t scratch_bytes;
   bool have_lhs;                 // EGmass/BDiag hold a (preconditioned) system
+  bool tet_uniform_rule;         // same N_a,xi and weight at every tet quadrature point
   // host copies of the block structure (pointers stay caller-owned, as mien(iblk)%p does)
   std::vector<int> h_lcblk;
   std::vector<const int *> h_mien;
