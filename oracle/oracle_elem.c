@@ -723,9 +723,9 @@ void orc_asigmr(const orc_part *p, int iblk, const double *qres, double *res,
     /* the reference passes the strided section EGmass(iel:inum,:,:)
      * (elmgmr.f:160); gfortran packs it into a contiguous temporary.  Here the
      * element's nedof x nedof slab is accumulated contiguously and copied out. */
-    double EGl[900]; /* nedof <= 30 (wedges) */
+    double EGl[1600]; /* nedof <= 40 (hexes) */
     if (EGmass) {
-      if (nedof * nedof > 900) { fprintf(stderr, "orc_asigmr: nedof>30\n"); abort(); }
+      if (nedof * nedof > 1600) { fprintf(stderr, "orc_asigmr: nedof>40\n"); abort(); }
       memset(EGl, 0, sizeof(double) * (size_t)nedof * nedof);
     }
     e3_element(p, lcsyst, nshl, nenl, ngauss, ycl, acl, xl, ql, rl[e],

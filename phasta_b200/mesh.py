@@ -55,8 +55,12 @@ class MeshPart:
         return int(self.ilwork.size)
 
     def ien_all(self):
-        """(numel, nshl) connectivity, 1-based, file order."""
+        """(numel, nshl) connectivity, 1-based, file order (single-topology meshes)."""
         return np.concatenate([np.asarray(b) for b in self.mien], axis=0)
+
+    def elem_nodes(self):
+        """list over elements (file order) of 0-based node-id arrays; any topology mix."""
+        return [np.asarray(r) - 1 for b in self.mien for r in np.asarray(b)]
 
 
 _KUHN = list(permutations(range(3)))
@@ -84,22 +88,50 @@ def _box_tets(nx, ny, nz, node_id):
     return ien.reshape(nh * 6, 4)
 
 
-def _blocks(numel, ibksiz, lcsyst=1, ipord=1, nenl=4, nshl=4, nfacel=4):
-    """genblkPosix.f:52-96: consecutive runs of <= ibksiz elements."""
-    starts = np.arange(0, numel, ibksiz)
-    nb = starts.size
-    lcblk = np.zeros((10, nb + 1), dtype=np.int32, order="F")
-    lcblk[0, :nb] = starts + 1
-    lcblk[0, nb] = numel + 1
-    lcblk[2, :nb] = lcsyst
-    lcblk[3, :nb] = ipord
-    lcblk[4, :nb] = nenl
-    lcblk[5, :nb] = nfacel
-    lcblk[6, :nb] = 0          # mattyp
-    lcblk[7, :nb] = NDOF       # ndofl
-    lcblk[8, :nb] = 0          # nsymdl
-    lcblk[9, :nb] = nshl
-    return lcblk
+# topology -> (lcsyst, nenl, nshl, nfacel)  (genblkPosix.f:62-72, common.h:111)
+_TOPO = {"tet": (1, 4, 4, 4), "hex": (2, 8, 8, 6), "wedge": (3, 6, 6, 5)}
+
+
+def _blocks(groups, ibksiz, ipord=1):
+    """genblkPosix.f:52-96: per topology (file order = order of `groups`),
+    consecutive runs of <= ibksiz elements.  groups: list of (topo, ien1)
+    with ien1 (n, nshl) 1-based.  Returns lcblk(10,nelblk+1) and mien."""
+    cols, mien = [], []
+    first = 1
+    for topo, ien1 in groups:
+        lcsyst, nenl, nshl, nfacel = _TOPO[topo]
+        n = ien1.shape[0]
+        for a in range(0, n, ibksiz):
+            b = min(a + ibksiz, n)
+            cols.append([first + a, 0, lcsyst, ipord, nenl, nfacel, 0, NDOF, 0, nshl])
+            mien.append(np.asfortranarray(ien1[a:b], dtype=np.int32))
+        first += n
+    cols.append([first, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    lcblk = np.asfortranarray(np.array(cols, dtype=np.int32).T)
+    return lcblk, mien
+
+
+def _box_hexes(I, J, K, node_id):
+    """8-node hexes in HexShapeAndDrv order (newshape.cc:431-432): node a at
+    (xi,eta,zeta) = n[a], x = i, y = j, z = k."""
+    off = [(0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0), (0, 0, 1), (1, 0, 1), (1, 1, 1), (0, 1, 1)]
+    return np.stack([node_id(I + a, J + b, K + c) for a, b, c in off], axis=1)
+
+
+def _box_wedges(I, J, K, node_id):
+    """Two 6-node wedges per hex, prism axis along y (wall normal).  The
+    triangles use the (0,0)-(1,1) diagonal of the x-z face, which is the
+    diagonal the Kuhn tets put on that face, so wedge layers are conforming
+    with the tets above them.  Node order (newshape.cc:735-740): 1-3 the
+    zeta=-1 triangle {1-r-s, r, s}, 4-6 the zeta=+1 triangle; ordered so
+    that det(dx/dxi) > 0."""
+    tris = [((0, 0), (1, 1), (1, 0)), ((0, 0), (0, 1), (1, 1))]   # (di,dk); x_r cross x_s points to +y
+    out = []
+    for tri in tris:
+        lo = [node_id(I + di, J, K + dk) for di, dk in tri]
+        hi = [node_id(I + di, J + 1, K + dk) for di, dk in tri]
+        out.append(np.stack(lo + hi, axis=1))
+    return np.stack(out, axis=1).reshape(-1, 6)
 
 
 def _boundary_elements(ien0, x, on_boundary_planes, gnode, ibksiz, natural, seed):
@@ -166,7 +198,8 @@ def _boundary_elements(ien0, x, on_boundary_planes, gnode, ibksiz, natural, seed
 
 
 def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15,
-             bc="channel", periodic_z=True, seed=1234, max_seg=0, only_rank=None, boundary=False, natural="none"):
+             bc="channel", periodic_z=True, seed=1234, max_seg=0, only_rank=None, boundary=False, natural="none",
+             topo="tet", wedge_layers=1):
     """Build `nparts` MeshPart objects for an nx*ny*nz-hex box (6 tets/hex).
 
     bc: "channel"  x-min inflow (velocity code 7 + T), x-max pressure,
@@ -176,6 +209,10 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
                    density BC, random slopes (exercises bc3* branches)
     max_seg: if >0 split ilwork segments to at most this length.
     only_rank: build (and return a 1-list with) just that rank's part.
+    topo: "tet" (6 Kuhn tets per hex), "hex", "wedge" (2 wedges per hex), or
+          "mixed" = `wedge_layers` hex layers at each y wall split into wedges,
+          tets in between (BASELINE.json configs[2]); blocks are grouped by
+          topology, tets first.
     boundary: also generate boundary elements (x-min, x-max, y walls; z faces
               unless periodic) with natural-BC codes per `natural`.
     """
@@ -216,15 +253,33 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
         x[:, 0], x[:, 1], x[:, 2] = X, Y, Z
         gnode = gid(I, J, K)
 
-        ien0 = _box_tets(nxl, ny, nz, lambda a, b, c: lid(a + i0, b, c))
-        numel = ien0.shape[0]
-        ien1 = (ien0 + 1).astype(np.int32)
-        lcblk = _blocks(numel, ibksiz)
-        mien = [np.asfortranarray(ien1[lcblk[0, b] - 1: lcblk[0, b + 1] - 1])
-                for b in range(lcblk.shape[1] - 1)]
-        hexid = (np.arange(nxl)[:, None, None] + i0) * ny * nz + \
-            np.arange(ny)[None, :, None] * nz + np.arange(nz)[None, None, :]
-        gelem = (hexid.ravel()[:, None] * 6 + np.arange(6)[None, :]).ravel()
+        nid = lambda a, b, c: lid(a + i0, b, c)   # noqa: E731
+        hexid = ((np.arange(nxl)[:, None, None] + i0) * ny * nz +
+                 np.arange(ny)[None, :, None] * nz + np.arange(nz)[None, None, :]).ravel()
+        HI, HJ, HK = (a.ravel() for a in np.meshgrid(np.arange(nxl), np.arange(ny), np.arange(nz), indexing="ij"))
+        ien0 = None
+        if topo == "tet":
+            ien0 = _box_tets(nxl, ny, nz, nid)
+            groups = [("tet", ien0 + 1)]
+            gelem = (hexid[:, None] * 6 + np.arange(6)[None, :]).ravel()
+        elif topo == "hex":
+            groups = [("hex", _box_hexes(HI, HJ, HK, nid) + 1)]
+            gelem = hexid * 6
+        elif topo == "wedge":
+            groups = [("wedge", _box_wedges(HI, HJ, HK, nid) + 1)]
+            gelem = (hexid[:, None] * 6 + np.arange(2)[None, :]).ravel()
+        elif topo == "mixed":
+            assert 2 * wedge_layers < ny, "wedge layers must leave tets in between"
+            nearwall = (HJ < wedge_layers) | (HJ >= ny - wedge_layers)
+            tets = _box_tets(nxl, ny, nz, nid).reshape(-1, 6, 4)[~nearwall].reshape(-1, 4)
+            wdg = _box_wedges(HI[nearwall], HJ[nearwall], HK[nearwall], nid)
+            groups = [("tet", tets + 1), ("wedge", wdg + 1)]
+            gelem = np.concatenate([(hexid[~nearwall][:, None] * 6 + np.arange(6)[None, :]).ravel(),
+                                    (hexid[nearwall][:, None] * 6 + np.arange(2)[None, :]).ravel()])
+        else:
+            raise ValueError("topo must be tet, hex, wedge or mixed")
+        numel = int(sum(g[1].shape[0] for g in groups))
+        lcblk, mien = _blocks(groups, ibksiz)
 
         iBC = np.zeros(nn, dtype=np.int32)
         BC = np.zeros((nn, NDOFBC), order="F")
@@ -286,6 +341,7 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
                       x=x, lcblk=lcblk, mien=mien, iBC=iBC, BC=BC, iper=iper,
                       ilwork=ilwork, gnode=gnode, gelem=gelem)
         if boundary:
+            assert topo == "tet", "boundary elements are generated for tet meshes only"
             planes = [J == 0, J == ny]
             if i0 == 0:
                 planes.append(I == 0)

@@ -3,8 +3,11 @@
 Qwt(MAXTOP,MAXQPT), nint(MAXTOP)        phSolver/common/common.h:92-96
 shp(MAXTOP,MAXSH,MAXQPT), shgl(MAXTOP,3,MAXSH,MAXQPT)
                                          phSolver/compressible/elmgmr.f:31-34
-Linear tets only for now: genint.f:30-75 (symtet 1-/4-pt rule, Qwt*4/3),
-genshp.f:34-37 (TetShapeAndDrv p=1, shgl/2).  In production the Fortran host
+Linear tets: genint.f:30-75 (symtet 1-/4-pt rule, Qwt*4/3), genshp.f:34-37
+(TetShapeAndDrv p=1, shgl/2); linear hexes (topology 2): genint.f:105-147
+(symhex 8-pt rule), genshp.f:39-45 (HexShapeAndDrv, newshape.cc:420-500);
+linear wedges (topology 3): genint.f:294-318 (symwdg 6-pt rule), genshp.f:47-53
+(WedgeShapeAndDrv, newshape.cc:706-768).  In production the Fortran host
 passes its own tables; these exist so the Python host mirror and the tests
 can drive the C-ABI without Fortran.  Pinned against the reference's own C
 generators in tests/test_tables.py (golden fixture tests/golden/tables_tet.npz).
@@ -36,6 +39,62 @@ def tri_points(rule):
     raise NotImplementedError("tri quadrature rule %d" % rule)
 
 
+_G2 = 0.577350269189626           # symhex.c / symwdg.c Qp21, Qp22
+_P23, _P24 = 0.166666666666667, 0.666666666666667
+
+
+def hex_points(rule):
+    """symhex 8-pt rule (phSolver/common/symhex.c rstw8/twt8)."""
+    if rule != 2:
+        raise NotImplementedError("hex quadrature rule %d" % rule)
+    pts = np.array([[sx * _G2, sy * _G2, sz * _G2, 0.0]
+                    for sz in (-1, 1) for sy in (-1, 1) for sx in (-1, 1)])
+    return pts, np.full(8, 1.0)
+
+
+def wedge_points(rule):
+    """symwdg 6-pt rule (phSolver/common/symwdg.c rstw6/twt6)."""
+    if rule != 2:
+        raise NotImplementedError("wedge quadrature rule %d" % rule)
+    tri = [(_P23, _P23), (_P24, _P23), (_P23, _P24)]
+    pts = np.array([[r, s, z * _G2, 0.0] for z in (-1, 1) for r, s in tri])
+    return pts, np.full(6, 0.666666666666667)
+
+
+def hex_shape(xi, eta, zeta):
+    """HexShapeAndDrv p=1 (phSolver/common/newshape.cc:420-500), same operation order."""
+    xim, etam, zetam = 1 - xi, 1 - eta, 1 - zeta
+    xip, etap, zetap = 1 + xi, 1 + eta, 1 + zeta
+    N = np.array([0.125 * xim * etam * zetam, 0.125 * xip * etam * zetam, 0.125 * xip * etap * zetam,
+                  0.125 * xim * etap * zetam, 0.125 * xim * etam * zetap, 0.125 * xip * etam * zetap,
+                  0.125 * xip * etap * zetap, 0.125 * xim * etap * zetap])
+    dN = np.array([
+        [-0.125 * etam * zetam, -0.125 * xim * zetam, -0.125 * xim * etam],
+        [0.125 * etam * zetam, -0.125 * xip * zetam, -0.125 * xip * etam],
+        [0.125 * etap * zetam, 0.125 * xip * zetam, -0.125 * xip * etap],
+        [-0.125 * etap * zetam, 0.125 * xim * zetam, -0.125 * xim * etap],
+        [-0.125 * etam * zetap, -0.125 * xim * zetap, 0.125 * xim * etam],
+        [0.125 * etam * zetap, -0.125 * xip * zetap, 0.125 * xip * etam],
+        [0.125 * etap * zetap, 0.125 * xip * zetap, 0.125 * xip * etap],
+        [-0.125 * etap * zetap, 0.125 * xim * zetap, 0.125 * xim * etap]])
+    return N, dN
+
+
+def wedge_shape(r, s, zeta):
+    """WedgeShapeAndDrv p=1 (phSolver/common/newshape.cc:706-768)."""
+    p0, p1, p2, p3 = 1.0 - r - s, r, s, zeta
+    N = np.array([0.5 * p0 * (1.0 - p3), 0.5 * p1 * (1.0 - p3), 0.5 * p2 * (1.0 - p3),
+                  0.5 * p0 * (1.0 + p3), 0.5 * p1 * (1.0 + p3), 0.5 * p2 * (1.0 + p3)])
+    dN = np.array([
+        [-0.25 * (1.0 - p3), -0.25 * (1.0 - p3), -0.5 * p0],
+        [0.25 * (1.0 - p3), 0.0, -0.5 * p1],
+        [0.0, 0.25 * (1.0 - p3), -0.5 * p2],
+        [-0.25 * (1.0 + p3), -0.25 * (1.0 + p3), 0.5 * p0],
+        [0.25 * (1.0 + p3), 0.0, 0.5 * p1],
+        [0.0, 0.25 * (1.0 + p3), 0.5 * p2]])
+    return N, dN
+
+
 def make_tables(rule=2, ruleb=2):
     nint = np.zeros(MAXTOP, dtype=np.int32)
     nintb = np.zeros(MAXTOP, dtype=np.int32)
@@ -54,6 +113,17 @@ def make_tables(rule=2, ruleb=2):
         r, s, t = pts[i, 0], pts[i, 1], pts[i, 2]
         shp[0, :4, i] = [r, s, t, 1.0 - r - s - t]
         shgl[0, :, :4, i] = dN.T / 2.0
+    if rule == 2:
+        # hexes (lcsyst 2) and wedges (lcsyst 3); the reference defines nint(3) only for rules 2..4
+        for top, points, shape, nsh in ((1, hex_points, hex_shape, 8), (2, wedge_points, wedge_shape, 6)):
+            pts, w = points(rule)
+            n = len(w)
+            nint[top] = n
+            Qwt[top, :n] = w
+            for i in range(n):
+                N, d = shape(pts[i, 0], pts[i, 1], pts[i, 2])
+                shp[top, :nsh, i] = N
+                shgl[top, :, :nsh, i] = d.T
     # boundary faces of tets: genint.f:44-75 (symtri, Qwtb*2), genshpb.f
     ptsb, wb = tri_points(ruleb)
     nb = len(wb)

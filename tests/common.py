@@ -12,11 +12,11 @@ def rel_l2(a, b):
 
 
 def make_case(nx, ny, nz, *, nparts=1, bc="channel", periodic_z=True, ibksiz=64, rule=2, seed=1234,
-              max_seg=0, boundary=False, natural="none", **pkw):
+              max_seg=0, boundary=False, natural="none", topo="tet", wedge_layers=1, **pkw):
     params = SolverParams(intg=rule, **pkw)
     tables = make_tables(rule, 2)
     parts = make_box(nx, ny, nz, nparts=nparts, bc=bc, periodic_z=periodic_z, ibksiz=ibksiz, seed=seed,
-                     max_seg=max_seg, boundary=boundary, natural=natural)
+                     max_seg=max_seg, boundary=boundary, natural=natural, topo=topo, wedge_layers=wedge_layers)
     ng = global_node_count(nx, ny, nz)
     states = [make_state(p, ng, seed=seed) for p in parts]
     return params, tables, parts, states

@@ -37,6 +37,23 @@ for n in (1, 3):
     err = C.c_int(0)
     L.symtri_(C.byref(C.c_int(n)), pt.ctypes.data_as(C.c_void_p), wt.ctypes.data_as(C.c_void_p), C.byref(err))
     out["tri%d_pt" % n], out["tri%d_wt" % n] = pt, wt
+# hexes (symhex 8-pt, shphex p=1) and wedges (symwdg 6-pt, shp6w p=1)
+for name, n, sym, shpf, nsh in (("hex", 8, L.symhex_, L.shphex_, 8), ("wdg", 6, L.symwdg_, L.shp6w_, 6)):
+    pt = np.zeros((n, 4))
+    wt = np.zeros(n)
+    err = C.c_int(0)
+    sym(C.byref(C.c_int(n)), pt.ctypes.data_as(C.c_void_p), wt.ctypes.data_as(C.c_void_p), C.byref(err))
+    out["%s%d_pt" % (name, n)], out["%s%d_wt" % (name, n)] = pt, wt
+    N = np.zeros((n, nsh))
+    dN = np.zeros((n, nsh, 3))
+    for i in range(n):
+        Ni = np.zeros(32)
+        dNi = np.zeros((32, 3))
+        par = pt[i, :3].copy()
+        shpf(C.byref(C.c_int(1)), par.ctypes.data_as(C.c_void_p), Ni.ctypes.data_as(C.c_void_p),
+             dNi.ctypes.data_as(C.c_void_p))
+        N[i], dN[i] = Ni[:nsh], dNi[:nsh]
+    out["%s%d_N" % (name, n)], out["%s%d_dN" % (name, n)] = N, dN
 np.savez(os.path.join(ROOT, "tests", "golden", "tables_ref.npz"), **out)
 for k, v in out.items():
     print(k, v.tolist())
