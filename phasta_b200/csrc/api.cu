@@ -16,6 +16,43 @@ static int dev_alloc(T **p, size_t n) {
   return 0;
 }
 
+// Concatenate the blocks of one topology: ien -> [nshl][numel_pad] 0-based, refel -> position in file order.
+static int upload_group(phb200_ctx *ctx, const int *lcblk, const int *const *mien, int lcsyst, int nshl, int *numel_out,
+                        size_t *pad_out, int **d_ien, int **d_refel) {
+  const phb200_common &c = ctx->c;
+  int numel = 0;
+  for (int b = 0; b < c.nelblk; b++) {
+    const int *lc = lcblk + 10 * b;
+    if (lc[2] == lcsyst && lc[9] == nshl) numel += lc[10] - lc[0];
+  }
+  size_t pad = ((size_t)numel + 63) / 64 * 64;
+  if (pad == 0) pad = 64;
+  std::vector<int> ien((size_t)nshl * pad, 0), refel((size_t)(numel ? numel : 1), 0);
+  size_t e0 = 0;
+  for (int b = 0; b < c.nelblk; b++) {
+    const int *lc = lcblk + 10 * b;
+    if (lc[2] != lcsyst || lc[9] != nshl) continue;
+    const int npro = lc[10] - lc[0];
+    const int *ib = mien[b];
+    for (int a = 0; a < nshl; a++)
+      for (int e = 0; e < npro; e++) {
+        int v = ib[e + (size_t)npro * a];
+        if (v < 0) v = -v;
+        if (v < 1 || v > c.nshg) return fail("init", "ien entry out of range");
+        ien[(size_t)a * pad + e0 + e] = v - 1;
+      }
+    for (int e = 0; e < npro; e++) refel[e0 + e] = lc[0] - 1 + e;
+    e0 += npro;
+  }
+  PHB_TRY(dev_alloc(d_ien, ien.size()));
+  PHB_CHECK(cudaMemcpy(*d_ien, ien.data(), sizeof(int) * ien.size(), cudaMemcpyHostToDevice));
+  PHB_TRY(dev_alloc(d_refel, refel.size()));
+  PHB_CHECK(cudaMemcpy(*d_refel, refel.data(), sizeof(int) * refel.size(), cudaMemcpyHostToDevice));
+  *numel_out = numel;
+  *pad_out = pad;
+  return 0;
+}
+
 extern "C" const char *phb200_version(void) { return "phb200 0.1 (sm_100a)"; }
 extern "C" int phb200_sizeof_common(void) { return (int)sizeof(phb200_common); }
 extern "C" int phb200_sizeof_step(void) { return (int)sizeof(phb200_step); }
@@ -53,36 +90,37 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   PHB_CHECK(cudaEventCreate(&ctx->pev0));
   PHB_CHECK(cudaEventCreate(&ctx->pev1));
   const int nshg = c->nshg, numnp = c->numnp;
-  // ---- connectivity: concatenate tet blocks in file order (genblkPosix.f:52-96)
-  int numel = 0;
-  for (int b = 0; b < c->nelblk; b++) {
-    const int *lc = lcblk + 10 * b;
-    int npro = lc[10] - lc[0];
-    if (lc[2] != 1 || lc[9] != 4) return fail("init", "only linear tet blocks (lcsyst=1,nshl=4) supported yet");
-    numel += npro;
-  }
-  if (numel != c->numel) return fail("init", "lcblk does not add up to numel");
-  ctx->numel_tet = numel;
-  ctx->numel_pad = ((size_t)numel + 63) / 64 * 64;
-  if (ctx->numel_pad == 0) ctx->numel_pad = 64;
+  // ---- connectivity: blocks grouped by topology (genblkPosix.f:52-96), file order kept inside a group
   {
-    std::vector<int> ien((size_t)4 * ctx->numel_pad, 0);
-    size_t e0 = 0;
-    for (int b = 0; b < c->nelblk; b++) {
-      const int *lc = lcblk + 10 * b;
-      int npro = lc[10] - lc[0];
-      const int *ib = mien[b];
-      for (int a = 0; a < 4; a++)
-        for (int e = 0; e < npro; e++) {
-          int v = ib[e + (size_t)npro * a];
-          if (v < 0) v = -v;
-          if (v < 1 || v > nshg) return fail("init", "ien entry out of range");
-          ien[(size_t)a * ctx->numel_pad + e0 + e] = v - 1;
-        }
-      e0 += npro;
+    int total = 0;
+    for (int b = 0; b < c->nelblk; b++) total += lcblk[10 * b + 10] - lcblk[10 * b];
+    if (total != c->numel) return fail("init", "lcblk does not add up to numel");
+    int nt = 0;
+    PHB_TRY(upload_group(ctx, lcblk, mien, 1, 4, &nt, &ctx->numel_pad, &ctx->d_ien, &ctx->d_refel_tet));
+    ctx->numel_tet = nt;
+    int covered = nt;
+    const int topo[2][2] = {{2, 8}, {3, 6}};  // hexes, wedges: (lcsyst, nshl)
+    for (int t = 0; t < 2; t++) {
+      ElemGroup g;
+      memset(&g, 0, sizeof g);
+      g.lcsyst = topo[t][0];
+      g.nshl = topo[t][1];
+      g.nq = c->nint[g.lcsyst - 1];
+      g.tab = t;
+      PHB_TRY(upload_group(ctx, lcblk, mien, g.lcsyst, g.nshl, &g.numel, &g.numel_pad, &g.d_ien, &g.d_refel));
+      if (g.numel == 0) {
+        cudaFree(g.d_ien);
+        cudaFree(g.d_refel);
+        continue;
+      }
+      if (g.nq != g.nshl) return fail("init", "hex/wedge blocks need quadrature rule 2 (8-pt hexes, 6-pt wedges)");
+      covered += g.numel;
+      ctx->gen.push_back(g);
     }
-    PHB_TRY(dev_alloc(&ctx->d_ien, ien.size()));
-    PHB_CHECK(cudaMemcpy(ctx->d_ien, ien.data(), sizeof(int) * ien.size(), cudaMemcpyHostToDevice));
+    if (covered != c->numel)
+      return fail("init", "only linear tet (lcsyst=1,nshl=4), hex (2,8) and wedge (3,6) blocks are supported");
+    if (c->nedof < 5 * 4 || (!ctx->gen.empty() && c->nedof < 5 * 6))
+      return fail("init", "nedof smaller than 5*nshl of a block");
   }
   // ---- nodal data
   PHB_TRY(dev_alloc(&ctx->d_x, (size_t)3 * numnp));
@@ -205,6 +243,12 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
                   ctx->d_nodeaos};
   for (void *p : ptrs)
     if (p) cudaFree(p);
+  if (ctx->d_refel_tet) cudaFree(ctx->d_refel_tet);
+  for (ElemGroup &g : ctx->gen) {
+    void *gp[] = {g.d_ien, g.d_refel, g.d_EG, g.d_eloc};
+    for (void *p : gp)
+      if (p) cudaFree(p);
+  }
   if (ctx->h_dots) cudaFreeHost(ctx->h_dots);
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
   cudaEventDestroy(ctx->pev0);
@@ -229,15 +273,17 @@ static int d2h(phb200_ctx *ctx, double *h, const double *d, size_t n) {
   return 0;
 }
 
-// device tiles -> EGmass(numel,nedof,nedof)
-__global__ void k_eg_to_ref(int numel, int nedof, const double *__restrict__ EG, double *__restrict__ out) {
+// device tiles of one topology group -> EGmass(numel,nedof,nedof); rows/columns beyond 5*nshl stay zero
+// (on mixed meshes nedof = 5*max nshl)
+__global__ void k_eg_to_ref(int ngrp, int nd, int numel, int nedof, const int *__restrict__ refel,
+                            const double *__restrict__ EG, double *__restrict__ out) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t tot = (size_t)numel * 400;
+  size_t tot = (size_t)ngrp * nd * nd;
   if (t >= tot) return;
-  size_t e = t % numel;
-  int k = (int)(t / numel), r = k % 20, c = k / 20;
-  out[e + (size_t)numel * (r + (size_t)nedof * c)] =
-      EG[((e / EG_TILE) * 400 + (size_t)(r + 20 * c)) * EG_TILE + (e % EG_TILE)];
+  size_t e = t % ngrp;
+  int k = (int)(t / ngrp), r = k % nd, c = k / nd;
+  out[refel[e] + (size_t)numel * (r + (size_t)nedof * c)] =
+      EG[((e / EG_TILE) * (size_t)(nd * nd) + (size_t)(r + nd * c)) * EG_TILE + (e % EG_TILE)];
 }
 
 extern "C" int phb200_set_state(phb200_ctx *ctx, const double *y, const double *ac) {
@@ -286,14 +332,24 @@ extern "C" int phb200_get_egmass(phb200_ctx *ctx, double *EGmass) {
   ENTER(ctx);
   const int numel = ctx->c.numel, nedof = ctx->c.nedof;
   if (numel == 0) return 0;
-  if (!ctx->d_EG) return fail("get_egmass", "no EBE LHS has been assembled");
+  if (!ctx->have_lhs) return fail("get_egmass", "no EBE LHS has been assembled");
   double *d_out = nullptr;
   size_t tot = (size_t)numel * nedof * nedof;
   PHB_CHECK(cudaMalloc(&d_out, sizeof(double) * tot));
   PHB_CHECK(cudaMemsetAsync(d_out, 0, sizeof(double) * tot, ctx->stream));
-  size_t nthr = (size_t)numel * 400;
-  k_eg_to_ref<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(numel, nedof, ctx->d_EG, d_out);
-  ctx->launches++;
+  if (ctx->numel_tet > 0) {
+    size_t nthr = (size_t)ctx->numel_tet * 400;
+    k_eg_to_ref<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(ctx->numel_tet, 20, numel, nedof,
+                                                                         ctx->d_refel_tet, ctx->d_EG, d_out);
+    ctx->launches++;
+  }
+  for (const ElemGroup &g : ctx->gen) {
+    const int nd = 5 * g.nshl;
+    size_t nthr = (size_t)g.numel * nd * nd;
+    k_eg_to_ref<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(g.numel, nd, numel, nedof, g.d_refel, g.d_EG,
+                                                                         d_out);
+    ctx->launches++;
+  }
   PHB_CHECK(cudaGetLastError());
   PHB_TRY(d2h(ctx, EGmass, d_out, tot));
   PHB_CHECK(cudaStreamSynchronize(ctx->stream));

@@ -39,6 +39,15 @@ struct TriTables {
   double dN[3][4][3];  // shglb(1,i,a,q)
   double Qwt[3];       // Qwtb(1,q)
 };
+// hexes (index 0, lcsyst 2) and wedges (index 1, lcsyst 3): N[q][a] = shp(lcsyst,a,q),
+// dN[q][a][i] = shgl(lcsyst,i,a,q), Qwt[q] = Qwt(lcsyst,q)
+struct GenTables {
+  int nq, nshl;
+  double N[8][8];
+  double dN[8][8][3];
+  double Qwt[8];
+};
+__constant__ GenTables c_gen[2];
 __constant__ TetTables c_tet;
 __constant__ TriTables c_tri;
 __constant__ PhysParams c_ph;
@@ -49,7 +58,8 @@ int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, co
   memset(&t, 0, sizeof t);
   const phb200_common &c = ctx->c;
   t.nq = c.nint[0];
-  if (t.nq != 1 && t.nq != 4) {
+  if (ctx->numel_tet == 0 && t.nq != 1 && t.nq != 4) t.nq = 0;
+  if (ctx->numel_tet > 0 && t.nq != 1 && t.nq != 4) {
     fprintf(stderr, "phb200: init: tet rule with %d points not supported\n", t.nq);
     return 1;
   }
@@ -75,6 +85,22 @@ int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, co
     return 1;
   }
   PHB_CHECK(cudaMemcpyToSymbol(c_tet, &t, sizeof t));
+  for (const ElemGroup &g : ctx->gen) {
+    GenTables gt;
+    memset(&gt, 0, sizeof gt);
+    const int top = g.lcsyst - 1;
+    gt.nq = g.nq;
+    gt.nshl = g.nshl;
+    for (int q = 0; q < g.nq; q++) {
+      gt.Qwt[q] = c.Qwt[top + PHB200_MAXTOP * q];
+      for (int a = 0; a < g.nshl; a++) {
+        gt.N[q][a] = shp[top + PHB200_MAXTOP * (a + PHB200_MAXSH * q)];
+        for (int i = 0; i < 3; i++)
+          gt.dN[q][a][i] = shgl[top + PHB200_MAXTOP * (i + 3 * (a + PHB200_MAXSH * q))];
+      }
+    }
+    PHB_CHECK(cudaMemcpyToSymbol(c_gen, &gt, sizeof gt, sizeof(GenTables) * g.tab));
+  }
   if (ctx->numelb > 0) {
     TriTables b;
     memset(&b, 0, sizeof b);
@@ -400,6 +426,75 @@ __device__ __forceinline__ int bc_elim_mask(int ibc) {
   return m;
 }
 
+// Tail of AsIGMR for one (a,b) block of one element: BDiag extraction before the BCs (asigmr.f:92-102, SURVEY
+// B3), bc3LHS on the block in registers (bc3lhs.f:1-290; rows by node a's code, columns by node b's), then the
+// coalesced store into the element tile (LHS==1) or the fillsparseC scatter into lhsK (LHS==2).
+template <int LHS, int NSHL>
+__device__ __forceinline__ void finish_block(double (&acc)[5][5], int a, int b, int ge, int numel, size_t numel_pad,
+                                             int nshg, int na, int nb, int ibca, int ibcb,
+                                             const double *__restrict__ BC, double *__restrict__ BDiag,
+                                             double *__restrict__ EG, const int *__restrict__ eloc,
+                                             double *__restrict__ lhsK) {
+  constexpr int ND = 5 * NSHL;
+  if (ge < numel) {
+    if (a == b && c_ph.iprec != 0) {
+#pragma unroll
+      for (int m = 0; m < 5; m++)
+#pragma unroll
+        for (int n = 0; n < 5; n++) atomicAdd(BDiag + (size_t)nshg * (m + 5 * n) + na, acc[m][n]);
+    }
+    if (ibca | ibcb) {
+      // local view with dofs {p,u1,u2,u3,T} = indices 0..4; bc_rows/cols use 1..3 for velocities
+      const int codea = (ibca >> 3) & 7, codeb = (ibcb >> 3) & 7;
+      if (codea != 0 && codea != 7) {
+        const double bc[3] = {__ldg(BC + (size_t)nshg * 3 + na), __ldg(BC + (size_t)nshg * 4 + na),
+                              __ldg(BC + (size_t)nshg * 5 + na)};
+        bc_rows(codea, bc, acc);
+      }
+      if (codeb != 0 && codeb != 7) {
+        const double bc[3] = {__ldg(BC + (size_t)nshg * 3 + nb), __ldg(BC + (size_t)nshg * 4 + nb),
+                              __ldg(BC + (size_t)nshg * 5 + nb)};
+        bc_cols(codeb, bc, acc);
+      }
+      const int ma = bc_elim_mask(ibca), mb = bc_elim_mask(ibcb);
+#pragma unroll
+      for (int m = 0; m < 5; m++)
+#pragma unroll
+        for (int n = 0; n < 5; n++) {
+          if (((ma >> m) & 1) | ((mb >> n) & 1)) acc[m][n] = 0.0;
+        }
+      if (a == b) {
+#pragma unroll
+        for (int m = 0; m < 5; m++)
+          if ((ma >> m) & 1) acc[m][m] = 1.0;
+      }
+    }
+  }
+  if (LHS == 2) {
+    // fillsparseC (fillsparse.f:66-126): lhsK(f+5g, k) += EGmass(e, r+f, s+g); the block index k
+    // comes from the precomputed sparseloc map
+    if (ge < numel) {
+      const int k = eloc[(size_t)(NSHL * a + b) * numel_pad + ge];
+      double *blk = lhsK + (size_t)25 * k;
+#pragma unroll
+      for (int n = 0; n < 5; n++)
+#pragma unroll
+        for (int m = 0; m < 5; m++) atomicAdd(blk + m + 5 * n, acc[m][n]);
+    }
+  } else {
+    // coalesced store of the block (also for padding lanes: zeros)
+    const size_t gtile = (size_t)ge / EG_TILE;
+    const int gl = ge % EG_TILE;
+    double *base = EG + gtile * (size_t)(ND * ND * EG_TILE) + gl;
+    const bool ok = ge < numel;
+#pragma unroll
+    for (int n = 0; n < 5; n++)
+#pragma unroll
+      for (int m = 0; m < 5; m++)
+        base[(size_t)((5 * a + m) + ND * (5 * b + n)) * EG_TILE] = ok ? acc[m][n] : 0.0;
+  }
+}
+
 // phase B' (e3wmlt.f:74-145): rl = W (N_a,i ri_i) + N_a W ri(16:20), one thread per (element, node)
 template <int TILE_E, int NQ>
 __device__ __forceinline__ void phase_bprime(const AsmSmem<TILE_E, NQ> &sm, int el, int sub, bool live, int nshg,
@@ -565,67 +660,8 @@ __device__ __forceinline__ void phase_b(const AsmSmem<TILE_E, NQ> &sm, int warp,
           }
           acc[4][4] += W * scon * gagb;
         }
-        if (ge < numel) {
-          const int na = sm.nd[a][le], nb = sm.nd[b][le];
-          // BDiag extraction BEFORE bc3LHS (asigmr.f:92-102)
-          if (a == b && c_ph.iprec != 0) {
-#pragma unroll
-            for (int m = 0; m < 5; m++)
-#pragma unroll
-              for (int n = 0; n < 5; n++) atomicAdd(BDiag + (size_t)nshg * (m + 5 * n) + na, acc[m][n]);
-          }
-          // bc3LHS (bc3lhs.f:1-290) on this block: rows by node a, columns by node b
-          const int ibca = sm.ibc[a][le], ibcb = sm.ibc[b][le];
-          if (ibca | ibcb) {
-            // local view with dofs {p,u1,u2,u3,T} = indices 0..4; bc_rows/cols use 1..3 for velocities
-            const int codea = (ibca >> 3) & 7, codeb = (ibcb >> 3) & 7;
-            if (codea != 0 && codea != 7) {
-              const double bc[3] = {__ldg(BC + (size_t)nshg * 3 + na), __ldg(BC + (size_t)nshg * 4 + na),
-                                    __ldg(BC + (size_t)nshg * 5 + na)};
-              bc_rows(codea, bc, acc);
-            }
-            if (codeb != 0 && codeb != 7) {
-              const double bc[3] = {__ldg(BC + (size_t)nshg * 3 + nb), __ldg(BC + (size_t)nshg * 4 + nb),
-                                    __ldg(BC + (size_t)nshg * 5 + nb)};
-              bc_cols(codeb, bc, acc);
-            }
-            const int ma = bc_elim_mask(ibca), mb = bc_elim_mask(ibcb);
-#pragma unroll
-            for (int m = 0; m < 5; m++)
-#pragma unroll
-              for (int n = 0; n < 5; n++) {
-                if (((ma >> m) & 1) | ((mb >> n) & 1)) acc[m][n] = 0.0;
-              }
-            if (a == b) {
-#pragma unroll
-              for (int m = 0; m < 5; m++)
-                if ((ma >> m) & 1) acc[m][m] = 1.0;
-            }
-          }
-        }
-        if (LHS == 2) {
-          // fillsparseC (fillsparse.f:66-126): lhsK(f+5g, k) += EGmass(e, r+f, s+g); the block index k
-          // comes from the precomputed sparseloc map
-          if (ge < numel) {
-            const int k = eloc[(size_t)(4 * a + b) * numel_pad + ge];
-            double *blk = lhsK + (size_t)25 * k;
-#pragma unroll
-            for (int n = 0; n < 5; n++)
-#pragma unroll
-              for (int m = 0; m < 5; m++) atomicAdd(blk + m + 5 * n, acc[m][n]);
-          }
-        } else {
-          // coalesced store of the block (also for padding lanes: zeros)
-          const size_t gtile = (size_t)ge / EG_TILE;
-          const int gl = ge % EG_TILE;
-          double *base = EG + gtile * (size_t)(400 * EG_TILE) + gl;
-          const bool ok = ge < numel;
-#pragma unroll
-          for (int n = 0; n < 5; n++)
-#pragma unroll
-            for (int m = 0; m < 5; m++)
-              base[(size_t)((5 * a + m) + 20 * (5 * b + n)) * EG_TILE] = ok ? acc[m][n] : 0.0;
-        }
+        finish_block<LHS, 4>(acc, a, b, ge, numel, numel_pad, nshg, sm.nd[a][le], sm.nd[b][le], sm.ibc[a][le],
+                             sm.ibc[b][le], BC, BDiag, EG, eloc, lhsK);
       }
 }
 
@@ -1400,6 +1436,403 @@ int phb_bc3per(phb200_ctx *ctx, double *d_r, int n) {
   return 0;
 }
 
+
+// ===========================================================================
+// Generic-topology element kernels (hexes lcsyst=2 / nshl=8 / 8-pt rule, wedges lcsyst=3 / nshl=6 / 6-pt rule).
+// Same phases and the same rank-2 algebra as the tet kernel, but N_a,i and W vary from point to point
+// (e3metric.f:22-77 per quadrature point) and g_ij is the plain xi,x^T xi,x (e3tau.f:1408-1431).
+// ===========================================================================
+template <int NSHL>
+struct GenMetric {
+  double shg[NSHL][3];
+  double dxidx[3][3];
+  double W;
+};
+
+template <int NSHL>
+__device__ __forceinline__ void gen_metric(const double xl[NSHL][3], const double (*dN)[3], double Qw,
+                                           GenMetric<NSHL> &g) {
+  double d[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int n = 0; n < NSHL; n++) s += xl[n][i] * dN[n][j];
+      d[i][j] = s;
+    }
+  double (*x)[3] = g.dxidx;
+  x[0][0] = d[1][1] * d[2][2] - d[2][1] * d[1][2];
+  x[0][1] = d[2][1] * d[0][2] - d[0][1] * d[2][2];
+  x[0][2] = d[0][1] * d[1][2] - d[0][2] * d[1][1];
+  double tmp = 1.0 / (x[0][0] * d[0][0] + x[0][1] * d[1][0] + x[0][2] * d[2][0]);
+  x[0][0] *= tmp; x[0][1] *= tmp; x[0][2] *= tmp;
+  x[1][0] = (d[1][2] * d[2][0] - d[1][0] * d[2][2]) * tmp;
+  x[1][1] = (d[0][0] * d[2][2] - d[2][0] * d[0][2]) * tmp;
+  x[1][2] = (d[1][0] * d[0][2] - d[0][0] * d[1][2]) * tmp;
+  x[2][0] = (d[1][0] * d[2][1] - d[1][1] * d[2][0]) * tmp;
+  x[2][1] = (d[2][0] * d[0][1] - d[0][0] * d[2][1]) * tmp;
+  x[2][2] = (d[0][0] * d[1][1] - d[0][1] * d[1][0]) * tmp;
+  g.W = Qw / tmp;
+#pragma unroll
+  for (int n = 0; n < NSHL; n++)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+      g.shg[n][i] = dN[n][0] * x[0][i] + dN[n][1] * x[1][i] + dN[n][2] * x[2][i];
+}
+
+// AsIq + e3q for any topology: thread per element, quadrature loop inside
+template <int NSHL>
+__global__ void __launch_bounds__(64) k_asiq_gen(int tab, int numel, size_t numel_pad, int nshg, int numnp,
+                                                  const int *__restrict__ ien, const double *__restrict__ x,
+                                                  const double *__restrict__ y, double *__restrict__ qres,
+                                                  double *__restrict__ rmass) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= numel) return;
+  const GenTables &T = c_gen[tab];
+  int nd[NSHL];
+  double xl[NSHL][3], yl[NSHL][5];
+#pragma unroll
+  for (int a = 0; a < NSHL; a++) {
+    nd[a] = ien[(size_t)a * numel_pad + e];
+#pragma unroll
+    for (int i = 0; i < 3; i++) xl[a][i] = __ldg(x + (size_t)numnp * i + nd[a]);
+    gather_y(y, nshg, nd[a], yl[a]);
+  }
+  const double cp = c_ph.Rgas * c_ph.gamma / c_ph.gamma1;
+#pragma unroll 1
+  for (int q = 0; q < T.nq; q++) {
+    GenMetric<NSHL> g;
+    gen_metric<NSHL>(xl, T.dN[q], T.Qwt[q], g);
+    double Y[5] = {0, 0, 0, 0, 0};
+    double gr[3][5];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int m = 0; m < 5; m++) gr[i][m] = 0.0;
+#pragma unroll
+    for (int a = 0; a < NSHL; a++) {
+      const double Na = T.N[q][a];
+#pragma unroll
+      for (int m = 0; m < 5; m++) {
+        Y[m] += Na * yl[a][m];
+#pragma unroll
+        for (int i = 0; i < 3; i++) gr[i][m] += g.shg[a][i] * yl[a][m];
+      }
+    }
+    double mu, lam, con;
+    diffusivities(Y[4], cp, mu, lam, con);
+    double f[3][4];
+    diff_flux(gr, Y[1], Y[2], Y[3], mu, lam, con, f);
+#pragma unroll
+    for (int a = 0; a < NSHL; a++) {
+      const double nw = T.N[q][a] * g.W;
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int m = 0; m < 4; m++) atomicAdd(qres + (size_t)nshg * (4 * i + m) + nd[a], nw * f[i][m]);
+      atomicAdd(rmass + nd[a], nw);
+    }
+  }
+}
+
+template <int NSHL, int NQ>
+struct GenSmem {
+  double st[NQ][S_NVAR][32];
+  double ri[NQ][20][32];
+  double shg[NQ][3 * NSHL][32];
+  double W[NQ][32];
+  int nd[NSHL][32];
+  int ibc[NSHL][32];
+};
+
+// LHS: 0 residual only, 1 EBE tiles, 2 fillsparseC into lhsK.  CTA = 32 elements x NQ quadrature points.
+template <int NSHL, int NQ, int LHS>
+__global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
+    int tab, int numel, size_t numel_pad, int nshg, int ntiles, const int *__restrict__ ien,
+    const double *__restrict__ aos, const int *__restrict__ iBC, const double *__restrict__ BC,
+    double *__restrict__ res, double *__restrict__ BDiag, double *__restrict__ EG, const int *__restrict__ eloc,
+    double *__restrict__ lhsK) {
+  static_assert(NQ >= NSHL, "phase B' maps one thread group per node");
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  GenSmem<NSHL, NQ> &sm = *reinterpret_cast<GenSmem<NSHL, NQ> *>(smem_raw);
+  const GenTables &T = c_gen[tab];
+  const int tid = threadIdx.x, el = tid & 31, sub = tid >> 5;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int e = tile * 32 + el;
+    const bool live = e < numel;
+    // ------------------------------ phase A: thread = (element, quadrature point) ------------------
+    {
+      const int q = sub;
+      int nd[NSHL];
+      double xl[NSHL][3];
+#pragma unroll
+      for (int a = 0; a < NSHL; a++) {
+        nd[a] = live ? ien[(size_t)a * numel_pad + e] : 0;
+        const double2 *rec = reinterpret_cast<const double2 *>(aos + (size_t)nd[a] * NREC);
+        const double2 v0 = __ldg(rec), v1 = __ldg(rec + 1);
+        xl[a][0] = v0.x; xl[a][1] = v0.y; xl[a][2] = v1.x;
+      }
+      GenMetric<NSHL> g;
+      gen_metric<NSHL>(xl, T.dN[q], T.Qwt[q], g);
+      if (q == 0) {
+#pragma unroll
+        for (int a = 0; a < NSHL; a++) {
+          sm.nd[a][el] = nd[a];
+          sm.ibc[a][el] = __ldg(iBC + nd[a]);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NSHL; a++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) sm.shg[q][3 * a + i][el] = g.shg[a][i];
+      sm.W[q][el] = g.W;
+      double Y[5] = {0, 0, 0, 0, 0}, At[5] = {0, 0, 0, 0, 0};
+      double gr[3][5];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int m = 0; m < 5; m++) gr[i][m] = 0.0;
+      double divq[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int a = 0; a < NSHL; a++) {
+        const double2 *rec = reinterpret_cast<const double2 *>(aos + (size_t)nd[a] * NREC);
+        const double2 v1 = __ldg(rec + 1), v2 = __ldg(rec + 2), v3 = __ldg(rec + 3), v4 = __ldg(rec + 4),
+                      v5 = __ldg(rec + 5), v6 = __ldg(rec + 6);
+        const double yl[5] = {v1.y, v2.x, v2.y, v3.x, v3.y};
+        const double al[5] = {v4.x, v4.y, v5.x, v5.y, v6.x};
+        const double Na = T.N[q][a];
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+          Y[m] += Na * yl[m];
+          At[m] += Na * al[m];
+#pragma unroll
+          for (int i = 0; i < 3; i++) gr[i][m] += g.shg[a][i] * yl[m];
+        }
+        if (c_ph.idiff >= 1) {  // div q (e3ivar.f:374-395)
+          const double2 v7 = __ldg(rec + 7), v8 = __ldg(rec + 8), v9 = __ldg(rec + 9), v10 = __ldg(rec + 10),
+                        v11 = __ldg(rec + 11), v12 = __ldg(rec + 12);
+          const double ql[12] = {v6.y, v7.x, v7.y, v8.x, v8.y, v9.x, v9.y, v10.x, v10.y, v11.x, v11.y, v12.x};
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int m = 0; m < 4; m++) divq[m] += g.shg[a][i] * ql[4 * i + m];
+        }
+      }
+      // e3gijd, lcsyst >= 2 (e3tau.f:1408-1431)
+      const double (*d)[3] = g.dxidx;
+      double gij[6];
+      gij[0] = d[0][0] * d[0][0] + d[1][0] * d[1][0] + d[2][0] * d[2][0];
+      gij[1] = d[0][0] * d[0][1] + d[1][0] * d[1][1] + d[2][0] * d[2][1];
+      gij[2] = d[0][1] * d[0][1] + d[1][1] * d[1][1] + d[2][1] * d[2][1];
+      gij[3] = d[0][0] * d[0][2] + d[1][0] * d[1][2] + d[2][0] * d[2][2];
+      gij[4] = d[0][1] * d[0][2] + d[1][1] * d[1][2] + d[2][1] * d[2][2];
+      gij[5] = d[0][2] * d[0][2] + d[1][2] * d[1][2] + d[2][2] * d[2][2];
+      double ri[20], st[S_NVAR];
+      point_math(Y, At, gr, divq, gij, ri, st);
+#pragma unroll
+      for (int k = 0; k < 20; k++) sm.ri[q][k][el] = ri[k];
+      if (LHS) {
+#pragma unroll
+        for (int k = 0; k < S_NVAR; k++) sm.st[q][k][el] = st[k];
+      }
+    }
+    __syncthreads();
+    // ------------------------------ phase B' (e3wmlt.f:74-145): thread = (element, node) -----------
+    if (sub < NSHL) {
+      const int a = sub;
+      double rl[5] = {0, 0, 0, 0, 0};
+#pragma unroll 1
+      for (int q = 0; q < NQ; q++) {
+        const double W = sm.W[q][el], Na = T.N[q][a];
+        const double s0 = sm.shg[q][3 * a][el], s1 = sm.shg[q][3 * a + 1][el], s2 = sm.shg[q][3 * a + 2][el];
+#pragma unroll
+        for (int m = 0; m < 5; m++)
+          rl[m] += W * (s0 * sm.ri[q][m][el] + s1 * sm.ri[q][5 + m][el] + s2 * sm.ri[q][10 + m][el]) +
+                   Na * W * sm.ri[q][15 + m][el];
+      }
+      if (live) {
+        const int node = sm.nd[a][el];
+#pragma unroll
+        for (int m = 0; m < 5; m++) atomicAdd(res + (size_t)nshg * m + node, rl[m]);
+      }
+    }
+    // ------------------------------ phase B: warp-task = (a,b) block, lane = element ---------------
+    if (LHS) {
+      const int lane = el, warp = sub;
+      const int ge = tile * 32 + lane;
+#pragma unroll 1
+      for (int pair = warp; pair < NSHL * NSHL; pair += NQ) {
+        const int a = pair / NSHL, b = pair % NSHL;
+        double acc[5][5];
+#pragma unroll
+        for (int m = 0; m < 5; m++)
+#pragma unroll
+          for (int n = 0; n < 5; n++) acc[m][n] = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < NQ; q++) {
+          const double W = sm.W[q][lane];
+          const double ga[3] = {sm.shg[q][3 * a][lane], sm.shg[q][3 * a + 1][lane], sm.shg[q][3 * a + 2][lane]};
+          const double gb[3] = {sm.shg[q][3 * b][lane], sm.shg[q][3 * b + 1][lane], sm.shg[q][3 * b + 2][lane]};
+          const double gagb = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+          const double rho = sm.st[q][S_RHO][lane];
+          const double u[3] = {sm.st[q][S_U1][lane], sm.st[q][S_U2][lane], sm.st[q][S_U3][lane]};
+          const double drdp = sm.st[q][S_DRDP][lane], drdT = sm.st[q][S_DRDT][lane];
+          const double e1p = sm.st[q][S_E1P][lane], e3p = sm.st[q][S_E3P][lane], e4p = sm.st[q][S_E4P][lane];
+          const double tw1 = W * sm.st[q][S_TAU1][lane], tw2 = W * sm.st[q][S_TAU2][lane],
+                       tw3 = W * sm.st[q][S_TAU3][lane];
+          const double mu = sm.st[q][S_MU][lane], lam = sm.st[q][S_LAM][lane], con = sm.st[q][S_CON][lane];
+          const double Na = T.N[q][a], Nb = T.N[q][b];
+          const double w[5] = {rho, rho * u[0], rho * u[1], rho * u[2], e3p};
+          const double al_a = u[0] * ga[0] + u[1] * ga[1] + u[2] * ga[2];
+          const double al_b = u[0] * gb[0] + u[1] * gb[1] + u[2] * gb[2];
+          // Tm = W (At_a tau + Na I), see phase_b of the tet kernel
+          double Tm[5][5];
+          {
+            const double c1 = al_a * drdp * tw1, c5 = al_a * drdT * tw3, aR = al_a * rho * tw2;
+            Tm[0][0] = c1;
+            Tm[1][0] = c1 * u[0] + ga[0] * tw1;
+            Tm[2][0] = c1 * u[1] + ga[1] * tw1;
+            Tm[3][0] = c1 * u[2] + ga[2] * tw1;
+            Tm[4][0] = al_a * tw1 * (e1p + 1.0);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+              const double gj = ga[j] * tw2;
+#pragma unroll
+              for (int m = 0; m < 5; m++) Tm[m][1 + j] = w[m] * gj;
+              Tm[1 + j][1 + j] += aR;
+              Tm[4][1 + j] += aR * u[j];
+            }
+            Tm[0][4] = c5;
+            Tm[1][4] = c5 * u[0];
+            Tm[2][4] = c5 * u[1];
+            Tm[3][4] = c5 * u[2];
+            Tm[4][4] = al_a * e4p * tw3;
+            const double WNa = W * Na;
+#pragma unroll
+            for (int m = 0; m < 5; m++) Tm[m][m] += WNa;
+          }
+          {
+            const double alp = al_b + c_ph.fct1 * Nb;
+            const double c1 = alp * drdp, c5 = alp * drdT, aR = alp * rho;
+            double bc[5];
+            bc[0] = c1;
+            bc[1] = c1 * u[0] + gb[0];
+            bc[2] = c1 * u[1] + gb[1];
+            bc[3] = c1 * u[2] + gb[2];
+            bc[4] = alp * e1p + al_b;
+#pragma unroll
+            for (int m = 0; m < 5; m++) {
+              double sacc = acc[m][0];
+#pragma unroll
+              for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
+              acc[m][0] = sacc;
+            }
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+#pragma unroll
+              for (int k = 0; k < 5; k++) bc[k] = w[k] * gb[j];
+              bc[1 + j] += aR;
+              bc[4] += aR * u[j];
+#pragma unroll
+              for (int m = 0; m < 5; m++) {
+                double sacc = acc[m][1 + j];
+#pragma unroll
+                for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
+                acc[m][1 + j] = sacc;
+              }
+            }
+            bc[0] = c5;
+            bc[1] = c5 * u[0];
+            bc[2] = c5 * u[1];
+            bc[3] = c5 * u[2];
+            bc[4] = alp * e4p;
+#pragma unroll
+            for (int m = 0; m < 5; m++) {
+              double sacc = acc[m][4];
+#pragma unroll
+              for (int k = 0; k < 5; k++) sacc += Tm[m][k] * bc[k];
+              acc[m][4] = sacc;
+            }
+          }
+          // viscous block N_a,i K_ij N_b,j W (e3visc.f:69-139, e3wmlt.f:154-223) at this point
+          {
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+              for (int sdx = 0; sdx < 3; sdx++)
+                acc[1 + r][1 + sdx] += W * (mu * ga[sdx] * gb[r] + lam * ga[r] * gb[sdx]);
+            const double d0 = W * mu * gagb;
+            acc[1][1] += d0;
+            acc[2][2] += d0;
+            acc[3][3] += d0;
+#pragma unroll
+            for (int sdx = 0; sdx < 3; sdx++) {
+              double ee = mu * u[sdx] * gagb;
+#pragma unroll
+              for (int r = 0; r < 3; r++) ee += mu * u[r] * ga[sdx] * gb[r] + lam * u[r] * ga[r] * gb[sdx];
+              acc[4][1 + sdx] += W * ee;
+            }
+            acc[4][4] += W * con * gagb;
+          }
+        }
+        finish_block<LHS, NSHL>(acc, a, b, ge, numel, numel_pad, nshg, sm.nd[a][lane], sm.nd[b][lane],
+                                sm.ibc[a][lane], sm.ibc[b][lane], BC, BDiag, EG, eloc, lhsK);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <int NSHL, int NQ, int LHS>
+static int launch_asigmr_gen(phb200_ctx *ctx, const ElemGroup &g) {
+  const size_t smem = sizeof(GenSmem<NSHL, NQ>);
+  auto kern = k_asigmr_gen<NSHL, NQ, LHS>;
+  static bool configured = false;
+  if (!configured) {
+    PHB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int ntiles = (g.numel + 31) / 32;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32 * NQ, smem);
+  if (occ < 1) occ = 1;
+  int grid = nsm * occ;
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  KScope ks(ctx, KC_ASM);
+  kern<<<grid, 32 * NQ, smem, ctx->stream>>>(g.tab, g.numel, g.numel_pad, ctx->c.nshg, ntiles, g.d_ien,
+                                             ctx->d_nodeaos, ctx->d_iBC, ctx->d_BC, ctx->d_res, ctx->d_BDiag, g.d_EG,
+                                             g.d_eloc, ctx->d_lhsK);
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
+
+template <int NSHL, int NQ>
+static int launch_asigmr_gen_mode(phb200_ctx *ctx, const ElemGroup &g, int mode) {
+  if (mode == 1) return launch_asigmr_gen<NSHL, NQ, 1>(ctx, g);
+  if (mode == 2) return launch_asigmr_gen<NSHL, NQ, 2>(ctx, g);
+  return launch_asigmr_gen<NSHL, NQ, 0>(ctx, g);
+}
+
+// EBE storage on first use: 8 * (5 nshl)^2 bytes per element and topology
+int phb_alloc_eg(phb200_ctx *ctx) {
+  if (!ctx->d_EG) {
+    PHB_CHECK(cudaMalloc(&ctx->d_EG, sizeof(double) * ctx->numel_pad * 400));
+    PHB_CHECK(cudaMemsetAsync(ctx->d_EG, 0, sizeof(double) * ctx->numel_pad * 400, ctx->stream));
+  }
+  for (ElemGroup &g : ctx->gen)
+    if (!g.d_EG) {
+      const size_t n = g.numel_pad * (size_t)(25 * g.nshl * g.nshl);
+      PHB_CHECK(cudaMalloc(&g.d_EG, sizeof(double) * n));
+      PHB_CHECK(cudaMemsetAsync(g.d_EG, 0, sizeof(double) * n, ctx->stream));
+    }
+  return 0;
+}
+
 template <int TILE_E, int NQ, int LHS>
 static int launch_asigmr(phb200_ctx *ctx) {
   const phb200_common &c = ctx->c;
@@ -1471,6 +1904,17 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
                                                               ctx->d_rmass);
       PHB_CHECK(cudaGetLastError());
     }
+    for (const ElemGroup &g : ctx->gen) {
+      KScope ks(ctx, KC_ASIQ);
+      const int nb = (g.numel + 63) / 64;
+      if (g.nshl == 8)
+        k_asiq_gen<8><<<nb, 64, 0, s>>>(g.tab, g.numel, g.numel_pad, nshg, c.numnp, g.d_ien, ctx->d_x, ctx->d_y,
+                                        ctx->d_qres, ctx->d_rmass);
+      else
+        k_asiq_gen<6><<<nb, 64, 0, s>>>(g.tab, g.numel, g.numel_pad, nshg, c.numnp, g.d_ien, ctx->d_x, ctx->d_y,
+                                        ctx->d_qres, ctx->d_rmass);
+      PHB_CHECK(cudaGetLastError());
+    }
     // qpbc (qpbc.f:37-95)
     PHB_TRY(phb_commu(ctx, ctx->d_qres, 12, 0));
     PHB_TRY(phb_commu(ctx, ctx->d_rmass, 1, 0));
@@ -1509,12 +1953,9 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
     }
     PHB_CHECK(cudaMemsetAsync(ctx->d_lhsK, 0, sizeof(double) * 25 * (size_t)ctx->nnz_tot, s));
   }
-  if (st->lhs == 1 && !sparse && !ctx->d_EG) {  // EBE storage on first use (3200 B/element)
-    PHB_CHECK(cudaMalloc(&ctx->d_EG, sizeof(double) * ctx->numel_pad * 400));
-    PHB_CHECK(cudaMemsetAsync(ctx->d_EG, 0, sizeof(double) * ctx->numel_pad * 400, s));
-  }
+  if (st->lhs == 1 && !sparse) PHB_TRY(phb_alloc_eg(ctx));  // EBE storage on first use (3200 B per tet)
+  const int mode = (st->lhs == 1) ? (sparse ? 2 : 1) : 0;
   if (ctx->numel_tet > 0) {
-    const int mode = (st->lhs == 1) ? (sparse ? 2 : 1) : 0;
     static const bool use_ws = !(getenv("PHB200_ASM_WS") && atoi(getenv("PHB200_ASM_WS")) == 0);
     if (nq == 4 && use_ws && ctx->tet_uniform_rule) {
       if (mode == 1) PHB_TRY((launch_asigmr_ws<1>(ctx)));
@@ -1529,6 +1970,10 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
       else if (mode == 2) PHB_TRY((launch_asigmr<32, 1, 2>(ctx)));
       else PHB_TRY((launch_asigmr<32, 1, 0>(ctx)));
     }
+  }
+  for (const ElemGroup &g : ctx->gen) {
+    if (g.nshl == 8) PHB_TRY((launch_asigmr_gen_mode<8, 8>(ctx, g, mode)));
+    else PHB_TRY((launch_asigmr_gen_mode<6, 6>(ctx, g, mode)));
   }
   if (st->lhs == 1) {
     if (sparse) ctx->have_lhs_sparse = true; else ctx->have_lhs = true;

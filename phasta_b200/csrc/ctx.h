@@ -32,6 +32,19 @@ __host__ __device__ inline size_t eg_index(size_t e, int r, int c, int nedof) {
   return ((e / EG_TILE) * (size_t)(nedof * nedof) + (size_t)(r + nedof * c)) * EG_TILE + (e % EG_TILE);
 }
 
+// interior elements of one non-tet topology (hexes lcsyst=2, wedges lcsyst=3),
+// handled by the generic-topology kernels; same tile layout as the tets with
+// nd = 5*nshl rows/columns per element matrix
+struct ElemGroup {
+  int lcsyst, nshl, nq, tab;  // tab: index into the generic shape tables (0 hex, 1 wedge)
+  int numel;
+  size_t numel_pad;
+  int *d_ien;     // [nshl][numel_pad] 0-based
+  int *d_refel;   // [numel] 0-based position of the element in the reference's (file) order
+  double *d_EG;   // [tile][c][r][32]
+  int *d_eloc;    // [nshl*nshl][numel_pad] CSR block of element block (a,b)
+};
+
 struct HaloTask {
   int peer, iacc, tag, count;  // count = number of nodes (all segments)
   int offset;                  // into d_halo_nodes
@@ -41,7 +54,10 @@ struct phb200_ctx {
   phb200_common c;
   int device;
   cudaStream_t stream;
-  // ---- mesh (tets only for now: lcsyst==1 blocks concatenated in file order)
+  // ---- mesh: lcsyst==1 blocks concatenated in file order (specialised tet kernels);
+  //      other topologies live in `gen` (generic kernels)
+  std::vector<ElemGroup> gen;
+  int *d_refel_tet;    // [numel_tet] position of each tet in the reference's element order
   int numel_tet;       // elements in tet blocks
   size_t numel_pad;    // padded to EG_TILE
   int *d_ien;          // [4][numel_pad] 0-based, padding repeats node 0 (masked)
@@ -126,6 +142,7 @@ struct KScope {
 int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, const double *shpb,
                       const double *shglb);
 int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse = 0);
+int phb_alloc_eg(phb200_ctx *ctx);
 // solver.cu
 int phb_i3lu(phb200_ctx *ctx, double *d_Diag, double *d_r, int code);
 int phb_i3pre(phb200_ctx *ctx);

@@ -97,19 +97,21 @@ int phb_i3lu(phb200_ctx *ctx, double *d_Diag, double *d_r, int code) {
 // i3pre (i3pre.f:43-133): EGmass <- L^-1 EGmass U^-1, block (a,b) at a time.
 // grid.y = pair (a,b); thread = element; loads/stores are 256 B coalesced.
 // ---------------------------------------------------------------------------
+template <int NSHL>
 __global__ void __launch_bounds__(128) k_i3pre_tet(int numel, size_t numel_pad, int nshg,
                                                     const int *__restrict__ ien, const double *__restrict__ BD,
                                                     double *EG) {
+  constexpr int ND = 5 * NSHL;
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= numel) return;
-  const int a = blockIdx.y >> 2, b = blockIdx.y & 3;
+  const int a = blockIdx.y / NSHL, b = blockIdx.y % NSHL;
   const int na = ien[(size_t)a * numel_pad + e], nb = ien[(size_t)b * numel_pad + e];
-  double *base = EG + ((size_t)e / EG_TILE) * (size_t)(400 * EG_TILE) + (e % EG_TILE);
+  double *base = EG + ((size_t)e / EG_TILE) * (size_t)(ND * ND * EG_TILE) + (e % EG_TILE);
   double B[5][5];
 #pragma unroll
   for (int n = 0; n < 5; n++)
 #pragma unroll
-    for (int m = 0; m < 5; m++) B[m][n] = base[(size_t)((5 * a + m) + 20 * (5 * b + n)) * EG_TILE];
+    for (int m = 0; m < 5; m++) B[m][n] = base[(size_t)((5 * a + m) + ND * (5 * b + n)) * EG_TILE];
   // rows: forward substitution with node a's L (i3pre.f:60-83)
 #define LA(r, c) __ldg(BD + (size_t)nshg * (((r)-1) + 5 * ((c)-1)) + na)
   {
@@ -143,13 +145,13 @@ __global__ void __launch_bounds__(128) k_i3pre_tet(int numel, size_t numel_pad, 
 #pragma unroll
   for (int n = 0; n < 5; n++)
 #pragma unroll
-    for (int m = 0; m < 5; m++) base[(size_t)((5 * a + m) + 20 * (5 * b + n)) * EG_TILE] = B[m][n];
+    for (int m = 0; m < 5; m++) base[(size_t)((5 * a + m) + ND * (5 * b + n)) * EG_TILE] = B[m][n];
 }
 
 int phb_i3pre(phb200_ctx *ctx) {
   const int nshg = ctx->c.nshg;
   const double *BD = ctx->d_BDiag;
-  if (!ctx->d_EG) {
+  if (!ctx->have_lhs) {
     fprintf(stderr, "phb200: i3pre: no EBE LHS has been assembled (lhs=1 call needed first)\n");
     return 1;
   }
@@ -163,7 +165,16 @@ int phb_i3pre(phb200_ctx *ctx) {
   if (ctx->numel_tet > 0) {
     KScope ks(ctx, KC_I3PRE);
     dim3 grid((ctx->numel_tet + 127) / 128, 16);
-    k_i3pre_tet<<<grid, 128, 0, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, nshg, ctx->d_ien, BD, ctx->d_EG);
+    k_i3pre_tet<4><<<grid, 128, 0, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, nshg, ctx->d_ien, BD, ctx->d_EG);
+    PHB_CHECK(cudaGetLastError());
+  }
+  for (const ElemGroup &g : ctx->gen) {
+    KScope ks(ctx, KC_I3PRE);
+    dim3 grid((g.numel + 127) / 128, g.nshl * g.nshl);
+    if (g.nshl == 8)
+      k_i3pre_tet<8><<<grid, 128, 0, ctx->stream>>>(g.numel, g.numel_pad, nshg, g.d_ien, BD, g.d_EG);
+    else
+      k_i3pre_tet<6><<<grid, 128, 0, ctx->stream>>>(g.numel, g.numel_pad, nshg, g.d_ien, BD, g.d_EG);
     PHB_CHECK(cudaGetLastError());
   }
   return 0;
@@ -179,6 +190,37 @@ __global__ void k_iper_copy(int n, const int *__restrict__ slaves, const int *__
   if (t >= n * 5) return;
   int j = slaves[t % n], k = t / n;
   u[(size_t)nshg * k + j] = u[(size_t)nshg * k + iper[j]];
+}
+
+template <int NSHL>
+__global__ void __launch_bounds__(128) k_ap_ebe_gen(int numel, size_t numel_pad, int nshg,
+                                                     const int *__restrict__ ien, const double *__restrict__ EG,
+                                                     const double *__restrict__ u, double *__restrict__ out) {
+  constexpr int ND = 5 * NSHL;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= numel) return;
+  int nd[NSHL];
+  double p[ND], q[ND];
+#pragma unroll
+  for (int a = 0; a < NSHL; a++) {
+    nd[a] = ien[(size_t)a * numel_pad + e];
+#pragma unroll
+    for (int m = 0; m < 5; m++) {
+      p[5 * a + m] = __ldg(u + (size_t)nshg * m + nd[a]);
+      q[5 * a + m] = 0.0;
+    }
+  }
+  const double *base = EG + ((size_t)e / EG_TILE) * (size_t)(ND * ND * EG_TILE) + (e % EG_TILE);
+#pragma unroll
+  for (int c = 0; c < ND; c++) {
+    const double pc = p[c];
+#pragma unroll
+    for (int r = 0; r < ND; r++) q[r] += __ldcs(base + (size_t)(r + ND * c) * EG_TILE) * pc;
+  }
+#pragma unroll
+  for (int a = 0; a < NSHL; a++)
+#pragma unroll
+    for (int m = 0; m < 5; m++) atomicAdd(out + (size_t)nshg * m + nd[a], q[5 * a + m]);
 }
 
 __global__ void __launch_bounds__(128) k_ap_ebe_tet(int numel, size_t numel_pad, int nshg,
@@ -249,6 +291,15 @@ int phb_au1gmr(phb200_ctx *ctx, double *d_u) {
     KScope ks(ctx, KC_AP);
     k_ap_ebe_tet<<<(ctx->numel_tet + 127) / 128, 128, 0, s>>>(ctx->numel_tet, ctx->numel_pad, nshg, ctx->d_ien,
                                                               ctx->d_EG, d_u, ctx->d_temp);
+    PHB_CHECK(cudaGetLastError());
+  }
+  for (const ElemGroup &g : ctx->gen) {
+    KScope ks(ctx, KC_AP);
+    const int nb = (g.numel + 127) / 128;
+    if (g.nshl == 8)
+      k_ap_ebe_gen<8><<<nb, 128, 0, s>>>(g.numel, g.numel_pad, nshg, g.d_ien, g.d_EG, d_u, ctx->d_temp);
+    else
+      k_ap_ebe_gen<6><<<nb, 128, 0, s>>>(g.numel, g.numel_pad, nshg, g.d_ien, g.d_EG, d_u, ctx->d_temp);
     PHB_CHECK(cudaGetLastError());
   }
   PHB_CHECK(cudaMemcpyAsync(d_u, ctx->d_temp, sizeof(double) * 5 * (size_t)nshg, cudaMemcpyDeviceToDevice, s));

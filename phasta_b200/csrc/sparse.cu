@@ -69,22 +69,22 @@ int phb_genadj_host(int nshg, int nelblk, const int *lcblk, const int *const *mi
 }
 
 // sparseloc (fillsparse.f:236-271) for every (element, a, b): CSR block index
-__global__ void k_eloc(int numel, size_t numel_pad, const int *__restrict__ ien, const int *__restrict__ colm,
-                       const int *__restrict__ rowp, int *__restrict__ eloc) {
+__global__ void k_eloc(int nshl, int numel, size_t numel_pad, const int *__restrict__ ien,
+                       const int *__restrict__ colm, const int *__restrict__ rowp, int *__restrict__ eloc) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= numel) return;
-  int nd[4];
-  for (int a = 0; a < 4; a++) nd[a] = ien[(size_t)a * numel_pad + e];
-  for (int a = 0; a < 4; a++) {
+  int nd[8];
+  for (int a = 0; a < nshl; a++) nd[a] = ien[(size_t)a * numel_pad + e];
+  for (int a = 0; a < nshl; a++) {
     const int c0 = colm[nd[a]], n = colm[nd[a] + 1] - c0;
-    for (int b = 0; b < 4; b++) {
+    for (int b = 0; b < nshl; b++) {
       const int target = nd[b];
       int lo = 0, hi = n;  // rowp[c0+lo] <= target < rowp[c0+hi]
       while (hi - lo > 1) {
         int mid = (hi + lo) >> 1;
         if (rowp[c0 + mid] > target) hi = mid; else lo = mid;
       }
-      eloc[(size_t)(4 * a + b) * numel_pad + e] = c0 + lo;
+      eloc[(size_t)(nshl * a + b) * numel_pad + e] = c0 + lo;
     }
   }
 }
@@ -119,8 +119,18 @@ int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_to
   PHB_CHECK(cudaMemcpy(ctx->d_rowofblk, rob.data(), sizeof(int) * rob.size(), cudaMemcpyHostToDevice));
   PHB_CHECK(cudaMemset(ctx->d_eloc, 0, sizeof(int) * 16 * ctx->numel_pad));
   if (ctx->numel_tet > 0) {
-    k_eloc<<<(ctx->numel_tet + 127) / 128, 128, 0, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, ctx->d_ien,
+    k_eloc<<<(ctx->numel_tet + 127) / 128, 128, 0, ctx->stream>>>(4, ctx->numel_tet, ctx->numel_pad, ctx->d_ien,
                                                                   ctx->d_colm, ctx->d_rowp, ctx->d_eloc);
+    ctx->launches++;
+    PHB_CHECK(cudaGetLastError());
+  }
+  for (ElemGroup &g : ctx->gen) {
+    if (g.d_eloc) cudaFree(g.d_eloc);
+    const size_t n = (size_t)g.nshl * g.nshl * g.numel_pad;
+    PHB_CHECK(cudaMalloc(&g.d_eloc, sizeof(int) * n));
+    PHB_CHECK(cudaMemset(g.d_eloc, 0, sizeof(int) * n));
+    k_eloc<<<(g.numel + 127) / 128, 128, 0, ctx->stream>>>(g.nshl, g.numel, g.numel_pad, g.d_ien, ctx->d_colm,
+                                                           ctx->d_rowp, g.d_eloc);
     ctx->launches++;
     PHB_CHECK(cudaGetLastError());
   }
