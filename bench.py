@@ -40,7 +40,22 @@ WORKLOADS = {
     "c2_channel_4M": (128, 64, 82),
     "c1_cube_50k": (20, 20, 21),
     "small": (32, 24, 24),
+    # BASELINE.json configs[2] shape at single-GPU size: flat-plate box, 4 wedge layers at each wall, tets above
+    "c3_plate_mixed_4M": (128, 64, 82, "mixed", 4),
+    "hex_1M": (128, 96, 82, "hex", 0),
 }
+
+
+def workload_elements(name):
+    w = WORKLOADS[name]
+    nxg, ny, nz = w[:3]
+    topo, wl = (w[3], w[4]) if len(w) > 3 else ("tet", 0)
+    nh = nxg * ny * nz
+    if topo == "hex":
+        return nh
+    if topo == "mixed":
+        return nxg * nz * (2 * wl * 2 + (ny - 2 * wl) * 6)
+    return nh * 6
 
 
 def peaks():
@@ -95,11 +110,13 @@ class ClockSampler(threading.Thread):
 
 def build_part(workload, rank, world):
     from phasta_b200 import make_box, make_state, global_node_count
-    nxg, ny, nz = WORKLOADS[workload]
+    w = WORKLOADS[workload]
+    nxg, ny, nz = w[:3]
+    topo, wl = (w[3], w[4]) if len(w) > 3 else ("tet", 1)
     nx = nxg * world
     L = (1.0 * world, 0.5, 0.64)
     parts = make_box(nx, ny, nz, L=L, nparts=world, bc="channel", periodic_z=True, ibksiz=1024,
-                     only_rank=rank)
+                     only_rank=rank, topo=topo, wedge_layers=max(wl, 1))
     part = parts[0]
     y, ac = make_state(part, global_node_count(nx, ny, nz))
     return part, y, ac
@@ -167,8 +184,7 @@ def reference_arm(args):
             vals.append(cb["value"])
     v = float(np.mean(vals))
     cb["value"] = v
-    nxg, ny, nz = WORKLOADS[args.workload]
-    numel = nxg * ny * nz * 6 * args.gpus
+    numel = workload_elements(args.workload) * args.gpus
     line = {"impl": "reference", "metric": "fp64_elements_assembled_per_s", "value": v, "unit": "elements/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * numel / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -420,7 +436,7 @@ def main():
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": args.workload, "elements": numel_total, "nodes_per_gpu": part.nshg,
-                           "elements_per_gpu": part.numel, "quadrature": "4-pt tets", "lhs": 1, "idiff": 1,
+                           "elements_per_gpu": part.numel, "quadrature": "rule 2 (4-pt tets, 6-pt wedges, 8-pt hexes)", "lhs": 1, "idiff": 1,
                            "l2": "inputs larger than L2 (EGmass %.1f GB per GPU)" % (part.numel * 3200 / 1e9),
                            "partition": "x-slabs, ilwork halo over NCCL" if world > 1 else "single part"},
                 "residual_only": {"value": numel_total / (res_ms * 1e-3), "unit": "elements/s", "ms": res_ms},

@@ -145,6 +145,27 @@ int phb200_sumgat(phb200_ctx *ctx, const double *u, int n, double *summed);
 int phb200_get_aerfrc(phb200_ctx *ctx, double *Force, double *HFlux,
                       double *flxID, int zero);
 
+/* ---- Newton / time-step shell on the device ----
+ * The predictor-multicorrector routines itrdrv calls around SolGMR*
+ * (itrdrv.f:393-394,590-594): itrPredict (itrPC.f:54-119, ipred 1..4),
+ * itrBC (itrbc.f:60-199; ylimit off, iabc=0), itrCorrect (itrPC.f:127-150),
+ * itrUpdate (itrPC.f:205-210) act on the device-resident y/ac (phb200_set_state)
+ * and yold/acold (phb200_set_old_state), so a step's vectors never cross PCIe.
+ * phb200_rstat: totres(1:2) of rstat.f:94-112 from the last solve's res / rmes.
+ * phb200_timestep: one whole step of itrdrv.f's flow sequence "0 1 0 1 ...":
+ * predictor, nitr x (SolGMRe | SolGMRs, rstat, itrCorrect, itrBC), itrUpdate;
+ * lhs = 1 - min(1, mod(ifuncs-1, LHSupd)) (itrdrv.f:456,511).  stats (nitr,6
+ * row-major, nullable): totres(1), totres(2), iKs, lGMRES, lhs, 0. */
+int phb200_set_old_state(phb200_ctx *ctx, const double *yold, const double *acold);
+int phb200_get_state(phb200_ctx *ctx, double *y, double *ac, double *yold, double *acold);
+int phb200_itrpredict(phb200_ctx *ctx, const phb200_step *step, int ipred);
+int phb200_itrbc(phb200_ctx *ctx, int ires);
+int phb200_itrcorrect(phb200_ctx *ctx, const phb200_step *step);
+int phb200_itrupdate(phb200_ctx *ctx, const phb200_step *step);
+int phb200_rstat(phb200_ctx *ctx, long long nshgt, double *totres);
+int phb200_timestep(phb200_ctx *ctx, const phb200_step *step, int ipred, int nitr, int sparse, int LHSupd,
+                    long long nshgt, int *ntotGM, double *stats);
+
 /* HBM-resident path (what bench.py's `value` times: inputs already on the
  * device).  set_state uploads y/ac once; the dev_* calls run on them. */
 int phb200_set_state(phb200_ctx *ctx, const double *y, const double *ac);

@@ -243,6 +243,35 @@ class Oracle:
                            C.byref(self.ntotGM))
         return iKs.value, lG.value
 
+    # ---- Newton / time-step shell (oracle_step.c) --------------------------
+    def _state(self):
+        if not hasattr(self, "yold"):
+            self.yold = [p.keep["y"].copy(order="F") for p in self.parts]
+            self.acold = [p.keep["ac"].copy(order="F") for p in self.parts]
+            self.ifuncs = C.c_int(0)
+        return [p.keep["y"] for p in self.parts], [p.keep["ac"] for p in self.parts]
+
+    def itrBC(self, ires=1):
+        y, ac = self._state()
+        self.L.orc_itrbc(self.n, self.arr, self._vecs(y), self._vecs(ac), ires)
+
+    def rstat(self, nshgt):
+        out = np.zeros(2)
+        self.L.orc_rstat(self.n, self.arr, int(nshgt), _ptr(out))
+        return out
+
+    def TimeStep(self, nitr=2, ipred=1, sparse=False, LHSupd=1, nshgt=None):
+        """One step of itrdrv.f's flow sequence; y/ac/yold/acold updated in place
+        (yold/acold start as copies of the initial y/ac).  Returns stats (nitr,6)."""
+        y, ac = self._state()
+        if nshgt is None:
+            nshgt = sum(p.mp.nshg for p in self.parts)
+        stats = np.zeros((nitr, 6))
+        self.L.orc_timestep(self.n, self.arr, self._vecs(y), self._vecs(ac), self._vecs(self.yold),
+                            self._vecs(self.acold), int(ipred), int(nitr), int(bool(sparse)), int(LHSupd),
+                            int(nshgt), C.byref(self.ifuncs), C.byref(self.ntotGM), _ptr(stats))
+        return stats
+
     def SolGMRe(self):
         iKs, lG = C.c_int(0), C.c_int(0)
         self.L.orc_solgmre(self.n, self.arr, _ptr(self.HBrg), _ptr(self.eBrg), _ptr(self.yBrg),

@@ -124,6 +124,19 @@ void orc_spsi3pre(int nparts, orc_part *parts);
 void orc_solgmrs(int nparts, orc_part *parts, double *HBrg, double *eBrg,
                  double *yBrg, double *Rcos, double *Rsin, int *iKs,
                  int *lGMRES, int *ntotGM);
+/* Newton / time-step shell (oracle_step.c): itrBC (itrbc.f:1-199), itrCorrect /
+ * itrUpdate (itrPC.f:127-150,205-210), rstat norms (rstat.f:94-112) and one
+ * whole step of itrdrv.f's flow sequence (predictor, nitr x (solve, correct,
+ * itrBC), update). */
+void orc_itrbc(int nparts, orc_part *parts, double **y, double **ac, int ires);
+void orc_itrcorrect(const orc_part *p, double *y, double *ac, const double *yold,
+                    const double *acold, const double *Dy);
+void orc_itrupdate(const orc_part *p, double *yold, double *acold, const double *y,
+                   const double *ac);
+void orc_rstat(int nparts, orc_part *parts, int nshgt, double *totres);
+void orc_timestep(int nparts, orc_part *parts, double **y, double **ac, double **yold,
+                  double **acold, int ipred, int nitr, int sparse, int LHSupd, int nshgt,
+                  int *ifuncs, int *ntotGM, double *stats);
 int orc_sizeof_part(void);
 int orc_sizeof_common(void);
 

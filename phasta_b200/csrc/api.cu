@@ -206,6 +206,8 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   ctx->d_BDtmp = nullptr;
   if (c->numpe > 1) PHB_TRY(dev_alloc(&ctx->d_BDtmp, (size_t)25 * nshg));
   ctx->d_EG = nullptr;  // allocated by the first EBE lhs=1 assembly
+  ctx->d_yold = ctx->d_acold = nullptr;
+  ctx->ifuncs = 0;
   ctx->nnz_tot = 0;
   ctx->d_colm = ctx->d_rowp = ctx->d_rowofblk = ctx->d_eloc = nullptr;
   ctx->d_lhsK = nullptr;
@@ -240,7 +242,7 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
                   ctx->d_rmass, ctx->d_res, ctx->d_rmes, ctx->d_Dy, ctx->d_temp, ctx->d_BDiag, ctx->d_BDtmp,
                   ctx->d_EG, ctx->d_uBrg, ctx->d_dots, ctx->d_scratch, ctx->d_ienb, ctx->d_iBCB,
                   ctx->d_BCB, ctx->d_aerfrc, ctx->d_colm, ctx->d_rowp, ctx->d_rowofblk, ctx->d_eloc, ctx->d_lhsK,
-                  ctx->d_nodeaos};
+                  ctx->d_nodeaos, ctx->d_yold, ctx->d_acold};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (ctx->d_refel_tet) cudaFree(ctx->d_refel_tet);
@@ -542,6 +544,66 @@ extern "C" int phb200_sumgat(phb200_ctx *ctx, const double *u, int n, double *su
   if (len * sizeof(double) > ctx->scratch_bytes) return fail("sumgat", "vector too long");
   PHB_TRY(h2d(ctx, ctx->d_scratch, u, len));
   return phb_sumgat_dev(ctx, ctx->d_scratch, len, summed);
+}
+
+// ---- Newton / time-step shell (timestep.cu) --------------------------------------------------------------
+extern "C" int phb200_set_old_state(phb200_ctx *ctx, const double *yold, const double *acold) {
+  ENTER(ctx);
+  if (!yold || !acold) return fail("set_old_state", "null argument");
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  if (!ctx->d_yold) {
+    PHB_TRY(dev_alloc(&ctx->d_yold, n5));
+    PHB_TRY(dev_alloc(&ctx->d_acold, n5));
+  }
+  PHB_TRY(h2d(ctx, ctx->d_yold, yold, n5));
+  PHB_TRY(h2d(ctx, ctx->d_acold, acold, n5));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_get_state(phb200_ctx *ctx, double *y, double *ac, double *yold, double *acold) {
+  ENTER(ctx);
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  if ((yold || acold) && !ctx->d_yold) return fail("get_state", "no old state on the device");
+  if (y) PHB_TRY(d2h(ctx, y, ctx->d_y, n5));
+  if (ac) PHB_TRY(d2h(ctx, ac, ctx->d_ac, n5));
+  if (yold) PHB_TRY(d2h(ctx, yold, ctx->d_yold, n5));
+  if (acold) PHB_TRY(d2h(ctx, acold, ctx->d_acold, n5));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+#define NEED_OLD(ctx, name) \
+  if (!(ctx)->d_yold) return fail(name, "no old state (call phb200_set_old_state first)");
+extern "C" int phb200_itrpredict(phb200_ctx *ctx, const phb200_step *st, int ipred) {
+  ENTER(ctx);
+  NEED_OLD(ctx, "itrpredict");
+  return phb_itrpredict(ctx, st, ipred);
+}
+extern "C" int phb200_itrbc(phb200_ctx *ctx, int ires) {
+  ENTER(ctx);
+  return phb_itrbc(ctx, ires);
+}
+extern "C" int phb200_itrcorrect(phb200_ctx *ctx, const phb200_step *st) {
+  ENTER(ctx);
+  NEED_OLD(ctx, "itrcorrect");
+  return phb_itrcorrect(ctx, st);
+}
+extern "C" int phb200_itrupdate(phb200_ctx *ctx, const phb200_step *st) {
+  ENTER(ctx);
+  NEED_OLD(ctx, "itrupdate");
+  return phb_itrupdate(ctx, st);
+}
+extern "C" int phb200_rstat(phb200_ctx *ctx, long long nshgt, double *totres) {
+  ENTER(ctx);
+  if (!totres || nshgt < 1) return fail("rstat", "bad argument");
+  return phb_rstat(ctx, nshgt, totres);
+}
+extern "C" int phb200_timestep(phb200_ctx *ctx, const phb200_step *st, int ipred, int nitr, int sparse, int LHSupd,
+                               long long nshgt, int *ntotGM, double *stats) {
+  ENTER(ctx);
+  NEED_OLD(ctx, "timestep");
+  if (!st || !ntotGM || nshgt < 1) return fail("timestep", "bad argument");
+  if (sparse && !ctx->d_lhsK) return fail("timestep", "no CSR structure (call phb200_set_sparse first)");
+  return phb_timestep(ctx, st, ipred, nitr, sparse, LHSupd, nshgt, ntotGM, stats);
 }
 
 // /aerfrc/ (common.h:106): Force(3), HFlux accumulate over calls with iter==nitr

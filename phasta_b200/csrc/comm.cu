@@ -69,7 +69,7 @@ struct LocalGroup {
   pthread_barrier_t bar;
   bool bar_init = false;
   phb200_ctx *members[64] = {};
-  double red[64] = {};
+  double red[64][8] = {};
 };
 static LocalGroup g_local;
 static std::mutex g_local_mu;
@@ -224,16 +224,17 @@ int phb_allreduce_sum(phb200_ctx *ctx, double *d_vals, int n) {
     return 0;
   }
   if (ctx->local_group) {
-    if (n != 1) return 1;
-    double v;
-    PHB_CHECK(cudaMemcpyAsync(&v, d_vals, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (n < 1 || n > 8) return 1;
+    double v[8];
+    PHB_CHECK(cudaMemcpyAsync(v, d_vals, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     PHB_CHECK(cudaStreamSynchronize(ctx->stream));
-    g_local.red[ctx->c.myrank] = v;
+    for (int k = 0; k < n; k++) g_local.red[ctx->c.myrank][k] = v[k];
     pthread_barrier_wait(&g_local.bar);
-    double s = 0.0;
-    for (int r = 0; r < g_local.n; r++) s += g_local.red[r];
+    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < g_local.n; r++)
+      for (int k = 0; k < n; k++) s[k] += g_local.red[r][k];
     pthread_barrier_wait(&g_local.bar);
-    PHB_CHECK(cudaMemcpyAsync(d_vals, &s, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    PHB_CHECK(cudaMemcpyAsync(d_vals, s, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     PHB_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;
   }

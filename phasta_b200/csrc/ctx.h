@@ -84,6 +84,8 @@ struct phb200_ctx {
   bool local_group;    // in-process multi-part transport (tests)
   // ---- state / results
   double *d_y, *d_ac;            // [5][nshg] {u,v,w,p,T}
+  double *d_yold, *d_acold;      // state at the beginning of the step (timestep.cu), allocated on first use
+  int ifuncs;                    // flow solves so far (itrdrv.f:432, drives LHSupd)
   double *d_qres, *d_rmass;      // [12][nshg], [nshg]
   double *d_nodeaos;             // [nshg][26] node records for the element gathers (assembly.cu)
   double *d_res, *d_rmes, *d_Dy, *d_temp;  // [5][nshg]
@@ -152,6 +154,14 @@ int phb_zero_slaves(phb200_ctx *ctx, double *d_r, int n, int identity);
 int phb_sumgat_dev(phb200_ctx *ctx, const double *d_u, size_t len, double *out);
 int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs, int *lGMRES, int *ntotGM);
 int phb_fp64_peak(phb200_ctx *ctx, double *tflops);
+// timestep.cu
+int phb_itrpredict(phb200_ctx *ctx, const phb200_step *st, int ipred);
+int phb_itrbc(phb200_ctx *ctx, int ires);
+int phb_itrcorrect(phb200_ctx *ctx, const phb200_step *st);
+int phb_itrupdate(phb200_ctx *ctx, const phb200_step *st);
+int phb_rstat(phb200_ctx *ctx, long long nshgt, double *totres);
+int phb_timestep(phb200_ctx *ctx, const phb200_step *st, int ipred, int nitr, int sparse, int LHSupd,
+                 long long nshgt, int *ntotGM, double *stats);
 // sparse.cu
 int phb_genadj_host(int nshg, int nelblk, const int *lcblk, const int *const *mien, int nnz, int *colm, int *rowp,
                     int *nnz_tot);

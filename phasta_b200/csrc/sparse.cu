@@ -199,10 +199,12 @@ int phb_spsi3pre(phb200_ctx *ctx) {
 }
 
 // ---------------------------------------------------------------------------
-// SparseAp (sparseap.f:45-101): one warp per row; the row's blocks are one
-// contiguous run of 25*nblk doubles, streamed with fully coalesced loads
-// (lane t reads flat entries t, t+32, ...); entry f+5g of block k multiplies
-// p(row(k), g) and lands in q(i, f).
+// SparseAp (sparseap.f:45-101): one warp per row.  Lane l < 25 owns entry
+// l = f + 5 g of every 5x5 block of the row (lhsK(25,k) is entry-fastest), so
+// a block is one coalesced 200-byte load, there is no index arithmetic in the
+// loop, and the column id is one broadcast load per block; four blocks are in
+// flight per warp.  q(i,f) = sum_g of lanes f+5g at the end (3 shuffles).
+// HBM-bound: 204 B per block.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sparseap(int nshg, const int *__restrict__ colm,
                                                    const int *__restrict__ rowp, const double *__restrict__ lhsK,
@@ -210,36 +212,30 @@ __global__ void __launch_bounds__(256) k_sparseap(int nshg, const int *__restric
   const int lane = threadIdx.x & 31;
   const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (row >= nshg) return;
+  const bool act = lane < 25;
+  const int l = act ? lane : 0;
+  const int g = l / 5;
+  const double *__restrict__ pg = p + (size_t)nshg * g;
   const int k0 = colm[row], k1 = colm[row + 1];
-  const size_t base = (size_t)25 * k0;
-  const int total = 25 * (k1 - k0);
-  double acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0, acc4 = 0;
-  for (int t = lane; t < total; t += 32) {
-    const int kb = t / 25, l = t - 25 * kb;
-    const int g = l / 5, f = l - 5 * g;
-    const int j = __ldg(rowp + k0 + kb);
-    const double v = __ldcs(lhsK + base + t) * __ldg(p + (size_t)nshg * g + j);
-    acc0 += (f == 0) ? v : 0.0;
-    acc1 += (f == 1) ? v : 0.0;
-    acc2 += (f == 2) ? v : 0.0;
-    acc3 += (f == 3) ? v : 0.0;
-    acc4 += (f == 4) ? v : 0.0;
+  const double *__restrict__ a = lhsK + (size_t)25 * k0 + l;
+  double acc0 = 0.0, acc1 = 0.0;
+  int k = k0;
+  for (; k + 4 <= k1; k += 4, a += 100) {
+    const int j0 = __ldg(rowp + k), j1 = __ldg(rowp + k + 1), j2 = __ldg(rowp + k + 2), j3 = __ldg(rowp + k + 3);
+    const double a0 = __ldcs(a), a1 = __ldcs(a + 25), a2 = __ldcs(a + 50), a3 = __ldcs(a + 75);
+    const double p0 = __ldg(pg + j0), p1 = __ldg(pg + j1), p2 = __ldg(pg + j2), p3 = __ldg(pg + j3);
+    acc0 += a0 * p0;
+    acc1 += a1 * p1;
+    acc0 += a2 * p2;
+    acc1 += a3 * p3;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    acc0 += __shfl_down_sync(0xffffffffu, acc0, o);
-    acc1 += __shfl_down_sync(0xffffffffu, acc1, o);
-    acc2 += __shfl_down_sync(0xffffffffu, acc2, o);
-    acc3 += __shfl_down_sync(0xffffffffu, acc3, o);
-    acc4 += __shfl_down_sync(0xffffffffu, acc4, o);
-  }
-  if (lane == 0) {
-    q[row] = acc0;
-    q[(size_t)nshg + row] = acc1;
-    q[(size_t)nshg * 2 + row] = acc2;
-    q[(size_t)nshg * 3 + row] = acc3;
-    q[(size_t)nshg * 4 + row] = acc4;
-  }
+  for (; k < k1; k++, a += 25) acc0 += __ldcs(a) * __ldg(pg + __ldg(rowp + k));
+  double acc = act ? acc0 + acc1 : 0.0;
+  const double t20 = __shfl_down_sync(0xffffffffu, acc, 20);
+  acc += __shfl_down_sync(0xffffffffu, acc, 10);
+  acc += __shfl_down_sync(0xffffffffu, acc, 5);
+  acc += t20;
+  if (lane < 5) q[(size_t)nshg * lane + row] = acc;
 }
 
 __global__ void k_iper_copy5(int n, const int *__restrict__ slaves, const int *__restrict__ iper, int nshg,

@@ -50,6 +50,8 @@ SYMBOLS = [
     "phb200_sizeof_step", "phb200_local_group_join", "phb200_genadj", "phb200_set_sparse",
     "phb200_elmgmrs", "phb200_spsi3pre", "phb200_sparseap", "phb200_solgmrs", "phb200_dev_elmgmrs",
     "phb200_dev_solve_sparse", "phb200_dev_sparseap",
+    "phb200_set_old_state", "phb200_get_state", "phb200_itrpredict", "phb200_itrbc", "phb200_itrcorrect",
+    "phb200_itrupdate", "phb200_rstat", "phb200_timestep",
 ]
 
 _LIB = None

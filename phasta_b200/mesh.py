@@ -291,6 +291,12 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
             iBC[inflow] |= (7 << 3) | (1 << 1)
             iBC[outflow & ~wall] |= (1 << 2)
             iBC[wall] |= (7 << 3) | (1 << 1)
+            # essential-BC values as itrBC applies them (itrbc.f:60-177): BC(:,1) pressure, BC(:,2)
+            # temperature, BC(:,3:5) the velocity of code 7; no-slip isothermal walls
+            BC[:, 0] = 1.0e5
+            BC[:, 1] = 300.0
+            BC[inflow, 2], BC[inflow, 3], BC[inflow, 4] = 30.0, 3.0, 1.5
+            BC[wall, 2:5] = 0.0
             if periodic_z:
                 slave = K == nz
                 iBC[slave] |= (1 << 10)
@@ -375,6 +381,31 @@ def make_state(part: MeshPart, nglobal_nodes: int, seed=1234):
     m = part.iper - 1
     y[:, :] = y[m, :]
     ac[:, :] = ac[m, :]
+    return y, ac
+
+
+def make_smooth_state(part: MeshPart, L=(1.0, 0.5, 0.5), amp=1.0e-3):
+    """Smooth subsonic channel state for time-stepping runs: Poiseuille-like
+    u1(y) that vanishes on the y walls, small smooth u2/u3/p/T perturbations,
+    ac = 0.  A function of the coordinates only, so parts agree on shared nodes;
+    periodic in z.  Also writes the matching essential-BC values into part.BC
+    (itrbc.f:60-177: BC(:,1) pressure, BC(:,2) temperature, BC(:,3:5) velocity
+    of code 7) so that itrBC leaves the initial state unchanged."""
+    x, yy, z = part.x[:, 0] / L[0], part.x[:, 1] / L[1], part.x[:, 2] / L[2]
+    two_pi = 2.0 * np.pi
+    prof = 4.0 * yy * (1.0 - yy)
+    y = np.empty((part.nshg, NDOF), order="F")
+    y[:, 0] = 30.0 * prof * (1.0 + 10 * amp * np.sin(two_pi * x) * np.cos(two_pi * z))
+    y[:, 1] = 30.0 * amp * prof * np.sin(two_pi * x) * np.sin(two_pi * z)
+    y[:, 2] = 30.0 * amp * prof * np.cos(two_pi * x) * np.sin(two_pi * z)
+    y[:, 3] = 1.0e5 * (1.0 + amp * np.cos(two_pi * x) * np.cos(two_pi * z) * (0.5 + yy))
+    y[:, 4] = 300.0 * (1.0 + amp * prof * np.sin(two_pi * x) * np.cos(two_pi * z))
+    m = part.iper - 1
+    y[:, :] = y[m, :]
+    ac = np.zeros_like(y)
+    part.BC[:, 0] = y[:, 3]
+    part.BC[:, 1] = y[:, 4]
+    part.BC[:, 2:5] = y[:, 0:3]
     return y, ac
 
 

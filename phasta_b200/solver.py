@@ -267,6 +267,53 @@ class PhastaGPU:
         self._ac = np.asfortranarray(ac, dtype=np.float64)
         _chk(self.L.phb200_set_state(self.ctx, _p(self._y), _p(self._ac)), "set_state")
 
+    # ------------------------------------- Newton / time-step shell (timestep.cu)
+    def set_old_state(self, yold, acold):
+        yo = np.asfortranarray(yold, dtype=np.float64)
+        ao = np.asfortranarray(acold, dtype=np.float64)
+        _chk(self.L.phb200_set_old_state(self.ctx, _p(yo), _p(ao)), "set_old_state")
+
+    def get_state(self, old=False):
+        """(y, ac) or, with old=True, (y, ac, yold, acold) copied back from the device."""
+        arrs = [self._vec() for _ in range(4 if old else 2)]
+        ptrs = [_p(a) for a in arrs] + [None] * (4 - len(arrs))
+        _chk(self.L.phb200_get_state(self.ctx, *ptrs), "get_state")
+        return tuple(arrs)
+
+    def itrPredict(self, ipred=1, step=None):
+        """itrPC.f:54-119 on the resident state."""
+        _chk(self.L.phb200_itrpredict(self.ctx, C.byref(step or self.step()), int(ipred)), "itrpredict")
+
+    def itrBC(self, ires=1):
+        """itrbc.f:1-199 on the resident y/ac (incl. commu 'out')."""
+        _chk(self.L.phb200_itrbc(self.ctx, int(ires)), "itrbc")
+
+    def itrCorrect(self, step=None):
+        """itrPC.f:127-150 with the Dy of the last solve."""
+        _chk(self.L.phb200_itrcorrect(self.ctx, C.byref(step or self.step())), "itrcorrect")
+
+    def itrUpdate(self, step=None):
+        """itrPC.f:205-210."""
+        _chk(self.L.phb200_itrupdate(self.ctx, C.byref(step or self.step())), "itrupdate")
+
+    def rstat(self, nshgt=None):
+        """rstat.f:94-112: totres(1:2) of the last solve."""
+        out = np.zeros(2)
+        _chk(self.L.phb200_rstat(self.ctx, C.c_longlong(int(nshgt or self.part.nshg)), _p(out)), "rstat")
+        return out
+
+    def TimeStep(self, nitr=2, ipred=1, sparse=False, LHSupd=1, nshgt=None, step=None):
+        """One step of itrdrv.f's flow sequence on the resident state (set_state +
+        set_old_state first).  Returns stats (nitr,6): totres(1), totres(2), iKs, lGMRES, lhs, 0."""
+        st = step or self.step()
+        stats = np.zeros((nitr, 6))
+        ntot = C.c_int(self.ntotGM)
+        _chk(self.L.phb200_timestep(self.ctx, C.byref(st), int(ipred), int(nitr), int(bool(sparse)), int(LHSupd),
+                                    C.c_longlong(int(nshgt or self.part.nshg)), C.byref(ntot), _p(stats)),
+             "timestep")
+        self.ntotGM = ntot.value
+        return stats
+
     def dev_elmgmre(self, step=None):
         st = step or self.step()
         _chk(self.L.phb200_dev_elmgmre(self.ctx, C.byref(st)), "dev_elmgmre")
