@@ -325,6 +325,7 @@ __global__ void k_qpbc_divide(int nshg, double *qres, double *rmass) {
 // node records for the element gathers: [node][NREC] = x(3), Y{p,u1,u2,u3,T}(5), Y,t(5), q(12), pad.
 // One 208-byte contiguous record per node (13 16-byte loads) instead of 25 strided 8-byte gathers.
 #define NREC 26
+#define STAGE_DBL (32 * 25)  // per-warp staging tile of the CSR scatter (finish_block, LHS==2)
 __global__ void k_pack_nodes(int nshg, int numnp, const double *__restrict__ x, const double *__restrict__ y,
                              const double *__restrict__ ac, const double *__restrict__ qres, int with_q,
                              double *__restrict__ aos) {
@@ -434,7 +435,7 @@ __device__ __forceinline__ void finish_block(double (&acc)[5][5], int a, int b, 
                                              int nshg, int na, int nb, int ibca, int ibcb,
                                              const double *__restrict__ BC, double *__restrict__ BDiag,
                                              double *__restrict__ EG, const int *__restrict__ eloc,
-                                             double *__restrict__ lhsK) {
+                                             double *__restrict__ lhsK, double *__restrict__ stage) {
   constexpr int ND = 5 * NSHL;
   if (ge < numel) {
     if (a == b && c_ph.iprec != 0) {
@@ -472,15 +473,22 @@ __device__ __forceinline__ void finish_block(double (&acc)[5][5], int a, int b, 
   }
   if (LHS == 2) {
     // fillsparseC (fillsparse.f:66-126): lhsK(f+5g, k) += EGmass(e, r+f, s+g); the block index k
-    // comes from the precomputed sparseloc map
-    if (ge < numel) {
-      const int k = eloc[(size_t)(NSHL * a + b) * numel_pad + ge];
-      double *blk = lhsK + (size_t)25 * k;
+    // comes from the precomputed sparseloc map.  The 32 blocks of the warp are transposed through a
+    // per-warp shared staging tile so that one warp-wide reduction covers the 25 contiguous doubles of ONE
+    // CSR block (7 L2 sectors) instead of 32 scattered blocks (32 sectors) per instruction.
+    const int lane = threadIdx.x & 31;
+    const int k = (ge < numel) ? eloc[(size_t)(NSHL * a + b) * numel_pad + ge] : -1;
 #pragma unroll
-      for (int n = 0; n < 5; n++)
+    for (int n = 0; n < 5; n++)
 #pragma unroll
-        for (int m = 0; m < 5; m++) atomicAdd(blk + m + 5 * n, acc[m][n]);
+      for (int m = 0; m < 5; m++) stage[lane * 25 + m + 5 * n] = acc[m][n];
+    __syncwarp();
+#pragma unroll 4
+    for (int e = 0; e < 32; e++) {
+      const int ke = __shfl_sync(0xffffffffu, k, e);
+      if (ke >= 0 && lane < 25) atomicAdd(lhsK + (size_t)25 * ke + lane, stage[e * 25 + lane]);
     }
+    __syncwarp();
   } else {
     // coalesced store of the block (also for padding lanes: zeros)
     const size_t gtile = (size_t)ge / EG_TILE;
@@ -525,7 +533,7 @@ __device__ __forceinline__ void phase_b(const AsmSmem<TILE_E, NQ> &sm, int warp,
                                         size_t numel_pad, int nshg, const int *__restrict__ iBC,
                                         const double *__restrict__ BC, double *__restrict__ BDiag,
                                         double *__restrict__ EG, const int *__restrict__ eloc,
-                                        double *__restrict__ lhsK) {
+                                        double *__restrict__ lhsK, double *__restrict__ stage) {
       constexpr int NHALF = TILE_E / 32;
       for (int task = warp; task < 16 * NHALF; task += NWARP) {
         const int pair = task / NHALF, half = task % NHALF;
@@ -661,7 +669,7 @@ __device__ __forceinline__ void phase_b(const AsmSmem<TILE_E, NQ> &sm, int warp,
           acc[4][4] += W * scon * gagb;
         }
         finish_block<LHS, 4>(acc, a, b, ge, numel, numel_pad, nshg, sm.nd[a][le], sm.nd[b][le], sm.ibc[a][le],
-                             sm.ibc[b][le], BC, BDiag, EG, eloc, lhsK);
+                             sm.ibc[b][le], BC, BDiag, EG, eloc, lhsK, stage);
       }
 }
 
@@ -804,6 +812,9 @@ __global__ void __launch_bounds__(192, 2) k_asigmr_tet_ws(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AsmSmem<TILE_E, NQ> *smb = reinterpret_cast<AsmSmem<TILE_E, NQ> *>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // LHS==2: per-consumer-warp staging tile for the CSR scatter (see finish_block)
+  double *stage = (LHS == 2) ? reinterpret_cast<double *>(smem_raw + 2 * sizeof(AsmSmem<TILE_E, NQ>)) + (warp & 3) * STAGE_DBL
+                             : nullptr;
   if (warp >= 4) {
     // ------------------------------ producers: warp 4 does points 0,1; warp 5 points 2,3 ----------
     const int qbeg = (warp - 4) * 2, qend = qbeg + 2;
@@ -903,7 +914,7 @@ __global__ void __launch_bounds__(192, 2) k_asigmr_tet_ws(
       bar_sync_named(1 + buf, NTHR);
       const bool live = (tile * TILE_E + lane) < numel;
       phase_bprime<TILE_E, NQ>(sm, lane, warp, live, nshg, res);
-      if (LHS) phase_b<TILE_E, NQ, LHS, 4>(sm, warp, lane, tile, numel, numel_pad, nshg, iBC, BC, BDiag, EG, eloc, lhsK);
+      if (LHS) phase_b<TILE_E, NQ, LHS, 4>(sm, warp, lane, tile, numel, numel_pad, nshg, iBC, BC, BDiag, EG, eloc, lhsK, stage);
       if (tile + 2 * (int)gridDim.x < ntiles) bar_arrive_named(3 + buf, NTHR);
     }
   }
@@ -919,6 +930,8 @@ __global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AsmSmem<TILE_E, NQ> &sm = *reinterpret_cast<AsmSmem<TILE_E, NQ> *>(smem_raw);
   const int tid = threadIdx.x;
+  double *stage = (LHS == 2) ? reinterpret_cast<double *>(smem_raw + sizeof(AsmSmem<TILE_E, NQ>)) + (tid >> 5) * STAGE_DBL
+                             : nullptr;
   const int el = tid % TILE_E;  // element within tile
   const int sub = tid / TILE_E; // 0..3: quadrature point (phase A) / node (phase B')
 
@@ -1141,7 +1154,7 @@ __global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
     }
     __syncthreads();
     phase_bprime<TILE_E, NQ>(sm, el, sub, live, nshg, res);
-    if (LHS) phase_b<TILE_E, NQ, LHS, TILE_E * 4 / 32>(sm, tid >> 5, tid & 31, tile, numel, numel_pad, nshg, iBC, BC, BDiag, EG, eloc, lhsK);
+    if (LHS) phase_b<TILE_E, NQ, LHS, TILE_E * 4 / 32>(sm, tid >> 5, tid & 31, tile, numel, numel_pad, nshg, iBC, BC, BDiag, EG, eloc, lhsK, stage);
     __syncthreads();
   }
 }
@@ -1559,6 +1572,7 @@ __global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
   GenSmem<NSHL, NQ> &sm = *reinterpret_cast<GenSmem<NSHL, NQ> *>(smem_raw);
   const GenTables &T = c_gen[tab];
   const int tid = threadIdx.x, el = tid & 31, sub = tid >> 5;
+  double *stage = (LHS == 2) ? reinterpret_cast<double *>(smem_raw + sizeof(GenSmem<NSHL, NQ>)) + sub * STAGE_DBL : nullptr;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int e = tile * 32 + el;
     const bool live = e < numel;
@@ -1778,7 +1792,7 @@ __global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
           }
         }
         finish_block<LHS, NSHL>(acc, a, b, ge, numel, numel_pad, nshg, sm.nd[a][lane], sm.nd[b][lane],
-                                sm.ibc[a][lane], sm.ibc[b][lane], BC, BDiag, EG, eloc, lhsK);
+                                sm.ibc[a][lane], sm.ibc[b][lane], BC, BDiag, EG, eloc, lhsK, stage);
       }
     }
     __syncthreads();
@@ -1787,7 +1801,7 @@ __global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
 
 template <int NSHL, int NQ, int LHS>
 static int launch_asigmr_gen(phb200_ctx *ctx, const ElemGroup &g) {
-  const size_t smem = sizeof(GenSmem<NSHL, NQ>);
+  const size_t smem = sizeof(GenSmem<NSHL, NQ>) + (LHS == 2 ? NQ * STAGE_DBL * sizeof(double) : 0);
   auto kern = k_asigmr_gen<NSHL, NQ, LHS>;
   static bool configured = false;
   if (!configured) {
@@ -1836,7 +1850,7 @@ int phb_alloc_eg(phb200_ctx *ctx) {
 template <int TILE_E, int NQ, int LHS>
 static int launch_asigmr(phb200_ctx *ctx) {
   const phb200_common &c = ctx->c;
-  size_t smem = sizeof(AsmSmem<TILE_E, NQ>);
+  size_t smem = sizeof(AsmSmem<TILE_E, NQ>) + (LHS == 2 ? (TILE_E * 4 / 32) * STAGE_DBL * sizeof(double) : 0);
   auto kern = k_asigmr_tet<TILE_E, NQ, LHS>;
   static bool configured = false;
   if (!configured) {
@@ -1863,7 +1877,7 @@ static int launch_asigmr(phb200_ctx *ctx) {
 template <int LHS>
 static int launch_asigmr_ws(phb200_ctx *ctx) {
   const phb200_common &c = ctx->c;
-  size_t smem = 2 * sizeof(AsmSmem<32, 4>);
+  size_t smem = 2 * sizeof(AsmSmem<32, 4>) + (LHS == 2 ? 4 * STAGE_DBL * sizeof(double) : 0);
   auto kern = k_asigmr_tet_ws<LHS>;
   static bool configured = false;
   if (!configured) {

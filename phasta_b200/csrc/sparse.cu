@@ -202,7 +202,7 @@ int phb_spsi3pre(phb200_ctx *ctx) {
 // SparseAp (sparseap.f:45-101): one warp per row.  Lane l < 25 owns entry
 // l = f + 5 g of every 5x5 block of the row (lhsK(25,k) is entry-fastest), so
 // a block is one coalesced 200-byte load, there is no index arithmetic in the
-// loop, and the column id is one broadcast load per block; four blocks are in
+// loop, and the column id is one broadcast load per block; eight blocks are in
 // flight per warp.  q(i,f) = sum_g of lanes f+5g at the end (3 shuffles).
 // HBM-bound: 204 B per block.
 // ---------------------------------------------------------------------------
@@ -219,17 +219,27 @@ __global__ void __launch_bounds__(256) k_sparseap(int nshg, const int *__restric
   const int k0 = colm[row], k1 = colm[row + 1];
   const double *__restrict__ a = lhsK + (size_t)25 * k0 + l;
   double acc0 = 0.0, acc1 = 0.0;
-  int k = k0;
-  for (; k + 4 <= k1; k += 4, a += 100) {
-    const int j0 = __ldg(rowp + k), j1 = __ldg(rowp + k + 1), j2 = __ldg(rowp + k + 2), j3 = __ldg(rowp + k + 3);
-    const double a0 = __ldcs(a), a1 = __ldcs(a + 25), a2 = __ldcs(a + 50), a3 = __ldcs(a + 75);
-    const double p0 = __ldg(pg + j0), p1 = __ldg(pg + j1), p2 = __ldg(pg + j2), p3 = __ldg(pg + j3);
-    acc0 += a0 * p0;
-    acc1 += a1 * p1;
-    acc0 += a2 * p2;
-    acc1 += a3 * p3;
+  // eight blocks (1.6 KB) in flight per warp; the tail is predicated instead of looped so a typical
+  // 15-block row takes two round trips to memory
+  for (int k = k0; k < k1; k += 8, a += 200) {
+    int j[8];
+    double av[8], pv[8];
+    // (ptxas keeps this at 32 registers by interleaving the FMAs with the loads; forcing all 24 loads ahead
+    // of the FMAs costs 52 registers and half the occupancy, and measured slower: 0.57 vs 0.47 ms)
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const bool ok = k + i < k1;
+      j[i] = ok ? __ldg(rowp + k + i) : row;
+      av[i] = ok ? __ldcs(a + 25 * i) : 0.0;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) pv[i] = __ldg(pg + j[i]);
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      acc0 += av[i] * pv[i];
+      acc1 += av[i + 1] * pv[i + 1];
+    }
   }
-  for (; k < k1; k++, a += 25) acc0 += __ldcs(a) * __ldg(pg + __ldg(rowp + k));
   double acc = act ? acc0 + acc1 : 0.0;
   const double t20 = __shfl_down_sync(0xffffffffu, acc, 20);
   acc += __shfl_down_sync(0xffffffffu, acc, 10);
