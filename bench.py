@@ -66,6 +66,22 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def ncu_traffic(kind):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the newest committed
+    `ncu --set full` summary under profiles/ (one launch on the c2 workload); None if there is none."""
+    import glob
+    import re
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_prof_%s.txt" % kind)))
+    if not files:
+        return None
+    tot, unit = 0.0, {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for ln in open(files[-1]):
+        m = re.match(r"\s*dram__bytes_(read|write)\.sum\s+(\w+)\s+([0-9.,]+)", ln)
+        if m:
+            tot += float(m.group(3).replace(",", "")) * unit.get(m.group(2), 1.0)
+    return {"bytes_per_launch": tot, "source": os.path.relpath(files[-1], ROOT)} if tot else None
+
+
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks + throttle reasons during the timed region."""
 
@@ -193,11 +209,34 @@ def reference_arm(args):
                        "note": "CPU arm: bounded sample per step, ms_per_step extrapolated to the full mesh"},
             "cpu_baseline": cb,
             "e2e": {"value": v, "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
+_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    """The driver wants ONE JSON line on stdout: send everything else that writes to fd 1 (NCCL's version
+    banner, library chatter) to stderr and keep the real stdout for emit()."""
+    global _STDOUT_FD
+    if _STDOUT_FD is None:
+        sys.stdout.flush()
+        _STDOUT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _STDOUT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_STDOUT_FD, data)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -414,9 +453,12 @@ def main():
         hbm, src = peaks()
         elem_per_launch = part.numel
         tf = elem_per_launch * FLOP_PER_ELEM_LHS / (kern_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "k_asigmr_tet<32,4,true>",
+        c2 = args.workload == "c2_channel_4M"
+        tr_asm, tr_ap = (ncu_traffic("asm"), ncu_traffic("ap")) if c2 else (None, None)
+        roof = {"bound": "tensor", "kernel": "k_asigmr_tet_ws<1> (FP64 pipe; 'tensor' = compute-bound)",
                 "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak if fp64_peak else None,
-                "traffic": None, "peak_source": "FP64 DFMA-chain microbenchmark run in this process "
+                "traffic": tr_asm and tr_asm["bytes_per_launch"], "traffic_source": tr_asm and tr_asm["source"],
+                "peak_source": "FP64 DFMA-chain microbenchmark run in this process "
                                                 "(MEASURED_PEAKS.json has no FP64 entry); nominal %.0f TF" % FP64_NOMINAL_TF,
                 "frac_of_nominal": tf / FP64_NOMINAL_TF,
                 "flop_per_element": FLOP_PER_ELEM_LHS, "kernel_ms": kern_ms, "asiq_kernel_ms": asiq_ms,
@@ -427,7 +469,9 @@ def main():
             rs["peak"], rs["frac"], rs["peak_source"] = hbm, rs["achieved"] / hbm, src
             gbs = elem_per_launch * BYTES_PER_ELEM_AP / (extra["ap"]["kernel_ms"] * 1e-3) / 1e9
             extra["roofline_ap"] = {"bound": "hbm", "kernel": "k_ap_ebe_tet", "achieved": gbs, "peak": hbm,
-                                    "unit": "GB/s", "frac": gbs / hbm, "traffic": None, "peak_source": src}
+                                    "unit": "GB/s", "frac": gbs / hbm,
+                                    "traffic": tr_ap and tr_ap["bytes_per_launch"],
+                                    "traffic_source": tr_ap and tr_ap["source"], "peak_source": src}
         cb = None
         if not args.no_cpu:
             cb = cpu_baseline(args.workload, os.cpu_count() or 1)
@@ -443,7 +487,7 @@ def main():
                 "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "kernel_class_ms": {k: v[0] / 2 for k, v in prof.items()}}
         line.update(extra)
-        print(json.dumps(line), flush=True)
+        emit(line)
     g.close()
     if world > 1:
         dist.destroy_process_group()
