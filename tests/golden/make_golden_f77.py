@@ -1,0 +1,303 @@
+"""Golden vectors from the reference's own Fortran statements.
+
+Runs the UNMODIFIED sources under /root/reference/phSolver through the f77np
+interpreter (tests/golden/f77np.py -- this container has no Fortran compiler)
+on small seeded meshes and writes tests/golden/f77_*.npz.  The block loops of
+ElmGMRe / ElmMFG (pointer_data modules, allocate of per-block tables) are
+driven from python exactly as elmgmr.f:131-186 does it; every arithmetic
+statement executed is the reference's.
+
+    python tests/golden/make_golden_f77.py            # writes the fixtures
+    python tests/golden/make_golden_f77.py --check     # also diffs vs the oracle
+
+Only runs where /root/reference exists (not on the GPU box); the tests read
+the committed .npz files.
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, HERE)
+
+from f77np import Program  # noqa: E402
+
+REF = "/root/reference/phSolver"
+COMP = ["e3.f", "e3ivar.f", "getthm.f", "getdiff.f", "e3mtrx.f", "e3conv.f", "e3visc.f", "e3ls.f", "e3tau.f",
+        "e3massr.f", "e3juel.f", "e3massl.f", "e3wmlt.f", "e3bdg.f", "e3q.f", "e3qvar.f", "e3b.f", "e3bvar.f",
+        "bc3lhs.f", "bc3res.f", "bc3bdg.f", "bc3per.f", "i3lu.f", "i3pre.f", "itrbc.f", "asigmr.f", "asiq.f",
+        "asbmfg.f", "asires.f", "asimfg.f", "localt.f", "shuffle.f", "asaugmr.f", "sparseap.f", "spsi3pre.f",
+        "itrPC.f", "rstat.f"]
+COMP += ["solgmr.f", "elmgmr.f", "au1gmr.f", "elmmfg.f", "solmfg.f", "au1mfg.f", "au2mfg.f", "itrres.f", "itrfdi.f"]
+COMMON = ["clear.f", "mpitools.f", "e3metric.f", "local.f", "localy.f", "hierarchic.f", "qpbc.f", "fillsparse.f", "genadj.f", "asadj.f"]
+
+
+def _noop(prog, *a):
+    return None
+
+
+def make_program():
+    stubs = {n: _noop for n in ("timer", "error", "mpi_barrier", "timeseries", "getsgn", "rotabc", "commu",
+                                "mpi_allreduce", "tnanq", "tnanqe", "flush", "mpi_abort")}
+    modules = dict(exts=False, freq=1, rls=None, ytarget=None, iturb=0)
+    prog = Program([os.path.join(REF, "common")], modules=modules, stubs=stubs)
+    for f in COMP:
+        prog.load(os.path.join(REF, "compressible", f))
+    for f in COMMON:
+        prog.load(os.path.join(REF, "common", f))
+    return prog
+
+
+def set_commons(prog, params, tables, mp, nedof):
+    """the COMMON scalars input.f / input_fform.cc / genint.f would have set"""
+    G, P = prog.G, params
+    numelb = int(sum(b.shape[0] for b in mp.mienb)) if mp.nelblb else 0
+    G.update(numnp=mp.numnp, numel=mp.numel, numelb=numelb, nshg=mp.nshg, ndof=5, nflow=5, nedof=nedof,
+             navier=int(P.Navier), nen=nedof // 5, nelblk=mp.nelblk, nelblb=mp.nelblb,
+             numpe=1, myrank=0, master=0, nlwork=mp.nlwork,
+             e3nsd=3, i3nsd=1, ndofbc=6, ndibcb=2, ndbcb=6, jactyp=0, jump=0, ires=1, iprec=int(P.iprec),
+             idiff=int(P.idiff), lhs=int(P.lhs), itau=int(P.itau), ipord=int(P.ipord), ipred=1,
+             dtsfct=float(P.dtsfct), taucfct=float(P.taucfct), ibksiz=int(P.ibksiz), iabc=0, isurf=0,
+             idflx=12 if P.idiff >= 1 else 0, entropypressure=int(P.EntropyPressure),
+             iremovestabtimeterm=int(P.iremoveStabTimeTerm), ilhscond=0, bo=0.0,
+             pr=float(P.pr), rgas=float(P.Rgas), gamma=float(P.gamma), gamma1=float(P.gamma1), ithm=6,
+             temper=float(P.temper), epsm=float(P.epsM), iabres=0,
+             ivart=2, idc=int(P.iDC), kspace=int(P.Kspace), ngmres=int(P.nGMRES), iconvflow=1,
+             dtgl=float(P.Dtgl), almi=float(P.almi), alfi=float(P.alfi), gami=float(P.gami), etol=float(P.etol),
+             iter=1, nitr=2, istep=0, lstep=0, time=0.0,
+             irans=0, iles=0, ilset=0, ierrcalc=0, nsclr=0, isclr=0, irscale=-1, iale=0,
+             nshape=nedof // 5, nshapeb=nedof // 5, minitters=0)
+    G["datmat"][...] = 0.0
+    G["matflg"][...] = 0
+    G["datmat"][0, 1, 0] = P.datmat121   # datmat(1,2,1) viscosity
+    G["datmat"][1, 1, 0] = P.datmat221
+    G["datmat"][2, 1, 0] = P.datmat321
+    G["datmat"][0, 2, 0] = P.datmat131   # datmat(1,3,1) bulk viscosity
+    G["matflg"][1, 0] = int(P.matflg2)
+    G["matflg"][2, 0] = int(P.matflg3)
+    G["qwt"][...] = np.asarray(tables["Qwt"])
+    G["qwtb"][...] = np.asarray(tables["Qwtb"])
+    G["nint"][...] = np.asarray(tables["nint"])
+    G["nintb"][...] = np.asarray(tables["nintb"])
+    G["ylimit"][...] = 0.0
+    G["lcblk"][:, :mp.lcblk.shape[1]] = mp.lcblk
+    if mp.nelblb:
+        G["lcblkb"][:, :mp.lcblkb.shape[1]] = mp.lcblkb
+
+
+def set_block(prog, mp, iblk):
+    """elmgmr.f:131-143"""
+    G, lc = prog.G, mp.lcblk
+    G["iel"] = int(lc[0, iblk]) if "iel" in G else 0
+    G.update(lelcat=int(lc[1, iblk]), lcsyst=int(lc[2, iblk]), iorder=int(lc[3, iblk]), nenl=int(lc[4, iblk]),
+             nshl=int(lc[9, iblk]), mattyp=int(lc[6, iblk]), ndofl=int(lc[7, iblk]), nsymdl=int(lc[8, iblk]),
+             npro=int(lc[0, iblk + 1] - lc[0, iblk]))
+    G["ngauss"] = int(G["nint"][G["lcsyst"] - 1])
+    return int(lc[0, iblk]), G["npro"], G["nshl"], G["lcsyst"]
+
+
+def block_tables(tables, lcsyst, nshl, which=""):
+    """tmpshp(1:nshl,:) = shp(lcsyst,1:nshl,:) (elmgmr.f:145-151)"""
+    shp = np.asfortranarray(np.asarray(tables["shp" + which])[lcsyst - 1, :nshl, :])
+    shgl = np.asfortranarray(np.asarray(tables["shgl" + which])[lcsyst - 1, :, :nshl, :])
+    return shp, shgl
+
+
+def F(a, dtype=np.float64):
+    return np.asfortranarray(np.array(a, dtype=dtype, order="F"))
+
+
+# ----------------------------------------------------------------------------
+def run_elmgmre(prog, case, lhs=1, with_boundary=True):
+    """ElmGMRe (elmgmr.f:1-274) on part 0 of a single-part case."""
+    params, tables, parts, states = case
+    mp = parts[0]
+    y, ac = (F(a) for a in states[0])
+    nshape = max(int(b.shape[1]) for b in mp.mien)
+    nedof = 5 * nshape
+    set_commons(prog, params, tables, mp, nedof)
+    G = prog.G
+    G["lhs"], G["iprec"], G["ires"] = lhs, lhs, 1
+    nshg, numel = mp.nshg, mp.numel
+    x = F(mp.x)
+    iBC = np.array(mp.iBC, dtype=np.int64)
+    BC = F(mp.BC)
+    iper = np.array(mp.iper, dtype=np.int64)
+    ilwork = np.array(mp.ilwork, dtype=np.int64) if mp.nlwork else np.zeros(1, dtype=np.int64)
+    qres = np.zeros((nshg, 12), order="F")
+    rmass = np.zeros(nshg)
+    out = {}
+    if G["idiff"] in (1, 3):
+        for iblk in range(mp.nelblk):
+            iel, npro, nshl, lcsyst = set_block(prog, mp, iblk)
+            shp, shgl = block_tables(tables, lcsyst, nshl)
+            ien = np.asfortranarray(mp.mien[iblk], dtype=np.int64)
+            xmudmi = np.zeros((npro, G["ngauss"]), order="F")
+            prog.call("asiq", y, x, shp, shgl, ien, xmudmi, qres, rmass)
+        out["qres_raw"], out["rmass_raw"] = qres.copy(order="F"), rmass.copy()
+        prog.call("qpbc", rmass, qres, iBC, iper, ilwork)
+        out["qres"], out["rmass"] = qres.copy(order="F"), rmass.copy()
+    res = np.zeros((nshg, 5), order="F")
+    rmes = np.zeros((nshg, 5), order="F")
+    BDiag = np.zeros((nshg, 5, 5), order="F")
+    rerr = np.zeros((nshg, 10), order="F")
+    EGmass = np.zeros((numel, nedof, nedof), order="F") if lhs == 1 else None
+    for iblk in range(mp.nelblk):
+        iel, npro, nshl, lcsyst = set_block(prog, mp, iblk)
+        shp, shgl = block_tables(tables, lcsyst, nshl)
+        ien = np.asfortranarray(mp.mien[iblk], dtype=np.int64)
+        xmudmi = np.zeros((npro, G["ngauss"]), order="F")
+        mater = np.ones(npro, dtype=np.int64)
+        # EGmass(iel:inum,:,:) is passed as a section (elmgmr.f:161); the
+        # callee declares it (npro,nedof,nedof): copy-in / copy-out
+        EGb = np.zeros((npro, nedof, nedof), order="F")
+        prog.call("asigmr", y, ac, x, xmudmi, shp, shgl, ien, mater, res, rmes, BDiag, qres, EGb, rerr)
+        if lhs == 1:
+            out.setdefault("EGmass_nobc", np.zeros((numel, nedof, nedof), order="F"))[iel - 1:iel - 1 + npro] = EGb
+            prog.call("bc3lhs", iBC, BC, ien, EGb)
+            EGmass[iel - 1:iel - 1 + npro] = EGb
+    out["res_interior"] = res.copy(order="F")
+    if with_boundary and mp.nelblb:
+        G["flxid"][...] = 0.0
+        lcb = mp.lcblkb
+        for iblk in range(mp.nelblb):
+            G.update(lelcat=int(lcb[1, iblk]), lcsyst=int(lcb[2, iblk]), iorder=int(lcb[3, iblk]),
+                     nenl=int(lcb[4, iblk]), nenbl=int(lcb[5, iblk]), mattyp=int(lcb[6, iblk]),
+                     ndofl=int(lcb[7, iblk]), nshl=int(lcb[8, iblk]), nshlb=int(lcb[9, iblk]),
+                     npro=int(lcb[0, iblk + 1] - lcb[0, iblk]))
+            lcsyst = G["lcsyst"]
+            if lcsyst == 3:
+                lcsyst = G["nenbl"]
+                G["lcsyst"] = lcsyst
+            G["ngaussb"] = int(G["nintb"][lcsyst - 1])
+            shpb, shglb = block_tables(tables, lcsyst, G["nshl"], "b")
+            ienb = np.asfortranarray(mp.mienb[iblk], dtype=np.int64)
+            iBCB = np.asfortranarray(mp.miBCB[iblk], dtype=np.int64)
+            BCB = F(mp.mBCB[iblk])
+            materb = np.ones(G["npro"], dtype=np.int64)
+            prog.call("asbmfg", y, x, shpb, shglb, ienb, materb, iBCB, BCB, res, rmes)
+        out["flxID"] = np.array(G["flxid"][:, :2], order="F")
+        out["Force"] = np.array(G["force"])
+        out["HFlux"] = float(G["hflux"])
+    out["res_nobc"] = res.copy(order="F")
+    out["BDiag_nobc"] = BDiag.copy(order="F")
+    prog.call("bc3res", y, iBC, BC, res, iper, ilwork)
+    if lhs == 1:
+        prog.call("bc3bdg", y, iBC, BC, BDiag, iper, ilwork)
+    out["res"], out["BDiag"] = res, BDiag
+    if lhs == 1:
+        out["EGmass"] = EGmass
+    return out
+
+
+class _P:
+    """one entry of a pointer_data array: mien(iblk)%p"""
+
+    def __init__(self, p):
+        self.p = p
+
+
+def set_pointer_data(prog, mp, tables):
+    """module pointer_data (common/pointer.f:42-47) filled as genblk/gensav do"""
+    G, M = prog.G, prog.M
+    M["mien"] = [_P(np.asfortranarray(b, dtype=np.int64)) for b in mp.mien]
+    M["mmat"] = [_P(np.ones(b.shape[0], dtype=np.int64)) for b in mp.mien]
+    M["mxmudmi"] = [_P(np.zeros((b.shape[0], 8), order="F")) for b in mp.mien]
+    M["mienb"] = [_P(np.asfortranarray(b, dtype=np.int64)) for b in mp.mienb]
+    M["mmatb"] = [_P(np.ones(b.shape[0], dtype=np.int64)) for b in mp.mienb]
+    M["mibcb"] = [_P(np.asfortranarray(b, dtype=np.int64)) for b in mp.miBCB]
+    M["mbcb"] = [_P(F(b)) for b in mp.mBCB]
+
+
+def full_tables(tables):
+    return tuple(F(tables[k]) for k in ("shp", "shgl", "shpb", "shglb"))
+
+
+def run_solgmre(prog, case, etol=None):
+    """SolGMRe (solgmr.f:1-362) through the reference's own driver chain
+    SolGMRe -> ElmGMRe -> AsIq/AsIGMR/AsBMFG/bc3*, i3LU, i3pre, Au1GMR, sumgat."""
+    params, tables, parts, states = case
+    mp = parts[0]
+    y, ac = (F(a) for a in states[0])
+    nshape = max(int(b.shape[1]) for b in mp.mien)
+    nedof = 5 * nshape
+    set_commons(prog, params, tables, mp, nedof)
+    set_pointer_data(prog, mp, tables)
+    G = prog.G
+    if etol is not None:
+        G["etol"] = float(etol)
+    G["lhs"], G["iprec"] = 1, 1
+    nshg, numel, K = mp.nshg, mp.numel, int(params.Kspace)
+    x, BC = F(mp.x), F(mp.BC)
+    iBC = np.array(mp.iBC, dtype=np.int64)
+    iper = np.array(mp.iper, dtype=np.int64)
+    ilwork = np.array(mp.ilwork, dtype=np.int64) if mp.nlwork else np.zeros(1, dtype=np.int64)
+    shp, shgl, shpb, shglb = full_tables(tables)
+    res = np.zeros((nshg, 5), order="F")
+    BDiag = np.zeros((nshg, 5, 5), order="F")
+    EGmass = np.zeros((numel, nedof, nedof), order="F")
+    HBrg = np.zeros((K + 1, K), order="F")
+    eBrg, yBrg, Rcos, Rsin = (np.zeros(K + 1) for _ in range(4))
+    Dy = np.zeros((nshg, 5), order="F")
+    rerr = np.zeros((nshg, 10), order="F")
+    G["ntotgm"] = 0
+    prog.call("solgmre", y, ac, y.copy(order="F"), ac.copy(order="F"), x, iBC, BC, EGmass, res, BDiag, HBrg,
+              eBrg, yBrg, Rcos, Rsin, iper, ilwork, shp, shgl, shpb, shglb, Dy, rerr)
+    return dict(res=res, BDiag=BDiag, EGmass=EGmass, HBrg=HBrg, eBrg=eBrg, yBrg=yBrg, Dy=Dy,
+                iKs=int(G["iks"]), lGMRES=int(G["lgmres"]), ntotGM=int(G["ntotgm"]),
+                Force=np.array(G["force"]), HFlux=float(G["hflux"]), flxID=np.array(G["flxid"][:, :2], order="F"))
+
+
+def check(name, a, b, tol):
+    a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
+    nb = np.linalg.norm(b.ravel())
+    err = np.linalg.norm((a - b).ravel()) / (nb if nb > 0 else 1.0)
+    flag = "ok " if err <= tol else "BAD"
+    print("   %s %-14s rel-L2 %.3e  (|ref| %.3e)" % (flag, name, err, nb))
+    return err <= tol
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--check", action="store_true")
+    args = ap.parse_args()
+    from common import make_case, make_oracle
+    prog = make_program()
+    t0 = time.time()
+    case = make_case(3, 2, 2, bc="channel", ibksiz=16, boundary=True, natural="mixed")
+    out = run_elmgmre(prog, case, lhs=1)
+    print("ElmGMRe tets via f77np: %.1f s" % (time.time() - t0))
+    if args.check:
+        o = make_oracle(case)
+        o.ElmGMRe()
+        p = o.parts[0]
+        ok = check("qres", p.qres, out["qres"], 1e-12)
+        ok &= check("res", p.res, out["res"], 1e-12)
+        ok &= check("BDiag", p.BDiag, out["BDiag"], 1e-12)
+        ok &= check("EGmass", p.EGmass, out["EGmass"], 1e-12)
+        print("ALL OK" if ok else "MISMATCH")
+    t0 = time.time()
+    case = make_case(3, 2, 2, bc="channel", ibksiz=16, boundary=True, natural="mixed", etol=1e-6)
+    out = run_solgmre(prog, case)
+    print("SolGMRe via f77np: %.1f s, iKs %d" % (time.time() - t0, out["iKs"]))
+    if args.check:
+        o = make_oracle(case)
+        iKs, lG = o.SolGMRe()
+        p = o.parts[0]
+        print("   oracle iKs", iKs)
+        ok = check("res(precond)", p.res, out["res"], 1e-12)
+        ok &= check("BDiag(LU)", p.BDiag, out["BDiag"], 1e-12)
+        ok &= check("EGmass(pre)", p.EGmass, out["EGmass"], 1e-11)
+        ok &= check("HBrg", o.HBrg, out["HBrg"], 1e-9)
+        ok &= check("Dy", p.Dy, out["Dy"], 1e-9)
+        print("ALL OK" if ok else "MISMATCH")
+
+
+if __name__ == "__main__":
+    main()
