@@ -107,12 +107,14 @@ static void e3metric(const orc_common *c, qpstate *s, double xl[][4]) {
 
 /* e3ivar (compressible/e3ivar.f:1-489).  ycl/acl(nshl,5) element-local in
  * {p,u1,u2,u3,T} order, ql(nshl,idflx). */
-static void e3ivar(const orc_common *c, qpstate *s, double ycl[][6],
+static void e3ivar(const orc_common *c, qpstate *s, double yl[][6], double ycl[][6],
                    double acl[][6], double xl[][4], double ql[][13]) {
   int nshl = s->nshl;
+  /* dui and the gradients come from yl, the point state from ycl; the two
+   * alias in AsIGMR / AsIMFG and differ in AsIRes (perturbed vs base state) */
   for (int m = 1; m <= 5; m++) s->dui[m] = 0.0;
   for (int n = 1; n <= nshl; n++)
-    for (int m = 1; m <= 5; m++) s->dui[m] += s->shape[n] * ycl[n][m];
+    for (int m = 1; m <= 5; m++) s->dui[m] += s->shape[n] * yl[n][m];
   /* conservative variables (:164-185) */
   s->rk = 0.5 * (s->dui[2] * s->dui[2] + s->dui[3] * s->dui[3] +
                  s->dui[4] * s->dui[4]);
@@ -145,9 +147,9 @@ static void e3ivar(const orc_common *c, qpstate *s, double ycl[][6],
   for (int m = 1; m <= 5; m++) s->g1yi[m] = s->g2yi[m] = s->g3yi[m] = 0.0;
   for (int n = 1; n <= nshl; n++)
     for (int m = 1; m <= 5; m++) {
-      s->g1yi[m] += s->shg[n][1] * ycl[n][m];
-      s->g2yi[m] += s->shg[n][2] * ycl[n][m];
-      s->g3yi[m] += s->shg[n][3] * ycl[n][m];
+      s->g1yi[m] += s->shg[n][1] * yl[n][m];
+      s->g2yi[m] += s->shg[n][2] * yl[n][m];
+      s->g3yi[m] += s->shg[n][3] * yl[n][m];
     }
   /* div q (:358-395) */
   for (int m = 1; m <= 5; m++) s->divqi[m] = 0.0;
@@ -315,57 +317,61 @@ static void e3conv(const orc_common *c, qpstate *s, double *EG,
 }
 
 /* e3visc (compressible/e3visc.f:57-357), itau<10, rlsli=0 */
+/* K_ij of e3visc.f:69-139 into a 15x15 array of 5x5 blocks (sparse pattern) */
+static void visc_stiff(const qpstate *s, double (*st)[16]) {
+  double rmu = s->rmu, rlm = s->rlm, rlm2mu = s->rlm2mu, con = s->con;
+  double u1 = s->u1, u2 = s->u2, u3 = s->u3;
+  st[2][2] = rlm2mu;
+  st[3][3] = rmu;
+  st[4][4] = rmu;
+  st[5][2] = rlm2mu * u1;
+  st[5][3] = rmu * u2;
+  st[5][4] = rmu * u3;
+  st[5][5] = con;
+  st[2][8] = rlm;
+  st[3][7] = rmu;
+  st[5][7] = rmu * u2;
+  st[5][8] = rlm * u1;
+  st[2][14] = rlm;
+  st[4][12] = rmu;
+  st[5][12] = rmu * u3;
+  st[5][14] = rlm * u1;
+  st[7][3] = rmu;
+  st[8][2] = rlm;
+  st[10][2] = rlm * u2;
+  st[10][3] = rmu * u1;
+  st[7][7] = rmu;
+  st[8][8] = rlm2mu;
+  st[9][9] = rmu;
+  st[10][7] = rmu * u1;
+  st[10][8] = rlm2mu * u2;
+  st[10][9] = rmu * u3;
+  st[10][10] = con;
+  st[8][14] = rlm;
+  st[9][13] = rmu;
+  st[10][13] = rmu * u3;
+  st[10][14] = rlm * u2;
+  st[12][4] = rmu;
+  st[14][2] = rlm;
+  st[15][2] = rlm * u3;
+  st[15][4] = rmu * u1;
+  st[13][9] = rmu;
+  st[14][8] = rlm;
+  st[15][8] = rlm * u3;
+  st[15][9] = rmu * u2;
+  st[12][12] = rmu;
+  st[13][13] = rmu;
+  st[14][14] = rlm2mu;
+  st[15][12] = rmu * u1;
+  st[15][13] = rmu * u2;
+  st[15][14] = rlm2mu * u3;
+  st[15][15] = con;
+}
+
 static void e3visc(const orc_common *c, qpstate *s) {
   double rmu = s->rmu, rlm = s->rlm, rlm2mu = s->rlm2mu, con = s->con;
   double u1 = s->u1, u2 = s->u2, u3 = s->u3;
-  double(*st)[16] = s->stiff;
-  if (c->lhs == 1) {
-    st[2][2] = rlm2mu;
-    st[3][3] = rmu;
-    st[4][4] = rmu;
-    st[5][2] = rlm2mu * u1;
-    st[5][3] = rmu * u2;
-    st[5][4] = rmu * u3;
-    st[5][5] = con;
-    st[2][8] = rlm;
-    st[3][7] = rmu;
-    st[5][7] = rmu * u2;
-    st[5][8] = rlm * u1;
-    st[2][14] = rlm;
-    st[4][12] = rmu;
-    st[5][12] = rmu * u3;
-    st[5][14] = rlm * u1;
-    st[7][3] = rmu;
-    st[8][2] = rlm;
-    st[10][2] = rlm * u2;
-    st[10][3] = rmu * u1;
-    st[7][7] = rmu;
-    st[8][8] = rlm2mu;
-    st[9][9] = rmu;
-    st[10][7] = rmu * u1;
-    st[10][8] = rlm2mu * u2;
-    st[10][9] = rmu * u3;
-    st[10][10] = con;
-    st[8][14] = rlm;
-    st[9][13] = rmu;
-    st[10][13] = rmu * u3;
-    st[10][14] = rlm * u2;
-    st[12][4] = rmu;
-    st[14][2] = rlm;
-    st[15][2] = rlm * u3;
-    st[15][4] = rmu * u1;
-    st[13][9] = rmu;
-    st[14][8] = rlm;
-    st[15][8] = rlm * u3;
-    st[15][9] = rmu * u2;
-    st[12][12] = rmu;
-    st[13][13] = rmu;
-    st[14][14] = rlm2mu;
-    st[15][12] = rmu * u1;
-    st[15][13] = rmu * u2;
-    st[15][14] = rlm2mu * u3;
-    st[15][15] = con;
-  }
+  if (c->lhs == 1) visc_stiff(s, s->stiff);
   double *g1 = s->g1yi, *g2 = s->g2yi, *g3 = s->g3yi, *rmi = s->rmi,
          *ri = s->ri;
   /* x1 (:278-292) */
@@ -599,9 +605,14 @@ static void e3massl(const orc_common *c, qpstate *s, double *EG,
 }
 
 /* e3wmlt (compressible/e3wmlt.f:60-223) */
-static void e3wmlt(const orc_common *c, qpstate *s, double rl[][6], double *EG,
+static void e3wmlt(const orc_common *c, qpstate *s, double rl[][6], double rml[][6], double *EG,
                    size_t eg_stride, int nedof) {
   double W = s->WdetJ;
+  if ((c->ires == 2 || c->ires == 3) && rml) /* :95-122 */
+    for (int i = 1; i <= s->nshl; i++)
+      for (int m = 1; m <= 5; m++)
+        rml[i][m] += W * (s->shg[i][1] * s->rmi[m] + s->shg[i][2] * s->rmi[5 + m] +
+                          s->shg[i][3] * s->rmi[10 + m] + s->shape[i] * s->rmi[15 + m]);
   if (c->ires == 1 || c->ires == 3)
     for (int i = 1; i <= s->nshl; i++)
       for (int m = 1; m <= 5; m++)
@@ -651,12 +662,68 @@ static void getshp(const orc_part *p, qpstate *s) {
   }
 }
 
+/* e3bdg (compressible/e3bdg.f:1-2594), itau<10, bcool=0, ivart>=2, ngauss>1:
+ * the block-diagonal preconditioner of the matrix-free solver built directly,
+ *   BDiagl(a) += N_a W N_a,i A_i                       (:34-189, "Ex-E3conv")
+ *              + N_a N_a W fct1 A0                      (:218-246, "Ex-e3mass")
+ *              + N_a W fct1 N_a,i A_i tau A0            (:251-343)
+ *              + W N_a,i N_a,j (K_ij + A_i tau A_j)     (:344-2590)
+ * i.e. the four terms of EGmass(a,a).  The reference writes every entry out
+ * with the structural zeros of A_i removed; the sums below are the same terms
+ * in loop form (differences are at round-off level). */
+static void e3bdg(const orc_common *c, const qpstate *s, double BDl[][6][6]) {
+  const double(*A[4])[6] = {NULL, s->A1, s->A2, s->A3};
+  double fct1 = c->almi / c->gami / c->alfi * c->Dtgl;
+  double W = s->WdetJ;
+  double K[16][16];
+  memset(K, 0, sizeof K);
+  if (c->Navier == 1) visc_stiff(s, K);
+  double Atau[4][6][6], AtauA0[4][6][6];
+  for (int ii = 1; ii <= 3; ii++) {
+    for (int i = 1; i <= 5; i++) {
+      Atau[ii][i][1] = A[ii][i][1] * s->tau[1];
+      Atau[ii][i][2] = A[ii][i][2] * s->tau[2];
+      Atau[ii][i][3] = A[ii][i][3] * s->tau[2];
+      Atau[ii][i][4] = A[ii][i][4] * s->tau[2];
+      Atau[ii][i][5] = A[ii][i][5] * s->tau[3];
+    }
+    for (int j = 1; j <= 5; j++)
+      for (int i = 1; i <= 5; i++) {
+        double acc = 0.0;
+        for (int k = 1; k <= 5; k++) acc += Atau[ii][i][k] * s->A0[k][j];
+        AtauA0[ii][i][j] = acc;
+      }
+    for (int jj = 1; jj <= 3; jj++)
+      for (int j = 1; j <= 5; j++)
+        for (int i = 1; i <= 5; i++) {
+          double acc = 0.0;
+          for (int k = 1; k <= 5; k++) acc += Atau[ii][i][k] * A[jj][k][j];
+          K[i + 5 * (ii - 1)][j + 5 * (jj - 1)] += acc;
+        }
+  }
+  for (int a = 1; a <= s->nshl; a++) {
+    double Na = s->shape[a];
+    for (int i = 1; i <= 5; i++)
+      for (int k = 1; k <= 5; k++) {
+        double v = 0.0;
+        v += Na * W * (s->shg[a][1] * s->A1[i][k] + s->shg[a][2] * s->A2[i][k] + s->shg[a][3] * s->A3[i][k]);
+        v += (Na * Na) * (W * fct1) * s->A0[i][k];
+        v += (Na * W * fct1) * (s->shg[a][1] * AtauA0[1][i][k] + s->shg[a][2] * AtauA0[2][i][k] +
+                                s->shg[a][3] * AtauA0[3][i][k]);
+        for (int ii = 1; ii <= 3; ii++)
+          for (int jj = 1; jj <= 3; jj++)
+            v += W * s->shg[a][ii] * s->shg[a][jj] * K[i + 5 * (ii - 1)][k + 5 * (jj - 1)];
+        BDl[a][i][k] += v;
+      }
+  }
+}
+
 /* e3 (compressible/e3.f:1-306) for element iel of a block; EG points at
- * EGmass(iel_global,1,1), stride numel */
+ * EGmass(iel_global,1,1), stride numel.  yl: see e3ivar; rml / BDl nullable. */
 static void e3_element(const orc_part *p, int lcsyst, int nshl, int nenl,
-                       int ngauss, double ycl[][6], double acl[][6],
-                       double xl[][4], double ql[][13], double rl[][6],
-                       double *EG, size_t eg_stride, int nedof) {
+                       int ngauss, double yl[][6], double ycl[][6], double acl[][6],
+                       double xl[][4], double ql[][13], double rl[][6], double rml[][6],
+                       double BDl[][6][6], double *EG, size_t eg_stride, int nedof) {
   const orc_common *c = &p->c;
   qpstate s;
   s.nshl = nshl;
@@ -670,17 +737,18 @@ static void e3_element(const orc_part *p, int lcsyst, int nshl, int nenl,
     memset(s.ri, 0, sizeof s.ri);
     memset(s.rmi, 0, sizeof s.rmi);
     if (c->lhs == 1) memset(s.stiff, 0, sizeof s.stiff);
-    e3ivar(c, &s, ycl, acl, xl, ql);
+    e3ivar(c, &s, yl, ycl, acl, xl, ql);
     e3mtrx(&s);
     e3conv(c, &s, EG, eg_stride, nedof);
     if (c->Navier == 1) e3visc(c, &s);
     e3ls(c, &s, EG, eg_stride, nedof);
     if (ngauss == 1 && nshl == 4)
-      e3juel(c, &s, ycl, acl, rl);
+      e3juel(c, &s, yl, acl, rl);
     else
       e3massr(c, &s);
     if (c->lhs == 1) e3massl(c, &s, EG, eg_stride, nedof);
-    e3wmlt(c, &s, rl, EG, eg_stride, nedof);
+    if (c->iprec == 1 && c->lhs != 1 && BDl) e3bdg(c, &s, BDl); /* e3.f:258-285 */
+    e3wmlt(c, &s, rl, rml, EG, eg_stride, nedof);
   }
 }
 
@@ -728,7 +796,7 @@ void orc_asigmr(const orc_part *p, int iblk, const double *qres, double *res,
       if (nedof * nedof > 1600) { fprintf(stderr, "orc_asigmr: nedof>40\n"); abort(); }
       memset(EGl, 0, sizeof(double) * (size_t)nedof * nedof);
     }
-    e3_element(p, lcsyst, nshl, nenl, ngauss, ycl, acl, xl, ql, rl[e],
+    e3_element(p, lcsyst, nshl, nenl, ngauss, ycl, ycl, acl, xl, ql, rl[e], NULL, NULL,
                EGmass ? EGl : NULL, 1, nedof);
     if (EGmass) {
       double *EG = EGmass + (size_t)(iel - 1 + e);
@@ -759,6 +827,93 @@ void orc_asigmr(const orc_part *p, int iblk, const double *qres, double *res,
 }
 
 /* AsIq + e3q + e3qvar (compressible/asiq.f:1-71, e3q.f:1-246, e3qvar.f) */
+/* gather of one element's nodal data (localy / localx / local, asigmr.f:53-62) */
+static void gather_elem(const orc_part *p, const int *ien, int npro, int e, int nshl, const double *y,
+                        const double *ac, const double *qres, double ycl[][6], double acl[][6],
+                        double xl[][4], double ql[][13]) {
+  const orc_common *c = &p->c;
+  int nshg = c->nshg, idflx = (c->idiff >= 1 && qres) ? 12 : 0;
+  for (int n = 1; n <= nshl; n++) {
+    int A = ien[e + (size_t)npro * (n - 1)] - 1;
+    static const int src[6] = {0, 3, 0, 1, 2, 4}; /* localy.f:47-72 */
+    for (int m = 1; m <= 5; m++) {
+      if (ycl) ycl[n][m] = y[A + (size_t)nshg * src[m]];
+      if (acl) acl[n][m] = ac[A + (size_t)nshg * src[m]];
+    }
+    if (xl)
+      for (int i = 1; i <= 3; i++) xl[n][i] = p->x[A + (size_t)c->numnp * (i - 1)];
+    if (ql) {
+      memset(ql[n], 0, sizeof(double) * 13);
+      for (int k = 1; k <= idflx; k++) ql[n][k] = qres[A + (size_t)nshg * (k - 1)];
+    }
+  }
+}
+
+/* AsIMFG (compressible/asimfg.f:1-110) for one block: ires=3 residual rl,
+ * modified residual rml and (iprec=1, lhs/=1) the e3bdg block diagonal. */
+void orc_asimfg(const orc_part *p, int iblk, const double *qres, double *res, double *rmes,
+                double *BDiag) {
+  const orc_common *c = &p->c;
+  const int *lc = p->lcblk + 10 * iblk;
+  int iel = lc[0], lcsyst = lc[2], nenl = lc[4], nshl = lc[9];
+  int npro = lc[10] - iel;
+  int ngauss = c->nint[lcsyst - 1];
+  const int *ien = p->ien + p->ien_off[iblk];
+  int nshg = c->nshg;
+  if (ngauss == 1 && nshl == 4) {
+    fprintf(stderr, "orc_asimfg: the matrix-free path is restated for ngauss>1 only\n");
+    abort();
+  }
+  for (int e = 0; e < npro; e++) {
+    double ycl[ORC_MAXSH + 1][6], acl[ORC_MAXSH + 1][6], xl[ORC_MAXSH + 1][4], ql[ORC_MAXSH + 1][13];
+    double rl[ORC_MAXSH + 1][6], rml[ORC_MAXSH + 1][6], BDl[ORC_MAXSH + 1][6][6];
+    memset(rl, 0, sizeof rl);
+    memset(rml, 0, sizeof rml);
+    memset(BDl, 0, sizeof BDl);
+    gather_elem(p, ien, npro, e, nshl, p->y, p->ac, qres, ycl, acl, xl, ql);
+    e3_element(p, lcsyst, nshl, nenl, ngauss, ycl, ycl, acl, xl, ql, rl, rml, BDl, NULL, 1, c->nedof);
+    for (int i = 1; i <= nshl; i++) {
+      int A = ien[e + (size_t)npro * (i - 1)] - 1;
+      for (int j = 1; j <= 5; j++) {
+        res[A + (size_t)nshg * (j - 1)] += rl[i][j];
+        rmes[A + (size_t)nshg * (j - 1)] += rml[i][j];
+        if (c->iprec != 0)
+          for (int k = 1; k <= 5; k++) BDiag[A + (size_t)nshg * ((j - 1) + 5 * (k - 1))] += BDl[i][j][k];
+      }
+    }
+  }
+}
+
+/* AsIRes (compressible/asires.f:1-94) for one block: ires=2 modified residual
+ * with yl = yp (perturbed, (nshg,5) {u,p,T} global order) and ycl = p->y. */
+void orc_asires(const orc_part *p, int iblk, const double *yp, double *rmes, int iabres) {
+  const orc_common *c = &p->c;
+  const int *lc = p->lcblk + 10 * iblk;
+  int iel = lc[0], lcsyst = lc[2], nenl = lc[4], nshl = lc[9];
+  int npro = lc[10] - iel;
+  int ngauss = c->nint[lcsyst - 1];
+  const int *ien = p->ien + p->ien_off[iblk];
+  int nshg = c->nshg;
+  for (int e = 0; e < npro; e++) {
+    double yl[ORC_MAXSH + 1][6], ycl[ORC_MAXSH + 1][6], acl[ORC_MAXSH + 1][6], xl[ORC_MAXSH + 1][4],
+        ql[ORC_MAXSH + 1][13];
+    double rml[ORC_MAXSH + 1][6];
+    memset(rml, 0, sizeof rml);
+    memset(ql, 0, sizeof ql);
+    gather_elem(p, ien, npro, e, nshl, p->y, p->ac, NULL, ycl, acl, xl, NULL);
+    gather_elem(p, ien, npro, e, nshl, yp, p->ac, NULL, yl, NULL, NULL, NULL);
+    e3_element(p, lcsyst, nshl, nenl, ngauss, yl, ycl, acl, xl, ql, rml, rml, NULL, NULL, 1, c->nedof);
+    for (int i = 1; i <= nshl; i++) {
+      int A = ien[e + (size_t)npro * (i - 1)] - 1;
+      for (int j = 1; j <= 5; j++) {
+        double v = rml[i][j];
+        if (iabres == 1) v = fabs(v);
+        rmes[A + (size_t)nshg * (j - 1)] += v;
+      }
+    }
+  }
+}
+
 void orc_asiq(const orc_part *p, int iblk, double *qres, double *rmass) {
   const orc_common *c = &p->c;
   const int *lc = p->lcblk + 10 * iblk;

@@ -336,6 +336,11 @@ class ExprParser:
             src = val
             if self.accept("("):
                 args = self.arglist()
+                if val in FUNCTION_UNITS:
+                    # actual arguments of a function subprogram: an array element is
+                    # sequence-associated (flat view from that element)
+                    args = [re.sub(r"^_ref\(", "_elemview(", a) if re.match(r"^_ref\(_E,'\w+',\([^:]*\)\)$", a)
+                            and "_sl(" not in a else a for a in args]
                 src = "_ref(_E,%r,(%s))" % (val, "".join(a + "," for a in args))
             while self.accept("%"):
                 k, f = self.next()
@@ -545,6 +550,7 @@ INTRINSICS = {
     "dot_product": lambda a, b: _sum(a * b),
     "merge": lambda a, b, m: np.where(m, a, b),
     "trim": lambda s: s.rstrip(), "len": len,
+    "minloc": lambda a: np.array([int(np.argmin(a)) + 1]), "maxloc": lambda a: np.array([int(np.argmax(a)) + 1]),
 }
 
 
@@ -557,6 +563,8 @@ def _ref(E, name, args):
         return obj[_conv_index(args, E.lbounds(name))]
     if isinstance(obj, (list, tuple)):
         return obj[int(args[0]) - 1]
+    if obj is None and name in E.prog.units:     # function subprogram: result = variable named like it
+        return E.prog.call(name, *args)[name]
     if obj is None or callable(obj):
         f = obj if callable(obj) else INTRINSICS.get(name)
         if f is None:
@@ -568,7 +576,30 @@ def _ref(E, name, args):
     raise TypeError("f77np: %r is a scalar (%r) but is referenced with arguments" % (name, obj))
 
 
-HELPERS = dict(_ref=_ref, _idx=_idx, _sl=_sl, _div=_div, _pow=_pow, _eq=_eq, _ne=_ne, _and=_and,
+def _elemview(E, name, args):
+    try:
+        obj = E[name]
+    except KeyError:
+        obj = None
+    if isinstance(obj, np.ndarray) and all(not isinstance(a, (_Sl, np.ndarray)) for a in args):
+        idx = _conv_index(args, E.lbounds(name))
+        off = int(np.ravel_multi_index(idx, obj.shape, order="F"))
+        return obj.reshape(-1, order="F")[off:]
+    return _ref(E, name, args)
+
+
+FUNCTION_UNITS = set()
+
+
+def scan_functions(path):
+    """register the function subprograms of a file before anything is parsed"""
+    for label, text, no in read_statements(path):
+        m = re.match(r"^(?:[\w*() ]+\s+)?function\s+(\w+)\s*\(", text, re.I)
+        if m and not re.match(r"^\s*end", text, re.I):
+            FUNCTION_UNITS.add(m.group(1).lower())
+
+
+HELPERS = dict(_elemview=_elemview, _ref=_ref, _idx=_idx, _sl=_sl, _div=_div, _pow=_pow, _eq=_eq, _ne=_ne, _and=_and,
                _or=_or, _not=_not, _eqv=_eqv, _neqv=_neqv, np=np, math=math)
 
 
@@ -1090,6 +1121,12 @@ class Program:
         for k, dummy in enumerate(unit.args):
             if k < len(actuals):
                 L[dummy] = actuals[k]
+        for dummy in unit.args:       # scalar dummy fed from a sequence-associated element view
+            d = unit.decls.get(dummy)
+            if (d is None or d.dims is None) and isinstance(L.get(dummy), np.ndarray) and L[dummy].ndim == 1 \
+                    and unit.name in FUNCTION_UNITS:
+                v = L[dummy][0]
+                L[dummy] = int(v) if L[dummy].dtype.kind in "iu" else float(v)
         env = _Env(self, L, unit)
         copyback = []
         for pname, code in unit.params:

@@ -26,7 +26,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, HERE)
 
-from f77np import Program  # noqa: E402
+from f77np import Program, scan_functions  # noqa: E402
 
 REF = "/root/reference/phSolver"
 COMP = ["e3.f", "e3ivar.f", "getthm.f", "getdiff.f", "e3mtrx.f", "e3conv.f", "e3visc.f", "e3ls.f", "e3tau.f",
@@ -44,9 +44,13 @@ def _noop(prog, *a):
 
 def make_program():
     stubs = {n: _noop for n in ("timer", "error", "mpi_barrier", "timeseries", "getsgn", "rotabc", "commu",
-                                "mpi_allreduce", "tnanq", "tnanqe", "flush", "mpi_abort")}
+                                "mpi_allreduce", "tnanq", "tnanqe", "flush", "mpi_abort", "rstatcheck", "restar")}
     modules = dict(exts=False, freq=1, rls=None, ytarget=None, iturb=0)
     prog = Program([os.path.join(REF, "common")], modules=modules, stubs=stubs)
+    for f in COMP:
+        scan_functions(os.path.join(REF, "compressible", f))
+    for f in COMMON:
+        scan_functions(os.path.join(REF, "common", f))
     for f in COMP:
         prog.load(os.path.join(REF, "compressible", f))
     for f in COMMON:
@@ -70,7 +74,7 @@ def set_commons(prog, params, tables, mp, nedof):
              temper=float(P.temper), epsm=float(P.epsM), iabres=0,
              ivart=2, idc=int(P.iDC), kspace=int(P.Kspace), ngmres=int(P.nGMRES), iconvflow=1,
              dtgl=float(P.Dtgl), almi=float(P.almi), alfi=float(P.alfi), gami=float(P.gami), etol=float(P.etol),
-             iter=1, nitr=2, istep=0, lstep=0, time=0.0,
+             iter=1, nitr=1, istep=0, lstep=0, time=0.0,
              irans=0, iles=0, ilset=0, ierrcalc=0, nsclr=0, isclr=0, irscale=-1, iale=0,
              nshape=nedof // 5, nshapeb=nedof // 5, minitters=0)
     G["datmat"][...] = 0.0
@@ -86,6 +90,9 @@ def set_commons(prog, params, tables, mp, nedof):
     G["nint"][...] = np.asarray(tables["nint"])
     G["nintb"][...] = np.asarray(tables["nintb"])
     G["ylimit"][...] = 0.0
+    G["force"][...] = 0.0          # itrdrv.f:437-442
+    G["hflux"] = 0.0
+    G["flxid"][...] = 0.0
     G["lcblk"][:, :mp.lcblk.shape[1]] = mp.lcblk
     if mp.nelblb:
         G["lcblkb"][:, :mp.lcblkb.shape[1]] = mp.lcblkb
@@ -254,49 +261,119 @@ def run_solgmre(prog, case, etol=None):
                 Force=np.array(G["force"]), HFlux=float(G["hflux"]), flxID=np.array(G["flxid"][:, :2], order="F"))
 
 
+def run_solgmrs(prog, case, nnz=35):
+    """genadj (genadj.f, asadj.f) + SolGMRs (solgmr.f:368-744): ElmGMRs with
+    fillsparseC, Spsi3pre, SparseAp."""
+    params, tables, parts, states = case
+    mp = parts[0]
+    y, ac = (F(a) for a in states[0])
+    nshape = max(int(b.shape[1]) for b in mp.mien)
+    nedof = 5 * nshape
+    set_commons(prog, params, tables, mp, nedof)
+    set_pointer_data(prog, mp, tables)
+    G = prog.G
+    G["lhs"], G["iprec"], G["nnz"] = 1, 1, nnz
+    nshg, K = mp.nshg, int(params.Kspace)
+    colm = np.zeros(nshg + 1, dtype=np.int64)
+    rowp = np.zeros(nshg * nnz, dtype=np.int64)
+    L = prog.call("genadj", colm, rowp, 0)
+    nnz_tot = int(L["icnt"])
+    G["nnz_tot"] = nnz_tot
+    x, BC = F(mp.x), F(mp.BC)
+    iBC = np.array(mp.iBC, dtype=np.int64)
+    iper = np.array(mp.iper, dtype=np.int64)
+    ilwork = np.array(mp.ilwork, dtype=np.int64) if mp.nlwork else np.zeros(1, dtype=np.int64)
+    shp, shgl, shpb, shglb = full_tables(tables)
+    lhsK = np.zeros((25, nnz_tot), order="F")
+    res = np.zeros((nshg, 5), order="F")
+    BDiag = np.zeros((nshg, 5, 5), order="F")
+    HBrg = np.zeros((K + 1, K), order="F")
+    eBrg, yBrg, Rcos, Rsin = (np.zeros(K + 1) for _ in range(4))
+    Dy = np.zeros((nshg, 5), order="F")
+    rerr = np.zeros((nshg, 10), order="F")
+    G["ntotgm"] = 0
+    prog.call("solgmrs", y, ac, y.copy(order="F"), ac.copy(order="F"), x, iBC, BC, colm, rowp, lhsK, res, BDiag,
+              HBrg, eBrg, yBrg, Rcos, Rsin, iper, ilwork, shp, shgl, shpb, shglb, Dy, rerr)
+    return dict(colm=colm, rowp=rowp[:nnz_tot].copy(), nnz_tot=nnz_tot, lhsK=lhsK, res=res, BDiag=BDiag,
+                HBrg=HBrg, Dy=Dy, iKs=int(G["iks"]), lGMRES=int(G["lgmres"]))
+
+
 def check(name, a, b, tol):
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     nb = np.linalg.norm(b.ravel())
     err = np.linalg.norm((a - b).ravel()) / (nb if nb > 0 else 1.0)
     flag = "ok " if err <= tol else "BAD"
-    print("   %s %-14s rel-L2 %.3e  (|ref| %.3e)" % (flag, name, err, nb))
+    print("   %s %-16s rel-L2 %.3e  (|ref| %.3e)" % (flag, name, err, nb))
     return err <= tol
+
+
+from golden_cases import CASES, build_case, input_digest  # noqa: E402
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--check", action="store_true", help="diff against the oracle as well")
+    ap.add_argument("--only", default=None)
+    ap.add_argument("--no-write", action="store_true")
     args = ap.parse_args()
-    from common import make_case, make_oracle
+    from common import make_oracle
     prog = make_program()
-    t0 = time.time()
-    case = make_case(3, 2, 2, bc="channel", ibksiz=16, boundary=True, natural="mixed")
-    out = run_elmgmre(prog, case, lhs=1)
-    print("ElmGMRe tets via f77np: %.1f s" % (time.time() - t0))
+    allok = True
+    for name in CASES:
+        if args.only and name not in args.only.split(","):
+            continue
+        case, runs = build_case(name)
+        out = {"digest": input_digest(case)}
+        for run in runs:
+            t0 = time.time()
+            if run in ("elmgmre", "elmgmre0"):
+                r = run_elmgmre(prog, case, lhs=1 if run == "elmgmre" else 0)
+            elif run == "solgmre":
+                r = run_solgmre(prog, case)
+            else:
+                r = run_solgmrs(prog, case)
+            print("%s/%s via f77np: %.1f s" % (name, run, time.time() - t0))
+            for k, v in r.items():
+                out["%s.%s" % (run, k)] = v
+            if args.check:
+                o = make_oracle(case)
+                p = o.parts[0]
+                if run == "elmgmre0":
+                    o.set_flags(lhs=0, iprec=0)
+                if run.startswith("elmgmre"):
+                    o.ElmGMRe()
+                    if "qres" in r:
+                        allok &= check("qres", p.qres, r["qres"], 1e-12)
+                    allok &= check("res", p.res, r["res"], 1e-12)
+                    if run == "elmgmre":
+                        allok &= check("BDiag", p.BDiag, r["BDiag"], 1e-12)
+                        allok &= check("EGmass", p.EGmass, r["EGmass"], 1e-12)
+                    if "Force" in r:
+                        allok &= check("Force,HFlux", p.aerfrc[:4], np.r_[r["Force"], r["HFlux"]], 1e-12)
+                        allok &= check("flxID", p.aerfrc[4:24].reshape((10, 2), order="F"), r["flxID"], 1e-12)
+                elif run == "solgmre":
+                    iKs, lG = o.SolGMRe()
+                    print("   iKs oracle %d reference %d" % (iKs, r["iKs"]))
+                    allok &= iKs == r["iKs"]
+                    allok &= check("res(precond)", p.res, r["res"], 1e-12)
+                    allok &= check("BDiag(LU)", p.BDiag, r["BDiag"], 1e-12)
+                    allok &= check("EGmass(pre)", p.EGmass, r["EGmass"], 1e-11)
+                    allok &= check("HBrg", o.HBrg, r["HBrg"], 1e-9)
+                    allok &= check("Dy", p.Dy, r["Dy"], 1e-9)
+                else:
+                    ntot = o.genadj()[0]
+                    allok &= ntot == r["nnz_tot"] and np.array_equal(p.colm, r["colm"]) and \
+                        np.array_equal(p.rowp, r["rowp"])
+                    print("   genadj nnz_tot %d/%d colm/rowp equal: %s" % (ntot, r["nnz_tot"], np.array_equal(p.rowp, r["rowp"])))
+                    iKs, lG = o.SolGMRs()
+                    allok &= iKs == r["iKs"]
+                    allok &= check("lhsK(pre)", p.lhsK, r["lhsK"], 1e-11)
+                    allok &= check("HBrg", o.HBrg, r["HBrg"], 1e-9)
+                    allok &= check("Dy", p.Dy, r["Dy"], 1e-9)
+        if not args.no_write:
+            np.savez_compressed(os.path.join(HERE, "f77_%s.npz" % name), **out)
     if args.check:
-        o = make_oracle(case)
-        o.ElmGMRe()
-        p = o.parts[0]
-        ok = check("qres", p.qres, out["qres"], 1e-12)
-        ok &= check("res", p.res, out["res"], 1e-12)
-        ok &= check("BDiag", p.BDiag, out["BDiag"], 1e-12)
-        ok &= check("EGmass", p.EGmass, out["EGmass"], 1e-12)
-        print("ALL OK" if ok else "MISMATCH")
-    t0 = time.time()
-    case = make_case(3, 2, 2, bc="channel", ibksiz=16, boundary=True, natural="mixed", etol=1e-6)
-    out = run_solgmre(prog, case)
-    print("SolGMRe via f77np: %.1f s, iKs %d" % (time.time() - t0, out["iKs"]))
-    if args.check:
-        o = make_oracle(case)
-        iKs, lG = o.SolGMRe()
-        p = o.parts[0]
-        print("   oracle iKs", iKs)
-        ok = check("res(precond)", p.res, out["res"], 1e-12)
-        ok &= check("BDiag(LU)", p.BDiag, out["BDiag"], 1e-12)
-        ok &= check("EGmass(pre)", p.EGmass, out["EGmass"], 1e-11)
-        ok &= check("HBrg", o.HBrg, out["HBrg"], 1e-9)
-        ok &= check("Dy", p.Dy, out["Dy"], 1e-9)
-        print("ALL OK" if ok else "MISMATCH")
+        print("ALL OK" if allok else "MISMATCH")
 
 
 if __name__ == "__main__":

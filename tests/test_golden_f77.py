@@ -1,0 +1,167 @@
+"""Pinning against the reference itself.
+
+tests/golden/f77_*.npz hold the outputs of the reference's own Fortran sources
+(solgmr.f, elmgmr.f, asigmr.f, e3*.f, bc3*.f, i3lu.f, i3pre.f, au1gmr.f,
+sparseap.f, fillsparse.f, genadj.f, ... unmodified, from /root/reference)
+executed in the build container by the f77np interpreter
+(tests/golden/f77np.py, driver tests/golden/make_golden_f77.py) on the seeded
+cases of tests/golden_cases.py.
+
+* CPU tests: the oracle (oracle/*.c) reproduces every stored array
+  (connectivity-derived integer data exactly, floating point to round-off);
+  where /root/reference is present one case is re-run through the interpreter
+  to show the fixtures are reproducible.
+* GPU tests: libphb200.so, through the C-ABI, against the same stored arrays
+  at BASELINE.json's tolerances (1e-10 assembled, 1e-8 solution).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from common import make_oracle, rel_l2
+from golden_cases import CASES, build_case, input_digest
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL_ASM = 1e-10
+TOL_SOL = 1e-8
+
+
+def load(name):
+    z = np.load(os.path.join(GOLD, "f77_%s.npz" % name))
+    case, runs = build_case(name)
+    assert np.allclose(z["digest"], input_digest(case), rtol=1e-14, atol=0), \
+        "the seeded generator no longer reproduces the fixture's inputs; rerun tests/golden/make_golden_f77.py"
+    return z, case, runs
+
+
+def names(run):
+    return [n for n, (_, _, runs) in CASES.items() if run in runs]
+
+
+# ------------------------------------------------------------------ CPU: oracle
+@pytest.mark.parametrize("name", names("elmgmre") + names("elmgmre0"))
+def test_oracle_elmgmre_matches_reference_fortran(name):
+    z, case, runs = load(name)
+    run = "elmgmre" if "elmgmre" in runs else "elmgmre0"
+    o = make_oracle(case)
+    if run == "elmgmre0":
+        o.set_flags(lhs=0, iprec=0)
+    o.ElmGMRe()
+    p = o.parts[0]
+    if run + ".qres" in z:
+        assert rel_l2(p.qres, z[run + ".qres"]) < 1e-13
+    assert rel_l2(p.res, z[run + ".res"]) < 1e-13
+    if run == "elmgmre":
+        assert rel_l2(p.BDiag, z[run + ".BDiag"]) < 1e-13
+        assert p.EGmass.shape == z[run + ".EGmass"].shape
+        assert rel_l2(p.EGmass, z[run + ".EGmass"]) < 1e-13
+    if run + ".Force" in z:
+        ref = np.r_[z[run + ".Force"], z[run + ".HFlux"]]
+        assert rel_l2(p.aerfrc[:4], ref) < 1e-12
+        assert rel_l2(p.aerfrc[4:24].reshape((10, 2), order="F"), z[run + ".flxID"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", names("solgmre"))
+def test_oracle_solgmre_matches_reference_fortran(name):
+    z, case, _ = load(name)
+    o = make_oracle(case)
+    iKs, lG = o.SolGMRe()
+    p = o.parts[0]
+    assert (iKs, lG) == (int(z["solgmre.iKs"]), int(z["solgmre.lGMRES"]))
+    assert rel_l2(p.res, z["solgmre.res"]) < 1e-13          # L^-1 res
+    assert rel_l2(p.BDiag, z["solgmre.BDiag"]) < 1e-13      # LU factors (i3lu.f)
+    assert rel_l2(p.EGmass, z["solgmre.EGmass"]) < 1e-12    # after i3pre
+    assert rel_l2(o.HBrg, z["solgmre.HBrg"]) < 1e-9
+    assert rel_l2(p.Dy, z["solgmre.Dy"]) < 1e-10
+
+
+@pytest.mark.parametrize("name", names("solgmrs"))
+def test_oracle_solgmrs_matches_reference_fortran(name):
+    z, case, _ = load(name)
+    o = make_oracle(case)
+    ntot = o.genadj()[0]
+    p = o.parts[0]
+    assert ntot == int(z["solgmrs.nnz_tot"])
+    assert np.array_equal(p.colm, z["solgmrs.colm"])        # bit-exact integer targets (genadj.f)
+    assert np.array_equal(p.rowp, z["solgmrs.rowp"])
+    iKs, lG = o.SolGMRs()
+    assert (iKs, lG) == (int(z["solgmrs.iKs"]), int(z["solgmrs.lGMRES"]))
+    assert rel_l2(p.lhsK, z["solgmrs.lhsK"]) < 1e-12        # after Spsi3pre
+    assert rel_l2(o.HBrg, z["solgmrs.HBrg"]) < 1e-9
+    assert rel_l2(p.Dy, z["solgmrs.Dy"]) < 1e-10
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/phSolver/compressible"),
+                    reason="reference sources not present (GPU box)")
+def test_fixture_is_reproducible_from_the_reference_sources():
+    import sys
+    sys.path.insert(0, GOLD)
+    import make_golden_f77 as mg
+    prog = mg.make_program()
+    z, case, _ = load("tet_sutherland")
+    r = mg.run_elmgmre(prog, case, lhs=1)
+    for k in ("qres", "res", "BDiag", "EGmass"):
+        assert np.array_equal(r[k], z["elmgmre." + k]), k
+
+
+# ------------------------------------------------------------------ GPU: libphb200.so
+def gpu(case, dev=0):
+    from phasta_b200.solver import PhastaGPU
+    params, tables, parts, states = case
+    return PhastaGPU(parts[0], params, tables, device=dev)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", names("elmgmre") + names("elmgmre0"))
+def test_gpu_elmgmre_matches_reference_fortran(name):
+    z, case, runs = load(name)
+    run = "elmgmre" if "elmgmre" in runs else "elmgmre0"
+    g = gpu(case)
+    y, ac = case[3][0]
+    if run == "elmgmre":
+        out = g.ElmGMRe(y, ac, want_egmass=True, want_qres=True)
+    else:
+        out = g.ElmGMRe(y, ac, step=g.step(lhs=0, iprec=0), want_qres=True)
+    if run + ".qres" in z:
+        assert rel_l2(out["qres"], z[run + ".qres"]) < TOL_ASM
+    assert rel_l2(out["res"], z[run + ".res"]) < TOL_ASM
+    if run == "elmgmre":
+        assert rel_l2(out["BDiag"], z[run + ".BDiag"]) < TOL_ASM
+        assert rel_l2(out["EGmass"], z[run + ".EGmass"]) < TOL_ASM
+    if run + ".Force" in z:
+        Fo, H, fl = g.aerfrc()
+        ref = np.r_[z[run + ".Force"], z[run + ".HFlux"]]
+        assert rel_l2(np.r_[Fo, H], ref) < TOL_ASM
+        assert rel_l2(fl[:, :2], z[run + ".flxID"]) < TOL_ASM
+    g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", names("solgmre"))
+def test_gpu_solgmre_matches_reference_fortran(name):
+    z, case, _ = load(name)
+    g = gpu(case)
+    y, ac = case[3][0]
+    res, Dy = g.SolGMRe(y, ac)
+    assert (g.iKs, g.lGMRES) == (int(z["solgmre.iKs"]), int(z["solgmre.lGMRES"]))
+    assert rel_l2(res, z["solgmre.res"]) < TOL_ASM
+    assert rel_l2(Dy, z["solgmre.Dy"]) < TOL_SOL
+    k = g.iKs
+    assert rel_l2(g.HBrg[:k + 1, :k], z["solgmre.HBrg"][:k + 1, :k]) < 1e-8
+    g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", names("solgmrs"))
+def test_gpu_solgmrs_matches_reference_fortran(name):
+    z, case, _ = load(name)
+    g = gpu(case)
+    colm, rowp, ntot = g.genadj()
+    assert ntot == int(z["solgmrs.nnz_tot"])
+    assert np.array_equal(colm, z["solgmrs.colm"]) and np.array_equal(rowp, z["solgmrs.rowp"])
+    y, ac = case[3][0]
+    res, Dy = g.SolGMRs(y, ac)
+    assert (g.iKs, g.lGMRES) == (int(z["solgmrs.iKs"]), int(z["solgmrs.lGMRES"]))
+    assert rel_l2(Dy, z["solgmrs.Dy"]) < TOL_SOL
+    g.close()
