@@ -6,9 +6,13 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.
  *
- * PARITY UNPINNED at residual/matrix level: the reference ships no golden
- * vectors for this path; quadrature/shape tables ARE pinned
- * against the reference's own C generators (oracle/_ref, tests/golden).
+ * PINNED: the reference ships no golden vectors for this path
+ * and no Fortran compiler exists here, so the reference's own unmodified
+ * Fortran sources are executed by the f77np interpreter (tests/golden/f77np.py,
+ * make_golden_f77.py) and this oracle reproduces their outputs (res bit for
+ * bit, EGmass/BDiag/Dy to round-off, colm/rowp exactly; tests/test_golden_f77.py).
+ * Quadrature/shape tables are pinned against the reference's own C generators
+ * (oracle/_ref, tests/golden/tables_ref.npz).
  *
  * Every function cites the reference file:line (relative to /root/reference)
  * it restates.  Array layouts are the Fortran ones (column-major, 1-based

@@ -1148,7 +1148,10 @@ class Program:
                 if isinstance(act, (list, tuple)):
                     continue
                 if not isinstance(act, np.ndarray):
-                    raise TypeError("%s: dummy %s is an array but a scalar was passed" % (unit.name, dname))
+                    # scalar actual for an array dummy (asimfg.f passes `EGmassd = one` for EGmass): only the
+                    # first element exists; touching anything else raises IndexError
+                    L[dname] = np.array([act], dtype=np.float64 if isinstance(act, float) else np.int64)
+                    continue
                 shape, lbs = self._eval_dims(d.dims, env, total=act.size)
                 if tuple(shape) != act.shape:
                     n = int(np.prod(shape))
