@@ -761,10 +761,13 @@ void orc_au1gmr(int nparts, orc_part *parts, double **u) {
 /* ---------------- GMRES shared by SolGMRe / SolGMRs ---------------- */
 typedef void (*ap_fn)(int, orc_part *, double **);
 
+/* skip_bc3per / restart_fn: the matrix-free flavour (solmfg.f) applies no
+ * bc3per after its Ap and rebuilds the restart residual with Au2MFG, which
+ * leaves it in parts[m].temp. */
 static void gmres_core(int nparts, orc_part *parts, ap_fn Ap, int minIters,
                        int restart_recompute, double *HBrg, double *eBrg, double *yBrg, double *Rcos,
                        double *Rsin, int *iKs_out, int *lGMRES_out,
-                       int *ntotGM) {
+                       int *ntotGM, int skip_bc3per, ap_fn restart_fn) {
   const orc_common *c = &parts[0].c;
   int Kspace = c->Kspace, nGMRES = c->nGMRES;
   double **v = malloc(sizeof(double *) * nparts);
@@ -784,7 +787,18 @@ static void gmres_core(int nparts, orc_part *parts, ap_fn Ap, int minIters,
   double epsnrm = c->etol * unorm;
   for (int mGMRES = 1; mGMRES <= nGMRES; mGMRES++) {
     lGMRES = mGMRES - 1;
-    if (lGMRES > 0 && restart_recompute) { /* restart: R - A x (:149-178) */
+    if (lGMRES > 0 && restart_fn) { /* solmfg.f:167-180 */
+      for (int m = 0; m < nparts; m++) t[m] = parts[m].temp;
+      restart_fn(nparts, parts, t);
+      for (int m = 0; m < nparts; m++) {
+        size_t n = (size_t)parts[m].c.nshg * 5;
+        for (size_t i = 0; i < n; i++) {
+          UB(m, 1)[i] = parts[m].temp[i];
+          parts[m].temp[i] = parts[m].temp[i] * parts[m].temp[i];
+        }
+      }
+      unorm = sqrt(orc_sumgat(nparts, parts, t, 5));
+    } else if (lGMRES > 0 && restart_recompute) { /* restart: R - A x (:149-178) */
       for (int m = 0; m < nparts; m++) {
         size_t n = (size_t)parts[m].c.nshg * 5;
         memcpy(parts[m].temp, parts[m].Dy, sizeof(double) * n);
@@ -816,7 +830,8 @@ static void gmres_core(int nparts, orc_part *parts, ap_fn Ap, int minIters,
         v[m] = UB(m, iKs + 1);
       }
       Ap(nparts, parts, v);
-      for (int m = 0; m < nparts; m++) orc_bc3per(&parts[m], v[m], 5);
+      if (!skip_bc3per)
+        for (int m = 0; m < nparts; m++) orc_bc3per(&parts[m], v[m], 5);
       /* modified Gram-Schmidt (:224-252) */
       double beta = 0.0;
       for (int jK = 1; jK <= iKs + 1; jK++) {
@@ -900,7 +915,7 @@ void orc_solgmre(int nparts, orc_part *parts, double *HBrg, double *eBrg,
   }
   orc_i3pre(nparts, parts);
   gmres_core(nparts, parts, orc_au1gmr, 0, 1, HBrg, eBrg, yBrg, Rcos, Rsin, iKs,
-             lGMRES, ntotGM);
+             lGMRES, ntotGM, 0, NULL);
   for (int m = 0; m < nparts; m++)
     orc_i3lu(&parts[m].c, parts[m].BDiag, parts[m].Dy, 2); /* :347 */
 }
@@ -912,5 +927,15 @@ void orc_gmres_core(int nparts, orc_part *parts,
                     double *yBrg, double *Rcos, double *Rsin, int *iKs,
                     int *lGMRES, int *ntotGM) {
   gmres_core(nparts, parts, Ap, minIters, restart_recompute, HBrg, eBrg, yBrg,
-             Rcos, Rsin, iKs, lGMRES, ntotGM);
+             Rcos, Rsin, iKs, lGMRES, ntotGM, 0, NULL);
+}
+
+/* the same loop for SolMFG (oracle_mfg.c) */
+void orc_gmres_core_mfg(int nparts, orc_part *parts,
+                        void (*Ap)(int, orc_part *, double **),
+                        void (*restart)(int, orc_part *, double **), int minIters,
+                        double *HBrg, double *eBrg, double *yBrg, double *Rcos, double *Rsin,
+                        int *iKs, int *lGMRES, int *ntotGM) {
+  gmres_core(nparts, parts, Ap, minIters, 0, HBrg, eBrg, yBrg, Rcos, Rsin, iKs, lGMRES, ntotGM, 1,
+             restart);
 }

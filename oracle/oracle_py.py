@@ -272,6 +272,37 @@ class Oracle:
                             int(nshgt), C.byref(self.ifuncs), C.byref(self.ntotGM), _ptr(stats))
         return stats
 
+    # ---- matrix-free flavour (oracle_mfg.c) ----------------------------------
+    def ElmMFG(self):
+        self.L.orc_elmmfg(self.n, self.arr)
+
+    def ItrRes(self, yp, iabres=0):
+        """itrres.f on part 0 (single part): returns the modified residual of yp."""
+        yp = [np.asfortranarray(yp, dtype=np.float64).copy(order="F")]
+        out = [np.zeros((self.parts[0].mp.nshg, 5), order="F")]
+        self.L.orc_itrres(self.n, self.arr, self._vecs(yp), self._vecs(out), int(iabres))
+        return out[0]
+
+    def Au1MFG_once(self, u, eGMRES):
+        """solmfg.f:97-135 set-up on the current ElmMFG outputs, then one Au1MFG."""
+        for i, p in enumerate(self.parts):
+            c = C.byref(self.arr[i].c)
+            self.L.orc_i3lu(c, _ptr(p.BDiag), _ptr(p.res), 0)
+            self.L.orc_i3lu(c, _ptr(p.BDiag), _ptr(p.res), 1)
+            self.L.orc_i3lu(c, _ptr(p.BDiag), _ptr(p.rmes), 1)
+        self.L.orc_mfg_begin(self.n, self.arr, C.c_double(eGMRES))
+        v = [np.asfortranarray(u, dtype=np.float64).copy(order="F")]
+        self.L.orc_au1mfg(self.n, self.arr, self._vecs(v))
+        self.L.orc_mfg_end(self.n)
+        return v[0]
+
+    def SolMFG(self, eGMRES=0.0, iter=1, istep=0):
+        iKs, lG, eG = C.c_int(0), C.c_int(0), C.c_double(eGMRES)
+        self.L.orc_solmfg(self.n, self.arr, _ptr(self.HBrg), _ptr(self.eBrg), _ptr(self.yBrg),
+                          _ptr(self.Rcos), _ptr(self.Rsin), C.byref(iKs), C.byref(lG),
+                          C.byref(self.ntotGM), C.byref(eG), int(iter), int(istep))
+        return iKs.value, lG.value, eG.value
+
     def SolGMRe(self):
         iKs, lG = C.c_int(0), C.c_int(0)
         self.L.orc_solgmre(self.n, self.arr, _ptr(self.HBrg), _ptr(self.eBrg), _ptr(self.yBrg),

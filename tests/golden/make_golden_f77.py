@@ -298,6 +298,80 @@ def run_solgmrs(prog, case, nnz=35):
                 HBrg=HBrg, Dy=Dy, iKs=int(G["iks"]), lGMRES=int(G["lgmres"]))
 
 
+def run_solmfg(prog, case):
+    """itrBC (itrbc.f) on the state, then ElmMFG (elmmfg.f: AsIMFG, e3bdg), one
+    Au1MFG (au1mfg.f: i3LU, yshuffle, itrBC, ItrRes/AsIRes) on a seeded vector
+    with a fixed interval, then the whole SolMFG (solmfg.f: itrFDI, GMRES)."""
+    params, tables, parts, states = case
+    mp = parts[0]
+    y, ac = (F(a) for a in states[0])
+    nshape = max(int(b.shape[1]) for b in mp.mien)
+    set_commons(prog, params, tables, mp, 5 * nshape)
+    set_pointer_data(prog, mp, tables)
+    G = prog.G
+    nshg, K = mp.nshg, int(params.Kspace)
+    x, BC = F(mp.x), F(mp.BC)
+    iBC = np.array(mp.iBC, dtype=np.int64)
+    iper = np.array(mp.iper, dtype=np.int64)
+    ilwork = np.array(mp.ilwork, dtype=np.int64) if mp.nlwork else np.zeros(1, dtype=np.int64)
+    shp, shgl, shpb, shglb = full_tables(tables)
+    G["ires"] = 1
+    prog.call("itrbc", y, ac, iBC, BC, iper, ilwork)
+    out = dict(y_bc=y.copy(order="F"), ac_bc=ac.copy(order="F"))
+    stub = prog.stubs.get("rstat")
+    prog.stubs["rstat"] = _noop     # solmfg.f:367 calls rstat without its third argument
+    try:
+        # --- ElmMFG
+        G["lhs"], G["iprec"], G["nedof"] = 0, 1, 0          # itrdrv.f:496-498
+        res = np.zeros((nshg, 5), order="F")
+        rmes = np.zeros((nshg, 5), order="F")
+        BDiag = np.zeros((nshg, 5, 5), order="F")
+        rerr = np.zeros((nshg, 10), order="F")
+        prog.call("elmmfg", y, ac, x, shp, shgl, iBC, BC, shpb, shglb, res, rmes, BDiag, iper, ilwork, rerr)
+        out.update(elm_res=res.copy(order="F"), elm_rmes=rmes.copy(order="F"), elm_BDiag=BDiag.copy(order="F"))
+        # --- one Au1MFG with eGMRES = 1e-7 on a seeded unit vector (solmfg.f:97-135 set-up)
+        prog.call("i3lu", BDiag, res, "LU_Fact ")
+        prog.call("i3lu", BDiag, res, "forward ")
+        prog.call("i3lu", BDiag, rmes, "forward ")
+        ypre = np.asfortranarray(y[:, :5].copy(order="F"))
+        prog.call("yshuffle", ypre, "new2old ")
+        prog.call("i3lu", BDiag, ypre, "product ")
+        u = np.asfortranarray(np.random.default_rng(11).standard_normal((nshg, 5)))
+        u /= np.linalg.norm(u)
+        out["au1_in"] = u.copy(order="F")
+        G["egmres"] = 1.0e-7
+        G["ires"] = 2
+        prog.call("au1mfg", ypre, y, ac, x, rmes, res, u, BDiag, iBC, BC, iper, ilwork, shp, shgl, shpb, shglb)
+        out["au1_out"] = u.copy(order="F")
+        # --- ItrRes of a perturbed state (global {u,p,T} order), plain and iabres=1
+        yp = np.asfortranarray(y[:, :5] * (1.0 + 1.0e-3 * np.random.default_rng(12).standard_normal((nshg, 5))))
+        out["itrres_in"] = yp.copy(order="F")
+        for iab in (0, 1):
+            G["iabres"] = iab
+            r = np.zeros((nshg, 5), order="F")
+            prog.call("itrres", yp.copy(order="F"), y, x, shp, shgl, iBC, BC, shpb, shglb, r, iper, ilwork, ac)
+            out["itrres_out%d" % iab] = r
+        G["iabres"] = 0
+        # --- SolMFG
+        G["lhs"], G["iprec"], G["ires"] = 0, 1, 3
+        G["iter"], G["istep"], G["egmres"], G["ntotgm"] = 1, 0, 0.0, 0
+        res = np.zeros((nshg, 5), order="F")
+        BDiag = np.zeros((nshg, 5, 5), order="F")
+        HBrg = np.zeros((K + 1, K), order="F")
+        eBrg, yBrg, Rcos, Rsin = (np.zeros(K + 1) for _ in range(4))
+        Dy = np.zeros((nshg, 5), order="F")
+        prog.call("solmfg", y, ac, y.copy(order="F"), ac.copy(order="F"), x, iBC, BC, res, BDiag, HBrg, eBrg, yBrg,
+                  Rcos, Rsin, iper, ilwork, shp, shgl, shpb, shglb, Dy, rerr)
+        out.update(res=res, BDiag=BDiag, HBrg=HBrg, Dy=Dy, iKs=int(G["iks"]), lGMRES=int(G["lgmres"]),
+                   eGMRES=float(G["egmres"]))
+    finally:
+        if stub is None:
+            del prog.stubs["rstat"]
+        else:
+            prog.stubs["rstat"] = stub
+    return out
+
+
 def check(name, a, b, tol):
     a, b = np.asarray(a, dtype=float), np.asarray(b, dtype=float)
     nb = np.linalg.norm(b.ravel())
@@ -330,6 +404,8 @@ def main():
                 r = run_elmgmre(prog, case, lhs=1 if run == "elmgmre" else 0)
             elif run == "solgmre":
                 r = run_solgmre(prog, case)
+            elif run == "solmfg":
+                r = run_solmfg(prog, case)
             else:
                 r = run_solgmrs(prog, case)
             print("%s/%s via f77np: %.1f s" % (name, run, time.time() - t0))
@@ -351,6 +427,25 @@ def main():
                     if "Force" in r:
                         allok &= check("Force,HFlux", p.aerfrc[:4], np.r_[r["Force"], r["HFlux"]], 1e-12)
                         allok &= check("flxID", p.aerfrc[4:24].reshape((10, 2), order="F"), r["flxID"], 1e-12)
+                elif run == "solmfg":
+                    o.itrBC()
+                    allok &= check("itrBC y", p.keep["y"], r["y_bc"], 0.0)
+                    o.set_flags(lhs=0, iprec=1)
+                    o.ElmMFG()
+                    allok &= check("ElmMFG res", p.res, r["elm_res"], 1e-12)
+                    allok &= check("ElmMFG rmes", p.rmes, r["elm_rmes"], 1e-12)
+                    allok &= check("e3bdg BDiag", p.BDiag, r["elm_BDiag"], 1e-12)
+                    allok &= check("Au1MFG", o.Au1MFG_once(r["au1_in"], 1.0e-7), r["au1_out"], 1e-6)
+                    for iab in (0, 1):
+                        allok &= check("ItrRes iabres=%d" % iab, o.ItrRes(r["itrres_in"], iab),
+                                       r["itrres_out%d" % iab], 1e-12)
+                    o.set_flags(lhs=0, iprec=1)
+                    iKs, lG, eG = o.SolMFG(eGMRES=0.0, iter=1, istep=0)
+                    print("   iKs oracle %d reference %d   eGMRES %.6e / %.6e" % (iKs, r["iKs"], eG, r["eGMRES"]))
+                    allok &= iKs == r["iKs"] and abs(eG - r["eGMRES"]) <= 1e-4 * r["eGMRES"]
+                    allok &= check("res(precond)", p.res, r["res"], 1e-12)
+                    allok &= check("BDiag(LU)", p.BDiag, r["BDiag"], 1e-12)
+                    allok &= check("Dy", p.Dy, r["Dy"], 1e-4)
                 elif run == "solgmre":
                     iKs, lG = o.SolGMRe()
                     print("   iKs oracle %d reference %d" % (iKs, r["iKs"]))

@@ -18,13 +18,23 @@ CASES = {
     # (numel,nshape,5,5) array to local's (npro,nshl,25) dummy, which scrambles the tet blocks when nshl<nshape
     # (the reference's EBE solver is only well defined on single-topology meshes; its default SolGMRs is fine)
     "mixed_channel": ((2, 4, 2), dict(bc="channel", topo="mixed", ibksiz=16, etol=1e-6), ("elmgmre", "solgmrs")),
+    # matrix-free flavour (SolMFG): acoustic units (see common.nondimensional) and a state that has been through
+    # itrBC, as in itrdrv.f:394 -- Au1MFG applies itrBC to the perturbed state
+    "tet_nd_mfg": ((3, 2, 2), dict(bc="channel", ibksiz=16, boundary=True, natural="mixed", etol=1e-4, nd=True),
+                   ("solmfg",)),
+    "hex_nd_mfg": ((2, 2, 2), dict(bc="channel", topo="hex", ibksiz=8, etol=1e-4, nd=True), ("solmfg",)),
 }
 
 
 def build_case(name):
-    from common import make_case
+    from common import make_case, nondimensional
     a, kw, runs = CASES[name]
-    return make_case(*a, **kw), runs
+    kw = dict(kw)
+    nd = kw.pop("nd", False)
+    case = make_case(*a, **kw)
+    if nd:
+        case = nondimensional(case)
+    return case, runs
 
 
 def input_digest(case):

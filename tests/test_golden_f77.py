@@ -92,6 +92,35 @@ def test_oracle_solgmrs_matches_reference_fortran(name):
     assert rel_l2(p.Dy, z["solgmrs.Dy"]) < 1e-10
 
 
+@pytest.mark.parametrize("name", names("solmfg"))
+def test_oracle_solmfg_matches_reference_fortran(name):
+    """Matrix-free flavour.  Au1MFG is a finite difference with an interval of
+    ~1e-7 (itrfdi.f), so round-off in the residual is amplified by ~1e7: the
+    reference's own Ap carries ~1e-9 noise and eGMRES (a second difference)
+    ~1e-5; the tolerances on those two and on Dy reflect that, everything
+    upstream of the difference is at round-off."""
+    z, case, _ = load(name)
+    o = make_oracle(case)
+    p = o.parts[0]
+    o.itrBC()
+    assert np.array_equal(p.keep["y"], z["solmfg.y_bc"]) and np.array_equal(p.keep["ac"], z["solmfg.ac_bc"])
+    o.set_flags(lhs=0, iprec=1)
+    o.ElmMFG()
+    assert rel_l2(p.res, z["solmfg.elm_res"]) < 1e-13
+    assert rel_l2(p.rmes, z["solmfg.elm_rmes"]) < 1e-13
+    assert rel_l2(p.BDiag, z["solmfg.elm_BDiag"]) < 1e-13         # e3bdg.f
+    assert rel_l2(o.Au1MFG_once(z["solmfg.au1_in"], 1.0e-7), z["solmfg.au1_out"]) < 1e-7
+    for iab in (0, 1):
+        assert rel_l2(o.ItrRes(z["solmfg.itrres_in"], iab), z["solmfg.itrres_out%d" % iab]) < 1e-13
+    o.set_flags(lhs=0, iprec=1)
+    iKs, lG, eG = o.SolMFG(eGMRES=0.0, iter=1, istep=0)
+    assert (iKs, lG) == (int(z["solmfg.iKs"]), int(z["solmfg.lGMRES"]))
+    assert abs(eG - float(z["solmfg.eGMRES"])) < 1e-4 * float(z["solmfg.eGMRES"])
+    assert rel_l2(p.res, z["solmfg.res"]) < 1e-13
+    assert rel_l2(p.BDiag, z["solmfg.BDiag"]) < 1e-13
+    assert rel_l2(p.Dy, z["solmfg.Dy"]) < 1e-6
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference/phSolver/compressible"),
                     reason="reference sources not present (GPU box)")
 def test_fixture_is_reproducible_from_the_reference_sources():
