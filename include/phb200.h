@@ -47,7 +47,8 @@ typedef struct phb200_common {
 /* Scalars that change per call: /timdat/ (common.h:252-255; itrPC.f:18-47)
  * and the per-solve switches itrdrv sets (itrdrv.f:456-457,511-512). */
 typedef struct phb200_step {
-  int lhs, iprec, iter, nitr, lstep, pad;
+  int lhs, iprec, iter, nitr, lstep;
+  int istep; /* steps taken in this run (COMMON /timdat/): SolMFG recomputes eGMRES when mod(istep,20)==0 */
   double Dtgl, almi, alfi, gami, etol;
 } phb200_step;
 
@@ -207,6 +208,27 @@ int phb200_sizeof_step(void);
 /* test transport: several parts on ONE GPU, one host thread per part (see
  * csrc/comm.cu); stands in for phb200_comm_init on a single-GPU box */
 int phb200_local_group_join(phb200_ctx *ctx, int nranks);
+
+/* ---- matrix-free flavour: SolMFG (compressible/solmfg.f:1-381), called from the same ladder in itrdrv
+ * (itrdrv.f:494-505, lhs=0, iprec per LHSupd).  No EGmass / lhsK is ever stored: the Ap is a finite
+ * difference of the modified residual (Au1MFG, au1mfg.f:52-90; ItrRes/AsIRes, itrres.f, asires.f) and the
+ * block-diagonal preconditioner is built directly (e3bdg.f).  eGMRES is COMMON /itrpar/'s interval
+ * (common.h:217): in/out, recomputed by itrFDI (itrfdi.f) when st->iter==1 and mod(st->istep,20)==0.
+ * y must have been through itrBC (itrdrv.f:394), as Au1MFG applies itrBC to the perturbed state. */
+int phb200_solmfg(phb200_ctx *ctx, const double *y, const double *ac, const phb200_step *st, double *res,
+                  double *BDiag, double *Dy, double *HBrg, int *iKs, int *lGMRES, int *ntotGM, double *eGMRES);
+/* ElmMFG (elmmfg.f:1-256): res, modified residual rmes, e3bdg block diagonal (iprec/=0); any may be NULL */
+int phb200_elmmfg(phb200_ctx *ctx, const double *y, const double *ac, const phb200_step *st, double *res,
+                  double *rmes, double *BDiag);
+/* ItrRes (itrres.f:1-171) of yp(nshg,5) against the state of the last phb200_elmmfg / phb200_solmfg call */
+int phb200_itrres(phb200_ctx *ctx, const double *yp, double *rmes, int iabres);
+/* Au1MFG (au1mfg.f:1-98) in place on u(nshg,5); setup!=0 first performs solmfg.f:97-135 (LU_Fact, forward
+ * reduction of res / rmes, ypre) on the outputs of phb200_elmmfg */
+int phb200_au1mfg(phb200_ctx *ctx, double *u, double eGMRES, int setup);
+/* HBM-resident variants (state from phb200_set_state) */
+int phb200_dev_elmmfg(phb200_ctx *ctx, const phb200_step *st);
+int phb200_dev_solve_mfg(phb200_ctx *ctx, const phb200_step *st, int *iKs, int *lGMRES, int *ntotGM);
+int phb200_dev_au1mfg(phb200_ctx *ctx, int slot);
 
 #ifdef __cplusplus
 }

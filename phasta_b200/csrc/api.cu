@@ -207,6 +207,8 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   if (c->numpe > 1) PHB_TRY(dev_alloc(&ctx->d_BDtmp, (size_t)25 * nshg));
   ctx->d_EG = nullptr;  // allocated by the first EBE lhs=1 assembly
   ctx->d_yold = ctx->d_acold = nullptr;
+  ctx->d_mfg = nullptr;
+  ctx->eGMRES = 0.0;
   ctx->ifuncs = 0;
   ctx->nnz_tot = 0;
   ctx->d_colm = ctx->d_rowp = ctx->d_rowofblk = ctx->d_eloc = nullptr;
@@ -242,7 +244,7 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
                   ctx->d_rmass, ctx->d_res, ctx->d_rmes, ctx->d_Dy, ctx->d_temp, ctx->d_BDiag, ctx->d_BDtmp,
                   ctx->d_EG, ctx->d_uBrg, ctx->d_dots, ctx->d_scratch, ctx->d_ienb, ctx->d_iBCB,
                   ctx->d_BCB, ctx->d_aerfrc, ctx->d_colm, ctx->d_rowp, ctx->d_rowofblk, ctx->d_eloc, ctx->d_lhsK,
-                  ctx->d_nodeaos, ctx->d_yold, ctx->d_acold};
+                  ctx->d_nodeaos, ctx->d_yold, ctx->d_acold, ctx->d_mfg};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (ctx->d_refel_tet) cudaFree(ctx->d_refel_tet);
@@ -467,6 +469,95 @@ extern "C" int phb200_solgmrs(phb200_ctx *ctx, const double *y, const double *ac
   if (Rsin) memcpy(Rsin, ctx->Rsin.data(), sizeof(double) * (K + 1));
   return 0;
 }
+// ---------------------------------------------------------------------------
+// matrix-free flavour (solmfg.f, elmmfg.f, itrres.f, au1mfg.f)
+// ---------------------------------------------------------------------------
+extern "C" int phb200_elmmfg(phb200_ctx *ctx, const double *y, const double *ac, const phb200_step *st, double *res,
+                             double *rmes, double *BDiag) {
+  ENTER(ctx);
+  if (!y || !ac || !st) return fail("elmmfg", "null argument");
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  PHB_TRY(phb200_set_state(ctx, y, ac));
+  PHB_TRY(phb_elmmfg(ctx, st));
+  if (res) PHB_TRY(d2h(ctx, res, ctx->d_res, n5));
+  if (rmes) PHB_TRY(d2h(ctx, rmes, ctx->d_rmes, n5));
+  if (BDiag && st->iprec != 0) PHB_TRY(d2h(ctx, BDiag, ctx->d_BDiag, (size_t)25 * ctx->c.nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+// ItrRes (itrres.f): rmes(nshg,5) = modified residual of yp(nshg,5) {u,v,w,p,T}, coefficients frozen at the
+// state of the last phb200_elmmfg / phb200_solmfg call
+extern "C" int phb200_itrres(phb200_ctx *ctx, const double *yp, double *rmes, int iabres) {
+  ENTER(ctx);
+  if (!yp || !rmes) return fail("itrres", "null argument");
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  double *d_yp = ctx->d_uBrg, *d_out = ctx->d_uBrg + n5;
+  PHB_TRY(h2d(ctx, d_yp, yp, n5));
+  PHB_CHECK(cudaMemsetAsync(d_out, 0, sizeof(double) * n5, ctx->stream));
+  PHB_TRY(phb_itrres(ctx, d_yp, d_out, iabres));
+  PHB_TRY(d2h(ctx, rmes, d_out, n5));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+// the set-up of solmfg.f:97-135 on the outputs of phb200_elmmfg (LU_Fact, forward reduction of res and rmes,
+// ypre) followed by ONE Au1MFG of u(nshg,5) with the given interval (a parity seam)
+extern "C" int phb200_au1mfg(phb200_ctx *ctx, double *u, double eGMRES, int setup) {
+  ENTER(ctx);
+  if (!u) return fail("au1mfg", "null argument");
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  if (setup) {
+    PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, nullptr, 0));
+    PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, ctx->d_res, 1));
+    PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, ctx->d_rmes, 1));
+    PHB_TRY(phb_mfg_begin(ctx));
+  }
+  ctx->eGMRES = eGMRES;
+  double *d_u = ctx->d_uBrg;
+  PHB_TRY(h2d(ctx, d_u, u, n5));
+  PHB_TRY(phb_au1mfg(ctx, d_u));
+  PHB_TRY(d2h(ctx, u, d_u, n5));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+// SolMFG (solmfg.f:1-381).  eGMRES is COMMON /itrpar/'s finite-difference interval: in/out, recomputed by
+// itrFDI when st->iter==1 and mod(st->istep,20)==0.
+extern "C" int phb200_solmfg(phb200_ctx *ctx, const double *y, const double *ac, const phb200_step *st, double *res,
+                             double *BDiag, double *Dy, double *HBrg, int *iKs, int *lGMRES, int *ntotGM,
+                             double *eGMRES) {
+  ENTER(ctx);
+  if (!y || !ac || !st || !Dy || !iKs || !lGMRES || !ntotGM || !eGMRES) return fail("solmfg", "null argument");
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  ctx->eGMRES = *eGMRES;
+  PHB_TRY(phb200_set_state(ctx, y, ac));
+  PHB_TRY(phb_elmmfg(ctx, st));
+  PHB_TRY(phb_solve(ctx, st, 2, iKs, lGMRES, ntotGM));
+  PHB_TRY(d2h(ctx, Dy, ctx->d_Dy, n5));
+  if (res) PHB_TRY(d2h(ctx, res, ctx->d_res, n5));
+  if (BDiag) PHB_TRY(d2h(ctx, BDiag, ctx->d_BDiag, (size_t)25 * ctx->c.nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  const int K = ctx->c.Kspace;
+  if (HBrg) memcpy(HBrg, ctx->HBrg.data(), sizeof(double) * (size_t)(K + 1) * K);
+  *eGMRES = ctx->eGMRES;
+  return 0;
+}
+// HBM-resident variants for bench.py: state set by phb200_set_state
+extern "C" int phb200_dev_elmmfg(phb200_ctx *ctx, const phb200_step *st) {
+  ENTER(ctx);
+  return phb_elmmfg(ctx, st);
+}
+extern "C" int phb200_dev_solve_mfg(phb200_ctx *ctx, const phb200_step *st, int *iKs, int *lGMRES, int *ntotGM) {
+  ENTER(ctx);
+  return phb_solve(ctx, st, 2, iKs, lGMRES, ntotGM);
+}
+extern "C" int phb200_dev_au1mfg(phb200_ctx *ctx, int slot) {
+  ENTER(ctx);
+  if (slot < 0 || slot >= ctx->c.Kspace) return fail("dev_au1mfg", "slot out of range");
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  double *src = ctx->d_uBrg + (size_t)slot * n5, *dst = src + n5;
+  PHB_CHECK(cudaMemcpyAsync(dst, src, sizeof(double) * n5, cudaMemcpyDeviceToDevice, ctx->stream));
+  return phb_au1mfg(ctx, dst);
+}
+
 extern "C" int phb200_dev_elmgmrs(phb200_ctx *ctx, const phb200_step *st) {
   ENTER(ctx);
   return phb_elmgmre(ctx, st, 1);

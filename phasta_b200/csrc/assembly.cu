@@ -444,6 +444,7 @@ __device__ __forceinline__ void finish_block(double (&acc)[5][5], int a, int b, 
 #pragma unroll
         for (int n = 0; n < 5; n++) atomicAdd(BDiag + (size_t)nshg * (m + 5 * n) + na, acc[m][n]);
     }
+    if (LHS == 3) return;  // e3bdg (e3.f:258-285): only the block diagonal is wanted, nothing is stored
     if (ibca | ibcb) {
       // local view with dofs {p,u1,u2,u3,T} = indices 0..4; bc_rows/cols use 1..3 for velocities
       const int codea = (ibca >> 3) & 7, codeb = (ibcb >> 3) & 7;
@@ -471,6 +472,7 @@ __device__ __forceinline__ void finish_block(double (&acc)[5][5], int a, int b, 
       }
     }
   }
+  if (LHS == 3) return;
   if (LHS == 2) {
     // fillsparseC (fillsparse.f:66-126): lhsK(f+5g, k) += EGmass(e, r+f, s+g); the block index k
     // comes from the precomputed sparseloc map.  The 32 blocks of the warp are transposed through a
@@ -535,8 +537,9 @@ __device__ __forceinline__ void phase_b(const AsmSmem<TILE_E, NQ> &sm, int warp,
                                         double *__restrict__ EG, const int *__restrict__ eloc,
                                         double *__restrict__ lhsK, double *__restrict__ stage) {
       constexpr int NHALF = TILE_E / 32;
-      for (int task = warp; task < 16 * NHALF; task += NWARP) {
-        const int pair = task / NHALF, half = task % NHALF;
+      constexpr int NPAIR = (LHS == 3) ? 4 : 16;  // LHS==3: the four (a,a) blocks only (e3bdg.f)
+      for (int task = warp; task < NPAIR * NHALF; task += NWARP) {
+        const int pair = (LHS == 3) ? 5 * (task / NHALF) : task / NHALF, half = task % NHALF;
         const int a = pair >> 2, b = pair & 3;
         const int le = half * 32 + lane;
         const int ge = tile * TILE_E + le;
@@ -1677,7 +1680,8 @@ __global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
       const int lane = el, warp = sub;
       const int ge = tile * 32 + lane;
 #pragma unroll 1
-      for (int pair = warp; pair < NSHL * NSHL; pair += NQ) {
+      for (int pair0 = warp; pair0 < ((LHS == 3) ? NSHL : NSHL * NSHL); pair0 += NQ) {
+        const int pair = (LHS == 3) ? pair0 * (NSHL + 1) : pair0;  // LHS==3: (a,a) blocks only (e3bdg.f)
         const int a = pair / NSHL, b = pair % NSHL;
         double acc[5][5];
 #pragma unroll
@@ -1829,6 +1833,7 @@ template <int NSHL, int NQ>
 static int launch_asigmr_gen_mode(phb200_ctx *ctx, const ElemGroup &g, int mode) {
   if (mode == 1) return launch_asigmr_gen<NSHL, NQ, 1>(ctx, g);
   if (mode == 2) return launch_asigmr_gen<NSHL, NQ, 2>(ctx, g);
+  if (mode == 3) return launch_asigmr_gen<NSHL, NQ, 3>(ctx, g);
   return launch_asigmr_gen<NSHL, NQ, 0>(ctx, g);
 }
 
@@ -1901,6 +1906,223 @@ static int launch_asigmr_ws(phb200_ctx *ctx) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// AsIRes + e3 with ires=2 (asires.f:1-94, e3ivar.f, e3conv.f:100-186, e3visc.f:278-343, e3ls.f:95-346,
+// e3tau.f, e3massr.f:73-83, e3wmlt.f:95-122): the modified residual of the matrix-free solver,
+//   rml_a = W [ N_a ( A_i Y,i + fct1 U(Y) ) + N_a,i ( K_ij Y,j + A_i tau ( A_j Y,j + fct1 U(Y) ) ) ]
+// with Y,i and U from the perturbed state yp and every coefficient (A_i, K, tau, metric) frozen at the base
+// state (node records).  Thread = element, quadrature loop inside; 20 gathered doubles of yp per element
+// (L2 resident), nshl*5 atomicAdds.  The Ap of the matrix-free GMRES is one launch of this kernel:
+// 8 B * (ien nshl*4/8 + ...) ~ 150 B and ~6 kflop per tet instead of 3 200 B of EGmass.
+// ---------------------------------------------------------------------------
+template <int NSHL, int NQ>
+__global__ void __launch_bounds__(128) k_asires(int tab, int numel, size_t numel_pad, int nshg,
+                                                const int *__restrict__ ien, const double *__restrict__ aos,
+                                                const double *__restrict__ yp, double *__restrict__ rmes,
+                                                int iabres) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= numel) return;
+  int nd[NSHL];
+  double xl[NSHL][3], yc[NSHL][5], yl[NSHL][5];
+#pragma unroll
+  for (int a = 0; a < NSHL; a++) {
+    nd[a] = ien[(size_t)a * numel_pad + e];
+    const double2 *rec = reinterpret_cast<const double2 *>(aos + (size_t)nd[a] * NREC);
+    const double2 v0 = __ldg(rec), v1 = __ldg(rec + 1), v2 = __ldg(rec + 2), v3 = __ldg(rec + 3);
+    xl[a][0] = v0.x; xl[a][1] = v0.y; xl[a][2] = v1.x;
+    yc[a][0] = v1.y; yc[a][1] = v2.x; yc[a][2] = v2.y; yc[a][3] = v3.x; yc[a][4] = v3.y;
+    gather_y(yp, nshg, nd[a], yl[a]);
+  }
+  double rml[NSHL][5];
+#pragma unroll
+  for (int a = 0; a < NSHL; a++)
+#pragma unroll
+    for (int m = 0; m < 5; m++) rml[a][m] = 0.0;
+  GenMetric<NSHL> g;
+  double gij[6];
+  double gr[3][5];
+#pragma unroll 1
+  for (int q = 0; q < NQ; q++) {
+    const double *Nq = (NSHL == 4) ? c_tet.N[q] : c_gen[tab].N[q];
+    if (NSHL != 4 || q == 0) {  // metric, gradients and g_ij are constant on a linear tet
+      const double (*dN)[3] = (NSHL == 4) ? c_tet.dN[0] : c_gen[tab].dN[q];
+      const double Qw = (NSHL == 4) ? c_tet.Qwt[0] : c_gen[tab].Qwt[q];
+      gen_metric<NSHL>(xl, dN, Qw, g);
+      if (NSHL == 4) {
+        tet_gij(g.dxidx, gij);
+      } else {  // e3gijd, lcsyst >= 2 (e3tau.f:1408-1431)
+        const double (*d)[3] = g.dxidx;
+        gij[0] = d[0][0] * d[0][0] + d[1][0] * d[1][0] + d[2][0] * d[2][0];
+        gij[1] = d[0][0] * d[0][1] + d[1][0] * d[1][1] + d[2][0] * d[2][1];
+        gij[2] = d[0][1] * d[0][1] + d[1][1] * d[1][1] + d[2][1] * d[2][1];
+        gij[3] = d[0][0] * d[0][2] + d[1][0] * d[1][2] + d[2][0] * d[2][2];
+        gij[4] = d[0][1] * d[0][2] + d[1][1] * d[1][2] + d[2][1] * d[2][2];
+        gij[5] = d[0][2] * d[0][2] + d[1][2] * d[1][2] + d[2][2] * d[2][2];
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int m = 0; m < 5; m++) {
+          double sacc = 0.0;
+#pragma unroll
+          for (int a = 0; a < NSHL; a++) sacc += g.shg[a][i] * yl[a][m];
+          gr[i][m] = sacc;
+        }
+    }
+    double Yc[5] = {0, 0, 0, 0, 0}, Yp[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < NSHL; a++)
+#pragma unroll
+      for (int m = 0; m < 5; m++) {
+        Yc[m] += Nq[a] * yc[a][m];
+        Yp[m] += Nq[a] * yl[a][m];
+      }
+    // conservative variables of the perturbed state (e3ivar.f:164-185)
+    double dui[5];
+    {
+      const double rkp = 0.5 * (Yp[1] * Yp[1] + Yp[2] * Yp[2] + Yp[3] * Yp[3]);
+      const double rhop = Yp[0] / (c_ph.Rgas * Yp[4]);
+      const double eip = Yp[4] * (c_ph.Rgas / c_ph.gamma1);
+      dui[0] = rhop;
+      dui[1] = rhop * Yp[1];
+      dui[2] = rhop * Yp[2];
+      dui[3] = rhop * Yp[3];
+      dui[4] = rhop * (eip + rkp);
+    }
+    // point state of the base solution (e3ivar.f:186-252, getthm.f, getdiff.f, e3mtrx.f:87-97)
+    const double pres = Yc[0], u1 = Yc[1], u2 = Yc[2], u3 = Yc[3], T = Yc[4];
+    const double rho = pres / (c_ph.Rgas * T);
+    const double h = T * (c_ph.Rgas * c_ph.gamma / c_ph.gamma1);
+    const double cv = c_ph.Rgas / c_ph.gamma1;
+    const double cp = c_ph.Rgas * c_ph.gamma / c_ph.gamma1;
+    const double alfap = 1.0 / T, betaT = 1.0 / pres;
+    const double rk = 0.5 * (u1 * u1 + u2 * u2 + u3 * u3);
+    double mu, lam, con;
+    diffusivities(T, cp, mu, lam, con);
+    const double drdp = rho * betaT, drdT = -rho * alfap;
+    const double e1p = drdp * (h + rk) - alfap * T;
+    const double e3p = rho * (h + rk);
+    const double e4p = drdT * (h + rk) + rho * cp;
+    const double u[3] = {u1, u2, u3};
+    const double w[5] = {rho, rho * u1, rho * u2, rho * u3, e3p};
+    auto A0v = [&](const double v[5], double o[5]) {
+      double c1 = drdp * v[0] + drdT * v[4];
+      o[0] = c1;
+      o[1] = u1 * c1 + rho * v[1];
+      o[2] = u2 * c1 + rho * v[2];
+      o[3] = u3 * c1 + rho * v[3];
+      o[4] = e1p * v[0] + rho * (u1 * v[1] + u2 * v[2] + u3 * v[3]) + e4p * v[4];
+    };
+    double rmi[20];
+#pragma unroll
+    for (int k = 0; k < 20; k++) rmi[k] = 0.0;
+    // A_i Y,i (e3conv.f:100-179) -> rmi(16:20) (e3conv.f:183-186), + fct1 U (e3massr.f:73-83)
+    double adv[5], L[5], tmpv[5];
+#pragma unroll
+    for (int m = 0; m < 5; m++) adv[m] = u1 * gr[0][m] + u2 * gr[1][m] + u3 * gr[2][m];
+    const double divu = gr[0][1] + gr[1][2] + gr[2][3];
+    A0v(adv, tmpv);
+    L[0] = tmpv[0] + w[0] * divu;
+    L[1] = tmpv[1] + w[1] * divu + gr[0][0];
+    L[2] = tmpv[2] + w[2] * divu + gr[1][0];
+    L[3] = tmpv[3] + w[3] * divu + gr[2][0];
+    L[4] = tmpv[4] + w[4] * divu + adv[0];
+#pragma unroll
+    for (int m = 0; m < 5; m++) {
+      L[m] = L[m] + c_ph.fct1 * dui[m];  // rLymi (e3ls.f:103)
+      rmi[15 + m] = L[m];
+    }
+    // viscous / heat flux K_ij Y,j (e3visc.f:278-343)
+    double f[3][4];
+    diff_flux(gr, u1, u2, u3, mu, lam, con, f);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int m = 0; m < 4; m++) rmi[5 * i + 1 + m] = f[i][m];
+    // Shakib tau (e3tau.f:140-176)
+    const double fff = (c_ph.ipord == 1) ? 36.0 : (c_ph.ipord == 2 ? 60.0 : 128.0);
+    const double dts = c_ph.iremove ? 0.0 : c_ph.dtsfct * c_ph.Dtgl;
+    double tau2 = rho * rho * ((2.0 * dts) * (2.0 * dts) +
+                               (u1 * (u1 * gij[0] + 2.0 * (u2 * gij[1] + u3 * gij[3])) +
+                                u2 * (u2 * gij[2] + 2.0 * u3 * gij[4]) + u3 * u3 * gij[5])) +
+                  fff * mu * mu * (gij[0] * gij[0] + gij[2] * gij[2] + gij[5] * gij[5] +
+                                   2.0 * (gij[1] * gij[1] + gij[3] * gij[3] + gij[4] * gij[4]));
+    const double fact = sqrt(tau2);
+    const double tau1 = 0.125 * fact / (rho * (gij[0] + gij[2] + gij[5])) * c_ph.taucfct;
+    tau2 = 1.0 / fact;
+    const double tau3 = tau2 / cv * c_ph.temper;
+    L[0] *= tau1; L[1] *= tau2; L[2] *= tau2; L[3] *= tau2; L[4] *= tau3;
+    A0v(L, tmpv);  // A_i tau Lm (e3ls.f:231-346)
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int m = 0; m < 5; m++) rmi[5 * i + m] += u[i] * tmpv[m] + w[m] * L[1 + i];
+      rmi[5 * i + 1 + i] += L[0];
+      rmi[5 * i + 4] += u[i] * L[0];
+    }
+    // e3wmlt.f:95-122
+    const double W = g.W;
+#pragma unroll
+    for (int a = 0; a < NSHL; a++) {
+      const double Na = Nq[a];
+#pragma unroll
+      for (int m = 0; m < 5; m++)
+        rml[a][m] += W * (g.shg[a][0] * rmi[m] + g.shg[a][1] * rmi[5 + m] + g.shg[a][2] * rmi[10 + m] +
+                          Na * rmi[15 + m]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < NSHL; a++)
+#pragma unroll
+    for (int m = 0; m < 5; m++) {
+      const double v = iabres ? fabs(rml[a][m]) : rml[a][m];  // asires.f:83
+      atomicAdd(rmes + (size_t)nshg * m + nd[a], v);
+    }
+}
+
+// interior part of ItrRes (itrres.f:58-92): d_rmes += modified residual of d_yp ([5][nshg], {u,v,w,p,T});
+// the node records must hold the base state (phb_elmgmre packs them)
+int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres) {
+  const phb200_common &c = ctx->c;
+  cudaStream_t s = ctx->stream;
+  const int nq = c.nint[0];
+  if (ctx->numel_tet > 0) {
+    if (nq != 4) {
+      fprintf(stderr, "phb200: matrix-free path: tets need the 4-point rule (e3juel's 1-point mass is not built)\n");
+      return 1;
+    }
+    KScope ks(ctx, KC_ASM);
+    k_asires<4, 4><<<(ctx->numel_tet + 127) / 128, 128, 0, s>>>(0, ctx->numel_tet, ctx->numel_pad, c.nshg, ctx->d_ien,
+                                                                ctx->d_nodeaos, d_yp, d_rmes, iabres);
+    PHB_CHECK(cudaGetLastError());
+  }
+  for (const ElemGroup &g : ctx->gen) {
+    KScope ks(ctx, KC_ASM);
+    const int nb = (g.numel + 127) / 128;
+    if (g.nshl == 8)
+      k_asires<8, 8><<<nb, 128, 0, s>>>(g.tab, g.numel, g.numel_pad, c.nshg, g.d_ien, ctx->d_nodeaos, d_yp, d_rmes,
+                                        iabres);
+    else
+      k_asires<6, 6><<<nb, 128, 0, s>>>(g.tab, g.numel, g.numel_pad, c.nshg, g.d_ien, ctx->d_nodeaos, d_yp, d_rmes,
+                                        iabres);
+    PHB_CHECK(cudaGetLastError());
+  }
+  return 0;
+}
+
+// bc3Res + periodic + slave zeroing of a residual-like vector (the tail of ElmGMRe / ItrRes)
+int phb_bc3res_vec(phb200_ctx *ctx, double *d_r) {
+  const phb200_common &c = ctx->c;
+  {
+    KScope ks(ctx, KC_NODE);
+    k_bc3res<<<(c.nshg + 255) / 256, 256, 0, ctx->stream>>>(c.nshg, ctx->d_iBC, ctx->d_BC, c.Rgas, d_r);
+    PHB_CHECK(cudaGetLastError());
+  }
+  PHB_TRY(phb_bc3per(ctx, d_r, 5));
+  PHB_TRY(phb_zero_slaves(ctx, d_r, 5, 0));
+  return 0;
+}
+
 // ElmGMRe (elmgmr.f:1-274) on the resident state
 int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   const phb200_common &c = ctx->c;
@@ -1968,20 +2190,25 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
     PHB_CHECK(cudaMemsetAsync(ctx->d_lhsK, 0, sizeof(double) * 25 * (size_t)ctx->nnz_tot, s));
   }
   if (st->lhs == 1 && !sparse) PHB_TRY(phb_alloc_eg(ctx));  // EBE storage on first use (3200 B per tet)
-  const int mode = (st->lhs == 1) ? (sparse ? 2 : 1) : 0;
+  // mode 3 (matrix-free flavour, itrdrv.f:496-498: lhs=0, iprec per LHSupd): the block diagonal is built
+  // directly (e3bdg, e3.f:258-285) = the (a,a) blocks of what EGmass would hold
+  const int mode = (st->lhs == 1) ? (sparse ? 2 : 1) : ((st->iprec != 0) ? 3 : 0);
   if (ctx->numel_tet > 0) {
     static const bool use_ws = !(getenv("PHB200_ASM_WS") && atoi(getenv("PHB200_ASM_WS")) == 0);
     if (nq == 4 && use_ws && ctx->tet_uniform_rule) {
       if (mode == 1) PHB_TRY((launch_asigmr_ws<1>(ctx)));
       else if (mode == 2) PHB_TRY((launch_asigmr_ws<2>(ctx)));
+      else if (mode == 3) PHB_TRY((launch_asigmr<32, 4, 3>(ctx)));
       else PHB_TRY((launch_asigmr<32, 4, 0>(ctx)));  // residual only: phase A dominates, no producer split
     } else if (nq == 4) {
       if (mode == 1) PHB_TRY((launch_asigmr<32, 4, 1>(ctx)));
       else if (mode == 2) PHB_TRY((launch_asigmr<32, 4, 2>(ctx)));
+      else if (mode == 3) PHB_TRY((launch_asigmr<32, 4, 3>(ctx)));
       else PHB_TRY((launch_asigmr<32, 4, 0>(ctx)));
     } else {
       if (mode == 1) PHB_TRY((launch_asigmr<32, 1, 1>(ctx)));
       else if (mode == 2) PHB_TRY((launch_asigmr<32, 1, 2>(ctx)));
+      else if (mode == 3) PHB_TRY((launch_asigmr<32, 1, 3>(ctx)));
       else PHB_TRY((launch_asigmr<32, 1, 0>(ctx)));
     }
   }

@@ -105,6 +105,9 @@ struct phb200_ctx {
   double *d_scratch;             // L2 flush / fp64 peak
   size_t scratch_bytes;
   bool have_lhs;                 // EGmass/BDiag hold a (preconditioned) system
+  // ---- matrix-free flavour (SolMFG): ypre, two work vectors [3][5][nshg]; eGMRES of COMMON /itrpar/
+  double *d_mfg;
+  double eGMRES;
   bool tet_uniform_rule;         // same N_a,xi and weight at every tet quadrature point
   // host copies of the block structure (pointers stay caller-owned, as mien(iblk)%p does)
   std::vector<int> h_lcblk;
@@ -145,6 +148,8 @@ int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, co
                       const double *shglb);
 int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse = 0);
 int phb_alloc_eg(phb200_ctx *ctx);
+int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres);
+int phb_bc3res_vec(phb200_ctx *ctx, double *d_r);
 // solver.cu
 int phb_i3lu(phb200_ctx *ctx, double *d_Diag, double *d_r, int code);
 int phb_i3pre(phb200_ctx *ctx);
@@ -157,6 +162,14 @@ int phb_fp64_peak(phb200_ctx *ctx, double *tflops);
 // timestep.cu
 int phb_itrpredict(phb200_ctx *ctx, const phb200_step *st, int ipred);
 int phb_itrbc(phb200_ctx *ctx, int ires);
+int phb_itrbc_vec(phb200_ctx *ctx, double *d_y, double *d_ac, int ires);
+// mfg.cu (matrix-free flavour)
+int phb_elmmfg(phb200_ctx *ctx, const phb200_step *st);
+int phb_itrres(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres);
+int phb_mfg_begin(phb200_ctx *ctx);
+int phb_au1mfg(phb200_ctx *ctx, double *d_u);
+int phb_au2mfg(phb200_ctx *ctx, double *d_out);
+int phb_itrfdi(phb200_ctx *ctx);
 int phb_itrcorrect(phb200_ctx *ctx, const phb200_step *st);
 int phb_itrupdate(phb200_ctx *ctx, const phb200_step *st);
 int phb_rstat(phb200_ctx *ctx, long long nshgt, double *totres);

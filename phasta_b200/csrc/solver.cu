@@ -436,17 +436,24 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, 
   double *HBrg = ctx->HBrg.data(), *eBrg = ctx->eBrg.data(), *yBrg = ctx->yBrg.data(), *Rcos = ctx->Rcos.data(),
          *Rsin = ctx->Rsin.data();
 #define H(a, b) HBrg[((a)-1) + (size_t)(Kspace + 1) * ((b)-1)]
+  // sparse==2: SolMFG (solmfg.f:86-375) after ElmMFG: rmes is the modified residual (forward-reduced like res,
+  // :106-107), Ap = Au1MFG without bc3per, restarts through Au2MFG, itrFDI sets the interval (mfg.cu)
+  const bool mfg = (sparse == 2);
+  if (mfg) sparse = 0;
   // rmes = res (solgmr.f:83)
-  PHB_CHECK(cudaMemcpyAsync(ctx->d_rmes, ctx->d_res, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-  auto Ap = [&](double *v) { return sparse ? phb_sparseap(ctx, v) : phb_au1gmr(ctx, v); };
-  const int minIters = sparse ? c.minIters : 0;
+  if (!mfg) PHB_CHECK(cudaMemcpyAsync(ctx->d_rmes, ctx->d_res, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
+  auto Ap = [&](double *v) { return mfg ? phb_au1mfg(ctx, v) : (sparse ? phb_sparseap(ctx, v) : phb_au1gmr(ctx, v)); };
+  const int minIters = (sparse || mfg) ? c.minIters : 0;
   if (st->iprec != 0) {
     PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, nullptr, 0));
     if (sparse) PHB_TRY(phb_commu(ctx, ctx->d_BDiag, 25, 1));
   }
   PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, ctx->d_res, 1));
   PHB_CHECK(cudaMemsetAsync(ctx->d_Dy, 0, sizeof(double) * n, s));
-  if (sparse) {
+  if (mfg) {
+    PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, ctx->d_rmes, 1));
+    PHB_TRY(phb_mfg_begin(ctx));
+  } else if (sparse) {
     if (st->lhs == 1) PHB_TRY(phb_spsi3pre(ctx));
   } else {
     PHB_TRY(phb_i3pre(ctx));  // unconditional in SolGMRe (solgmr.f:112)
@@ -459,9 +466,14 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, 
   std::fill(ctx->HBrg.begin(), ctx->HBrg.end(), 0.0);
   if (!(unorm < 100.0 * c.epsM * c.epsM)) {
     const double epsnrm = st->etol * unorm;
+    if (mfg && st->iter == 1 && (st->istep % 20) == 0) PHB_TRY(phb_itrfdi(ctx));  // solmfg.f:150-157
     for (int mGMRES = 1; mGMRES <= nGMRES; mGMRES++) {
       lGMRES = mGMRES - 1;
-      if (lGMRES > 0 && !sparse) {  // restart: R - A x (solgmr.f:149-178)
+      if (lGMRES > 0 && mfg) {  // solmfg.f:167-180
+        PHB_TRY(phb_au2mfg(ctx, Uk(1)));
+        PHB_TRY(dot_host(ctx, n, Uk(1), Uk(1), &summed));
+        unorm = sqrt(summed);
+      } else if (lGMRES > 0 && !sparse) {  // restart: R - A x (solgmr.f:149-178)
         double *tmp = Uk(Kspace + 1);  // free slot at restart time
         PHB_CHECK(cudaMemcpyAsync(tmp, ctx->d_Dy, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
         PHB_TRY(Ap(tmp));
@@ -486,7 +498,7 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, 
         double *w = Uk(iKs + 1);
         PHB_CHECK(cudaMemcpyAsync(w, Uk(iKs), sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
         PHB_TRY(Ap(w));
-        PHB_TRY(phb_bc3per(ctx, w, 5));
+        if (!mfg) PHB_TRY(phb_bc3per(ctx, w, 5));
         // modified Gram-Schmidt, beta_j stay on the device (d_dots[j]) unless
         // an allreduce is needed between steps
         PHB_CHECK(cudaMemsetAsync(ctx->d_dots, 0, sizeof(double) * (iKs + 2), s));

@@ -167,24 +167,28 @@ int phb_itrpredict(phb200_ctx *ctx, const phb200_step *st, int ipred) {
   return 0;
 }
 
-int phb_itrbc(phb200_ctx *ctx, int ires) {
+// itrBC on any (y, ac) pair in the global {u,v,w,p,T} layout; Au1MFG applies it to the perturbed state with
+// ires=2, where ac is not touched (itrbc.f:177-191)
+int phb_itrbc_vec(phb200_ctx *ctx, double *d_y, double *d_ac, int ires) {
   const int nshg = ctx->c.nshg;
   {
     KScope ks(ctx, KC_NODE);
-    k_itr_bc<<<nblk(nshg, 256), 256, 0, ctx->stream>>>(nshg, ctx->d_iBC, ctx->d_BC, ctx->c.Rgas, ctx->d_y);
+    k_itr_bc<<<nblk(nshg, 256), 256, 0, ctx->stream>>>(nshg, ctx->d_iBC, ctx->d_BC, ctx->c.Rgas, d_y);
     if (ctx->n_perslave) {
       k_itr_per<<<nblk((size_t)ctx->n_perslave * 5, 256), 256, 0, ctx->stream>>>(
-          ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, ctx->d_y, ires != 2 ? ctx->d_ac : nullptr);
+          ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, d_y, ires != 2 ? d_ac : nullptr);
       ctx->launches++;
     }
     PHB_CHECK(cudaGetLastError());
   }
   if (ctx->c.numpe > 1) {
-    PHB_TRY(phb_commu(ctx, ctx->d_y, 5, 1));
-    if (ires != 2) PHB_TRY(phb_commu(ctx, ctx->d_ac, 5, 1));
+    PHB_TRY(phb_commu(ctx, d_y, 5, 1));
+    if (ires != 2) PHB_TRY(phb_commu(ctx, d_ac, 5, 1));
   }
   return 0;
 }
+
+int phb_itrbc(phb200_ctx *ctx, int ires) { return phb_itrbc_vec(ctx, ctx->d_y, ctx->d_ac, ires); }
 
 int phb_itrcorrect(phb200_ctx *ctx, const phb200_step *st) {
   KScope ks(ctx, KC_NODE);

@@ -34,7 +34,7 @@ class PhbCommon(C.Structure):
 
 class PhbStep(C.Structure):
     """struct phb200_step."""
-    _fields_ = [*[(n, C.c_int) for n in ("lhs", "iprec", "iter", "nitr", "lstep", "pad")],
+    _fields_ = [*[(n, C.c_int) for n in ("lhs", "iprec", "iter", "nitr", "lstep", "istep")],
                 *[(n, C.c_double) for n in ("Dtgl", "almi", "alfi", "gami", "etol")]]
 
 
@@ -52,6 +52,8 @@ SYMBOLS = [
     "phb200_dev_solve_sparse", "phb200_dev_sparseap",
     "phb200_set_old_state", "phb200_get_state", "phb200_itrpredict", "phb200_itrbc", "phb200_itrcorrect",
     "phb200_itrupdate", "phb200_rstat", "phb200_timestep",
+    "phb200_solmfg", "phb200_elmmfg", "phb200_itrres", "phb200_au1mfg", "phb200_dev_elmmfg",
+    "phb200_dev_solve_mfg", "phb200_dev_au1mfg",
 ]
 
 _LIB = None

@@ -207,6 +207,60 @@ class PhastaGPU:
         self.rmes = rmes
         return res, Dy
 
+    # ------------------------------------------------------ matrix-free flavour
+    def ElmMFG(self, y, ac, *, step=None):
+        """elmmfg.f:1-256.  Returns dict(res, rmes, BDiag): residual, modified
+        residual and the e3bdg block diagonal (lhs=0, iprec=1; itrdrv.f:496-498)."""
+        st = step or self.step(lhs=0, iprec=1)
+        y = np.asfortranarray(y, dtype=np.float64)
+        ac = np.asfortranarray(ac, dtype=np.float64)
+        res, rmes = self._vec(), self._vec()
+        BD = np.zeros((self.part.nshg, 5, 5), order="F") if st.iprec else None
+        _chk(self.L.phb200_elmmfg(self.ctx, _p(y), _p(ac), C.byref(st), _p(res), _p(rmes), _p(BD)), "elmmfg")
+        return dict(res=res, rmes=rmes, BDiag=BD)
+
+    def ItrRes(self, yp, iabres=0):
+        """itrres.f:1-171: modified residual of yp(nshg,5) {u,v,w,p,T}."""
+        yp = np.asfortranarray(yp, dtype=np.float64)
+        out = self._vec()
+        _chk(self.L.phb200_itrres(self.ctx, _p(yp), _p(out), int(iabres)), "itrres")
+        return out
+
+    def Au1MFG(self, u, eGMRES, setup=True):
+        """au1mfg.f:1-98 on a copy of u; setup performs solmfg.f:97-135 first."""
+        u = np.asfortranarray(u, dtype=np.float64).copy(order="F")
+        _chk(self.L.phb200_au1mfg(self.ctx, _p(u), C.c_double(eGMRES), int(bool(setup))), "au1mfg")
+        return u
+
+    def SolMFG(self, y, ac, *, step=None, eGMRES=None):
+        """solmfg.f:1-381.  Returns (res, Dy); self.eGMRES carries COMMON /itrpar/'s
+        interval between calls."""
+        st = step or self.step(lhs=0, iprec=1)
+        y = np.asfortranarray(y, dtype=np.float64)
+        ac = np.asfortranarray(ac, dtype=np.float64)
+        res, Dy = self._vec(), self._vec()
+        BD = np.zeros((self.part.nshg, 5, 5), order="F")
+        iKs, lG, ntot = C.c_int(0), C.c_int(0), C.c_int(self.ntotGM)
+        eG = C.c_double(getattr(self, "eGMRES", 0.0) if eGMRES is None else eGMRES)
+        _chk(self.L.phb200_solmfg(self.ctx, _p(y), _p(ac), C.byref(st), _p(res), _p(BD), _p(Dy), _p(self.HBrg),
+                                  C.byref(iKs), C.byref(lG), C.byref(ntot), C.byref(eG)), "solmfg")
+        self.iKs, self.lGMRES, self.ntotGM, self.eGMRES, self.BDiag = iKs.value, lG.value, ntot.value, eG.value, BD
+        return res, Dy
+
+    def dev_elmmfg(self, step=None):
+        st = step or self.step(lhs=0, iprec=1)
+        _chk(self.L.phb200_dev_elmmfg(self.ctx, C.byref(st)), "dev_elmmfg")
+
+    def dev_solve_mfg(self, step=None):
+        st = step or self.step(lhs=0, iprec=1)
+        iKs, lG, ntot = C.c_int(0), C.c_int(0), C.c_int(self.ntotGM)
+        _chk(self.L.phb200_dev_solve_mfg(self.ctx, C.byref(st), C.byref(iKs), C.byref(lG), C.byref(ntot)),
+             "dev_solve_mfg")
+        self.iKs, self.lGMRES, self.ntotGM = iKs.value, lG.value, ntot.value
+
+    def dev_au1mfg(self, slot=0):
+        _chk(self.L.phb200_dev_au1mfg(self.ctx, int(slot)), "dev_au1mfg")
+
     def dev_elmgmrs(self, step=None):
         st = step or self.step()
         _chk(self.L.phb200_dev_elmgmrs(self.ctx, C.byref(st)), "dev_elmgmrs")

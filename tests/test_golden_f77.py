@@ -194,3 +194,31 @@ def test_gpu_solgmrs_matches_reference_fortran(name):
     assert (g.iKs, g.lGMRES) == (int(z["solgmrs.iKs"]), int(z["solgmrs.lGMRES"]))
     assert rel_l2(Dy, z["solgmrs.Dy"]) < TOL_SOL
     g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", names("solmfg"))
+def test_gpu_solmfg_matches_reference_fortran(name):
+    """Matrix-free flavour on the device against the reference's solmfg.f chain.
+    Tolerances: everything upstream of the finite difference at 1e-10; Au1MFG
+    (difference over eGMRES=1e-7, which amplifies round-off ~1e7 times) 1e-6;
+    eGMRES (a second difference) 1e-3; Dy 1e-5 -- the reference's own result
+    carries that much round-off noise, see the oracle test above."""
+    z, case, _ = load(name)
+    params, tables, parts, states = case
+    y, ac = z["solmfg.y_bc"], z["solmfg.ac_bc"]
+    g = gpu(case)
+    out = g.ElmMFG(y, ac)
+    assert rel_l2(out["res"], z["solmfg.elm_res"]) < TOL_ASM
+    assert rel_l2(out["rmes"], z["solmfg.elm_rmes"]) < TOL_ASM
+    assert rel_l2(out["BDiag"], z["solmfg.elm_BDiag"]) < TOL_ASM
+    for iab in (0, 1):
+        assert rel_l2(g.ItrRes(z["solmfg.itrres_in"], iab), z["solmfg.itrres_out%d" % iab]) < TOL_ASM
+    assert rel_l2(g.Au1MFG(z["solmfg.au1_in"], 1.0e-7), z["solmfg.au1_out"]) < 1e-6
+    res, Dy = g.SolMFG(y, ac, step=g.step(lhs=0, iprec=1, iter=1, istep=0), eGMRES=0.0)
+    assert (g.iKs, g.lGMRES) == (int(z["solmfg.iKs"]), int(z["solmfg.lGMRES"]))
+    assert abs(g.eGMRES - float(z["solmfg.eGMRES"])) < 1e-3 * float(z["solmfg.eGMRES"])
+    assert rel_l2(res, z["solmfg.res"]) < TOL_ASM
+    assert rel_l2(g.BDiag, z["solmfg.BDiag"]) < TOL_ASM
+    assert rel_l2(Dy, z["solmfg.Dy"]) < 1e-5
+    g.close()
