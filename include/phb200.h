@@ -225,6 +225,8 @@ int phb200_itrres(phb200_ctx *ctx, const double *yp, double *rmes, int iabres);
 /* Au1MFG (au1mfg.f:1-98) in place on u(nshg,5); setup!=0 first performs solmfg.f:97-135 (LU_Fact, forward
  * reduction of res / rmes, ypre) on the outputs of phb200_elmmfg */
 int phb200_au1mfg(phb200_ctx *ctx, double *u, double eGMRES, int setup);
+/* COMMON /itrpar/ eGMRES (common.h:217) as kept by the context: set!=0 stores *e, else reads it */
+int phb200_egmres(phb200_ctx *ctx, double *e, int set);
 /* HBM-resident variants (state from phb200_set_state) */
 int phb200_dev_elmmfg(phb200_ctx *ctx, const phb200_step *st);
 int phb200_dev_solve_mfg(phb200_ctx *ctx, const phb200_step *st, int *iKs, int *lGMRES, int *ntotGM);

@@ -540,6 +540,12 @@ extern "C" int phb200_solmfg(phb200_ctx *ctx, const double *y, const double *ac,
   *eGMRES = ctx->eGMRES;
   return 0;
 }
+// COMMON /itrpar/ eGMRES (common.h:217): set != 0 stores *e, else reads it back
+extern "C" int phb200_egmres(phb200_ctx *ctx, double *e, int set) {
+  if (!ctx || !e) return fail("egmres", "null argument");
+  if (set) ctx->eGMRES = *e; else *e = ctx->eGMRES;
+  return 0;
+}
 // HBM-resident variants for bench.py: state set by phb200_set_state
 extern "C" int phb200_dev_elmmfg(phb200_ctx *ctx, const phb200_step *st) {
   ENTER(ctx);

@@ -53,7 +53,7 @@ SYMBOLS = [
     "phb200_set_old_state", "phb200_get_state", "phb200_itrpredict", "phb200_itrbc", "phb200_itrcorrect",
     "phb200_itrupdate", "phb200_rstat", "phb200_timestep",
     "phb200_solmfg", "phb200_elmmfg", "phb200_itrres", "phb200_au1mfg", "phb200_dev_elmmfg",
-    "phb200_dev_solve_mfg", "phb200_dev_au1mfg",
+    "phb200_dev_solve_mfg", "phb200_dev_au1mfg", "phb200_egmres",
 ]
 
 _LIB = None

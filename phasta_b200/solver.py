@@ -241,10 +241,10 @@ class PhastaGPU:
         res, Dy = self._vec(), self._vec()
         BD = np.zeros((self.part.nshg, 5, 5), order="F")
         iKs, lG, ntot = C.c_int(0), C.c_int(0), C.c_int(self.ntotGM)
-        eG = C.c_double(getattr(self, "eGMRES", 0.0) if eGMRES is None else eGMRES)
+        eG = C.c_double(self.eGMRES if eGMRES is None else eGMRES)
         _chk(self.L.phb200_solmfg(self.ctx, _p(y), _p(ac), C.byref(st), _p(res), _p(BD), _p(Dy), _p(self.HBrg),
                                   C.byref(iKs), C.byref(lG), C.byref(ntot), C.byref(eG)), "solmfg")
-        self.iKs, self.lGMRES, self.ntotGM, self.eGMRES, self.BDiag = iKs.value, lG.value, ntot.value, eG.value, BD
+        self.iKs, self.lGMRES, self.ntotGM, self.BDiag = iKs.value, lG.value, ntot.value, BD
         return res, Dy
 
     def dev_elmmfg(self, step=None):
@@ -257,6 +257,17 @@ class PhastaGPU:
         _chk(self.L.phb200_dev_solve_mfg(self.ctx, C.byref(st), C.byref(iKs), C.byref(lG), C.byref(ntot)),
              "dev_solve_mfg")
         self.iKs, self.lGMRES, self.ntotGM = iKs.value, lG.value, ntot.value
+
+    @property
+    def eGMRES(self):
+        e = C.c_double(0)
+        _chk(self.L.phb200_egmres(self.ctx, C.byref(e), 0), "egmres")
+        return e.value
+
+    @eGMRES.setter
+    def eGMRES(self, v):
+        e = C.c_double(v)
+        _chk(self.L.phb200_egmres(self.ctx, C.byref(e), 1), "egmres")
 
     def dev_au1mfg(self, slot=0):
         _chk(self.L.phb200_dev_au1mfg(self.ctx, int(slot)), "dev_au1mfg")
