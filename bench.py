@@ -43,6 +43,8 @@ WORKLOADS = {
     # BASELINE.json configs[2] shape at single-GPU size: flat-plate box, 4 wedge layers at each wall, tets above
     "c3_plate_mixed_4M": (128, 64, 82, "mixed", 4),
     "hex_1M": (128, 96, 82, "hex", 0),
+    # north_star's single-GPU target size: 256x128x163 hexes x 6 = 32 047 104 tets (EGmass 102.6 GB in HBM)
+    "c5_tet_32M": (256, 128, 163),
 }
 
 
@@ -320,6 +322,8 @@ def main():
     ap.add_argument("--workload", default="c2_channel_4M", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-solve", action="store_true", help="skip the Ap / SolGMRe legs (profiling runs)")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the block-CSR (SolGMRs) leg")
+    ap.add_argument("--no-mfg", action="store_true", help="skip the matrix-free (SolMFG) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -456,7 +460,7 @@ def main():
                         "krylov_its_per_s": its[-1] / (np.mean(solve_ms) * 1e-3), "etol": params.etol},
         }
 
-    if not args.no_solve:
+    if not args.no_solve and not args.no_sparse:
         # ------------------------------------------------ block-CSR flavour (SolGMRs)
         t0 = time.perf_counter()
         _, _, nnz_tot = g.genadj()
@@ -507,7 +511,7 @@ def main():
                                   "algorithmic_bytes": csr_bytes}}
 
     # ------------------------------------------------ matrix-free flavour (SolMFG): no stored LHS at all
-    if not args.no_solve:
+    if not args.no_solve and not args.no_mfg:
         try:
             extra["mfg"] = bench_mfg(args, init_comm, part, params, tables, y, ac, local_rank, world, barrier,
                                      maxrank, numel_total)
@@ -555,9 +559,10 @@ def main():
                 "flop_per_element": FLOP_PER_ELEM_LHS, "kernel_ms": kern_ms, "asiq_kernel_ms": asiq_ms,
                 "hbm_GBps_algorithmic": elem_per_launch * BYTES_PER_ELEM_LHS / (kern_ms * 1e-3) / 1e9,
                 "hbm_peak_GBps": hbm, "hbm_peak_source": src}
-        if extra:
+        if "sparse" in extra:
             rs = extra["sparse"]["roofline_sparseap"]
             rs["peak"], rs["frac"], rs["peak_source"] = hbm, rs["achieved"] / hbm, src
+        if extra:
             gbs = elem_per_launch * BYTES_PER_ELEM_AP / (extra["ap"]["kernel_ms"] * 1e-3) / 1e9
             extra["roofline_ap"] = {"bound": "hbm", "kernel": "k_ap_ebe_tet", "achieved": gbs, "peak": hbm,
                                     "unit": "GB/s", "frac": gbs / hbm,

@@ -103,7 +103,9 @@ def _blocks(groups, ibksiz, ipord=1):
         n = ien1.shape[0]
         for a in range(0, n, ibksiz):
             b = min(a + ibksiz, n)
-            cols.append([first + a, 0, lcsyst, ipord, nenl, nfacel, 0, NDOF, 0, nshl])
+            # rows 6 and 9 as genblkPosix.f:66-69 leaves them: nfacel is never assigned on the read path
+            # (COMMON /elmpar/ stays 0), nsymdl = nsymdf = ndof(ndof+1)/2 (readnblk.f:175)
+            cols.append([first + a, 0, lcsyst, ipord, nenl, 0, 0, NDOF, NDOF * (NDOF + 1) // 2, nshl])
             mien.append(np.asfortranarray(ien1[a:b], dtype=np.int32))
         first += n
     cols.append([first, 0, 0, 0, 0, 0, 0, 0, 0, 0])
