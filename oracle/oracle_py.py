@@ -42,6 +42,25 @@ class OrcPart(C.Structure):
     _fields_ = [("c", OrcCommon)] + [(n, C.c_void_p) for n in _PTRS]
 
 
+class OrcIncomp(C.Structure):
+    """oracle_incomp.h orc_incomp"""
+    _fields_ = [*[(n, C.c_int) for n in ("iconvflow", "itau", "idiff", "ipord", "lhs", "matflg5")],
+                ("rho", C.c_double), ("rmu", C.c_double), ("bf", C.c_double * 3),
+                *[(n, C.c_double) for n in ("flmpl", "flmpr", "Delt", "Dtgl", "almi", "alfi", "gami",
+                                            "dtsfct", "taucfct")]]
+
+    @classmethod
+    def from_params(cls, ip):
+        s = cls()
+        for n in ("iconvflow", "itau", "idiff", "ipord", "lhs", "matflg5"):
+            setattr(s, n, int(getattr(ip, n)))
+        for n in ("rho", "rmu", "flmpl", "flmpr", "Delt", "Dtgl", "almi", "alfi", "gami", "dtsfct", "taucfct"):
+            setattr(s, n, float(getattr(ip, n)))
+        for i in range(3):
+            s.bf[i] = float(ip.bf[i])
+        return s
+
+
 def build(force=False):
     so = os.path.join(_HERE, "libphasta_oracle.so")
     srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
@@ -79,6 +98,7 @@ def lib():
         assert _LIB.orc_sizeof_part() == C.sizeof(OrcPart), "orc_part layout mismatch"
         assert _LIB.orc_sizeof_common() == C.sizeof(OrcCommon)
         _LIB.orc_sumgat.restype = C.c_double
+        assert _LIB.orc_sizeof_incomp() == C.sizeof(OrcIncomp)
     return _LIB
 
 
@@ -242,6 +262,48 @@ class Oracle:
                            _ptr(self.Rcos), _ptr(self.Rsin), C.byref(iKs), C.byref(lG),
                            C.byref(self.ntotGM))
         return iKs.value, lG.value
+
+    # ---- incompressible assembly + lesSparse products (oracle_incomp.c) -----
+    def IncElmGMR(self, ip, want_ebe=False):
+        """incompressible ElmGMR on every part (genadj first): sets p.res4 (nshg,4), p.lhsK9 (9,nnz_tot),
+        p.lhsP4 (4,nnz_tot) and, if asked, p.xKebe (numel,9,nshape,nshape) / p.xGoC (numel,4,..)."""
+        s = OrcIncomp.from_params(ip)
+        for p in self.parts:
+            ntot = p.rowp.size
+            nsm = self.arr[0].c.nshape
+            p.res4 = np.zeros((p.mp.nshg, 4), order="F")
+            p.lhsK9 = np.zeros((9, ntot), order="F")
+            p.lhsP4 = np.zeros((4, ntot), order="F")
+            if want_ebe:
+                p.xKebe = np.zeros((p.mp.numel, 9, nsm, nsm), order="F")
+                p.xGoC = np.zeros((p.mp.numel, 4, nsm, nsm), order="F")
+        ebe = (self._vecs([p.xKebe for p in self.parts]), self._vecs([p.xGoC for p in self.parts])) \
+            if want_ebe else (None, None)
+        self.L.orc_inc_elmgmr(self.n, self.arr, C.byref(s), self._vecs([p.res4 for p in self.parts]),
+                              self._vecs([p.lhsK9 for p in self.parts]), self._vecs([p.lhsP4 for p in self.parts]),
+                              ebe[0], ebe[1])
+
+    def LesAp(self, kind, pvec, part=0):
+        """fLesSparseAp{G,KG,NGt,NGtC,Full} (lesSparse.f:204-492) on one part's lhsK9/lhsP4."""
+        p = self.parts[part]
+        n = p.mp.nshg
+        v = np.asfortranarray(pvec, dtype=np.float64)
+        col, row = _ptr(p.colm), _ptr(p.rowp)
+        if kind == "G":
+            q = np.zeros((n, 3), order="F")
+            self.L.orc_les_apg(n, col, row, _ptr(p.lhsP4), _ptr(v), _ptr(q))
+        elif kind == "KG":
+            q = np.zeros((n, 3), order="F")
+            self.L.orc_les_apkg(n, col, row, _ptr(p.lhsK9), _ptr(p.lhsP4), _ptr(v), _ptr(q))
+        elif kind in ("NGt", "NGtC"):
+            q = np.zeros(n)
+            self.L.orc_les_apngt(n, col, row, _ptr(p.lhsP4), _ptr(v), _ptr(q), int(kind == "NGtC"))
+        elif kind == "Full":
+            q = np.zeros((n, 4), order="F")
+            self.L.orc_les_apfull(n, col, row, _ptr(p.lhsK9), _ptr(p.lhsP4), _ptr(v), _ptr(q))
+        else:
+            raise ValueError(kind)
+        return q
 
     # ---- Newton / time-step shell (oracle_step.c) --------------------------
     def _state(self):

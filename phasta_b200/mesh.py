@@ -286,7 +286,7 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
         iBC = np.zeros(nn, dtype=np.int32)
         BC = np.zeros((nn, NDOFBC), order="F")
         iper = np.arange(1, nn + 1, dtype=np.int32)
-        if bc in ("channel", "mixed"):
+        if bc in ("channel", "mixed", "allcodes"):
             inflow = I == 0
             outflow = I == nx
             wall = (J == 0) | (J == ny)
@@ -303,6 +303,20 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
                 slave = K == nz
                 iBC[slave] |= (1 << 10)
                 iper[slave] = lid(I[slave], J[slave], 0) + 1
+        if bc == "allcodes":
+            # every interior node carries a code: velocity codes 1..7 round-robin in the GLOBAL node id,
+            # density / pressure+temperature on the eighth; random slopes (small meshes still see every
+            # branch of bc3LHS / bc3Res / bc3BDg / itrBC)
+            interior = (I > 0) & (I < nx) & (J > 0) & (J < ny) & (K > 0) & (K < nz)
+            h = gnode % 9
+            for code in range(1, 8):
+                iBC[interior & (h == code)] |= (code << 3)
+            iBC[interior & (h == 0)] |= 1
+            iBC[interior & (h == 8)] |= (1 << 2) | (1 << 1)
+            r = np.random.default_rng(seed + 11)
+            slopes = r.uniform(-0.5, 0.5, size=((nx + 1) * nyp * nzp, NDOFBC))
+            BC[:, :] = slopes[gnode]
+            BC[:, 0] = 1.1 + 0.1 * slopes[gnode, 0]
         if bc == "mixed":
             # sprinkle the remaining velocity codes / density BC on interior
             # nodes, deterministic in the GLOBAL node id
@@ -355,7 +369,7 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
                 planes.append(I == 0)
             if i1 == nx:
                 planes.append(I == nx)
-            if not (periodic_z and bc in ("channel", "mixed")):
+            if not (periodic_z and bc in ("channel", "mixed", "allcodes")):
                 planes += [K == 0, K == nz]
             lcb, ienb, ibcb, bcb = _boundary_elements(ien0, x, planes, gnode, ibksiz, natural, seed)
             if lcb is not None:

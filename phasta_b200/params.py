@@ -62,3 +62,43 @@ class SolverParams:
 
     def as_dict(self):
         return asdict(self)
+
+
+@dataclass
+class IncompParams:
+    """The COMMON scalars the incompressible assembly reads beyond SolverParams
+    (incompressible/e3ivar.f, e3stab.f, e3res.f, e3lhs.f; defaults common/input.config:
+    Flow Advection Form: Convective -> iconvflow=2 (:227, input_fform.cc:650-653),
+    Tau Matrix: Diagonal-Shakib -> itau=0 (:233), viscous correction -> idiff=1 (:248),
+    lumped mass fractions 0 (:250-251)); water-like defaults rho=1, mu=1e-3."""
+    iconvflow: int = 2
+    itau: int = 0
+    idiff: int = 1
+    ipord: int = 1
+    lhs: int = 1
+    matflg5: int = 0              # matflg(5,1): 0 none, 1 constant body force datmat(1:3,5,1)
+    rho: float = 1.0              # datmat(1,1,1)
+    rmu: float = 1.0e-3           # datmat(1,2,1)
+    bf: tuple = (0.0, 0.0, 0.0)
+    flmpl: float = 0.0
+    flmpr: float = 0.0
+    Delt: float = 1.0e-2          # Delt(itseq); Dtgl = 1/Delt (itrdrv.f)
+    almi: float = 1.0
+    alfi: float = 1.0
+    gami: float = 1.0
+    dtsfct: float = 1.0
+    taucfct: float = 1.0
+
+    @property
+    def Dtgl(self):
+        return 1.0 / self.Delt
+
+    def with_rhoinf(self, rhoinf):
+        """generalized-alpha scalars of itrPC.f:18-26 (itrSetup)"""
+        if 0.0 <= rhoinf <= 1.0:
+            self.almi = (3.0 - rhoinf) / (1.0 + rhoinf) / 2.0
+            self.alfi = 1.0 / (1.0 + rhoinf)
+            self.gami = 0.5 + self.almi - self.alfi
+        else:
+            self.almi = self.alfi = self.gami = 1.0
+        return self

@@ -823,6 +823,25 @@ class Program:
             attrs = toks[j:k]
             ent = toks[k + 1:]
             alloc = any(t == ("id", "allocatable") or t == ("id", "pointer") for t in attrs)
+            if ("id", "dimension") in attrs:
+                # F90 attribute form `double precision, dimension(npro,nsd) :: a, b`: give the shape to
+                # every entity that does not carry its own
+                a0 = attrs.index(("id", "dimension")) + 1
+                depth, a1 = 0, a0
+                for a1 in range(a0, len(attrs)):
+                    if attrs[a1] == ("op", "("):
+                        depth += 1
+                    elif attrs[a1] == ("op", ")"):
+                        depth -= 1
+                        if depth == 0:
+                            break
+                shape = attrs[a0:a1 + 1]
+                out = []
+                for e in _split_top(ent):
+                    if out:
+                        out.append(("op", ","))
+                    out += e if ("op", "(") in e else e + shape
+                ent = out
             return (typ + ("+alloc" if alloc else "")), ent
         # real*8 x / character*8 code / character(8) x / integer*8
         if j < len(toks) and toks[j] == ("op", "*"):
@@ -869,7 +888,7 @@ class Program:
                     continue
                 head = toks[0][1]
                 h2 = toks[1][1] if len(toks) > 1 else ""
-                key = head + h2 if head == "end" and h2 in ("do", "if", "where") else head
+                key = head + h2 if head == "end" and h2 in ("do", "if", "where", "select") else head
                 if head == "else" and h2 == "if":
                     key = "elseif"
                 if key in terminators:
@@ -975,6 +994,28 @@ class Program:
                 return with_label(("if", branches, else_block, where))
             inner = self._parse_stmt(unit, rest, text, no, parse_block, pos, decl, None)
             return with_label(("if", [(cond, [inner] if inner is not None else [])], None, where))
+        if head == "select":
+            # SELECT CASE (expr) / CASE (v1, v2) / CASE DEFAULT / END SELECT  ->  an IF chain
+            sel = toks[2:]          # "( expr )"
+            _, term, ttoks, _ = parse_block(("case", "endselect"))
+            branches, else_block = [], None
+            while term == "case":
+                pos[0] += 1
+                if len(ttoks) > 1 and ttoks[1] == ("id", "default"):
+                    else_block, term, ttoks, _ = parse_block(("case", "endselect"))
+                    continue
+                ct = []
+                for v in _split_top(ttoks[2:-1]):
+                    if ct:
+                        ct.append(("op", ".or."))
+                    ct += sel + [("op", ".eq."), ("op", "(")] + v + [("op", ")")]
+                cond = compile_expr(parse_expr_tokens(ct))
+                block, term, ttoks, _ = parse_block(("case", "endselect"))
+                branches.append((cond, block))
+            if term != "endselect":
+                raise SyntaxError("%s: unterminated SELECT CASE" % where)
+            pos[0] += 1
+            return with_label(("if", branches, else_block, where))
         if head == "do":
             j = 1
             dolabel = None

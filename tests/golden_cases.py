@@ -9,6 +9,8 @@ CASES = {
     "tet_channel_bnd": ((3, 2, 2), dict(bc="channel", ibksiz=16, boundary=True, natural="mixed", etol=1e-6),
                         ("elmgmre", "solgmre", "solgmrs")),
     "tet_allbc": ((3, 3, 2), dict(bc="mixed", ibksiz=16, etol=1e-6), ("elmgmre", "solgmre")),
+    # every velocity code 1..7, density and pressure+temperature codes on interior nodes (bc3LHS/bc3Res/bc3BDg branches)
+    "tet_allcodes": ((4, 4, 3), dict(bc="allcodes", ibksiz=50, etol=1e-6), ("elmgmre", "solgmre", "solgmrs")),
     "tet_1pt_nodiff": ((3, 2, 2), dict(bc="channel", ibksiz=64, rule=1, idiff=0, etol=1e-6), ("elmgmre", "solgmre")),
     "tet_sutherland": ((2, 2, 2), dict(bc="channel", ibksiz=64, matflg2=1, etol=1e-6), ("elmgmre",)),
     "tet_resonly": ((3, 2, 2), dict(bc="channel", ibksiz=16, boundary=True, natural="mixed"), ("elmgmre0",)),
