@@ -52,6 +52,16 @@ typedef struct phb200_step {
   double Dtgl, almi, alfi, gami, etol;
 } phb200_step;
 
+/* Incompressible flavour (PHASTA_INCOMPRESSIBLE; BASELINE.json configs[3]): the COMMON scalars its element
+ * routines read beyond phb200_common -- /solpar/ iconvflow (input_fform.cc:650-653), /genpar/ itau idiff ipord
+ * lhs dtsfct taucfct, /matdat/ datmat(1,1,1) rho, datmat(1,2,1) mu, matflg(5,1) + datmat(1:3,5,1) constant body
+ * force, /timdat/ flmpl flmpr Delt(itseq) Dtgl almi alfi gami (common.h:184-255; incompressible/itrPC.f:18-26). */
+typedef struct phb200_incomp {
+  int iconvflow, itau, idiff, ipord, lhs, matflg5;
+  double rho, rmu, bf[3];
+  double flmpl, flmpr, Delt, Dtgl, almi, alfi, gami, dtsfct, taucfct;
+} phb200_incomp;
+
 typedef struct phb200_ctx phb200_ctx;
 
 /* One-time setup, called after genadj in itrdrv (itrdrv.f:169).  Replaces the
@@ -122,6 +132,24 @@ int phb200_dev_elmgmrs(phb200_ctx *ctx, const phb200_step *step);
 int phb200_dev_solve_sparse(phb200_ctx *ctx, const phb200_step *step, int *iKs,
                             int *lGMRESs, int *ntotGM);
 int phb200_dev_sparseap(phb200_ctx *ctx, int slot);
+
+/* ---- incompressible flavour: ElmGMR into block-CSR + the lesSparse products ----
+ * ElmGMR (incompressible/elmgmr.f:1-330 called from SolFlow, incompressible/solfar.f): AsIq/e3q + qpbc (idiff=1),
+ * AsIGMR/e3 (e3ivar, e3stab itau=0, e3Res, e3LHS), bc3LHS, fillsparseI (common/fillsparse.f:1-65), halo 'in',
+ * bc3Res.  y, ac (nshg,ndof) as for SolGMRe; res (nshg,4) {mom1,mom2,mom3,continuity}; lhsK (9,nnz_tot) with the
+ * 3x3 block entry (r,c) at 3(r-1)+c, lhsP (4,nnz_tot) = {G1,G2,G3,C}; the CSR structure is the one of
+ * phb200_set_sparse.  Output pointers may be null (the matrices stay device-resident for phb200_les_ap).
+ * Boundary-element blocks (AsBMFG/e3b of the incompressible code) are not built: refused when nelblb > 0. */
+int phb200_inc_elmgmr(phb200_ctx *ctx, const double *y, const double *ac, const phb200_incomp *ip, double *res,
+                      double *lhsK, double *lhsP);
+int phb200_inc_dev_elmgmr(phb200_ctx *ctx, const phb200_incomp *ip);
+/* fLesSparseAp{G,KG,NGt,NGtC,Full} (incompressible/lesSparse.f:204-492), the matrix-vector products the
+ * reference's Krylov solver calls back, on the device-resident lhsK/lhsP of the last phb200_inc_elmgmr:
+ * kind 0 ApG  p(n)   -> q(n,3);  1 ApKG  p(n,4) -> q(n,3);  2 ApNGt p(n,3) -> q(n);
+ *      3 ApNGtC p(n,4) -> q(n);  4 ApFull p(n,4) -> q(n,4). */
+int phb200_les_ap(phb200_ctx *ctx, int kind, const double *p, double *q);
+/* ApFull on device work vectors (Ap/s timing) */
+int phb200_inc_dev_apfull(phb200_ctx *ctx);
 
 /* Finer seams, all on host arrays: */
 /* i3LU (i3lu.f:1-181) code 0 LU_Fact / 1 forward / 2 backward / 3 product */
@@ -204,6 +232,7 @@ int phb200_flush_l2(phb200_ctx *ctx);
 const char *phb200_version(void);
 /* struct sizes, so a binding can verify its mirror of the two structs */
 int phb200_sizeof_common(void);
+int phb200_sizeof_incomp(void);
 int phb200_sizeof_step(void);
 /* test transport: several parts on ONE GPU, one host thread per part (see
  * csrc/comm.cu); stands in for phb200_comm_init on a single-GPU box */

@@ -55,6 +55,7 @@ static int upload_group(phb200_ctx *ctx, const int *lcblk, const int *const *mie
 
 extern "C" const char *phb200_version(void) { return "phb200 0.1 (sm_100a)"; }
 extern "C" int phb200_sizeof_common(void) { return (int)sizeof(phb200_common); }
+extern "C" int phb200_sizeof_incomp(void) { return (int)sizeof(phb200_incomp); }
 extern "C" int phb200_sizeof_step(void) { return (int)sizeof(phb200_step); }
 
 extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *lcblk, const int *const *mien,
@@ -208,6 +209,11 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   ctx->d_EG = nullptr;  // allocated by the first EBE lhs=1 assembly
   ctx->d_yold = ctx->d_acold = nullptr;
   ctx->d_mfg = nullptr;
+  ctx->d_res4 = ctx->d_lhsK9 = ctx->d_lhsP4 = ctx->d_lesp = ctx->d_lesq = nullptr;
+  ctx->d_tpos = nullptr;
+  ctx->have_inc_tabs = false;
+  ctx->h_shp.assign(shp, shp + (size_t)PHB200_MAXTOP * PHB200_MAXSH * PHB200_MAXQPT);
+  ctx->h_shgl.assign(shgl, shgl + (size_t)PHB200_MAXTOP * 3 * PHB200_MAXSH * PHB200_MAXQPT);
   ctx->eGMRES = 0.0;
   ctx->ifuncs = 0;
   ctx->nnz_tot = 0;
@@ -239,6 +245,7 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   phb_comm_free(ctx);
+  phb_inc_free(ctx);
   void *ptrs[] = {ctx->d_ien, ctx->d_iBC, ctx->d_BC, ctx->d_iper, ctx->d_x, ctx->d_perslave, ctx->d_halo_nodes,
                   ctx->d_slave_nodes, ctx->d_sendbuf, ctx->d_recvbuf, ctx->d_y, ctx->d_ac, ctx->d_qres,
                   ctx->d_rmass, ctx->d_res, ctx->d_rmes, ctx->d_Dy, ctx->d_temp, ctx->d_BDiag, ctx->d_BDtmp,
@@ -580,6 +587,43 @@ extern "C" int phb200_dev_sparseap(phb200_ctx *ctx, int slot) {
   PHB_CHECK(cudaMemcpyAsync(dst, src, sizeof(double) * n5, cudaMemcpyDeviceToDevice, ctx->stream));
   PHB_TRY(phb_sparseap(ctx, dst));
   return phb_bc3per(ctx, dst, 5);
+}
+
+// ---- incompressible flavour (incomp.cu) ------------------------------------
+extern "C" int phb200_inc_elmgmr(phb200_ctx *ctx, const double *y, const double *ac, const phb200_incomp *ip,
+                                 double *res, double *lhsK, double *lhsP) {
+  ENTER(ctx);
+  if (!y || !ac || !ip) return fail("inc_elmgmr", "null argument");
+  PHB_TRY(phb200_set_state(ctx, y, ac));
+  PHB_TRY(phb_inc_elmgmr(ctx, ip));
+  if (res) PHB_TRY(d2h(ctx, res, ctx->d_res4, (size_t)4 * ctx->c.nshg));
+  if (lhsK && ip->lhs == 1) PHB_TRY(d2h(ctx, lhsK, ctx->d_lhsK9, (size_t)9 * ctx->nnz_tot));
+  if (lhsP && ip->lhs == 1) PHB_TRY(d2h(ctx, lhsP, ctx->d_lhsP4, (size_t)4 * ctx->nnz_tot));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_inc_dev_elmgmr(phb200_ctx *ctx, const phb200_incomp *ip) {
+  ENTER(ctx);
+  if (!ip) return fail("inc_dev_elmgmr", "null argument");
+  return phb_inc_elmgmr(ctx, ip);
+}
+extern "C" int phb200_les_ap(phb200_ctx *ctx, int kind, const double *p, double *q) {
+  ENTER(ctx);
+  if (!p || !q) return fail("les_ap", "null argument");
+  if (kind < 0 || kind > 4) return fail("les_ap", "kind must be 0..4");
+  if (!ctx->d_lesp) return fail("les_ap", "no incompressible LHS (call phb200_inc_elmgmr first)");
+  static const int ncp[5] = {1, 4, 3, 4, 4}, ncq[5] = {3, 3, 1, 1, 4};
+  const size_t nshg = ctx->c.nshg;
+  PHB_TRY(h2d(ctx, ctx->d_lesp, p, ncp[kind] * nshg));
+  PHB_TRY(phb_les_ap(ctx, kind, ctx->d_lesp, ctx->d_lesq));
+  PHB_TRY(d2h(ctx, q, ctx->d_lesq, ncq[kind] * nshg));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+extern "C" int phb200_inc_dev_apfull(phb200_ctx *ctx) {
+  ENTER(ctx);
+  if (!ctx->d_lesp) return fail("inc_dev_apfull", "no incompressible LHS (call phb200_inc_elmgmr first)");
+  return phb_les_ap(ctx, 4, ctx->d_lesp, ctx->d_lesq);
 }
 
 // ---- finer seams on host arrays: stage through d_temp / d_BDiag ------------

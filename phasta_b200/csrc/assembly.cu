@@ -1442,6 +1442,31 @@ __global__ void k_per_copy(int n, const int *__restrict__ slaves, const int *__r
   v[(size_t)nshg * k + j] = v[(size_t)nshg * k + i];
 }
 
+// qpbc (common/qpbc.f:37-95) on the device-resident qres (12 planes; the incompressible path uses 9 and
+// keeps the rest zero) and rmass: halo 'in', periodic sum + copy, q = qres / rmass, halo 'out'
+int phb_qpbc(phb200_ctx *ctx) {
+  const int nshg = ctx->c.nshg;
+  cudaStream_t s = ctx->stream;
+  PHB_TRY(phb_commu(ctx, ctx->d_qres, 12, 0));
+  PHB_TRY(phb_commu(ctx, ctx->d_rmass, 1, 0));
+  {
+    KScope ks(ctx, KC_NODE);
+    if (ctx->n_perslave) {
+      int nb = (ctx->n_perslave + 127) / 128;
+      k_qpbc_peradd<<<nb, 128, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, ctx->d_qres,
+                                       ctx->d_rmass);
+      k_qpbc_percopy<<<nb, 128, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, ctx->d_qres,
+                                        ctx->d_rmass);
+      ctx->launches++;
+    }
+    k_qpbc_divide<<<(nshg + 255) / 256, 256, 0, s>>>(nshg, ctx->d_qres, ctx->d_rmass);
+    ctx->launches++;
+    PHB_CHECK(cudaGetLastError());
+  }
+  PHB_TRY(phb_commu(ctx, ctx->d_qres, 12, 1));
+  return 0;
+}
+
 int phb_bc3per(phb200_ctx *ctx, double *d_r, int n) {
   if (ctx->n_perslave == 0) return 0;
   KScope ks(ctx, KC_NODE);
@@ -2151,24 +2176,7 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
                                         ctx->d_qres, ctx->d_rmass);
       PHB_CHECK(cudaGetLastError());
     }
-    // qpbc (qpbc.f:37-95)
-    PHB_TRY(phb_commu(ctx, ctx->d_qres, 12, 0));
-    PHB_TRY(phb_commu(ctx, ctx->d_rmass, 1, 0));
-    {
-      KScope ks(ctx, KC_NODE);
-      if (ctx->n_perslave) {
-        int nb = (ctx->n_perslave + 127) / 128;
-        k_qpbc_peradd<<<nb, 128, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, ctx->d_qres,
-                                         ctx->d_rmass);
-        k_qpbc_percopy<<<nb, 128, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, ctx->d_qres,
-                                          ctx->d_rmass);
-        ctx->launches++;
-      }
-      k_qpbc_divide<<<(nshg + 255) / 256, 256, 0, s>>>(nshg, ctx->d_qres, ctx->d_rmass);
-      ctx->launches++;
-      PHB_CHECK(cudaGetLastError());
-    }
-    PHB_TRY(phb_commu(ctx, ctx->d_qres, 12, 1));
+    PHB_TRY(phb_qpbc(ctx));
   } else if (c.idiff != 0) {
     fprintf(stderr, "phb200: elmgmre: idiff=%d not supported (0 or 1)\n", c.idiff);
     return 1;

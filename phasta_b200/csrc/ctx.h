@@ -105,6 +105,12 @@ struct phb200_ctx {
   double *d_scratch;             // L2 flush / fp64 peak
   size_t scratch_bytes;
   bool have_lhs;                 // EGmass/BDiag hold a (preconditioned) system
+  // ---- incompressible flavour (incomp.cu): res(nshg,4), lhsK(9,nnz_tot), lhsP(4,nnz_tot), position of the
+  //      transposed CSR entry of every entry, two work vectors [4][nshg] for the lesSparse products
+  double *d_res4, *d_lhsK9, *d_lhsP4, *d_lesp, *d_lesq;
+  int *d_tpos;
+  bool have_inc_tabs;
+  std::vector<double> h_shp, h_shgl;   // host copies of shp / shgl (the incompressible kernels build their tables lazily)
   // ---- matrix-free flavour (SolMFG): ypre, two work vectors [3][5][nshg]; eGMRES of COMMON /itrpar/
   double *d_mfg;
   double eGMRES;
@@ -150,6 +156,7 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse = 0);
 int phb_alloc_eg(phb200_ctx *ctx);
 int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres);
 int phb_bc3res_vec(phb200_ctx *ctx, double *d_r);
+int phb_qpbc(phb200_ctx *ctx);
 // solver.cu
 int phb_i3lu(phb200_ctx *ctx, double *d_Diag, double *d_r, int code);
 int phb_i3pre(phb200_ctx *ctx);
@@ -175,6 +182,10 @@ int phb_itrupdate(phb200_ctx *ctx, const phb200_step *st);
 int phb_rstat(phb200_ctx *ctx, long long nshgt, double *totres);
 int phb_timestep(phb200_ctx *ctx, const phb200_step *st, int ipred, int nitr, int sparse, int LHSupd,
                  long long nshgt, int *ntotGM, double *stats);
+// incomp.cu (incompressible ElmGMR into block-CSR, lesSparse products)
+int phb_inc_elmgmr(phb200_ctx *ctx, const phb200_incomp *ip);
+int phb_les_ap(phb200_ctx *ctx, int kind, const double *d_p, double *d_q);
+void phb_inc_free(phb200_ctx *ctx);
 // sparse.cu
 int phb_genadj_host(int nshg, int nelblk, const int *lcblk, const int *const *mien, int nnz, int *colm, int *rowp,
                     int *nnz_tot);

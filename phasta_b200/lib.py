@@ -38,6 +38,25 @@ class PhbStep(C.Structure):
                 *[(n, C.c_double) for n in ("Dtgl", "almi", "alfi", "gami", "etol")]]
 
 
+class PhbIncomp(C.Structure):
+    """struct phb200_incomp."""
+    _fields_ = [*[(n, C.c_int) for n in ("iconvflow", "itau", "idiff", "ipord", "lhs", "matflg5")],
+                ("rho", C.c_double), ("rmu", C.c_double), ("bf", C.c_double * 3),
+                *[(n, C.c_double) for n in ("flmpl", "flmpr", "Delt", "Dtgl", "almi", "alfi", "gami",
+                                            "dtsfct", "taucfct")]]
+
+    @classmethod
+    def from_params(cls, ip, **over):
+        s = cls()
+        for n in ("iconvflow", "itau", "idiff", "ipord", "lhs", "matflg5"):
+            setattr(s, n, int(over.get(n, getattr(ip, n))))
+        for n in ("rho", "rmu", "flmpl", "flmpr", "Delt", "Dtgl", "almi", "alfi", "gami", "dtsfct", "taucfct"):
+            setattr(s, n, float(over.get(n, getattr(ip, n))))
+        for i in range(3):
+            s.bf[i] = float(ip.bf[i])
+        return s
+
+
 # every symbol include/phb200.h declares (tests/test_abi.py checks the .so exports them all)
 SYMBOLS = [
     "phb200_init", "phb200_finalize", "phb200_nccl_unique_id", "phb200_comm_init",
@@ -54,6 +73,7 @@ SYMBOLS = [
     "phb200_itrupdate", "phb200_rstat", "phb200_timestep",
     "phb200_solmfg", "phb200_elmmfg", "phb200_itrres", "phb200_au1mfg", "phb200_dev_elmmfg",
     "phb200_dev_solve_mfg", "phb200_dev_au1mfg", "phb200_egmres",
+    "phb200_inc_elmgmr", "phb200_inc_dev_elmgmr", "phb200_les_ap", "phb200_inc_dev_apfull", "phb200_sizeof_incomp",
 ]
 
 _LIB = None
@@ -77,7 +97,8 @@ def load():
         lib.phb200_version.restype = C.c_char_p
         lib.phb200_launch_count.restype = C.c_longlong
         lib.phb200_finalize.restype = None
-        if lib.phb200_sizeof_common() != C.sizeof(PhbCommon) or lib.phb200_sizeof_step() != C.sizeof(PhbStep):
+        if lib.phb200_sizeof_common() != C.sizeof(PhbCommon) or lib.phb200_sizeof_step() != C.sizeof(PhbStep) \
+                or lib.phb200_sizeof_incomp() != C.sizeof(PhbIncomp):
             raise RuntimeError('phb200 struct layout mismatch between include/phb200.h and lib.py')
         _LIB = lib
     return _LIB

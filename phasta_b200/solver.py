@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from . import lib as _lib
-from .lib import PhbCommon, PhbStep, MAXTOP, MAXQPT
+from .lib import PhbCommon, PhbStep, PhbIncomp, MAXTOP, MAXQPT
 from .mesh import MeshPart
 from .params import SolverParams
 
@@ -331,6 +331,41 @@ class PhastaGPU:
         self._y = np.asfortranarray(y, dtype=np.float64)
         self._ac = np.asfortranarray(ac, dtype=np.float64)
         _chk(self.L.phb200_set_state(self.ctx, _p(self._y), _p(self._ac)), "set_state")
+
+    # ---- incompressible flavour (incompressible/elmgmr.f ElmGMR, lesSparse.f) ----
+    def IncElmGMR(self, y, ac, ip, *, want_lhs=True, **over):
+        """ElmGMR(u, y, ac, x, shp, shgl, iBC, BC, shpb, shglb, res, iper, ilwork, rowp, colm, lhsK, lhsP, ...)
+        of the incompressible code (elmgmr.f:1-6): returns dict(res (nshg,4)[, lhsK (9,nnz_tot), lhsP (4,nnz_tot)]).
+        genadj / set_sparse must have been called (itrdrv does it once)."""
+        s = PhbIncomp.from_params(ip, **over)
+        y = np.asfortranarray(y, dtype=np.float64)
+        ac = np.asfortranarray(ac, dtype=np.float64)
+        out = {"res": np.zeros((self.part.nshg, 4), order="F")}
+        lhs = bool(s.lhs) and want_lhs
+        if lhs:
+            out["lhsK"] = np.zeros((9, self.nnz_tot), order="F")
+            out["lhsP"] = np.zeros((4, self.nnz_tot), order="F")
+        _chk(self.L.phb200_inc_elmgmr(self.ctx, _p(y), _p(ac), C.byref(s), _p(out["res"]),
+                                      _p(out.get("lhsK")), _p(out.get("lhsP"))), "inc_elmgmr")
+        return out
+
+    def dev_inc_elmgmr(self, ip, **over):
+        s = PhbIncomp.from_params(ip, **over)
+        _chk(self.L.phb200_inc_dev_elmgmr(self.ctx, C.byref(s)), "inc_dev_elmgmr")
+
+    def LesAp(self, kind, p):
+        """fLesSparseAp{G,KG,NGt,NGtC,Full}(col, row, kLhs, pLhs, p, q, nNodes, nnz_tot) (lesSparse.f:204-492)
+        on the device-resident lhsK/lhsP of the last IncElmGMR."""
+        k = {"G": 0, "KG": 1, "NGt": 2, "NGtC": 3, "Full": 4}[kind]
+        n = self.part.nshg
+        p = np.asfortranarray(p, dtype=np.float64)
+        shape = {0: (n, 3), 1: (n, 3), 2: (n,), 3: (n,), 4: (n, 4)}[k]
+        q = np.zeros(shape, order="F")
+        _chk(self.L.phb200_les_ap(self.ctx, k, _p(p), _p(q)), "les_ap")
+        return q
+
+    def dev_inc_apfull(self):
+        _chk(self.L.phb200_inc_dev_apfull(self.ctx), "inc_dev_apfull")
 
     # ------------------------------------- Newton / time-step shell (timestep.cu)
     def set_old_state(self, yold, acold):

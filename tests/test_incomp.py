@@ -158,3 +158,77 @@ def test_partitioned_equals_serial():
             pos += 4 + 2 * nseg
         assert rel_l2(p.res4[own], ref[p.mp.gnode[own]]) < 1e-12
         assert not p.res4[~own].any()                   # bc3per.f:28-43 zeroes the rows another part owns
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+def _gpu(case):
+    from phasta_b200.solver import PhastaGPU
+    params, tables, parts, states = case
+    g = PhastaGPU(parts[0], params, tables, device=0)
+    g.genadj()
+    return g
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(CASES))
+def test_gpu_matches_reference_fortran(name):
+    """CUDA ElmGMR / fLesSparseAp* through the C-ABI against the reference's Fortran (f77np fixtures)."""
+    z, case, ip = load(name)
+    g = _gpu(case)
+    y, ac = case[3][0]
+    out = g.IncElmGMR(y, ac, ip)
+    assert rel_l2(out["res"], z["res"]) < TOL_ASM
+    if ip.lhs:
+        assert rel_l2(out["lhsK"], z["lhsK"]) < TOL_ASM
+        assert rel_l2(out["lhsP"], z["lhsP"]) < TOL_ASM
+        # per-entry check so that one wrong block cannot hide in the norm
+        d = np.abs(out["lhsK"] - z["lhsK"]).max(axis=0)
+        s = np.abs(z["lhsK"]).max(axis=0) + 1e-300
+        assert (d / np.maximum(s, 1e-8 * s.max())).max() < 1e-8
+        pin = z["ap_in"]
+        assert rel_l2(g.LesAp("G", pin[:, 3].copy()), z["apG"]) < TOL_ASM
+        assert rel_l2(g.LesAp("KG", pin), z["apKG"]) < TOL_ASM
+        assert rel_l2(g.LesAp("NGt", pin[:, :3]), z["apNGt"]) < TOL_ASM
+        assert rel_l2(g.LesAp("NGtC", pin), z["apNGtC"]) < TOL_ASM
+        assert rel_l2(g.LesAp("Full", pin), z["apFull"]) < TOL_ASM
+    g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("topo,n", [("tet", (12, 10, 9)), ("mixed", (8, 10, 6)), ("hex", (9, 7, 6))])
+def test_gpu_matches_oracle_on_a_larger_mesh(topo, n):
+    case = make_case(*n, bc="allcodes", topo=topo, ibksiz=128)
+    ip = IncompParams(rho=1.1, rmu=2.0e-3).with_rhoinf(0.2)
+    o = make_oracle(case)
+    o.genadj()
+    o.IncElmGMR(ip)
+    p = o.parts[0]
+    g = _gpu(case)
+    y, ac = case[3][0]
+    out = g.IncElmGMR(y, ac, ip)
+    assert rel_l2(out["res"], p.res4) < TOL_ASM
+    assert rel_l2(out["lhsK"], p.lhsK9) < TOL_ASM
+    assert rel_l2(out["lhsP"], p.lhsP4) < TOL_ASM
+    v = np.random.default_rng(9).standard_normal((p.mp.nshg, 4))
+    assert rel_l2(g.LesAp("Full", v), o.LesAp("Full", v)) < TOL_ASM
+    # residual-only call leaves the resident matrices alone
+    out0 = g.IncElmGMR(y, ac, ip, lhs=0)
+    assert rel_l2(out0["res"], p.res4) < TOL_ASM
+    assert rel_l2(g.LesAp("Full", v), o.LesAp("Full", v)) < TOL_ASM
+    g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_refuses_what_is_not_built():
+    from phasta_b200.solver import PhastaError
+    case = make_case(4, 3, 3, bc="channel")
+    g = _gpu(case)
+    y, ac = case[3][0]
+    with pytest.raises(PhastaError):
+        g.IncElmGMR(y, ac, IncompParams(itau=1))
+    g.close()
+    caseb = make_case(4, 3, 3, bc="channel", boundary=True, natural="all")
+    g = _gpu(caseb)
+    with pytest.raises(PhastaError):
+        g.IncElmGMR(y, ac, IncompParams())
+    g.close()
