@@ -45,6 +45,8 @@ WORKLOADS = {
     "hex_1M": (128, 96, 82, "hex", 0),
     # north_star's single-GPU target size: 256x128x163 hexes x 6 = 32 047 104 tets (EGmass 102.6 GB in HBM)
     "c5_tet_32M": (256, 128, 163),
+    # BASELINE.json configs[3] size: incompressible channel, 256x128x82 hexes x 6 = 16 121 856 tets
+    "c4_incomp_16M": (256, 128, 82),
 }
 
 
@@ -290,6 +292,62 @@ def bench_mfg(args, init_comm, part, params, tables, y, ac, local_rank, world, b
     return out
 
 
+def bench_incomp(args, g, part, barrier, maxrank, numel_total, hbm):
+    """Incompressible flavour (BASELINE.json configs[3]) on the same mesh and CSR structure: ElmGMR into
+    lhsK(9,nnz)/lhsP(4,nnz) (AsIq + qpbc + AsIGMR/e3 + bc3LHS + fillsparseI + bc3Res) and fLesSparseApFull."""
+    from phasta_b200 import IncompParams
+    ip = IncompParams()
+    if not getattr(g, "nnz_tot", 0):
+        g.genadj()
+    for _ in range(2):
+        g.dev_inc_elmgmr(ip)
+    barrier()
+    g.event(10)
+    for _ in range(args.steps):
+        g.dev_inc_elmgmr(ip)
+    g.event(11)
+    barrier()
+    asm_ms = maxrank(g.elapsed_ms(10, 11)) / args.steps
+    g.profile(True)
+    g.profile_reset()
+    for _ in range(2):
+        g.dev_inc_elmgmr(ip)
+    pk = g.profile_get()
+    g.profile(False)
+    g.event(12)
+    for _ in range(args.steps):
+        g.dev_inc_elmgmr(ip, lhs=0)
+    g.event(13)
+    barrier()
+    res_ms = maxrank(g.elapsed_ms(12, 13)) / args.steps
+    g.dev_inc_elmgmr(ip)
+    nap = max(20, args.steps)
+    for _ in range(3):
+        g.dev_inc_apfull()
+    barrier()
+    g.event(14)
+    for _ in range(nap):
+        g.dev_inc_apfull()
+    g.event(15)
+    barrier()
+    ap_ms = maxrank(g.elapsed_ms(14, 15)) / nap
+    nnz = g.nnz_tot
+    # algorithmic traffic: per CSR entry kLhs 72 B + pLhs 32 B + column id 4 B; per node p, q (4 doubles each) + row ptr
+    ap_bytes = nnz * 108.0 + part.nshg * 68.0
+    # assembly: 16 blocks x 13 doubles written per tet + 19 doubles gathered per node (x, Y, Y,t, q) + eloc + ien
+    asm_bytes = part.numel * (16 * 13 * 8 + 16 * 4 + 16) + part.nshg * (19 * 8)
+    gbs = ap_bytes / (ap_ms * 1e-3) / 1e9
+    return {"workload": "incompressible ElmGMR (lhs=1, idiff=1, convective form, itau=0) + fLesSparseApFull",
+            "elements_assembled_per_s": numel_total / (asm_ms * 1e-3), "assembly_ms": asm_ms,
+            "assembly_kernel_ms": pk["assembly"][0] / 2, "asiq_kernel_ms": pk["asiq"][0] / 2,
+            "node_halo_ms": (pk["node"][0] + pk["halo"][0]) / 2,
+            "residual_only_ms": res_ms, "nnz_tot_per_gpu": int(nnz),
+            "assembly_GBps_algorithmic": asm_bytes / (pk["assembly"][0] / 2 * 1e-3) / 1e9,
+            "apfull_per_s": 1e3 / ap_ms, "apfull_ms": ap_ms,
+            "roofline_apfull": {"bound": "hbm", "kernel": "k_les_ap<15>", "unit": "GB/s", "achieved": gbs,
+                                "algorithmic_bytes": ap_bytes, "peak": hbm, "frac": gbs / hbm}}
+
+
 _STDOUT_FD = None
 
 
@@ -324,6 +382,7 @@ def main():
     ap.add_argument("--no-solve", action="store_true", help="skip the Ap / SolGMRe legs (profiling runs)")
     ap.add_argument("--no-sparse", action="store_true", help="skip the block-CSR (SolGMRs) leg")
     ap.add_argument("--no-mfg", action="store_true", help="skip the matrix-free (SolMFG) leg")
+    ap.add_argument("--no-incomp", action="store_true", help="skip the incompressible (ElmGMR + ApFull) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -509,6 +568,13 @@ def main():
             "roofline_sparseap": {"bound": "hbm", "kernel": "k_sparseap", "unit": "GB/s",
                                   "achieved": csr_bytes / (sap_k_ms * 1e-3) / 1e9,
                                   "algorithmic_bytes": csr_bytes}}
+
+    # ------------------------------------------------ incompressible flavour on the same mesh / CSR structure
+    if not args.no_solve and not args.no_incomp:
+        try:
+            extra["incomp"] = bench_incomp(args, g, part, barrier, maxrank, numel_total, peaks()[0])
+        except Exception as e:
+            extra["incomp"] = {"error": repr(e)}
 
     # ------------------------------------------------ matrix-free flavour (SolMFG): no stored LHS at all
     if not args.no_solve and not args.no_mfg:

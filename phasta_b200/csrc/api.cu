@@ -209,7 +209,7 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   ctx->d_EG = nullptr;  // allocated by the first EBE lhs=1 assembly
   ctx->d_yold = ctx->d_acold = nullptr;
   ctx->d_mfg = nullptr;
-  ctx->d_res4 = ctx->d_lhsK9 = ctx->d_lhsP4 = ctx->d_lesp = ctx->d_lesq = nullptr;
+  ctx->d_res4 = ctx->d_lhsK9 = ctx->d_lhsP4 = ctx->d_lesp = ctx->d_lesq = ctx->d_lesp4 = nullptr;
   ctx->d_tpos = nullptr;
   ctx->have_inc_tabs = false;
   ctx->h_shp.assign(shp, shp + (size_t)PHB200_MAXTOP * PHB200_MAXSH * PHB200_MAXQPT);

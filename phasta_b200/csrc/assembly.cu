@@ -1442,6 +1442,16 @@ __global__ void k_per_copy(int n, const int *__restrict__ slaves, const int *__r
   v[(size_t)nshg * k + j] = v[(size_t)nshg * k + i];
 }
 
+// node records [nshg][26] = x(3), Y{p,u1,u2,u3,T}(5), Y,t(5), q(12) from the resident x / y / ac / qres
+int phb_pack_nodes(phb200_ctx *ctx, int with_q) {
+  KScope ks(ctx, KC_NODE);
+  const size_t tot = (size_t)ctx->c.nshg * NREC;
+  k_pack_nodes<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->c.nshg, ctx->c.numnp, ctx->d_x, ctx->d_y,
+                                                                       ctx->d_ac, ctx->d_qres, with_q, ctx->d_nodeaos);
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // qpbc (common/qpbc.f:37-95) on the device-resident qres (12 planes; the incompressible path uses 9 and
 // keeps the rest zero) and rmass: halo 'in', periodic sum + copy, q = qres / rmass, halo 'out'
 int phb_qpbc(phb200_ctx *ctx) {

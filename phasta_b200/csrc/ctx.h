@@ -107,9 +107,10 @@ struct phb200_ctx {
   bool have_lhs;                 // EGmass/BDiag hold a (preconditioned) system
   // ---- incompressible flavour (incomp.cu): res(nshg,4), lhsK(9,nnz_tot), lhsP(4,nnz_tot), position of the
   //      transposed CSR entry of every entry, two work vectors [4][nshg] for the lesSparse products
-  double *d_res4, *d_lhsK9, *d_lhsP4, *d_lesp, *d_lesq;
+  double *d_res4, *d_lhsK9, *d_lhsP4, *d_lesp, *d_lesq, *d_lesp4;
   int *d_tpos;
   bool have_inc_tabs;
+  int inc_idiff;
   std::vector<double> h_shp, h_shgl;   // host copies of shp / shgl (the incompressible kernels build their tables lazily)
   // ---- matrix-free flavour (SolMFG): ypre, two work vectors [3][5][nshg]; eGMRES of COMMON /itrpar/
   double *d_mfg;
@@ -157,6 +158,7 @@ int phb_alloc_eg(phb200_ctx *ctx);
 int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres);
 int phb_bc3res_vec(phb200_ctx *ctx, double *d_r);
 int phb_qpbc(phb200_ctx *ctx);
+int phb_pack_nodes(phb200_ctx *ctx, int with_q);
 // solver.cu
 int phb_i3lu(phb200_ctx *ctx, double *d_Diag, double *d_r, int code);
 int phb_i3pre(phb200_ctx *ctx);

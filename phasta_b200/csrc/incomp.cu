@@ -560,6 +560,287 @@ __global__ void __launch_bounds__(128) k_inc_asigmr(int tab, int numel, size_t n
   }
 }
 
+// ---------------------------------------------------------------------------
+// Linear tets: N_a,i, the metric tensor, grad Y and div q are constant over the element, so the point loop only
+// interpolates u, Y,t, p and evaluates tau; the tangent needs no point loop at all once a handful of point sums
+// are kept (e3lhs.f with constant N_a,i):
+//   K_ij(a,b) = d_ij [ M_ab + UB_a . g_b + mu~ g_a.g_b + g_a^T UU g_b + g_a^T RR g_b ] + tauC~ g_b,i g_a,j + mu~ g_b,j g_a,i
+//   G_i(a,b)  = TL_a g_b,i        C(a,b) = tauMr~ g_a.g_b
+// with M_ab = sum_q tsFct N_a N_b, UB_a = sum_q rho tlW ubar N_a, TL_a = sum_q tlW N_a, UU = sum_q tlW tauM rho u u^T,
+// RR = sum_q tlW tauBar r r^T, x~ = sum_q tlW x.  Node data comes from the 208-byte node records (13 16-byte loads
+// per node); the 13 entries of every block go through a per-warp shared tile so that one reduction instruction
+// covers whole CSR blocks (4 L2 sectors each) instead of one double of 32 different blocks.
+#define INC_NREC 26
+template <int NQ, bool LHS>
+__global__ void __launch_bounds__(128) k_inc_asigmr_tet(int numel, size_t numel_pad, int nshg,
+                                                         const int *__restrict__ ien, const double *__restrict__ aos,
+                                                         const int *__restrict__ iBC, const double *__restrict__ BC,
+                                                         const int *__restrict__ eloc, double *__restrict__ res,
+                                                         double *__restrict__ lhsK, double *__restrict__ lhsP) {
+  __shared__ double stage_all[LHS ? 4 * 32 * 13 : 1];
+  const int e0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = e0 < numel;
+  const int e = valid ? e0 : numel - 1;
+  const int lane = threadIdx.x & 31;
+  const IncTab &T = c_it[0];
+  const double rho = c_ip.rho, rmu = c_ip.rmu;
+  const int iconv = c_ip.iconvflow;
+  int nd[4];
+  double xl[4][3], yl[4][4], al[4][3], ql[4][9];
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    const int A = ien[(size_t)a * numel_pad + e];
+    nd[a] = A;
+    const double2 *rec = reinterpret_cast<const double2 *>(aos + (size_t)A * INC_NREC);
+    double v[INC_NREC];
+#pragma unroll
+    for (int k = 0; k < 11; k++) {  // x(3) Y(5) Y,t(5) q(9) = 22 doubles
+      const double2 t = __ldg(rec + k);
+      v[2 * k] = t.x;
+      v[2 * k + 1] = t.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) xl[a][i] = v[i];
+#pragma unroll
+    for (int m = 0; m < 4; m++) yl[a][m] = v[3 + m];
+#pragma unroll
+    for (int i = 0; i < 3; i++) al[a][i] = v[9 + i];
+#pragma unroll
+    for (int k = 0; k < 9; k++) ql[a][k] = v[13 + k];
+  }
+  double shg[4][3], dxidx[3][3], W1;
+  inc_metric<4>(xl, T.dN[0], 1.0, shg, dxidx, W1);
+  double g[3][4];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int m = 0; m < 4; m++) g[i][m] = shg[0][i] * yl[0][m] + shg[1][i] * yl[1][m] + shg[2][i] * yl[2][m] + shg[3][i] * yl[3][m];
+  double divq[3] = {0.0, 0.0, 0.0};
+  if (c_ip.idiff >= 1) {
+#pragma unroll
+    for (int n = 0; n < 4; n++)
+#pragma unroll
+      for (int m = 0; m < 3; m++) divq[m] = divq[m] + shg[n][0] * ql[n][m] + shg[n][1] * ql[n][3 + m] + shg[n][2] * ql[n][6 + m];
+  }
+  double gd[6];
+  inc_gijd<true>(dxidx, gd);
+  const double trg = gd[0] + gd[1] + gd[2];
+  const double rhoinv = 1.0 / rho, rnu = rmu * rhoinv, dts = c_ip.dts;
+  const double visc2 = 36.0 * (rnu * rnu) *
+                       (gd[0] * gd[0] + gd[1] * gd[1] + gd[2] * gd[2] + 2.0 * (gd[3] * gd[3] + gd[4] * gd[4] + gd[5] * gd[5]));
+  double src[3] = {0.0, 0.0, 0.0};
+  if (c_ip.matflg5 == 1) { src[0] = c_ip.bf[0]; src[1] = c_ip.bf[1]; src[2] = c_ip.bf[2]; }
+  const double divu = g[0][1] + g[1][2] + g[2][3];
+  const double s12 = rmu * (g[1][1] + g[0][2]), s23 = rmu * (g[2][2] + g[1][3]), s13 = rmu * (g[0][3] + g[2][1]);
+  double rl[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int m = 0; m < 4; m++) rl[a][m] = 0.0;
+  // point sums for the tangent
+  double UB[4][3], UU[6], RR[6], sC = 0.0, sMr = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) { UU[k] = 0.0; RR[k] = 0.0; }
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) UB[a][i] = 0.0;
+#pragma unroll 1
+  for (int q = 0; q < NQ; q++) {
+    const double W = T.Qwt[q] * W1;
+    double pres = 0.0, u[3] = {0.0, 0.0, 0.0}, aci[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+      const double Nn = T.N[q][n];
+      pres += Nn * yl[n][0];
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        u[i] += Nn * yl[n][1 + i];
+        aci[i] += Nn * al[n][i];
+      }
+    }
+    double r[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+      r[m] = (aci[m] + u[0] * g[0][1 + m] + u[1] * g[1][1 + m] + u[2] * g[2][1 + m] - src[m]) * rho + g[m][0] - divq[m];
+    if (iconv == 1) {
+#pragma unroll
+      for (int m = 0; m < 3; m++) r[m] = r[m] + u[m] * (divu * rho);
+    }
+    double tauM = ((2.0 * dts) * (2.0 * dts) +
+                   (u[0] * (gd[0] * u[0] + gd[3] * u[1] + gd[5] * u[2]) + u[1] * (gd[3] * u[0] + gd[1] * u[1] + gd[4] * u[2]) +
+                    u[2] * (gd[5] * u[0] + gd[4] * u[1] + gd[2] * u[2]))) + visc2;
+    const double fact = sqrt(tauM);
+    const double tauC = rho * 0.125 * fact / trg * c_ip.ff;
+    tauM = 1.0 / fact;
+    double tauBar = r[0] * (gd[0] * r[0] + gd[3] * r[1] + gd[5] * r[2]) + r[1] * (gd[3] * r[0] + gd[1] * r[1] + gd[4] * r[2]) +
+                    r[2] * (gd[5] * r[0] + gd[4] * r[1] + gd[2] * r[2]);
+    if (tauBar != 0.0) tauBar = tauM * rsqrt(tauBar);
+    double uBar[3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) uBar[m] = u[m] - tauM * r[m] * rhoinv;
+    double rNa[3], rG[3][3];
+#pragma unroll
+    for (int m = 0; m < 3; m++) rNa[m] = aci[m] * c_ip.tmps - src[m];
+    const double tmp = -pres + tauC * divu;
+    rG[0][0] = 2.0 * rmu * g[0][1] + tmp; rG[0][1] = s12; rG[0][2] = s13;
+    rG[1][0] = s12; rG[1][1] = 2.0 * rmu * g[1][2] + tmp; rG[1][2] = s23;
+    rG[2][0] = s13; rG[2][1] = s23; rG[2][2] = 2.0 * rmu * g[2][3] + tmp;
+    if (iconv == 2) {
+#pragma unroll
+      for (int m = 0; m < 3; m++) rNa[m] = rNa[m] + uBar[0] * g[0][1 + m] + uBar[1] * g[1][1 + m] + uBar[2] * g[2][1 + m];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) rG[i][j] = rG[i][j] - u[i] * u[j] * rho;
+    }
+    {
+      double t[3] = {tauM * r[0], tauM * r[1], tauM * r[2]};
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) rG[i][j] = rG[i][j] + t[i] * u[j];
+      if (iconv == 1) {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) rG[i][j] = rG[i][j] + t[j] * u[i];
+      } else {
+#pragma unroll
+        for (int m = 0; m < 3; m++) t[m] = tauBar * (r[0] * g[0][1 + m] + r[1] * g[1][1 + m] + r[2] * g[2][1 + m]);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+          for (int j = 0; j < 3; j++) rG[i][j] = rG[i][j] + t[i] * r[j];
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 3; m++) rNa[m] = rNa[m] * rho;
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const double Na = T.N[q][a];
+      rl[a][3] = rl[a][3] + W * (shg[a][0] * uBar[0] + shg[a][1] * uBar[1] + shg[a][2] * uBar[2]);
+#pragma unroll
+      for (int m = 0; m < 3; m++)
+        rl[a][m] = rl[a][m] - W * (Na * rNa[m] + shg[a][0] * rG[m][0] + shg[a][1] * rG[m][1] + shg[a][2] * rG[m][2]);
+    }
+    if (LHS) {
+      const double tlW = c_ip.lhsFct * W;
+      const double tM = tlW * tauM;
+      sC += tlW * tauC;
+      sMr += tM / rho;
+      const double tMr = tM * rho;
+      UU[0] += tMr * u[0] * u[0]; UU[1] += tMr * u[1] * u[1]; UU[2] += tMr * u[2] * u[2];
+      UU[3] += tMr * u[0] * u[1]; UU[4] += tMr * u[1] * u[2]; UU[5] += tMr * u[0] * u[2];
+      if (iconv == 2) {
+        const double tB = tlW * tauBar;
+        RR[0] += tB * r[0] * r[0]; RR[1] += tB * r[1] * r[1]; RR[2] += tB * r[2] * r[2];
+        RR[3] += tB * r[0] * r[1]; RR[4] += tB * r[1] * r[2]; RR[5] += tB * r[0] * r[2];
+      }
+      const double t1 = tlW * rho;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const double w = t1 * T.N[q][a];
+#pragma unroll
+        for (int i = 0; i < 3; i++) UB[a][i] += w * (iconv == 2 ? uBar[i] : u[i]);
+      }
+    }
+  }
+  if (valid) {
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+#pragma unroll
+      for (int m = 0; m < 4; m++) atomicAdd(res + (size_t)nshg * m + nd[a], rl[a][m]);
+  }
+  if (!LHS) return;
+  // ------------------------------------------------------------------ tangent blocks
+  double *stage = stage_all + (threadIdx.x >> 5) * (32 * 13);
+  if (iconv == 2) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) UU[k] += RR[k];
+  }
+  double sW = 0.0;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) sW += T.Qwt[q];
+  const double sMu = c_ip.lhsFct * W1 * sW * rmu;      // sum_q tlW rmu
+  const double cM = c_ip.lhmFct * W1 * rho, cTL = c_ip.lhsFct * W1;
+  int code[4];
+#pragma unroll
+  for (int a = 0; a < 4; a++) code[a] = (__ldg(iBC + nd[a]) >> 3) & 7;
+#pragma unroll
+  for (int a = 0; a < 4; a++) {
+    double TLa = 0.0;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) TLa += T.Qwt[q] * T.N[q][a];
+    TLa *= cTL;
+    // h_a = (UU + RR) g_a
+    const double *ga = shg[a];
+    const double ha[3] = {UU[0] * ga[0] + UU[3] * ga[1] + UU[5] * ga[2], UU[3] * ga[0] + UU[1] * ga[1] + UU[4] * ga[2],
+                          UU[5] * ga[0] + UU[4] * ga[1] + UU[2] * ga[2]};
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+      const double *gb = shg[b];
+      double Mab = 0.0;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) Mab += T.Qwt[q] * T.N[q][a] * T.N[q][b];
+      const double gg = ga[0] * gb[0] + ga[1] * gb[1] + ga[2] * gb[2];
+      const double dcom = cM * Mab + (UB[a][0] * gb[0] + UB[a][1] * gb[1] + UB[a][2] * gb[2]) + sMu * gg +
+                          (ha[0] * gb[0] + ha[1] * gb[1] + ha[2] * gb[2]);
+      double K[9], G[4];
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) K[3 * i + j] = sC * gb[i] * ga[j] + sMu * gb[j] * ga[i] + (i == j ? dcom : 0.0);
+#pragma unroll
+      for (int i = 0; i < 3; i++) G[i] = TLa * gb[i];
+      G[3] = sMr * gg;
+      const int ca = code[a], cb = code[b];
+      const bool ra = (ca != 0 && ca != 7), rb = (cb != 0 && cb != 7);
+      if (ra || rb) {
+        double Kt[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) Kt[k] = K[k];
+        const double a4 = __ldg(BC + (size_t)nshg * 3 + nd[a]), a5 = __ldg(BC + (size_t)nshg * 4 + nd[a]),
+                     a6 = __ldg(BC + (size_t)nshg * 5 + nd[a]);
+        const double b4 = __ldg(BC + (size_t)nshg * 3 + nd[b]), b5 = __ldg(BC + (size_t)nshg * 4 + nd[b]),
+                     b6 = __ldg(BC + (size_t)nshg * 5 + nd[b]);
+        if (a < b) {
+          if (ra) inc_bc_row(Kt, ca, a4, a5, a6);
+          if (rb) inc_bc_col(Kt, cb, b4, b5, b6);
+        } else {
+          if (rb) inc_bc_col(Kt, cb, b4, b5, b6);
+          if (ra) inc_bc_row(Kt, ca, a4, a5, a6);
+          if (a == b) inc_bc_diag(Kt, ca);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) K[k] = Kt[k];
+      }
+      // fillsparseI through the per-warp tile: lanes 0..12 / 16..28 add the 13 entries of two blocks per step.
+      // (The reduction rate is set by the SM's REDG issue, ~1.3 cycles per lane; grouping equal slots of the warp
+      // with match.any before the reduction was measured and costs more than the 2x fewer reductions save.)
+      const int kslot = valid ? eloc[(size_t)(4 * a + b) * numel_pad + e] : -1;
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 9; m++) stage[lane * 13 + m] = K[m];
+#pragma unroll
+      for (int m = 0; m < 4; m++) stage[lane * 13 + 9 + m] = G[m];
+      __syncwarp();
+      const int m = lane & 15, half = lane >> 4;
+#pragma unroll 4
+      for (int it = 0; it < 16; it++) {
+        const int el = 2 * it + half;
+        const int kk = __shfl_sync(0xffffffffu, kslot, el);
+        if (m < 13 && kk >= 0) {
+          const double v = stage[el * 13 + m];
+          if (m < 9) atomicAdd(lhsK + (size_t)9 * kk + m, v);
+          else atomicAdd(lhsP + (size_t)4 * kk + (m - 9), v);
+        }
+      }
+    }
+  }
+}
+
 // bc3Res (incompressible/bc3res.f:1-90, intpres=0) after bc3per: node-wise
 __global__ void k_inc_bc3res(int nshg, const int *__restrict__ iBC, const double *__restrict__ BC, double *res) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -610,8 +891,31 @@ static int launch_group(phb200_ctx *ctx, int tab, int numel, size_t numel_pad, c
   return 0;
 }
 
+template <int NQ>
+static int launch_tet(phb200_ctx *ctx, bool lhs) {
+  KScope ks(ctx, KC_ASM);
+  const int nb = (ctx->numel_tet + 127) / 128;
+  if (lhs)
+    k_inc_asigmr_tet<NQ, true><<<nb, 128, 0, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, ctx->c.nshg, ctx->d_ien,
+                                                            ctx->d_nodeaos, ctx->d_iBC, ctx->d_BC, ctx->d_eloc,
+                                                            ctx->d_res4, ctx->d_lhsK9, ctx->d_lhsP4);
+  else
+    k_inc_asigmr_tet<NQ, false><<<nb, 128, 0, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, ctx->c.nshg, ctx->d_ien,
+                                                             ctx->d_nodeaos, ctx->d_iBC, ctx->d_BC, ctx->d_eloc,
+                                                             ctx->d_res4, ctx->d_lhsK9, ctx->d_lhsP4);
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
+
 static int launch_all(phb200_ctx *ctx, bool lhs, bool asiq) {
-  if (ctx->numel_tet > 0) {
+  static const bool generic_tets = getenv("PHB200_INC_GENERIC") && atoi(getenv("PHB200_INC_GENERIC")) != 0;
+  if (ctx->numel_tet > 0 && !asiq && !generic_tets && ctx->tet_uniform_rule) {
+    const int nq = ctx->c.nint[0];
+    PHB_TRY(phb_pack_nodes(ctx, ctx->inc_idiff >= 1));
+    if (nq == 4) PHB_TRY(launch_tet<4>(ctx, lhs));
+    else if (nq == 1) PHB_TRY(launch_tet<1>(ctx, lhs));
+    else { fprintf(stderr, "phb200: inc_elmgmr: tet rule with %d points not supported\n", nq); return 1; }
+  } else if (ctx->numel_tet > 0) {
     const int nq = ctx->c.nint[0];
     if (nq == 4) PHB_TRY((launch_group<4, 4>(ctx, 0, ctx->numel_tet, ctx->numel_pad, ctx->d_ien, ctx->d_eloc, lhs, asiq)));
     else if (nq == 1) PHB_TRY((launch_group<4, 1>(ctx, 0, ctx->numel_tet, ctx->numel_pad, ctx->d_ien, ctx->d_eloc, lhs, asiq)));
@@ -649,6 +953,7 @@ static int inc_alloc(phb200_ctx *ctx) {
     PHB_CHECK(cudaMalloc(&ctx->d_res4, sizeof(double) * 4 * nshg));
     PHB_CHECK(cudaMalloc(&ctx->d_lesp, sizeof(double) * 4 * nshg));
     PHB_CHECK(cudaMalloc(&ctx->d_lesq, sizeof(double) * 4 * nshg));
+    PHB_CHECK(cudaMalloc(&ctx->d_lesp4, sizeof(double) * 4 * nshg));
     PHB_CHECK(cudaMemsetAsync(ctx->d_lesp, 0, sizeof(double) * 4 * nshg, ctx->stream));
   }
   if (!ctx->d_lhsK9 && ctx->nnz_tot > 0) {
@@ -674,10 +979,10 @@ static int inc_alloc(phb200_ctx *ctx) {
 }
 
 void phb_inc_free(phb200_ctx *ctx) {
-  void *p[] = {ctx->d_res4, ctx->d_lhsK9, ctx->d_lhsP4, ctx->d_lesp, ctx->d_lesq, ctx->d_tpos};
+  void *p[] = {ctx->d_res4, ctx->d_lhsK9, ctx->d_lhsP4, ctx->d_lesp, ctx->d_lesq, ctx->d_lesp4, ctx->d_tpos};
   for (void *q : p)
     if (q) cudaFree(q);
-  ctx->d_res4 = ctx->d_lhsK9 = ctx->d_lhsP4 = ctx->d_lesp = ctx->d_lesq = nullptr;
+  ctx->d_res4 = ctx->d_lhsK9 = ctx->d_lhsP4 = ctx->d_lesp = ctx->d_lesq = ctx->d_lesp4 = nullptr;
   ctx->d_tpos = nullptr;
 }
 
@@ -711,6 +1016,7 @@ int phb_inc_elmgmr(phb200_ctx *ctx, const phb200_incomp *ip) {
   p.ff = ip->taucfct / ip->dtsfct;
   p.iconvflow = ip->iconvflow; p.idiff = ip->idiff; p.matflg5 = ip->matflg5; p.lhs = ip->lhs;
   PHB_CHECK(cudaMemcpyToSymbolAsync(c_ip, &p, sizeof p, 0, cudaMemcpyHostToDevice, s));
+  ctx->inc_idiff = ip->idiff;
   if (ip->idiff == 1) {  // elmgmr.f:44-86
     PHB_CHECK(cudaMemsetAsync(ctx->d_qres, 0, sizeof(double) * 12 * nshg, s));
     PHB_CHECK(cudaMemsetAsync(ctx->d_rmass, 0, sizeof(double) * nshg, s));
@@ -737,52 +1043,65 @@ int phb_inc_elmgmr(phb200_ctx *ctx, const phb200_incomp *ip) {
 
 // ---------------------------------------------------------------------------
 // lesSparse.f products.  MODE bits: 1 = K p(:,1:3) into q(:,1:3); 2 = -G^T p(:,4) into q(:,1:3) (through tpos);
-// 4 = G p(:,1:3) into the scalar row; 8 = + C p(:,4).  pcol4 / qcol4: plane of p holding the scalar / plane of
-// q receiving the scalar row (ApG reads a bare p(n), ApNGt* write a bare q(n)).
+// 4 = G p(:,1:3) into the scalar row; 8 = + C p(:,4).
+// Half a warp per CSR row (about 15 entries per row on tet meshes), lane = entry: each lane streams its entry's
+// kLhs (72 B) and pLhs (32 B, two 16-byte loads), fetches the transposed entry's pLhs through tpos and gathers p from
+// 32-byte node records (p is packed first: one L2 sector per gathered column instead of four); the four row sums
+// are reduced with shuffles inside the half warp.  (A 16-lanes-per-entry variant, every load a contiguous run,
+// was measured 3x slower: too few bytes in flight per warp.)
+__global__ void k_les_pack(int nshg, int ncol, int scalar_only, const double *__restrict__ p, double *__restrict__ p4) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 4 * nshg) return;
+  const int i = t >> 2, c = t & 3;
+  double v = 0.0;
+  if (scalar_only) { if (c == 3) v = p[i]; }
+  else if (c < ncol) v = p[(size_t)nshg * c + i];
+  p4[t] = v;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(128) k_les_ap(int nshg, const int *__restrict__ colm, const int *__restrict__ rowp,
                                                  const int *__restrict__ tpos, const double *__restrict__ lhsK,
-                                                 const double *__restrict__ lhsP, const double *__restrict__ p,
-                                                 double *__restrict__ q, int pcol4, int qcol4) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= nshg) return;
-  const int k0 = colm[row], k1 = colm[row + 1];
+                                                 const double *__restrict__ lhsP, const double *__restrict__ p4,
+                                                 double *__restrict__ q, int qcol4) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, l16 = threadIdx.x & 15;
+  const bool live = row < nshg;
+  int k0 = 0, k1 = 0;
+  if (live) { k0 = colm[row]; k1 = colm[row + 1]; }
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  for (int k = k0 + lane; k < k1; k += 32) {
-    const int j = rowp[k];
-    double p1 = 0.0, p2 = 0.0, p3 = 0.0, p4 = 0.0;
-    if (MODE & (1 | 4)) {
-      p1 = __ldg(p + j);
-      p2 = __ldg(p + (size_t)nshg + j);
-      p3 = __ldg(p + (size_t)2 * nshg + j);
-    }
-    if (MODE & (2 | 8)) p4 = __ldg(p + (size_t)pcol4 * nshg + j);
+  for (int k = k0 + l16; k < k1; k += 16) {
+    const int j = __ldg(rowp + k);
+    const double2 pa = __ldg(reinterpret_cast<const double2 *>(p4 + (size_t)4 * j));
+    const double2 pb = __ldg(reinterpret_cast<const double2 *>(p4 + (size_t)4 * j) + 1);
+    const double p1 = pa.x, p2 = pa.y, p3 = pb.x, pp = pb.y;
     if (MODE & 1) {
       const double *K = lhsK + (size_t)9 * k;  // lesSparse.f:283-294: the three rows use kLhs entries 1,4,7 / 2,5,8 / 3,6,9
-      s0 = s0 + K[0] * p1 + K[3] * p2 + K[6] * p3;
-      s1 = s1 + K[1] * p1 + K[4] * p2 + K[7] * p3;
-      s2 = s2 + K[2] * p1 + K[5] * p2 + K[8] * p3;
+      s0 = s0 + __ldcs(K + 0) * p1 + __ldcs(K + 3) * p2 + __ldcs(K + 6) * p3;
+      s1 = s1 + __ldcs(K + 1) * p1 + __ldcs(K + 4) * p2 + __ldcs(K + 7) * p3;
+      s2 = s2 + __ldcs(K + 2) * p1 + __ldcs(K + 5) * p2 + __ldcs(K + 8) * p3;
     }
     if (MODE & 2) {
-      const double *Pt = lhsP + (size_t)4 * tpos[k];
-      s0 -= Pt[0] * p4;
-      s1 -= Pt[1] * p4;
-      s2 -= Pt[2] * p4;
+      const double2 *Pt = reinterpret_cast<const double2 *>(lhsP + (size_t)4 * __ldg(tpos + k));
+      const double2 ta = __ldg(Pt), tb = __ldg(Pt + 1);
+      s0 -= ta.x * pp;
+      s1 -= ta.y * pp;
+      s2 -= tb.x * pp;
     }
     if (MODE & (4 | 8)) {
-      const double *P = lhsP + (size_t)4 * k;
-      if (MODE & 4) s3 = s3 + P[0] * p1 + P[1] * p2 + P[2] * p3;
-      if (MODE & 8) s3 += P[3] * p4;
+      const double2 *P = reinterpret_cast<const double2 *>(lhsP + (size_t)4 * k);
+      const double2 ga = __ldg(P), gb = __ldg(P + 1);
+      if (MODE & 4) s3 = s3 + ga.x * p1 + ga.y * p2 + gb.x * p3;
+      if (MODE & 8) s3 += gb.y * pp;
     }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
+  for (int o = 8; o > 0; o >>= 1) {
     s0 += __shfl_xor_sync(0xffffffffu, s0, o);
     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
     s3 += __shfl_xor_sync(0xffffffffu, s3, o);
   }
-  if (lane == 0) {
+  if (live && l16 == 0) {
     if (MODE & (1 | 2)) {
       q[row] = s0;
       q[(size_t)nshg + row] = s1;
@@ -799,19 +1118,25 @@ int phb_les_ap(phb200_ctx *ctx, int kind, const double *d_p, double *d_q) {
     return 1;
   }
   const int nshg = ctx->c.nshg;
-  const unsigned nb = (unsigned)(((size_t)nshg * 32 + 127) / 128);
-  KScope ks(ctx, KC_AP);
   cudaStream_t s = ctx->stream;
-#define LES(MODE, pc, qc)                                                                                            \
-  k_les_ap<MODE><<<nb, 128, 0, s>>>(nshg, ctx->d_colm, ctx->d_rowp, ctx->d_tpos, ctx->d_lhsK9, ctx->d_lhsP4, d_p, d_q, \
-                                    pc, qc)
+  static const int ncol[5] = {1, 4, 3, 4, 4};
+  if (kind < 0 || kind > 4) { fprintf(stderr, "phb200: les_ap: kind %d\n", kind); return 1; }
+  {
+    KScope ks(ctx, KC_BLAS);
+    k_les_pack<<<(4 * nshg + 255) / 256, 256, 0, s>>>(nshg, ncol[kind], kind == 0, d_p, ctx->d_lesp4);
+    PHB_CHECK(cudaGetLastError());
+  }
+  const unsigned nb = (unsigned)(((size_t)nshg * 16 + 127) / 128);
+  KScope ks(ctx, KC_AP);
+#define LES(MODE, qc)                                                                                           \
+  k_les_ap<MODE><<<nb, 128, 0, s>>>(nshg, ctx->d_colm, ctx->d_rowp, ctx->d_tpos, ctx->d_lhsK9, ctx->d_lhsP4, \
+                                    ctx->d_lesp4, d_q, qc)
   switch (kind) {
-    case 0: LES(2, 0, 0); break;
-    case 1: LES(1 | 2, 3, 0); break;
-    case 2: LES(4, 0, 0); break;
-    case 3: LES(4 | 8, 3, 0); break;
-    case 4: LES(1 | 2 | 4 | 8, 3, 3); break;
-    default: fprintf(stderr, "phb200: les_ap: kind %d\n", kind); return 1;
+    case 0: LES(2, 0); break;
+    case 1: LES(1 | 2, 0); break;
+    case 2: LES(4, 0); break;
+    case 3: LES(4 | 8, 0); break;
+    default: LES(1 | 2 | 4 | 8, 3); break;
   }
 #undef LES
   PHB_CHECK(cudaGetLastError());
