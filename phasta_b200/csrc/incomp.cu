@@ -571,8 +571,11 @@ __global__ void __launch_bounds__(128) k_inc_asigmr(int tab, int numel, size_t n
 // per node); the 13 entries of every block go through a per-warp shared tile so that one reduction instruction
 // covers whole CSR blocks (4 L2 sectors each) instead of one double of 32 different blocks.
 #define INC_NREC 26
+#ifndef INC_TET_MINB
+#define INC_TET_MINB 3
+#endif
 template <int NQ, bool LHS>
-__global__ void __launch_bounds__(128) k_inc_asigmr_tet(int numel, size_t numel_pad, int nshg,
+__global__ void __launch_bounds__(128, INC_TET_MINB) k_inc_asigmr_tet(int numel, size_t numel_pad, int nshg,
                                                          const int *__restrict__ ien, const double *__restrict__ aos,
                                                          const int *__restrict__ iBC, const double *__restrict__ BC,
                                                          const int *__restrict__ eloc, double *__restrict__ res,
@@ -827,7 +830,7 @@ __global__ void __launch_bounds__(128) k_inc_asigmr_tet(int numel, size_t numel_
       for (int m = 0; m < 4; m++) stage[lane * 13 + 9 + m] = G[m];
       __syncwarp();
       const int m = lane & 15, half = lane >> 4;
-#pragma unroll 4
+#pragma unroll
       for (int it = 0; it < 16; it++) {
         const int el = 2 * it + half;
         const int kk = __shfl_sync(0xffffffffu, kslot, el);
