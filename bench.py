@@ -199,7 +199,8 @@ def reference_arm(args):
     vals = []
     cb = None
     for i in range(args.warmup + args.steps):
-        cb = cpu_baseline(args.workload, cores, seconds_target=max(2.0, 40.0 / max(1, args.warmup + args.steps)))
+        tgt = args.cpu_seconds or max(2.0, 40.0 / max(1, args.warmup + args.steps))
+        cb = cpu_baseline(args.workload, cores, seconds_target=tgt)
         if i >= args.warmup:
             vals.append(cb["value"])
     v = float(np.mean(vals))
@@ -383,6 +384,7 @@ def main():
     ap.add_argument("--no-sparse", action="store_true", help="skip the block-CSR (SolGMRs) leg")
     ap.add_argument("--no-mfg", action="store_true", help="skip the matrix-free (SolMFG) leg")
     ap.add_argument("--no-incomp", action="store_true", help="skip the incompressible (ElmGMR + ApFull) leg")
+    ap.add_argument("--cpu-seconds", type=float, default=0.0, help="CPU sample length per step of --impl reference")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
