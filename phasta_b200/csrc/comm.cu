@@ -30,6 +30,7 @@ static struct {
   ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*GroupStart)();
   ncclResult_t (*GroupEnd)();
   const char *(*GetErrorString)(ncclResult_t);
@@ -49,7 +50,7 @@ static int nccl_load() {
     fprintf(stderr, "phb200: comm_init: missing nccl" #f "\n");   \
     return 1;                                                     \
   }
-  SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(GroupStart)
+  SYM(GetUniqueId) SYM(CommInitRank) SYM(CommDestroy) SYM(Send) SYM(Recv) SYM(AllReduce) SYM(AllGather) SYM(GroupStart)
   SYM(GroupEnd) SYM(GetErrorString)
 #undef SYM
   return 0;
@@ -217,8 +218,42 @@ int phb_commu(phb200_ctx *ctx, double *g, int n, int code) {
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// small all-reduces over NVLink peer memory: protocol and device routine in ctx.h (phb_p2p_allreduce_warp)
+__global__ void k_p2p_allreduce(PhbP2P p, double *vals, int n) {
+  phb_p2p_allreduce_warp(p, vals, n);
+}
+
+PhbP2P phb_p2p_next(phb200_ctx *ctx) {
+  PhbP2P p;
+  p.peer = ctx->d_peer_mail;
+  p.me = ctx->c.myrank;
+  p.world = ctx->c.numpe;
+  p.seq = ++ctx->p2p_seq;
+  p.err = ctx->d_p2p_err;
+  return p;
+}
+
+int phb_p2p_check(phb200_ctx *ctx) {
+  if (!ctx->p2p) return 0;
+  int e = 0;
+  PHB_CHECK(cudaMemcpyAsync(&e, ctx->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (e) {
+    fprintf(stderr, "phb200: peer all-reduce timed out waiting for rank %d\n", e - 1);
+    return 1;
+  }
+  return 0;
+}
+
 int phb_allreduce_sum(phb200_ctx *ctx, double *d_vals, int n) {
   if (ctx->c.numpe <= 1) return 0;
+  if (ctx->p2p && n <= PHB_MAILW) {
+    KScope ks(ctx, KC_HALO);
+    k_p2p_allreduce<<<1, 32, 0, ctx->stream>>>(phb_p2p_next(ctx), d_vals, n);
+    PHB_CHECK(cudaGetLastError());
+    return 0;
+  }
   if (ctx->nccl) {
     NCCL_CHECK(N.AllReduce(d_vals, d_vals, (size_t)n, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
     return 0;
@@ -242,6 +277,69 @@ int phb_allreduce_sum(phb200_ctx *ctx, double *d_vals, int n) {
   return 1;
 }
 
+// map every rank's mailbox into this process (handles travel through one ncclAllGather)
+static int p2p_setup(phb200_ctx *ctx) {
+  const int world = ctx->c.numpe, me = ctx->c.myrank;
+  ctx->p2p = false;
+  const char *env = getenv("PHB200_P2P");
+  if (env && atoi(env) == 0) return 0;
+  if (world > PHB_MAXR) return 0;
+  const size_t mail_dbl = (size_t)2 * PHB_MAXR * PHB_MAILW + (size_t)2 * PHB_MAXR;
+  PHB_CHECK(cudaMalloc(&ctx->d_mail, sizeof(double) * mail_dbl));
+  PHB_CHECK(cudaMemset(ctx->d_mail, 0, sizeof(double) * mail_dbl));
+  PHB_CHECK(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
+  PHB_CHECK(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
+  PHB_CHECK(cudaMalloc(&ctx->d_p2p_err, sizeof(int)));
+  PHB_CHECK(cudaMemset(ctx->d_p2p_err, 0, sizeof(int)));
+  cudaIpcMemHandle_t mine;
+  if (cudaIpcGetMemHandle(&mine, ctx->d_mail) != cudaSuccess) {
+    cudaGetLastError();
+    fprintf(stderr, "phb200: comm_init: cudaIpcGetMemHandle failed; small all-reduces stay on NCCL\n");
+    return 0;
+  }
+  unsigned char *d_h;
+  PHB_CHECK(cudaMalloc(&d_h, (size_t)(world + 1) * sizeof(mine)));
+  PHB_CHECK(cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  NCCL_CHECK(N.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), /*ncclInt8*/ 0, (ncclComm_t)ctx->nccl, ctx->stream));
+  std::vector<cudaIpcMemHandle_t> all(world);
+  PHB_CHECK(cudaMemcpyAsync(all.data(), d_h + sizeof(mine), (size_t)world * sizeof(mine), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_h);
+  std::vector<double *> ptrs(world, nullptr);
+  int ok = 1;
+  for (int r = 0; r < world; r++) {
+    ctx->peer_mapped[r] = nullptr;
+    if (r == me) { ptrs[r] = ctx->d_mail; continue; }
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = 0;
+      break;
+    }
+    ctx->peer_mapped[r] = p;
+    ptrs[r] = (double *)p;
+  }
+  // every rank must take the same decision: agree through one NCCL all-reduce (min)
+  double *d_ok;
+  PHB_CHECK(cudaMalloc(&d_ok, sizeof(double)));
+  double okd = ok ? 0.0 : 1.0;
+  PHB_CHECK(cudaMemcpy(d_ok, &okd, sizeof(double), cudaMemcpyHostToDevice));
+  NCCL_CHECK(N.AllReduce(d_ok, d_ok, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+  PHB_CHECK(cudaMemcpyAsync(&okd, d_ok, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_ok);
+  if (okd != 0.0) {
+    if (me == 0) fprintf(stderr, "phb200: comm_init: peer mapping unavailable on %d rank(s); small all-reduces stay on NCCL\n", (int)okd);
+    return 0;
+  }
+  PHB_CHECK(cudaMalloc(&ctx->d_peer_mail, sizeof(double *) * world));
+  PHB_CHECK(cudaMemcpy(ctx->d_peer_mail, ptrs.data(), sizeof(double *) * world, cudaMemcpyHostToDevice));
+  ctx->p2p_seq = 0;
+  ctx->p2p = true;
+  return 0;
+}
+
 int phb_comm_unique_id(void *id128) {
   PHB_TRY(nccl_load());
   ncclUniqueId id;
@@ -259,10 +357,22 @@ int phb_comm_init(phb200_ctx *ctx, const void *id128) {
   NCCL_CHECK(N.CommInitRank(&comm, ctx->c.numpe, id, ctx->c.myrank));
   ctx->nccl = comm;
   ctx->local_group = false;
+  PHB_TRY(p2p_setup(ctx));
   return 0;
 }
 
 void phb_comm_free(phb200_ctx *ctx) {
+  if (ctx->p2p) {
+    cudaStreamSynchronize(ctx->stream);
+    for (int r = 0; r < ctx->c.numpe && r < 64; r++)
+      if (ctx->peer_mapped[r]) cudaIpcCloseMemHandle(ctx->peer_mapped[r]);
+    ctx->p2p = false;
+  }
+  if (ctx->d_mail) cudaFree(ctx->d_mail);
+  if (ctx->d_peer_mail) cudaFree(ctx->d_peer_mail);
+  if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  if (ctx->d_p2p_err) cudaFree(ctx->d_p2p_err);
+  ctx->d_mail = nullptr; ctx->d_peer_mail = nullptr; ctx->d_ticket = nullptr; ctx->d_p2p_err = nullptr;
   if (ctx->nccl && N.CommDestroy) N.CommDestroy((ncclComm_t)ctx->nccl);
   ctx->nccl = nullptr;
   if (ctx->local_group) {

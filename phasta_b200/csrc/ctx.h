@@ -81,6 +81,15 @@ struct phb200_ctx {
   double *d_sendbuf, *d_recvbuf;
   size_t halo_cap;     // doubles per buffer
   void *nccl;          // ncclComm_t
+  // ---- NVLink peer-memory mailboxes (comm.cu): every rank maps every other rank's mailbox through CUDA IPC; small
+  //      all-reduces (the Krylov dot products) are done by the reducing kernel itself with peer stores + flags
+  double *d_mail;             // this rank's mailbox: vals[2][PHB_MAXR][PHB_MAILW] doubles, then seq[2][PHB_MAXR] u64
+  double **d_peer_mail;       // device array [numpe] of mailbox pointers (own pointer at myrank)
+  void *peer_mapped[64];      // host copies of the mapped peer pointers (for cudaIpcCloseMemHandle)
+  unsigned long long p2p_seq; // all-reduces issued so far (identical on all ranks)
+  unsigned int *d_ticket;     // last-block detection for the fused reduction kernels
+  int *d_p2p_err;             // set by a kernel whose wait on a peer flag timed out
+  bool p2p;
   bool local_group;    // in-process multi-part transport (tests)
   // ---- state / results
   double *d_y, *d_ac;            // [5][nshg] {u,v,w,p,T}
@@ -198,6 +207,60 @@ int phb_sparseap(phb200_ctx *ctx, double *d_u);
 int phb_halo_setup(phb200_ctx *ctx, const int *ilwork);
 int phb_commu(phb200_ctx *ctx, double *d_global, int n, int code);
 int phb_allreduce_sum(phb200_ctx *ctx, double *d_vals, int n);
+int phb_p2p_check(phb200_ctx *ctx);
+#define PHB_MAXR 16   // ranks a mailbox has room for
+#define PHB_MAILW 8   // doubles per all-reduce
+// All-reduce of up to PHB_MAILW doubles over NVLink peer memory, done by the kernel that produced them (called by
+// ONE warp of one block).  Every rank owns a mailbox  vals[2][MAXR][MAILW] | seq[2][MAXR]  that all peers have
+// mapped through CUDA IPC (comm.cu p2p_setup).  For all-reduce number `seq` (the same on all ranks: the solver is
+// SPMD) lane r of the calling warp
+//   1. stores this rank's partial values into slot [seq&1][me] of rank r's mailbox, fences at system scope, then
+//      stores `seq` into the matching flag;
+//   2. spins on flag [seq&1][r] of its OWN mailbox until rank r's contribution has arrived;
+//   3. lane 0 adds the `world` contributions in rank order -- every rank computes the same bits.
+// Two slots (parity of seq) suffice: a rank can only start all-reduce seq+2 after seq+1 completed, and seq+1
+// completes only after every rank has contributed to it, i.e. after every rank has finished reading seq.
+// The spin is bounded; a time-out raises *err (checked on the host at the end of the solve) instead of hanging.
+struct PhbP2P {
+  double *const *peer;  // [world] mailbox pointers
+  int me, world;
+  unsigned long long seq;
+  int *err;
+};
+#ifdef __CUDACC__
+static __device__ __forceinline__ void phb_p2p_allreduce_warp(const PhbP2P &p, volatile double *vals, int n) {
+  const int lane = threadIdx.x & 31;
+  const int par = (int)(p.seq & 1ull);
+  const size_t voff = (size_t)par * PHB_MAXR * PHB_MAILW, foff = (size_t)2 * PHB_MAXR * PHB_MAILW;
+  if (lane < p.world) {
+    volatile double *mb = p.peer[lane];
+    for (int k = 0; k < n; k++) mb[voff + (size_t)p.me * PHB_MAILW + k] = vals[k];
+    __threadfence_system();
+    volatile unsigned long long *fl = reinterpret_cast<volatile unsigned long long *>(p.peer[lane] + foff);
+    fl[par * PHB_MAXR + p.me] = p.seq;
+  }
+  double *mine = p.peer[p.me];
+  if (lane < p.world) {
+    volatile unsigned long long *fl = reinterpret_cast<volatile unsigned long long *>(mine + foff);
+    long long spins = 0;
+    while (fl[par * PHB_MAXR + lane] != p.seq) {
+      if (++spins > (1ll << 27)) { atomicExch(p.err, 1 + lane); break; }
+    }
+    __threadfence_system();
+  }
+  __syncwarp();
+  if (lane == 0) {
+    volatile double *v = mine + voff;
+    for (int k = 0; k < n; k++) {
+      double s = 0.0;
+      for (int r = 0; r < p.world; r++) s += v[(size_t)r * PHB_MAILW + k];
+      vals[k] = s;
+    }
+  }
+  __syncwarp();
+}
+#endif
+PhbP2P phb_p2p_next(phb200_ctx *ctx);
 int phb_comm_init(phb200_ctx *ctx, const void *id128);
 int phb_comm_unique_id(void *id128);
 void phb_comm_free(phb200_ctx *ctx);

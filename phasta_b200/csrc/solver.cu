@@ -329,10 +329,13 @@ __device__ __forceinline__ double block_sum(double v) {
 
 // MGS step (solgmr.f:224-244): w -= beta_prev * uprev (if uprev); out = (w, uj)
 // beta_prev is read from device memory; *out must be zero on entry.
+// With `fuse` the block that finishes last also all-reduces the sum over NVLink peer memory (ctx.h), so that
+// "subtract, dot, all-reduce" of one MGS step is ONE kernel and the next step's beta is ready when it ends.
 __global__ void __launch_bounds__(RED_BLOCK) k_mgs_step(size_t n, double *__restrict__ w,
                                                          const double *__restrict__ uprev,
                                                          const double *__restrict__ beta_prev,
-                                                         const double *__restrict__ uj, double *out) {
+                                                         const double *__restrict__ uj, double *out, int fuse,
+                                                         PhbP2P p2p, unsigned int *ticket) {
   double s = 0.0;
   const double beta = uprev ? *beta_prev : 0.0;
   const bool self = (uj == w);
@@ -346,6 +349,23 @@ __global__ void __launch_bounds__(RED_BLOCK) k_mgs_step(size_t n, double *__rest
   }
   s = block_sum(s);
   if (threadIdx.x == 0) atomicAdd(out, s);
+  if (!fuse) return;
+  __shared__ int last;
+  __shared__ double sv[1];
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    if (threadIdx.x == 0) {
+      sv[0] = atomicAdd(out, 0.0);  // the complete local sum
+      *ticket = 0u;
+    }
+    __syncwarp();
+    phb_p2p_allreduce_warp(p2p, sv, 1);
+    if (threadIdx.x == 0) *out = sv[0];
+  }
 }
 // v <- v / sqrt(*nrm2) (solgmr.f:251-256) or v <- v * alpha
 __global__ void k_scale_dev(size_t n, double *v, const double *nrm2) {
@@ -410,10 +430,12 @@ static int dot_host(phb200_ctx *ctx, size_t n, double *a, const double *b, doubl
   PHB_CHECK(cudaMemsetAsync(ctx->d_dots, 0, sizeof(double), s));
   {
     KScope ks(ctx, KC_BLAS);
-    k_mgs_step<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, a, nullptr, nullptr, b, ctx->d_dots);
+    const bool fuse = ctx->p2p && ctx->c.numpe > 1;
+    k_mgs_step<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, a, nullptr, nullptr, b, ctx->d_dots, fuse ? 1 : 0,
+                                                 fuse ? phb_p2p_next(ctx) : PhbP2P(), ctx->d_ticket);
     PHB_CHECK(cudaGetLastError());
+    if (!fuse) PHB_TRY(phb_allreduce_sum(ctx, ctx->d_dots, 1));
   }
-  PHB_TRY(phb_allreduce_sum(ctx, ctx->d_dots, 1));
   PHB_CHECK(cudaMemcpyAsync(ctx->h_dots, ctx->d_dots, sizeof(double), cudaMemcpyDeviceToHost, s));
   PHB_CHECK(cudaStreamSynchronize(s));
   *out = ctx->h_dots[0];
@@ -460,6 +482,7 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, 
   }
   PHB_CHECK(cudaMemcpyAsync(Uk(1), ctx->d_res, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
   double summed = 0.0;
+  const bool fuse = ctx->p2p && c.numpe > 1;  // dot + all-reduce in one kernel over NVLink peer memory
   PHB_TRY(dot_host(ctx, n, ctx->d_res, ctx->d_res, &summed));
   double unorm = sqrt(summed);
   int iKs = 0, lGMRES = 0;
@@ -506,10 +529,12 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, 
           {
             KScope ks(ctx, KC_BLAS);
             k_mgs_step<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, w, jK == 1 ? nullptr : Uk(jK - 1),
-                                                         ctx->d_dots + (jK - 1), Uk(jK), ctx->d_dots + jK);
+                                                         ctx->d_dots + (jK - 1), Uk(jK), ctx->d_dots + jK,
+                                                         fuse ? 1 : 0, fuse ? phb_p2p_next(ctx) : PhbP2P(),
+                                                         ctx->d_ticket);
             PHB_CHECK(cudaGetLastError());
           }
-          PHB_TRY(phb_allreduce_sum(ctx, ctx->d_dots + jK, 1));
+          if (!fuse) PHB_TRY(phb_allreduce_sum(ctx, ctx->d_dots + jK, 1));
         }
         {
           KScope ks(ctx, KC_BLAS);
@@ -554,6 +579,7 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, 
   }
 #undef H
   PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, ctx->d_Dy, 2));  // solgmr.f:347
+  PHB_TRY(phb_p2p_check(ctx));
   *iKs_out = iKs;
   *lGMRES_out = lGMRES;
   return 0;
