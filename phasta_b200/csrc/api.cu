@@ -87,6 +87,10 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   memset(ctx->kc_ms, 0, sizeof ctx->kc_ms);
   memset(ctx->kc_n, 0, sizeof ctx->kc_n);
   PHB_CHECK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  PHB_CHECK(cudaStreamCreateWithFlags(&ctx->cstream, cudaStreamNonBlocking));
+  PHB_CHECK(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
+  PHB_CHECK(cudaEventCreateWithFlags(&ctx->ev_ac, cudaEventDisableTiming));
+  ctx->ac_pending = false;
   for (int i = 0; i < 16; i++) PHB_CHECK(cudaEventCreate(&ctx->ev[i]));
   PHB_CHECK(cudaEventCreate(&ctx->pev0));
   PHB_CHECK(cudaEventCreate(&ctx->pev1));
@@ -267,6 +271,9 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
   cudaEventDestroy(ctx->pev0);
   cudaEventDestroy(ctx->pev1);
+  cudaEventDestroy(ctx->ev_main);
+  cudaEventDestroy(ctx->ev_ac);
+  cudaStreamDestroy(ctx->cstream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -305,6 +312,19 @@ extern "C" int phb200_set_state(phb200_ctx *ctx, const double *y, const double *
   const size_t n5 = (size_t)5 * ctx->c.nshg;
   PHB_TRY(h2d(ctx, ctx->d_y, y, n5));
   PHB_TRY(h2d(ctx, ctx->d_ac, ac, n5));
+  return 0;
+}
+// y on the compute stream, ac on the copy stream (after everything already queued on the compute stream, which
+// may still read the old d_ac); phb_elmgmre orders its first reader of d_ac behind ev_ac
+static int set_state_split(phb200_ctx *ctx, const double *y, const double *ac) {
+  const size_t n5 = (size_t)5 * ctx->c.nshg;
+  PHB_TRY(h2d(ctx, ctx->d_y, y, n5));
+  // Y,t follows Y on the link (so Y is not slowed down) but on the copy stream, i.e. concurrently with AsIq
+  PHB_CHECK(cudaEventRecord(ctx->ev_main, ctx->stream));
+  PHB_CHECK(cudaStreamWaitEvent(ctx->cstream, ctx->ev_main, 0));
+  PHB_CHECK(cudaMemcpyAsync(ctx->d_ac, ac, sizeof(double) * n5, cudaMemcpyHostToDevice, ctx->cstream));
+  PHB_CHECK(cudaEventRecord(ctx->ev_ac, ctx->cstream));
+  ctx->ac_pending = true;
   return 0;
 }
 extern "C" int phb200_dev_elmgmre(phb200_ctx *ctx, const phb200_step *st) {
@@ -375,7 +395,7 @@ extern "C" int phb200_elmgmre(phb200_ctx *ctx, const double *y, const double *ac
                               double *BDiag, double *EGmass, double *qres) {
   ENTER(ctx);
   if (!y || !ac || !st) return fail("elmgmre", "null argument");
-  PHB_TRY(phb200_set_state(ctx, y, ac));
+  PHB_TRY(set_state_split(ctx, y, ac));
   PHB_TRY(phb_elmgmre(ctx, st));
   if (res) PHB_TRY(d2h(ctx, res, ctx->d_res, (size_t)5 * ctx->c.nshg));
   if (BDiag && st->iprec) PHB_TRY(d2h(ctx, BDiag, ctx->d_BDiag, (size_t)25 * ctx->c.nshg));
@@ -391,7 +411,7 @@ extern "C" int phb200_solgmre(phb200_ctx *ctx, const double *y, const double *ac
   ENTER(ctx);
   if (!y || !ac || !st || !Dy || !iKs || !lGMRES || !ntotGM) return fail("solgmre", "null argument");
   const size_t n5 = (size_t)5 * ctx->c.nshg;
-  PHB_TRY(phb200_set_state(ctx, y, ac));
+  PHB_TRY(set_state_split(ctx, y, ac));
   PHB_TRY(phb_elmgmre(ctx, st));
   PHB_TRY(phb_solve(ctx, st, 0, iKs, lGMRES, ntotGM));
   PHB_TRY(d2h(ctx, Dy, ctx->d_Dy, n5));
@@ -463,7 +483,7 @@ extern "C" int phb200_solgmrs(phb200_ctx *ctx, const double *y, const double *ac
   if (!y || !ac || !st || !Dy || !iKs || !lGMRESs || !ntotGM) return fail("solgmrs", "null argument");
   if (!ctx->d_lhsK) return fail("solgmrs", "no CSR structure (call phb200_set_sparse with colm/rowp first)");
   const size_t n5 = (size_t)5 * ctx->c.nshg;
-  PHB_TRY(phb200_set_state(ctx, y, ac));
+  PHB_TRY(set_state_split(ctx, y, ac));
   PHB_TRY(phb_elmgmre(ctx, st, 1));
   PHB_TRY(phb_solve(ctx, st, 1, iKs, lGMRESs, ntotGM));
   PHB_TRY(d2h(ctx, Dy, ctx->d_Dy, n5));

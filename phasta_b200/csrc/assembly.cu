@@ -2191,6 +2191,10 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
     fprintf(stderr, "phb200: elmgmre: idiff=%d not supported (0 or 1)\n", c.idiff);
     return 1;
   }
+  if (ctx->ac_pending) {  // Y,t was copied on the copy stream while AsIq/qpbc ran (api.cu set_state_split)
+    PHB_CHECK(cudaStreamWaitEvent(s, ctx->ev_ac, 0));
+    ctx->ac_pending = false;
+  }
   {
     KScope ks(ctx, KC_NODE);
     const size_t tot = (size_t)nshg * NREC;

@@ -54,6 +54,11 @@ struct phb200_ctx {
   phb200_common c;
   int device;
   cudaStream_t stream;
+  // second stream for the host->device copy of Y,t in the host-array entry points: it runs under AsIq/qpbc,
+  // which only need Y (api.cu set_state_split; phb_elmgmre waits on ev_ac before the first reader of d_ac)
+  cudaStream_t cstream;
+  cudaEvent_t ev_main, ev_ac;
+  bool ac_pending;
   // ---- mesh: lcsyst==1 blocks concatenated in file order (specialised tet kernels);
   //      other topologies live in `gen` (generic kernels)
   std::vector<ElemGroup> gen;
@@ -243,7 +248,8 @@ static __device__ __forceinline__ void phb_p2p_allreduce_warp(const PhbP2P &p, v
   if (lane < p.world) {
     volatile unsigned long long *fl = reinterpret_cast<volatile unsigned long long *>(mine + foff);
     long long spins = 0;
-    while (fl[par * PHB_MAXR + lane] != p.seq) {
+    const bool dead = *reinterpret_cast<volatile int *>(p.err) != 0;  // an earlier wait timed out: do not wait again
+    while (!dead && fl[par * PHB_MAXR + lane] != p.seq) {
       if (++spins > (1ll << 27)) { atomicExch(p.err, 1 + lane); break; }
     }
     __threadfence_system();
