@@ -28,6 +28,8 @@ typedef struct qpstate {
   double A0[6][6], A1[6][6], A2[6][6], A3[6][6];
   double rLyi[6], rLymi[6], tau[6];
   double ri[21], rmi[21], stiff[16][16];
+  /* discontinuity capturing (iDC /= 0): e3mtrx.f:232-298, e3tau.f:177-247, e3dc.f */
+  double A0DC[5], A0inv[16], dVdY[16], giju[7], rTLS, raLS, DC;
 } qpstate;
 
 /* getthm, ipress=0 (compressible/getthm.f:111,148) ithm=6 */
@@ -167,7 +169,59 @@ static void e3ivar(const orc_common *c, qpstate *s, double yl[][6], double ycl[]
   }
 }
 
-/* e3mtrx (compressible/e3mtrx.f:75-227), iDC=0 */
+/* the iDC /= 0 tail of e3mtrx (compressible/e3mtrx.f:232-298): A0DC, A0^-1 (15 symmetric entries), dV/dY */
+static void e3mtrx_dc(qpstate *s) {
+  double rho = s->rho, T = s->T, u1 = s->u1, u2 = s->u2, u3 = s->u3, rk = s->rk, h = s->h, cp = s->cp;
+  double alfap = s->alfap, betaT = s->betaT;
+  double s1 = 1.0 / (rho * rho * betaT * T);
+  double cv = cp - (alfap * alfap * T / rho / betaT);
+  s->A0DC[1] = (rho * betaT) * (rho * betaT) * s1;
+  s->A0DC[2] = -rho * alfap * rho * betaT * s1;
+  s->A0DC[3] = rho / T;
+  s->A0DC[4] = (-rho * alfap) * (-rho * alfap) * s1 + (rho * cv / (T * T));
+  double fact1 = 1.0 / (rho * cv * (T * T));
+  double d = alfap * T / rho / betaT;
+  double e1bar = h - rk, e2bar = e1bar - d, e3bar = e2bar - cv * T;
+  double e5bar = e1bar * e1bar - 2 * e1bar * d + 2 * rk * cv * T + cp * T / rho / betaT;
+  double c1bar = u1 * u1 + cv * T, c2bar = u2 * u2 + cv * T, c3bar = u3 * u3 + cv * T;
+  double u12 = u1 * u2, u31 = u3 * u1, u23 = u2 * u3;
+  double *Ai = s->A0inv;
+  Ai[1] = e5bar * fact1;
+  Ai[2] = c1bar * fact1;
+  Ai[3] = c2bar * fact1;
+  Ai[4] = c3bar * fact1;
+  Ai[5] = 1 * fact1;
+  Ai[6] = u1 * e3bar * fact1;
+  Ai[7] = u2 * e3bar * fact1;
+  Ai[8] = u3 * e3bar * fact1;
+  Ai[9] = -e2bar * fact1;
+  Ai[10] = u12 * fact1;
+  Ai[11] = u31 * fact1;
+  Ai[12] = -u1 * fact1;
+  Ai[13] = u23 * fact1;
+  Ai[14] = -u2 * fact1;
+  Ai[15] = -u3 * fact1;
+  fact1 = 1 / T;
+  double fact2 = fact1 / T;
+  double *V = s->dVdY;
+  V[1] = fact1 / rho;
+  V[2] = -fact1 * u1;
+  V[3] = fact1;
+  V[4] = -fact1 * u2;
+  V[5] = 0.0;
+  V[6] = fact1;
+  V[7] = -fact1 * u3;
+  V[8] = 0.0;
+  V[9] = 0.0;
+  V[10] = fact1;
+  V[11] = -(h - rk) * fact2;
+  V[12] = -fact2 * u1;
+  V[13] = -fact2 * u2;
+  V[14] = -fact2 * u3;
+  V[15] = fact2;
+}
+
+/* e3mtrx (compressible/e3mtrx.f:75-227) */
 static void e3mtrx(qpstate *s) {
   double rho = s->rho, u1 = s->u1, u2 = s->u2, u3 = s->u3;
   memset(s->A0, 0, sizeof s->A0);
@@ -457,12 +511,42 @@ static void e3tau(const orc_common *c, qpstate *s) {
       0.125 * fact / (rho * (gijd[1] + gijd[3] + gijd[6])) * c->taucfct;
   s->tau[2] = 1.0 / fact;
   s->tau[3] = s->tau[2] / s->cv * c->temper;
+  double rt[6];
+  if (c->iDC != 0)
+    for (int m = 1; m <= 5; m++) rt[m] = s->rLyi[m]; /* rLyitemp, e3tau.f:177 */
   if (c->ires == 3 || c->ires == 1) {
     s->rLyi[1] *= s->tau[1];
     s->rLyi[2] *= s->tau[2];
     s->rLyi[3] *= s->tau[2];
     s->rLyi[4] *= s->tau[2];
     s->rLyi[5] *= s->tau[3];
+  }
+  if (c->iDC != 0) { /* e3tau.f:186-247 */
+    const double *V = s->dVdY, *Ai = s->A0inv, *r = s->rLyi;
+    s->rTLS = rt[1] * (r[1] * V[1] + V[2] * r[2] + V[4] * r[3] + r[4] * V[7] + V[11] * r[5]) +
+              rt[2] * (r[2] * V[3] + r[3] * V[5] + V[8] * r[4] + r[5] * V[12]) +
+              rt[3] * (r[3] * V[6] + V[9] * r[4] + V[13] * r[5]) + rt[4] * (r[4] * V[10] + V[14] * r[5]) +
+              rt[5] * (V[15] * r[5]);
+    s->raLS = 2.0 * rt[4] * rt[5] * Ai[15] + 2.0 * rt[3] * rt[5] * Ai[14] + 2.0 * rt[1] * rt[2] * Ai[6] +
+              2.0 * rt[2] * rt[3] * Ai[10] + 2.0 * rt[2] * rt[4] * Ai[11] + 2.0 * rt[1] * rt[3] * Ai[7] +
+              2.0 * rt[3] * rt[4] * Ai[13] + 2.0 * rt[2] * rt[5] * Ai[12] + 2.0 * rt[1] * rt[4] * Ai[8] +
+              2.0 * rt[1] * rt[5] * Ai[9] + rt[1] * rt[1] * Ai[1] + rt[2] * rt[2] * Ai[2] + rt[3] * rt[3] * Ai[3] +
+              rt[4] * rt[4] * Ai[4] + rt[5] * rt[5] * Ai[5];
+    double gu[7];
+    gu[1] = gijd[1];
+    gu[2] = gijd[3];
+    gu[3] = gijd[6];
+    gu[4] = gijd[2];
+    gu[5] = gijd[4];
+    gu[6] = gijd[5];
+    double detI = 1.0 / (gu[1] * gu[2] * gu[3] - gu[1] * gu[6] * gu[6] - gu[4] * gu[4] * gu[3] +
+                         gu[4] * gu[5] * gu[6] * 2.0 - gu[5] * gu[5] * gu[2]);
+    s->giju[1] = detI * (gu[2] * gu[3] - gu[6] * gu[6]);
+    s->giju[2] = detI * (gu[1] * gu[3] - gu[5] * gu[5]);
+    s->giju[3] = detI * (gu[1] * gu[2] - gu[4] * gu[4]);
+    s->giju[4] = detI * (gu[5] * gu[6] - gu[4] * gu[3]);
+    s->giju[5] = detI * (gu[4] * gu[6] - gu[5] * gu[2]);
+    s->giju[6] = detI * (gu[4] * gu[5] - gu[1] * gu[6]);
   }
   if (c->ires != 1) {
     s->rLymi[1] *= s->tau[1];
@@ -550,6 +634,73 @@ static void e3ls(const orc_common *c, qpstate *s, double *EG, size_t eg_stride,
             EGE(i0 + idof, j0 + jdof) += fact * Atau[idof][jdof];
       }
     }
+  }
+}
+
+/* e3DC (compressible/e3dc.f:1-330): discontinuity-capturing viscosity DC (iDC = 1, 2, 3), its flux
+ * DC g^ij A0 Y,j into ri/rmi and its tangent DC g^ij A0 into stiff.  The statement for rmi(:,11) reads
+ * rmi(:,12) and gAgyi(:,12) (e3dc.f:262) -- kept. */
+static void e3dc(const orc_common *c, qpstate *s) {
+  const double *g[4] = {NULL, s->g1yi, s->g2yi, s->g3yi};
+  const double *gj = s->giju, *D = s->A0DC;
+  double A0g[16], gA[16], yy[7];
+  for (int i = 1; i <= 3; i++)
+    for (int m = 1; m <= 5; m++)
+      A0g[5 * (i - 1) + m] = s->A0[m][1] * g[i][1] + s->A0[m][2] * g[i][2] + s->A0[m][3] * g[i][3] +
+                             s->A0[m][4] * g[i][4] + s->A0[m][5] * g[i][5];
+  for (int m = 1; m <= 5; m++) {
+    gA[m] = gj[1] * A0g[m] + gj[4] * A0g[5 + m] + gj[5] * A0g[10 + m];
+    gA[5 + m] = gj[4] * A0g[m] + gj[2] * A0g[5 + m] + gj[6] * A0g[10 + m];
+    gA[10 + m] = gj[5] * A0g[m] + gj[6] * A0g[5 + m] + gj[3] * A0g[10 + m];
+  }
+  for (int i = 1; i <= 3; i++)
+    yy[i] = D[1] * (g[i][1] * g[i][1]) + 2.0 * g[i][1] * D[2] * g[i][5] + D[3] * (g[i][2] * g[i][2]) +
+            D[3] * (g[i][3] * g[i][3]) + D[3] * (g[i][4] * g[i][4]) + D[4] * (g[i][5] * g[i][5]);
+  const int pi[4] = {0, 1, 1, 2}, pj[4] = {0, 2, 3, 3};
+  for (int k = 1; k <= 3; k++) {
+    const double *a = g[pi[k]], *b = g[pj[k]];
+    yy[3 + k] = a[1] * D[1] * b[1] + a[1] * D[2] * b[5] + a[2] * D[3] * b[2] + a[3] * D[3] * b[3] +
+                a[4] * D[3] * b[4] + a[5] * D[2] * b[1] + a[5] * D[4] * b[5];
+  }
+  double gnorm = 1.0 / (gj[1] * yy[1] + 2.0 * gj[4] * yy[4] + 2.0 * gj[5] * yy[5] + gj[2] * yy[2] +
+                        2.0 * gj[6] * yy[6] + gj[3] * yy[3] + c->epsM);
+  double DC = 0.0;
+  if (c->iDC == 1) {
+    double fact = 1.0;
+    if (c->ipord == 2) fact = 0.9;
+    if (c->ipord == 3) fact = 0.75;
+    DC = fmax(0.0, (fact * sqrt(s->raLS * gnorm)) - (s->rTLS * gnorm));
+  } else if (c->iDC == 2) {
+    DC = 2.0 * s->rTLS * gnorm;
+  } else if (c->iDC == 3) {
+    double fact = 1.0;
+    if (c->ipord == 2) fact = 0.5;
+    DC = fmin(fmax(0.0, fact * sqrt(s->raLS * gnorm) - s->rTLS * gnorm), 2.0 * s->rTLS * gnorm);
+  }
+  s->DC = DC;
+  if (c->ires == 1 || c->ires == 3) {
+    for (int k = 1; k <= 15; k++) {
+      s->ri[k] = s->ri[k] + DC * gA[k];
+      if (k != 11) s->rmi[k] = s->rmi[k] + DC * gA[k];
+      else s->rmi[11] = s->rmi[12] + DC * gA[12]; /* the reference's statement (:262), before rmi(:,12) is updated */
+    }
+  }
+  if (c->ires == 2)
+    for (int k = 1; k <= 15; k++) s->rmi[k] = s->rmi[k] + DC * gA[k];
+  if (c->iprec == 1 && c->lhs == 1) {
+    for (int j = 1; j <= 5; j++)
+      for (int i = 1; i <= 5; i++) {
+        double dt = s->A0[i][j] * DC;
+        s->stiff[i][j] += dt * gj[1];
+        s->stiff[i][j + 5] += dt * gj[4];
+        s->stiff[i][j + 10] += dt * gj[5];
+        s->stiff[i + 5][j] += dt * gj[4];
+        s->stiff[i + 5][j + 5] += dt * gj[2];
+        s->stiff[i + 5][j + 10] += dt * gj[6];
+        s->stiff[i + 10][j] += dt * gj[5];
+        s->stiff[i + 10][j + 5] += dt * gj[6];
+        s->stiff[i + 10][j + 10] += dt * gj[3];
+      }
   }
 }
 
@@ -739,9 +890,11 @@ static void e3_element(const orc_part *p, int lcsyst, int nshl, int nenl,
     if (c->lhs == 1) memset(s.stiff, 0, sizeof s.stiff);
     e3ivar(c, &s, yl, ycl, acl, xl, ql);
     e3mtrx(&s);
+    if (c->iDC != 0) e3mtrx_dc(&s);
     e3conv(c, &s, EG, eg_stride, nedof);
     if (c->Navier == 1) e3visc(c, &s);
     e3ls(c, &s, EG, eg_stride, nedof);
+    if (c->iDC != 0) e3dc(c, &s); /* e3.f:217-222 */
     if (ngauss == 1 && nshl == 4)
       e3juel(c, &s, yl, acl, rl);
     else

@@ -71,7 +71,7 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   if (c->nflow != 5 || c->ndof != 5) return fail("init", "only nflow=ndof=5 (no scalars) supported");
   if (c->ipord != 1) return fail("init", "only ipord=1 supported");
   if (c->itau != 0) return fail("init", "only itau=0 (Shakib diagonal tau) supported");
-  if (c->iDC != 0) return fail("init", "iDC!=0 (discontinuity capturing) not supported");
+  if (c->iDC < 0 || c->iDC > 3) return fail("init", "iDC must be 0..3 (e3dc.f)");
   if (c->Navier != 1) return fail("init", "Navier must be 1");
   if (c->EntropyPressure != 0) return fail("init", "EntropyPressure=1 not supported");
   PHB_CHECK(cudaSetDevice(device));

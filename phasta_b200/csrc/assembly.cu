@@ -31,7 +31,8 @@ struct TetTables {
 struct PhysParams {
   double Rgas, gamma, gamma1, pr, mu0, Tref, Ssuth, dat131;
   double dtsfct, taucfct, temper, Dtgl, fct1;  // fct1 = almi/gami/alfi*Dtgl
-  int matflg2, matflg3, idiff, iremove, ipord, lhs, iprec, pad;
+  int matflg2, matflg3, idiff, iremove, ipord, lhs, iprec, iDC;
+  double epsM;
 };
 struct TriTables {
   int nq;
@@ -132,7 +133,7 @@ static int upload_phys(phb200_ctx *ctx, const phb200_step *st) {
   p.fct1 = st->almi / st->gami / st->alfi * st->Dtgl;
   p.matflg2 = c.matflg2; p.matflg3 = c.matflg3; p.idiff = c.idiff;
   p.iremove = c.iremoveStabTimeTerm; p.ipord = c.ipord;
-  p.lhs = st->lhs; p.iprec = st->iprec; p.pad = 0;
+  p.lhs = st->lhs; p.iprec = st->iprec; p.iDC = c.iDC; p.epsM = c.epsM;
   PHB_CHECK(cudaMemcpyToSymbolAsync(c_ph, &p, sizeof p, 0, cudaMemcpyHostToDevice, ctx->stream));
   return 0;
 }
@@ -353,10 +354,12 @@ __global__ void k_pack_nodes(int nshg, int numnp, const double *__restrict__ x, 
 // ---------------------------------------------------------------------------
 // per-(qp,element) state in shared memory
 enum { S_RHO = 0, S_U1, S_U2, S_U3, S_DRDP, S_DRDT, S_E1P, S_E3P, S_E4P, S_TAU1, S_TAU2, S_TAU3, S_MU, S_LAM, S_CON, S_NVAR };
+// discontinuity capturing (iDC /= 0) carries 7 more scalars per point: DC and g^ij (11,22,33,12,13,23)
+enum { S_DC = S_NVAR, S_GU = S_NVAR + 1, S_NVAR_DC = S_NVAR + 7 };
 
-template <int TILE_E, int NQ>
+template <int TILE_E, int NQ, int NV = S_NVAR>
 struct AsmSmem {
-  double st[NQ][S_NVAR][TILE_E];
+  double st[NQ][NV][TILE_E];
   double ri[NQ][20][TILE_E];
   double shg[12][TILE_E];
   double W[TILE_E];
@@ -506,8 +509,8 @@ __device__ __forceinline__ void finish_block(double (&acc)[5][5], int a, int b, 
 }
 
 // phase B' (e3wmlt.f:74-145): rl = W (N_a,i ri_i) + N_a W ri(16:20), one thread per (element, node)
-template <int TILE_E, int NQ>
-__device__ __forceinline__ void phase_bprime(const AsmSmem<TILE_E, NQ> &sm, int el, int sub, bool live, int nshg,
+template <int TILE_E, int NQ, class SM>
+__device__ __forceinline__ void phase_bprime(const SM &sm, int el, int sub, bool live, int nshg,
                                              double *__restrict__ res) {
       const int a = sub;  // 4 subs == 4 nodes
       const double W = sm.W[el];
@@ -530,8 +533,8 @@ __device__ __forceinline__ void phase_bprime(const AsmSmem<TILE_E, NQ> &sm, int 
 }
 
 // phase B: the 5x5 blocks of EGmass; one warp-task per (a,b) pair and 32-element half tile
-template <int TILE_E, int NQ, int LHS, int NWARP>
-__device__ __forceinline__ void phase_b(const AsmSmem<TILE_E, NQ> &sm, int warp, int lane, int tile, int numel,
+template <int TILE_E, int NQ, int LHS, int NWARP, bool DCON = false, class SM>
+__device__ __forceinline__ void phase_b(const SM &sm, int warp, int lane, int tile, int numel,
                                         size_t numel_pad, int nshg, const int *__restrict__ iBC,
                                         const double *__restrict__ BC, double *__restrict__ BDiag,
                                         double *__restrict__ EG, const int *__restrict__ eloc,
@@ -571,6 +574,26 @@ __device__ __forceinline__ void phase_b(const AsmSmem<TILE_E, NQ> &sm, int warp,
           for (int r = 0; r < 3; r++) {
             smuu[r] += mu * u[r];
             slamu[r] += lam * u[r];
+          }
+          if (DCON) {
+            // e3dc.f:300-325 + e3wmlt.f:154-223: W N_a,i (DC g^ij A0) N_b,j = W DC (g_a^T G g_b) A0
+            const double g1 = sm.st[q][S_GU + 0][le], g2 = sm.st[q][S_GU + 1][le], g3 = sm.st[q][S_GU + 2][le],
+                         g4 = sm.st[q][S_GU + 3][le], g5 = sm.st[q][S_GU + 4][le], g6 = sm.st[q][S_GU + 5][le];
+            const double sdc = W * sm.st[q][S_DC][le] *
+                               (ga[0] * (g1 * gb[0] + g4 * gb[1] + g5 * gb[2]) + ga[1] * (g4 * gb[0] + g2 * gb[1] + g6 * gb[2]) +
+                                ga[2] * (g5 * gb[0] + g6 * gb[1] + g3 * gb[2]));
+            const double e4p_ = sm.st[q][S_E4P][le];
+            acc[0][0] += sdc * drdp;
+            acc[0][4] += sdc * drdT;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+              acc[1 + r][0] += sdc * drdp * u[r];
+              acc[1 + r][1 + r] += sdc * rho;
+              acc[1 + r][4] += sdc * drdT * u[r];
+              acc[4][1 + r] += sdc * rho * u[r];
+            }
+            acc[4][0] += sdc * e1p;
+            acc[4][4] += sdc * e4p_;
           }
           const double Na = c_tet.N[q][a], Nb = c_tet.N[q][b];
           const double w[5] = {rho, rho * u[0], rho * u[1], rho * u[2], e3p};
@@ -700,6 +723,83 @@ __device__ __forceinline__ void tet_gij(const double d[3][3], double gij[6]) {
   gij[3] = d[0][0] * t1 + d[1][0] * t2 + d[2][0] * t3;
   gij[4] = d[0][1] * t1 + d[1][1] * t2 + d[2][1] * t3;
   gij[5] = d[0][2] * t1 + d[1][2] * t2 + d[2][2] * t3;
+}
+
+// Discontinuity capturing at one quadrature point: the iDC tails of e3mtrx (e3mtrx.f:232-298: A0DC, A0^-1, dV/dY),
+// of e3tau (e3tau.f:186-247: rTLS, raLS, the inverse metric g^ij) and e3DC (e3dc.f).  rt = strong residual before the
+// tau scaling, rs = after; A0v multiplies by A0.  Adds DC g^ij A0 Y,j to ri(1:15) and returns DC, g^ij.
+template <class A0F>
+__device__ __forceinline__ void dc_point(double rho, double T, const double u[3], double rk, double h, double cp,
+                                         double alfap, double betaT, const double gr[3][5], const double gij[6],
+                                         const double rt[5], const double rs[5], A0F A0v, double ri[20], double &DC,
+                                         double gu_out[6]) {
+  const double u1 = u[0], u2 = u[1], u3 = u[2];
+  const double s1 = 1.0 / (rho * rho * betaT * T);
+  const double cv = cp - (alfap * alfap * T / rho / betaT);
+  const double D1 = (rho * betaT) * (rho * betaT) * s1, D2 = -rho * alfap * rho * betaT * s1, D3 = rho / T,
+               D4 = (-rho * alfap) * (-rho * alfap) * s1 + (rho * cv / (T * T));
+  double f1 = 1.0 / (rho * cv * (T * T));
+  const double d = alfap * T / rho / betaT;
+  const double e1b = h - rk, e2b = e1b - d, e3b = e2b - cv * T;
+  const double e5b = e1b * e1b - 2 * e1b * d + 2 * rk * cv * T + cp * T / rho / betaT;
+  double Ai[15];
+  Ai[0] = e5b * f1; Ai[1] = (u1 * u1 + cv * T) * f1; Ai[2] = (u2 * u2 + cv * T) * f1; Ai[3] = (u3 * u3 + cv * T) * f1;
+  Ai[4] = f1; Ai[5] = u1 * e3b * f1; Ai[6] = u2 * e3b * f1; Ai[7] = u3 * e3b * f1; Ai[8] = -e2b * f1;
+  Ai[9] = u1 * u2 * f1; Ai[10] = u3 * u1 * f1; Ai[11] = -u1 * f1; Ai[12] = u2 * u3 * f1; Ai[13] = -u2 * f1;
+  Ai[14] = -u3 * f1;
+  f1 = 1.0 / T;
+  const double f2 = f1 / T;
+  const double V1 = f1 / rho, V2 = -f1 * u1, V3 = f1, V4 = -f1 * u2, V6 = f1, V7 = -f1 * u3, V10 = f1,
+               V11 = -(h - rk) * f2, V12 = -f2 * u1, V13 = -f2 * u2, V14 = -f2 * u3, V15 = f2;
+  const double rTLS = rt[0] * (rs[0] * V1 + V2 * rs[1] + V4 * rs[2] + rs[3] * V7 + V11 * rs[4]) +
+                      rt[1] * (rs[1] * V3 + rs[3] * 0.0 + rs[4] * V12) + rt[2] * (rs[2] * V6 + V13 * rs[4]) +
+                      rt[3] * (rs[3] * V10 + V14 * rs[4]) + rt[4] * (V15 * rs[4]);
+  const double raLS = 2.0 * rt[3] * rt[4] * Ai[14] + 2.0 * rt[2] * rt[4] * Ai[13] + 2.0 * rt[0] * rt[1] * Ai[5] +
+                      2.0 * rt[1] * rt[2] * Ai[9] + 2.0 * rt[1] * rt[3] * Ai[10] + 2.0 * rt[0] * rt[2] * Ai[6] +
+                      2.0 * rt[2] * rt[3] * Ai[12] + 2.0 * rt[1] * rt[4] * Ai[11] + 2.0 * rt[0] * rt[3] * Ai[7] +
+                      2.0 * rt[0] * rt[4] * Ai[8] + rt[0] * rt[0] * Ai[0] + rt[1] * rt[1] * Ai[1] + rt[2] * rt[2] * Ai[2] +
+                      rt[3] * rt[3] * Ai[3] + rt[4] * rt[4] * Ai[4];
+  // g^ij: inverse of the metric tensor (compressible order of gij: 11,12,22,13,23,33)
+  const double a1 = gij[0], a2 = gij[2], a3 = gij[5], a4 = gij[1], a5 = gij[3], a6 = gij[4];
+  const double detI = 1.0 / (a1 * a2 * a3 - a1 * a6 * a6 - a4 * a4 * a3 + a4 * a5 * a6 * 2.0 - a5 * a5 * a2);
+  const double gu[6] = {detI * (a2 * a3 - a6 * a6), detI * (a1 * a3 - a5 * a5), detI * (a1 * a2 - a4 * a4),
+                        detI * (a5 * a6 - a4 * a3), detI * (a4 * a6 - a5 * a2), detI * (a4 * a5 - a1 * a6)};
+  double A0g[3][5];
+#pragma unroll
+  for (int i = 0; i < 3; i++) A0v(gr[i], A0g[i]);
+  double yy[6];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    yy[i] = D1 * (gr[i][0] * gr[i][0]) + 2.0 * gr[i][0] * D2 * gr[i][4] + D3 * (gr[i][1] * gr[i][1]) +
+            D3 * (gr[i][2] * gr[i][2]) + D3 * (gr[i][3] * gr[i][3]) + D4 * (gr[i][4] * gr[i][4]);
+  auto cross = [&](const double *a, const double *b) {
+    return a[0] * D1 * b[0] + a[0] * D2 * b[4] + a[1] * D3 * b[1] + a[2] * D3 * b[2] + a[3] * D3 * b[3] +
+           a[4] * D2 * b[0] + a[4] * D4 * b[4];
+  };
+  yy[3] = cross(gr[0], gr[1]);
+  yy[4] = cross(gr[0], gr[2]);
+  yy[5] = cross(gr[1], gr[2]);
+  const double gnorm = 1.0 / (gu[0] * yy[0] + 2.0 * gu[3] * yy[3] + 2.0 * gu[4] * yy[4] + gu[1] * yy[1] +
+                              2.0 * gu[5] * yy[5] + gu[2] * yy[2] + c_ph.epsM);
+  double dc = 0.0;
+  if (c_ph.iDC == 1) {
+    const double fact = (c_ph.ipord == 2) ? 0.9 : (c_ph.ipord == 3 ? 0.75 : 1.0);
+    dc = fmax(0.0, (fact * sqrt(raLS * gnorm)) - (rTLS * gnorm));
+  } else if (c_ph.iDC == 2) {
+    dc = 2.0 * rTLS * gnorm;
+  } else if (c_ph.iDC == 3) {
+    const double fact = (c_ph.ipord == 2) ? 0.5 : 1.0;
+    dc = fmin(fmax(0.0, fact * sqrt(raLS * gnorm) - rTLS * gnorm), 2.0 * rTLS * gnorm);
+  }
+#pragma unroll
+  for (int m = 0; m < 5; m++) {
+    ri[m] += dc * (gu[0] * A0g[0][m] + gu[3] * A0g[1][m] + gu[4] * A0g[2][m]);
+    ri[5 + m] += dc * (gu[3] * A0g[0][m] + gu[1] * A0g[1][m] + gu[5] * A0g[2][m]);
+    ri[10 + m] += dc * (gu[4] * A0g[0][m] + gu[5] * A0g[1][m] + gu[2] * A0g[2][m]);
+  }
+  DC = dc;
+#pragma unroll
+  for (int k = 0; k < 6; k++) gu_out[k] = gu[k];
 }
 
 __device__ __forceinline__ void point_math(const double Y[5], const double At[5], const double gr[3][5],
@@ -924,16 +1024,17 @@ __global__ void __launch_bounds__(192, 2) k_asigmr_tet_ws(
 }
 
 // LHS: 0 residual only, 1 EBE tiles (ElmGMRe), 2 scatter into lhsK (ElmGMRs + fillsparseC)
-template <int TILE_E, int NQ, int LHS>
+template <int TILE_E, int NQ, int LHS, bool DCON = false>
 __global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
     int numel, size_t numel_pad, int nshg, int numnp, int ntiles, const int *__restrict__ ien,
     const double *__restrict__ aos, const int *__restrict__ iBC, const double *__restrict__ BC,
     double *__restrict__ res, double *__restrict__ BDiag, double *__restrict__ EG, const int *__restrict__ eloc,
     double *__restrict__ lhsK) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  AsmSmem<TILE_E, NQ> &sm = *reinterpret_cast<AsmSmem<TILE_E, NQ> *>(smem_raw);
+  using SM = AsmSmem<TILE_E, NQ, DCON ? S_NVAR_DC : S_NVAR>;
+  SM &sm = *reinterpret_cast<SM *>(smem_raw);
   const int tid = threadIdx.x;
-  double *stage = (LHS == 2) ? reinterpret_cast<double *>(smem_raw + sizeof(AsmSmem<TILE_E, NQ>)) + (tid >> 5) * STAGE_DBL
+  double *stage = (LHS == 2) ? reinterpret_cast<double *>(smem_raw + sizeof(SM)) + (tid >> 5) * STAGE_DBL
                              : nullptr;
   const int el = tid % TILE_E;  // element within tile
   const int sub = tid / TILE_E; // 0..3: quadrature point (phase A) / node (phase B')
@@ -1098,6 +1199,11 @@ __global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
       const double tau1 = 0.125 * fact / (rho * (gij[0] + gij[2] + gij[5])) * c_ph.taucfct;
       tau2 = 1.0 / fact;
       const double tau3 = tau2 / cv * c_ph.temper;
+      double rt[5];
+      if (DCON) {
+#pragma unroll
+        for (int m = 0; m < 5; m++) rt[m] = L[m];  // rLyitemp (e3tau.f:177)
+      }
       L[0] *= tau1; L[1] *= tau2; L[2] *= tau2; L[3] *= tau2; L[4] *= tau3;
       // ri += A_i tau L (e3ls.f:352-457): A_i v = u_i A0 v + w v[i+1] + e_{i+1} v[0] + e_5 u_i v[0]
       A0v(L, tmpv);
@@ -1107,6 +1213,15 @@ __global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
         for (int m = 0; m < 5; m++) ri[5 * i + m] += u[i] * tmpv[m] + w[m] * L[1 + i];
         ri[5 * i + 1 + i] += L[0];
         ri[5 * i + 4] += u[i] * L[0];
+      }
+      if (DCON) {  // e3.f:217-222
+        double dcv, gu[6];
+        dc_point(rho, T, u, rk, h, cp, alfap, betaT, gr, gij, rt, L, A0v, ri, dcv, gu);
+        if (LHS) {
+          sm.st[q][S_DC][el] = dcv;
+#pragma unroll
+          for (int k = 0; k < 6; k++) sm.st[q][S_GU + k][el] = gu[k];
+        }
       }
       if (NQ == 1) {
         // e3juel (e3juel.f:50,98-151): exact tet mass, rl_a += A0 (W/(15 Qwt)) (ac_a + sum_b ac_b)
@@ -1157,7 +1272,7 @@ __global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
     }
     __syncthreads();
     phase_bprime<TILE_E, NQ>(sm, el, sub, live, nshg, res);
-    if (LHS) phase_b<TILE_E, NQ, LHS, TILE_E * 4 / 32>(sm, tid >> 5, tid & 31, tile, numel, numel_pad, nshg, iBC, BC, BDiag, EG, eloc, lhsK, stage);
+    if (LHS) phase_b<TILE_E, NQ, LHS, TILE_E * 4 / 32, DCON>(sm, tid >> 5, tid & 31, tile, numel, numel_pad, nshg, iBC, BC, BDiag, EG, eloc, lhsK, stage);
     __syncthreads();
   }
 }
@@ -1887,11 +2002,12 @@ int phb_alloc_eg(phb200_ctx *ctx) {
   return 0;
 }
 
-template <int TILE_E, int NQ, int LHS>
+template <int TILE_E, int NQ, int LHS, bool DCON = false>
 static int launch_asigmr(phb200_ctx *ctx) {
   const phb200_common &c = ctx->c;
-  size_t smem = sizeof(AsmSmem<TILE_E, NQ>) + (LHS == 2 ? (TILE_E * 4 / 32) * STAGE_DBL * sizeof(double) : 0);
-  auto kern = k_asigmr_tet<TILE_E, NQ, LHS>;
+  size_t smem = sizeof(AsmSmem<TILE_E, NQ, DCON ? S_NVAR_DC : S_NVAR>) +
+                (LHS == 2 ? (TILE_E * 4 / 32) * STAGE_DBL * sizeof(double) : 0);
+  auto kern = k_asigmr_tet<TILE_E, NQ, LHS, DCON>;
   static bool configured = false;
   if (!configured) {
     PHB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2118,6 +2234,10 @@ __global__ void __launch_bounds__(128) k_asires(int tab, int numel, size_t numel
 // interior part of ItrRes (itrres.f:58-92): d_rmes += modified residual of d_yp ([5][nshg], {u,v,w,p,T});
 // the node records must hold the base state (phb_elmgmre packs them)
 int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres) {
+  if (ctx->c.iDC != 0) {
+    fprintf(stderr, "phb200: itrres: iDC=%d is not built for the matrix-free flavour\n", ctx->c.iDC);
+    return 1;
+  }
   const phb200_common &c = ctx->c;
   cudaStream_t s = ctx->stream;
   const int nq = c.nint[0];
@@ -2215,7 +2335,22 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   // mode 3 (matrix-free flavour, itrdrv.f:496-498: lhs=0, iprec per LHSupd): the block diagonal is built
   // directly (e3bdg, e3.f:258-285) = the (a,a) blocks of what EGmass would hold
   const int mode = (st->lhs == 1) ? (sparse ? 2 : 1) : ((st->iprec != 0) ? 3 : 0);
-  if (ctx->numel_tet > 0) {
+  if (c.iDC != 0) {
+    // discontinuity capturing (e3dc.f): built into the phase A/B tet kernel (not the warp-specialised one)
+    if (!ctx->gen.empty() || mode == 3) {
+      fprintf(stderr, "phb200: elmgmr: iDC=%d is built for tet blocks of the EBE / block-CSR flavours only\n", c.iDC);
+      return 1;
+    }
+    if (nq == 4) {
+      if (mode == 1) PHB_TRY((launch_asigmr<32, 4, 1, true>(ctx)));
+      else if (mode == 2) PHB_TRY((launch_asigmr<32, 4, 2, true>(ctx)));
+      else PHB_TRY((launch_asigmr<32, 4, 0, true>(ctx)));
+    } else {
+      if (mode == 1) PHB_TRY((launch_asigmr<32, 1, 1, true>(ctx)));
+      else if (mode == 2) PHB_TRY((launch_asigmr<32, 1, 2, true>(ctx)));
+      else PHB_TRY((launch_asigmr<32, 1, 0, true>(ctx)));
+    }
+  } else if (ctx->numel_tet > 0) {
     static const bool use_ws = !(getenv("PHB200_ASM_WS") && atoi(getenv("PHB200_ASM_WS")) == 0);
     if (nq == 4 && use_ws && ctx->tet_uniform_rule) {
       if (mode == 1) PHB_TRY((launch_asigmr_ws<1>(ctx)));

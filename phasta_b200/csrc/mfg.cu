@@ -92,6 +92,10 @@ int phb_itrres(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres) 
 // ElmMFG (elmmfg.f:60-250): res (ires=3 == the ElmGMRe residual), e3bdg block diagonal when iprec/=0, and the
 // modified residual of the base state
 int phb_elmmfg(phb200_ctx *ctx, const phb200_step *st) {
+  if (ctx->c.iDC != 0) {
+    fprintf(stderr, "phb200: elmmfg: iDC=%d is not built for the matrix-free flavour\n", ctx->c.iDC);
+    return 1;
+  }
   phb200_step s2 = *st;
   s2.lhs = 0;  // itrdrv.f:496
   PHB_TRY(phb_elmgmre(ctx, &s2, 0));

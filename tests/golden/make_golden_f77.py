@@ -30,7 +30,7 @@ from f77np import Program, scan_functions  # noqa: E402
 
 REF = "/root/reference/phSolver"
 COMP = ["e3.f", "e3ivar.f", "getthm.f", "getdiff.f", "e3mtrx.f", "e3conv.f", "e3visc.f", "e3ls.f", "e3tau.f",
-        "e3massr.f", "e3juel.f", "e3massl.f", "e3wmlt.f", "e3bdg.f", "e3q.f", "e3qvar.f", "e3b.f", "e3bvar.f",
+        "e3massr.f", "e3juel.f", "e3massl.f", "e3wmlt.f", "e3bdg.f", "e3dc.f", "e3q.f", "e3qvar.f", "e3b.f", "e3bvar.f",
         "bc3lhs.f", "bc3res.f", "bc3bdg.f", "bc3per.f", "i3lu.f", "i3pre.f", "itrbc.f", "asigmr.f", "asiq.f",
         "asbmfg.f", "asires.f", "asimfg.f", "localt.f", "shuffle.f", "asaugmr.f", "sparseap.f", "spsi3pre.f",
         "itrPC.f", "rstat.f"]

@@ -11,6 +11,11 @@ CASES = {
     "tet_allbc": ((3, 3, 2), dict(bc="mixed", ibksiz=16, etol=1e-6), ("elmgmre", "solgmre")),
     # every velocity code 1..7, density and pressure+temperature codes on interior nodes (bc3LHS/bc3Res/bc3BDg branches)
     "tet_allcodes": ((4, 4, 3), dict(bc="allcodes", ibksiz=50, etol=1e-6), ("elmgmre", "solgmre", "solgmrs")),
+    # discontinuity capturing (e3dc.f): iDC = 1 (the DC viscosity of e3dc.f:208-222), 2 and 3
+    "tet_dc1": ((3, 3, 2), dict(bc="channel", ibksiz=16, iDC=1, etol=1e-6), ("elmgmre", "solgmre")),
+    "tet_dc2": ((3, 2, 2), dict(bc="channel", ibksiz=64, iDC=2), ("elmgmre",)),
+    "tet_dc3": ((3, 2, 2), dict(bc="channel", ibksiz=64, iDC=3), ("elmgmre", "elmgmre0")),
+    "hex_dc1": ((2, 2, 2), dict(bc="channel", topo="hex", ibksiz=8, iDC=1), ("elmgmre",)),
     "tet_1pt_nodiff": ((3, 2, 2), dict(bc="channel", ibksiz=64, rule=1, idiff=0, etol=1e-6), ("elmgmre", "solgmre")),
     "tet_sutherland": ((2, 2, 2), dict(bc="channel", ibksiz=64, matflg2=1, etol=1e-6), ("elmgmre",)),
     "tet_resonly": ((3, 2, 2), dict(bc="channel", ibksiz=16, boundary=True, natural="mixed"), ("elmgmre0",)),

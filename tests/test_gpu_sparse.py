@@ -105,3 +105,31 @@ def test_solgmrs_partitioned():
         assert rel_l2(res, op.res) < 1e-10
         assert rel_l2(Dy, op.Dy) < 1e-8
     [g.close() for g in gs]
+
+
+@pytest.mark.parametrize("iDC,rule", [(1, 2), (3, 2), (2, 1)])
+def test_discontinuity_capturing_in_both_flavours(iDC, rule):
+    """e3dc.f (iDC = 1, 2, 3): the DC flux in the residual and DC g^ij A0 in the tangent, on a larger mesh than
+    the reference-Fortran fixtures (tests/golden/f77_tet_dc*.npz), EBE and block-CSR flavours, 4-pt and 1-pt rules."""
+    case = make_case(7, 6, 5, bc="allcodes", boundary=True, natural="mixed", iDC=iDC, rule=rule, etol=1e-6)
+    o = make_oracle(case)
+    o.ElmGMRe()
+    op = o.parts[0]
+    g = gpu(case)
+    y, ac = case[3][0]
+    out = g.ElmGMRe(y, ac, want_egmass=True)
+    assert rel_l2(out["res"], op.res) < 1e-10
+    assert rel_l2(out["BDiag"], op.BDiag) < 1e-10
+    assert rel_l2(out["EGmass"], op.EGmass) < 1e-10
+    o2 = make_oracle(case)
+    o2.genadj()
+    iKs, _ = o2.SolGMRs()
+    g.genadj()
+    res, Dy = g.SolGMRs(y, ac)
+    assert g.iKs == iKs
+    assert rel_l2(Dy, o2.parts[0].Dy) < 1e-8
+    g.close()
+    # and it is not a no-op on this state
+    o0 = make_oracle(make_case(7, 6, 5, bc="allcodes", boundary=True, natural="mixed", iDC=0, rule=rule, etol=1e-6))
+    o0.ElmGMRe()
+    assert rel_l2(op.res, o0.parts[0].res) > 1e-3
