@@ -87,45 +87,71 @@ def ncu_traffic(kind):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region."""
+    """SM clock + throttle reasons during the timed region: NVML (pynvml, ~5 ms period) when importable,
+    else `nvidia-smi` polling."""
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+             0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index = index
         self.stop_evt = threading.Event()
-        self.rows = []
+        self.sm, self.smax, self.reasons = [], 0.0, set()
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
 
-    def run(self):
+    def _nvml(self):
+        nv = self.nv
+        while not self.stop_evt.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, nm in self.NAMES.items():
+                    if mask & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_evt.wait(0.005)
+
+    def _smi(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_evt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True,
                                      timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                r = [c.strip() for c in out.split(",")]
+                self.sm.append(float(r[0]))
+                self.smax = max(self.smax, float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
             except Exception:
                 pass
-            self.stop_evt.wait(0.2)
+            self.stop_evt.wait(0.1)
+
+    def run(self):
+        (self._nvml if self.nv else self._smi)()
 
     def summary(self):
         self.stop_evt.set()
         self.join(timeout=3)
-        sm, smax, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                smax = max(smax, float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax or None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 def build_part(workload, rank, world):
@@ -455,7 +481,6 @@ def main():
     barrier()
     asm_ms = maxrank(g.elapsed_ms(0, 1)) / args.steps
     launches = g.launches() - l0
-    clocks = sampler.summary() if rank == 0 else {}
     value = numel_total / (asm_ms * 1e-3)
 
     # per-kernel-class share (events around every launch; separate pass)
@@ -608,6 +633,8 @@ def main():
            "h2d_bytes_per_step": int(2 * y.nbytes), "d2h_bytes_per_step": int(y.nbytes), "ms_per_step": e2e_ms,
            "api": "phb200_elmgmre (host y, ac in; host res out; EGmass/BDiag stay in HBM)"}
 
+    # the sampler ran through every timed leg above (assembly, Ap, solves, e2e): median SM clock under load
+    clocks = sampler.summary() if rank == 0 else {}
     if rank == 0:
         hbm, src = peaks()
         elem_per_launch = part.numel
