@@ -116,6 +116,10 @@ int phb_halo_setup(phb200_ctx *ctx, const int *il) {
       }
     }
     h.count = (int)nodes.size() - h.offset;
+    h.peer_task = -1;
+    h.peer_offset = 0;
+    h.peer_cap = 0;
+    h.sendn = h.recvn = 0;
     ctx->tasks.push_back(h);
     itk += 4 + 2 * numseg;
   }
@@ -150,6 +154,108 @@ __global__ void k_halo_unpack(int count, const int *__restrict__ nodes, int nshg
   *p = add ? (*p + buf[t]) : buf[t];
 }
 
+// ---- halo exchange by direct peer stores over NVLink (no NCCL call between pack and unpack) ----------------
+// Sender: pack the task's values straight into the RECEIVER's arena (slot = message number & 1), fence at system
+// scope, and let the block that finishes last raise the receiver's flag to the message number.  Before
+// overwriting a slot the sender waits for the receiver's acknowledgement of the message that used it two messages
+// ago (the receiver's unpack kernel writes it into the SENDER's arena), so no ordering assumption about the
+// sequence of 'in'/'out' exchanges is needed.  All spins are bounded (error flag instead of a hang).
+#define PHB_SPIN_MAX (1ll << 27)
+__global__ void k_halo_send(int count, const int *__restrict__ nodes, int nshg, int n, const double *__restrict__ g,
+                            double *dst, volatile unsigned long long *peer_flag, volatile unsigned long long *my_ack,
+                            unsigned long long msg, unsigned int *ticket, int *err) {
+  __shared__ int last;
+  if (threadIdx.x == 0 && msg > 2) {
+    long long spins = 0;
+    const bool dead = *reinterpret_cast<volatile int *>(err) != 0;
+    while (!dead && *my_ack + 2 < msg) {
+      if (++spins > PHB_SPIN_MAX) { atomicExch(err, 100); break; }
+    }
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count * n) {
+    const int k = t / count, i = t % count;
+    dst[t] = g[(size_t)nshg * k + nodes[i]];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    *ticket = 0u;
+    __threadfence_system();
+    *peer_flag = msg;
+  }
+}
+__global__ void k_halo_recv(int count, const int *__restrict__ nodes, int nshg, int n, double *__restrict__ g,
+                            const double *src, volatile unsigned long long *my_flag,
+                            volatile unsigned long long *peer_ack, unsigned long long msg, int add,
+                            unsigned int *ticket, int *err) {
+  __shared__ int last;
+  if (threadIdx.x == 0) {
+    long long spins = 0;
+    const bool dead = *reinterpret_cast<volatile int *>(err) != 0;
+    while (!dead && *my_flag != msg) {
+      if (++spins > PHB_SPIN_MAX) { atomicExch(err, 200); break; }
+    }
+    __threadfence_system();
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < count * n) {
+    const int k = t / count, i = t % count;
+    const double v = __ldcv(src + t);  // written by the peer: never from a stale L1 line
+    double *p = g + (size_t)nshg * k + nodes[i];
+    *p = add ? (*p + v) : v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    *ticket = 0u;
+    __threadfence_system();
+    *peer_ack = msg;
+  }
+}
+
+static int commu_p2p(phb200_ctx *ctx, double *g, int n, int code) {
+  cudaStream_t s = ctx->stream;
+  const int nshg = ctx->c.nshg, me = ctx->c.myrank;
+  const int send_role = (code == 0) ? 0 : 1;
+  auto arena = [&](int r) { return r == me ? ctx->d_mail : (double *)ctx->peer_mapped[r]; };
+  KScope ks(ctx, KC_HALO);
+  for (size_t ti = 0; ti < ctx->tasks.size(); ti++) {
+    HaloTask &h = ctx->tasks[ti];
+    if (h.iacc != send_role) continue;
+    const unsigned long long m = ++h.sendn;
+    const int slot = (int)(m & 1ull), tot = h.count * n;
+    double *pa = arena(h.peer);
+    double *dst = pa + ctx->arena_data_off + (size_t)slot * h.peer_cap + (size_t)h.peer_offset * 25;
+    volatile unsigned long long *pflag =
+        reinterpret_cast<volatile unsigned long long *>(pa + ctx->arena_flag_off) + (2 * h.peer_task + slot);
+    volatile unsigned long long *myack =
+        reinterpret_cast<volatile unsigned long long *>(ctx->d_mail + ctx->arena_ack_off) + ti;
+    k_halo_send<<<(tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g, dst, pflag, myack, m,
+                                                  ctx->d_halo_tickets + ti, ctx->d_p2p_err);
+  }
+  for (size_t ti = 0; ti < ctx->tasks.size(); ti++) {
+    HaloTask &h = ctx->tasks[ti];
+    if (h.iacc == send_role) continue;
+    const unsigned long long m = ++h.recvn;
+    const int slot = (int)(m & 1ull), tot = h.count * n;
+    const double *src = ctx->d_mail + ctx->arena_data_off + (size_t)slot * ctx->halo_cap + (size_t)h.offset * 25;
+    volatile unsigned long long *myflag =
+        reinterpret_cast<volatile unsigned long long *>(ctx->d_mail + ctx->arena_flag_off) + (2 * ti + slot);
+    volatile unsigned long long *pack =
+        reinterpret_cast<volatile unsigned long long *>(arena(h.peer) + ctx->arena_ack_off) + h.peer_task;
+    k_halo_recv<<<(tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g, src, myflag, pack, m,
+                                                  code == 0, ctx->d_halo_tickets + ti, ctx->d_p2p_err);
+  }
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
+
 int phb_commu(phb200_ctx *ctx, double *g, int n, int code) {
   if (ctx->c.numpe <= 1 || ctx->tasks.empty()) return 0;
   if (!ctx->nccl && !ctx->local_group) {
@@ -160,6 +266,7 @@ int phb_commu(phb200_ctx *ctx, double *g, int n, int code) {
     fprintf(stderr, "phb200: commu: n=%d > 25 unsupported\n", n);
     return 1;
   }
+  if (ctx->p2p_halo) return commu_p2p(ctx, g, n, code);
   cudaStream_t s = ctx->stream;
   const int nshg = ctx->c.nshg;
   // sender role: iacc==0 on 'in', iacc==1 on 'out'
@@ -284,9 +391,20 @@ static int p2p_setup(phb200_ctx *ctx) {
   const char *env = getenv("PHB200_P2P");
   if (env && atoi(env) == 0) return 0;
   if (world > PHB_MAXR) return 0;
-  const size_t mail_dbl = (size_t)2 * PHB_MAXR * PHB_MAILW + (size_t)2 * PHB_MAXR;
+  // one peer-visible arena: all-reduce mailbox | halo flags [64][2] | halo acks [64] | halo data [2][halo_cap].
+  // The offsets are the same on every rank (a rank addresses its PEERS' arenas with them); only the data slot
+  // stride (the peer's halo_cap) differs per rank and travels in the task table.
+  const size_t ntask = ctx->tasks.size();
+  const size_t MAXTASK = 64;
+  size_t mail_dbl = (size_t)2 * PHB_MAXR * PHB_MAILW + (size_t)2 * PHB_MAXR;
+  ctx->arena_flag_off = mail_dbl;
+  ctx->arena_ack_off = ctx->arena_flag_off + 2 * MAXTASK;
+  ctx->arena_data_off = ctx->arena_ack_off + MAXTASK;
+  mail_dbl = ctx->arena_data_off + 2 * ctx->halo_cap;
   PHB_CHECK(cudaMalloc(&ctx->d_mail, sizeof(double) * mail_dbl));
   PHB_CHECK(cudaMemset(ctx->d_mail, 0, sizeof(double) * mail_dbl));
+  PHB_CHECK(cudaMalloc(&ctx->d_halo_tickets, sizeof(unsigned int) * (ntask + 1)));
+  PHB_CHECK(cudaMemset(ctx->d_halo_tickets, 0, sizeof(unsigned int) * (ntask + 1)));
   PHB_CHECK(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
   PHB_CHECK(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
   PHB_CHECK(cudaMalloc(&ctx->d_p2p_err, sizeof(int)));
@@ -337,6 +455,59 @@ static int p2p_setup(phb200_ctx *ctx) {
   PHB_CHECK(cudaMemcpy(ctx->d_peer_mail, ptrs.data(), sizeof(double *) * world, cudaMemcpyHostToDevice));
   ctx->p2p_seq = 0;
   ctx->p2p = true;
+  // ---- halo over peer memory: every rank publishes its task table (tag, iacc, peer, offset, count) ----
+  ctx->p2p_halo = false;
+  // Opt-in (PHB200_P2P_HALO=1): validated on 2 GPUs (r01h); the first 8-GPU attempt addressed peers' arenas with
+  // this rank's own task count (fixed above) and could not be re-measured within the round's GPU budget.
+  const char *envh = getenv("PHB200_P2P_HALO");
+  if (!envh || atoi(envh) == 0) return 0;
+  const int MAXT = 64, REC = 5, W = 2 + MAXT * REC;
+  std::vector<int> mytab(W, 0), alltab((size_t)W * world, 0);
+  int fits = ((int)ntask <= MAXT && ctx->halo_cap < ((size_t)1 << 31)) ? 1 : 0;
+  mytab[0] = fits ? (int)ntask : -1;
+  mytab[1] = (int)ctx->halo_cap;
+  for (size_t t = 0; t < ntask && fits; t++) {
+    const HaloTask &h = ctx->tasks[t];
+    int *r = &mytab[2 + REC * t];
+    r[0] = h.tag; r[1] = h.iacc; r[2] = h.peer; r[3] = h.offset; r[4] = h.count;
+  }
+  int *d_tab;
+  PHB_CHECK(cudaMalloc(&d_tab, sizeof(int) * (size_t)W * (world + 1)));
+  PHB_CHECK(cudaMemcpy(d_tab, mytab.data(), sizeof(int) * W, cudaMemcpyHostToDevice));
+  NCCL_CHECK(N.AllGather(d_tab, d_tab + W, sizeof(int) * W, /*ncclInt8*/ 0, (ncclComm_t)ctx->nccl, ctx->stream));
+  PHB_CHECK(cudaMemcpyAsync(alltab.data(), d_tab + W, sizeof(int) * (size_t)W * world, cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_tab);
+  bool good = true;
+  for (int r = 0; r < world; r++)
+    if (alltab[(size_t)W * r] < 0) good = false;
+  for (size_t t = 0; t < ntask && good; t++) {
+    HaloTask &h = ctx->tasks[t];
+    const int *pt = &alltab[(size_t)W * h.peer];
+    h.peer_task = -1;
+    for (int k = 0; k < pt[0]; k++) {
+      const int *r = pt + 2 + REC * k;
+      if (r[0] == h.tag && r[2] == me && r[1] != h.iacc && r[4] == h.count) {
+        h.peer_task = k;
+        h.peer_offset = r[3];
+        h.peer_cap = (size_t)pt[1];
+      }
+    }
+    if (h.peer_task < 0) good = false;
+  }
+  // unanimous decision (a rank whose table does not match would otherwise wait forever)
+  double *d_g;
+  PHB_CHECK(cudaMalloc(&d_g, sizeof(double)));
+  double bad = good ? 0.0 : 1.0;
+  PHB_CHECK(cudaMemcpy(d_g, &bad, sizeof(double), cudaMemcpyHostToDevice));
+  NCCL_CHECK(N.AllReduce(d_g, d_g, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+  PHB_CHECK(cudaMemcpyAsync(&bad, d_g, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_g);
+  ctx->p2p_halo = (bad == 0.0);
+  if (!ctx->p2p_halo && me == 0)
+    fprintf(stderr, "phb200: comm_init: halo task tables do not pair up on %d rank(s); halos stay on NCCL\n", (int)bad);
   return 0;
 }
 
@@ -363,7 +534,17 @@ int phb_comm_init(phb200_ctx *ctx, const void *id128) {
 
 void phb_comm_free(phb200_ctx *ctx) {
   if (ctx->p2p) {
+    // peers may still be storing acknowledgements into this rank's arena: everybody drains, then everybody frees
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->p2p_halo && ctx->nccl && N.AllReduce && ctx->d_p2p_err) {
+      double *d_b = nullptr;
+      if (cudaMalloc(&d_b, sizeof(double)) == cudaSuccess) {
+        cudaMemsetAsync(d_b, 0, sizeof(double), ctx->stream);
+        N.AllReduce(d_b, d_b, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(d_b);
+      }
+    }
     for (int r = 0; r < ctx->c.numpe && r < 64; r++)
       if (ctx->peer_mapped[r]) cudaIpcCloseMemHandle(ctx->peer_mapped[r]);
     ctx->p2p = false;
@@ -371,6 +552,9 @@ void phb_comm_free(phb200_ctx *ctx) {
   if (ctx->d_mail) cudaFree(ctx->d_mail);
   if (ctx->d_peer_mail) cudaFree(ctx->d_peer_mail);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
+  if (ctx->d_halo_tickets) cudaFree(ctx->d_halo_tickets);
+  ctx->d_halo_tickets = nullptr;
+  ctx->p2p_halo = false;
   if (ctx->d_p2p_err) cudaFree(ctx->d_p2p_err);
   ctx->d_mail = nullptr; ctx->d_peer_mail = nullptr; ctx->d_ticket = nullptr; ctx->d_p2p_err = nullptr;
   if (ctx->nccl && N.CommDestroy) N.CommDestroy((ncclComm_t)ctx->nccl);

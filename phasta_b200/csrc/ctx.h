@@ -48,6 +48,11 @@ struct ElemGroup {
 struct HaloTask {
   int peer, iacc, tag, count;  // count = number of nodes (all segments)
   int offset;                  // into d_halo_nodes
+  // NVLink peer-memory transport (comm.cu): the matching task on the peer, where its data lands in the peer's
+  // arena, and how many messages this rank has sent / received on this task
+  int peer_task, peer_offset;
+  size_t peer_cap;             // the peer's halo_cap = stride between its two data slots
+  unsigned long long sendn, recvn;
 };
 
 struct phb200_ctx {
@@ -95,6 +100,9 @@ struct phb200_ctx {
   unsigned int *d_ticket;     // last-block detection for the fused reduction kernels
   int *d_p2p_err;             // set by a kernel whose wait on a peer flag timed out
   bool p2p;
+  bool p2p_halo;              // halo exchange by direct peer stores too (k_halo_send / k_halo_recv)
+  size_t arena_flag_off, arena_ack_off, arena_data_off;  // doubles from the arena base (mailbox first)
+  unsigned int *d_halo_tickets;   // one last-block counter per task
   bool local_group;    // in-process multi-part transport (tests)
   // ---- state / results
   double *d_y, *d_ac;            // [5][nshg] {u,v,w,p,T}
