@@ -31,6 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_ELEM_LHS = 52000.0     # hand count, 4-pt rule, lhs=1, incl. AsIq
+FLOP_PER_ELEM_INSTR = 51026.0   # counted while executing the reference Fortran (tests/golden/count_flops_f77.py)
 BYTES_PER_ELEM_LHS = 3310.0     # EGmass 3200 + ien 16 + node data/6
 BYTES_PER_ELEM_AP = 3215.0      # EBE Ap
 FP64_NOMINAL_TF = 40.0          # BASELINE.json north_star
@@ -651,7 +652,10 @@ def main():
                 "peak_source": "FP64 DFMA-chain microbenchmark run in this process "
                                                 "(MEASURED_PEAKS.json has no FP64 entry); nominal %.0f TF" % FP64_NOMINAL_TF,
                 "frac_of_nominal": (tf / FP64_NOMINAL_TF) if all_tets else None,
-                "flop_per_element": FLOP_PER_ELEM_LHS, "kernel_ms": kern_ms, "asiq_kernel_ms": asiq_ms,
+                "flop_per_element": FLOP_PER_ELEM_LHS, "flop_per_element_instrumented": FLOP_PER_ELEM_INSTR,
+                "frac_instrumented": (tf * FLOP_PER_ELEM_INSTR / FLOP_PER_ELEM_LHS / fp64_peak)
+                if (fp64_peak and all_tets) else None,
+                "kernel_ms": kern_ms, "asiq_kernel_ms": asiq_ms,
                 "hbm_GBps_algorithmic": elem_per_launch * BYTES_PER_ELEM_LHS / (kern_ms * 1e-3) / 1e9,
                 "hbm_peak_GBps": hbm, "hbm_peak_source": src}
         if "sparse" in extra:
