@@ -140,3 +140,72 @@ def test_timestep_partitioned():
         assert rel_l2(yg, o.parts[i].keep["y"]) < 1e-10
         assert rel_l2(yog, o.yold[i]) < 1e-10
     [g.close() for g in gs]
+
+
+# ------------------------------------------------------------------------------------------------
+# one whole step of itrdrv.f's flow sequence executed by the reference's own Fortran (f77np):
+# tests/golden/make_golden_step.py -> tests/golden/f77_step_*.npz
+def _step_fixture(name):
+    import os
+    import sys
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, gold)
+    from make_golden_step import build_case
+    from golden_cases import input_digest
+    z = np.load(os.path.join(gold, "f77_step_%s.npz" % name))
+    case, opt = build_case(name)
+    assert np.array_equal(z["digest"], input_digest(case)), "seeded generators drifted from the fixture"
+    params = case[0]
+    for k in ("almi", "alfi", "gami", "Dtgl"):
+        setattr(params, k, float(z[k]))        # what the reference's itrSetup derived from rhoinf / Delt
+    return z, case, opt
+
+
+STEP_CASES = ["be_channel", "genalpha_lhsupd2"]
+
+
+def test_itrsetup_scalars_in_the_fixtures():
+    z, _, opt = _step_fixture("genalpha_lhsupd2")
+    rho = opt["rhoinf"]
+    assert np.isclose(z["almi"], (3 - rho) / (1 + rho) / 2) and np.isclose(z["alfi"], 1 / (1 + rho))
+    assert np.isclose(z["gami"], 0.5 + z["almi"] - z["alfi"])
+    z, _, _ = _step_fixture("be_channel")
+    assert (float(z["almi"]), float(z["alfi"]), float(z["gami"])) == (1.0, 1.0, 1.0)
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_oracle_step_matches_reference_fortran(name):
+    """predictor, nitr x (SolGMRe, itrCorrect, itrBC) with LHSupd reuse, itrUpdate -- against itrPC.f / itrbc.f /
+    solgmr.f driven in itrdrv.f's order"""
+    from oracle.oracle_py import Oracle
+    z, case, opt = _step_fixture(name)
+    params, tables, parts, states = case
+    o = Oracle(parts, params, tables, [(y.copy(order="F"), ac.copy(order="F")) for y, ac in states])
+    st = o.TimeStep(nitr=opt["nitr"], ipred=opt["ipred"], LHSupd=opt["LHSupd"])
+    assert np.array_equal(st[:, 2].astype(int), z["iKs"]) and np.array_equal(st[:, 4].astype(int), z["lhs"])
+    p = o.parts[0]
+    assert rel_l2(p.keep["y"], z["y"]) < 1e-10 and rel_l2(o.yold[0], z["yold"]) < 1e-10
+    assert rel_l2(p.keep["ac"], z["ac"]) < 1e-9 and rel_l2(o.acold[0], z["acold"]) < 1e-9
+    assert np.allclose(st[:, 0], z["totres1"], rtol=1e-8)      # rstat's totres(1)
+
+
+# The generalized-alpha / LHSupd=2 fixture is pinned on the oracle above; its GPU run is left for the next round
+# (the round's GPU budget was spent before it could be measured, and an unmeasured GPU assertion is not added).
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", STEP_CASES[:1])
+def test_gpu_step_matches_reference_fortran(name):
+    from phasta_b200.solver import PhastaGPU
+    z, case, opt = _step_fixture(name)
+    params, tables, parts, states = case
+    g = PhastaGPU(parts[0], params, tables, device=0)
+    y, ac = states[0]
+    g.set_state(y, ac)
+    g.set_old_state(y, ac)
+    st = g.TimeStep(nitr=opt["nitr"], ipred=opt["ipred"], LHSupd=opt["LHSupd"])
+    diks = np.abs(st[:, 2].astype(int) - z["iKs"])
+    assert diks.max() <= 1, (st[:, 2], z["iKs"])     # a Krylov count next to the tolerance may flip by one
+    tol = 1e-9 if diks.max() == 0 else 1e-6
+    yg, acg, yog, acog = g.get_state(old=True)
+    assert rel_l2(yg, z["y"]) < tol and rel_l2(yog, z["yold"]) < tol
+    assert rel_l2(acg, z["ac"]) < max(tol, 1e-6)     # ac = (y - yold) Dtgl amplifies the round-off of y
+    g.close()
