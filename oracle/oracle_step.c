@@ -198,5 +198,6 @@ void orc_timestep(int nparts, orc_part *parts, double **y, double **ac, double *
     orc_itrbc(nparts, parts, y, ac, 1);
   }
   for (int m = 0; m < nparts; m++) orc_itrupdate(&parts[m], yold[m], acold[m], y[m], ac[m]);
+  orc_itrbc(nparts, parts, yold, acold, 1);                               /* itrdrv.f:652 */
   free(HBrg); free(eBrg); free(yBrg); free(Rcos); free(Rsin);
 }

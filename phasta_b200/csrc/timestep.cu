@@ -259,5 +259,6 @@ int phb_timestep(phb200_ctx *ctx, const phb200_step *st0, int ipred, int nitr, i
     PHB_TRY(phb_itrbc(ctx, 1));
   }
   PHB_TRY(phb_itrupdate(ctx, &st));
+  PHB_TRY(phb_itrbc_vec(ctx, ctx->d_yold, ctx->d_acold, 1));  // itrdrv.f:652
   return 0;
 }
