@@ -139,8 +139,32 @@ def main():
                 ok &= d < 1e-9
             print("   iKs oracle", st[:, 2].astype(int), "reference", r["iKs"])
             ok &= np.array_equal(st[:, 2].astype(int), r["iKs"])
+    case, yb, acb = run_itrbc_allcodes(prog)
+    if args.check:
+        from common import make_oracle
+        o = make_oracle(case)
+        o.itrBC()
+        same = np.array_equal(o.parts[0].keep["y"], yb) and np.array_equal(o.parts[0].keep["ac"], acb)
+        print("itrbc_allcodes: oracle bit-equal", same)
+        ok &= same
     if args.check:
         print("ALL OK" if ok else "MISMATCH")
+
+
+def run_itrbc_allcodes(prog):
+    """itrBC (itrbc.f) on a random state with every essential-BC code (velocity codes 1..7, density,
+    pressure, temperature, periodic slaves) -> tests/golden/f77_itrbc_allcodes.npz"""
+    from common import make_case
+    case = make_case(4, 4, 3, bc="allcodes", ibksiz=50)
+    params, tables, parts, states = case
+    mp = parts[0]
+    mg.set_commons(prog, params, tables, mp, 20)
+    y, ac = (mg.F(a) for a in states[0])
+    iBC = np.array(mp.iBC, dtype=np.int64)
+    prog.G["ires"] = 1
+    prog.call("itrbc", y, ac, iBC, mg.F(mp.BC), np.array(mp.iper, dtype=np.int64), np.zeros(1, dtype=np.int64))
+    np.savez_compressed(os.path.join(HERE, "f77_itrbc_allcodes.npz"), y=y, ac=ac, digest=input_digest(case))
+    return case, y, ac
 
 
 if __name__ == "__main__":
