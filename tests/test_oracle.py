@@ -115,7 +115,7 @@ def test_i3lu_is_the_reference_factorisation():
     assert rel_l2(z, np.einsum("nij,nj->ni", Um, x)) < 1e-9
 
 
-@pytest.mark.parametrize("nparts,max_seg,topo", [(2, 0, "tet"), (4, 7, "tet"), (2, 5, "mixed")])
+@pytest.mark.parametrize("nparts,max_seg,topo", [(2, 0, "tet"), (4, 7, "tet"), (2, 5, "mixed"), (8, 0, "tet")])
 def test_partitioned_equals_serial(nparts, max_seg, topo):
     kw = dict(bc="channel", etol=1e-8, Kspace=30, topo=topo)
     ser = make_case(8, 4, 3, **kw)
@@ -143,6 +143,37 @@ def test_partitioned_equals_serial(nparts, max_seg, topo):
             else:
                 # Dy on slave rows is U^-1 of a zero row with identity LU = 0; compare owned rows
                 assert rel_l2(getattr(pp, name)[own], glob[mp.gnode[own]]) < tol
+
+
+def test_eight_way_slabs_sparse_flavour_and_incompressible():
+    """the decomposition bench.py uses on 8 GPUs (x-slabs, chain of master/slave planes): SolGMRs and the
+    incompressible ElmGMR of 8 parts against the serial run"""
+    from phasta_b200 import IncompParams
+    kw = dict(bc="channel", etol=1e-8, Kspace=30, minIters=0)
+    ser, par = make_case(8, 3, 3, **kw), make_case(8, 3, 3, nparts=8, **kw)
+    os_, op_ = make_oracle(ser), make_oracle(par)
+    os_.genadj()
+    op_.genadj()
+    assert os_.SolGMRs()[0] == op_.SolGMRs()[0]
+    ip = IncompParams()
+    os_.IncElmGMR(ip)
+    op_.IncElmGMR(ip)
+    gs = ser[2][0].gnode
+    ref_dy = np.zeros((gs.max() + 1, 5))
+    ref_dy[gs] = os_.parts[0].Dy
+    ref_r4 = np.zeros((gs.max() + 1, 4))
+    ref_r4[gs] = os_.parts[0].res4
+    for pp, mp in zip(op_.parts, par[2]):
+        own = np.ones(mp.nshg, bool)
+        il, itk = mp.ilwork, 1
+        for _ in range(il[0]):
+            if il[itk + 1] == 0:
+                for s in range(il[itk + 3]):
+                    b, ln = il[itk + 4 + 2 * s], il[itk + 5 + 2 * s]
+                    own[b - 1:b - 1 + ln] = False
+            itk += 4 + 2 * il[itk + 3]
+        assert rel_l2(pp.Dy[own], ref_dy[mp.gnode[own]]) < 1e-9
+        assert rel_l2(pp.res4[own], ref_r4[mp.gnode[own]]) < 1e-12
 
 
 def test_solgmre_reduces_the_true_residual():
