@@ -10,7 +10,9 @@
  * and no Fortran compiler exists here, so the reference's own unmodified
  * Fortran sources are executed by the f77np interpreter (tests/golden/f77np.py,
  * make_golden_f77.py) and this oracle reproduces their outputs (res bit for
- * bit, EGmass/BDiag/Dy to round-off, colm/rowp exactly; tests/test_golden_f77.py).
+ * bit, EGmass/BDiag/Dy to round-off, colm/rowp exactly; tests/test_golden_f77.py);
+ * the halo exchange against the executed ctypes.f + commu.f (tests/test_reference_commu.py), whole time steps
+ * against itrdrv.f's sequence (tests/test_timestep.py), the incompressible flavour (tests/test_incomp.py).
  * Quadrature/shape tables are pinned against the reference's own C generators
  * (oracle/_ref, tests/golden/tables_ref.npz).
  *

@@ -1424,7 +1424,7 @@ class Program:
 
     def _exec_call(self, s, env):
         _, name, args, where = s
-        actuals, writeback = [], []
+        actuals, writeback, elem_out = [], [], []
         callee = self.units.get(name)
         try:
             for k, a in enumerate(args):
@@ -1442,6 +1442,9 @@ class Program:
                     if callee is not None and k < len(callee.args):
                         d = callee.decls.get(callee.args[k])
                         wants_array = d is not None and d.dims is not None
+                    elif name in self.stubs:
+                        # a python stub may ask for sequence association too (MPI buffers: `global(isgbeg,1)`)
+                        wants_array = k in getattr(self.stubs[name], "array_args", ())
                     if isinstance(arr, np.ndarray) and wants_array:
                         idx = _conv_index(eval(a[2], HELPERS, env), env.lbounds(a[1]))
                         off = int(np.ravel_multi_index(idx, arr.shape, order="F"))
@@ -1450,6 +1453,9 @@ class Program:
                         actuals.append(arr.reshape(-1, order="F")[off:])
                     else:
                         actuals.append(eval(a[3], HELPERS, env))
+                        if name in self.stubs and isinstance(arr, np.ndarray):
+                            # an array element as an output argument of a python stub (sevsegtype(itask,1))
+                            elem_out.append((k, a[1], eval(a[2], HELPERS, env)))
                 else:
                     actuals.append(eval(a[1], HELPERS, env))
             if name in self.stubs:
@@ -1458,6 +1464,9 @@ class Program:
                     for k, nm in writeback:
                         if k in out:
                             self._assign(env, nm, None, out[k])
+                    for k, nm, idx in elem_out:
+                        if k in out:
+                            self._assign(env, nm, idx, out[k])
                 return
             if callee is None:
                 raise NameError("f77np: subroutine %r is not loaded" % name)
