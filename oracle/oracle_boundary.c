@@ -1,8 +1,11 @@
 /*
  * oracle_boundary.c -- TEST INFRASTRUCTURE ONLY (see phasta_oracle.h).
- * Boundary-element flux AsBMFG -> e3b -> e3bvar for tets with triangular
- * boundary faces (compressible/asbmfg.f:1-66, e3b.f:1-386, e3bvar.f:1-374),
- * ires=1, Navier=1, iLHScond=0.
+ * Boundary-element flux AsBMFG -> e3b -> e3bvar (compressible/asbmfg.f:1-66,
+ * e3b.f:1-386, e3bvar.f:1-374), ires=1, Navier=1, iLHScond=0, for linear
+ * tets (triangular face, lcsyst 1), hexes (quadrilateral face, lcsyst 2) and
+ * wedges with a triangular (lcsyst 3) or quadrilateral (lcsyst 4) boundary
+ * face: lnode from getbnodes (common/hierarchic.f:90-190), the per-topology
+ * normals and WdetJb of e3bvar.f:139-165.
  */
 #include "oracle_internal.h"
 #include <math.h>
@@ -68,18 +71,30 @@ void orc_asbmfg(const orc_part *p, int iblk, double *res) {
   int iel = lc[0], lcsyst = lc[2], nenl = lc[4], nenbl = lc[5], nshl = lc[8],
       nshlb = lc[9];
   int npro = lc[10] - iel;
-  if (lcsyst != 1 || nshl != 4 || nshlb != 3 || nenbl != 3) {
-    fprintf(stderr, "orc_asbmfg: only tet/tri-face boundary blocks restated\n");
+  if (lcsyst == 3) lcsyst = nenbl; /* elmgmr.f:191 */
+  /* getbnodes (hierarchic.f:102-168), ipord = 1 */
+  int lnode[5] = {0, 1, 2, 3, 4};
+  int ok = (lcsyst == 1 && nshl == 4 && nshlb == 3 && nenbl == 3) ||
+           (lcsyst == 2 && nshl == 8 && nshlb == 4 && nenbl == 4) ||
+           (lcsyst == 3 && nshl == 6 && nshlb == 3 && nenbl == 3) ||
+           (lcsyst == 4 && nshl == 6 && nshlb == 4 && nenbl == 4);
+  if (!ok) {
+    fprintf(stderr, "orc_asbmfg: boundary block lcsyst %d nshl %d nshlb %d not restated\n", lcsyst, nshl, nshlb);
     abort();
+  }
+  if (lcsyst == 4) {
+    lnode[2] = 4;
+    lnode[3] = 5;
+    lnode[4] = 2;
   }
   int ngaussb = c->nintb[lcsyst - 1];
   const int *ien = p->ienb + p->ienb_off[iblk];
   const int *iBCB = p->iBCB + p->iBCB_off[iblk];     /* (npro,2)         */
   const double *BCB = p->BCB + p->BCB_off[iblk];     /* (npro,nshlb,6)   */
   int nshg = c->nshg;
-  double(*rl)[5][6] = calloc((size_t)npro, sizeof *rl);
+  double(*rl)[9][6] = calloc((size_t)npro, sizeof *rl);
   for (int e = 0; e < npro; e++) {
-    double yl[5][6], xlb[5][4];
+    double yl[9][6], xlb[9][4];
     for (int n = 1; n <= nshl; n++) {
       int A = ien[e + (size_t)npro * (n - 1)] - 1;
       yl[n][1] = p->y[A + (size_t)nshg * 3];
@@ -93,14 +108,15 @@ void orc_asbmfg(const orc_part *p, int iblk, double *res) {
     int ibcb = iBCB[e];
     for (int intp = 1; intp <= ngaussb; intp++) {
       if (QWTB(c, lcsyst, intp) == 0.0) continue;
-      double shape[5], shdrv[4][5];
+      double shape[9], shdrv[4][9];
       for (int n = 1; n <= nshl; n++) {
         shape[n] = SHPB(p, lcsyst, n, intp);
         for (int i = 1; i <= 3; i++) shdrv[i][n] = SHGLB(p, lcsyst, i, n, intp);
       }
       /* ---- e3bvar (e3bvar.f:78-356) ---- */
       double pres = 0, u1 = 0, u2 = 0, u3 = 0, T = 0;
-      for (int n = 1; n <= nshlb; n++) { /* lnode(n)=n (hierarchic.f:103-105) */
+      for (int k = 1; k <= nshlb; k++) {
+        int n = lnode[k];
         pres += shape[n] * yl[n][1];
         u1 += shape[n] * yl[n][2];
         u2 += shape[n] * yl[n][3];
@@ -121,12 +137,29 @@ void orc_asbmfg(const orc_part *p, int iblk, double *res) {
         v1[i] = xlb[2][i] - xlb[1][i];
         v2[i] = xlb[3][i] - xlb[1][i];
       }
-      double t1 = v1[2] * v2[3] - v2[2] * v1[3];
-      double t2 = v2[1] * v1[3] - v1[1] * v2[3];
-      double t3 = v1[1] * v2[2] - v2[1] * v1[2];
+      double t1, t2, t3;
+      if (lcsyst == 4) { /* e3bvar.f:139-146 */
+        t1 = dxdxib[2][1] * dxdxib[3][3] - dxdxib[2][3] * dxdxib[3][1];
+        t2 = dxdxib[3][1] * dxdxib[1][3] - dxdxib[3][3] * dxdxib[1][1];
+        t3 = dxdxib[1][1] * dxdxib[2][3] - dxdxib[1][3] * dxdxib[2][1];
+      } else if (lcsyst == 1) {
+        t1 = v1[2] * v2[3] - v2[2] * v1[3];
+        t2 = v2[1] * v1[3] - v1[1] * v2[3];
+        t3 = v1[1] * v2[2] - v2[1] * v1[2];
+      } else { /* e3bvar.f:152-155 */
+        t1 = -v1[2] * v2[3] + v2[2] * v1[3];
+        t2 = -v2[1] * v1[3] + v1[1] * v2[3];
+        t3 = -v1[1] * v2[2] + v2[1] * v1[2];
+      }
       double temp = 1.0 / sqrt(t1 * t1 + t2 * t2 + t3 * t3);
       double bn[4] = {0, t1 * temp, t2 * temp, t3 * temp};
-      double WdetJb = QWTB(c, lcsyst, intp) / (4.0 * temp);
+      double WdetJb; /* e3bvar.f:163-176 */
+      if (lcsyst == 3)
+        WdetJb = (1 - QWTB(c, lcsyst, intp)) / (4.0 * temp);
+      else if (lcsyst == 4)
+        WdetJb = QWTB(c, lcsyst, intp) / temp;
+      else
+        WdetJb = QWTB(c, lcsyst, intp) / (4.0 * temp);
       double d[4][4];
       d[1][1] = dxdxib[2][2] * dxdxib[3][3] - dxdxib[3][2] * dxdxib[2][3];
       d[1][2] = dxdxib[3][2] * dxdxib[1][3] - dxdxib[1][2] * dxdxib[3][3];
@@ -156,12 +189,13 @@ void orc_asbmfg(const orc_part *p, int iblk, double *res) {
       double rou = 0, pb = 0, Fv2 = 0, Fv3 = 0, Fv4 = 0, Fh5 = 0;
       for (int n = 1; n <= nshlb; n++) {
 #define BCBv(n, k) BCB[e + (size_t)npro * (((n)-1) + (size_t)nshlb * ((k)-1))]
-        rou += shape[n] * BCBv(n, 1);
-        pb += shape[n] * BCBv(n, 2);
-        Fv2 += shape[n] * BCBv(n, 3);
-        Fv3 += shape[n] * BCBv(n, 4);
-        Fv4 += shape[n] * BCBv(n, 5);
-        Fh5 += shape[n] * BCBv(n, 6);
+        double sh = shape[lnode[n]];
+        rou += sh * BCBv(n, 1);
+        pb += sh * BCBv(n, 2);
+        Fv2 += sh * BCBv(n, 3);
+        Fv3 += sh * BCBv(n, 4);
+        Fv4 += sh * BCBv(n, 5);
+        Fh5 += sh * BCBv(n, 6);
 #undef BCBv
       }
       /* ---- e3b (e3b.f:123-283) ---- */
@@ -218,7 +252,8 @@ void orc_asbmfg(const orc_part *p, int iblk, double *res) {
           p->aerfrc[3] += -heat * WdetJb;
         }
       }
-      for (int n = 1; n <= nshlb; n++) {
+      for (int k = 1; k <= nshlb; k++) {
+        int n = lnode[k];
         rl[e][n][1] += WdetJb * shape[n] * F1;
         rl[e][n][2] += WdetJb * shape[n] * F2;
         rl[e][n][3] += WdetJb * shape[n] * F3;

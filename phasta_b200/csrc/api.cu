@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" boundary declared in include/phb200.h.
 #include "ctx.h"
+#include "bnd_pack.h"
 #include <cstring>
 #include <new>
 
@@ -156,41 +157,33 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   ctx->d_ienb = nullptr; ctx->d_iBCB = nullptr; ctx->d_BCB = nullptr;
   if (c->nelblb > 0) {
     if (!lcblkb || !mienb || !miBCB || !mBCB || !shpb || !shglb) return fail("init", "null boundary arrays");
-    int nb = 0;
-    for (int b = 0; b < c->nelblb; b++) {
-      const int *lc = lcblkb + 10 * b;
-      if (lc[2] != 1 || lc[8] != 4 || lc[9] != 3 || lc[5] != 3)
-        return fail("init", "only tet boundary blocks with triangular faces supported yet");
-      nb += lc[10] - lc[0];
-    }
-    ctx->numelb = nb;
-    std::vector<int> ienb((size_t)4 * nb), ib((size_t)2 * nb);
-    std::vector<double> bcb((size_t)18 * nb);
-    size_t e0 = 0;
-    for (int b = 0; b < c->nelblb; b++) {
-      const int *lc = lcblkb + 10 * b;
-      int npro = lc[10] - lc[0];
-      for (int e = 0; e < npro; e++) {
-        for (int a = 0; a < 4; a++) {
-          int v = mienb[b][e + (size_t)npro * a];
-          if (v < 0) v = -v;
-          if (v < 1 || v > nshg) return fail("init", "ienb entry out of range");
-          ienb[(size_t)a * nb + e0 + e] = v - 1;
-        }
-        ib[e0 + e] = miBCB[b][e];
-        ib[(size_t)nb + e0 + e] = miBCB[b][e + (size_t)npro];
-        for (int k = 0; k < 6; k++)
-          for (int n = 0; n < 3; n++)
-            bcb[(size_t)(k * 3 + n) * nb + e0 + e] = mBCB[b][e + (size_t)npro * (n + 3 * k)];
+    for (int b = 0; b < c->nelblb; b++)
+      if (phb_bnd_kind(lcblkb + 10 * b) < 0)
+        return fail("init", "boundary block is not a linear tet, hex or wedge (lcsyst 1..4) with its face on lnode");
+    for (int k = 0; k < 4; k++) {
+      std::vector<int> ienb, ib;
+      std::vector<double> bcb;
+      const int nb = phb_bnd_pack(k, c->nelblb, lcblkb, mienb, miBCB, mBCB, nshg, ienb, ib, bcb);
+      if (nb < 0) return fail("init", "ienb entry out of range");
+      if (nb == 0) continue;
+      int *d_i = nullptr, *d_b = nullptr;
+      double *d_v = nullptr;
+      PHB_TRY(dev_alloc(&d_i, ienb.size()));
+      PHB_CHECK(cudaMemcpy(d_i, ienb.data(), sizeof(int) * ienb.size(), cudaMemcpyHostToDevice));
+      PHB_TRY(dev_alloc(&d_b, ib.size()));
+      PHB_CHECK(cudaMemcpy(d_b, ib.data(), sizeof(int) * ib.size(), cudaMemcpyHostToDevice));
+      PHB_TRY(dev_alloc(&d_v, bcb.size()));
+      PHB_CHECK(cudaMemcpy(d_v, bcb.data(), sizeof(double) * bcb.size(), cudaMemcpyHostToDevice));
+      if (k == 0) {
+        ctx->numelb = nb;
+        ctx->d_ienb = d_i; ctx->d_iBCB = d_b; ctx->d_BCB = d_v;
+      } else {
+        BndGroup g;
+        g.lcsyst = PHB_BND_LCSYST[k]; g.nshl = PHB_BND_NSHL[k]; g.nshlb = PHB_BND_NSHLB[k]; g.n = nb;
+        g.d_ien = d_i; g.d_iBCB = d_b; g.d_BCB = d_v;
+        ctx->bgen.push_back(g);
       }
-      e0 += npro;
     }
-    PHB_TRY(dev_alloc(&ctx->d_ienb, ienb.size()));
-    PHB_CHECK(cudaMemcpy(ctx->d_ienb, ienb.data(), sizeof(int) * ienb.size(), cudaMemcpyHostToDevice));
-    PHB_TRY(dev_alloc(&ctx->d_iBCB, ib.size()));
-    PHB_CHECK(cudaMemcpy(ctx->d_iBCB, ib.data(), sizeof(int) * ib.size(), cudaMemcpyHostToDevice));
-    PHB_TRY(dev_alloc(&ctx->d_BCB, bcb.size()));
-    PHB_CHECK(cudaMemcpy(ctx->d_BCB, bcb.data(), sizeof(double) * bcb.size(), cudaMemcpyHostToDevice));
   }
   PHB_TRY(dev_alloc(&ctx->d_aerfrc, (size_t)4 + 10 * 1001));
   PHB_CHECK(cudaMemset(ctx->d_aerfrc, 0, sizeof(double) * (4 + 10 * 1001)));
@@ -264,6 +257,11 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
   if (ctx->d_refel_tet) cudaFree(ctx->d_refel_tet);
   for (ElemGroup &g : ctx->gen) {
     void *gp[] = {g.d_ien, g.d_refel, g.d_EG, g.d_eloc};
+    for (void *p : gp)
+      if (p) cudaFree(p);
+  }
+  for (BndGroup &g : ctx->bgen) {
+    void *gp[] = {g.d_ien, g.d_iBCB, g.d_BCB};
     for (void *p : gp)
       if (p) cudaFree(p);
   }

@@ -21,18 +21,13 @@
 //    per (a,b,qp):  W (At_a tau + N_a I) (At_b + c N_b A0).
 #include "ctx.h"
 #include <cstring>
+#include "bnd_pack.h"
 
 struct TetTables {
   int nq;
   double N[4][4];      // N[q][a]       shp(1,a,q)
   double dN[4][4][3];  // dN[q][a][i]   shgl(1,i,a,q)
   double Qwt[4];       // Qwt(1,q)
-};
-struct PhysParams {
-  double Rgas, gamma, gamma1, pr, mu0, Tref, Ssuth, dat131;
-  double dtsfct, taucfct, temper, Dtgl, fct1;  // fct1 = almi/gami/alfi*Dtgl
-  int matflg2, matflg3, idiff, iremove, ipord, lhs, iprec, iDC;
-  double epsM;
 };
 struct TriTables {
   int nq;
@@ -52,6 +47,8 @@ __constant__ GenTables c_gen[2];
 __constant__ TetTables c_tet;
 __constant__ TriTables c_tri;
 __constant__ PhysParams c_ph;
+__constant__ BndTables c_bnd[3];
+#include "boundary.cuh"
 
 int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, const double *shpb,
                       const double *shglb) {
@@ -102,7 +99,7 @@ int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, co
     }
     PHB_CHECK(cudaMemcpyToSymbol(c_gen, &gt, sizeof gt, sizeof(GenTables) * g.tab));
   }
-  if (ctx->numelb > 0) {
+  if (ctx->numelb > 0) {  // boundary tets
     TriTables b;
     memset(&b, 0, sizeof b);
     b.nq = c.nintb[0];
@@ -119,6 +116,11 @@ int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, co
       }
     }
     PHB_CHECK(cudaMemcpyToSymbol(c_tri, &b, sizeof b));
+  }
+  for (const BndGroup &g : ctx->bgen) {
+    BndTables b;
+    if (phb_bnd_fill_tables(&b, g.lcsyst, g.nshl, c.nintb, c.Qwtb, shpb, shglb)) return 1;
+    PHB_CHECK(cudaMemcpyToSymbol(c_bnd, &b, sizeof b, sizeof(BndTables) * (g.lcsyst - 2)));
   }
   return 0;
 }
@@ -180,15 +182,6 @@ __device__ __forceinline__ void tet_metric(const double xl[4][3], const double (
 }
 
 // getDiff (compressible/getdiff.f:127,156-171), DNS
-__device__ __forceinline__ void diffusivities(double T, double cp, double &mu, double &lam, double &con) {
-  const double pt66 = 0.6666666666666666666666666666667;
-  if (c_ph.matflg2 == 0)
-    mu = c_ph.mu0;
-  else
-    mu = c_ph.mu0 * (T / c_ph.Tref) * sqrt(T / c_ph.Tref) * (c_ph.Tref + c_ph.Ssuth) / (T + c_ph.Ssuth);
-  lam = (c_ph.matflg3 == 0) ? (-pt66 * mu) : ((c_ph.dat131 - pt66) * mu);
-  con = mu * cp / c_ph.pr;
-}
 
 // viscous + heat flux (e3visc.f:278-343 == e3q.f:103-146), f[i][m], m=1..4
 // (momentum 1-3, energy); g[i][m] = dY_m/dx_i with m: 0 p,1..3 u,4 T
@@ -221,14 +214,6 @@ __device__ __forceinline__ void gather_x(const double *__restrict__ x, int numnp
     for (int i = 0; i < 3; i++) xl[a][i] = __ldg(x + (size_t)numnp * i + nd[a]);
 }
 
-// localy (common/localy.f:47-72): global {u,v,w,p,T} -> local {p,u,v,w,T}
-__device__ __forceinline__ void gather_y(const double *__restrict__ y, int nshg, int node, double yl[5]) {
-  yl[0] = __ldg(y + (size_t)nshg * 3 + node);
-  yl[1] = __ldg(y + node);
-  yl[2] = __ldg(y + (size_t)nshg * 1 + node);
-  yl[3] = __ldg(y + (size_t)nshg * 2 + node);
-  yl[4] = __ldg(y + (size_t)nshg * 4 + node);
-}
 
 // ---------------------------------------------------------------------------
 // AsIq + e3q (asiq.f:1-71, e3q.f:1-246): thread per element
@@ -2379,12 +2364,25 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   if (st->lhs == 1) {
     if (sparse) ctx->have_lhs_sparse = true; else ctx->have_lhs = true;
   }
-  if (ctx->numelb > 0) {  // boundary blocks (elmgmr.f:180-222); flxID = 0 first (elmgmr.f:122)
+  if (ctx->numelb > 0 || !ctx->bgen.empty()) {  // boundary blocks (elmgmr.f:180-222); flxID = 0 first (elmgmr.f:122)
     PHB_CHECK(cudaMemsetAsync(ctx->d_aerfrc + 4, 0, sizeof(double) * 10 * 1001, s));
     KScope ks(ctx, KC_ASM);
-    k_asbmfg_tet<<<(ctx->numelb + 127) / 128, 128, 0, s>>>(ctx->numelb, nshg, c.numnp, ctx->d_ienb, ctx->d_iBCB,
-                                                           ctx->d_BCB, ctx->d_x, ctx->d_y, ctx->d_res, ctx->d_aerfrc,
-                                                           st->iter == st->nitr);
+    const int do_force = st->iter == st->nitr;
+    if (ctx->numelb > 0)
+      k_asbmfg_tet<<<(ctx->numelb + 127) / 128, 128, 0, s>>>(ctx->numelb, nshg, c.numnp, ctx->d_ienb, ctx->d_iBCB,
+                                                             ctx->d_BCB, ctx->d_x, ctx->d_y, ctx->d_res,
+                                                             ctx->d_aerfrc, do_force);
+    for (const BndGroup &g : ctx->bgen) {
+      const int grid = (g.n + 127) / 128;
+#define PHB_BND_LAUNCH(NSHL, NSHLB, LCS)                                                                            \
+  k_asbmfg_gen<NSHL, NSHLB, LCS><<<grid, 128, 0, s>>>(g.n, nshg, c.numnp, g.d_ien, g.d_iBCB, g.d_BCB, ctx->d_x, \
+                                                      ctx->d_y, ctx->d_res, ctx->d_aerfrc, do_force)
+      if (g.lcsyst == 2) PHB_BND_LAUNCH(8, 4, 2);
+      else if (g.lcsyst == 3) PHB_BND_LAUNCH(6, 3, 3);
+      else PHB_BND_LAUNCH(6, 4, 4);
+#undef PHB_BND_LAUNCH
+    }
+    ctx->launches += (long long)ctx->bgen.size() + (ctx->numelb > 0 ? 1 : 0) - 1;  // KScope counted one
     PHB_CHECK(cudaGetLastError());
   }
   // halo + BC post-processing (elmgmr.f:249-268)

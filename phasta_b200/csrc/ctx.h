@@ -45,6 +45,15 @@ struct ElemGroup {
   int *d_eloc;    // [nshl*nshl][numel_pad] CSR block of element block (a,b)
 };
 
+// boundary elements that are not tets: one group per kind -- hexes (quadrilateral face, lcsyst 2), wedges with a
+// triangular (3) or quadrilateral (4) boundary face (elmgmr.f:191 turns the wedge's lcsyst into nenbl)
+struct BndGroup {
+  int lcsyst, nshl, nshlb, n;
+  int *d_ien;     // [nshl][n] 0-based
+  int *d_iBCB;    // [2][n]  iBCB(:,1) flux codes, iBCB(:,2) surfID
+  double *d_BCB;  // [6][nshlb][n]  BCB(e,k,j) -> [(j*nshlb+k)*n + e]
+};
+
 struct HaloTask {
   int peer, iacc, tag, count;  // count = number of nodes (all segments)
   int offset;                  // into d_halo_nodes
@@ -78,7 +87,8 @@ struct phb200_ctx {
   int n_perslave;      // periodic slave nodes (iBC bit 10)
   int *d_perslave;     // their ids
   // ---- boundary elements (tet volume element, tri face = local nodes 1..3)
-  int numelb;          // boundary elements in all blocks
+  int numelb;          // boundary TETS in all blocks (the other kinds: bgen)
+  std::vector<BndGroup> bgen;
   int *d_ienb;         // [4][numelb] 0-based
   int *d_iBCB;         // [2][numelb]  iBCB(:,1) flux codes, iBCB(:,2) surfID
   double *d_BCB;       // [6][3][numelb]  BCB(e,n,k) -> [(k*3+n)*numelb + e]

@@ -136,38 +136,28 @@ def _box_wedges(I, J, K, node_id):
     return np.stack(out, axis=1).reshape(-1, 6)
 
 
-def _boundary_elements(ien0, x, on_boundary_planes, gnode, ibksiz, natural, seed):
-    """Boundary elements of a tet part (genbkbPosix.f:47-123): each is the
-    volume tet re-ordered so that local nodes 1..3 are the boundary triangle
-    with outward normal (v1 x v2, e3bvar.f:120-140) and node 4 is interior.
-    on_boundary_planes: list of boolean node masks, one per selected plane.
-    natural: "none" -> iBCB=0 (all fluxes floating); "mixed" -> deterministic
-    sprinkle of mass-flux / pressure / traction / heat-flux codes + values."""
-    faces_of = ((1, 2, 3), (0, 3, 2), (0, 1, 3), (0, 2, 1))   # face opposite node k
-    out = []
-    for mask in on_boundary_planes:
-        m = mask[ien0]                                         # (numel,4)
-        for k in range(4):
-            f = faces_of[k]
-            sel = m[:, f[0]] & m[:, f[1]] & m[:, f[2]] & ~m[:, k]
-            if not sel.any():
-                continue
-            t = ien0[sel]
-            out.append(np.stack([t[:, f[0]], t[:, f[1]], t[:, f[2]], t[:, k]], axis=1))
-    if not out:
-        return None, [], [], []
-    b = np.concatenate(out, axis=0)
-    # orient: normal (b-a)x(c-a) must point away from d
-    a_, b_, c_, d_ = (x[b[:, i]] for i in range(4))
-    nrm = np.cross(b_ - a_, c_ - a_)
-    flip = np.einsum("ij,ij->i", nrm, d_ - a_) > 0
-    b[flip, 1], b[flip, 2] = b[flip, 2].copy(), b[flip, 1].copy()
-    nb = b.shape[0]
-    ienb = (b + 1).astype(np.int32)
+# boundary-element kinds: lcsyst of the boundary block (genbkbPosix.f:52-59; a wedge with a quadrilateral boundary
+# face is lcsyst 4, elmgmr.f:191), nenl, nenbl, nshl, nshlb, lnode (getbnodes, hierarchic.f:90-190, 0-based) and
+# the proper rotations of the reference element that bring each of its faces of that kind onto lnode
+_BKIND = {
+    "hex": dict(lcsyst=2, nenl=8, nenbl=4, lnode=(0, 1, 2, 3),
+                rots=((0, 1, 2, 3, 4, 5, 6, 7), (0, 4, 5, 1, 3, 7, 6, 2), (0, 3, 7, 4, 1, 2, 6, 5),
+                      (1, 5, 6, 2, 0, 4, 7, 3), (2, 6, 7, 3, 1, 5, 4, 0), (4, 7, 6, 5, 0, 3, 2, 1))),
+    "wedge3": dict(lcsyst=3, nenl=6, nenbl=3, lnode=(0, 1, 2),
+                   rots=((0, 1, 2, 3, 4, 5), (3, 5, 4, 0, 2, 1))),
+    "wedge4": dict(lcsyst=4, nenl=6, nenbl=4, lnode=(0, 3, 4, 1),
+                   rots=((0, 1, 2, 3, 4, 5), (1, 2, 0, 4, 5, 3), (2, 0, 1, 5, 3, 4))),
+}
+
+
+def _natural_codes(face_gnodes, natural, seed, nshlb):
+    """iBCB(nb,2) / BCB(nb,nshlb,6): "none" -> all fluxes floating; "mixed" -> deterministic sprinkle of
+    mass-flux / pressure / traction / heat-flux codes + values, keyed on the GLOBAL ids of the face nodes."""
+    nb = face_gnodes.shape[0]
     iBCB = np.zeros((nb, 2), dtype=np.int32)
-    BCB = np.zeros((nb, 3, NDOF + 1))
+    BCB = np.zeros((nb, nshlb, NDOF + 1))
     if natural == "mixed":
-        gkey = np.sort(gnode[b[:, :3]], axis=1)
+        gkey = np.sort(face_gnodes, axis=1)
         h = (gkey[:, 0] * 73856093 ^ gkey[:, 1] * 19349663 ^ gkey[:, 2] * 83492791) % 11
         r = np.random.default_rng(seed + 11)
         vals = r.uniform(0.5, 1.5, size=(11, 6)) * np.array([30.0, 1.0e5, 2.0, 2.0, 2.0, 50.0])
@@ -181,22 +171,88 @@ def _boundary_elements(ien0, x, on_boundary_planes, gnode, ibksiz, natural, seed
         BCB[(iBCB[:, 0] & 2) == 0, :, 1] = 0.0
         BCB[(iBCB[:, 0] & 4) == 0, :, 2:5] = 0.0
         BCB[(iBCB[:, 0] & 8) == 0, :, 5] = 0.0
-    starts = np.arange(0, nb, ibksiz)
-    nblk = starts.size
-    lcblkb = np.zeros((10, nblk + 1), dtype=np.int32, order="F")
-    lcblkb[0, :nblk] = starts + 1
-    lcblkb[0, nblk] = nb + 1
-    lcblkb[2, :nblk] = 1       # lcsyst
-    lcblkb[3, :nblk] = 1       # ipord
-    lcblkb[4, :nblk] = 4       # nenl
-    lcblkb[5, :nblk] = 3       # nenbl
-    lcblkb[6, :nblk] = 0       # mattyp
-    lcblkb[7, :nblk] = NDOF    # ndofl
-    lcblkb[8, :nblk] = 4       # nshl
-    lcblkb[9, :nblk] = 3       # nshlb
-    sl = [slice(lcblkb[0, i] - 1, lcblkb[0, i + 1] - 1) for i in range(nblk)]
-    return (lcblkb, [np.asfortranarray(ienb[q]) for q in sl], [np.asfortranarray(iBCB[q]) for q in sl],
-            [np.asfortranarray(BCB[q]) for q in sl])
+    return iBCB, BCB
+
+
+def _boundary_tets(ien0, x, on_boundary_planes):
+    """each boundary tet is the volume tet re-ordered so that local nodes 1..3 are the boundary triangle
+    with outward normal (v1 x v2, e3bvar.f:120-140) and node 4 is interior"""
+    faces_of = ((1, 2, 3), (0, 3, 2), (0, 1, 3), (0, 2, 1))   # face opposite node k
+    out = []
+    for mask in on_boundary_planes:
+        m = mask[ien0]                                         # (numel,4)
+        for k in range(4):
+            f = faces_of[k]
+            sel = m[:, f[0]] & m[:, f[1]] & m[:, f[2]] & ~m[:, k]
+            if not sel.any():
+                continue
+            t = ien0[sel]
+            out.append(np.stack([t[:, f[0]], t[:, f[1]], t[:, f[2]], t[:, k]], axis=1))
+    if not out:
+        return None
+    b = np.concatenate(out, axis=0)
+    # orient: normal (b-a)x(c-a) must point away from d
+    a_, b_, c_, d_ = (x[b[:, i]] for i in range(4))
+    nrm = np.cross(b_ - a_, c_ - a_)
+    flip = np.einsum("ij,ij->i", nrm, d_ - a_) > 0
+    b[flip, 1], b[flip, 2] = b[flip, 2].copy(), b[flip, 1].copy()
+    return b
+
+
+def _boundary_rotated(ien0, kind, on_boundary_planes):
+    """boundary hexes / wedges: the volume element rotated (a proper rotation of the reference element, so
+    det(dx/dxi) stays positive) until the boundary face sits on lnode; the normals of e3bvar.f:139-152 then
+    point outward for positively oriented elements"""
+    K = _BKIND[kind]
+    ln = list(K["lnode"])
+    rest = [a for a in range(K["nenl"]) if a not in ln]
+    out = []
+    for mask in on_boundary_planes:
+        for rot in K["rots"]:
+            t = ien0[:, list(rot)]
+            m = mask[t]
+            sel = m[:, ln].all(axis=1) & ~m[:, rest].any(axis=1)
+            if sel.any():
+                out.append(t[sel])
+    return np.concatenate(out, axis=0) if out else None
+
+
+def _boundary_elements(groups0, x, on_boundary_planes, gnode, ibksiz, natural, seed):
+    """Boundary elements of a part (genbkbPosix.f:47-123), one run of blocks per kind in the order tets,
+    hexes, wedges with a triangular face, wedges with a quadrilateral face.
+    groups0: list of (topo, ien0) with ien0 (n,nshl) 0-based; on_boundary_planes: boolean node masks."""
+    runs = []
+    for topo, ien0 in groups0:
+        if topo == "tet":
+            b = _boundary_tets(ien0, x, on_boundary_planes)
+            if b is not None:
+                runs.append((1, 4, 3, (0, 1, 2), b))
+        else:
+            for kind in (("hex",) if topo == "hex" else ("wedge3", "wedge4")):
+                b = _boundary_rotated(ien0, kind, on_boundary_planes)
+                if b is not None:
+                    K = _BKIND[kind]
+                    runs.append((K["lcsyst"], K["nenl"], K["nenbl"], K["lnode"], b))
+    if not runs:
+        return None, [], [], []
+    runs.sort(key=lambda r: r[0])
+    cols, mienb, miBCB, mBCB = [], [], [], []
+    first = 1
+    for lcsyst, nenl, nenbl, lnode, b in runs:
+        nb = b.shape[0]
+        ienb = (b + 1).astype(np.int32)
+        iBCB, BCB = _natural_codes(gnode[b[:, list(lnode)]], natural, seed, nenbl)
+        for a in range(0, nb, ibksiz):
+            q = slice(a, min(a + ibksiz, nb))
+            #            iel       -  lcsyst  ipord nenl  nenbl  mattyp ndofl nshl  nshlb   (genbkbPosix.f:103-114)
+            cols.append([first + a, 0, lcsyst, 1, nenl, nenbl, 0, NDOF, nenl, nenbl])
+            mienb.append(np.asfortranarray(ienb[q]))
+            miBCB.append(np.asfortranarray(iBCB[q]))
+            mBCB.append(np.asfortranarray(BCB[q]))
+        first += nb
+    cols.append([first, 0, 0, 0, 0, 0, 0, 0, 0, 0])
+    lcblkb = np.asfortranarray(np.array(cols, dtype=np.int32).T)
+    return lcblkb, mienb, miBCB, mBCB
 
 
 def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15,
@@ -363,7 +419,6 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
                       x=x, lcblk=lcblk, mien=mien, iBC=iBC, BC=BC, iper=iper,
                       ilwork=ilwork, gnode=gnode, gelem=gelem)
         if boundary:
-            assert topo == "tet", "boundary elements are generated for tet meshes only"
             planes = [J == 0, J == ny]
             if i0 == 0:
                 planes.append(I == 0)
@@ -371,7 +426,8 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
                 planes.append(I == nx)
             if not (periodic_z and bc in ("channel", "mixed", "allcodes")):
                 planes += [K == 0, K == nz]
-            lcb, ienb, ibcb, bcb = _boundary_elements(ien0, x, planes, gnode, ibksiz, natural, seed)
+            lcb, ienb, ibcb, bcb = _boundary_elements([(t, g1 - 1) for t, g1 in groups], x, planes, gnode, ibksiz,
+                                                       natural, seed)
             if lcb is not None:
                 mp.lcblkb, mp.mienb, mp.miBCB, mp.mBCB = lcb, ienb, ibcb, bcb
         parts.append(mp)

@@ -9,8 +9,10 @@ Linear tets: genint.f:30-75 (symtet 1-/4-pt rule, Qwt*4/3), genshp.f:34-37
 linear wedges (topology 3): genint.f:294-318 (symwdg 6-pt rule), genshp.f:47-53
 (WedgeShapeAndDrv, newshape.cc:706-768).  In production the Fortran host
 passes its own tables; these exist so the Python host mirror and the tests
-can drive the C-ABI without Fortran.  Pinned against the reference's own C
-generators in tests/test_tables.py (golden fixture tests/golden/tables_tet.npz).
+can drive the C-ABI without Fortran.  Boundary faces: triangles of tets
+(genint.f:44-75), quadrilaterals of hexes, triangles / quadrilaterals of wedges (genint.f:116-141,303-343,
+genshpb.f).  Pinned against the reference's own C generators and against genint.f / genshp.f / genshpb.f
+executed by f77np in tests/test_tables.py (tests/golden/tables_ref.npz, tables_f77.npz).
 """
 import numpy as np
 
@@ -59,6 +61,37 @@ def wedge_points(rule):
     tri = [(_P23, _P23), (_P24, _P23), (_P23, _P24)]
     pts = np.array([[r, s, z * _G2, 0.0] for z in (-1, 1) for r, s in tri])
     return pts, np.full(6, 0.666666666666667)
+
+
+_PW1, _PW2 = 0.211324865405187, 0.788675134594813     # symquadw.c Pp21, Pp22
+
+
+def quad_points(rule):
+    """boundary quadrilateral of a hex: symquad 4-pt rule on the zeta = -1 face (phSolver/common/symquad.c)."""
+    if rule != 2:
+        raise NotImplementedError("quad quadrature rule %d" % rule)
+    pts = np.array([[sx * _G2, sy * _G2, -1.0, 0.0] for sy in (-1, 1) for sx in (-1, 1)])
+    return pts, np.full(4, 1.0)
+
+
+def wedge_tri_points(rule):
+    """boundary triangle of a wedge (genint.f:320-331): the symtri points rotated by one (the last point comes
+    first), third coordinate zeta = -1, weights as symtri gives them (not doubled)."""
+    pts, w = tri_points(rule)
+    n = len(w)
+    out = np.zeros((n, 4))
+    out[1:, :2] = pts[:n - 1, :2]
+    out[0, :2] = pts[n - 1, :2]
+    out[:, 2:] = -1.0
+    return out, w
+
+
+def wedge_quad_points(rule):
+    """boundary quadrilateral of a wedge: symquadw 4-pt rule on the s = 0 face (phSolver/common/symquadw.c)."""
+    if rule != 2:
+        raise NotImplementedError("wedge quad quadrature rule %d" % rule)
+    pts = np.array([[r, 0.0, z * _G2, 0.0] for z in (-1, 1) for r in (_PW1, _PW2)])
+    return pts, np.full(4, 1.0)
 
 
 def hex_shape(xi, eta, zeta):
@@ -133,5 +166,18 @@ def make_tables(rule=2, ruleb=2):
         r, s, t = ptsb[i, 0], ptsb[i, 1], ptsb[i, 2]   # Qptb(1,1:3,i) (genshpb.f:24)
         shpb[0, :4, i] = [r, s, t, 1.0 - r - s - t]
         shglb[0, :, :4, i] = dN.T / 2.0
+    if ruleb == 2:
+        # boundary faces of hexes (lcsyst 2), wedges with a triangular (3) or quadrilateral (4) boundary face:
+        # genint.f:116-141,303-343 (no weight rescaling), genshpb.f:36-56 (volume shape functions at the face points)
+        for top, points, shape, nsh in ((1, quad_points, hex_shape, 8), (2, wedge_tri_points, wedge_shape, 6),
+                                        (3, wedge_quad_points, wedge_shape, 6)):
+            pts, w = points(ruleb)
+            n = len(w)
+            nintb[top] = n
+            Qwtb[top, :n] = w
+            for i in range(n):
+                N, d = shape(pts[i, 0], pts[i, 1], pts[i, 2])
+                shpb[top, :nsh, i] = N
+                shglb[top, :, :nsh, i] = d.T
     return dict(nint=nint, nintb=nintb, Qwt=Qwt, Qwtb=Qwtb, shp=shp, shgl=shgl,
                 shpb=shpb, shglb=shglb)

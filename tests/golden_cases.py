@@ -25,6 +25,14 @@ CASES = {
     # (numel,nshape,5,5) array to local's (npro,nshl,25) dummy, which scrambles the tet blocks when nshl<nshape
     # (the reference's EBE solver is only well defined on single-topology meshes; its default SolGMRs is fine)
     "mixed_channel": ((2, 4, 2), dict(bc="channel", topo="mixed", ibksiz=16, etol=1e-6), ("elmgmre", "solgmrs")),
+    # boundary elements on quadrilateral faces of hexes (lcsyst 2), triangular (3) and quadrilateral (4) faces of
+    # wedges (e3bvar.f:139-176 per-topology normals / WdetJb, getbnodes lnode), every natural-BC code; z faces too
+    "hex_bnd": ((3, 2, 2), dict(bc="channel", topo="hex", ibksiz=8, boundary=True, natural="mixed", periodic_z=False,
+                                etol=1e-6), ("elmgmre", "solgmre", "solgmrs")),
+    "wedge_bnd": ((2, 3, 2), dict(bc="channel", topo="wedge", ibksiz=16, boundary=True, natural="mixed",
+                                  periodic_z=False, etol=1e-6), ("elmgmre", "elmgmre0", "solgmrs")),
+    "mixed_bnd": ((2, 4, 2), dict(bc="channel", topo="mixed", ibksiz=16, boundary=True, natural="mixed", etol=1e-6),
+                  ("elmgmre", "solgmrs")),
     # matrix-free flavour (SolMFG): acoustic units (see common.nondimensional) and a state that has been through
     # itrBC, as in itrdrv.f:394 -- Au1MFG applies itrBC to the perturbed state
     "tet_nd_mfg": ((3, 2, 2), dict(bc="channel", ibksiz=16, boundary=True, natural="mixed", etol=1e-4, nd=True),

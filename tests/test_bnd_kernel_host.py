@@ -1,0 +1,70 @@
+"""The product's boundary-flux kernel for hexes and wedges (phasta_b200/csrc/boundary.cuh: k_asbmfg_gen, with the
+group packing and face tables of bnd_pack.h) compiled for the HOST behind tests/host_emul/cuda_shim.h and run one
+thread after the other, against what the reference's asbmfg.f / e3b.f / e3bvar.f added to the residual and to
+/aerfrc/ in the f77np fixtures.  This checks the kernel's arithmetic and data layout where there is no GPU; the
+same cases run on the device in the GPU suite."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import rel_l2
+from test_golden_f77 import load
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emul", "bnd_host.cpp")
+OUT = os.path.join(HERE, "host_emul", "_build", "libbnd_host.so")
+
+
+@pytest.fixture(scope="module")
+def emul():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                           "-o", OUT, SRC])
+    return C.CDLL(OUT)
+
+
+def _ptrs(arrs, ctype):
+    keep = [np.ascontiguousarray(np.asfortranarray(a).ravel(order="F")) for a in arrs]
+    return keep, (C.POINTER(ctype) * len(keep))(*[a.ctypes.data_as(C.POINTER(ctype)) for a in keep])
+
+
+@pytest.mark.parametrize("name", ["hex_bnd", "wedge_bnd", "mixed_bnd"])
+def test_boundary_kernel_on_the_host_matches_reference_fortran(emul, name):
+    z, case, _ = load(name)
+    params, tables, parts, states = case
+    mp = parts[0]
+    y = np.asfortranarray(states[0][0])
+    res = np.zeros((mp.nshg, 5), order="F")
+    aer = np.zeros(4 + 10 * 1001)
+    k1, pien = _ptrs([b.astype(np.int32) for b in mp.mienb], C.c_int)
+    k2, pibc = _ptrs([b.astype(np.int32) for b in mp.miBCB], C.c_int)
+    k3, pbcb = _ptrs([b.astype(np.float64) for b in mp.mBCB], C.c_double)
+    lcb = np.ascontiguousarray(mp.lcblkb.T.astype(np.int32).ravel())           # column b at lcblkb + 10 b
+    P = params
+    phys = np.array([P.Rgas, P.gamma, P.gamma1, P.pr, P.datmat121, P.datmat221, P.datmat321, P.datmat131])
+    iphys = np.array([P.matflg2, P.matflg3], dtype=np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)       # noqa: E731
+    T = {k: np.asfortranarray(tables[k]) for k in ("nintb", "Qwtb", "shpb", "shglb")}
+    nintb = T["nintb"].astype(np.int32)
+    n = emul.bnd_host_asbmfg(mp.nelblb, vp(lcb), pien, pibc, pbcb, mp.nshg, mp.numnp, vp(np.asfortranarray(mp.x)),
+                             vp(y), vp(nintb), vp(T["Qwtb"]), vp(T["shpb"]), vp(T["shglb"]), vp(phys), vp(iphys),
+                             vp(res), vp(aer), 1)
+    nontet = sum(b.shape[0] for b, lc in zip(mp.mienb, mp.lcblkb.T) if lc[2] != 1)
+    assert n == nontet > 0
+    ref = z["elmgmre.res_nobc"] - z["elmgmre.res_interior"]        # what the boundary blocks added
+    if name == "mixed_bnd":
+        # the tets' share comes from k_asbmfg_tet (GPU suite); compare on the nodes no boundary tet touches
+        tetnodes = np.unique(np.concatenate([b[:, :3].ravel() for b, lc in zip(mp.mienb, mp.lcblkb.T) if lc[2] == 1])) - 1
+        keep = np.ones(mp.nshg, dtype=bool)
+        keep[tetnodes] = False
+        assert keep.sum() > 0 and np.abs(ref[keep]).max() > 0
+        assert rel_l2(res[keep], ref[keep]) < 1e-12
+        return
+    assert rel_l2(res, ref) < 1e-12
+    ref_f = np.r_[z["elmgmre.Force"], z["elmgmre.HFlux"]]
+    assert rel_l2(aer[:4], ref_f) < 1e-12
+    fl = aer[4:4 + 20].reshape((10, 2), order="F")
+    assert rel_l2(fl, z["elmgmre.flxID"]) < 1e-12

@@ -48,23 +48,3 @@ def test_oracle_commu_matches_reference_fortran_bit_for_bit(n):
         assert np.array_equal(w[p.rank], z["afterout_n%d_r%d" % (n, p.rank)])
     # the middle part is master of one plane and slave of the other: both roles are in the fixture
     assert any(not np.array_equal(z["in_n%d_r1" % n], z["afterin_n%d_r1" % n]) for _ in (0,))
-
-
-@pytest.mark.gpu
-@pytest.mark.parametrize("n", NS)
-def test_gpu_commu_matches_reference_fortran(n):
-    from test_gpu_multipart import run_parts
-    z, case = _load()
-
-    def fn(g, y, ac):
-        v = z["in_n%d_r%d" % (n, g.part.rank)].copy(order="F")
-        g.commu(v, n, "in")
-        a = v.copy(order="F")
-        g.commu(v, n, "out")
-        return a, v
-
-    gs, out = run_parts(case, fn)
-    for p, (a, b) in zip(case[2], out):
-        assert rel_l2(a, z["afterin_n%d_r%d" % (n, p.rank)]) < 1e-14
-        assert rel_l2(b, z["afterout_n%d_r%d" % (n, p.rank)]) < 1e-14
-    [g.close() for g in gs]

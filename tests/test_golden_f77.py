@@ -35,8 +35,14 @@ def load(name):
     return z, case, runs
 
 
-def names(run):
-    return [n for n, (_, _, runs) in CASES.items() if run in runs]
+# cases added after the round's GPU budget was spent: their device runs sit in tests/test_zz_gpu_late.py, which
+# sorts last, so that a failure there cannot stop (-x) the suite that has been measured on a B200
+LATE = ("hex_bnd", "wedge_bnd", "mixed_bnd")
+
+
+def names(run, late=None):
+    """late=None: every case; False: those measured on a B200 this round; True: the late ones"""
+    return [n for n, (_, _, runs) in CASES.items() if run in runs and (late is None or (n in LATE) == late)]
 
 
 # ------------------------------------------------------------------ CPU: oracle
@@ -146,10 +152,14 @@ def gpu(case, dev=0):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", names("elmgmre") + names("elmgmre0"))
+@pytest.mark.parametrize("name", names("elmgmre", False) + names("elmgmre0", False))
 def test_gpu_elmgmre_matches_reference_fortran(name):
+    check_gpu_elmgmre(name)
+
+
+def check_gpu_elmgmre(name, run=None):
     z, case, runs = load(name)
-    run = "elmgmre" if "elmgmre" in runs else "elmgmre0"
+    run = run or ("elmgmre" if "elmgmre" in runs else "elmgmre0")
     g = gpu(case)
     y, ac = case[3][0]
     if name == "hex_dc1":
@@ -178,8 +188,12 @@ def test_gpu_elmgmre_matches_reference_fortran(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", names("solgmre"))
+@pytest.mark.parametrize("name", names("solgmre", False))
 def test_gpu_solgmre_matches_reference_fortran(name):
+    check_gpu_solgmre(name)
+
+
+def check_gpu_solgmre(name):
     z, case, _ = load(name)
     g = gpu(case)
     y, ac = case[3][0]
@@ -193,8 +207,12 @@ def test_gpu_solgmre_matches_reference_fortran(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", names("solgmrs"))
+@pytest.mark.parametrize("name", names("solgmrs", False))
 def test_gpu_solgmrs_matches_reference_fortran(name):
+    check_gpu_solgmrs(name)
+
+
+def check_gpu_solgmrs(name):
     z, case, _ = load(name)
     g = gpu(case)
     colm, rowp, ntot = g.genadj()

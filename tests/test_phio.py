@@ -81,7 +81,8 @@ def test_write_sequence_errors(tmp_path):
 
 @pytest.mark.parametrize("bc,nparts,boundary,topo", [("channel", 1, True, "tet"), ("mixed", 2, False, "tet"),
                                                      ("channel", 2, True, "tet"), ("channel", 1, False, "mixed"),
-                                                     ("none", 1, False, "hex")])
+                                                     ("none", 1, False, "hex"), ("channel", 1, True, "hex"),
+                                                     ("channel", 2, True, "mixed"), ("none", 1, True, "wedge")])
 def test_geombc_restart_round_trip(tmp_path, bc, nparts, boundary, topo):
     case = make_case(8, 6, 5, nparts=nparts, bc=bc, boundary=boundary, natural="all" if boundary else "none",
                      topo=topo, periodic_z=(bc != "none"))

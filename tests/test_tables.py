@@ -46,6 +46,21 @@ def test_hex_wedge_tables_bit_exact(name, top, n, nsh):
         assert np.array_equal(T["shgl"][top, :, :nsh, i], GOLD["%s%d_dN" % (name, n)][i].T)
 
 
+def test_all_tables_match_genint_genshp_genshpb_executed_by_f77np():
+    """the whole COMMON tables (rule 2, interior lcsyst 1..3, boundary lcsyst 1..4) against the reference's
+    genint.f / genshp.f / genshpb.f run on top of its own C generators: bit for bit"""
+    Z = np.load(os.path.join(HERE, "golden", "tables_f77.npz"))
+    T = make_tables(2, 2)
+    assert np.array_equal(T["nint"][:3], Z["nint"][:3]) and np.array_equal(T["nintb"][:4], Z["nintb"][:4])
+    for k in ("Qwt", "shp", "shgl"):
+        assert np.array_equal(T[k][:3], Z[k][:3]), k
+    for k in ("Qwtb", "shpb", "shglb"):
+        assert np.array_equal(T[k][:4], Z[k][:4]), k
+    # the wedge's triangular face: rotated points, weights NOT doubled (e3bvar.f:147 uses 1 - Qwtb)
+    assert np.array_equal(Z["Qptb"][2, :3, 0], [0.166666666666667, 0.166666666666667, -1.0])
+    assert np.array_equal(Z["Qwtb"][2, :3], np.full(3, 0.333333333333333))
+
+
 def test_oracle_tables_match_python_tables():
     from oracle.oracle_py import lib
     L = lib()

@@ -211,39 +211,3 @@ def test_oracle_itrbc_all_codes_matches_reference_fortran():
     o = make_oracle(case)
     o.itrBC()
     assert np.array_equal(o.parts[0].keep["y"], z["y"]) and np.array_equal(o.parts[0].keep["ac"], z["ac"])
-
-
-@pytest.mark.gpu
-def test_gpu_itrbc_all_codes_matches_reference_fortran():
-    from phasta_b200.solver import PhastaGPU
-    _step_fixture("be_channel")
-    z, case = _itrbc_fixture()
-    params, tables, parts, states = case
-    g = PhastaGPU(parts[0], params, tables, device=0)
-    g.set_state(*states[0])
-    g.itrBC()
-    y, ac = g.get_state()
-    assert rel_l2(y, z["y"]) < 1e-14 and np.array_equal(ac, z["ac"])     # FMA contraction: last-bit differences in y
-    g.close()
-
-
-# The generalized-alpha / LHSupd=2 fixture is pinned on the oracle above; its GPU run is left for the next round
-# (the round's GPU budget was spent before it could be measured, and an unmeasured GPU assertion is not added).
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", STEP_CASES[:1])
-def test_gpu_step_matches_reference_fortran(name):
-    from phasta_b200.solver import PhastaGPU
-    z, case, opt = _step_fixture(name)
-    params, tables, parts, states = case
-    g = PhastaGPU(parts[0], params, tables, device=0)
-    y, ac = states[0]
-    g.set_state(y, ac)
-    g.set_old_state(y, ac)
-    st = g.TimeStep(nitr=opt["nitr"], ipred=opt["ipred"], LHSupd=opt["LHSupd"])
-    diks = np.abs(st[:, 2].astype(int) - z["iKs"])
-    assert diks.max() <= 1, (st[:, 2], z["iKs"])     # a Krylov count next to the tolerance may flip by one
-    tol = 1e-9 if diks.max() == 0 else 1e-6
-    yg, acg, yog, acog = g.get_state(old=True)
-    assert rel_l2(yg, z["y"]) < tol and rel_l2(yog, z["yold"]) < tol
-    assert rel_l2(acg, z["ac"]) < max(tol, 1e-6)     # ac = (y - yold) Dtgl amplifies the round-off of y
-    g.close()
