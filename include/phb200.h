@@ -60,6 +60,11 @@ typedef struct phb200_incomp {
   int iconvflow, itau, idiff, ipord, lhs, matflg5;
   double rho, rmu, bf[3];
   double flmpl, flmpr, Delt, Dtgl, almi, alfi, gami, dtsfct, taucfct;
+  /* the boundary integral (incompressible/asbmfg.f, e3b.f, e3bvar.f): /nomodule/ iviscflux, /turbvari/ itwmod
+   * (|itwmod| = 1 integrates Force), /aerfrc/ nsrflist(0:MAXSURF) -- the 1001 switches that put a surface ID
+   * in the flux / force list (common.h:98-108); NULL = no surface listed.  Rigid walls only (ideformwall = 0). */
+  int iviscflux, itwmod;
+  const int *nsrflist;
 } phb200_incomp;
 
 typedef struct phb200_ctx phb200_ctx;
@@ -139,7 +144,8 @@ int phb200_dev_sparseap(phb200_ctx *ctx, int slot);
  * bc3Res.  y, ac (nshg,ndof) as for SolGMRe; res (nshg,4) {mom1,mom2,mom3,continuity}; lhsK (9,nnz_tot) with the
  * 3x3 block entry (r,c) at 3(r-1)+c, lhsP (4,nnz_tot) = {G1,G2,G3,C}; the CSR structure is the one of
  * phb200_set_sparse.  Output pointers may be null (the matrices stay device-resident for phb200_les_ap).
- * Boundary-element blocks (AsBMFG/e3b of the incompressible code) are not built: refused when nelblb > 0. */
+ * Boundary-element blocks (AsBMFG/e3b/e3bvar of the incompressible code, elmgmr.f:246-320) add their flux to res
+ * and integrate flxID / Force (read back with phb200_get_aerfrc); deformable-wall elements (iBCB bit 4) are refused. */
 int phb200_inc_elmgmr(phb200_ctx *ctx, const double *y, const double *ac, const phb200_incomp *ip, double *res,
                       double *lhsK, double *lhsP);
 int phb200_inc_dev_elmgmr(phb200_ctx *ctx, const phb200_incomp *ip);

@@ -17,9 +17,9 @@
  *   bc3Res/bc3per     incompressible/bc3res.f:1-90, bc3per.f:1-45
  *   fLesSparseApG/ApKG/ApNGt/ApNGtC/ApFull  incompressible/lesSparse.f:204-492
  * Scope: DNS (iLES=iRANS=iLSet=0), ipord=1, itau=0, idiff in {0,1}, iconvflow in
- * {1,2}, constant body force (matflg(5,1) in {0,1}), no boundary-element blocks
- * (the reference's boundary integral AsBMFG/e3b for incompressible flow is not
- * restated; callers must pass nelblb=0), ipvsq=0.  Pinned against the
+ * {1,2}, constant body force (matflg(5,1) in {0,1}), the boundary integral
+ * AsBMFG/e3b/e3bvar with rigid walls (ideformwall=0) on tet, hex and wedge
+ * faces, ipvsq=0.  Pinned against the
  * reference's own Fortran executed by f77np (tests/golden/f77_incomp_*.npz).
  */
 #include "oracle_internal.h"
@@ -676,16 +676,199 @@ static void bc3res_i(const orc_part *p, double *res) {
 #undef BCv
 }
 
-/* ElmGMR (incompressible/elmgmr.f:1-330), interior blocks only.  res[m] (nshg,4),
+/* AsBMFG + e3b + e3bvar of the incompressible code (incompressible/asbmfg.f:1-68, e3b.f:1-262, e3bvar.f:1-230) for one
+ * boundary block, rigid walls (ideformwall = 0: vdot = rlKwall = 0, xKebe = 0 so the bc3lhs / fillsparseI that follow
+ * in elmgmr.f:303-313 add nothing).  getbnodes lnode (hierarchic.f:90-190); normals "curl into element for tets, all
+ * others out" (e3bvar.f:100-127), WdetJb per topology (e3bvar.f:129-142).  flxID / Force go to p->aerfrc as in the
+ * compressible path: Force(1:3) at [0..2], flxID(k,iface) at [4 + 10 iface + k-1]. */
+static void asbmfg_i(const orc_part *p, const orc_incomp *ip, int iblk, double *res) {
+  const orc_common *c = &p->c;
+  const int *lc = p->lcblkb + 10 * iblk;
+  int iel = lc[0], lcsyst = lc[2], nenl = lc[4], nenbl = lc[5], nshl = lc[8], nshlb = lc[9];
+  int npro = lc[10] - iel, nshg = c->nshg;
+  if (lcsyst == 3) lcsyst = nenbl; /* elmgmr.f:267 */
+  int lnode[5] = {0, 1, 2, 3, 4}, ipt2, ipt3;
+  if (lcsyst == 4) {
+    lnode[2] = 4;
+    lnode[3] = 5;
+    lnode[4] = 2;
+  }
+  if (lcsyst == 1) {
+    ipt2 = 2;
+    ipt3 = 3;
+  } else if (lcsyst == 2) {
+    ipt2 = 4;
+    ipt3 = 2;
+  } else if (lcsyst == 3) {
+    ipt2 = 3;
+    ipt3 = 2;
+  } else if (lcsyst == 4) {
+    ipt2 = 2;
+    ipt3 = 4;
+  } else {
+    fprintf(stderr, "orc_inc_elmgmr: boundary block lcsyst %d not restated\n", lcsyst);
+    abort();
+  }
+  int ngaussb = c->nintb[lcsyst - 1];
+  const int *ien = p->ienb + p->ienb_off[iblk];
+  const int *iBCB = p->iBCB + p->iBCB_off[iblk];
+  const double *BCB = p->BCB + p->BCB_off[iblk];
+  double(*rl)[9][5] = calloc((size_t)npro, sizeof *rl);
+  for (int intp = 1; intp <= ngaussb; intp++) {
+    double sum1 = 0, sum2 = 0, sum3 = 0; /* Force uses sum() over the block (e3b.f:236-238) */
+    for (int e = 0; e < npro; e++) {
+      double yl[9][5], xlb[9][4];
+      for (int n = 1; n <= nshl; n++) {
+        int A = abs(ien[e + (size_t)npro * (n - 1)]) - 1;
+        yl[n][1] = p->y[A + (size_t)nshg * 3];
+        yl[n][2] = p->y[A + (size_t)nshg * 0];
+        yl[n][3] = p->y[A + (size_t)nshg * 1];
+        yl[n][4] = p->y[A + (size_t)nshg * 2];
+        for (int i = 1; i <= 3; i++) xlb[n][i] = p->x[A + (size_t)c->numnp * (i - 1)];
+      }
+      double shape[9], shdrv[4][9];
+      for (int n = 1; n <= nshl; n++) {
+        shape[n] = SHPB(p, lcsyst, n, intp);
+        for (int i = 1; i <= 3; i++) shdrv[i][n] = SHGLB(p, lcsyst, i, n, intp);
+      }
+      double rmu = ip->rmu, rho = ip->rho;
+      double pres = 0, u1 = 0, u2 = 0, u3 = 0;
+      for (int k = 1; k <= nshlb; k++) {
+        int n = lnode[k];
+        pres += shape[n] * yl[n][1];
+        u1 += shape[n] * yl[n][2];
+        u2 += shape[n] * yl[n][3];
+        u3 += shape[n] * yl[n][4];
+      }
+      double dxdxib[4][4];
+      memset(dxdxib, 0, sizeof dxdxib);
+      for (int n = 1; n <= nenl; n++)
+        for (int i = 1; i <= 3; i++)
+          for (int j = 1; j <= 3; j++) dxdxib[i][j] += xlb[n][i] * shdrv[j][n];
+      double v1[4], v2[4];
+      for (int i = 1; i <= 3; i++) {
+        v1[i] = xlb[ipt2][i] - xlb[1][i];
+        v2[i] = xlb[ipt3][i] - xlb[1][i];
+      }
+      double t1 = v1[2] * v2[3] - v2[2] * v1[3];
+      double t2 = v2[1] * v1[3] - v1[1] * v2[3];
+      double t3 = v1[1] * v2[2] - v2[1] * v1[2];
+      double temp = 1.0 / sqrt(t1 * t1 + t2 * t2 + t3 * t3);
+      double bn[4] = {0, t1 * temp, t2 * temp, t3 * temp};
+      double WdetJb = (lcsyst == 3) ? QWTB(c, lcsyst, intp) / (2.0 * temp) : QWTB(c, lcsyst, intp) / (4.0 * temp);
+      double d[4][4];
+      d[1][1] = dxdxib[2][2] * dxdxib[3][3] - dxdxib[3][2] * dxdxib[2][3];
+      d[1][2] = dxdxib[3][2] * dxdxib[1][3] - dxdxib[1][2] * dxdxib[3][3];
+      d[1][3] = dxdxib[1][2] * dxdxib[2][3] - dxdxib[1][3] * dxdxib[2][2];
+      temp = 1.0 / (d[1][1] * dxdxib[1][1] + d[1][2] * dxdxib[2][1] + d[1][3] * dxdxib[3][1]);
+      d[1][1] *= temp;
+      d[1][2] *= temp;
+      d[1][3] *= temp;
+      d[2][1] = (dxdxib[2][3] * dxdxib[3][1] - dxdxib[2][1] * dxdxib[3][3]) * temp;
+      d[2][2] = (dxdxib[1][1] * dxdxib[3][3] - dxdxib[3][1] * dxdxib[1][3]) * temp;
+      d[2][3] = (dxdxib[2][1] * dxdxib[1][3] - dxdxib[1][1] * dxdxib[2][3]) * temp;
+      d[3][1] = (dxdxib[2][1] * dxdxib[3][2] - dxdxib[2][2] * dxdxib[3][1]) * temp;
+      d[3][2] = (dxdxib[3][1] * dxdxib[1][2] - dxdxib[1][1] * dxdxib[3][2]) * temp;
+      d[3][3] = (dxdxib[1][1] * dxdxib[2][2] - dxdxib[1][2] * dxdxib[2][1]) * temp;
+      double gl[4][5];
+      memset(gl, 0, sizeof gl);
+      for (int n = 1; n <= nshl; n++)
+        for (int i = 1; i <= 3; i++)
+          for (int m = 1; m <= 4; m++) gl[i][m] += shdrv[i][n] * yl[n][m];
+      double g1[5], g2[5], g3[5];
+      for (int m = 2; m <= 4; m++) {
+        g1[m] = d[1][1] * gl[1][m] + d[2][1] * gl[2][m] + d[3][1] * gl[3][m];
+        g2[m] = d[1][2] * gl[1][m] + d[2][2] * gl[2][m] + d[3][2] * gl[3][m];
+        g3[m] = d[1][3] * gl[1][m] + d[2][3] * gl[2][m] + d[3][3] * gl[3][m];
+      }
+      double unm = bn[1] * u1 + bn[2] * u2 + bn[3] * u3;
+      double tau1n = bn[1] * 2.0 * rmu * g1[2] + bn[2] * (rmu * (g2[2] + g1[3])) + bn[3] * (rmu * (g3[2] + g1[4]));
+      double tau2n = bn[1] * (rmu * (g2[2] + g1[3])) + bn[2] * 2.0 * rmu * g2[3] + bn[3] * (rmu * (g3[3] + g2[4]));
+      double tau3n = bn[1] * (rmu * (g3[2] + g1[4])) + bn[2] * (rmu * (g3[3] + g2[4])) + bn[3] * 2.0 * rmu * g3[4];
+      double tn = bn[1] * tau1n + bn[2] * tau2n + bn[3] * tau3n;
+      pres = pres - tn;
+      tau1n = tau1n - bn[1] * tn;
+      tau2n = tau2n - bn[2] * tn;
+      tau3n = tau3n - bn[3] * tn;
+      tau1n = tau1n * ip->iviscflux;
+      tau2n = tau2n * ip->iviscflux;
+      tau3n = tau3n * ip->iviscflux;
+      /* ---- e3b.f:53-118 ---- */
+      int ibcb = iBCB[e], iface = abs(iBCB[e + (size_t)npro]);
+      int listed = ip->nsrflist && iface <= 1000 && ip->nsrflist[iface] != 0;
+      if (listed && p->aerfrc) {
+        double *fl = p->aerfrc + 4 + 10 * iface;
+        fl[0] = fl[0] + WdetJb;
+        fl[1] = fl[1] - WdetJb * unm;
+        fl[2] = fl[2] - (tau1n - bn[1] * pres) * WdetJb;
+        fl[3] = fl[3] - (tau2n - bn[2] * pres) * WdetJb;
+        fl[4] = fl[4] - (tau3n - bn[3] * pres) * WdetJb;
+      }
+#define BCBv(n, k) BCB[e + (size_t)npro * (((n)-1) + (size_t)nshlb * ((k)-1))]
+      if (ibcb & 1) {
+        unm = 0;
+        for (int n = 1; n <= nshlb; n++) unm = unm + shape[lnode[n]] * BCBv(n, 1);
+      }
+      if (ibcb & 2) {
+        pres = 0;
+        for (int n = 1; n <= nshlb; n++) pres = pres + shape[lnode[n]] * BCBv(n, 2);
+      }
+      if (ibcb & 4) {
+        tau1n = tau2n = tau3n = 0;
+        for (int n = 1; n <= nshlb; n++) {
+          tau1n = tau1n + shape[lnode[n]] * BCBv(n, 3);
+          tau2n = tau2n + shape[lnode[n]] * BCBv(n, 4);
+          tau3n = tau3n + shape[lnode[n]] * BCBv(n, 5);
+        }
+      }
+#undef BCBv
+      if (ibcb & 16) {
+        fprintf(stderr, "orc_inc_elmgmr: deformable-wall boundary elements (iBCB bit 4) are not restated\n");
+        abort();
+      }
+      double rNa[5];
+      rNa[1] = -WdetJb * (tau1n - bn[1] * pres - 0.0);
+      rNa[2] = -WdetJb * (tau2n - bn[2] * pres - 0.0);
+      rNa[3] = -WdetJb * (tau3n - bn[3] * pres - 0.0);
+      rNa[4] = WdetJb * unm;
+      if (ip->iconvflow == 1) {
+        double rou = rho * unm;
+        rNa[1] = rNa[1] + WdetJb * rou * u1;
+        rNa[2] = rNa[2] + WdetJb * rou * u2;
+        rNa[3] = rNa[3] + WdetJb * rou * u3;
+      }
+      for (int k = 1; k <= nshlb; k++) {
+        int n = lnode[k];
+        for (int m = 1; m <= 4; m++) rl[e][n][m] = rl[e][n][m] - shape[n] * rNa[m];
+      }
+      if (abs(ip->itwmod) == 1 && listed) { /* e3b.f:224-240, ires != 2, iter == nitr; nsrflist == 1 */
+        if (ip->nsrflist[iface] == 1) {
+          sum1 += (tau1n - bn[1] * pres) * WdetJb;
+          sum2 += (tau2n - bn[2] * pres) * WdetJb;
+          sum3 += (tau3n - bn[3] * pres) * WdetJb;
+        }
+      }
+    }
+    if (abs(ip->itwmod) == 1 && p->aerfrc) {
+      p->aerfrc[0] = p->aerfrc[0] - sum1;
+      p->aerfrc[1] = p->aerfrc[1] - sum2;
+      p->aerfrc[2] = p->aerfrc[2] - sum3;
+    }
+  }
+  for (int j = 1; j <= 4; j++)
+    for (int i = 1; i <= nshl; i++)
+      for (int e = 0; e < npro; e++) {
+        int A = abs(ien[e + (size_t)npro * (i - 1)]) - 1;
+        res[A + (size_t)nshg * (j - 1)] += rl[e][i][j];
+      }
+  free(rl);
+}
+
+/* ElmGMR (incompressible/elmgmr.f:1-330).  res[m] (nshg,4),
  * lhsK[m] (9,nnz_tot), lhsP[m] (4,nnz_tot) per part; qres/rmass of the parts are work
  * space; xKebe/xGoC (numel,9|4,nshape,nshape) per part optional (post-bc3LHS). */
 void orc_inc_elmgmr(int nparts, orc_part *parts, const orc_incomp *ip, double **res, double **lhsK, double **lhsP,
                     double **xKebe, double **xGoC) {
-  for (int m = 0; m < nparts; m++)
-    if (parts[m].c.nelblb > 0) {
-      fprintf(stderr, "orc_inc_elmgmr: boundary-element blocks are not restated for incompressible flow\n");
-      abort();
-    }
   if (ip->itau != 0 || ip->ipord != 1) {
     fprintf(stderr, "orc_inc_elmgmr: only itau=0, ipord=1 are restated\n");
     abort();
@@ -710,10 +893,16 @@ void orc_inc_elmgmr(int nparts, orc_part *parts, const orc_incomp *ip, double **
     }
     for (int iblk = 0; iblk < p->c.nelblk; iblk++)
       asigmr_i(p, ip, iblk, res[m], lhsK[m], lhsP[m], xKebe ? xKebe[m] : NULL, xGoC ? xGoC[m] : NULL);
+    if (p->aerfrc) memset(p->aerfrc + 4, 0, sizeof(double) * 10 * 1001); /* flxID = zero (elmgmr.f:130) */
+    for (int iblk = 0; iblk < p->c.nelblb; iblk++) asbmfg_i(p, ip, iblk, res[m]);
   }
   if (nparts > 1) orc_commu(nparts, parts, res, 4, 0);
   for (int m = 0; m < nparts; m++) bc3res_i(&parts[m], res[m]);
 }
+
+/* bc3Res alone on one part's res(nshg,4) (incompressible/bc3res.f): a linear map, which lets a test isolate what the
+ * boundary blocks contributed to the final residual */
+void orc_inc_bc3res(orc_part *p, double *res) { bc3res_i(p, res); }
 
 /* ---- lesSparse.f: the matrix-vector products of the coupled momentum/continuity system ---- */
 #define KL(m, k) kLhs[((m)-1) + 9 * (size_t)((k)-1)]

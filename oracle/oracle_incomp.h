@@ -12,6 +12,10 @@ typedef struct orc_incomp {
   int iconvflow, itau, idiff, ipord, lhs, matflg5;
   double rho, rmu, bf[3];
   double flmpl, flmpr, Delt, Dtgl, almi, alfi, gami, dtsfct, taucfct;
+  /* boundary integral (incompressible/e3b.f, e3bvar.f): /nomodule/ iviscflux, /turbvari/ itwmod,
+   * /aerfrc/ nsrflist(0:MAXSURF) (NULL = no surface in the flux list); ideformwall = 0 */
+  int iviscflux, itwmod;
+  const int *nsrflist;
 } orc_incomp;
 
 #ifdef __cplusplus
@@ -20,6 +24,7 @@ extern "C" {
 int orc_sizeof_incomp(void);
 void orc_inc_elmgmr(int nparts, orc_part *parts, const orc_incomp *ip, double **res, double **lhsK, double **lhsP,
                     double **xKebe, double **xGoC);
+void orc_inc_bc3res(orc_part *p, double *res);
 void orc_les_apg(int n, const int *col, const int *row, const double *pLhs, const double *p, double *q);
 void orc_les_apkg(int n, const int *col, const int *row, const double *kLhs, const double *pLhs, const double *p,
                   double *q);

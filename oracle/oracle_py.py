@@ -47,7 +47,8 @@ class OrcIncomp(C.Structure):
     _fields_ = [*[(n, C.c_int) for n in ("iconvflow", "itau", "idiff", "ipord", "lhs", "matflg5")],
                 ("rho", C.c_double), ("rmu", C.c_double), ("bf", C.c_double * 3),
                 *[(n, C.c_double) for n in ("flmpl", "flmpr", "Delt", "Dtgl", "almi", "alfi", "gami",
-                                            "dtsfct", "taucfct")]]
+                                            "dtsfct", "taucfct")],
+                ("iviscflux", C.c_int), ("itwmod", C.c_int), ("nsrflist", C.POINTER(C.c_int))]
 
     @classmethod
     def from_params(cls, ip):
@@ -58,6 +59,11 @@ class OrcIncomp(C.Structure):
             setattr(s, n, float(getattr(ip, n)))
         for i in range(3):
             s.bf[i] = float(ip.bf[i])
+        s.iviscflux, s.itwmod = int(ip.iviscflux), int(ip.itwmod)
+        s._nsrf = (C.c_int * 1001)()            # nsrflist(0:MAXSURF), kept alive with the struct
+        for k in ip.surfaces:
+            s._nsrf[int(k)] = 1
+        s.nsrflist = C.cast(s._nsrf, C.POINTER(C.c_int))
         return s
 
 
@@ -282,6 +288,12 @@ class Oracle:
         self.L.orc_inc_elmgmr(self.n, self.arr, C.byref(s), self._vecs([p.res4 for p in self.parts]),
                               self._vecs([p.lhsK9 for p in self.parts]), self._vecs([p.lhsP4 for p in self.parts]),
                               ebe[0], ebe[1])
+
+    def IncBc3Res(self, res, part=0):
+        """bc3Res of the incompressible code alone, in place on res (nshg,4)"""
+        assert res.flags.f_contiguous and res.shape == (self.parts[part].mp.nshg, 4)
+        self.L.orc_inc_bc3res(C.byref(self.arr[part]), _ptr(res))
+        return res
 
     def LesAp(self, kind, pvec, part=0):
         """fLesSparseAp{G,KG,NGt,NGtC,Full} (lesSparse.f:204-492) on one part's lhsK9/lhsP4."""

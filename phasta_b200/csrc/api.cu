@@ -155,11 +155,16 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   // ---- boundary elements (genbkbPosix.f:113-123 lcblkb rows; asbmfg.f)
   ctx->numelb = 0;
   ctx->d_ienb = nullptr; ctx->d_iBCB = nullptr; ctx->d_BCB = nullptr;
+  ctx->have_inc_btabs = false; ctx->d_nsrflist = nullptr; ctx->bnd_deformable = false;
   if (c->nelblb > 0) {
     if (!lcblkb || !mienb || !miBCB || !mBCB || !shpb || !shglb) return fail("init", "null boundary arrays");
-    for (int b = 0; b < c->nelblb; b++)
+    for (int b = 0; b < c->nelblb; b++) {
       if (phb_bnd_kind(lcblkb + 10 * b) < 0)
         return fail("init", "boundary block is not a linear tet, hex or wedge (lcsyst 1..4) with its face on lnode");
+      const int npro = lcblkb[10 * b + 10] - lcblkb[10 * b];
+      for (int e = 0; e < npro; e++)
+        if (miBCB[b][e] & 16) ctx->bnd_deformable = true;   // e3b.f (incompressible): vessel-wall elements
+    }
     for (int k = 0; k < 4; k++) {
       std::vector<int> ienb, ib;
       std::vector<double> bcb;
@@ -212,6 +217,10 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   ctx->d_res4 = ctx->d_lhsK9 = ctx->d_lhsP4 = ctx->d_lesp = ctx->d_lesq = ctx->d_lesp4 = nullptr;
   ctx->d_tpos = nullptr;
   ctx->have_inc_tabs = false;
+  if (shpb && shglb) {
+    ctx->h_shpb.assign(shpb, shpb + (size_t)PHB200_MAXTOP * PHB200_MAXSH * PHB200_MAXQPT);
+    ctx->h_shglb.assign(shglb, shglb + (size_t)PHB200_MAXTOP * 3 * PHB200_MAXSH * PHB200_MAXQPT);
+  }
   ctx->h_shp.assign(shp, shp + (size_t)PHB200_MAXTOP * PHB200_MAXSH * PHB200_MAXQPT);
   ctx->h_shgl.assign(shgl, shgl + (size_t)PHB200_MAXTOP * 3 * PHB200_MAXSH * PHB200_MAXQPT);
   ctx->eGMRES = 0.0;

@@ -143,6 +143,10 @@ struct phb200_ctx {
   int *d_tpos;
   bool have_inc_tabs;
   int inc_idiff;
+  std::vector<double> h_shpb, h_shglb; // the same for the boundary-face tables
+  bool have_inc_btabs;                 // c_ibnd uploaded, d_nsrflist allocated
+  int *d_nsrflist;                     // nsrflist(0:MAXSURF) of the last incompressible call
+  bool bnd_deformable;                 // some boundary element carries iBCB bit 4 (deformable wall)
   std::vector<double> h_shp, h_shgl;   // host copies of shp / shgl (the incompressible kernels build their tables lazily)
   // ---- matrix-free flavour (SolMFG): ypre, two work vectors [3][5][nshg]; eGMRES of COMMON /itrpar/
   double *d_mfg;

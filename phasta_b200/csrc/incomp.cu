@@ -42,6 +42,15 @@ struct IncPhys {
   int iconvflow, idiff, matflg5, lhs;
 };
 __constant__ IncPhys c_ip;
+#include "bnd_pack.h"
+struct IncBndPhys {
+  double rho, rmu;                  // getDiff (incompressible/getdiff.f:24-27), iLSet = 0, DNS
+  int iviscflux, iconvflow, itwmod;
+};
+__constant__ IncBndPhys c_ibp;
+__constant__ BndTables c_ibnd[4];   // face tables of lcsyst 1..4 (index lcsyst-1)
+#include "inc_boundary.cuh"
+
 
 static int inc_tab_index(int lcsyst) { return lcsyst == 1 ? 0 : (lcsyst == 2 ? 1 : 2); }
 
@@ -987,6 +996,59 @@ void phb_inc_free(phb200_ctx *ctx) {
     if (q) cudaFree(q);
   ctx->d_res4 = ctx->d_lhsK9 = ctx->d_lhsP4 = ctx->d_lesp = ctx->d_lesq = ctx->d_lesp4 = nullptr;
   ctx->d_tpos = nullptr;
+  if (ctx->d_nsrflist) cudaFree(ctx->d_nsrflist);
+  ctx->d_nsrflist = nullptr;
+  ctx->have_inc_btabs = false;
+}
+
+// the boundary blocks of ElmGMR (incompressible/elmgmr.f:246-320): flxID = 0 (elmgmr.f:130), AsBMFG per block
+static int inc_boundary(phb200_ctx *ctx, const phb200_incomp *ip) {
+  const phb200_common &c = ctx->c;
+  cudaStream_t s = ctx->stream;
+  const int nshg = c.nshg;
+  if (!ctx->have_inc_btabs) {
+    const double *shpb = ctx->h_shpb.data(), *shglb = ctx->h_shglb.data();
+    auto fill = [&](int lcsyst, int nshl) -> int {
+      BndTables b;
+      if (phb_bnd_fill_tables(&b, lcsyst, nshl, c.nintb, c.Qwtb, shpb, shglb)) return 1;
+      PHB_CHECK(cudaMemcpyToSymbol(c_ibnd, &b, sizeof b, sizeof(BndTables) * (lcsyst - 1)));
+      return 0;
+    };
+    if (ctx->numelb > 0) PHB_TRY(fill(1, 4));
+    for (const BndGroup &g : ctx->bgen) PHB_TRY(fill(g.lcsyst, g.nshl));
+    PHB_CHECK(cudaMalloc(&ctx->d_nsrflist, sizeof(int) * 1001));
+    ctx->have_inc_btabs = true;
+  }
+  IncBndPhys bp;
+  bp.rho = ip->rho; bp.rmu = ip->rmu;
+  bp.iviscflux = ip->iviscflux; bp.iconvflow = ip->iconvflow; bp.itwmod = ip->itwmod;
+  PHB_CHECK(cudaMemcpyToSymbolAsync(c_ibp, &bp, sizeof bp, 0, cudaMemcpyHostToDevice, s));
+  if (ip->nsrflist) {
+    // pageable source: the copy is staged before the call returns, the caller's array may go away afterwards
+    PHB_CHECK(cudaMemcpyAsync(ctx->d_nsrflist, ip->nsrflist, sizeof(int) * 1001, cudaMemcpyHostToDevice, s));
+  } else {
+    PHB_CHECK(cudaMemsetAsync(ctx->d_nsrflist, 0, sizeof(int) * 1001, s));
+  }
+  PHB_CHECK(cudaMemsetAsync(ctx->d_aerfrc + 4, 0, sizeof(double) * 10 * 1001, s));
+  KScope ks(ctx, KC_ASM);
+  long long nl = 0;
+#define PHB_IBND_LAUNCH(NSHL, NSHLB, LCS, N, IEN, IB, BCBP)                                                       \
+  k_inc_asbmfg<NSHL, NSHLB, LCS><<<((N) + 127) / 128, 128, 0, s>>>((N), nshg, c.numnp, (IEN), (IB), (BCBP), ctx->d_x, \
+                                                                  ctx->d_y, ctx->d_nsrflist, ctx->d_res4, ctx->d_aerfrc)
+  if (ctx->numelb > 0) {
+    PHB_IBND_LAUNCH(4, 3, 1, ctx->numelb, ctx->d_ienb, ctx->d_iBCB, ctx->d_BCB);
+    nl++;
+  }
+  for (const BndGroup &g : ctx->bgen) {
+    if (g.lcsyst == 2) PHB_IBND_LAUNCH(8, 4, 2, g.n, g.d_ien, g.d_iBCB, g.d_BCB);
+    else if (g.lcsyst == 3) PHB_IBND_LAUNCH(6, 3, 3, g.n, g.d_ien, g.d_iBCB, g.d_BCB);
+    else PHB_IBND_LAUNCH(6, 4, 4, g.n, g.d_ien, g.d_iBCB, g.d_BCB);
+    nl++;
+  }
+#undef PHB_IBND_LAUNCH
+  ctx->launches += nl - 1;  // KScope counted one
+  PHB_CHECK(cudaGetLastError());
+  return 0;
 }
 
 // ElmGMR (incompressible/elmgmr.f:1-330) on the device-resident y / ac
@@ -994,8 +1056,8 @@ int phb_inc_elmgmr(phb200_ctx *ctx, const phb200_incomp *ip) {
   const phb200_common &c = ctx->c;
   const size_t nshg = c.nshg;
   cudaStream_t s = ctx->stream;
-  if (c.nelblb > 0) {
-    fprintf(stderr, "phb200: inc_elmgmr: boundary-element blocks (AsBMFG/e3b of the incompressible code) are not built\n");
+  if (c.nelblb > 0 && ctx->bnd_deformable) {
+    fprintf(stderr, "phb200: inc_elmgmr: deformable-wall boundary elements (iBCB bit 4, ideformwall) are not built\n");
     return 1;
   }
   if (ip->itau != 0 || ip->ipord != 1 || (ip->idiff != 0 && ip->idiff != 1) || (ip->iconvflow != 1 && ip->iconvflow != 2) ||
@@ -1032,6 +1094,7 @@ int phb_inc_elmgmr(phb200_ctx *ctx, const phb200_incomp *ip) {
     PHB_CHECK(cudaMemsetAsync(ctx->d_lhsP4, 0, sizeof(double) * 4 * (size_t)ctx->nnz_tot, s));
   }
   PHB_TRY(launch_all(ctx, ip->lhs == 1, false));
+  if (c.nelblb > 0) PHB_TRY(inc_boundary(ctx, ip));  // elmgmr.f:246-320
   PHB_TRY(phb_commu(ctx, ctx->d_res4, 4, 0));
   // bc3Res: bc3per (periodic sum, rows owned by another part zeroed) then the essential-BC projections
   PHB_TRY(phb_bc3per(ctx, ctx->d_res4, 4));

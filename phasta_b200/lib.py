@@ -43,7 +43,8 @@ class PhbIncomp(C.Structure):
     _fields_ = [*[(n, C.c_int) for n in ("iconvflow", "itau", "idiff", "ipord", "lhs", "matflg5")],
                 ("rho", C.c_double), ("rmu", C.c_double), ("bf", C.c_double * 3),
                 *[(n, C.c_double) for n in ("flmpl", "flmpr", "Delt", "Dtgl", "almi", "alfi", "gami",
-                                            "dtsfct", "taucfct")]]
+                                            "dtsfct", "taucfct")],
+                ("iviscflux", C.c_int), ("itwmod", C.c_int), ("nsrflist", C.POINTER(C.c_int))]
 
     @classmethod
     def from_params(cls, ip, **over):
@@ -54,6 +55,11 @@ class PhbIncomp(C.Structure):
             setattr(s, n, float(over.get(n, getattr(ip, n))))
         for i in range(3):
             s.bf[i] = float(ip.bf[i])
+        s.iviscflux, s.itwmod = int(ip.iviscflux), int(ip.itwmod)
+        s._nsrf = (C.c_int * 1001)()            # nsrflist(0:MAXSURF); lives as long as the struct
+        for k in ip.surfaces:
+            s._nsrf[int(k)] = 1
+        s.nsrflist = C.cast(s._nsrf, C.POINTER(C.c_int))
         return s
 
 

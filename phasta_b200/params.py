@@ -88,6 +88,12 @@ class IncompParams:
     gami: float = 1.0
     dtsfct: float = 1.0
     taucfct: float = 1.0
+    # boundary integral (incompressible/e3b.f, e3bvar.f): viscous flux flag (/nomodule/ iviscflux), wall-model
+    # switch whose |1| turns the Force integral on (/turbvari/ itwmod), the surface IDs whose nsrflist entry is 1
+    # (/aerfrc/ nsrflist(0:MAXSURF): flux through / force on these surfaces is integrated)
+    iviscflux: int = 1
+    itwmod: int = 0
+    surfaces: tuple = ()
 
     @property
     def Dtgl(self):

@@ -22,7 +22,7 @@ from make_golden_f77 import F, set_commons, set_pointer_data, full_tables  # noq
 
 REF = "/root/reference/phSolver"
 INC = ["elmgmr.f", "asigmr.f", "asiq.f", "e3.f", "e3ivar.f", "e3stab.f", "e3res.f", "e3lhs.f", "e3q.f", "e3qvar.f",
-       "getdiff.f", "bc3lhs.f", "bc3res.f", "bc3per.f", "lesSparse.f"]
+       "getdiff.f", "bc3lhs.f", "bc3res.f", "bc3per.f", "lesSparse.f", "asbmfg.f", "e3b.f", "e3bvar.f"]
 COMMON = ["clear.f", "mpitools.f", "e3metric.f", "local.f", "localy.f", "hierarchic.f", "qpbc.f", "fillsparse.f", "genadj.f",
           "asadj.f"]
 
@@ -36,6 +36,14 @@ CASES = {
     "hex_allbc": ((4, 3, 3), dict(bc="allcodes", topo="hex", ibksiz=8), dict()),
     "mixed_topo": ((2, 4, 2), dict(bc="channel", topo="mixed", ibksiz=16), dict(iconvflow=1)),
     "resonly": ((3, 3, 3), dict(bc="allcodes", ibksiz=16), dict(lhs=0)),
+    # the boundary integral (incompressible/asbmfg.f, e3b.f, e3bvar.f; rigid walls): tets, then hexes, then a mixed
+    # mesh with triangular and quadrilateral wedge faces; every natural-BC code; flux through surfaces 1..3 recorded
+    "tet_bnd": ((3, 2, 2), dict(bc="channel", ibksiz=16, boundary=True, natural="mixed"),
+                dict(itwmod=1, surfaces=(1, 2, 3))),
+    "hex_bnd": ((3, 2, 2), dict(bc="channel", topo="hex", ibksiz=8, boundary=True, natural="mixed", periodic_z=False),
+                dict(iconvflow=1, itwmod=1, surfaces=(2, 3, 5), iviscflux=0)),
+    "mixed_bnd": ((2, 4, 2), dict(bc="channel", topo="mixed", ibksiz=16, boundary=True, natural="mixed",
+                                  periodic_z=False), dict(itwmod=-1, surfaces=(1, 4, 6))),
 }
 
 
@@ -86,7 +94,13 @@ def run(prog, case, ip, nnz=35):
              iconvflow=int(ip.iconvflow), ipord=int(ip.ipord), flmpl=float(ip.flmpl), flmpr=float(ip.flmpr),
              almi=float(ip.almi), alfi=float(ip.alfi), gami=float(ip.gami), dtgl=float(ip.Dtgl),
              dtsfct=float(ip.dtsfct), taucfct=float(ip.taucfct), itseq=1, iles=0, irans=0, ilset=0, isurf=0,
-             ierrcalc=0, icomputevort=0, ipvsq=0, iabc=0, intpres=0, nnz=nnz, iter=1, nitr=1, numpe=1)
+             ierrcalc=0, icomputevort=0, ipvsq=0, iabc=0, intpres=0, nnz=nnz, iter=1, nitr=1, numpe=1,
+             ideformwall=0, iviscflux=int(ip.iviscflux), itwmod=int(ip.itwmod), navier=1)
+    G["nsrflist"][...] = 0
+    for k in ip.surfaces:           # the force / flux list (input.config "Surface ID's for Integrated Mass")
+        G["nsrflist"][int(k)] = 1
+    G["flxid"][...] = 0.0
+    G["force"][...] = 0.0
     G["delt"][0] = float(ip.Delt)
     G["impl"][0] = 10
     G["datmat"][...] = 0.0
@@ -116,6 +130,9 @@ def run(prog, case, ip, nnz=35):
     prog.call("elmgmr", u, y, ac, x, shp, shgl, iBC, BC, shpb, shglb, res, iper, ilwork, rowp, colm, lhsK, lhsP,
               rerr, GradV)
     out = dict(res=res, colm=colm, rowp=rowp[:nnz_tot].copy(), nnz_tot=nnz_tot)
+    if mp.nelblb:
+        out["flxID"] = np.array(G["flxid"][:5, :7], order="F")
+        out["Force"] = np.array(G["force"])
     if ip.lhs:
         out.update(lhsK=lhsK, lhsP=lhsP)
         rng = np.random.default_rng(4242)
@@ -171,6 +188,9 @@ def main():
             o.IncElmGMR(ip)
             p = o.parts[0]
             allok &= check("res", p.res4, r["res"], 1e-13)
+            if "flxID" in r:
+                allok &= check("flxID", p.aerfrc[4:4 + 70].reshape((10, 7), order="F")[:5], r["flxID"], 1e-13)
+                allok &= check("Force", p.aerfrc[:3], r["Force"], 1e-13)
             if ip.lhs:
                 allok &= check("lhsK", p.lhsK9, r["lhsK"], 1e-13)
                 allok &= check("lhsP", p.lhsP4, r["lhsP"], 1e-13)

@@ -26,6 +26,15 @@ def emul():
     return C.CDLL(OUT)
 
 
+@pytest.fixture(scope="module")
+def emul_inc():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    out = os.path.join(os.path.dirname(OUT), "libinc_bnd_host.so")
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                           "-o", out, os.path.join(HERE, "host_emul", "inc_bnd_host.cpp")])
+    return C.CDLL(out)
+
+
 def _ptrs(arrs, ctype):
     keep = [np.ascontiguousarray(np.asfortranarray(a).ravel(order="F")) for a in arrs]
     return keep, (C.POINTER(ctype) * len(keep))(*[a.ctypes.data_as(C.POINTER(ctype)) for a in keep])
@@ -68,3 +77,54 @@ def test_boundary_kernel_on_the_host_matches_reference_fortran(emul, name):
     assert rel_l2(aer[:4], ref_f) < 1e-12
     fl = aer[4:4 + 20].reshape((10, 2), order="F")
     assert rel_l2(fl, z["elmgmre.flxID"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["tet_bnd", "hex_bnd", "mixed_bnd"])
+def test_incompressible_boundary_kernel_on_the_host_matches_reference_fortran(emul_inc, name):
+    """k_inc_asbmfg (inc_boundary.cuh) against incompressible/asbmfg.f + e3b.f + e3bvar.f: flxID and Force come from
+    the boundary blocks alone; their share of the residual is isolated through the linearity of bc3Res:
+    res(with boundary blocks) - res(without) = bc3Res(what the kernel scattered)."""
+    import copy
+    from common import make_oracle
+    from test_incomp import load as load_inc
+    z, case, ip = load_inc(name)
+    params, tables, parts, states = case
+    mp = parts[0]
+    y = np.asfortranarray(states[0][0])
+    contrib = np.zeros((mp.nshg, 4), order="F")
+    aer = np.zeros(4 + 10 * 1001)
+    k1, pien = _ptrs([b.astype(np.int32) for b in mp.mienb], C.c_int)
+    k2, pibc = _ptrs([b.astype(np.int32) for b in mp.miBCB], C.c_int)
+    k3, pbcb = _ptrs([b.astype(np.float64) for b in mp.mBCB], C.c_double)
+    lcb = np.ascontiguousarray(mp.lcblkb.T.astype(np.int32).ravel())
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)       # noqa: E731
+    T = {k: np.asfortranarray(tables[k]) for k in ("nintb", "Qwtb", "shpb", "shglb")}
+    nintb = T["nintb"].astype(np.int32)
+    nsrf = np.zeros(1001, dtype=np.int32)
+    nsrf[list(ip.surfaces)] = 1
+    emul_inc.inc_bnd_host_asbmfg.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.c_double, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]
+    n = emul_inc.inc_bnd_host_asbmfg(mp.nelblb, vp(lcb), pien, pibc, pbcb, mp.nshg, mp.numnp,
+                                     vp(np.asfortranarray(mp.x)), vp(y), vp(nintb), vp(T["Qwtb"]), vp(T["shpb"]),
+                                     vp(T["shglb"]), float(ip.rho), float(ip.rmu), int(ip.iviscflux),
+                                     int(ip.iconvflow), int(ip.itwmod), vp(nsrf), vp(contrib), vp(aer))
+    assert n == sum(b.shape[0] for b in mp.mienb) > 0
+    fl = aer[4:4 + 70].reshape((10, 7), order="F")[:5]
+    assert rel_l2(fl, z["flxID"]) < 1e-12 and np.abs(z["flxID"]).max() > 0
+    assert rel_l2(aer[:3], z["Force"]) < 1e-12 and np.abs(z["Force"]).max() > 0
+    # the residual: oracle == reference bit for bit with the boundary blocks (tests/test_incomp.py); without them:
+    o = make_oracle(case)
+    o.genadj()
+    o.IncElmGMR(ip)
+    assert np.array_equal(o.parts[0].res4, z["res"])
+    bare = copy.copy(mp)
+    bare.lcblkb, bare.mienb, bare.miBCB, bare.mBCB = None, [], [], []
+    o2 = make_oracle((params, tables, [bare], states))
+    o2.genadj()
+    o2.IncElmGMR(ip)
+    ref = z["res"] - o2.parts[0].res4
+    o.IncBc3Res(contrib)
+    assert np.abs(ref).max() > 0
+    assert np.abs(contrib - ref).max() < 1e-11 * np.abs(z["res"]).max()

@@ -35,6 +35,9 @@ def test_oracle_matches_reference_fortran_bit_for_bit(name):
     assert np.array_equal(p.colm, z["colm"]) and np.array_equal(p.rowp, z["rowp"])
     o.IncElmGMR(ip)
     assert np.array_equal(p.res4, z["res"])
+    if "flxID" in z:        # the boundary integral (incompressible/asbmfg.f, e3b.f, e3bvar.f): /aerfrc/
+        assert np.array_equal(p.aerfrc[4:4 + 70].reshape((10, 7), order="F")[:5], z["flxID"])
+        assert np.allclose(p.aerfrc[:3], z["Force"], rtol=1e-13, atol=0)      # sum() order in e3b.f:236-238
     if ip.lhs:
         assert np.array_equal(p.lhsK9, z["lhsK"])
         assert np.array_equal(p.lhsP4, z["lhsP"])
@@ -169,10 +172,18 @@ def _gpu(case):
     return g
 
 
+# fixtures added after the round's GPU budget was spent: their device runs are in tests/test_zz_gpu_late.py
+LATE = ("tet_bnd", "hex_bnd", "mixed_bnd")
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", [n for n in CASES if n not in LATE])
 def test_gpu_matches_reference_fortran(name):
     """CUDA ElmGMR / fLesSparseAp* through the C-ABI against the reference's Fortran (f77np fixtures)."""
+    check_gpu_case(name)
+
+
+def check_gpu_case(name):
     z, case, ip = load(name)
     g = _gpu(case)
     y, ac = case[3][0]
@@ -191,6 +202,10 @@ def test_gpu_matches_reference_fortran(name):
         assert rel_l2(g.LesAp("NGt", pin[:, :3]), z["apNGt"]) < TOL_ASM
         assert rel_l2(g.LesAp("NGtC", pin), z["apNGtC"]) < TOL_ASM
         assert rel_l2(g.LesAp("Full", pin), z["apFull"]) < TOL_ASM
+    if "flxID" in z:
+        Fo, _, fl = g.aerfrc()
+        assert rel_l2(fl[:5, :7], z["flxID"]) < TOL_ASM
+        assert rel_l2(Fo, z["Force"]) < TOL_ASM
     g.close()
 
 
@@ -226,9 +241,4 @@ def test_gpu_refuses_what_is_not_built():
     y, ac = case[3][0]
     with pytest.raises(PhastaError):
         g.IncElmGMR(y, ac, IncompParams(itau=1))
-    g.close()
-    caseb = make_case(4, 3, 3, bc="channel", boundary=True, natural="all")
-    g = _gpu(caseb)
-    with pytest.raises(PhastaError):
-        g.IncElmGMR(y, ac, IncompParams())
     g.close()

@@ -32,6 +32,27 @@ def test_gpu_solgmrs_with_hex_wedge_boundary_elements(name):
     check_gpu_solgmrs(name)
 
 
+# ---- the incompressible boundary integral (k_inc_asbmfg) on tet, hex and wedge faces ---------------------------
+@pytest.mark.parametrize("name", ["tet_bnd", "hex_bnd", "mixed_bnd"])
+def test_gpu_incompressible_boundary_integral(name):
+    from test_incomp import check_gpu_case
+    check_gpu_case(name)
+
+
+def test_gpu_incompressible_refuses_deformable_wall_elements():
+    from common import make_case
+    from phasta_b200 import IncompParams
+    from phasta_b200.solver import PhastaError
+    from test_incomp import _gpu
+    case = make_case(4, 3, 3, bc="channel", boundary=True, natural="mixed")
+    case[2][0].miBCB[0][0, 0] |= 16          # iBCB bit 4: vessel-wall element (incompressible/e3b.f)
+    g = _gpu(case)
+    y, ac = case[3][0]
+    with pytest.raises(PhastaError):
+        g.IncElmGMR(y, ac, IncompParams())
+    g.close()
+
+
 # ---- halo exchange against the reference's ctypes.f + commu.f fixture ------------------------------------------
 def _commu_ns():
     from test_commu_golden import NS
