@@ -19,7 +19,12 @@
 //    (w = {rho, rho u, rho(h+k)}), so sum_i N_a,i A_i is a rank-2 update of A0
 //    and all LHS terms except the viscous one collapse to ONE 5x5x5 product
 //    per (a,b,qp):  W (At_a tau + N_a I) (At_b + c N_b A0).
+// PHB_HOST_EMUL: tests/host_emul/ compiles the DEVICE code of this file with g++ behind a SIMT shim (one pthread per
+// CUDA thread) to check kernels against the reference-Fortran fixtures where there is no GPU; the host-side launch
+// code and the kernel with inline PTX are left out of that build.  The product build never defines it.
+#ifndef PHB_HOST_EMUL
 #include "ctx.h"
+#endif
 #include <cstring>
 #include "bnd_pack.h"
 
@@ -50,6 +55,7 @@ __constant__ PhysParams c_ph;
 __constant__ BndTables c_bnd[3];
 #include "boundary.cuh"
 
+#ifndef PHB_HOST_EMUL  // host: table / parameter upload
 int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, const double *shpb,
                       const double *shglb) {
   TetTables t;
@@ -143,6 +149,7 @@ static int upload_phys(phb200_ctx *ctx, const phb200_step *st) {
 // ---------------------------------------------------------------------------
 // point-wise helpers
 // ---------------------------------------------------------------------------
+#endif  // PHB_HOST_EMUL
 struct Metric {
   double shg[4][3];
   double dxidx[3][3];
@@ -790,9 +797,11 @@ __device__ __forceinline__ void dc_point(double rho, double T, const double u[3]
   for (int k = 0; k < 6; k++) gu_out[k] = gu[k];
 }
 
+// DCON: also the discontinuity-capturing operator (e3dc.f through dc_point): st then has S_NVAR_DC entries
+template <bool DCON = false>
 __device__ __forceinline__ void point_math(const double Y[5], const double At[5], const double gr[3][5],
                                            const double divq[4], const double gij[6], double ri[20],
-                                           double st[S_NVAR]) {
+                                           double *st) {
   const double pres = Y[0], u1 = Y[1], u2 = Y[2], u3 = Y[3], T = Y[4];
   const double rho = pres / (c_ph.Rgas * T);                       // getthm.f:111
   const double ei = T * (c_ph.Rgas / c_ph.gamma1);                 // getthm.f:148
@@ -859,6 +868,11 @@ __device__ __forceinline__ void point_math(const double Y[5], const double At[5]
   const double tau1 = 0.125 * fact / (rho * (gij[0] + gij[2] + gij[5])) * c_ph.taucfct;
   tau2 = 1.0 / fact;
   const double tau3 = tau2 / cv * c_ph.temper;
+  double rt[5];
+  if (DCON) {
+#pragma unroll
+    for (int m = 0; m < 5; m++) rt[m] = L[m];                      // rLyitemp (e3tau.f:177)
+  }
   L[0] *= tau1; L[1] *= tau2; L[2] *= tau2; L[3] *= tau2; L[4] *= tau3;
   A0v(L, tmpv);                                                    // e3ls.f:352-457
 #pragma unroll
@@ -868,6 +882,13 @@ __device__ __forceinline__ void point_math(const double Y[5], const double At[5]
     ri[5 * i + 1 + i] += L[0];
     ri[5 * i + 4] += u[i] * L[0];
   }
+  if (DCON) {                                                      // e3.f:217-222
+    double dcv, gu[6];
+    dc_point(rho, T, u, rk, h, cp, alfap, betaT, gr, gij, rt, L, A0v, ri, dcv, gu);
+    st[S_DC] = dcv;
+#pragma unroll
+    for (int k = 0; k < 6; k++) st[S_GU + k] = gu[k];
+  }
 #pragma unroll
   for (int m = 0; m < 5; m++) ri[15 + m] = massr[m];
   st[S_RHO] = rho; st[S_U1] = u1; st[S_U2] = u2; st[S_U3] = u3;
@@ -876,6 +897,7 @@ __device__ __forceinline__ void point_math(const double Y[5], const double At[5]
   st[S_MU] = mu; st[S_LAM] = lam; st[S_CON] = con;
 }
 
+#ifndef PHB_HOST_EMUL  // inline PTX (named barriers) and the warp-specialised kernel that uses them
 __device__ __forceinline__ void bar_sync_named(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
@@ -1012,6 +1034,7 @@ __global__ void __launch_bounds__(192, 2) k_asigmr_tet_ws(
 }
 
 // LHS: 0 residual only, 1 EBE tiles (ElmGMRe), 2 scatter into lhsK (ElmGMRs + fillsparseC)
+#endif  // PHB_HOST_EMUL
 template <int TILE_E, int NQ, int LHS, bool DCON = false>
 __global__ void __launch_bounds__(TILE_E * 4, 3) k_asigmr_tet(
     int numel, size_t numel_pad, int nshg, int numnp, int ntiles, const int *__restrict__ ien,
@@ -1546,6 +1569,7 @@ __global__ void k_per_copy(int n, const int *__restrict__ slaves, const int *__r
 }
 
 // node records [nshg][26] = x(3), Y{p,u1,u2,u3,T}(5), Y,t(5), q(12) from the resident x / y / ac / qres
+#ifndef PHB_HOST_EMUL  // host: node records, qpbc, bc3per
 int phb_pack_nodes(phb200_ctx *ctx, int with_q) {
   KScope ks(ctx, KC_NODE);
   const size_t tot = (size_t)ctx->c.nshg * NREC;
@@ -1596,6 +1620,7 @@ int phb_bc3per(phb200_ctx *ctx, double *d_r, int n) {
 // Same phases and the same rank-2 algebra as the tet kernel, but N_a,i and W vary from point to point
 // (e3metric.f:22-77 per quadrature point) and g_ij is the plain xi,x^T xi,x (e3tau.f:1408-1431).
 // ===========================================================================
+#endif  // PHB_HOST_EMUL
 template <int NSHL>
 struct GenMetric {
   double shg[NSHL][3];
@@ -1691,9 +1716,9 @@ __global__ void __launch_bounds__(64) k_asiq_gen(int tab, int numel, size_t nume
   }
 }
 
-template <int NSHL, int NQ>
+template <int NSHL, int NQ, int NV = S_NVAR>
 struct GenSmem {
-  double st[NQ][S_NVAR][32];
+  double st[NQ][NV][32];
   double ri[NQ][20][32];
   double shg[NQ][3 * NSHL][32];
   double W[NQ][32];
@@ -1702,7 +1727,7 @@ struct GenSmem {
 };
 
 // LHS: 0 residual only, 1 EBE tiles, 2 fillsparseC into lhsK.  CTA = 32 elements x NQ quadrature points.
-template <int NSHL, int NQ, int LHS>
+template <int NSHL, int NQ, int LHS, bool DCON = false>
 __global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
     int tab, int numel, size_t numel_pad, int nshg, int ntiles, const int *__restrict__ ien,
     const double *__restrict__ aos, const int *__restrict__ iBC, const double *__restrict__ BC,
@@ -1710,10 +1735,12 @@ __global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
     double *__restrict__ lhsK) {
   static_assert(NQ >= NSHL, "phase B' maps one thread group per node");
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  GenSmem<NSHL, NQ> &sm = *reinterpret_cast<GenSmem<NSHL, NQ> *>(smem_raw);
+  constexpr int NV = DCON ? S_NVAR_DC : S_NVAR;
+  using SM = GenSmem<NSHL, NQ, NV>;
+  SM &sm = *reinterpret_cast<SM *>(smem_raw);
   const GenTables &T = c_gen[tab];
   const int tid = threadIdx.x, el = tid & 31, sub = tid >> 5;
-  double *stage = (LHS == 2) ? reinterpret_cast<double *>(smem_raw + sizeof(GenSmem<NSHL, NQ>)) + sub * STAGE_DBL : nullptr;
+  double *stage = (LHS == 2) ? reinterpret_cast<double *>(smem_raw + sizeof(SM)) + sub * STAGE_DBL : nullptr;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int e = tile * 32 + el;
     const bool live = e < numel;
@@ -1784,13 +1811,13 @@ __global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
       gij[3] = d[0][0] * d[0][2] + d[1][0] * d[1][2] + d[2][0] * d[2][2];
       gij[4] = d[0][1] * d[0][2] + d[1][1] * d[1][2] + d[2][1] * d[2][2];
       gij[5] = d[0][2] * d[0][2] + d[1][2] * d[1][2] + d[2][2] * d[2][2];
-      double ri[20], st[S_NVAR];
-      point_math(Y, At, gr, divq, gij, ri, st);
+      double ri[20], st[NV];
+      point_math<DCON>(Y, At, gr, divq, gij, ri, st);
 #pragma unroll
       for (int k = 0; k < 20; k++) sm.ri[q][k][el] = ri[k];
       if (LHS) {
 #pragma unroll
-        for (int k = 0; k < S_NVAR; k++) sm.st[q][k][el] = st[k];
+        for (int k = 0; k < NV; k++) sm.st[q][k][el] = st[k];
       }
     }
     __syncthreads();
@@ -1839,6 +1866,25 @@ __global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
           const double tw1 = W * sm.st[q][S_TAU1][lane], tw2 = W * sm.st[q][S_TAU2][lane],
                        tw3 = W * sm.st[q][S_TAU3][lane];
           const double mu = sm.st[q][S_MU][lane], lam = sm.st[q][S_LAM][lane], con = sm.st[q][S_CON][lane];
+          if (DCON) {
+            // e3dc.f:300-325 + e3wmlt.f:154-223: W N_a,i (DC g^ij A0) N_b,j = W DC (g_a^T G g_b) A0
+            const double g1 = sm.st[q][S_GU + 0][lane], g2 = sm.st[q][S_GU + 1][lane], g3 = sm.st[q][S_GU + 2][lane],
+                         g4 = sm.st[q][S_GU + 3][lane], g5 = sm.st[q][S_GU + 4][lane], g6 = sm.st[q][S_GU + 5][lane];
+            const double sdc = W * sm.st[q][S_DC][lane] *
+                               (ga[0] * (g1 * gb[0] + g4 * gb[1] + g5 * gb[2]) + ga[1] * (g4 * gb[0] + g2 * gb[1] + g6 * gb[2]) +
+                                ga[2] * (g5 * gb[0] + g6 * gb[1] + g3 * gb[2]));
+            acc[0][0] += sdc * drdp;
+            acc[0][4] += sdc * drdT;
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+              acc[1 + r][0] += sdc * drdp * u[r];
+              acc[1 + r][1 + r] += sdc * rho;
+              acc[1 + r][4] += sdc * drdT * u[r];
+              acc[4][1 + r] += sdc * rho * u[r];
+            }
+            acc[4][0] += sdc * e1p;
+            acc[4][4] += sdc * e4p;
+          }
           const double Na = T.N[q][a], Nb = T.N[q][b];
           const double w[5] = {rho, rho * u[0], rho * u[1], rho * u[2], e3p};
           const double al_a = u[0] * ga[0] + u[1] * ga[1] + u[2] * ga[2];
@@ -1941,10 +1987,11 @@ __global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
   }
 }
 
-template <int NSHL, int NQ, int LHS>
+#ifndef PHB_HOST_EMUL  // host: launchers
+template <int NSHL, int NQ, int LHS, bool DCON = false>
 static int launch_asigmr_gen(phb200_ctx *ctx, const ElemGroup &g) {
-  const size_t smem = sizeof(GenSmem<NSHL, NQ>) + (LHS == 2 ? NQ * STAGE_DBL * sizeof(double) : 0);
-  auto kern = k_asigmr_gen<NSHL, NQ, LHS>;
+  const size_t smem = sizeof(GenSmem<NSHL, NQ, DCON ? S_NVAR_DC : S_NVAR>) + (LHS == 2 ? NQ * STAGE_DBL * sizeof(double) : 0);
+  auto kern = k_asigmr_gen<NSHL, NQ, LHS, DCON>;
   static bool configured = false;
   if (!configured) {
     PHB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1969,6 +2016,11 @@ static int launch_asigmr_gen(phb200_ctx *ctx, const ElemGroup &g) {
 
 template <int NSHL, int NQ>
 static int launch_asigmr_gen_mode(phb200_ctx *ctx, const ElemGroup &g, int mode) {
+  if (ctx->c.iDC != 0) {  // discontinuity capturing: EBE / block-CSR / residual-only flavours (mode 3 is refused above)
+    if (mode == 1) return launch_asigmr_gen<NSHL, NQ, 1, true>(ctx, g);
+    if (mode == 2) return launch_asigmr_gen<NSHL, NQ, 2, true>(ctx, g);
+    return launch_asigmr_gen<NSHL, NQ, 0, true>(ctx, g);
+  }
   if (mode == 1) return launch_asigmr_gen<NSHL, NQ, 1>(ctx, g);
   if (mode == 2) return launch_asigmr_gen<NSHL, NQ, 2>(ctx, g);
   if (mode == 3) return launch_asigmr_gen<NSHL, NQ, 3>(ctx, g);
@@ -2054,6 +2106,7 @@ static int launch_asigmr_ws(phb200_ctx *ctx) {
 // (L2 resident), nshl*5 atomicAdds.  The Ap of the matrix-free GMRES is one launch of this kernel:
 // 8 B * (ien nshl*4/8 + ...) ~ 150 B and ~6 kflop per tet instead of 3 200 B of EGmass.
 // ---------------------------------------------------------------------------
+#endif  // PHB_HOST_EMUL
 template <int NSHL, int NQ>
 __global__ void __launch_bounds__(128) k_asires(int tab, int numel, size_t numel_pad, int nshg,
                                                 const int *__restrict__ ien, const double *__restrict__ aos,
@@ -2221,6 +2274,7 @@ __global__ void __launch_bounds__(128) k_asires(int tab, int numel, size_t numel
 
 // interior part of ItrRes (itrres.f:58-92): d_rmes += modified residual of d_yp ([5][nshg], {u,v,w,p,T});
 // the node records must hold the base state (phb_elmgmre packs them)
+#ifndef PHB_HOST_EMUL  // host: residual-only pass, ElmGMRe driver
 int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres) {
   if (ctx->c.iDC != 0) {
     fprintf(stderr, "phb200: itrres: iDC=%d is not built for the matrix-free flavour\n", ctx->c.iDC);
@@ -2324,12 +2378,15 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   // directly (e3bdg, e3.f:258-285) = the (a,a) blocks of what EGmass would hold
   const int mode = (st->lhs == 1) ? (sparse ? 2 : 1) : ((st->iprec != 0) ? 3 : 0);
   if (c.iDC != 0) {
-    // discontinuity capturing (e3dc.f): built into the phase A/B tet kernel (not the warp-specialised one)
-    if (!ctx->gen.empty() || mode == 3) {
-      fprintf(stderr, "phb200: elmgmr: iDC=%d is built for tet blocks of the EBE / block-CSR flavours only\n", c.iDC);
+    // discontinuity capturing (e3dc.f): built into the phase A/B tet kernel (not the warp-specialised one) and into
+    // the hex / wedge kernel
+    if (mode == 3) {
+      fprintf(stderr, "phb200: elmgmr: iDC=%d is built for the EBE / block-CSR flavours only (not the matrix-free one)\n", c.iDC);
       return 1;
     }
-    if (nq == 4) {
+    if (ctx->numel_tet == 0) {
+      // no tet blocks: the hex / wedge groups below carry the operator (k_asigmr_gen<..., DCON>)
+    } else if (nq == 4) {
       if (mode == 1) PHB_TRY((launch_asigmr<32, 4, 1, true>(ctx)));
       else if (mode == 2) PHB_TRY((launch_asigmr<32, 4, 2, true>(ctx)));
       else PHB_TRY((launch_asigmr<32, 4, 0, true>(ctx)));
@@ -2412,3 +2469,4 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   if (st->iprec != 0) PHB_TRY(phb_zero_slaves(ctx, ctx->d_BDiag, 25, 1));
   return 0;
 }
+#endif  // PHB_HOST_EMUL

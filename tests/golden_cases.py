@@ -16,6 +16,8 @@ CASES = {
     "tet_dc2": ((3, 2, 2), dict(bc="channel", ibksiz=64, iDC=2), ("elmgmre",)),
     "tet_dc3": ((3, 2, 2), dict(bc="channel", ibksiz=64, iDC=3), ("elmgmre", "elmgmre0")),
     "hex_dc1": ((2, 2, 2), dict(bc="channel", topo="hex", ibksiz=8, iDC=1), ("elmgmre",)),
+    "wedge_dc3": ((2, 3, 2), dict(bc="channel", topo="wedge", ibksiz=16, iDC=3), ("elmgmre", "elmgmre0")),
+    "mixed_dc1": ((2, 4, 2), dict(bc="channel", topo="mixed", ibksiz=16, iDC=1, etol=1e-6), ("elmgmre", "solgmrs")),
     "tet_1pt_nodiff": ((3, 2, 2), dict(bc="channel", ibksiz=64, rule=1, idiff=0, etol=1e-6), ("elmgmre", "solgmre")),
     "tet_sutherland": ((2, 2, 2), dict(bc="channel", ibksiz=64, matflg2=1, etol=1e-6), ("elmgmre",)),
     "tet_resonly": ((3, 2, 2), dict(bc="channel", ibksiz=16, boundary=True, natural="mixed"), ("elmgmre0",)),

@@ -128,3 +128,69 @@ def test_incompressible_boundary_kernel_on_the_host_matches_reference_fortran(em
     o.IncBc3Res(contrib)
     assert np.abs(ref).max() > 0
     assert np.abs(contrib - ref).max() < 1e-11 * np.abs(z["res"]).max()
+
+
+# ------------------------------------------------------------------------------------------------
+# the hex / wedge assembly kernel (k_asigmr_gen in assembly.cu: AsIGMR + e3 [+ e3dc] + BDiag + bc3LHS) on the host:
+# assembly.cu's device code compiled with g++ behind tests/host_emul/cuda_shim_simt.h (one pthread per CUDA thread)
+@pytest.fixture(scope="module")
+def emul_asm():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    out = os.path.join(os.path.dirname(OUT), "libasm_host.so")
+    subprocess.check_call(["g++", "-O1", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas",
+                           "-pthread", "-x", "c++", "-o", out, os.path.join(HERE, "host_emul", "asm_host.cpp")])
+    return C.CDLL(out)
+
+
+@pytest.mark.parametrize("name,lhs", [("hex_channel", 1), ("hex_dc1", 1), ("wedge_dc3", 1), ("wedge_dc3", 0),
+                                      ("wedge_allbc", 1)])
+def test_hex_wedge_assembly_kernel_on_the_host_matches_reference_fortran(emul_asm, name, lhs):
+    """hex_channel / wedge_allbc have run on a B200 (they calibrate the emulation); the discontinuity-capturing
+    instantiations (DCON) of the same kernel have not"""
+    z, case, _ = load(name)
+    params, tables, parts, states = case
+    mp = parts[0]
+    P = params
+    run = "elmgmre" if lhs else "elmgmre0"
+    nshl = mp.mien[0].shape[1]
+    ien = np.concatenate([np.asarray(b) for b in mp.mien], axis=0).astype(np.int32) - 1     # (numel,nshl)
+    numel = ien.shape[0]
+    pad = (numel + 31) // 32 * 32
+    ienp = np.zeros((nshl, pad), dtype=np.int32)
+    ienp[:, :numel] = ien.T
+    y, ac = (np.asfortranarray(a) for a in states[0])
+    q = np.asfortranarray(z[run + ".qres"])
+    res = np.zeros((mp.nshg, 5), order="F")
+    BDiag = np.zeros((mp.nshg, 5, 5), order="F")
+    nedof = 5 * nshl
+    EG = np.zeros(pad * nedof * nedof)
+    fct1 = P.almi / P.gami / P.alfi * P.Dtgl
+    phys = np.array([P.Rgas, P.gamma, P.gamma1, P.pr, P.datmat121, P.datmat221, P.datmat321, P.datmat131, P.dtsfct,
+                     P.taucfct, P.temper, P.Dtgl, fct1, P.epsM])
+    iphys = np.array([P.matflg2, P.matflg3, P.idiff, P.iremoveStabTimeTerm, P.ipord, lhs, lhs, P.iDC], dtype=np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)       # noqa: E731
+    T = {k: np.asfortranarray(tables[k]) for k in ("Qwt", "shp", "shgl")}
+    nint = np.asarray(tables["nint"]).astype(np.int32)
+    iBC = np.ascontiguousarray(mp.iBC, dtype=np.int32)
+    BC = np.asfortranarray(mp.BC)
+    rc = emul_asm.asm_host_gen(nshl, lhs, numel, mp.nshg, mp.numnp, vp(ienp), vp(np.asfortranarray(mp.x)), vp(y), vp(ac),
+                               vp(q), vp(iBC), vp(BC), vp(nint), vp(T["Qwt"]), vp(T["shp"]), vp(T["shgl"]), vp(phys),
+                               vp(iphys), vp(res), vp(BDiag), vp(EG))
+    assert rc == 0
+    assert rel_l2(res, z[run + ".res_interior"]) < 1e-12
+    if lhs:
+        assert rel_l2(BDiag, z[run + ".BDiag_nobc"]) < 1e-12
+        # EBE tiles EG[tile][c][r][lane] -> EGmass(e, r, c) (post bc3LHS, asigmr.f:36 + bc3lhs.f)
+        eg = EG.reshape(pad // 32, nedof, nedof, 32).transpose(0, 3, 2, 1).reshape(pad, nedof, nedof)[:numel]
+        assert rel_l2(eg, z[run + ".EGmass"]) < 1e-12
+    if P.iDC:
+        # the fixture is sensitive to the operator: the same kernel without it is far off
+        iphys[7] = 0
+        res0 = np.zeros_like(res)
+        EG0, BD0 = np.zeros_like(EG), np.zeros_like(BDiag)
+        emul_asm.asm_host_gen(nshl, lhs, numel, mp.nshg, mp.numnp, vp(ienp), vp(np.asfortranarray(mp.x)), vp(y), vp(ac),
+                              vp(q), vp(iBC), vp(BC), vp(nint), vp(T["Qwt"]), vp(T["shp"]), vp(T["shgl"]), vp(phys),
+                              vp(iphys), vp(res0), vp(BD0), vp(EG0))
+        assert rel_l2(res0, z[run + ".res_interior"]) > 1e-3
+        if lhs:
+            assert rel_l2(EG0, EG) > 1e-3

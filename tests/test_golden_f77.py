@@ -37,7 +37,7 @@ def load(name):
 
 # cases added after the round's GPU budget was spent: their device runs sit in tests/test_zz_gpu_late.py, which
 # sorts last, so that a failure there cannot stop (-x) the suite that has been measured on a B200
-LATE = ("hex_bnd", "wedge_bnd", "mixed_bnd")
+LATE = ("hex_bnd", "wedge_bnd", "mixed_bnd", "hex_dc1", "wedge_dc3", "mixed_dc1")
 
 
 def names(run, late=None):
@@ -162,13 +162,6 @@ def check_gpu_elmgmre(name, run=None):
     run = run or ("elmgmre" if "elmgmre" in runs else "elmgmre0")
     g = gpu(case)
     y, ac = case[3][0]
-    if name == "hex_dc1":
-        # discontinuity capturing is built for tet blocks only: hexes must be refused loudly, not computed wrongly
-        from phasta_b200.solver import PhastaError
-        with pytest.raises(PhastaError):
-            g.ElmGMRe(y, ac)
-        g.close()
-        return
     if run == "elmgmre":
         out = g.ElmGMRe(y, ac, want_egmass=True, want_qres=True)
     else:
