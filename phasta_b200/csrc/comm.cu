@@ -100,29 +100,7 @@ int phb_halo_setup(phb200_ctx *ctx, const int *il) {
   ctx->halo_cap = 0;
   if (ctx->c.numpe <= 1 || !il || ctx->c.nlwork < 1) return 0;
   std::vector<int> nodes, slaves;
-  int numtask = il[0], itk = 1;
-  for (int t = 0; t < numtask; t++) {
-    HaloTask h;
-    h.tag = il[itk];
-    h.iacc = il[itk + 1];
-    h.peer = il[itk + 2];
-    int numseg = il[itk + 3];
-    h.offset = (int)nodes.size();
-    for (int s = 0; s < numseg; s++) {
-      int beg = il[itk + 4 + 2 * s], len = il[itk + 5 + 2 * s];
-      for (int k = 0; k < len; k++) {
-        nodes.push_back(beg + k - 1);
-        if (h.iacc == 0) slaves.push_back(beg + k - 1);
-      }
-    }
-    h.count = (int)nodes.size() - h.offset;
-    h.peer_task = -1;
-    h.peer_offset = 0;
-    h.peer_cap = 0;
-    h.sendn = h.recvn = 0;
-    ctx->tasks.push_back(h);
-    itk += 4 + 2 * numseg;
-  }
+  phb_parse_ilwork(il, ctx->tasks, nodes, slaves);
   if (nodes.empty()) return 0;
   PHB_CHECK(cudaMalloc(&ctx->d_halo_nodes, sizeof(int) * nodes.size()));
   PHB_CHECK(cudaMemcpy(ctx->d_halo_nodes, nodes.data(), sizeof(int) * nodes.size(), cudaMemcpyHostToDevice));
@@ -154,103 +132,28 @@ __global__ void k_halo_unpack(int count, const int *__restrict__ nodes, int nshg
   *p = add ? (*p + buf[t]) : buf[t];
 }
 
-// ---- halo exchange by direct peer stores over NVLink (no NCCL call between pack and unpack) ----------------
-// Sender: pack the task's values straight into the RECEIVER's arena (slot = message number & 1), fence at system
-// scope, and let the block that finishes last raise the receiver's flag to the message number.  Before
-// overwriting a slot the sender waits for the receiver's acknowledgement of the message that used it two messages
-// ago (the receiver's unpack kernel writes it into the SENDER's arena), so no ordering assumption about the
-// sequence of 'in'/'out' exchanges is needed.  All spins are bounded (error flag instead of a hang).
-#define PHB_SPIN_MAX (1ll << 27)
-__global__ void k_halo_send(int count, const int *__restrict__ nodes, int nshg, int n, const double *__restrict__ g,
-                            double *dst, volatile unsigned long long *peer_flag, volatile unsigned long long *my_ack,
-                            unsigned long long msg, unsigned int *ticket, int *err) {
-  __shared__ int last;
-  if (threadIdx.x == 0 && msg > 2) {
-    long long spins = 0;
-    const bool dead = *reinterpret_cast<volatile int *>(err) != 0;
-    while (!dead && *my_ack + 2 < msg) {
-      if (++spins > PHB_SPIN_MAX) { atomicExch(err, 100); break; }
-    }
-  }
-  __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < count * n) {
-    const int k = t / count, i = t % count;
-    dst[t] = g[(size_t)nshg * k + nodes[i]];
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    *ticket = 0u;
-    __threadfence_system();
-    *peer_flag = msg;
-  }
-}
-__global__ void k_halo_recv(int count, const int *__restrict__ nodes, int nshg, int n, double *__restrict__ g,
-                            const double *src, volatile unsigned long long *my_flag,
-                            volatile unsigned long long *peer_ack, unsigned long long msg, int add,
-                            unsigned int *ticket, int *err) {
-  __shared__ int last;
-  if (threadIdx.x == 0) {
-    long long spins = 0;
-    const bool dead = *reinterpret_cast<volatile int *>(err) != 0;
-    while (!dead && *my_flag != msg) {
-      if (++spins > PHB_SPIN_MAX) { atomicExch(err, 200); break; }
-    }
-    __threadfence_system();
-  }
-  __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < count * n) {
-    const int k = t / count, i = t % count;
-    const double v = __ldcv(src + t);  // written by the peer: never from a stale L1 line
-    double *p = g + (size_t)nshg * k + nodes[i];
-    *p = add ? (*p + v) : v;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    *ticket = 0u;
-    __threadfence_system();
-    *peer_ack = msg;
-  }
-}
+#include "halo_p2p.cuh"  // k_halo_send / k_halo_recv: halo exchange by direct peer stores over NVLink
 
 static int commu_p2p(phb200_ctx *ctx, double *g, int n, int code) {
   cudaStream_t s = ctx->stream;
   const int nshg = ctx->c.nshg, me = ctx->c.myrank;
   const int send_role = (code == 0) ? 0 : 1;
   auto arena = [&](int r) { return r == me ? ctx->d_mail : (double *)ctx->peer_mapped[r]; };
+  const PhbArena A = phb_arena_layout(ctx->halo_cap);
   KScope ks(ctx, KC_HALO);
   for (size_t ti = 0; ti < ctx->tasks.size(); ti++) {
     HaloTask &h = ctx->tasks[ti];
     if (h.iacc != send_role) continue;
-    const unsigned long long m = ++h.sendn;
-    const int slot = (int)(m & 1ull), tot = h.count * n;
-    double *pa = arena(h.peer);
-    double *dst = pa + ctx->arena_data_off + (size_t)slot * h.peer_cap + (size_t)h.peer_offset * 25;
-    volatile unsigned long long *pflag =
-        reinterpret_cast<volatile unsigned long long *>(pa + ctx->arena_flag_off) + (2 * h.peer_task + slot);
-    volatile unsigned long long *myack =
-        reinterpret_cast<volatile unsigned long long *>(ctx->d_mail + ctx->arena_ack_off) + ti;
-    k_halo_send<<<(tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g, dst, pflag, myack, m,
-                                                  ctx->d_halo_tickets + ti, ctx->d_p2p_err);
+    const PhbHaloMsg m = phb_p2p_send_msg(h, ti, n, ctx->d_mail, arena(h.peer), A);
+    k_halo_send<<<(m.tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g, m.data, m.flag,
+                                                    m.ack, m.msg, ctx->d_halo_tickets + ti, ctx->d_p2p_err);
   }
   for (size_t ti = 0; ti < ctx->tasks.size(); ti++) {
     HaloTask &h = ctx->tasks[ti];
     if (h.iacc == send_role) continue;
-    const unsigned long long m = ++h.recvn;
-    const int slot = (int)(m & 1ull), tot = h.count * n;
-    const double *src = ctx->d_mail + ctx->arena_data_off + (size_t)slot * ctx->halo_cap + (size_t)h.offset * 25;
-    volatile unsigned long long *myflag =
-        reinterpret_cast<volatile unsigned long long *>(ctx->d_mail + ctx->arena_flag_off) + (2 * ti + slot);
-    volatile unsigned long long *pack =
-        reinterpret_cast<volatile unsigned long long *>(arena(h.peer) + ctx->arena_ack_off) + h.peer_task;
-    k_halo_recv<<<(tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g, src, myflag, pack, m,
-                                                  code == 0, ctx->d_halo_tickets + ti, ctx->d_p2p_err);
+    const PhbHaloMsg m = phb_p2p_recv_msg(h, ti, n, ctx->d_mail, arena(h.peer), A, ctx->halo_cap);
+    k_halo_recv<<<(m.tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g, m.data, m.flag,
+                                                    m.ack, m.msg, code == 0, ctx->d_halo_tickets + ti, ctx->d_p2p_err);
   }
   PHB_CHECK(cudaGetLastError());
   return 0;
@@ -395,12 +298,11 @@ static int p2p_setup(phb200_ctx *ctx) {
   // The offsets are the same on every rank (a rank addresses its PEERS' arenas with them); only the data slot
   // stride (the peer's halo_cap) differs per rank and travels in the task table.
   const size_t ntask = ctx->tasks.size();
-  const size_t MAXTASK = 64;
-  size_t mail_dbl = (size_t)2 * PHB_MAXR * PHB_MAILW + (size_t)2 * PHB_MAXR;
-  ctx->arena_flag_off = mail_dbl;
-  ctx->arena_ack_off = ctx->arena_flag_off + 2 * MAXTASK;
-  ctx->arena_data_off = ctx->arena_ack_off + MAXTASK;
-  mail_dbl = ctx->arena_data_off + 2 * ctx->halo_cap;
+  const PhbArena A = phb_arena_layout(ctx->halo_cap);
+  ctx->arena_flag_off = A.flag_off;
+  ctx->arena_ack_off = A.ack_off;
+  ctx->arena_data_off = A.data_off;
+  const size_t mail_dbl = A.total;
   PHB_CHECK(cudaMalloc(&ctx->d_mail, sizeof(double) * mail_dbl));
   PHB_CHECK(cudaMemset(ctx->d_mail, 0, sizeof(double) * mail_dbl));
   PHB_CHECK(cudaMalloc(&ctx->d_halo_tickets, sizeof(unsigned int) * (ntask + 1)));
@@ -461,16 +363,9 @@ static int p2p_setup(phb200_ctx *ctx) {
   // this rank's own task count (fixed above) and could not be re-measured within the round's GPU budget.
   const char *envh = getenv("PHB200_P2P_HALO");
   if (!envh || atoi(envh) == 0) return 0;
-  const int MAXT = 64, REC = 5, W = 2 + MAXT * REC;
+  const int W = PHB_P2P_W;
   std::vector<int> mytab(W, 0), alltab((size_t)W * world, 0);
-  int fits = ((int)ntask <= MAXT && ctx->halo_cap < ((size_t)1 << 31)) ? 1 : 0;
-  mytab[0] = fits ? (int)ntask : -1;
-  mytab[1] = (int)ctx->halo_cap;
-  for (size_t t = 0; t < ntask && fits; t++) {
-    const HaloTask &h = ctx->tasks[t];
-    int *r = &mytab[2 + REC * t];
-    r[0] = h.tag; r[1] = h.iacc; r[2] = h.peer; r[3] = h.offset; r[4] = h.count;
-  }
+  phb_p2p_mytab(ctx->tasks, ctx->halo_cap, mytab.data());
   int *d_tab;
   PHB_CHECK(cudaMalloc(&d_tab, sizeof(int) * (size_t)W * (world + 1)));
   PHB_CHECK(cudaMemcpy(d_tab, mytab.data(), sizeof(int) * W, cudaMemcpyHostToDevice));
@@ -479,23 +374,7 @@ static int p2p_setup(phb200_ctx *ctx) {
                             ctx->stream));
   PHB_CHECK(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_tab);
-  bool good = true;
-  for (int r = 0; r < world; r++)
-    if (alltab[(size_t)W * r] < 0) good = false;
-  for (size_t t = 0; t < ntask && good; t++) {
-    HaloTask &h = ctx->tasks[t];
-    const int *pt = &alltab[(size_t)W * h.peer];
-    h.peer_task = -1;
-    for (int k = 0; k < pt[0]; k++) {
-      const int *r = pt + 2 + REC * k;
-      if (r[0] == h.tag && r[2] == me && r[1] != h.iacc && r[4] == h.count) {
-        h.peer_task = k;
-        h.peer_offset = r[3];
-        h.peer_cap = (size_t)pt[1];
-      }
-    }
-    if (h.peer_task < 0) good = false;
-  }
+  const bool good = phb_p2p_pair(me, world, alltab.data(), ctx->tasks);
   // unanimous decision (a rank whose table does not match would otherwise wait forever)
   double *d_g;
   PHB_CHECK(cudaMalloc(&d_g, sizeof(double)));

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../../include/phb200.h"
+#include "halo_task.h"
 
 #define PHB_CHECK(call)                                                        \
   do {                                                                         \
@@ -54,15 +55,6 @@ struct BndGroup {
   double *d_BCB;  // [6][nshlb][n]  BCB(e,k,j) -> [(j*nshlb+k)*n + e]
 };
 
-struct HaloTask {
-  int peer, iacc, tag, count;  // count = number of nodes (all segments)
-  int offset;                  // into d_halo_nodes
-  // NVLink peer-memory transport (comm.cu): the matching task on the peer, where its data lands in the peer's
-  // arena, and how many messages this rank has sent / received on this task
-  int peer_task, peer_offset;
-  size_t peer_cap;             // the peer's halo_cap = stride between its two data slots
-  unsigned long long sendn, recvn;
-};
 
 struct phb200_ctx {
   phb200_common c;
@@ -235,8 +227,7 @@ int phb_halo_setup(phb200_ctx *ctx, const int *ilwork);
 int phb_commu(phb200_ctx *ctx, double *d_global, int n, int code);
 int phb_allreduce_sum(phb200_ctx *ctx, double *d_vals, int n);
 int phb_p2p_check(phb200_ctx *ctx);
-#define PHB_MAXR 16   // ranks a mailbox has room for
-#define PHB_MAILW 8   // doubles per all-reduce
+// PHB_MAXR ranks x PHB_MAILW doubles per mailbox: halo_task.h
 // All-reduce of up to PHB_MAILW doubles over NVLink peer memory, done by the kernel that produced them (called by
 // ONE warp of one block).  Every rank owns a mailbox  vals[2][MAXR][MAILW] | seq[2][MAXR]  that all peers have
 // mapped through CUDA IPC (comm.cu p2p_setup).  For all-reduce number `seq` (the same on all ranks: the solver is

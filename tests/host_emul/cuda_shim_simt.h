@@ -56,6 +56,12 @@ static inline double atomicAdd(double *p, double v) {
   return o;
 }
 
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+static inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+static inline void __threadfence_system() { __sync_synchronize(); }
+template <class T>
+static inline T __ldcv(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
+
 // run `kernel()` for a grid of `grid` blocks of `block` threads (block a multiple of 32), block after block
 struct ShimArg {
   const std::function<void()> *fn;
