@@ -40,6 +40,9 @@ CASES = {
     "tet_nd_mfg": ((3, 2, 2), dict(bc="channel", ibksiz=16, boundary=True, natural="mixed", etol=1e-4, nd=True),
                    ("solmfg",)),
     "hex_nd_mfg": ((2, 2, 2), dict(bc="channel", topo="hex", ibksiz=8, etol=1e-4, nd=True), ("solmfg",)),
+    # the matrix-free flavour through wedge boundary faces (ElmMFG -> AsBMFG on lcsyst 3 and 4)
+    "wedge_bnd_nd_mfg": ((2, 3, 2), dict(bc="channel", topo="wedge", ibksiz=16, boundary=True, natural="mixed",
+                                         periodic_z=False, etol=1e-4, nd=True), ("solmfg",)),
 }
 
 

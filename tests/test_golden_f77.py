@@ -37,7 +37,7 @@ def load(name):
 
 # cases added after the round's GPU budget was spent: their device runs sit in tests/test_zz_gpu_late.py, which
 # sorts last, so that a failure there cannot stop (-x) the suite that has been measured on a B200
-LATE = ("hex_bnd", "wedge_bnd", "mixed_bnd", "hex_dc1", "wedge_dc3", "mixed_dc1")
+LATE = ("hex_bnd", "wedge_bnd", "mixed_bnd", "hex_dc1", "wedge_dc3", "mixed_dc1", "wedge_bnd_nd_mfg")
 
 
 def names(run, late=None):
@@ -219,8 +219,12 @@ def check_gpu_solgmrs(name):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", names("solmfg"))
+@pytest.mark.parametrize("name", names("solmfg", False))
 def test_gpu_solmfg_matches_reference_fortran(name):
+    check_gpu_solmfg(name)
+
+
+def check_gpu_solmfg(name):
     """Matrix-free flavour on the device against the reference's solmfg.f chain.
     Tolerances: everything upstream of the finite difference at 1e-10; Au1MFG
     (difference over eGMRES=1e-7, which amplifies round-off ~1e7 times) 1e-6;

@@ -6,12 +6,13 @@ import numpy as np
 import pytest
 
 from common import rel_l2
-from test_golden_f77 import check_gpu_elmgmre, check_gpu_solgmre, check_gpu_solgmrs, names
+from test_golden_f77 import check_gpu_elmgmre, check_gpu_solgmre, check_gpu_solgmrs, check_gpu_solmfg, names
 
 pytestmark = pytest.mark.gpu
 
 
-# ---- boundary elements on hex / wedge faces (k_asbmfg_gen), EBE and block-CSR flavours ----------------------
+# ---- boundary elements on hex / wedge faces (k_asbmfg_gen) and discontinuity capturing on hex / wedge blocks
+# (k_asigmr_gen<..., DCON>): EBE, block-CSR and matrix-free flavours ------------------------------------------
 @pytest.mark.parametrize("name", names("elmgmre", True))
 def test_gpu_elmgmre_with_hex_wedge_boundary_elements(name):
     check_gpu_elmgmre(name, "elmgmre")
@@ -30,6 +31,11 @@ def test_gpu_solgmre_with_hex_boundary_elements(name):
 @pytest.mark.parametrize("name", names("solgmrs", True))
 def test_gpu_solgmrs_with_hex_wedge_boundary_elements(name):
     check_gpu_solgmrs(name)
+
+
+@pytest.mark.parametrize("name", names("solmfg", True))
+def test_gpu_solmfg_with_wedge_boundary_elements(name):
+    check_gpu_solmfg(name)
 
 
 # ---- the incompressible boundary integral (k_inc_asbmfg) on tet, hex and wedge faces ---------------------------
