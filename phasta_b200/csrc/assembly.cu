@@ -570,7 +570,7 @@ __device__ __forceinline__ void phase_b(const SM &sm, int warp, int lane, int ti
             smuu[r] += mu * u[r];
             slamu[r] += lam * u[r];
           }
-          if (DCON) {
+          if (DCON && LHS != 3) {  // (e3bdg.f builds the block diagonal without the DC operator)
             // e3dc.f:300-325 + e3wmlt.f:154-223: W N_a,i (DC g^ij A0) N_b,j = W DC (g_a^T G g_b) A0
             const double g1 = sm.st[q][S_GU + 0][le], g2 = sm.st[q][S_GU + 1][le], g3 = sm.st[q][S_GU + 2][le],
                          g4 = sm.st[q][S_GU + 3][le], g5 = sm.st[q][S_GU + 4][le], g6 = sm.st[q][S_GU + 5][le];
@@ -1866,7 +1866,7 @@ __global__ void __launch_bounds__(32 * NQ, 1) k_asigmr_gen(
           const double tw1 = W * sm.st[q][S_TAU1][lane], tw2 = W * sm.st[q][S_TAU2][lane],
                        tw3 = W * sm.st[q][S_TAU3][lane];
           const double mu = sm.st[q][S_MU][lane], lam = sm.st[q][S_LAM][lane], con = sm.st[q][S_CON][lane];
-          if (DCON) {
+          if (DCON && LHS != 3) {  // (e3bdg.f builds the block diagonal without the DC operator)
             // e3dc.f:300-325 + e3wmlt.f:154-223: W N_a,i (DC g^ij A0) N_b,j = W DC (g_a^T G g_b) A0
             const double g1 = sm.st[q][S_GU + 0][lane], g2 = sm.st[q][S_GU + 1][lane], g3 = sm.st[q][S_GU + 2][lane],
                          g4 = sm.st[q][S_GU + 3][lane], g5 = sm.st[q][S_GU + 4][lane], g6 = sm.st[q][S_GU + 5][lane];
@@ -2016,9 +2016,10 @@ static int launch_asigmr_gen(phb200_ctx *ctx, const ElemGroup &g) {
 
 template <int NSHL, int NQ>
 static int launch_asigmr_gen_mode(phb200_ctx *ctx, const ElemGroup &g, int mode) {
-  if (ctx->c.iDC != 0) {  // discontinuity capturing: EBE / block-CSR / residual-only flavours (mode 3 is refused above)
+  if (ctx->c.iDC != 0) {  // discontinuity capturing
     if (mode == 1) return launch_asigmr_gen<NSHL, NQ, 1, true>(ctx, g);
     if (mode == 2) return launch_asigmr_gen<NSHL, NQ, 2, true>(ctx, g);
+    if (mode == 3) return launch_asigmr_gen<NSHL, NQ, 3, true>(ctx, g);
     return launch_asigmr_gen<NSHL, NQ, 0, true>(ctx, g);
   }
   if (mode == 1) return launch_asigmr_gen<NSHL, NQ, 1>(ctx, g);
@@ -2107,7 +2108,11 @@ static int launch_asigmr_ws(phb200_ctx *ctx) {
 // 8 B * (ien nshl*4/8 + ...) ~ 150 B and ~6 kflop per tet instead of 3 200 B of EGmass.
 // ---------------------------------------------------------------------------
 #endif  // PHB_HOST_EMUL
-template <int NSHL, int NQ>
+// DCM: discontinuity capturing (e3dc.f) in the modified residual -- 0 none; 2 as ItrRes runs it (ires=2: the
+// operator's size from the unscaled A_i Y,i of the perturbed state, e3tau.f:177-185); 3 as ElmMFG runs it (ires=3:
+// from the full strong residual before / after the tau scaling, and the reference's statement for rmi(:,11),
+// e3dc.f:262, which reads rmi(:,12) and gAgyi(:,12))
+template <int NSHL, int NQ, int DCM = 0>
 __global__ void __launch_bounds__(128) k_asires(int tab, int numel, size_t numel_pad, int nshg,
                                                 const int *__restrict__ ien, const double *__restrict__ aos,
                                                 const double *__restrict__ yp, double *__restrict__ rmes,
@@ -2219,6 +2224,11 @@ __global__ void __launch_bounds__(128) k_asires(int tab, int numel, size_t numel
     L[2] = tmpv[2] + w[2] * divu + gr[1][0];
     L[3] = tmpv[3] + w[3] * divu + gr[2][0];
     L[4] = tmpv[4] + w[4] * divu + adv[0];
+    double Lraw[5];
+    if (DCM) {
+#pragma unroll
+      for (int m = 0; m < 5; m++) Lraw[m] = L[m];  // rLyi = A_i Y,i
+    }
 #pragma unroll
     for (int m = 0; m < 5; m++) {
       L[m] = L[m] + c_ph.fct1 * dui[m];  // rLymi (e3ls.f:103)
@@ -2252,6 +2262,48 @@ __global__ void __launch_bounds__(128) k_asires(int tab, int numel, size_t numel
       rmi[5 * i + 1 + i] += L[0];
       rmi[5 * i + 4] += u[i] * L[0];
     }
+    if (DCM == 2) {  // rmi(1:15) += DC g^ij A0 Y,j; rTLS / raLS from the unscaled A_i Y,i
+      double dcv, gu[6];
+      dc_point(rho, T, u, rk, h, cp, alfap, betaT, gr, gij, Lraw, Lraw, A0v, rmi, dcv, gu);
+    }
+    if (DCM == 3) {
+      // the strong residual of ires=3 (e3ls.f:108-154): A_i Y,i + A0 Y,t - div q, unscaled and tau-scaled
+      double At[5] = {0, 0, 0, 0, 0}, divq[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int a = 0; a < NSHL; a++) {
+        const double2 *rec = reinterpret_cast<const double2 *>(aos + (size_t)nd[a] * NREC);
+        const double2 v4 = __ldg(rec + 4), v5 = __ldg(rec + 5), v6 = __ldg(rec + 6);
+        const double al[5] = {v4.x, v4.y, v5.x, v5.y, v6.x};
+#pragma unroll
+        for (int m = 0; m < 5; m++) At[m] += Nq[a] * al[m];
+        if (c_ph.idiff >= 1) {
+          const double2 v7 = __ldg(rec + 7), v8 = __ldg(rec + 8), v9 = __ldg(rec + 9), v10 = __ldg(rec + 10),
+                        v11 = __ldg(rec + 11), v12 = __ldg(rec + 12);
+          const double ql[12] = {v6.y, v7.x, v7.y, v8.x, v8.y, v9.x, v9.y, v10.x, v10.y, v11.x, v11.y, v12.x};
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int m = 0; m < 4; m++) divq[m] += g.shg[a][i] * ql[4 * i + m];
+        }
+      }
+      double rt[5], rs[5], massr[5];
+      A0v(At, massr);
+#pragma unroll
+      for (int m = 0; m < 5; m++) rt[m] = Lraw[m] + massr[m];
+      if (c_ph.idiff >= 1) {
+        rt[1] -= divq[0]; rt[2] -= divq[1]; rt[3] -= divq[2]; rt[4] -= divq[3];
+      }
+      rs[0] = rt[0] * tau1; rs[1] = rt[1] * tau2; rs[2] = rt[2] * tau2; rs[3] = rt[3] * tau2; rs[4] = rt[4] * tau3;
+      double dfl[20], dcv, gu[6];
+#pragma unroll
+      for (int k = 0; k < 20; k++) dfl[k] = 0.0;
+      dc_point(rho, T, u, rk, h, cp, alfap, betaT, gr, gij, rt, rs, A0v, dfl, dcv, gu);
+#pragma unroll
+      for (int k = 0; k < 15; k++) {
+        if (k != 10) rmi[k] = rmi[k] + dfl[k];
+        else rmi[10] = rmi[11] + dfl[11];  // e3dc.f:262, before rmi(:,12) is updated
+      }
+    }
     // e3wmlt.f:95-122
     const double W = g.W;
 #pragma unroll
@@ -2275,12 +2327,9 @@ __global__ void __launch_bounds__(128) k_asires(int tab, int numel, size_t numel
 // interior part of ItrRes (itrres.f:58-92): d_rmes += modified residual of d_yp ([5][nshg], {u,v,w,p,T});
 // the node records must hold the base state (phb_elmgmre packs them)
 #ifndef PHB_HOST_EMUL  // host: residual-only pass, ElmGMRe driver
-int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres) {
-  if (ctx->c.iDC != 0) {
-    fprintf(stderr, "phb200: itrres: iDC=%d is not built for the matrix-free flavour\n", ctx->c.iDC);
-    return 1;
-  }
+int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres, int ires) {
   const phb200_common &c = ctx->c;
+  const int dcm = (c.iDC != 0) ? (ires == 3 ? 3 : 2) : 0;
   cudaStream_t s = ctx->stream;
   const int nq = c.nint[0];
   if (ctx->numel_tet > 0) {
@@ -2289,19 +2338,26 @@ int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres) 
       return 1;
     }
     KScope ks(ctx, KC_ASM);
-    k_asires<4, 4><<<(ctx->numel_tet + 127) / 128, 128, 0, s>>>(0, ctx->numel_tet, ctx->numel_pad, c.nshg, ctx->d_ien,
-                                                                ctx->d_nodeaos, d_yp, d_rmes, iabres);
+#define PHB_ASIRES(NSHL, NQ, DCM, TAB, NUMEL, PAD, IEN)                                                       \
+  k_asires<NSHL, NQ, DCM><<<((NUMEL) + 127) / 128, 128, 0, s>>>(TAB, NUMEL, PAD, c.nshg, IEN, ctx->d_nodeaos, d_yp, \
+                                                               d_rmes, iabres)
+    if (dcm == 3) PHB_ASIRES(4, 4, 3, 0, ctx->numel_tet, ctx->numel_pad, ctx->d_ien);
+    else if (dcm == 2) PHB_ASIRES(4, 4, 2, 0, ctx->numel_tet, ctx->numel_pad, ctx->d_ien);
+    else PHB_ASIRES(4, 4, 0, 0, ctx->numel_tet, ctx->numel_pad, ctx->d_ien);
     PHB_CHECK(cudaGetLastError());
   }
   for (const ElemGroup &g : ctx->gen) {
     KScope ks(ctx, KC_ASM);
-    const int nb = (g.numel + 127) / 128;
-    if (g.nshl == 8)
-      k_asires<8, 8><<<nb, 128, 0, s>>>(g.tab, g.numel, g.numel_pad, c.nshg, g.d_ien, ctx->d_nodeaos, d_yp, d_rmes,
-                                        iabres);
-    else
-      k_asires<6, 6><<<nb, 128, 0, s>>>(g.tab, g.numel, g.numel_pad, c.nshg, g.d_ien, ctx->d_nodeaos, d_yp, d_rmes,
-                                        iabres);
+    if (g.nshl == 8) {
+      if (dcm == 3) PHB_ASIRES(8, 8, 3, g.tab, g.numel, g.numel_pad, g.d_ien);
+      else if (dcm == 2) PHB_ASIRES(8, 8, 2, g.tab, g.numel, g.numel_pad, g.d_ien);
+      else PHB_ASIRES(8, 8, 0, g.tab, g.numel, g.numel_pad, g.d_ien);
+    } else {
+      if (dcm == 3) PHB_ASIRES(6, 6, 3, g.tab, g.numel, g.numel_pad, g.d_ien);
+      else if (dcm == 2) PHB_ASIRES(6, 6, 2, g.tab, g.numel, g.numel_pad, g.d_ien);
+      else PHB_ASIRES(6, 6, 0, g.tab, g.numel, g.numel_pad, g.d_ien);
+    }
+#undef PHB_ASIRES
     PHB_CHECK(cudaGetLastError());
   }
   return 0;
@@ -2380,16 +2436,16 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   if (c.iDC != 0) {
     // discontinuity capturing (e3dc.f): built into the phase A/B tet kernel (not the warp-specialised one) and into
     // the hex / wedge kernel
-    if (mode == 3) {
-      fprintf(stderr, "phb200: elmgmr: iDC=%d is built for the EBE / block-CSR flavours only (not the matrix-free one)\n", c.iDC);
-      return 1;
-    }
     if (ctx->numel_tet == 0) {
       // no tet blocks: the hex / wedge groups below carry the operator (k_asigmr_gen<..., DCON>)
     } else if (nq == 4) {
       if (mode == 1) PHB_TRY((launch_asigmr<32, 4, 1, true>(ctx)));
       else if (mode == 2) PHB_TRY((launch_asigmr<32, 4, 2, true>(ctx)));
+      else if (mode == 3) PHB_TRY((launch_asigmr<32, 4, 3, true>(ctx)));  // ElmMFG: DC flux in res, none in BDiag
       else PHB_TRY((launch_asigmr<32, 4, 0, true>(ctx)));
+    } else if (mode == 3) {
+      fprintf(stderr, "phb200: elmmfg: tets need the 4-point rule\n");
+      return 1;
     } else {
       if (mode == 1) PHB_TRY((launch_asigmr<32, 1, 1, true>(ctx)));
       else if (mode == 2) PHB_TRY((launch_asigmr<32, 1, 2, true>(ctx)));

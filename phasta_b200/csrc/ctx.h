@@ -183,7 +183,7 @@ int phb_upload_tables(phb200_ctx *ctx, const double *shp, const double *shgl, co
                       const double *shglb);
 int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse = 0);
 int phb_alloc_eg(phb200_ctx *ctx);
-int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres);
+int phb_asires(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres, int ires = 2);
 int phb_bc3res_vec(phb200_ctx *ctx, double *d_r);
 int phb_qpbc(phb200_ctx *ctx);
 int phb_pack_nodes(phb200_ctx *ctx, int with_q);
@@ -202,7 +202,7 @@ int phb_itrbc(phb200_ctx *ctx, int ires);
 int phb_itrbc_vec(phb200_ctx *ctx, double *d_y, double *d_ac, int ires);
 // mfg.cu (matrix-free flavour)
 int phb_elmmfg(phb200_ctx *ctx, const phb200_step *st);
-int phb_itrres(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres);
+int phb_itrres(phb200_ctx *ctx, const double *d_yp, double *d_rmes, int iabres, int ires = 2);
 int phb_mfg_begin(phb200_ctx *ctx);
 int phb_au1mfg(phb200_ctx *ctx, double *d_u);
 int phb_au2mfg(phb200_ctx *ctx, double *d_out);

@@ -40,6 +40,16 @@ CASES = {
     "tet_nd_mfg": ((3, 2, 2), dict(bc="channel", ibksiz=16, boundary=True, natural="mixed", etol=1e-4, nd=True),
                    ("solmfg",)),
     "hex_nd_mfg": ((2, 2, 2), dict(bc="channel", topo="hex", ibksiz=8, etol=1e-4, nd=True), ("solmfg",)),
+    # the matrix-free flavour with discontinuity capturing: ElmMFG runs e3dc with ires=3 (incl. the rmi(:,11) statement
+    # of e3dc.f:262), ItrRes / Au1MFG with ires=2
+    "tet_nd_mfg_dc1": ((3, 2, 2), dict(bc="channel", ibksiz=16, boundary=True, natural="mixed", etol=1e-4, nd=True,
+                                       iDC=1), ("solmfg",)),
+    "hex_nd_mfg_dc3": ((2, 2, 2), dict(bc="channel", topo="hex", ibksiz=8, etol=1e-4, nd=True, iDC=3), ("solmfg",)),
+    # the same without essential BCs, periodicity or boundary elements: residuals and block diagonal are then the raw
+    # element sums, which tests/test_bnd_kernel_host.py compares with the kernels run on the host
+    "tet_nd_mfg_dc1_raw": ((3, 2, 2), dict(bc="none", periodic_z=False, ibksiz=16, etol=1e-4, nd=True, iDC=1), ("solmfg",)),
+    "hex_nd_mfg_dc3_raw": ((2, 2, 2), dict(bc="none", periodic_z=False, topo="hex", ibksiz=8, etol=1e-4, nd=True, iDC=3),
+                           ("solmfg",)),
     # the matrix-free flavour through wedge boundary faces (ElmMFG -> AsBMFG on lcsyst 3 and 4)
     "wedge_bnd_nd_mfg": ((2, 3, 2), dict(bc="channel", topo="wedge", ibksiz=16, boundary=True, natural="mixed",
                                          periodic_z=False, etol=1e-4, nd=True), ("solmfg",)),

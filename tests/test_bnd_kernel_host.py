@@ -194,3 +194,60 @@ def test_hex_wedge_assembly_kernel_on_the_host_matches_reference_fortran(emul_as
         assert rel_l2(res0, z[run + ".res_interior"]) > 1e-3
         if lhs:
             assert rel_l2(EG0, EG) > 1e-3
+
+
+@pytest.mark.parametrize("name", ["hex_nd_mfg_dc3_raw", "tet_nd_mfg_dc1_raw"])
+def test_matrix_free_kernels_with_dc_on_the_host_match_reference_fortran(emul_asm, name):
+    """The matrix-free flavour with discontinuity capturing, kernel source on the host against the reference's
+    solmfg.f chain on a case without essential BCs (residuals and block diagonal = raw element sums):
+    ElmMFG's element pass (k_asigmr_tet / k_asigmr_gen in e3bdg mode with DCON: DC flux in res, none in BDiag),
+    its modified residual (k_asires DCM 3: ires=3, incl. the rmi(:,11) statement of e3dc.f:262) and ItrRes
+    (k_asires DCM 2) with iabres 0 and 1."""
+    from common import make_oracle
+    z, case, _ = load(name)
+    params, tables, parts, states = case
+    mp, P = parts[0], params
+    assert not mp.iBC.any() and P.iDC != 0
+    nshl = mp.mien[0].shape[1]
+    ien = np.concatenate([np.asarray(b) for b in mp.mien], axis=0).astype(np.int32) - 1
+    numel = ien.shape[0]
+    pad = (numel + 31) // 32 * 32
+    ienp = np.zeros((nshl, pad), dtype=np.int32)
+    ienp[:, :numel] = ien.T
+    y, ac = np.asfortranarray(z["solmfg.y_bc"]), np.asfortranarray(z["solmfg.ac_bc"])
+    o = make_oracle(case)
+    o.itrBC()
+    o.set_flags(lhs=0, iprec=1)
+    o.ElmMFG()
+    q = np.asfortranarray(o.parts[0].qres)              # q = qres / rmass after qpbc (bit-equal to the reference's)
+    fct1 = P.almi / P.gami / P.alfi * P.Dtgl
+    phys = np.array([P.Rgas, P.gamma, P.gamma1, P.pr, P.datmat121, P.datmat221, P.datmat321, P.datmat131, P.dtsfct,
+                     P.taucfct, P.temper, P.Dtgl, fct1, P.epsM])
+    iphys = np.array([P.matflg2, P.matflg3, P.idiff, P.iremoveStabTimeTerm, P.ipord, 0, 1, P.iDC], dtype=np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)       # noqa: E731
+    T = {k: np.asfortranarray(tables[k]) for k in ("Qwt", "shp", "shgl")}
+    nint = np.asarray(tables["nint"]).astype(np.int32)
+    iBC = np.ascontiguousarray(mp.iBC, dtype=np.int32)
+    BC = np.asfortranarray(mp.BC)
+    x = np.asfortranarray(mp.x)
+    res = np.zeros((mp.nshg, 5), order="F")
+    BDiag = np.zeros((mp.nshg, 5, 5), order="F")
+    assert emul_asm.asm_host_bdg(nshl, numel, mp.nshg, mp.numnp, vp(ienp), vp(x), vp(y), vp(ac), vp(q), vp(iBC), vp(BC),
+                                 vp(nint), vp(T["Qwt"]), vp(T["shp"]), vp(T["shgl"]), vp(phys), vp(iphys), vp(res),
+                                 vp(BDiag)) == 0
+    assert rel_l2(res, z["solmfg.elm_res"]) < 1e-11          # the residual nearly cancels: |res| << |terms|
+    assert rel_l2(BDiag, z["solmfg.elm_BDiag"]) < 1e-12
+
+    def asires(ires, iabres, yp):
+        out = np.zeros((mp.nshg, 5), order="F")
+        yp = np.asfortranarray(yp)
+        assert emul_asm.asm_host_asires(nshl, ires, iabres, numel, mp.nshg, mp.numnp, vp(ienp), vp(x), vp(y), vp(ac),
+                                        vp(q), vp(yp), vp(nint), vp(T["Qwt"]), vp(T["shp"]), vp(T["shgl"]), vp(phys),
+                                        vp(iphys), vp(out)) == 0
+        return out
+
+    assert rel_l2(asires(3, 0, y), z["solmfg.elm_rmes"]) < 1e-12
+    r2 = asires(2, 0, y)
+    assert rel_l2(r2, z["solmfg.elm_rmes"]) > 1e-6           # ires=2 on the same state is a different vector
+    for iab in (0, 1):
+        assert rel_l2(asires(2, iab, z["solmfg.itrres_in"]), z["solmfg.itrres_out%d" % iab]) < 1e-12
