@@ -206,17 +206,41 @@ def test_commu_in_then_out_roundtrip():
         assert rel_l2(v, glob[mp.gnode]) < 1e-14
 
 
-def test_boundary_flux_closes_the_patch_test():
-    """With boundary elements on every face, a uniform flow gives zero residual
-    at EVERY node (interior Galerkin flux and e3b boundary flux cancel)."""
-    parts = make_box(5, 4, 3, bc="none", periodic_z=False, boundary=True)
+@pytest.mark.parametrize("topo", ["tet", "hex", "wedge", "mixed"])
+def test_boundary_flux_closes_the_patch_test(topo):
+    """With boundary elements on every face, a uniform flow gives zero residual at EVERY node (interior Galerkin
+    flux and e3b boundary flux cancel) -- on triangular faces of tets, quadrilateral faces of hexes, triangular and
+    quadrilateral faces of wedges: normals, face rules and the per-topology WdetJb of e3bvar.f:139-176 are
+    consistent with the volume elements (the wedge's in-plane derivatives are halved like the tet's, so its
+    quadrilateral face takes Qwtb / temp with symquadw's unit weights)."""
+    parts = make_box(5, 4, 3, bc="none", periodic_z=False, boundary=True, topo=topo)
     y, ac = uniform_state(parts[0])
     o = Oracle(parts, SolverParams(), make_tables(2, 2), [(y, ac)])
     o.ElmGMRe()
     scale = np.array([30.0 * 1.2, 1.0e5, 1.0e5, 1.0e5, 1.0e5 * 30.0])    # rho u, p, p, p, rho h u
     assert (np.abs(o.parts[0].res).max(axis=0) / scale).max() < 1e-13
     nb = sum(b.shape[0] for b in parts[0].mienb)
-    assert nb == 2 * 2 * (5 * 4 + 5 * 3 + 4 * 3)
+    per_hex_face = {"tet": 2, "hex": 1}
+    if topo in per_hex_face:
+        assert nb == per_hex_face[topo] * 2 * (5 * 4 + 5 * 3 + 4 * 3)
+    elif topo == "wedge":       # y faces are the wedges' triangles (2 per hex face), x and z faces their quadrilaterals
+        assert nb == 2 * (2 * 5 * 3 + 4 * 3 + 5 * 4)
+
+
+@pytest.mark.parametrize("topo", ["tet", "hex", "wedge", "mixed"])
+@pytest.mark.parametrize("iconvflow", [1, 2])
+def test_incompressible_boundary_integral_closes_the_patch_test(topo, iconvflow):
+    """the same for the incompressible code (asbmfg.f, e3b.f, e3bvar.f): uniform velocity and pressure, boundary
+    elements on every face -> momentum and continuity residuals vanish at every node, in both advective forms"""
+    from phasta_b200 import IncompParams
+    parts = make_box(5, 4, 3, bc="none", periodic_z=False, boundary=True, topo=topo)
+    mp = parts[0]
+    y = np.zeros((mp.nshg, 5), order="F")
+    y[:, 0], y[:, 1], y[:, 2], y[:, 3], y[:, 4] = 1.3, -0.4, 0.7, 2.5, 300.0
+    o = Oracle(parts, SolverParams(), make_tables(2, 2), [(y, np.zeros_like(y))])
+    o.genadj()
+    o.IncElmGMR(IncompParams(iconvflow=iconvflow, lhs=0))
+    assert np.abs(o.parts[0].res4).max() < 1e-14
 
 
 def test_genadj_equals_scipy_csr_and_sparse_equals_ebe():

@@ -33,6 +33,21 @@ def test_gpu_solgmrs_with_hex_wedge_boundary_elements(name):
     check_gpu_solgmrs(name)
 
 
+@pytest.mark.parametrize("topo", ["hex", "wedge", "mixed"])
+def test_gpu_boundary_flux_closes_the_patch_test(topo):
+    """a size-independent property: uniform flow, boundary elements on every face -> zero residual at every node"""
+    from phasta_b200 import SolverParams, make_box, make_tables
+    from phasta_b200.solver import PhastaGPU
+    from test_oracle import uniform_state
+    parts = make_box(20, 14, 10, bc="none", periodic_z=False, boundary=True, topo=topo, ibksiz=256)
+    y, ac = uniform_state(parts[0])
+    g = PhastaGPU(parts[0], SolverParams(ibksiz=256), make_tables(2, 2), device=0)
+    out = g.ElmGMRe(y, ac, step=g.step(lhs=0, iprec=0))
+    scale = np.array([30.0 * 1.2, 1.0e5, 1.0e5, 1.0e5, 1.0e5 * 30.0])
+    assert (np.abs(out["res"]).max(axis=0) / scale).max() < 1e-12
+    g.close()
+
+
 @pytest.mark.parametrize("name", names("solmfg", True))
 def test_gpu_solmfg_with_wedge_boundary_elements(name):
     check_gpu_solmfg(name)
@@ -101,18 +116,20 @@ def test_gpu_itrbc_all_codes_matches_reference_fortran():
     g.close()
 
 
-# The generalized-alpha / LHSupd=2 step fixture is pinned on the oracle (tests/test_timestep.py); its device run
-# is left for the next round.
-def test_gpu_step_matches_reference_fortran():
+@pytest.mark.parametrize("name", ["be_channel", "genalpha_lhsupd2"])
+def test_gpu_step_matches_reference_fortran(name):
+    """one whole step of itrdrv.f's flow sequence (predictor, nitr x (SolGMRe, itrCorrect, itrBC) with LHSupd reuse,
+    itrUpdate, closing itrBC) against the reference's Fortran: backward Euler, and generalized-alpha with LHSupd=2"""
     from phasta_b200.solver import PhastaGPU
     from test_timestep import _step_fixture
-    z, case, opt = _step_fixture("be_channel")
+    z, case, opt = _step_fixture(name)
     params, tables, parts, states = case
     g = PhastaGPU(parts[0], params, tables, device=0)
     y, ac = states[0]
     g.set_state(y, ac)
     g.set_old_state(y, ac)
     st = g.TimeStep(nitr=opt["nitr"], ipred=opt["ipred"], LHSupd=opt["LHSupd"])
+    assert np.array_equal(st[:, 4].astype(int), z["lhs"])          # which iterations re-formed the LHS
     diks = np.abs(st[:, 2].astype(int) - z["iKs"])
     assert diks.max() <= 1, (st[:, 2], z["iKs"])     # a Krylov count next to the tolerance may flip by one
     tol = 1e-9 if diks.max() == 0 else 1e-6
