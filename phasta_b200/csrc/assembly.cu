@@ -19,6 +19,7 @@
 //    (w = {rho, rho u, rho(h+k)}), so sum_i N_a,i A_i is a rank-2 update of A0
 //    and all LHS terms except the viscous one collapse to ONE 5x5x5 product
 //    per (a,b,qp):  W (At_a tau + N_a I) (At_b + c N_b A0).
+// (PHB_HOST_FULL, the other test-only switch: tests/host_emul/fullhost builds the whole library for the host.)
 // PHB_HOST_EMUL: tests/host_emul/ compiles the DEVICE code of this file with g++ behind a SIMT shim (one pthread per
 // CUDA thread) to check kernels against the reference-Fortran fixtures where there is no GPU; the host-side launch
 // code and the kernel with inline PTX are left out of that build.  The product build never defines it.
@@ -897,7 +898,7 @@ __device__ __forceinline__ void point_math(const double Y[5], const double At[5]
   st[S_MU] = mu; st[S_LAM] = lam; st[S_CON] = con;
 }
 
-#ifndef PHB_HOST_EMUL  // inline PTX (named barriers) and the warp-specialised kernel that uses them
+#if !defined(PHB_HOST_EMUL) && !defined(PHB_HOST_FULL)  // inline PTX (named barriers) and the warp-specialised kernel that uses them
 __device__ __forceinline__ void bar_sync_named(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
@@ -2071,6 +2072,10 @@ static int launch_asigmr(phb200_ctx *ctx) {
   return 0;
 }
 
+#ifdef PHB_HOST_FULL  // tests/host_emul/fullhost: no inline PTX on the host, the phase-A/B kernel stands in
+template <int LHS>
+static int launch_asigmr_ws(phb200_ctx *ctx) { return launch_asigmr<32, 4, LHS>(ctx); }
+#else
 template <int LHS>
 static int launch_asigmr_ws(phb200_ctx *ctx) {
   const phb200_common &c = ctx->c;
@@ -2097,6 +2102,7 @@ static int launch_asigmr_ws(phb200_ctx *ctx) {
   PHB_CHECK(cudaGetLastError());
   return 0;
 }
+#endif  // PHB_HOST_FULL
 
 // ---------------------------------------------------------------------------
 // AsIRes + e3 with ires=2 (asires.f:1-94, e3ivar.f, e3conv.f:100-186, e3visc.f:278-343, e3ls.f:95-346,

@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    if os.environ.get("PHB200_TEST_HOST_EMUL") == "1":
+        # TEST INFRASTRUCTURE: exercise the `-m gpu` suite where there is no GPU, against the whole product library
+        # compiled for the host (tests/host_emul/fullhost: fake CUDA runtime, one fiber per CUDA thread).  Only the
+        # test process is redirected; phasta_b200/ knows nothing about it and has no CPU fallback.
+        sys.path.insert(0, os.path.join(ROOT, "tests", "host_emul"))
+        from build_fullhost import build
+        import phasta_b200.lib as lib
+        lib.LIB_PATH = build()
 
 
 def _has_gpu():
