@@ -48,6 +48,23 @@ def test_gpu_boundary_flux_closes_the_patch_test(topo):
     g.close()
 
 
+@pytest.mark.parametrize("topo,nparts", [("mixed", 2), ("hex", 3)])
+def test_gpu_partitioned_with_hex_wedge_boundary_elements(topo, nparts):
+    """one part per (emulated) rank: boundary elements of every kind on partitioned hex / mixed meshes, in-process halo"""
+    from common import make_case, make_oracle
+    from test_gpu_multipart import run_parts
+    case = make_case(6, 4, 2, nparts=nparts, bc="channel", topo=topo, boundary=True, natural="mixed", periodic_z=False,
+                     max_seg=4)
+    o = make_oracle(case)
+    o.ElmGMRe()
+    gs, out = run_parts(case, lambda g, y, ac: g.ElmGMRe(y, ac, want_qres=True))
+    for op, r in zip(o.parts, out):
+        assert rel_l2(r["qres"], op.qres) < 1e-10
+        assert rel_l2(r["res"], op.res) < 1e-10
+        assert rel_l2(r["BDiag"], op.BDiag) < 1e-10
+    [g.close() for g in gs]
+
+
 @pytest.mark.parametrize("name", names("solmfg", True))
 def test_gpu_solmfg_with_wedge_boundary_elements(name):
     check_gpu_solmfg(name)
