@@ -48,9 +48,32 @@ static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSucces
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr, int) { *v = 4; return cudaSuccess; }
-template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)malloc(n ? n : 1); return *p ? cudaSuccess : 2; }
+// "device" allocations carry a 128-byte guard zone on either side, checked when they are freed: a kernel (or a
+// cudaMemcpy) that writes past its buffer aborts the test run instead of corrupting a neighbour silently
+static inline void *shim_dev_alloc(size_t n) {
+  const size_t G = 128;
+  unsigned char *raw = (unsigned char *)malloc(n + 2 * G + 16);
+  if (!raw) return nullptr;
+  memcpy(raw, &n, sizeof n);
+  memset(raw + 16, 0xA5, G - 16);
+  memset(raw + G + n, 0x5A, G);
+  return raw + G;
+}
+static inline void shim_dev_free(void *p) {
+  if (!p) return;
+  const size_t G = 128;
+  unsigned char *raw = (unsigned char *)p - G;
+  size_t n;
+  memcpy(&n, raw, sizeof n);
+  for (size_t i = 16; i < G; i++)
+    if (raw[i] != 0xA5) { fprintf(stderr, "host emulation: write BEFORE a device buffer of %zu bytes\n", n); abort(); }
+  for (size_t i = 0; i < G; i++)
+    if (raw[G + n + i] != 0x5A) { fprintf(stderr, "host emulation: write PAST a device buffer of %zu bytes (+%zu)\n", n, i); abort(); }
+  free(raw);
+}
+template <class T> static inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)shim_dev_alloc(n ? n : 1); return *p ? cudaSuccess : 2; }
 template <class T> static inline cudaError_t cudaMallocHost(T **p, size_t n) { *p = (T *)malloc(n ? n : 1); return cudaSuccess; }
-static inline cudaError_t cudaFree(void *p) { free(p); return cudaSuccess; }
+static inline cudaError_t cudaFree(void *p) { shim_dev_free(p); return cudaSuccess; }
 static inline cudaError_t cudaFreeHost(void *p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = 0) { memmove(d, s, n); return cudaSuccess; }
