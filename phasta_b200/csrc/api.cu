@@ -703,6 +703,7 @@ extern "C" int phb200_commu(phb200_ctx *ctx, double *global, int n, int code) {
   if (n < 1 || n > 25) return fail("commu", "n must be 1..25");
   const size_t len = (size_t)n * ctx->c.nshg;
   double *d = (n <= 5) ? ctx->d_uBrg : ctx->d_scratch;
+  if (n > 5 && len * sizeof(double) > ctx->scratch_bytes) return fail("commu", "vector too long for the staging buffer");
   PHB_TRY(h2d(ctx, d, global, len));
   PHB_TRY(phb_commu(ctx, d, n, code));
   PHB_TRY(d2h(ctx, global, d, len));

@@ -9,11 +9,12 @@
 // -> send, slaves recv -> overwrite.  Transport is NCCL point-to-point over
 // NVLink (one process per GPU), resolved with dlopen so a single-GPU run
 // needs no NCCL at all.  A second transport, the in-process "local group"
-// (several parts on ONE GPU, one host thread each, pthread barrier), exists
+// (several parts on ONE GPU, one host thread each, a barrier with a time-out), exists
 // so the partitioned path can be parity-tested on a single-GPU box.
 #include "ctx.h"
 #include <dlfcn.h>
-#include <pthread.h>
+#include <chrono>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
 
@@ -65,10 +66,57 @@ static int nccl_load() {
   } while (0)
 
 // ---- in-process local group ------------------------------------------------
+// A barrier that gives up: a member that never arrives (its thread died on an exception, or left through an error
+// return) turns into an error on every waiting member after PHB200_LOCAL_TIMEOUT_S seconds (default 60) instead of
+// a process that can never exit.  `failed` is sticky for the group: once one member has reported an error or timed
+// out, every later wait returns at once.
+struct TimedBarrier {
+  std::mutex mu;
+  std::condition_variable cv;
+  int n = 0, waiting = 0;
+  unsigned long gen = 0;
+  bool failed = false;
+  void reset(int nranks) {
+    std::lock_guard<std::mutex> lk(mu);
+    n = nranks;
+    waiting = 0;
+    gen++;
+    failed = false;
+  }
+  // err != 0: this member arrives carrying an error; everybody (including it) gets 1 back
+  int wait(int err = 0) {
+    static const double tmo = [] {
+      const char *e = getenv("PHB200_LOCAL_TIMEOUT_S");
+      double t = e ? atof(e) : 60.0;
+      return t > 0 ? t : 60.0;
+    }();
+    std::unique_lock<std::mutex> lk(mu);
+    if (err) failed = true;
+    if (failed) {
+      cv.notify_all();
+      return 1;
+    }
+    const unsigned long my = gen;
+    if (++waiting == n) {
+      waiting = 0;
+      gen++;
+      cv.notify_all();
+      return 0;
+    }
+    const bool ok = cv.wait_for(lk, std::chrono::duration<double>(tmo), [&] { return gen != my || failed; });
+    if (!ok) {
+      failed = true;
+      cv.notify_all();
+      fprintf(stderr, "phb200: local group: barrier timed out after %.0f s (%d of %d members arrived)\n", tmo, waiting, n);
+      return 1;
+    }
+    return failed ? 1 : 0;
+  }
+};
+
 struct LocalGroup {
   int n = 0;
-  pthread_barrier_t bar;
-  bool bar_init = false;
+  TimedBarrier bar;
   phb200_ctx *members[64] = {};
   double red[64][8] = {};
 };
@@ -77,12 +125,12 @@ static std::mutex g_local_mu;
 
 extern "C" int phb200_local_group_join(phb200_ctx *ctx, int nranks) {
   std::lock_guard<std::mutex> lk(g_local_mu);
-  if (nranks > 64) return 1;
-  if (!g_local.bar_init || g_local.n != nranks) {
-    if (g_local.bar_init) pthread_barrier_destroy(&g_local.bar);
-    pthread_barrier_init(&g_local.bar, nullptr, nranks);
-    g_local.bar_init = true;
+  if (nranks > 64 || nranks < 1 || ctx->c.myrank < 0 || ctx->c.myrank >= nranks) return 1;
+  // a new group (different size, or the slot is taken by another live context) starts with a clean barrier
+  if (g_local.n != nranks || g_local.bar.failed || (g_local.members[ctx->c.myrank] && g_local.members[ctx->c.myrank] != ctx)) {
+    g_local.bar.reset(nranks);
     g_local.n = nranks;
+    for (auto &m : g_local.members) m = nullptr;
   }
   g_local.members[ctx->c.myrank] = ctx;
   ctx->nccl = nullptr;
@@ -143,14 +191,14 @@ static int commu_p2p(phb200_ctx *ctx, double *g, int n, int code) {
   KScope ks(ctx, KC_HALO);
   for (size_t ti = 0; ti < ctx->tasks.size(); ti++) {
     HaloTask &h = ctx->tasks[ti];
-    if (h.iacc != send_role) continue;
+    if (h.iacc != send_role || h.count * n == 0) continue;
     const PhbHaloMsg m = phb_p2p_send_msg(h, ti, n, ctx->d_mail, arena(h.peer), A);
     k_halo_send<<<(m.tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g, m.data, m.flag,
                                                     m.ack, m.msg, ctx->d_halo_tickets + ti, ctx->d_p2p_err);
   }
   for (size_t ti = 0; ti < ctx->tasks.size(); ti++) {
     HaloTask &h = ctx->tasks[ti];
-    if (h.iacc == send_role) continue;
+    if (h.iacc == send_role || h.count * n == 0) continue;
     const PhbHaloMsg m = phb_p2p_recv_msg(h, ti, n, ctx->d_mail, arena(h.peer), A, ctx->halo_cap);
     k_halo_recv<<<(m.tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g, m.data, m.flag,
                                                     m.ack, m.msg, code == 0, ctx->d_halo_tickets + ti, ctx->d_p2p_err);
@@ -177,7 +225,7 @@ int phb_commu(phb200_ctx *ctx, double *g, int n, int code) {
   {
     KScope ks(ctx, KC_HALO);
     for (auto &h : ctx->tasks)
-      if (h.iacc == send_role) {
+      if (h.iacc == send_role && h.count > 0) {
         int tot = h.count * n;
         k_halo_pack<<<(tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g,
                                                       ctx->d_sendbuf + (size_t)h.offset * 25);
@@ -197,28 +245,31 @@ int phb_commu(phb200_ctx *ctx, double *g, int n, int code) {
     NCCL_CHECK(N.GroupEnd());
   } else {
     // local group: every rank's packed data must be complete before peers read it
-    PHB_CHECK(cudaStreamSynchronize(s));
-    pthread_barrier_wait(&g_local.bar);
+    // (errors travel through the barrier so that no member is left waiting for one that has returned)
+    int err = cudaStreamSynchronize(s) != cudaSuccess;
+    if (g_local.bar.wait(err)) return 1;
     for (auto &h : ctx->tasks)
-      if (h.iacc != send_role) {
+      if (h.iacc != send_role && !err) {
         phb200_ctx *peer = g_local.members[h.peer];
         const HaloTask *ph = nullptr;
-        for (auto &t : peer->tasks)
-          if (t.tag == h.tag && t.peer == ctx->c.myrank && t.iacc == send_role) ph = &t;
+        if (peer)
+          for (auto &t : peer->tasks)
+            if (t.tag == h.tag && t.peer == ctx->c.myrank && t.iacc == send_role) ph = &t;
         if (!ph || ph->count != h.count) {
           fprintf(stderr, "phb200: commu: unmatched task tag %d\n", h.tag);
-          return 1;
+          err = 1;
+          break;
         }
-        PHB_CHECK(cudaMemcpyAsync(ctx->d_recvbuf + (size_t)h.offset * 25, peer->d_sendbuf + (size_t)ph->offset * 25,
-                                  sizeof(double) * h.count * n, cudaMemcpyDeviceToDevice, s));
+        err = cudaMemcpyAsync(ctx->d_recvbuf + (size_t)h.offset * 25, peer->d_sendbuf + (size_t)ph->offset * 25,
+                              sizeof(double) * h.count * n, cudaMemcpyDeviceToDevice, s) != cudaSuccess;
       }
-    PHB_CHECK(cudaStreamSynchronize(s));
-    pthread_barrier_wait(&g_local.bar);
+    err |= cudaStreamSynchronize(s) != cudaSuccess;
+    if (g_local.bar.wait(err)) return 1;
   }
   {
     KScope ks(ctx, KC_HALO);
     for (auto &h : ctx->tasks)
-      if (h.iacc != send_role) {
+      if (h.iacc != send_role && h.count > 0) {
         int tot = h.count * n;
         k_halo_unpack<<<(tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g,
                                                         ctx->d_recvbuf + (size_t)h.offset * 25, code == 0);
@@ -250,7 +301,14 @@ int phb_p2p_check(phb200_ctx *ctx) {
   PHB_CHECK(cudaMemcpyAsync(&e, ctx->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PHB_CHECK(cudaStreamSynchronize(ctx->stream));
   if (e) {
-    fprintf(stderr, "phb200: peer all-reduce timed out waiting for rank %d\n", e - 1);
+    // codes written by the device: 1..PHB_MAXR = all-reduce lane waiting for rank e-1; 100 = a halo sender
+    // waiting for the receiver's acknowledgement; 200 = a halo receiver waiting for the sender's flag
+    if (e == 200)
+      fprintf(stderr, "phb200: peer halo receive timed out waiting for a sender's flag\n");
+    else if (e == 100)
+      fprintf(stderr, "phb200: peer halo send timed out waiting for a receiver's acknowledgement\n");
+    else
+      fprintf(stderr, "phb200: peer all-reduce timed out waiting for rank %d\n", e - 1);
     return 1;
   }
   return 0;
@@ -271,14 +329,14 @@ int phb_allreduce_sum(phb200_ctx *ctx, double *d_vals, int n) {
   if (ctx->local_group) {
     if (n < 1 || n > 8) return 1;
     double v[8];
-    PHB_CHECK(cudaMemcpyAsync(v, d_vals, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+    int err = cudaMemcpyAsync(v, d_vals, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess;
+    err |= cudaStreamSynchronize(ctx->stream) != cudaSuccess;
     for (int k = 0; k < n; k++) g_local.red[ctx->c.myrank][k] = v[k];
-    pthread_barrier_wait(&g_local.bar);
+    if (g_local.bar.wait(err)) return 1;
     double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int r = 0; r < g_local.n; r++)
       for (int k = 0; k < n; k++) s[k] += g_local.red[r][k];
-    pthread_barrier_wait(&g_local.bar);
+    if (g_local.bar.wait(0)) return 1;
     PHB_CHECK(cudaMemcpyAsync(d_vals, s, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
     PHB_CHECK(cudaStreamSynchronize(ctx->stream));
     return 0;

@@ -236,6 +236,11 @@ int phb_timestep(phb200_ctx *ctx, const phb200_step *st0, int ipred, int nitr, i
     fprintf(stderr, "phb200: timestep: nitr and LHSupd must be >= 1\n");
     return 1;
   }
+  if (sparse != 0 && sparse != 1) {
+    // 2 would pair a CSR assembly with the matrix-free solve, which needs phb_elmmfg's rmes: not a step flavour
+    fprintf(stderr, "phb200: timestep: sparse must be 0 (EBE) or 1 (CSR), got %d\n", sparse);
+    return 1;
+  }
   phb200_step st = *st0;
   st.nitr = nitr;
   PHB_TRY(phb_itrpredict(ctx, &st, ipred));

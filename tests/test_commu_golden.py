@@ -15,7 +15,8 @@ from make_golden_commu import MAXSEG, NPARTS, NS, NX, NY, NZ  # noqa: E402
 
 
 def _load():
-    z = np.load(os.path.join(GOLD, "f77_commu.npz"))
+    with np.load(os.path.join(GOLD, "f77_commu.npz")) as f:
+        z = {k: f[k] for k in f.files}          # a plain dict: NpzFile must not be indexed from several threads
     case = make_case(NX, NY, NZ, nparts=NPARTS, bc="channel", max_seg=MAXSEG)
     return z, case
 

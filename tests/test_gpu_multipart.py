@@ -29,7 +29,8 @@ def run_parts(case, fn):
         except Exception as e:  # pragma: no cover
             errs.append(e)
 
-    th = [threading.Thread(target=work, args=(i,)) for i in range(n)]
+    # daemon threads: a worker stuck in the transport can fail the test but never keep the interpreter from exiting
+    th = [threading.Thread(target=work, args=(i,), daemon=True) for i in range(n)]
     [t.start() for t in th]
     [t.join(timeout=120) for t in th]
     assert not errs, errs

@@ -102,6 +102,8 @@ def test_gpu_commu_matches_reference_fortran(n):
     from test_commu_golden import _load
     from test_gpu_multipart import run_parts
     z, case = _load()
+    # NpzFile is not thread-safe (a shared zip handle): read every array before the worker threads start
+    assert isinstance(z, dict)
 
     def fn(g, y, ac):
         v = z["in_n%d_r%d" % (n, g.part.rank)].copy(order="F")
