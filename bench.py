@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FLOP_PER_ELEM_LHS = 52000.0     # hand count, 4-pt rule, lhs=1, incl. AsIq
+FLOP_PER_ELEM_ASIQ = 2800.0     # of which the AsIq/e3q pre-pass (k_asiq_tet, not the dominant kernel)
+FLOP_PER_ELEM_KERNEL = FLOP_PER_ELEM_LHS - FLOP_PER_ELEM_ASIQ   # what k_asigmr_tet_ws<1> replaces: 49.2 kflop/element
 FLOP_PER_ELEM_INSTR = 51026.0   # counted while executing the reference Fortran (tests/golden/count_flops_f77.py)
 BYTES_PER_ELEM_LHS = 3310.0     # EGmass 3200 + ien 16 + node data/6
 BYTES_PER_ELEM_AP = 3215.0      # EBE Ap
@@ -85,6 +87,22 @@ def ncu_traffic(kind):
         if m:
             tot += float(m.group(3).replace(",", "")) * unit.get(m.group(2), 1.0)
     return {"bytes_per_launch": tot, "source": os.path.relpath(files[-1], ROOT)} if tot else None
+
+
+def ncu_metric(kind, name):
+    """one metric of the newest committed `ncu --set full` summary profiles/r*_prof_<kind>.txt, or None"""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_prof_%s.txt" % kind)))
+    if not files:
+        return None
+    for ln in open(files[-1]):
+        f = ln.split()
+        if f and f[0] == name:
+            try:
+                return {"value": float(f[-1].replace(",", "")), "source": os.path.relpath(files[-1], ROOT)}
+            except ValueError:
+                return None
+    return None
 
 
 class ClockSampler(threading.Thread):
@@ -153,6 +171,71 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.smax or None,
                 "reasons": sorted(self.reasons), "samples": len(self.sm),
                 "source": "nvml" if self.nv else "nvidia-smi"}
+
+
+def pin_to_gpu_numa(local_rank):
+    """Bind this rank's host threads to the CPUs of its GPU's NUMA node (pinned-buffer copies of several ranks then
+    do not share one socket's memory controller).  Returns what was done, for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(local_rank), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (dom, bus, dev)
+        node = int(open(path + "/numa_node").read())
+        cpus = open(path + "/local_cpulist").read().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        ids &= allowed
+        if node >= 0 and ids and ids != allowed:
+            os.sched_setaffinity(0, ids)
+            return {"numa_node": node, "cpus": cpus, "pinned": True}
+        return {"numa_node": node, "cpus": cpus, "pinned": False}
+    except Exception as e:  # no sysfs entry (containers): leave the affinity alone
+        return {"pinned": False, "why": repr(e)[:80]}
+
+
+def parity_small(world, rank, local_rank, init_comm):
+    """SolGMRe of a small channel (4*world x 5 x 4 hexes, one x-slab per rank, split ilwork segments) through the
+    very transport the timed legs use, against the oracle run over all parts.  Every rank computes its own errors;
+    the caller takes the max over ranks."""
+    from phasta_b200 import SolverParams, make_box, make_state, make_tables, global_node_count
+    from phasta_b200.solver import PhastaGPU
+    from oracle import oracle_py
+    nx, ny, nz = 4 * world, 5, 4
+    params = SolverParams(etol=1e-7, Kspace=30)
+    tables = make_tables(2, 2)
+    parts = make_box(nx, ny, nz, nparts=world, bc="channel", max_seg=9)
+    ng = global_node_count(nx, ny, nz)
+    states = [make_state(p, ng) for p in parts]
+    g = PhastaGPU(parts[rank], params, tables, device=local_rank)
+    init_comm(g)
+    res, Dy = g.SolGMRe(*states[rank])
+    o = oracle_py.Oracle(parts, params, tables, states)
+    iKs, _ = o.SolGMRe()
+    op = o.parts[rank]
+
+    def rel(a, b):
+        return float(np.linalg.norm((a - b).ravel()) / max(np.linalg.norm(b.ravel()), 1e-300))
+    out = [rel(res, op.res), rel(g.rmes, op.rmes), rel(Dy, op.Dy), float(abs(g.iKs - iKs)), float(iKs)]
+    g.close()
+    return out
+
+
+def parity_at_size(g, part, params, tables, y, ac, workload, st):
+    """rank 0: the part just assembled on the device against the oracle on its first / middle / last x-slab
+    (oracle/spot_check.py).  g holds ElmGMRe(lhs=1) of (y, ac)."""
+    from oracle.spot_check import slab_check
+    ny, nz = WORKLOADS[workload][1:3]
+    t0 = time.perf_counter()
+    s = slab_check(g, part, params, tables, y, ac, (ny + 1) * (nz + 1), flavour="ebe", max_chunks=3)
+    return {"res": s["res"], "BDiag": s["BDiag"], "EGmass": s["EGmass"], "nodes_checked": s["nodes"],
+            "elements_checked": s["elements"], "last_element_checked": s["last_element_checked"], "slabs": s["slabs"],
+            "seconds": time.perf_counter() - t0, "tol": 1e-10,
+            "ok": bool(s["res"] < 1e-10 and s["BDiag"] < 1e-10 and s["EGmass"] < 1e-10)}
 
 
 def build_part(workload, rank, world):
@@ -398,92 +481,51 @@ def emit(line):
         os.write(_STDOUT_FD, data)
 
 
-def main():
-    _quiet_stdout()
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2_channel_4M", choices=list(WORKLOADS))
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--no-solve", action="store_true", help="skip the Ap / SolGMRe legs (profiling runs)")
-    ap.add_argument("--no-sparse", action="store_true", help="skip the block-CSR (SolGMRs) leg")
-    ap.add_argument("--no-mfg", action="store_true", help="skip the matrix-free (SolMFG) leg")
-    ap.add_argument("--no-incomp", action="store_true", help="skip the incompressible (ElmGMR + ApFull) leg")
-    ap.add_argument("--cpu-seconds", type=float, default=0.0, help="CPU sample length per step of --impl reference")
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        return reference_arm(args)
+class Env:
+    """rank bookkeeping + the contract's barrier / max-over-ranks"""
 
-    import torch
-    import torch.distributed as dist
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        print("bench.py: WORLD_SIZE=%d but --gpus %d" % (world, args.gpus), file=sys.stderr)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; phasta_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    def __init__(self, world, rank, local_rank):
+        self.world, self.rank, self.local_rank = world, rank, local_rank
+        self.g = None
 
-    from phasta_b200 import SolverParams, make_tables
-    from phasta_b200.solver import PhastaGPU, nccl_unique_id
-
-    params = SolverParams(ibksiz=1024, etol=1e-3, Kspace=50)
-    tables = make_tables(2, 2)
-    part, y, ac = build_part(args.workload, rank, world)
-    g = PhastaGPU(part, params, tables, device=local_rank)
-
-    def init_comm(gx):
-        if world > 1:
-            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                idt = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
-            dist.broadcast(idt, 0)
-            gx.comm_init(bytes(idt.cpu().tolist()))
-
-    init_comm(g)
-
-    def barrier():
-        g.sync()
-        if world > 1:
+    def barrier(self):
+        import torch
+        import torch.distributed as dist
+        if self.g is not None:
+            self.g.sync()
+        if self.world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def maxrank(ms):
-        if world == 1:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    def maxrank(self, v):
+        if self.world == 1:
+            return v
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+
+def time_workload(env, g, part, steps, warmup, *, solve=True, sparse=True, residual_only=True):
+    """The timed legs on a resident state: K ElmGMRe passes (the headline), per-kernel-class shares, residual-only
+    assembly, SolGMRe + Ap/s, and the block-CSR flavour (genadj, ElmGMRs, SolGMRs, SparseAp/s)."""
+    barrier, maxrank, world = env.barrier, env.maxrank, env.world
+    env.g = g
     numel_total = part.numel * world
     st = g.step()
-    g.set_state(y, ac)
-    fp64_peak = g.fp64_peak() if rank == 0 else 0.0
-
-    # ------------------------------------------------ timed: K assemblies
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         g.dev_elmgmre(st)
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     l0 = g.launches()
     g.profile_reset()
     g.event(0)
-    for _ in range(args.steps):
+    for _ in range(steps):
         g.dev_elmgmre(st)
     g.event(1)
     barrier()
-    asm_ms = maxrank(g.elapsed_ms(0, 1)) / args.steps
-    launches = g.launches() - l0
-    value = numel_total / (asm_ms * 1e-3)
-
+    asm_ms = maxrank(g.elapsed_ms(0, 1)) / steps
+    out = {"asm_ms": asm_ms, "value": numel_total / (asm_ms * 1e-3), "launches": g.launches() - l0}
     # per-kernel-class share (events around every launch; separate pass)
     g.profile(True)
     g.profile_reset()
@@ -491,30 +533,28 @@ def main():
         g.dev_elmgmre(st)
     prof = g.profile_get()
     g.profile(False)
-    kern_ms = prof["assembly"][0] / max(1, prof["assembly"][1])
-    asiq_ms = prof["asiq"][0] / max(1, prof["asiq"][1])
-
-    # residual-only assembly (lhs=0)
-    st0 = g.step(lhs=0, iprec=0)
-    for _ in range(2):
-        g.dev_elmgmre(st0)
-    barrier()
-    g.event(2)
-    for _ in range(args.steps):
-        g.dev_elmgmre(st0)
-    g.event(3)
-    barrier()
-    res_ms = maxrank(g.elapsed_ms(2, 3)) / args.steps
-    g.dev_elmgmre(st)   # restore the LHS
-
-    extra = {}
-    if not args.no_solve:
+    out["prof"] = prof
+    out["kern_ms"] = prof["assembly"][0] / max(1, prof["assembly"][1])
+    out["asiq_ms"] = prof["asiq"][0] / max(1, prof["asiq"][1])
+    if residual_only:
+        st0 = g.step(lhs=0, iprec=0)
+        for _ in range(2):
+            g.dev_elmgmre(st0)
+        barrier()
+        g.event(2)
+        for _ in range(steps):
+            g.dev_elmgmre(st0)
+        g.event(3)
+        barrier()
+        out["res_ms"] = maxrank(g.elapsed_ms(2, 3)) / steps
+        g.dev_elmgmre(st)   # restore the LHS
+    nap = max(20, steps)
+    if solve:
         # ------------------------------------------------ full SolGMRe, then Ap/s on its basis
         g.dev_elmgmre(st)
         g.dev_solve(st)
         barrier()
-        solve_ms = []
-        its = []
+        solve_ms, its = [], []
         for _ in range(3):
             g.dev_elmgmre(st)
             barrier()
@@ -523,7 +563,6 @@ def main():
             g.event(5)
             barrier()
             solve_ms.append(maxrank(g.elapsed_ms(4, 5)))
-        nap = max(20, args.steps)
         for _ in range(3):
             g.dev_ap(0)
         barrier()
@@ -539,15 +578,13 @@ def main():
             g.dev_ap(i)
         ap_k_ms = g.profile_get()["ap"][0] / 4
         g.profile(False)
-        extra = {
-            "ap": {"value": 1e3 / ap_ms, "unit": "Ap/s", "ms_per_ap": ap_ms, "kernel_ms": ap_k_ms,
-                   "elements_per_s": numel_total / (ap_ms * 1e-3)},
-            "solgmre": {"solve_ms": float(np.mean(solve_ms)), "gmres_iterations": int(its[-1]),
-                        "implicit_solve_ms": float(np.mean(solve_ms)) + asm_ms,
-                        "krylov_its_per_s": its[-1] / (np.mean(solve_ms) * 1e-3), "etol": params.etol},
-        }
-
-    if not args.no_solve and not args.no_sparse:
+        sm = float(np.mean(solve_ms))
+        out["ap"] = {"value": 1e3 / ap_ms, "unit": "Ap/s", "ms_per_ap": ap_ms, "kernel_ms": ap_k_ms,
+                     "elements_per_s": numel_total / (ap_ms * 1e-3)}
+        out["solgmre"] = {"solve_ms": sm, "gmres_iterations": int(its[-1]), "ms_per_iteration": sm / max(1, its[-1]),
+                          "implicit_solve_ms": sm + asm_ms, "krylov_its_per_s": its[-1] / (sm * 1e-3),
+                          "etol": g.params.etol}
+    if solve and sparse:
         # ------------------------------------------------ block-CSR flavour (SolGMRs)
         t0 = time.perf_counter()
         _, _, nnz_tot = g.genadj()
@@ -556,11 +593,16 @@ def main():
             g.dev_elmgmrs(st)
         barrier()
         g.event(10)
-        for _ in range(args.steps):
+        for _ in range(steps):
             g.dev_elmgmrs(st)
         g.event(11)
         barrier()
-        asm_s_ms = maxrank(g.elapsed_ms(10, 11)) / args.steps
+        asm_s_ms = maxrank(g.elapsed_ms(10, 11)) / steps
+        g.profile(True)
+        g.profile_reset()
+        g.dev_elmgmrs(st)
+        asm_s_k_ms = g.profile_get()["assembly"][0]
+        g.profile(False)
         g.dev_solve_sparse(st)
         barrier()
         s_ms, s_its = [], []
@@ -588,14 +630,192 @@ def main():
         sap_k_ms = g.profile_get()["ap"][0] / 4
         g.profile(False)
         csr_bytes = nnz_tot * 204.0 + part.nshg * 84.0
-        extra["sparse"] = {
-            "nnz_tot_per_gpu": int(nnz_tot), "genadj_host_s": genadj_s,
+        ssm = float(np.mean(s_ms))
+        out["sparse"] = {
+            "nnz_tot_per_gpu": int(nnz_tot), "genadj_s": genadj_s,
             "elements_assembled_per_s": numel_total / (asm_s_ms * 1e-3), "assembly_ms": asm_s_ms,
+            "assembly_kernel_ms": asm_s_k_ms,
             "sparseap_per_s": 1e3 / sap_ms, "sparseap_ms": sap_ms, "sparseap_kernel_ms": sap_k_ms,
-            "solve_ms": float(np.mean(s_ms)), "gmres_iterations": int(s_its[-1]),
+            "solve_ms": ssm, "gmres_iterations": int(s_its[-1]), "ms_per_iteration": ssm / max(1, s_its[-1]),
+            "implicit_solve_ms": ssm + asm_s_ms,
             "roofline_sparseap": {"bound": "hbm", "kernel": "k_sparseap", "unit": "GB/s",
                                   "achieved": csr_bytes / (sap_k_ms * 1e-3) / 1e9,
                                   "algorithmic_bytes": csr_bytes}}
+    return out
+
+
+def e2e_legs(env, g, part, y, ac, steps, sparse):
+    """The same metric through the reference-facing C-ABI calls with HOST buffers: pinned y / ac in, res (and Dy) out,
+    copies inside the timed region.  (1) phb200_elmgmre -- the headline's e2e; (2) the whole call the reference's
+    itrdrv makes, phb200_solgmrs (assembly into CSR + SolGMRs), when the CSR structure is resident."""
+    import ctypes as C
+    import torch
+    from phasta_b200.solver import _p, _chk
+    numel_total = part.numel * env.world
+    st = g.step()
+    yp = torch.from_numpy(np.ascontiguousarray(y.T)).pin_memory()      # (5,nshg) C == (nshg,5) F
+    acp = torch.from_numpy(np.ascontiguousarray(ac.T)).pin_memory()
+    resp = torch.empty_like(yp).pin_memory()
+    dyp = torch.empty_like(yp).pin_memory()
+    yv, acv, resv, dyv = (t.numpy().T for t in (yp, acp, resp, dyp))
+    for _ in range(2):
+        _chk(g.L.phb200_elmgmre(g.ctx, _p(yv), _p(acv), C.byref(st), _p(resv), None, None, None), "elmgmre")
+    env.barrier()
+    g.event(8)
+    ne2e = max(3, steps // 2)
+    for _ in range(ne2e):
+        _chk(g.L.phb200_elmgmre(g.ctx, _p(yv), _p(acv), C.byref(st), _p(resv), None, None, None), "elmgmre")
+    g.event(9)
+    env.barrier()
+    e2e_ms = env.maxrank(g.elapsed_ms(8, 9)) / ne2e
+    e2e = {"value": numel_total / (e2e_ms * 1e-3), "unit": "elements/s",
+           "h2d_bytes_per_step": int(2 * y.nbytes), "d2h_bytes_per_step": int(y.nbytes), "ms_per_step": e2e_ms,
+           "api": "phb200_elmgmre (host y, ac in; host res out; EGmass/BDiag stay in HBM)"}
+    if sparse:
+        iKs, lG, ntot = C.c_int(0), C.c_int(0), C.c_int(0)
+
+        def call():
+            _chk(g.L.phb200_solgmrs(g.ctx, _p(yv), _p(acv), C.byref(st), _p(resv), None, None, _p(dyv), None, None,
+                                    None, None, None, C.byref(iKs), C.byref(lG), C.byref(ntot)), "solgmrs")
+        call()
+        env.barrier()
+        g.event(8)
+        for _ in range(3):
+            call()
+        g.event(9)
+        env.barrier()
+        ms = env.maxrank(g.elapsed_ms(8, 9)) / 3
+        e2e["solgmrs"] = {"ms_per_call": ms, "elements_per_s": numel_total / (ms * 1e-3),
+                          "gmres_iterations": int(iKs.value),
+                          "h2d_bytes_per_step": int(2 * y.nbytes), "d2h_bytes_per_step": int(2 * y.nbytes),
+                          "api": "phb200_solgmrs (host y, ac in; ElmGMRs + SolGMRs; host res, Dy out)"}
+    return e2e
+
+
+def side_workload(env, args, name, params, tables, init_comm, steps):
+    """A second BASELINE.json configuration under the same driver call (its own context; the main one is closed
+    first so that 103 GB of EGmass fit): assembly, Ap, both solves, and the slab parity check on rank 0."""
+    from phasta_b200.solver import PhastaGPU
+    t0 = time.perf_counter()
+    part, y, ac = build_part(name, env.rank, env.world)
+    g = PhastaGPU(part, params, tables, device=env.local_rank)
+    init_comm(g)
+    g.set_state(y, ac)
+    setup_s = time.perf_counter() - t0
+    st = g.step()
+    g.dev_elmgmre(st)
+    par = None
+    if env.rank == 0 and not args.no_check:
+        try:
+            par = parity_at_size(g, part, params, tables, y, ac, name, st)
+        except Exception as e:
+            par = {"ok": False, "error": repr(e)[:200]}
+    r = time_workload(env, g, part, steps, 3, residual_only=False)
+    all_tets = len(WORKLOADS[name]) == 3
+    tf = part.numel * FLOP_PER_ELEM_KERNEL / (r["kern_ms"] * 1e-3) / 1e12 if all_tets else None
+    out = {"workload": name, "elements": part.numel * env.world, "elements_per_gpu": part.numel,
+           "nodes_per_gpu": part.nshg, "value": r["value"], "unit": "elements/s", "ms_per_step": r["asm_ms"],
+           "assembly_kernel_ms": r["kern_ms"], "assembly_kernel_TFLOPs_reference_equivalent": tf,
+           "ap": r.get("ap"), "solgmre": r.get("solgmre"), "sparse": r.get("sparse"), "parity": par,
+           "egmass_GB_per_gpu": part.numel * (5 * max(int(b.shape[1]) for b in part.mien)) ** 2 * 8 / 1e9,
+           "setup_s": setup_s}
+    env.g = None
+    g.close()
+    return out
+
+
+def main():
+    _quiet_stdout()
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_channel_4M", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-solve", action="store_true", help="skip the Ap / SolGMRe legs (profiling runs)")
+    ap.add_argument("--no-sparse", action="store_true", help="skip the block-CSR (SolGMRs) leg")
+    ap.add_argument("--no-mfg", action="store_true", help="skip the matrix-free (SolMFG) leg")
+    ap.add_argument("--no-incomp", action="store_true", help="skip the incompressible (ElmGMR + ApFull) leg")
+    ap.add_argument("--no-check", action="store_true", help="skip the parity legs (profiling runs)")
+    ap.add_argument("--no-side", action="store_true",
+                    help="skip the second configuration (c5_tet_32M at N=1, c3_plate_mixed_4M at N>1)")
+    ap.add_argument("--cpu-seconds", type=float, default=0.0, help="CPU sample length per step of --impl reference")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        print("bench.py: WORLD_SIZE=%d but --gpus %d" % (world, args.gpus), file=sys.stderr)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; phasta_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    numa = pin_to_gpu_numa(local_rank) if world > 1 else {"pinned": False, "why": "single rank"}
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from phasta_b200 import SolverParams, make_tables
+    from phasta_b200.solver import PhastaGPU, nccl_unique_id
+
+    env = Env(world, rank, local_rank)
+    params = SolverParams(ibksiz=1024, etol=1e-3, Kspace=50)
+    tables = make_tables(2, 2)
+
+    def init_comm(gx):
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt = torch.tensor(list(nccl_unique_id()), dtype=torch.uint8, device="cuda")
+            dist.broadcast(idt, 0)
+            gx.comm_init(bytes(idt.cpu().tolist()))
+
+    # ------------------------------------------------ parity before anything is timed (exit 1 on failure)
+    parity = None
+    if not args.no_check:
+        e = parity_small(world, rank, local_rank, init_comm)
+        if world > 1:
+            t = torch.tensor(e[:4], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e[:4] = t.cpu().tolist()
+        parity = {"case": "SolGMRe, %dx5x4-hex channel, %d part(s), transport %s" % (
+                      4 * world, world, "NCCL/NVLink (+peer-memory dots)" if world > 1 else "single part"),
+                  "res": e[0], "rmes": e[1], "Dy": e[2], "gmres_iterations": int(e[4]), "iterations_equal": e[3] == 0,
+                  "tol": {"res": 1e-10, "Dy": 1e-8},
+                  "ok": bool(e[0] < 1e-10 and e[1] < 1e-10 and e[2] < 1e-8 and e[3] == 0)}
+
+    part, y, ac = build_part(args.workload, rank, world)
+    g = PhastaGPU(part, params, tables, device=local_rank)
+    init_comm(g)
+    env.g = g
+    barrier, maxrank = env.barrier, env.maxrank
+    numel_total = part.numel * world
+    st = g.step()
+    g.set_state(y, ac)
+    fp64_peak = g.fp64_peak() if rank == 0 else 0.0
+    if parity is not None:
+        g.dev_elmgmre(st)
+        if rank == 0:
+            try:
+                parity["at_size"] = parity_at_size(g, part, params, tables, y, ac, args.workload, st)
+            except Exception as e:
+                parity["at_size"] = {"ok": False, "error": repr(e)[:200]}
+            parity["ok"] = bool(parity["ok"] and parity["at_size"]["ok"])
+        if world > 1:
+            dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    core = time_workload(env, g, part, args.steps, args.warmup, solve=not args.no_solve, sparse=not args.no_sparse)
+    asm_ms, value, launches, prof = core["asm_ms"], core["value"], core["launches"], core["prof"]
+    kern_ms, asiq_ms = core["kern_ms"], core["asiq_ms"]
+    extra = {k: core[k] for k in ("ap", "solgmre", "sparse") if k in core}
 
     # ------------------------------------------------ incompressible flavour on the same mesh / CSR structure
     if not args.no_solve and not args.no_incomp:
@@ -613,55 +833,52 @@ def main():
             extra["mfg"] = {"error": repr(e)}
 
     # ------------------------------------------------ e2e through the C-ABI with host buffers
-    import ctypes as C
-    yp = torch.from_numpy(np.ascontiguousarray(y.T)).pin_memory()      # (5,nshg) C == (nshg,5) F
-    acp = torch.from_numpy(np.ascontiguousarray(ac.T)).pin_memory()
-    resp = torch.empty_like(yp).pin_memory()
-    yv, acv, resv = (t.numpy().T for t in (yp, acp, resp))
-    from phasta_b200.solver import _p, _chk
-    for _ in range(2):
-        _chk(g.L.phb200_elmgmre(g.ctx, _p(yv), _p(acv), C.byref(st), _p(resv), None, None, None), "elmgmre")
-    barrier()
-    t0 = time.perf_counter()
-    g.event(8)
-    ne2e = max(3, args.steps // 2)
-    for _ in range(ne2e):
-        _chk(g.L.phb200_elmgmre(g.ctx, _p(yv), _p(acv), C.byref(st), _p(resv), None, None, None), "elmgmre")
-    g.event(9)
-    barrier()
-    e2e_ms = maxrank(g.elapsed_ms(8, 9)) / ne2e
-    e2e = {"value": numel_total / (e2e_ms * 1e-3), "unit": "elements/s",
-           "h2d_bytes_per_step": int(2 * y.nbytes), "d2h_bytes_per_step": int(y.nbytes), "ms_per_step": e2e_ms,
-           "api": "phb200_elmgmre (host y, ac in; host res out; EGmass/BDiag stay in HBM)"}
+    e2e = e2e_legs(env, g, part, y, ac, args.steps, "sparse" in extra)
 
     # the sampler ran through every timed leg above (assembly, Ap, solves, e2e): median SM clock under load
     clocks = sampler.summary() if rank == 0 else {}
+    env.g = None
+    g.close()
+
+    # ------------------------------------------------ the other BASELINE.json configuration this driver call covers
+    side = None
+    if not args.no_side and not args.no_solve and args.workload == "c2_channel_4M":
+        name = "c5_tet_32M" if world == 1 else "c3_plate_mixed_4M"
+        fits = name != "c5_tet_32M" or torch.cuda.mem_get_info(local_rank)[1] > 150e9
+        if fits:
+            try:
+                side = side_workload(env, args, name, params, tables, init_comm, max(3, args.steps // 2))
+            except Exception as e:
+                side = {"workload": name, "error": repr(e)[:300]}
+        else:
+            side = {"workload": name, "skipped": "needs a 180 GB GPU"}
+
     if rank == 0:
         hbm, src = peaks()
         elem_per_launch = part.numel
-        tf = elem_per_launch * FLOP_PER_ELEM_LHS / (kern_ms * 1e-3) / 1e12
         c2 = args.workload == "c2_channel_4M"
         tr_asm, tr_ap = (ncu_traffic("asm"), ncu_traffic("ap")) if c2 else (None, None)
         all_tets = len(WORKLOADS[args.workload]) == 3
-        if not all_tets:   # the 52 kflop/element count is for 4-pt tets; the class time covers every topology
-            tf = float("nan")
-        roof = {"bound": "tensor", "kernel": "k_asigmr_tet_ws<1> (FP64 pipe; 'tensor' = compute-bound)",
-                "achieved": tf if all_tets else None, "peak": fp64_peak, "unit": "TFLOP/s",
+        # reference-equivalent flops of the dominant kernel alone (the AsIq pre-pass runs in k_asiq_tet)
+        tf = elem_per_launch * FLOP_PER_ELEM_KERNEL / (kern_ms * 1e-3) / 1e12 if all_tets else None
+        roof = {"bound": "fp64", "kernel": "k_asigmr_tet_ws<1> (FP64 FMA pipe, not tensor cores; DESIGN 4.1d)",
+                "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": (tf / fp64_peak) if (fp64_peak and all_tets) else None,
                 "traffic": tr_asm and tr_asm["bytes_per_launch"], "traffic_source": tr_asm and tr_asm["source"],
-                "peak_source": "FP64 DFMA-chain microbenchmark run in this process "
-                                                "(MEASURED_PEAKS.json has no FP64 entry); nominal %.0f TF" % FP64_NOMINAL_TF,
+                "peak_source": "FP64 DFMA-chain microbenchmark run in this process at the clocks of this run "
+                               "(MEASURED_PEAKS.json has no FP64 entry); nominal %.0f TF" % FP64_NOMINAL_TF,
                 "frac_of_nominal": (tf / FP64_NOMINAL_TF) if all_tets else None,
-                "flop_per_element": FLOP_PER_ELEM_LHS, "flop_per_element_instrumented": FLOP_PER_ELEM_INSTR,
-                "frac_instrumented": (tf * FLOP_PER_ELEM_INSTR / FLOP_PER_ELEM_LHS / fp64_peak)
-                if (fp64_peak and all_tets) else None,
+                "flop_per_element": FLOP_PER_ELEM_KERNEL,
+                "flop_note": "reference-equivalent: SURVEY 8(d) 52 kflop/element minus the 2.8 k of the AsIq pre-pass; the "
+                             "kernel itself executes fewer (rank-2 algebra), see fp64_pipe_active_ncu",
+                "fp64_pipe_active_ncu": ncu_metric("asm", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
                 "kernel_ms": kern_ms, "asiq_kernel_ms": asiq_ms,
                 "hbm_GBps_algorithmic": elem_per_launch * BYTES_PER_ELEM_LHS / (kern_ms * 1e-3) / 1e9,
                 "hbm_peak_GBps": hbm, "hbm_peak_source": src}
         if "sparse" in extra:
             rs = extra["sparse"]["roofline_sparseap"]
             rs["peak"], rs["frac"], rs["peak_source"] = hbm, rs["achieved"] / hbm, src
-        if extra:
+        if "ap" in extra:
             gbs = elem_per_launch * BYTES_PER_ELEM_AP / (extra["ap"]["kernel_ms"] * 1e-3) / 1e9
             extra["roofline_ap"] = {"bound": "hbm", "kernel": "k_ap_ebe_tet", "achieved": gbs, "peak": hbm,
                                     "unit": "GB/s", "frac": gbs / hbm,
@@ -670,22 +887,42 @@ def main():
         cb = None
         if not args.no_cpu:
             cb = cpu_baseline(args.workload, os.cpu_count() or 1)
+        # short summary first: the driver keeps the head and the tail of long lines
+        krylov = {}
+        if "ap" in extra:
+            krylov = {"ap_per_s": extra["ap"]["value"], "solgmre_solve_ms": extra["solgmre"]["solve_ms"],
+                      "solgmre_ms_per_iteration": extra["solgmre"]["ms_per_iteration"]}
+        if "sparse" in extra:
+            krylov.update({"solgmrs_solve_ms": extra["sparse"]["solve_ms"],
+                           "solgmrs_ms_per_iteration": extra["sparse"]["ms_per_iteration"],
+                           "sparseap_per_s": extra["sparse"]["sparseap_per_s"],
+                           "elmgmrs_elements_per_s": extra["sparse"]["elements_assembled_per_s"]})
         line = {"metric": "fp64_elements_assembled_per_s", "value": value, "unit": "elements/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": asm_ms,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                "data": "synthetic",
+                "data": "synthetic", "krylov": krylov,
+                "parity": parity,
                 "config": {"workload": args.workload, "elements": numel_total, "nodes_per_gpu": part.nshg,
                            "elements_per_gpu": part.numel, "quadrature": "rule 2 (4-pt tets, 6-pt wedges, 8-pt hexes)", "lhs": 1, "idiff": 1,
                            "l2": "inputs larger than L2 (EGmass %.1f GB per GPU)" % (part.numel * 3200 / 1e9),
-                           "partition": "x-slabs, ilwork halo over NCCL" if world > 1 else "single part"},
-                "residual_only": {"value": numel_total / (res_ms * 1e-3), "unit": "elements/s", "ms": res_ms},
+                           "partition": "x-slabs, ilwork halo over NCCL" if world > 1 else "single part",
+                           "numa": numa},
+                "residual_only": {"value": numel_total / (core["res_ms"] * 1e-3), "unit": "elements/s", "ms": core["res_ms"]},
                 "roofline": roof, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "kernel_class_ms": {k: v[0] / 2 for k, v in prof.items()}}
         line.update(extra)
+        if side is not None:
+            line["side_workload"] = side
         emit(line)
-    g.close()
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None:
+        ok = parity["ok"] if rank == 0 else True
+        if side and isinstance(side.get("parity"), dict):
+            ok = ok and side["parity"].get("ok", False)
+        if not ok:
+            print("bench.py: PARITY FAILED: %s" % json.dumps(parity)[:600], file=sys.stderr)
+            return 1
     return 0
 
 

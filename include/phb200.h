@@ -214,6 +214,10 @@ int phb200_get_res(phb200_ctx *ctx, double *res);
 int phb200_get_dy(phb200_ctx *ctx, double *Dy);
 int phb200_get_bdiag(phb200_ctx *ctx, double *BDiag);
 int phb200_get_egmass(phb200_ctx *ctx, double *EGmass);
+/* spot reads for meshes whose whole LHS does not fit on the host: EGmass(e0+1:e0+n,:,:) of the reference's element
+ * order as out(n,nedof,nedof), and lhsK(:,k0+1:k0+n) as out(25,n) */
+int phb200_get_egmass_range(phb200_ctx *ctx, long long e0, int n, double *EGmass);
+int phb200_get_lhsk_range(phb200_ctx *ctx, long long k0, long long n, double *lhsK);
 
 /* Timing on the library's own stream (bench.py): record event `slot`
  * (0..15), elapsed ms between two recorded events, full sync, and the number

@@ -235,6 +235,15 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   PHB_TRY(dev_alloc(&ctx->d_uBrg, n5 * (size_t)(c->Kspace + 1)));
   PHB_TRY(dev_alloc(&ctx->d_dots, (size_t)c->Kspace + 8));
   PHB_CHECK(cudaMallocHost(&ctx->h_dots, sizeof(double) * ((size_t)c->Kspace + 8)));
+  PHB_TRY(dev_alloc(&ctx->d_ptmp, n5));
+  {
+    const size_t nk = phb_kry_doubles(c->Kspace), nf = (size_t)c->Kspace + 4;
+    PHB_TRY(dev_alloc(&ctx->d_kry, nk));
+    PHB_CHECK(cudaMallocHost(&ctx->h_kry, sizeof(double) * nk));
+    PHB_TRY(dev_alloc(&ctx->d_kflag, nf));
+    PHB_CHECK(cudaMallocHost(&ctx->h_kflag, sizeof(int) * nf));
+    for (int i = 0; i < 4; i++) PHB_CHECK(cudaEventCreateWithFlags(&ctx->kev[i], cudaEventDisableTiming));
+  }
   ctx->scratch_bytes = (size_t)256 << 20;
   PHB_TRY(dev_alloc((char **)&ctx->d_scratch, ctx->scratch_bytes));
   PHB_CHECK(cudaMemset(ctx->d_qres, 0, sizeof(double) * 12 * (size_t)nshg));
@@ -260,7 +269,7 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
                   ctx->d_rmass, ctx->d_res, ctx->d_rmes, ctx->d_Dy, ctx->d_temp, ctx->d_BDiag, ctx->d_BDtmp,
                   ctx->d_EG, ctx->d_uBrg, ctx->d_dots, ctx->d_scratch, ctx->d_ienb, ctx->d_iBCB,
                   ctx->d_BCB, ctx->d_aerfrc, ctx->d_colm, ctx->d_rowp, ctx->d_rowofblk, ctx->d_eloc, ctx->d_lhsK,
-                  ctx->d_nodeaos, ctx->d_yold, ctx->d_acold, ctx->d_mfg};
+                  ctx->d_nodeaos, ctx->d_yold, ctx->d_acold, ctx->d_mfg, ctx->d_ptmp, ctx->d_kry, ctx->d_kflag, ctx->d_apchunk};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (ctx->d_refel_tet) cudaFree(ctx->d_refel_tet);
@@ -275,6 +284,9 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
       if (p) cudaFree(p);
   }
   if (ctx->h_dots) cudaFreeHost(ctx->h_dots);
+  if (ctx->h_kry) cudaFreeHost(ctx->h_kry);
+  if (ctx->h_kflag) cudaFreeHost(ctx->h_kflag);
+  for (int i = 0; i < 4; i++) cudaEventDestroy(ctx->kev[i]);
   for (int i = 0; i < 16; i++) cudaEventDestroy(ctx->ev[i]);
   cudaEventDestroy(ctx->pev0);
   cudaEventDestroy(ctx->pev1);
@@ -347,8 +359,9 @@ extern "C" int phb200_dev_ap(phb200_ctx *ctx, int slot) {
   if (slot < 0 || slot >= ctx->c.Kspace) return fail("dev_ap", "slot out of range");
   const size_t n5 = (size_t)5 * ctx->c.nshg;
   double *src = ctx->d_uBrg + (size_t)slot * n5, *dst = src + n5;
-  PHB_CHECK(cudaMemcpyAsync(dst, src, sizeof(double) * n5, cudaMemcpyDeviceToDevice, ctx->stream));
-  PHB_TRY(phb_au1gmr(ctx, dst));
+  // as in the Krylov loop: a scratch copy gets the halo / periodic fill, the product lands in the next slot
+  PHB_CHECK(cudaMemcpyAsync(ctx->d_ptmp, src, sizeof(double) * n5, cudaMemcpyDeviceToDevice, ctx->stream));
+  PHB_TRY(phb_au1gmr2(ctx, ctx->d_ptmp, dst, nullptr));
   return phb_bc3per(ctx, dst, 5);
 }
 extern "C" int phb200_get_res(phb200_ctx *ctx, double *res) {
@@ -389,6 +402,49 @@ extern "C" int phb200_get_egmass(phb200_ctx *ctx, double *EGmass) {
     size_t nthr = (size_t)g.numel * nd * nd;
     k_eg_to_ref<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(g.numel, nd, numel, nedof, g.d_refel, g.d_EG,
                                                                          d_out);
+    ctx->launches++;
+  }
+  PHB_CHECK(cudaGetLastError());
+  PHB_TRY(d2h(ctx, EGmass, d_out, tot));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_out);
+  return 0;
+}
+
+// EGmass(e0+1 : e0+n, :, :) of the reference's element order, as out(n,nedof,nedof): spot checks on meshes whose
+// whole EGmass does not fit on the host (bench.py's parity leg, tests/test_gpu_at_size.py)
+__global__ void k_eg_to_ref_range(int ngrp, int nd, int e0, int n, int nedof, const int *__restrict__ refel,
+                                  const double *__restrict__ EG, double *__restrict__ out) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)ngrp * nd) return;
+  const size_t e = t % ngrp;
+  const int c = (int)(t / ngrp), pos = refel[e] - e0;
+  if (pos < 0 || pos >= n) return;
+  for (int r = 0; r < nd; r++)
+    out[pos + (size_t)n * (r + (size_t)nedof * c)] =
+        EG[((e / EG_TILE) * (size_t)(nd * nd) + (size_t)(r + nd * c)) * EG_TILE + (e % EG_TILE)];
+}
+extern "C" int phb200_get_egmass_range(phb200_ctx *ctx, long long e0, int n, double *EGmass) {
+  ENTER(ctx);
+  const int numel = ctx->c.numel, nedof = ctx->c.nedof;
+  if (!EGmass || e0 < 0 || n < 0 || e0 + n > numel) return fail("get_egmass_range", "range outside 0..numel");
+  if (n == 0) return 0;
+  if (!ctx->have_lhs) return fail("get_egmass_range", "no EBE LHS has been assembled");
+  double *d_out = nullptr;
+  const size_t tot = (size_t)n * nedof * nedof;
+  PHB_CHECK(cudaMalloc(&d_out, sizeof(double) * tot));
+  PHB_CHECK(cudaMemsetAsync(d_out, 0, sizeof(double) * tot, ctx->stream));
+  if (ctx->numel_tet > 0) {
+    const size_t nthr = (size_t)ctx->numel_tet * 20;
+    k_eg_to_ref_range<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(ctx->numel_tet, 20, (int)e0, n, nedof,
+                                                                               ctx->d_refel_tet, ctx->d_EG, d_out);
+    ctx->launches++;
+  }
+  for (const ElemGroup &g : ctx->gen) {
+    const int nd = 5 * g.nshl;
+    const size_t nthr = (size_t)g.numel * nd;
+    k_eg_to_ref_range<<<(unsigned)((nthr + 255) / 256), 256, 0, ctx->stream>>>(g.numel, nd, (int)e0, n, nedof, g.d_refel,
+                                                                               g.d_EG, d_out);
     ctx->launches++;
   }
   PHB_CHECK(cudaGetLastError());
@@ -450,6 +506,16 @@ extern "C" int phb200_set_sparse(phb200_ctx *ctx, const int *colm, const int *ro
 }
 static int get_lhsk(phb200_ctx *ctx, double *lhsK) {
   PHB_CHECK(cudaMemcpyAsync(lhsK, ctx->d_lhsK, sizeof(double) * 25 * (size_t)ctx->nnz_tot, cudaMemcpyDeviceToHost,
+                            ctx->stream));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+// lhsK(:, k0+1 : k0+n) (blocks of the CSR structure given to set_sparse), as out(25,n)
+extern "C" int phb200_get_lhsk_range(phb200_ctx *ctx, long long k0, long long n, double *lhsK) {
+  ENTER(ctx);
+  if (!lhsK || k0 < 0 || n < 0 || k0 + n > ctx->nnz_tot) return fail("get_lhsk_range", "range outside 0..nnz_tot");
+  if (!ctx->have_lhs_sparse) return fail("get_lhsk_range", "no sparse LHS has been assembled");
+  PHB_CHECK(cudaMemcpyAsync(lhsK, ctx->d_lhsK + 25 * (size_t)k0, sizeof(double) * 25 * (size_t)n, cudaMemcpyDeviceToHost,
                             ctx->stream));
   PHB_CHECK(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -614,8 +680,8 @@ extern "C" int phb200_dev_sparseap(phb200_ctx *ctx, int slot) {
   if (slot < 0 || slot >= ctx->c.Kspace) return fail("dev_sparseap", "slot out of range");
   const size_t n5 = (size_t)5 * ctx->c.nshg;
   double *src = ctx->d_uBrg + (size_t)slot * n5, *dst = src + n5;
-  PHB_CHECK(cudaMemcpyAsync(dst, src, sizeof(double) * n5, cudaMemcpyDeviceToDevice, ctx->stream));
-  PHB_TRY(phb_sparseap(ctx, dst));
+  PHB_CHECK(cudaMemcpyAsync(ctx->d_ptmp, src, sizeof(double) * n5, cudaMemcpyDeviceToDevice, ctx->stream));
+  PHB_TRY(phb_sparseap2(ctx, ctx->d_ptmp, dst, nullptr));
   return phb_bc3per(ctx, dst, 5);
 }
 

@@ -118,7 +118,7 @@ struct LocalGroup {
   int n = 0;
   TimedBarrier bar;
   phb200_ctx *members[64] = {};
-  double red[64][8] = {};
+  double red[64][PHB_MAILW] = {};
 };
 static LocalGroup g_local;
 static std::mutex g_local_mu;
@@ -327,13 +327,13 @@ int phb_allreduce_sum(phb200_ctx *ctx, double *d_vals, int n) {
     return 0;
   }
   if (ctx->local_group) {
-    if (n < 1 || n > 8) return 1;
-    double v[8];
+    if (n < 1 || n > PHB_MAILW) return 1;
+    double v[PHB_MAILW];
     int err = cudaMemcpyAsync(v, d_vals, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess;
     err |= cudaStreamSynchronize(ctx->stream) != cudaSuccess;
     for (int k = 0; k < n; k++) g_local.red[ctx->c.myrank][k] = v[k];
     if (g_local.bar.wait(err)) return 1;
-    double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double s[PHB_MAILW] = {};
     for (int r = 0; r < g_local.n; r++)
       for (int k = 0; k < n; k++) s[k] += g_local.red[r][k];
     if (g_local.bar.wait(0)) return 1;

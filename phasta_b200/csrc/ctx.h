@@ -56,6 +56,29 @@ struct BndGroup {
 };
 
 
+// Krylov scalars resident on the device (solver.cu): offsets, in doubles, into d_kry / h_kry.
+// HBrg(Kspace+1,Kspace), eBrg, yBrg, Rcos, Rsin as in solgmr.f:46-49; hcol = the Gram-Schmidt coefficients of the
+// column being built; scale = H(iKs+1,iKs) of the newest basis vector (it is normalised when the next iteration
+// reads it); red = one slot of PHB_MAILW reduction results per Gram-Schmidt pass of the current iteration.
+struct KryLayout {
+  int K, npass;
+  size_t H, e, y, rc, rs, hcol, scale, epsnrm, red, total;
+  __host__ __device__ explicit KryLayout(int K_) : K(K_) {
+    npass = K / 4 + 3;
+    H = 0;
+    e = H + (size_t)(K + 1) * K;
+    y = e + K + 1;
+    rc = y + K + 1;
+    rs = rc + K + 1;
+    hcol = rs + K + 1;
+    scale = hcol + K + 2;
+    epsnrm = scale + 1;
+    red = epsnrm + 1;
+    total = red + (size_t)npass * PHB_MAILW;
+  }
+};
+static inline size_t phb_kry_doubles(int K) { return KryLayout(K).total; }
+
 struct phb200_ctx {
   phb200_common c;
   int device;
@@ -122,10 +145,17 @@ struct phb200_ctx {
   int *d_rowofblk;               // row of every block
   int *d_eloc;                   // [16][numel_pad] CSR block of element block (a,b)
   double *d_lhsK;                // [nnz_tot][25]  lhsK(25,nnz_tot)
+  int *d_apchunk, n_apchunk;     // row chunks of SparseAp (first row of each, + nshg)
   bool have_lhs_sparse;
   double *d_uBrg;                // [Kspace+1][5][nshg]
   double *d_dots;                // device scalars for fused MGS
   double *h_dots;                // pinned
+  // Krylov loop without the host in it (solver.cu): the Ap input with slaves filled, the Hessenberg / Givens state
+  // and the per-iteration status words on the device, pinned mirrors, one event per in-flight iteration
+  double *d_ptmp;                // [5][nshg]
+  double *d_kry, *h_kry;         // layout: KryLayout (solver.cu)
+  int *d_kflag, *h_kflag;        // [0] done, [1] iKs at convergence, [2 + iK] status of iteration iK (1 run, 2 converged)
+  cudaEvent_t kev[4];
   double *d_scratch;             // L2 flush / fp64 peak
   size_t scratch_bytes;
   bool have_lhs;                 // EGmass/BDiag hold a (preconditioned) system
@@ -191,6 +221,7 @@ int phb_pack_nodes(phb200_ctx *ctx, int with_q);
 int phb_i3lu(phb200_ctx *ctx, double *d_Diag, double *d_r, int code);
 int phb_i3pre(phb200_ctx *ctx);
 int phb_au1gmr(phb200_ctx *ctx, double *d_u);
+int phb_au1gmr2(phb200_ctx *ctx, double *d_p, double *d_out, const int *d_skip);  // d_p is modified (halo, periodic slaves)
 int phb_bc3per(phb200_ctx *ctx, double *d_r, int n);
 int phb_zero_slaves(phb200_ctx *ctx, double *d_r, int n, int identity);
 int phb_sumgat_dev(phb200_ctx *ctx, const double *d_u, size_t len, double *out);
@@ -222,6 +253,7 @@ int phb_genadj_host(int nshg, int nelblk, const int *lcblk, const int *const *mi
 int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_tot);
 int phb_spsi3pre(phb200_ctx *ctx);
 int phb_sparseap(phb200_ctx *ctx, double *d_u);
+int phb_sparseap2(phb200_ctx *ctx, double *d_p, double *d_out, const int *d_skip);
 // comm.cu
 int phb_halo_setup(phb200_ctx *ctx, const int *ilwork);
 int phb_commu(phb200_ctx *ctx, double *d_global, int n, int code);

@@ -7,7 +7,7 @@
 #include <vector>
 
 #define PHB_MAXR 16   // ranks a mailbox has room for
-#define PHB_MAILW 8   // doubles per all-reduce
+#define PHB_MAILW 12  // doubles per all-reduce (one blocked Gram-Schmidt pass: 4 dots + 6 Gram entries + 1 norm)
 
 struct HaloTask {
   int peer, iacc, tag, count;  // count = number of nodes (all segments)

@@ -6,6 +6,7 @@
 // i3pre.f:27-133, au1gmr.f:29-101, asaugmr.f:26-74, bc3per.f:28-34,
 // common/mpitools.f:107-137 (sumgat).
 #include "ctx.h"
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 
@@ -195,10 +196,11 @@ __global__ void k_iper_copy(int n, const int *__restrict__ slaves, const int *__
 template <int NSHL>
 __global__ void __launch_bounds__(128) k_ap_ebe_gen(int numel, size_t numel_pad, int nshg,
                                                      const int *__restrict__ ien, const double *__restrict__ EG,
-                                                     const double *__restrict__ u, double *__restrict__ out) {
+                                                     const double *__restrict__ u, double *__restrict__ out,
+                                                     const int *__restrict__ skip) {
   constexpr int ND = 5 * NSHL;
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= numel) return;
+  if (e >= numel || (skip && *skip)) return;
   int nd[NSHL];
   double p[ND], q[ND];
 #pragma unroll
@@ -225,9 +227,10 @@ __global__ void __launch_bounds__(128) k_ap_ebe_gen(int numel, size_t numel_pad,
 
 __global__ void __launch_bounds__(128) k_ap_ebe_tet(int numel, size_t numel_pad, int nshg,
                                                      const int *__restrict__ ien, const double *__restrict__ EG,
-                                                     const double *__restrict__ u, double *__restrict__ out) {
+                                                     const double *__restrict__ u, double *__restrict__ out,
+                                                     const int *__restrict__ skip) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= numel) return;
+  if (e >= numel || (skip && *skip)) return;  // an iteration queued behind the converged one (phb_solve)
   int nd[4];
   double p[20], q[20];
 #pragma unroll
@@ -271,40 +274,48 @@ int phb_zero_slaves(phb200_ctx *ctx, double *d_r, int n, int identity) {
   return 0;
 }
 
-// u <- A u (in place, like the reference; uses d_temp as uBtmp)
-int phb_au1gmr(phb200_ctx *ctx, double *d_u) {
+// out <- A p (au1gmr.f:29-101).  d_p is the caller's scratch copy of the vector: the halo 'out' exchange and the
+// periodic copy fill its slave entries in place, exactly what the reference does to its uBrg(:,:,iKs+1) copy.
+int phb_au1gmr2(phb200_ctx *ctx, double *d_p, double *d_out, const int *d_skip) {
   const int nshg = ctx->c.nshg;
   cudaStream_t s = ctx->stream;
   if (!ctx->have_lhs) {
     fprintf(stderr, "phb200: au1gmr: no LHS has been assembled (lhs=1 call needed first)\n");
     return 1;
   }
-  PHB_TRY(phb_commu(ctx, d_u, 5, 1));
+  PHB_TRY(phb_commu(ctx, d_p, 5, 1));
   if (ctx->n_perslave) {
     KScope ks(ctx, KC_NODE);
     int tot = ctx->n_perslave * 5;
-    k_iper_copy<<<(tot + 255) / 256, 256, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, d_u);
+    k_iper_copy<<<(tot + 255) / 256, 256, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, d_p);
     PHB_CHECK(cudaGetLastError());
   }
-  PHB_CHECK(cudaMemsetAsync(ctx->d_temp, 0, sizeof(double) * 5 * (size_t)nshg, s));
+  PHB_CHECK(cudaMemsetAsync(d_out, 0, sizeof(double) * 5 * (size_t)nshg, s));
   if (ctx->numel_tet > 0) {
     KScope ks(ctx, KC_AP);
     k_ap_ebe_tet<<<(ctx->numel_tet + 127) / 128, 128, 0, s>>>(ctx->numel_tet, ctx->numel_pad, nshg, ctx->d_ien,
-                                                              ctx->d_EG, d_u, ctx->d_temp);
+                                                              ctx->d_EG, d_p, d_out, d_skip);
     PHB_CHECK(cudaGetLastError());
   }
   for (const ElemGroup &g : ctx->gen) {
     KScope ks(ctx, KC_AP);
     const int nb = (g.numel + 127) / 128;
     if (g.nshl == 8)
-      k_ap_ebe_gen<8><<<nb, 128, 0, s>>>(g.numel, g.numel_pad, nshg, g.d_ien, g.d_EG, d_u, ctx->d_temp);
+      k_ap_ebe_gen<8><<<nb, 128, 0, s>>>(g.numel, g.numel_pad, nshg, g.d_ien, g.d_EG, d_p, d_out, d_skip);
     else
-      k_ap_ebe_gen<6><<<nb, 128, 0, s>>>(g.numel, g.numel_pad, nshg, g.d_ien, g.d_EG, d_u, ctx->d_temp);
+      k_ap_ebe_gen<6><<<nb, 128, 0, s>>>(g.numel, g.numel_pad, nshg, g.d_ien, g.d_EG, d_p, d_out, d_skip);
     PHB_CHECK(cudaGetLastError());
   }
-  PHB_CHECK(cudaMemcpyAsync(d_u, ctx->d_temp, sizeof(double) * 5 * (size_t)nshg, cudaMemcpyDeviceToDevice, s));
-  PHB_TRY(phb_commu(ctx, d_u, 5, 0));
-  PHB_TRY(phb_zero_slaves(ctx, d_u, 5, 0));
+  PHB_TRY(phb_commu(ctx, d_out, 5, 0));
+  PHB_TRY(phb_zero_slaves(ctx, d_out, 5, 0));
+  return 0;
+}
+
+// u <- A u (in place, like the reference; uses d_temp as uBtmp)
+int phb_au1gmr(phb200_ctx *ctx, double *d_u) {
+  PHB_TRY(phb_au1gmr2(ctx, d_u, ctx->d_temp, nullptr));
+  PHB_CHECK(cudaMemcpyAsync(d_u, ctx->d_temp, sizeof(double) * 5 * (size_t)ctx->c.nshg, cudaMemcpyDeviceToDevice,
+                            ctx->stream));
   return 0;
 }
 
@@ -367,6 +378,169 @@ __global__ void __launch_bounds__(RED_BLOCK) k_mgs_step(size_t n, double *__rest
     if (threadIdx.x == 0) *out = sv[0];
   }
 }
+// ---------------------------------------------------------------------------
+// Modified Gram-Schmidt, four basis vectors per pass (solgmr.f:224-256 without its iKs+1 dependent sweeps).
+// One pass: w <- w - sum_k beta_k usub_k for the block of the PREVIOUS pass, then the dot products of the new w with
+// the up to four vectors of THIS block, their Gram entries (u_k,u_l), and optionally (w,w).  The coefficients follow
+// from the reduced values of the previous pass by the recurrence
+//     beta_k = (w,u_k) - sum_{l<k} beta_l (u_l,u_k),
+// which is the modified Gram-Schmidt coefficient (w - sum_{l<k} beta_l u_l, u_k) written out by linearity of the dot
+// product -- the same numbers up to the rounding of the sums, with one read-modify-write of w and ONE reduction
+// (all-reduce across GPUs) per four vectors instead of per vector.  Reduction slot: [0..3] dots, [4..9] Gram
+// (01,02,03,12,13,23), [10] (w,w).
+// ---------------------------------------------------------------------------
+struct MgsVecs {
+  const double *usub[4];
+  const double *udot[4];
+};
+__device__ __forceinline__ void mgs_betas(const double *__restrict__ r, int nsub, double beta[4]) {
+  beta[0] = r[0];
+  beta[1] = r[1] - beta[0] * r[4];
+  beta[2] = r[2] - beta[0] * r[5] - beta[1] * r[7];
+  beta[3] = r[3] - beta[0] * r[6] - beta[1] * r[8] - beta[2] * r[9];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (k >= nsub) beta[k] = 0.0;
+}
+__global__ void __launch_bounds__(RED_BLOCK) k_mgs_pass(size_t n, const double *w_in, double *w_out, int nsub,
+                                                         int ndot, int selfdot, MgsVecs v,
+                                                         const double *__restrict__ red_prev, double *red_out,
+                                                         double *hcol_sub, const int *__restrict__ done, int fuse,
+                                                         PhbP2P p2p, unsigned int *ticket) {
+  __shared__ double sh[11][RED_BLOCK / 32];
+  __shared__ int last;
+  if (done && *done) {
+    // an iteration queued behind the converged one: no vector work, but the peer all-reduce keeps its sequence
+    if (fuse && blockIdx.x == 0 && threadIdx.x < 32) {
+      if (threadIdx.x < 11) sh[threadIdx.x][0] = 0.0;
+      __syncwarp();
+      phb_p2p_allreduce_warp(p2p, &sh[0][0], 1);
+    }
+    return;
+  }
+  double beta[4] = {0, 0, 0, 0};
+  if (nsub > 0) {
+    mgs_betas(red_prev, nsub, beta);
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+      for (int k = 0; k < nsub; k++) hcol_sub[k] = beta[k];
+  }
+  double acc[11];
+#pragma unroll
+  for (int k = 0; k < 11; k++) acc[k] = 0.0;
+  const bool store = (nsub > 0) || (w_out != w_in);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double wi = w_in[i];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      if (k < nsub) wi = wi - beta[k] * v.usub[k][i];
+    if (store) w_out[i] = wi;
+    double u[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      u[k] = (k < ndot) ? v.udot[k][i] : 0.0;
+      acc[k] += wi * u[k];
+    }
+    acc[4] += u[0] * u[1];
+    acc[5] += u[0] * u[2];
+    acc[6] += u[0] * u[3];
+    acc[7] += u[1] * u[2];
+    acc[8] += u[1] * u[3];
+    acc[9] += u[2] * u[3];
+    if (selfdot) acc[10] += wi * wi;
+  }
+  const int wrp = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 11; k++) {
+    double x = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (l == 0) sh[k][wrp] = x;
+  }
+  __syncthreads();
+  if (threadIdx.x < 11) {
+    double x = 0.0;
+#pragma unroll
+    for (int j = 0; j < RED_BLOCK / 32; j++) x += sh[threadIdx.x][j];
+    atomicAdd(red_out + threadIdx.x, x);
+  }
+  if (!fuse) return;
+  if (threadIdx.x < 11) __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (last && threadIdx.x < 32) {
+    double *sv = &sh[0][0];
+    if (threadIdx.x < 11) sv[threadIdx.x] = atomicAdd(red_out + threadIdx.x, 0.0);  // the complete local sums
+    if (threadIdx.x == 0) *ticket = 0u;
+    __syncwarp();
+    phb_p2p_allreduce_warp(p2p, sv, 11);
+    if (threadIdx.x < 11) red_out[threadIdx.x] = sv[threadIdx.x];
+  }
+}
+
+// Start of a Krylov iteration: the newest basis vector is normalised in place (solgmr.f:251-256, deferred from the
+// end of the previous iteration so that it costs no pass of its own) and copied to the scratch vector Ap works on.
+__global__ void k_scale_copy(size_t n, double *u, double *copy, const double *__restrict__ scale,
+                             const int *__restrict__ done) {
+  if (done && *done) return;
+  const double f = *scale;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const double x = u[i] / f;
+    u[i] = x;
+    copy[i] = x;
+  }
+}
+
+// Hessenberg column, Givens rotations and the convergence test of one iteration (solgmr.f:258-300), one thread.
+// flags: [0] done, [1] iKs at convergence, [2 + iK] status of iteration iK (1 = ran, 2 = converged here)
+__global__ void k_givens(KryLayout L, double *kry, const double *__restrict__ red_last, int iKs, int minIters,
+                         int *flags) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (flags[0]) {
+    flags[2 + iKs] = 3;  // queued behind the converged iteration
+    return;
+  }
+  const int K = L.K;
+  double *H = kry + L.H, *e = kry + L.e, *rc = kry + L.rc, *rs = kry + L.rs;
+  const double *hcol = kry + L.hcol;
+#define HH(a, b) H[((a)-1) + (size_t)(K + 1) * ((b)-1)]
+  for (int j = 1; j <= iKs; j++) HH(j, iKs) = hcol[j - 1];
+  const double unorm = sqrt(red_last[10]);
+  HH(iKs + 1, iKs) = unorm;
+  kry[L.scale] = unorm;
+  for (int j = 1; j <= iKs - 1; j++) {
+    const double tmp = rc[j - 1] * HH(j, iKs) + rs[j - 1] * HH(j + 1, iKs);
+    HH(j + 1, iKs) = -rs[j - 1] * HH(j, iKs) + rc[j - 1] * HH(j + 1, iKs);
+    HH(j, iKs) = tmp;
+  }
+  double tmp = sqrt(HH(iKs, iKs) * HH(iKs, iKs) + HH(iKs + 1, iKs) * HH(iKs + 1, iKs));
+  rc[iKs - 1] = HH(iKs, iKs) / tmp;
+  rs[iKs - 1] = HH(iKs + 1, iKs) / tmp;
+  HH(iKs, iKs) = tmp;
+  HH(iKs + 1, iKs) = 0.0;
+  tmp = rc[iKs - 1] * e[iKs - 1] + rs[iKs - 1] * e[iKs];
+  e[iKs] = -rs[iKs - 1] * e[iKs - 1] + rc[iKs - 1] * e[iKs];
+  e[iKs - 1] = tmp;
+  if (fabs(e[iKs]) <= kry[L.epsnrm] && iKs >= minIters) {
+    flags[0] = 1;
+    flags[1] = iKs;
+    flags[2 + iKs] = 2;
+  } else {
+    flags[2 + iKs] = 1;
+  }
+#undef HH
+}
+// yBrg by back substitution (solgmr.f:303-311); e is consumed like the reference's eBrg
+__global__ void k_backsolve(KryLayout L, double *kry, int iKs) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int K = L.K;
+  double *H = kry + L.H, *e = kry + L.e, *y = kry + L.y;
+  for (int j = iKs; j >= 1; j--) {
+    y[j - 1] = e[j - 1] / H[(j - 1) + (size_t)(K + 1) * (j - 1)];
+    for (int l = 1; l <= j - 1; l++) e[l - 1] = e[l - 1] - y[j - 1] * H[(l - 1) + (size_t)(K + 1) * (j - 1)];
+  }
+}
+
 // v <- v / sqrt(*nrm2) (solgmr.f:251-256) or v <- v * alpha
 __global__ void k_scale_dev(size_t n, double *v, const double *nrm2) {
   const double f = sqrt(*nrm2);
@@ -448,6 +622,13 @@ static int dot_host(phb200_ctx *ctx, size_t n, double *a, const double *b, doubl
 // sparse=1: SolGMRs (solgmr.f:440-744): commu(BDiag,'out') after LU_Fact (:473-475), Spsi3pre only when
 // lhs=1 (:495), SparseAp, convergence also needs iKs >= minIters (:669), and the restart recomputation is
 // keyed on the stale EBE counter so it never runs (:526).
+//
+// The Krylov loop keeps the host out of the data path: Hessenberg column, Givens rotations, the convergence test
+// and the back substitution run on the device (k_givens, k_backsolve); the host only enqueues.  It learns the
+// status of iteration iK-2 (one 4-byte copy behind an event) right before it enqueues iteration iK, so the queue
+// stays two iterations deep and EVERY rank enqueues the same number of iterations (the status derives from
+// all-reduced values); the kernels of the at most two iterations queued behind the converged one return at once
+// on the device-side flag.  The matrix-free flavour (whose Ap is a whole residual evaluation) uses a lag of one.
 int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, int *lGMRES_out, int *ntotGM) {
   const phb200_common &c = ctx->c;
   const int nshg = c.nshg, Kspace = c.Kspace, nGMRES = c.nGMRES;
@@ -455,16 +636,15 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, 
   cudaStream_t s = ctx->stream;
   double *U = ctx->d_uBrg;
   auto Uk = [&](int k) { return U + (size_t)(k - 1) * n; };  // 1-based slot
-  double *HBrg = ctx->HBrg.data(), *eBrg = ctx->eBrg.data(), *yBrg = ctx->yBrg.data(), *Rcos = ctx->Rcos.data(),
-         *Rsin = ctx->Rsin.data();
-#define H(a, b) HBrg[((a)-1) + (size_t)(Kspace + 1) * ((b)-1)]
+  const KryLayout L(Kspace);
+  double *kry = ctx->d_kry;
+  int *flags = ctx->d_kflag, *hflags = ctx->h_kflag;
   // sparse==2: SolMFG (solmfg.f:86-375) after ElmMFG: rmes is the modified residual (forward-reduced like res,
   // :106-107), Ap = Au1MFG without bc3per, restarts through Au2MFG, itrFDI sets the interval (mfg.cu)
   const bool mfg = (sparse == 2);
   if (mfg) sparse = 0;
   // rmes = res (solgmr.f:83)
   if (!mfg) PHB_CHECK(cudaMemcpyAsync(ctx->d_rmes, ctx->d_res, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-  auto Ap = [&](double *v) { return mfg ? phb_au1mfg(ctx, v) : (sparse ? phb_sparseap(ctx, v) : phb_au1gmr(ctx, v)); };
   const int minIters = (sparse || mfg) ? c.minIters : 0;
   if (st->iprec != 0) {
     PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, nullptr, 0));
@@ -487,10 +667,13 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, 
   double unorm = sqrt(summed);
   int iKs = 0, lGMRES = 0;
   std::fill(ctx->HBrg.begin(), ctx->HBrg.end(), 0.0);
+  const int lag = mfg ? 1 : 2;
   if (!(unorm < 100.0 * c.epsM * c.epsM)) {
     const double epsnrm = st->etol * unorm;
     if (mfg && st->iter == 1 && (st->istep % 20) == 0) PHB_TRY(phb_itrfdi(ctx));  // solmfg.f:150-157
-    for (int mGMRES = 1; mGMRES <= nGMRES; mGMRES++) {
+    PHB_CHECK(cudaMemsetAsync(kry, 0, sizeof(double) * L.total, s));  // HBrg = 0 (solgmr.f:120)
+    bool converged = false;
+    for (int mGMRES = 1; mGMRES <= nGMRES && !converged; mGMRES++) {
       lGMRES = mGMRES - 1;
       if (lGMRES > 0 && mfg) {  // solmfg.f:167-180
         PHB_TRY(phb_au2mfg(ctx, Uk(1)));
@@ -499,7 +682,7 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, 
       } else if (lGMRES > 0 && !sparse) {  // restart: R - A x (solgmr.f:149-178)
         double *tmp = Uk(Kspace + 1);  // free slot at restart time
         PHB_CHECK(cudaMemcpyAsync(tmp, ctx->d_Dy, sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-        PHB_TRY(Ap(tmp));
+        PHB_TRY(phb_au1gmr(ctx, tmp));
         PHB_TRY(phb_bc3per(ctx, tmp, 5));
         {
           KScope ks(ctx, KC_BLAS);
@@ -509,75 +692,112 @@ int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs_out, 
         PHB_TRY(dot_host(ctx, n, Uk(1), Uk(1), &summed));
         unorm = sqrt(summed);
       }
-      for (int k = 0; k < Kspace + 1; k++) eBrg[k] = 0.0;
-      eBrg[0] = unorm;
+      // eBrg = (unorm, 0, ...), scale of u_1 = unorm, flags cleared (solgmr.f:186-196)
       {
-        KScope ks(ctx, KC_BLAS);
-        k_scale<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, Uk(1), unorm);
-        PHB_CHECK(cudaGetLastError());
+        double *hk = ctx->h_kry;
+        for (int k = 0; k < Kspace + 1; k++) hk[k] = 0.0;
+        hk[0] = unorm;
+        PHB_CHECK(cudaMemcpyAsync(kry + L.e, hk, sizeof(double) * (Kspace + 1), cudaMemcpyHostToDevice, s));
+        hk[Kspace + 1] = unorm;
+        hk[Kspace + 2] = epsnrm;
+        PHB_CHECK(cudaMemcpyAsync(kry + L.scale, hk + Kspace + 1, sizeof(double) * 2, cudaMemcpyHostToDevice, s));
+        PHB_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)Kspace + 4), s));
+        for (int k = 0; k < Kspace + 4; k++) hflags[k] = 0;
+        // h_kry is reused below only after the final synchronisation of this cycle
       }
+      int enq = 0;
       for (int iK = 1; iK <= Kspace; iK++) {
-        iKs = iK;
-        double *w = Uk(iKs + 1);
-        PHB_CHECK(cudaMemcpyAsync(w, Uk(iKs), sizeof(double) * n, cudaMemcpyDeviceToDevice, s));
-        PHB_TRY(Ap(w));
-        if (!mfg) PHB_TRY(phb_bc3per(ctx, w, 5));
-        // modified Gram-Schmidt, beta_j stay on the device (d_dots[j]) unless
-        // an allreduce is needed between steps
-        PHB_CHECK(cudaMemsetAsync(ctx->d_dots, 0, sizeof(double) * (iKs + 2), s));
-        for (int jK = 1; jK <= iKs + 1; jK++) {
+        if (iK > lag) {
+          PHB_CHECK(cudaEventSynchronize(ctx->kev[(iK - lag) & 3]));
+          if (hflags[2 + iK - lag] == 2) break;
+        }
+        enq = iK;
+        double *w = Uk(iK + 1);
+        // the vector Ap works on: u_iK normalised (in place) and copied; EBE / CSR products read the copy and write
+        // d_temp, the matrix-free product works in place on the new slot
+        double *p = mfg ? w : ctx->d_ptmp;
+        {
+          KScope ks(ctx, KC_BLAS);
+          k_scale_copy<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, Uk(iK), p, kry + L.scale, flags);
+          PHB_CHECK(cudaGetLastError());
+        }
+        const double *w_in = w;
+        if (mfg) {
+          PHB_TRY(phb_au1mfg(ctx, w));
+        } else {
+          PHB_TRY(sparse ? phb_sparseap2(ctx, p, ctx->d_temp, flags) : phb_au1gmr2(ctx, p, ctx->d_temp, flags));
+          PHB_TRY(phb_bc3per(ctx, ctx->d_temp, 5));
+          w_in = ctx->d_temp;  // the first Gram-Schmidt pass moves it into the slot
+        }
+        // modified Gram-Schmidt against u_1..u_iK, four vectors per pass, then (w,w)
+        const int nblk = (iK + 3) / 4;
+        PHB_CHECK(cudaMemsetAsync(kry + L.red, 0, sizeof(double) * (size_t)(nblk + 1) * PHB_MAILW, s));
+        for (int pass = 0; pass <= nblk; pass++) {
+          MgsVecs v;
+          int nsub = 0, ndot = 0;
+          for (int k = 0; k < 4; k++) v.usub[k] = v.udot[k] = Uk(1);
+          if (pass > 0) {
+            nsub = std::min(4, iK - 4 * (pass - 1));
+            for (int k = 0; k < nsub; k++) v.usub[k] = Uk(4 * (pass - 1) + k + 1);
+          }
+          if (pass < nblk) {
+            ndot = std::min(4, iK - 4 * pass);
+            for (int k = 0; k < ndot; k++) v.udot[k] = Uk(4 * pass + k + 1);
+          }
+          double *red_out = kry + L.red + (size_t)pass * PHB_MAILW;
           {
             KScope ks(ctx, KC_BLAS);
-            k_mgs_step<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, w, jK == 1 ? nullptr : Uk(jK - 1),
-                                                         ctx->d_dots + (jK - 1), Uk(jK), ctx->d_dots + jK,
+            k_mgs_pass<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, pass == 0 ? w_in : w, w, nsub, ndot, pass == nblk ? 1 : 0, v,
+                                                         pass > 0 ? red_out - PHB_MAILW : red_out, red_out,
+                                                         kry + L.hcol + 4 * (pass > 0 ? pass - 1 : 0), flags,
                                                          fuse ? 1 : 0, fuse ? phb_p2p_next(ctx) : PhbP2P(),
                                                          ctx->d_ticket);
             PHB_CHECK(cudaGetLastError());
           }
-          if (!fuse) PHB_TRY(phb_allreduce_sum(ctx, ctx->d_dots + jK, 1));
+          if (!fuse) PHB_TRY(phb_allreduce_sum(ctx, red_out, 11));
         }
         {
           KScope ks(ctx, KC_BLAS);
-          k_scale_dev<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, w, ctx->d_dots + iKs + 1);
+          k_givens<<<1, 32, 0, s>>>(L, kry, kry + L.red + (size_t)nblk * PHB_MAILW, iK, minIters, flags);
           PHB_CHECK(cudaGetLastError());
         }
-        PHB_CHECK(cudaMemcpyAsync(ctx->h_dots, ctx->d_dots + 1, sizeof(double) * (iKs + 1), cudaMemcpyDeviceToHost, s));
-        PHB_CHECK(cudaStreamSynchronize(s));
-        for (int jK = 1; jK <= iKs + 1; jK++) H(jK, iKs) = ctx->h_dots[jK - 1];
-        unorm = sqrt(ctx->h_dots[iKs]);
-        H(iKs + 1, iKs) = unorm;
-        // Givens (solgmr.f:270-288)
-        for (int jK = 1; jK <= iKs - 1; jK++) {
-          double tmp = Rcos[jK - 1] * H(jK, iKs) + Rsin[jK - 1] * H(jK + 1, iKs);
-          H(jK + 1, iKs) = -Rsin[jK - 1] * H(jK, iKs) + Rcos[jK - 1] * H(jK + 1, iKs);
-          H(jK, iKs) = tmp;
+        PHB_CHECK(cudaMemcpyAsync(hflags + 2 + iK, flags + 2 + iK, sizeof(int), cudaMemcpyDeviceToHost, s));
+        PHB_CHECK(cudaEventRecord(ctx->kev[iK & 3], s));
+      }
+      // the cycle's outcome: the first converged iteration, else all of Kspace (solgmr.f:296-300)
+      PHB_CHECK(cudaStreamSynchronize(s));
+      iKs = enq;
+      for (int iK = 1; iK <= enq; iK++)
+        if (hflags[2 + iK] == 2) {
+          iKs = iK;
+          converged = true;
+          break;
         }
-        double tmp = sqrt(H(iKs, iKs) * H(iKs, iKs) + H(iKs + 1, iKs) * H(iKs + 1, iKs));
-        Rcos[iKs - 1] = H(iKs, iKs) / tmp;
-        Rsin[iKs - 1] = H(iKs + 1, iKs) / tmp;
-        H(iKs, iKs) = tmp;
-        H(iKs + 1, iKs) = 0.0;
-        tmp = Rcos[iKs - 1] * eBrg[iKs - 1] + Rsin[iKs - 1] * eBrg[iKs];
-        eBrg[iKs] = -Rsin[iKs - 1] * eBrg[iKs - 1] + Rcos[iKs - 1] * eBrg[iKs];
-        eBrg[iKs - 1] = tmp;
-        *ntotGM += 1;
-        if (fabs(eBrg[iKs]) <= epsnrm && iKs >= minIters) break;
-      }
-      for (int jK = iKs; jK >= 1; jK--) {
-        yBrg[jK - 1] = eBrg[jK - 1] / H(jK, jK);
-        for (int lK = 1; lK <= jK - 1; lK++) eBrg[lK - 1] = eBrg[lK - 1] - yBrg[jK - 1] * H(lK, jK);
-      }
-      PHB_CHECK(cudaMemcpyAsync(ctx->d_dots, yBrg, sizeof(double) * iKs, cudaMemcpyHostToDevice, s));
+      *ntotGM += iKs;
       {
         KScope ks(ctx, KC_BLAS);
-        k_update<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, ctx->d_Dy, U, iKs, ctx->d_dots);
+        k_backsolve<<<1, 32, 0, s>>>(L, kry, iKs);
+        k_update<<<vec_grid(n), RED_BLOCK, 0, s>>>(n, ctx->d_Dy, U, iKs, kry + L.y);
         PHB_CHECK(cudaGetLastError());
       }
-      PHB_CHECK(cudaStreamSynchronize(s));  // yBrg is reused by the host next cycle
-      if (fabs(eBrg[iKs]) <= epsnrm) break;
+      if (!converged && mGMRES < nGMRES) {
+        // (a cycle that ran out of Kspace: |eBrg(iKs+1)| <= epsnrm below minIters also ends the solve, :326)
+        PHB_CHECK(cudaMemcpyAsync(ctx->h_kry, kry, sizeof(double) * L.total, cudaMemcpyDeviceToHost, s));
+        PHB_CHECK(cudaStreamSynchronize(s));
+        // e was consumed by the back substitution except its last entry
+        if (fabs(ctx->h_kry[L.e + iKs]) <= epsnrm) converged = true;
+      }
     }
+    // Hessenberg work arrays back to the host mirrors (the reference's arguments of the same names)
+    PHB_CHECK(cudaMemcpyAsync(ctx->h_kry, kry, sizeof(double) * L.total, cudaMemcpyDeviceToHost, s));
+    PHB_CHECK(cudaStreamSynchronize(s));
+    const double *hk = ctx->h_kry;
+    std::copy(hk + L.H, hk + L.H + (size_t)(Kspace + 1) * Kspace, ctx->HBrg.begin());
+    std::copy(hk + L.e, hk + L.e + Kspace + 1, ctx->eBrg.begin());
+    std::copy(hk + L.y, hk + L.y + Kspace + 1, ctx->yBrg.begin());
+    std::copy(hk + L.rc, hk + L.rc + Kspace + 1, ctx->Rcos.begin());
+    std::copy(hk + L.rs, hk + L.rs + Kspace + 1, ctx->Rsin.begin());
   }
-#undef H
   PHB_TRY(phb_i3lu(ctx, ctx->d_BDiag, ctx->d_Dy, 2));  // solgmr.f:347
   PHB_TRY(phb_p2p_check(ctx));
   *iKs_out = iKs;

@@ -9,6 +9,12 @@
 #include <algorithm>
 #include <cstring>
 
+// k_sparseap_tma: blocks / rows per staged chunk, stages in flight, consumer warps per CTA
+#define AP_CB 248
+#define AP_CR 64
+#define AP_STAGES 4
+#define AP_WARPS 16
+
 // ---------------------------------------------------------------------------
 // genadj: colm(nshg+1) 1-based row pointers, rowp ascending unique neighbour
 // ids incl. self.  The reference grows per-node lists with an O(deg^2) search
@@ -107,12 +113,32 @@ int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_to
       }
     }
   auto F = [](void *p) { if (p) cudaFree(p); };
-  F(ctx->d_colm); F(ctx->d_rowp); F(ctx->d_rowofblk); F(ctx->d_lhsK); F(ctx->d_eloc);
+  F(ctx->d_colm); F(ctx->d_rowp); F(ctx->d_rowofblk); F(ctx->d_lhsK); F(ctx->d_eloc); F(ctx->d_apchunk);
   ctx->nnz_tot = nnz_tot;
-  PHB_CHECK(cudaMalloc(&ctx->d_colm, sizeof(int) * ((size_t)nshg + 1)));
-  PHB_CHECK(cudaMalloc(&ctx->d_rowp, sizeof(int) * (size_t)std::max(nnz_tot, 1)));
+  // (+8: the bulk copies of k_sparseap_tma start and end on multiples of 4 entries)
+  PHB_CHECK(cudaMalloc(&ctx->d_colm, sizeof(int) * ((size_t)nshg + 1 + 8)));
+  PHB_CHECK(cudaMalloc(&ctx->d_rowp, sizeof(int) * ((size_t)nnz_tot + 8)));
   PHB_CHECK(cudaMalloc(&ctx->d_rowofblk, sizeof(int) * (size_t)std::max(nnz_tot, 1)));
-  PHB_CHECK(cudaMalloc(&ctx->d_lhsK, sizeof(double) * 25 * (size_t)std::max(nnz_tot, 1)));
+  PHB_CHECK(cudaMalloc(&ctx->d_lhsK, sizeof(double) * 25 * ((size_t)nnz_tot + 8)));
+  PHB_CHECK(cudaMemset(ctx->d_colm, 0, sizeof(int) * ((size_t)nshg + 1 + 8)));
+  PHB_CHECK(cudaMemset(ctx->d_rowp, 0, sizeof(int) * ((size_t)nnz_tot + 8)));
+  PHB_CHECK(cudaMemset(ctx->d_lhsK, 0, sizeof(double) * 25 * ((size_t)nnz_tot + 8)));
+  {
+    // row chunks of SparseAp: consecutive rows, at most AP_CB blocks and AP_CR rows each (a longer row is a chunk
+    // of its own and takes the direct-load path)
+    std::vector<int> ch;
+    int r = 0;
+    while (r < nshg) {
+      ch.push_back(r);
+      int e = r + 1;
+      while (e < nshg && e - r < AP_CR && c0[e + 1] - c0[r] <= AP_CB) e++;
+      r = e;
+    }
+    ch.push_back(nshg);
+    ctx->n_apchunk = (int)ch.size() - 1;
+    PHB_CHECK(cudaMalloc(&ctx->d_apchunk, sizeof(int) * ch.size()));
+    PHB_CHECK(cudaMemcpy(ctx->d_apchunk, ch.data(), sizeof(int) * ch.size(), cudaMemcpyHostToDevice));
+  }
   PHB_CHECK(cudaMalloc(&ctx->d_eloc, sizeof(int) * 16 * ctx->numel_pad));
   PHB_CHECK(cudaMemcpy(ctx->d_colm, c0.data(), sizeof(int) * c0.size(), cudaMemcpyHostToDevice));
   PHB_CHECK(cudaMemcpy(ctx->d_rowp, r0.data(), sizeof(int) * r0.size(), cudaMemcpyHostToDevice));
@@ -208,10 +234,11 @@ int phb_spsi3pre(phb200_ctx *ctx) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_sparseap(int nshg, const int *__restrict__ colm,
                                                    const int *__restrict__ rowp, const double *__restrict__ lhsK,
-                                                   const double *__restrict__ p, double *__restrict__ q) {
+                                                   const double *__restrict__ p, double *__restrict__ q,
+                                                   const int *__restrict__ skip) {
   const int lane = threadIdx.x & 31;
   const int row = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  if (row >= nshg) return;
+  if (row >= nshg || (skip && *skip)) return;
   const bool act = lane < 25;
   const int l = act ? lane : 0;
   const int g = l / 5;
@@ -248,6 +275,151 @@ __global__ void __launch_bounds__(256) k_sparseap(int nshg, const int *__restric
   if (lane < 5) q[(size_t)nshg * lane + row] = acc;
 }
 
+#if !defined(PHB_HOST_EMUL) && !defined(PHB_HOST_FULL)
+// ---------------------------------------------------------------------------
+// SparseAp with the matrix streamed through shared memory by the bulk-copy engine (cp.async.bulk + mbarrier).
+// The blocks of a run of consecutive rows are ONE contiguous piece of lhsK (and of rowp, colm), so a producer
+// warp keeps AP_STAGES such pieces (<= 51 KB each) in flight per SM with no registers tied up, and the 16 consumer
+// warps only ever wait on L2-resident gathers of p.  Rows are handed out dynamically inside a stage and a warp that
+// finds its stage empty moves on to the next one, so there is no tail at chunk boundaries.
+// Copies start / end on multiples of 4 CSR entries (16-byte rule of the bulk copy; the arrays are padded).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  // bounded: a protocol error becomes a launch failure (reported by the next CUDA call), not a hung GPU
+  for (long long spins = 0;; spins++) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spins > (1ll << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+struct ApStage {
+  double a[25 * (AP_CB + 8)];
+  int col[AP_CB + 8];
+  int rowptr[AP_CR + 8];
+};
+struct ApSmem {
+  ApStage st[AP_STAGES];
+  unsigned long long full[AP_STAGES], empty[AP_STAGES];
+  int next_row[AP_STAGES];
+};
+
+__global__ void __launch_bounds__(32 * (AP_WARPS + 1), 1)
+    k_sparseap_tma(int nshg, int nchunk, const int *__restrict__ chunk, const int *__restrict__ colm,
+                   const int *__restrict__ rowp, const double *__restrict__ lhsK, const double *__restrict__ p,
+                   double *__restrict__ q, const int *__restrict__ skip) {
+  extern __shared__ __align__(128) unsigned char ap_smem_raw[];
+  ApSmem &S = *reinterpret_cast<ApSmem *>(ap_smem_raw);
+  if (skip && *skip) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < AP_STAGES; i++) {
+      mbar_init(&S.full[i], 1);
+      mbar_init(&S.empty[i], AP_WARPS);
+      S.next_row[i] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == AP_WARPS) {
+    // ------------------------------------------------------------ producer (one lane)
+    if (lane == 0) {
+      int it = 0;
+      for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
+        const int stg = it % AP_STAGES;
+        if (it >= AP_STAGES) mbar_wait(&S.empty[stg], ((it / AP_STAGES) - 1) & 1);
+        const int r0 = chunk[c], r1 = chunk[c + 1];
+        const int k0 = colm[r0], k1 = colm[r1];
+        S.next_row[stg] = 0;
+        if (k1 - k0 > AP_CB) {  // a single very long row: consumers load it directly
+          mbar_arrive(&S.full[stg]);
+          continue;
+        }
+        const int ka = k0 & ~3, kb = (k1 + 3) & ~3, ra = r0 & ~3, rb = (r1 + 1 + 3) & ~3;
+        const unsigned ba = (unsigned)(kb - ka) * 200u, bc = (unsigned)(kb - ka) * 4u, br = (unsigned)(rb - ra) * 4u;
+        mbar_expect_tx(&S.full[stg], ba + bc + br);
+        bulk_g2s(S.st[stg].a, lhsK + (size_t)25 * ka, ba, &S.full[stg]);
+        bulk_g2s(S.st[stg].col, rowp + ka, bc, &S.full[stg]);
+        bulk_g2s(S.st[stg].rowptr, colm + ra, br, &S.full[stg]);
+      }
+    }
+    return;
+  }
+  // -------------------------------------------------------------- consumers
+  const bool act = lane < 25;
+  const int l = act ? lane : 0;
+  const double *__restrict__ pg = p + (size_t)nshg * (l / 5);
+  int it = 0;
+  for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
+    const int stg = it % AP_STAGES;
+    const ApStage &T = S.st[stg];
+    mbar_wait(&S.full[stg], (it / AP_STAGES) & 1);
+    const int r0 = chunk[c], r1 = chunk[c + 1];
+    const int ra = r0 & ~3;
+    for (;;) {
+      int r = 0;
+      if (lane == 0) r = atomicAdd(&S.next_row[stg], 1);
+      r = __shfl_sync(0xffffffffu, r, 0) + r0;
+      if (r >= r1) break;
+      double acc0 = 0.0, acc1 = 0.0;
+      if (r1 - r0 == 1 && colm[r1] - colm[r0] > AP_CB) {
+        // direct path for a row that does not fit a stage
+        const int k0 = colm[r], k1 = colm[r + 1];
+        for (int k = k0; k < k1; k++) acc0 += __ldcs(lhsK + (size_t)25 * k + l) * __ldg(pg + __ldg(rowp + k));
+      } else {
+        const int k0 = T.rowptr[r - ra], k1 = T.rowptr[r - ra + 1];
+        const int ka = T.rowptr[r0 - ra] & ~3;
+        const double *a = T.a + 25 * (k0 - ka) + l;
+        const int *cj = T.col + (k0 - ka);
+        for (int k = k0; k < k1; k += 8, a += 200, cj += 8) {
+          double pv[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) pv[i] = __ldg(pg + ((k + i < k1) ? cj[i] : r));
+#pragma unroll
+          for (int i = 0; i < 8; i += 2) {
+            acc0 += ((k + i < k1) ? a[25 * i] : 0.0) * pv[i];
+            acc1 += ((k + i + 1 < k1) ? a[25 * (i + 1)] : 0.0) * pv[i + 1];
+          }
+        }
+      }
+      double acc = act ? acc0 + acc1 : 0.0;
+      const double t20 = __shfl_down_sync(0xffffffffu, acc, 20);
+      acc += __shfl_down_sync(0xffffffffu, acc, 10);
+      acc += __shfl_down_sync(0xffffffffu, acc, 5);
+      acc += t20;
+      if (lane < 5) q[(size_t)nshg * lane + r] = acc;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&S.empty[stg]);
+  }
+}
+#endif
+
 __global__ void k_iper_copy5(int n, const int *__restrict__ slaves, const int *__restrict__ iper, int nshg,
                              double *u) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -256,30 +428,50 @@ __global__ void k_iper_copy5(int n, const int *__restrict__ slaves, const int *_
   u[(size_t)nshg * k + j] = u[(size_t)nshg * k + iper[j]];
 }
 
-// p <- A p in place (uses d_temp as q)
-int phb_sparseap(phb200_ctx *ctx, double *d_u) {
+// out <- A p (sparseap.f:26-135); d_p is the caller's scratch copy (halo 'out' + periodic copy fill its slaves)
+int phb_sparseap2(phb200_ctx *ctx, double *d_p, double *d_out, const int *d_skip) {
   const int nshg = ctx->c.nshg;
   cudaStream_t s = ctx->stream;
   if (!ctx->have_lhs_sparse) {
     fprintf(stderr, "phb200: sparseap: no sparse LHS has been assembled (elmgmrs with lhs=1 first)\n");
     return 1;
   }
-  PHB_TRY(phb_commu(ctx, d_u, 5, 1));
+  PHB_TRY(phb_commu(ctx, d_p, 5, 1));
   if (ctx->n_perslave) {
     KScope ks(ctx, KC_NODE);
     int tot = ctx->n_perslave * 5;
-    k_iper_copy5<<<(tot + 255) / 256, 256, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, d_u);
+    k_iper_copy5<<<(tot + 255) / 256, 256, 0, s>>>(ctx->n_perslave, ctx->d_perslave, ctx->d_iper, nshg, d_p);
     PHB_CHECK(cudaGetLastError());
   }
   {
     KScope ks(ctx, KC_AP);
+#if !defined(PHB_HOST_EMUL) && !defined(PHB_HOST_FULL)
+    static bool attr_set = false;
+    if (!attr_set) {
+      PHB_CHECK(cudaFuncSetAttribute(k_sparseap_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ApSmem)));
+      attr_set = true;
+    }
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+    const int grid = std::min(ctx->n_apchunk, nsm);
+    k_sparseap_tma<<<grid, 32 * (AP_WARPS + 1), sizeof(ApSmem), s>>>(nshg, ctx->n_apchunk, ctx->d_apchunk, ctx->d_colm,
+                                                                     ctx->d_rowp, ctx->d_lhsK, d_p, d_out, d_skip);
+#else
     size_t threads = (size_t)nshg * 32;
-    k_sparseap<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(nshg, ctx->d_colm, ctx->d_rowp, ctx->d_lhsK, d_u,
-                                                                 ctx->d_temp);
+    k_sparseap<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(nshg, ctx->d_colm, ctx->d_rowp, ctx->d_lhsK, d_p,
+                                                                 d_out, d_skip);
+#endif
     PHB_CHECK(cudaGetLastError());
   }
-  PHB_CHECK(cudaMemcpyAsync(d_u, ctx->d_temp, sizeof(double) * 5 * (size_t)nshg, cudaMemcpyDeviceToDevice, s));
-  PHB_TRY(phb_commu(ctx, d_u, 5, 0));
-  PHB_TRY(phb_zero_slaves(ctx, d_u, 5, 0));
+  PHB_TRY(phb_commu(ctx, d_out, 5, 0));
+  PHB_TRY(phb_zero_slaves(ctx, d_out, 5, 0));
+  return 0;
+}
+
+// p <- A p in place (uses d_temp as q)
+int phb_sparseap(phb200_ctx *ctx, double *d_u) {
+  PHB_TRY(phb_sparseap2(ctx, d_u, ctx->d_temp, nullptr));
+  PHB_CHECK(cudaMemcpyAsync(d_u, ctx->d_temp, sizeof(double) * 5 * (size_t)ctx->c.nshg, cudaMemcpyDeviceToDevice,
+                            ctx->stream));
   return 0;
 }

@@ -434,6 +434,44 @@ def make_box(nx, ny, nz, *, L=(1.0, 0.5, 0.5), nparts=1, ibksiz=64, perturb=0.15
     return parts
 
 
+def extract_slab(part: MeshPart, ia: int, ib: int, plane: int):
+    """The x-slab of hex columns [ia, ib) of a box part as a stand-alone single-rank MeshPart (node planes ia..ib,
+    renumbered from 1; essential BCs, periodicity and coordinates carried over; no boundary elements, no halo).
+    `plane` = nodes per x-plane ((ny+1)(nz+1)).  Returns (sub, node_offset, elems) where elems[i] is the 0-based
+    position, in `part`'s element order, of the slab's element i.  Used to spot-check meshes too large for a full
+    CPU oracle pass: away from its two cut faces the slab sees exactly the elements the whole mesh does."""
+    lo, hi = ia * plane, (ib + 1) * plane          # 0-based node range [lo, hi)
+    assert 0 <= lo < hi <= part.nshg
+    by_topo, order = {}, []
+    for b, ien in enumerate(part.mien):
+        ien = np.asarray(ien)
+        lcsyst = int(part.lcblk[2, b])
+        keep = ((ien.min(axis=1) - 1) >= lo) & ((ien.max(axis=1) - 1) < hi)
+        if lcsyst not in by_topo:
+            by_topo[lcsyst] = ([], [])
+            order.append(lcsyst)
+        by_topo[lcsyst][0].append(ien[keep] - lo)
+        by_topo[lcsyst][1].append(int(part.lcblk[0, b]) - 1 + np.nonzero(keep)[0])
+    name = {v[0]: k for k, v in _TOPO.items()}
+    groups, elems = [], []
+    for lcsyst in order:
+        rows = np.concatenate(by_topo[lcsyst][0], axis=0)
+        if rows.shape[0]:
+            groups.append((name[lcsyst], rows))
+            elems.append(np.concatenate(by_topo[lcsyst][1]))
+    ibksiz = int(max(np.asarray(b).shape[0] for b in part.mien))
+    lcblk, mien = _blocks(groups, ibksiz)
+    nn = hi - lo
+    iper = np.asarray(part.iper[lo:hi]) - lo
+    assert iper.min() >= 1 and iper.max() <= nn, "periodic partners must lie in the same x-plane"
+    sub = MeshPart(rank=0, numpe=1, nshg=nn, numnp=nn, numel=int(sum(g[1].shape[0] for g in groups)),
+                   x=np.asfortranarray(part.x[lo:hi]), lcblk=lcblk, mien=mien,
+                   iBC=np.ascontiguousarray(part.iBC[lo:hi]), BC=np.asfortranarray(part.BC[lo:hi]),
+                   iper=iper.astype(np.int32), ilwork=np.array([0], dtype=np.int32),
+                   gnode=None if part.gnode is None else part.gnode[lo:hi], gelem=None)
+    return sub, lo, np.concatenate(elems)
+
+
 def make_state(part: MeshPart, nglobal_nodes: int, seed=1234):
     """SURVEY 8(d) synthetic state, deterministic in the GLOBAL node id so
     partitioned and serial runs see identical fields.

@@ -446,6 +446,19 @@ class PhastaGPU:
             raise KeyError(what)
         return a
 
+    def get_egmass_range(self, e0, n):
+        """EGmass(e0:e0+n, :, :) (0-based element range of the reference's order) without moving the rest"""
+        a = np.zeros((int(n), self.nedof, self.nedof), order="F")
+        _chk(self.L.phb200_get_egmass_range(self.ctx, C.c_longlong(int(e0)), int(n), _p(a)), "get_egmass_range")
+        return a
+
+    def get_lhsk_range(self, k0, n):
+        """lhsK(:, k0:k0+n) (0-based CSR block range)"""
+        a = np.zeros((25, int(n)), order="F")
+        _chk(self.L.phb200_get_lhsk_range(self.ctx, C.c_longlong(int(k0)), C.c_longlong(int(n)), _p(a)),
+             "get_lhsk_range")
+        return a
+
     # ------------------------------------------------------ instrumentation
     def sync(self):
         _chk(self.L.phb200_sync(self.ctx), "sync")

@@ -1,0 +1,127 @@
+"""The reference's own entry points -- solgmre_, solgmrs_, solmfg_ with the argument lists of solgmr.f / solmfg.f and
+the COMMON blocks as hidden inputs (phasta_b200/csrc/fortran_abi.c -> libphb200_f.so).  CPU: the library exports
+them, and the C argument lists are the Fortran subroutine statements name for name.  GPU: a C stand-in for the
+Fortran executable (tests/fortran_abi/commons.c) owns the COMMON blocks, registers the block pointers as the
+five-line Fortran hook would, calls the three routines and must get what phb200_solgmre / solgmrs / solmfg return."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from common import make_case, rel_l2
+from phasta_b200 import lib as _lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIBF = os.path.join(ROOT, "phasta_b200", "libphb200_f.so")
+SRC = os.path.join(ROOT, "phasta_b200", "csrc", "fortran_abi.c")
+REF = "/root/reference/phSolver/compressible"
+
+# the dummy arguments of the three subroutine statements (solgmr.f:1-5, solgmr.f:368-373, solmfg.f:1-5)
+ARGS = {
+    "solgmre": "y ac yold acold x iBC BC EGmass res BDiag HBrg eBrg yBrg Rcos Rsin iper ilwork shp shgl shpb shglb "
+               "Dy rerr".split(),
+    "solgmrs": "y ac yold acold x iBC BC col row lhsk res BDiag HBrg eBrg yBrg Rcos Rsin iper ilwork shp shgl shpb "
+               "shglb Dy rerr".split(),
+    "solmfg": "y ac yold acold x iBC BC res BDiag HBrg eBrg yBrg Rcos Rsin iper ilwork shp shgl shpb shglb Dy "
+              "rerr".split(),
+}
+
+
+def _c_args(name):
+    src = open(SRC).read()
+    m = re.search(r"void %s_\((.*?)\)\s*\{" % name, src, re.S)
+    return [a.split()[-1].lstrip("*") for a in m.group(1).replace("\n", " ").split(",")]
+
+
+def _fortran_args(path, name):
+    txt = open(path, errors="replace").read()
+    m = re.search(r"subroutine\s+%s\s*\((.*?)\)" % name, txt, re.S | re.I)
+    body = re.sub(r"\n\s{5}\S", " ", m.group(1))          # continuation lines
+    return [a.strip() for a in body.replace("\n", " ").replace("\t", " ").split(",")]
+
+
+@pytest.mark.parametrize("name", list(ARGS))
+def test_exported_with_the_reference_argument_list(name):
+    out = subprocess.run(["nm", "-D", "--defined-only", LIBF], capture_output=True, text=True, check=True).stdout
+    assert re.search(r" T %s_$" % name, out, re.M), "libphb200_f.so does not export %s_" % name
+    assert [a.lower() for a in _c_args(name)] == [a.lower() for a in ARGS[name]]
+    f = {"solgmre": ("solgmr.f", "SolGMRe"), "solgmrs": ("solgmr.f", "SolGMRs"), "solmfg": ("solmfg.f", "SolMFG")}[name]
+    if os.path.exists(os.path.join(REF, f[0])):            # pin the list above to the reference source when it is here
+        assert [a.lower() for a in _fortran_args(os.path.join(REF, f[0]), f[1])] == [a.lower() for a in ARGS[name]]
+
+
+def test_common_blocks_stay_undefined_in_the_drop_in():
+    """the Fortran executable owns the COMMON storage: the library must only reference it"""
+    out = subprocess.run(["nm", "-D", LIBF], capture_output=True, text=True, check=True).stdout
+    for blk in ("conpar", "genpar", "timdat", "solpar", "itrpar", "blkdat", "intpt", "workfc", "fronts", "elmpar",
+                "matdat", "mmatpar", "precis", "outpar", "incomp", "shpdat"):
+        assert re.search(r"^\s+U %s_$" % blk, out, re.M), blk
+
+
+# ---------------------------------------------------------------------------------------------------- GPU
+def _stand_in():
+    bdir = os.path.join(HERE, "fortran_abi", "_build")
+    os.makedirs(bdir, exist_ok=True)
+    so = os.path.join(bdir, "libcommons.so")
+    src = os.path.join(HERE, "fortran_abi", "commons.c")
+    hdr = os.path.join(ROOT, "phasta_b200", "csrc", "fortran_commons.h")
+    if not os.path.exists(so) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+        subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", "-o", so, src])
+    com = C.CDLL(so, mode=C.RTLD_GLOBAL)        # the COMMON blocks must be visible when the drop-in is loaded
+    return com, C.CDLL(LIBF)
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+@pytest.mark.gpu
+def test_gpu_reference_entry_points_match_the_c_abi():
+    from phasta_b200.solver import PhastaGPU
+    case = make_case(8, 5, 4, bc="channel", etol=1e-7, Kspace=30)
+    params, tables, parts, states = case
+    mp = parts[0]
+    y, ac = states[0]
+    g = PhastaGPU(mp, params, tables, device=0)           # the C-ABI path: what the drop-in must reproduce
+    res0, Dy0 = g.SolGMRe(y, ac)
+    iKs0 = g.iKs
+    H0 = g.HBrg.copy()
+    colm, rowp, nnz_tot = g.genadj()
+    colm, rowp = colm.copy(), g.rowp.copy()
+    res1, Dy1 = g.SolGMRs(y, ac)
+    iKs1 = g.iKs
+
+    com, f = _stand_in()
+    st = g.step()
+    k = g._keep
+    com.drv_fill_commons(C.byref(g.common), C.byref(st), _p(k["lcblk"]), None, int(nnz_tot))
+    for b, ien in enumerate(k["mien"]):
+        f.phb200_register_block_(C.byref(C.c_int(b + 1)), _p(ien))
+    nshg, K = mp.nshg, params.Kspace
+    vec = lambda n=5: np.zeros((nshg, n), order="F")  # noqa: E731
+    yold, acold, res, Dy, rerr = y.copy(order="F"), ac.copy(order="F"), vec(), vec(), vec(10)
+    BD = np.zeros((nshg, 5, 5), order="F")
+    H, e, yb, rc, rs = np.zeros((K + 1, K), order="F"), np.zeros(K + 1), np.zeros(K + 1), np.zeros(K + 1), np.zeros(K + 1)
+    yf, acf = np.asfortranarray(y), np.asfortranarray(ac)
+    EG = np.zeros(1)                                        # never touched: EGmass stays in HBM
+    f.solgmre_(_p(yf), _p(acf), _p(yold), _p(acold), _p(k["x"]), _p(k["iBC"]), _p(k["BC"]), _p(EG), _p(res), _p(BD),
+               _p(H), _p(e), _p(yb), _p(rc), _p(rs), _p(k["iper"]), _p(k["ilwork"]), _p(k["shp"]), _p(k["shgl"]),
+               _p(k["shpb"]), _p(k["shglb"]), _p(Dy), _p(rerr))
+    itr, eg = (C.c_int * 6)(), C.c_double(0)
+    com.drv_get_itrpar(itr, C.byref(eg))
+    assert itr[0] == iKs0 and itr[2] == iKs0
+    assert rel_l2(res, res0) < 1e-12 and rel_l2(Dy, Dy0) < 1e-10 and rel_l2(H, H0) < 1e-10
+    lhsk = np.zeros(1)
+    res[:], Dy[:] = 0, 0
+    f.solgmrs_(_p(yf), _p(acf), _p(yold), _p(acold), _p(k["x"]), _p(k["iBC"]), _p(k["BC"]), _p(colm), _p(rowp),
+               _p(lhsk), _p(res), _p(BD), _p(H), _p(e), _p(yb), _p(rc), _p(rs), _p(k["iper"]), _p(k["ilwork"]),
+               _p(k["shp"]), _p(k["shgl"]), _p(k["shpb"]), _p(k["shglb"]), _p(Dy), _p(rerr))
+    com.drv_get_itrpar(itr, C.byref(eg))
+    assert itr[3] == iKs1 and itr[5] == iKs1
+    assert rel_l2(res, res1) < 1e-12 and rel_l2(Dy, Dy1) < 1e-10
+    f.phb200_fortran_finalize_()
+    g.close()
