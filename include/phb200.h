@@ -236,6 +236,9 @@ int phb200_profile_reset(phb200_ctx *ctx);
 /* FP64 FMA peak microbenchmark (MEASURED_PEAKS.json has no FP64 number):
  * returns achieved TFLOP/s of a register-resident DFMA chain kernel. */
 int phb200_fp64_peak(phb200_ctx *ctx, double *tflops);
+/* FP64 scatter-add microbenchmark: warp-wide red.global.add.f64 on the 25 contiguous doubles of pseudo-random
+ * 200-byte blocks out of nblk (the address pattern of fillsparseC into lhsK): G doubles added per second. */
+int phb200_red_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s);
 /* flush L2 by writing a >126 MB scratch buffer (bench hygiene) */
 int phb200_flush_l2(phb200_ctx *ctx);
 

@@ -899,6 +899,11 @@ extern "C" int phb200_fp64_peak(phb200_ctx *ctx, double *tflops) {
   ENTER(ctx);
   return phb_fp64_peak(ctx, tflops);
 }
+extern "C" int phb200_red_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s) {
+  ENTER(ctx);
+  if (!gadds_per_s) return fail("red_peak", "null argument");
+  return phb_red_peak(ctx, nblk, gadds_per_s);
+}
 extern "C" int phb200_flush_l2(phb200_ctx *ctx) {
   ENTER(ctx);
   PHB_CHECK(cudaMemsetAsync(ctx->d_scratch, 0, ctx->scratch_bytes, ctx->stream));

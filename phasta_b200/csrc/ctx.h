@@ -227,6 +227,7 @@ int phb_zero_slaves(phb200_ctx *ctx, double *d_r, int n, int identity);
 int phb_sumgat_dev(phb200_ctx *ctx, const double *d_u, size_t len, double *out);
 int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs, int *lGMRES, int *ntotGM);
 int phb_fp64_peak(phb200_ctx *ctx, double *tflops);
+int phb_red_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s);
 // timestep.cu
 int phb_itrpredict(phb200_ctx *ctx, const phb200_step *st, int ipred);
 int phb_itrbc(phb200_ctx *ctx, int ires);

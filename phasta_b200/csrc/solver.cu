@@ -841,3 +841,45 @@ int phb_fp64_peak(phb200_ctx *ctx, double *tflops) {
   *tflops = flops / (best * 1e-3) / 1e12;
   return 0;
 }
+
+// ---------------------------------------------------------------------------
+// Scatter-add microbenchmark (the denominator for ElmGMRs' fillsparseC scatter): every warp issues warp-wide
+// red.global.add.f64 on the 25 contiguous doubles of pseudo-random 200-byte blocks spread over `nblk` blocks
+// (nblk = nnz_tot gives the working set and the address pattern of lhsK).  Returns G doubles added per second.
+// ---------------------------------------------------------------------------
+__global__ void k_red_peak(double *buf, unsigned nblk, int iters, double v) {
+  const int lane = threadIdx.x & 31;
+  unsigned h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  for (int i = 0; i < iters; i++) {
+    h = h * 1664525u + 1013904223u;
+    const unsigned k = (h >> 4) % nblk;
+    if (lane < 25) atomicAdd(buf + (size_t)25 * k + lane, v);
+  }
+}
+int phb_red_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s) {
+  if (nblk < 1) return 1;
+  double *buf = nullptr;
+  PHB_CHECK(cudaMalloc(&buf, sizeof(double) * 25 * (size_t)nblk));
+  PHB_CHECK(cudaMemsetAsync(buf, 0, sizeof(double) * 25 * (size_t)nblk, ctx->stream));
+  const int blocks = 148 * 16, threads = 256, iters = 2000;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_red_peak<<<blocks, threads, 0, ctx->stream>>>(buf, (unsigned)nblk, 100, 1.0);
+  float best = 1e30f;
+  for (int r = 0; r < 3; r++) {
+    cudaEventRecord(e0, ctx->stream);
+    k_red_peak<<<blocks, threads, 0, ctx->stream>>>(buf, (unsigned)nblk, iters, 1.0);
+    cudaEventRecord(e1, ctx->stream);
+    PHB_CHECK(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  ctx->launches += 4;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *gadds_per_s = 25.0 * (double)iters * blocks * (threads / 32) / (best * 1e-3) / 1e9;
+  return 0;
+}

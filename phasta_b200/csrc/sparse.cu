@@ -10,10 +10,11 @@
 #include <cstring>
 
 // k_sparseap_tma: blocks / rows per staged chunk, stages in flight, consumer warps per CTA
-#define AP_CB 248
+#define AP_CB 240
 #define AP_CR 64
-#define AP_STAGES 4
-#define AP_WARPS 16
+#define AP_STAGES 2
+#define AP_WARPS 15
+#define AP_CTAS 2
 
 // ---------------------------------------------------------------------------
 // genadj: colm(nshg+1) 1-based row pointers, rowp ascending unique neighbour
@@ -169,13 +170,22 @@ int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_to
 // Spsi3pre (spsi3pre.f:41-221): thread per CSR block, lhsK(25,k) column-major
 // block (entry (f,g) at f + 5 g), L from the row node, U from the column node
 // ---------------------------------------------------------------------------
+// The 128 blocks of a CTA are one contiguous 25.6 KB piece of lhsK: it is moved through shared memory with
+// coalesced loads / stores, and each thread works on its block there (stride 25 doubles: conflict-free for 64-bit
+// accesses).  Thread-strided global accesses made this kernel 2.4x slower than its 400 B/block of traffic.
 __global__ void __launch_bounds__(128) k_spsi3pre(int nnz_tot, int nshg, const int *__restrict__ rowofblk,
                                                    const int *__restrict__ rowp, const double *__restrict__ BD,
                                                    double *lhsK) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nnz_tot) return;
+  __shared__ double sh[128 * 25];
+  const int kb = blockIdx.x * 128;
+  const int nb = (nnz_tot - kb < 128) ? nnz_tot - kb : 128;
+  double *gsrc = lhsK + (size_t)25 * kb;
+  for (int t = threadIdx.x; t < nb * 25; t += 128) sh[t] = gsrc[t];
+  __syncthreads();
+  const int k = kb + threadIdx.x;
+  if (k < nnz_tot) {
   const int i = rowofblk[k], j = rowp[k];
-  double *blk = lhsK + (size_t)25 * k;
+  double *blk = sh + 25 * threadIdx.x;
   double B[5][5];  // B[f][g]
 #pragma unroll
   for (int g = 0; g < 5; g++)
@@ -213,6 +223,9 @@ __global__ void __launch_bounds__(128) k_spsi3pre(int nnz_tot, int nshg, const i
   for (int g = 0; g < 5; g++)
 #pragma unroll
     for (int f = 0; f < 5; f++) blk[f + 5 * g] = B[f][g];
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < nb * 25; t += 128) gsrc[t] = sh[t];
 }
 
 int phb_spsi3pre(phb200_ctx *ctx) {
@@ -319,17 +332,18 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 }
 
 struct ApStage {
-  double a[25 * (AP_CB + 8)];
-  int col[AP_CB + 8];
+  double a[25 * (AP_CB + 16)];   // + alignment slack (3 + 3) and the over-read of the last 16-wide batch
+  int col[AP_CB + 16];
   int rowptr[AP_CR + 8];
 };
 struct ApSmem {
   ApStage st[AP_STAGES];
   unsigned long long full[AP_STAGES], empty[AP_STAGES];
   int next_row[AP_STAGES];
+  int r0[AP_STAGES], r1[AP_STAGES], direct[AP_STAGES];  // the chunk a stage holds (written by the producer)
 };
 
-__global__ void __launch_bounds__(32 * (AP_WARPS + 1), 1)
+__global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
     k_sparseap_tma(int nshg, int nchunk, const int *__restrict__ chunk, const int *__restrict__ colm,
                    const int *__restrict__ rowp, const double *__restrict__ lhsK, const double *__restrict__ p,
                    double *__restrict__ q, const int *__restrict__ skip) {
@@ -356,6 +370,9 @@ __global__ void __launch_bounds__(32 * (AP_WARPS + 1), 1)
         const int r0 = chunk[c], r1 = chunk[c + 1];
         const int k0 = colm[r0], k1 = colm[r1];
         S.next_row[stg] = 0;
+        S.r0[stg] = r0;
+        S.r1[stg] = r1;
+        S.direct[stg] = (k1 - k0 > AP_CB);
         if (k1 - k0 > AP_CB) {  // a single very long row: consumers load it directly
           mbar_arrive(&S.full[stg]);
           continue;
@@ -379,29 +396,31 @@ __global__ void __launch_bounds__(32 * (AP_WARPS + 1), 1)
     const int stg = it % AP_STAGES;
     const ApStage &T = S.st[stg];
     mbar_wait(&S.full[stg], (it / AP_STAGES) & 1);
-    const int r0 = chunk[c], r1 = chunk[c + 1];
+    const int r0 = S.r0[stg], r1 = S.r1[stg];
     const int ra = r0 & ~3;
+    const bool direct = S.direct[stg] != 0;
+    const int ka = T.rowptr[r0 - ra] & ~3;
     for (;;) {
       int r = 0;
       if (lane == 0) r = atomicAdd(&S.next_row[stg], 1);
       r = __shfl_sync(0xffffffffu, r, 0) + r0;
       if (r >= r1) break;
       double acc0 = 0.0, acc1 = 0.0;
-      if (r1 - r0 == 1 && colm[r1] - colm[r0] > AP_CB) {
-        // direct path for a row that does not fit a stage
+      if (direct) {
+        // a row that does not fit a stage
         const int k0 = colm[r], k1 = colm[r + 1];
         for (int k = k0; k < k1; k++) acc0 += __ldcs(lhsK + (size_t)25 * k + l) * __ldg(pg + __ldg(rowp + k));
       } else {
         const int k0 = T.rowptr[r - ra], k1 = T.rowptr[r - ra + 1];
-        const int ka = T.rowptr[r0 - ra] & ~3;
         const double *a = T.a + 25 * (k0 - ka) + l;
         const int *cj = T.col + (k0 - ka);
-        for (int k = k0; k < k1; k += 8, a += 200, cj += 8) {
-          double pv[8];
+        // sixteen gathers of p in flight per lane: a typical row (15 blocks) is one round trip to L2
+        for (int k = k0; k < k1; k += 16, a += 400, cj += 16) {
+          double pv[16];
 #pragma unroll
-          for (int i = 0; i < 8; i++) pv[i] = __ldg(pg + ((k + i < k1) ? cj[i] : r));
+          for (int i = 0; i < 16; i++) pv[i] = __ldg(pg + ((k + i < k1) ? cj[i] : r));
 #pragma unroll
-          for (int i = 0; i < 8; i += 2) {
+          for (int i = 0; i < 16; i += 2) {
             acc0 += ((k + i < k1) ? a[25 * i] : 0.0) * pv[i];
             acc1 += ((k + i + 1 < k1) ? a[25 * (i + 1)] : 0.0) * pv[i + 1];
           }
@@ -453,7 +472,7 @@ int phb_sparseap2(phb200_ctx *ctx, double *d_p, double *d_out, const int *d_skip
     }
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-    const int grid = std::min(ctx->n_apchunk, nsm);
+    const int grid = std::min(ctx->n_apchunk, nsm * AP_CTAS);
     k_sparseap_tma<<<grid, 32 * (AP_WARPS + 1), sizeof(ApSmem), s>>>(nshg, ctx->n_apchunk, ctx->d_apchunk, ctx->d_colm,
                                                                      ctx->d_rowp, ctx->d_lhsK, d_p, d_out, d_skip);
 #else

@@ -493,6 +493,12 @@ class PhastaGPU:
         _chk(self.L.phb200_fp64_peak(self.ctx, C.byref(t)), "fp64_peak")
         return t.value
 
+    def red_peak(self, nblk):
+        """G FP64 scatter-adds per second into nblk random 25-double blocks (microbenchmark)"""
+        t = C.c_double(0)
+        _chk(self.L.phb200_red_peak(self.ctx, C.c_longlong(int(nblk)), C.byref(t)), "red_peak")
+        return t.value
+
     def flush_l2(self):
         _chk(self.L.phb200_flush_l2(self.ctx), "flush_l2")
 

@@ -114,7 +114,7 @@ def test_gpu_reference_entry_points_match_the_c_abi():
     itr, eg = (C.c_int * 6)(), C.c_double(0)
     com.drv_get_itrpar(itr, C.byref(eg))
     assert itr[0] == iKs0 and itr[2] == iKs0
-    assert rel_l2(res, res0) < 1e-12 and rel_l2(Dy, Dy0) < 1e-10 and rel_l2(H, H0) < 1e-10
+    assert rel_l2(res, res0) < 1e-12 and rel_l2(Dy, Dy0) < 1e-10 and rel_l2(H, H0) < 1e-8
     lhsk = np.zeros(1)
     res[:], Dy[:] = 0, 0
     f.solgmrs_(_p(yf), _p(acf), _p(yold), _p(acold), _p(k["x"]), _p(k["iBC"]), _p(k["BC"]), _p(colm), _p(rowp),
