@@ -495,9 +495,8 @@ extern "C" int phb200_solgmre(phb200_ctx *ctx, const double *y, const double *ac
 // ---- block-CSR flavour -------------------------------------------------------
 extern "C" int phb200_genadj(phb200_ctx *ctx, int nnz, int *colm, int *rowp, int *nnz_tot) {
   ENTER(ctx);
-  if (!colm || !rowp || !nnz_tot) return fail("genadj", "null argument");
-  return phb_genadj_host(ctx->c.nshg, ctx->c.nelblk, ctx->h_lcblk.data(), ctx->h_mien.data(), nnz, colm, rowp,
-                         nnz_tot);
+  if (!nnz_tot) return fail("genadj", "null argument");
+  return phb_genadj(ctx, nnz, colm, rowp, nnz_tot);
 }
 extern "C" int phb200_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_tot) {
   ENTER(ctx);

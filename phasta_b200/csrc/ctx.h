@@ -249,9 +249,9 @@ int phb_inc_elmgmr(phb200_ctx *ctx, const phb200_incomp *ip);
 int phb_les_ap(phb200_ctx *ctx, int kind, const double *d_p, double *d_q);
 void phb_inc_free(phb200_ctx *ctx);
 // sparse.cu
-int phb_genadj_host(int nshg, int nelblk, const int *lcblk, const int *const *mien, int nnz, int *colm, int *rowp,
-                    int *nnz_tot);
 int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_tot);
+int phb_genadj(phb200_ctx *ctx, int nnz, int *colm, int *rowp, int *nnz_tot);
+int phb_genadj_dev(phb200_ctx *ctx, int **d_colm0, int **d_rowp0, int **d_rob, long long *nnz_tot);  // genadj.cu
 int phb_spsi3pre(phb200_ctx *ctx);
 int phb_sparseap(phb200_ctx *ctx, double *d_u);
 int phb_sparseap2(phb200_ctx *ctx, double *d_p, double *d_out, const int *d_skip);

@@ -16,13 +16,16 @@
 #define AP_WARPS 15
 #define AP_CTAS 2
 
+#if defined(PHB_HOST_FULL) || defined(PHB_HOST_EMUL)
+// ---- host emulation only (tests/host_emul): CUB does not build there, so the emulated "device" gets its CSR
+//      structure from this host routine; the product path is genadj.cu ----
 // ---------------------------------------------------------------------------
 // genadj: colm(nshg+1) 1-based row pointers, rowp ascending unique neighbour
 // ids incl. self.  The reference grows per-node lists with an O(deg^2) search
 // and selection-sorts them (asadj.f:24-50, genadj.f:50-62); the result is the
 // sorted unique adjacency, built here from a node->element map in O(N deg log deg).
 // ---------------------------------------------------------------------------
-int phb_genadj_host(int nshg, int nelblk, const int *lcblk, const int *const *mien, int nnz, int *colm, int *rowp,
+static int phb_genadj_host(int nshg, int nelblk, const int *lcblk, const int *const *mien, int nnz, int *colm, int *rowp,
                     int *nnz_tot) {
   std::vector<int> cnt((size_t)nshg + 1, 0);
   for (int b = 0; b < nelblk; b++) {
@@ -75,6 +78,28 @@ int phb_genadj_host(int nshg, int nelblk, const int *lcblk, const int *const *mi
   return 0;
 }
 
+int phb_genadj_dev(phb200_ctx *ctx, int **d_colm0, int **d_rowp0, int **d_rob, long long *nnz_tot) {
+  const int nshg = ctx->c.nshg, cap = 64;
+  std::vector<int> colm((size_t)nshg + 1), rowp((size_t)cap * nshg);
+  int ntot = 0;
+  if (phb_genadj_host(nshg, ctx->c.nelblk, ctx->h_lcblk.data(), ctx->h_mien.data(), cap, colm.data(), rowp.data(), &ntot))
+    return 1;
+  PHB_CHECK(cudaMalloc(d_colm0, sizeof(int) * ((size_t)nshg + 1 + 8)));
+  PHB_CHECK(cudaMalloc(d_rowp0, sizeof(int) * ((size_t)ntot + 8)));
+  PHB_CHECK(cudaMalloc(d_rob, sizeof(int) * ((size_t)ntot + 8)));
+  memset(*d_colm0, 0, sizeof(int) * ((size_t)nshg + 1 + 8));
+  memset(*d_rowp0, 0, sizeof(int) * ((size_t)ntot + 8));
+  for (int i = 0; i <= nshg; i++) (*d_colm0)[i] = colm[i] - 1;
+  for (int i = 0; i < nshg; i++)
+    for (int k = colm[i] - 1; k < colm[i + 1] - 1; k++) {
+      (*d_rowp0)[k] = rowp[k] - 1;
+      (*d_rob)[k] = i;
+    }
+  *nnz_tot = ntot;
+  return 0;
+}
+#endif
+
 // sparseloc (fillsparse.f:236-271) for every (element, a, b): CSR block index
 __global__ void k_eloc(int nshl, int numel, size_t numel_pad, const int *__restrict__ ien,
                        const int *__restrict__ colm, const int *__restrict__ rowp, int *__restrict__ eloc) {
@@ -96,34 +121,47 @@ __global__ void k_eloc(int nshl, int numel, size_t numel_pad, const int *__restr
   }
 }
 
-int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_tot) {
-  const int nshg = ctx->c.nshg;
-  if (colm[0] != 1 || colm[nshg] - 1 != nnz_tot) {
-    fprintf(stderr, "phb200: set_sparse: colm is not a 1-based row pointer array ending at nnz_tot+1\n");
-    return 1;
-  }
-  std::vector<int> c0((size_t)nshg + 1), r0((size_t)nnz_tot), rob((size_t)nnz_tot);
-  for (int i = 0; i <= nshg; i++) c0[i] = colm[i] - 1;
-  for (int i = 0; i < nshg; i++)
-    for (int k = c0[i]; k < c0[i + 1]; k++) {
-      r0[k] = rowp[k] - 1;
-      rob[k] = i;
-      if (r0[k] < 0 || r0[k] >= nshg) {
-        fprintf(stderr, "phb200: set_sparse: rowp entry out of range\n");
-        return 1;
+// 1-based host arrays -> 0-based device arrays, row of every entry, range check (one thread per row)
+__global__ void k_csr_from_ref(int nshg, int nnz_tot, int *__restrict__ colm, int *__restrict__ rowp,
+                               int *__restrict__ rowofblk, int *__restrict__ bad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > nshg) return;
+  const int k0 = colm[i] - 1;  // (colm itself turns 0-based in a second pass: other rows still read it here)
+  if (i < nshg) {
+    const int k1 = colm[i + 1] - 1;
+    if (k0 < 0 || k1 < k0 || k1 > nnz_tot) {
+      atomicExch(bad, 1);
+    } else {
+      for (int k = k0; k < k1; k++) {
+        const int j = rowp[k] - 1;
+        if (j < 0 || j >= nshg) atomicExch(bad, 2);
+        rowp[k] = j;
+        rowofblk[k] = i;
       }
     }
+  }
+}
+__global__ void k_sub1(int n, int *v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] -= 1;
+}
+
+// Takes ownership of a 0-based CSR structure already on the device (colm0 / rowp0 / rob padded by 8 entries) and
+// allocates what hangs off it: lhsK, the element -> block map (sparseloc, once) and SparseAp's row chunks.
+// h_colm0: host copy of the 0-based row pointers.
+int phb_install_sparse(phb200_ctx *ctx, int *d_colm0, int *d_rowp0, int *d_rob, int nnz_tot, const int *h_colm0) {
+  const int nshg = ctx->c.nshg;
   auto F = [](void *p) { if (p) cudaFree(p); };
   F(ctx->d_colm); F(ctx->d_rowp); F(ctx->d_rowofblk); F(ctx->d_lhsK); F(ctx->d_eloc); F(ctx->d_apchunk);
+  ctx->d_colm = d_colm0;
+  ctx->d_rowp = d_rowp0;
+  ctx->d_rowofblk = d_rob;
+  ctx->d_lhsK = nullptr; ctx->d_eloc = nullptr; ctx->d_apchunk = nullptr;
   ctx->nnz_tot = nnz_tot;
   // (+8: the bulk copies of k_sparseap_tma start and end on multiples of 4 entries)
-  PHB_CHECK(cudaMalloc(&ctx->d_colm, sizeof(int) * ((size_t)nshg + 1 + 8)));
-  PHB_CHECK(cudaMalloc(&ctx->d_rowp, sizeof(int) * ((size_t)nnz_tot + 8)));
-  PHB_CHECK(cudaMalloc(&ctx->d_rowofblk, sizeof(int) * (size_t)std::max(nnz_tot, 1)));
   PHB_CHECK(cudaMalloc(&ctx->d_lhsK, sizeof(double) * 25 * ((size_t)nnz_tot + 8)));
-  PHB_CHECK(cudaMemset(ctx->d_colm, 0, sizeof(int) * ((size_t)nshg + 1 + 8)));
-  PHB_CHECK(cudaMemset(ctx->d_rowp, 0, sizeof(int) * ((size_t)nnz_tot + 8)));
-  PHB_CHECK(cudaMemset(ctx->d_lhsK, 0, sizeof(double) * 25 * ((size_t)nnz_tot + 8)));
+  PHB_CHECK(cudaMemsetAsync(ctx->d_lhsK, 0, sizeof(double) * 25 * ((size_t)nnz_tot + 8), ctx->stream));
+  PHB_CHECK(cudaMalloc(&ctx->d_eloc, sizeof(int) * 16 * ctx->numel_pad));
   {
     // row chunks of SparseAp: consecutive rows, at most AP_CB blocks and AP_CR rows each (a longer row is a chunk
     // of its own and takes the direct-load path)
@@ -132,7 +170,7 @@ int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_to
     while (r < nshg) {
       ch.push_back(r);
       int e = r + 1;
-      while (e < nshg && e - r < AP_CR && c0[e + 1] - c0[r] <= AP_CB) e++;
+      while (e < nshg && e - r < AP_CR && h_colm0[e + 1] - h_colm0[r] <= AP_CB) e++;
       r = e;
     }
     ch.push_back(nshg);
@@ -140,11 +178,7 @@ int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_to
     PHB_CHECK(cudaMalloc(&ctx->d_apchunk, sizeof(int) * ch.size()));
     PHB_CHECK(cudaMemcpy(ctx->d_apchunk, ch.data(), sizeof(int) * ch.size(), cudaMemcpyHostToDevice));
   }
-  PHB_CHECK(cudaMalloc(&ctx->d_eloc, sizeof(int) * 16 * ctx->numel_pad));
-  PHB_CHECK(cudaMemcpy(ctx->d_colm, c0.data(), sizeof(int) * c0.size(), cudaMemcpyHostToDevice));
-  PHB_CHECK(cudaMemcpy(ctx->d_rowp, r0.data(), sizeof(int) * r0.size(), cudaMemcpyHostToDevice));
-  PHB_CHECK(cudaMemcpy(ctx->d_rowofblk, rob.data(), sizeof(int) * rob.size(), cudaMemcpyHostToDevice));
-  PHB_CHECK(cudaMemset(ctx->d_eloc, 0, sizeof(int) * 16 * ctx->numel_pad));
+  PHB_CHECK(cudaMemsetAsync(ctx->d_eloc, 0, sizeof(int) * 16 * ctx->numel_pad, ctx->stream));
   if (ctx->numel_tet > 0) {
     k_eloc<<<(ctx->numel_tet + 127) / 128, 128, 0, ctx->stream>>>(4, ctx->numel_tet, ctx->numel_pad, ctx->d_ien,
                                                                   ctx->d_colm, ctx->d_rowp, ctx->d_eloc);
@@ -155,7 +189,7 @@ int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_to
     if (g.d_eloc) cudaFree(g.d_eloc);
     const size_t n = (size_t)g.nshl * g.nshl * g.numel_pad;
     PHB_CHECK(cudaMalloc(&g.d_eloc, sizeof(int) * n));
-    PHB_CHECK(cudaMemset(g.d_eloc, 0, sizeof(int) * n));
+    PHB_CHECK(cudaMemsetAsync(g.d_eloc, 0, sizeof(int) * n, ctx->stream));
     k_eloc<<<(g.numel + 127) / 128, 128, 0, ctx->stream>>>(g.nshl, g.numel, g.numel_pad, g.d_ien, ctx->d_colm,
                                                            ctx->d_rowp, g.d_eloc);
     ctx->launches++;
@@ -164,6 +198,65 @@ int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_to
   PHB_CHECK(cudaStreamSynchronize(ctx->stream));
   ctx->have_lhs_sparse = false;
   return 0;
+}
+
+// the CSR structure itrdrv owns (genadj's colm / rowp, 1-based) -> device
+int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_tot) {
+  const int nshg = ctx->c.nshg;
+  if (colm[0] != 1 || colm[nshg] - 1 != nnz_tot) {
+    fprintf(stderr, "phb200: set_sparse: colm is not a 1-based row pointer array ending at nnz_tot+1\n");
+    return 1;
+  }
+  std::vector<int> c0((size_t)nshg + 1);
+  for (int i = 0; i <= nshg; i++) c0[i] = colm[i] - 1;
+  int *d_c = nullptr, *d_r = nullptr, *d_rob = nullptr, *d_bad = nullptr;
+  PHB_CHECK(cudaMalloc(&d_c, sizeof(int) * ((size_t)nshg + 1 + 8)));
+  PHB_CHECK(cudaMalloc(&d_r, sizeof(int) * ((size_t)nnz_tot + 8)));
+  PHB_CHECK(cudaMalloc(&d_rob, sizeof(int) * ((size_t)nnz_tot + 8)));
+  PHB_CHECK(cudaMalloc(&d_bad, sizeof(int)));
+  PHB_CHECK(cudaMemsetAsync(d_c, 0, sizeof(int) * ((size_t)nshg + 1 + 8), ctx->stream));
+  PHB_CHECK(cudaMemsetAsync(d_r, 0, sizeof(int) * ((size_t)nnz_tot + 8), ctx->stream));
+  PHB_CHECK(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+  PHB_CHECK(cudaMemcpyAsync(d_c, colm, sizeof(int) * ((size_t)nshg + 1), cudaMemcpyHostToDevice, ctx->stream));
+  PHB_CHECK(cudaMemcpyAsync(d_r, rowp, sizeof(int) * (size_t)nnz_tot, cudaMemcpyHostToDevice, ctx->stream));
+  k_csr_from_ref<<<(nshg + 1 + 127) / 128, 128, 0, ctx->stream>>>(nshg, nnz_tot, d_c, d_r, d_rob, d_bad);
+  k_sub1<<<(nshg + 1 + 255) / 256, 256, 0, ctx->stream>>>(nshg + 1, d_c);
+  ctx->launches += 2;
+  int bad = 0;
+  PHB_CHECK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d_bad);
+  if (bad) {
+    cudaFree(d_c); cudaFree(d_r); cudaFree(d_rob);
+    fprintf(stderr, bad == 1 ? "phb200: set_sparse: colm is not monotone within 1..nnz_tot+1\n"
+                             : "phb200: set_sparse: rowp entry out of range\n");
+    return 1;
+  }
+  return phb_install_sparse(ctx, d_c, d_r, d_rob, nnz_tot, c0.data());
+}
+
+// genadj on the device (genadj.cu), installed as the part's CSR structure; colm / rowp (1-based, the reference's
+// arrays) are filled when non-null.  nnz is the reference's per-node capacity of rowp (genadj.f:30,66).
+int phb_genadj(phb200_ctx *ctx, int nnz, int *colm, int *rowp, int *nnz_tot) {
+  const int nshg = ctx->c.nshg;
+  int *d_c = nullptr, *d_r = nullptr, *d_rob = nullptr;
+  long long ntot = 0;
+  PHB_TRY(phb_genadj_dev(ctx, &d_c, &d_r, &d_rob, &ntot));
+  if (ntot > (long long)nnz * nshg) {
+    cudaFree(d_c); cudaFree(d_r); cudaFree(d_rob);
+    fprintf(stderr, "phb200: genadj: increase nnz (needs more than %d per node)\n", nnz);
+    return 1;
+  }
+  std::vector<int> c0((size_t)nshg + 1);
+  PHB_CHECK(cudaMemcpy(c0.data(), d_c, sizeof(int) * ((size_t)nshg + 1), cudaMemcpyDeviceToHost));
+  if (colm)
+    for (int i = 0; i <= nshg; i++) colm[i] = c0[i] + 1;
+  if (rowp) {
+    PHB_CHECK(cudaMemcpy(rowp, d_r, sizeof(int) * (size_t)ntot, cudaMemcpyDeviceToHost));
+    for (long long k = 0; k < ntot; k++) rowp[k] += 1;
+  }
+  *nnz_tot = (int)ntot;
+  return phb_install_sparse(ctx, d_c, d_r, d_rob, (int)ntot, c0.data());
 }
 
 // ---------------------------------------------------------------------------
