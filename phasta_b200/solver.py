@@ -154,15 +154,15 @@ class PhastaGPU:
     # ------------------------------------------------------ block-CSR flavour
     def genadj(self, nnz=35):
         """common/genadj.f: returns (colm, rowp, nnz_tot) with the reference's
-        1-based conventions and hands them to the device (set_sparse)."""
+        1-based conventions; the device keeps the structure it has just built."""
         nshg = self.part.nshg
         colm = np.zeros(nshg + 1, dtype=np.int32)
         rowp = np.zeros(nnz * nshg, dtype=np.int32)
         ntot = C.c_int(0)
         _chk(self.L.phb200_genadj(self.ctx, int(nnz), _p(colm, C.c_int), _p(rowp, C.c_int), C.byref(ntot)),
              "genadj")
+        # (phb200_genadj builds the structure on the device and installs it: no phb200_set_sparse round trip)
         self.colm, self.rowp, self.nnz_tot = colm, rowp, ntot.value
-        self.set_sparse(colm, rowp, ntot.value)
         return colm, rowp[:ntot.value], ntot.value
 
     def set_sparse(self, colm, rowp, nnz_tot):

@@ -332,6 +332,8 @@ class ExprParser:
             return "False"
         if kind == "op" and val == "-":
             return "(-%s)" % self.primary()
+        if kind == "id" and val.endswith("_") and self.peek() is not None and self.peek()[0] == "str":
+            return repr(self.next()[1])          # kind-prefixed character literal: c_char_'integer'
         if kind == "id":
             src = val
             if self.accept("("):
@@ -550,6 +552,7 @@ INTRINSICS = {
     "dot_product": lambda a, b: _sum(a * b),
     "merge": lambda a, b, m: np.where(m, a, b),
     "trim": lambda s: s.rstrip(), "len": len,
+    "c_loc": lambda a: a, "char": lambda i: chr(int(i)),     # iso_c_binding: the array itself stands for its address
     "minloc": lambda a: np.array([int(np.argmin(a)) + 1]), "maxloc": lambda a: np.array([int(np.argmax(a)) + 1]),
 }
 
@@ -621,6 +624,11 @@ class Unit:
         self.body = []
         self.uses_common = False
         self.params = []     # (name, code)
+
+
+class CompPtr:
+    """one element of a module array of derived-type pointers (x(i)%p)"""
+    p = None
 
 
 class _Return(Exception):
@@ -925,6 +933,13 @@ class Program:
             if self._load_common(fname):
                 unit.uses_common = True
             return None
+        if head == "write" and len(toks) == 6 and toks[1] == ("op", "(") and toks[2][0] == "id" \
+                and toks[3] == ("op", ",") and toks[4][0] == "str" and toks[5] == ("op", ")"):
+            # internal write of a literal-only format into a character variable: write (name,"('text')")
+            m = re.match(r"^\(\s*'((?:[^']|'')*)'\s*\)$", toks[4][1])
+            if m:
+                lit = m.group(1).replace("''", "'")
+                return with_label(self._parse_assign([toks[2], ("op", "="), ("str", lit)], where))
         if head in _IGNORED:
             if head == "use":
                 return None
@@ -1078,6 +1093,13 @@ class Program:
         if head in ("goto", "go"):
             target = int(toks[-1][1])
             return with_label(("goto", target))
+        if head == "allocate" and ("op", "%") in toks:
+            inner = toks[2:-1]
+            k = inner.index(("op", "%"))
+            base, field = inner[0][1], inner[k + 1][1]
+            idx = compile_expr(parse_expr_tokens(inner[2:k - 1]))
+            dims = _parse_entities([("id", "_c")] + inner[k + 2:])[0][1]
+            return with_label(("allocate_comp", base, idx, field, dims, where))
         if head == "allocate":
             ents = _parse_entities(toks[2:-1])
             return with_label(("allocate", ents, where))
@@ -1378,6 +1400,17 @@ class Program:
                 typ = (d.typ if d and d.typ else None) or ("integer" if name[0] in "ijklmn" else "real")
                 dt = np.int64 if typ == "integer" else np.float64
                 env.L[name] = np.full(shape, np.nan if (dt == np.float64 and self.nan_locals) else 0, dtype=dt, order="F")
+        elif kind == "allocate_comp":
+            # module array of derived-type pointers (pointer.f:42-47), kept by the driver as a python list in M;
+            # M["_comp_dtype"][base] says integer / real (the module declaration is not parsed)
+            _, base, idx, field, dims, where = s
+            lst = self.M[base]
+            i = int(eval(idx, HELPERS, env))
+            while len(lst) < i:
+                lst.append(CompPtr())
+            shape, lbs = self._eval_dims(dims, env, None)
+            dt = self.M.get("_comp_dtype", {}).get(base, np.float64)
+            setattr(lst[i - 1], field, np.full(shape, np.nan if dt == np.float64 else 0, dtype=dt, order="F"))
         elif kind == "assign_obj":
             tgt = eval(s[1], HELPERS, env)
             tgt[...] = eval(s[2], HELPERS, env)

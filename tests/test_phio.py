@@ -3,6 +3,7 @@
 geombc/restart round trips of synthetic parts, genBC1 against the reference's genbc1.f executed by f77np
 (tests/golden/f77_genbc1.npz), and the solver on a part that went through the files."""
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -188,3 +189,40 @@ def test_gpu_solve_from_files_c1_cube(tmp_path):
     assert rel_l2(g.rmes, o.parts[0].rmes) < 1e-10
     assert rel_l2(Dy, o.parts[0].Dy) < 1e-8
     g.close()
+
+
+# ---- a28: genblk / gensav / lcblk / mien against the reference's own genblkPosix.f + gensav.f -----------------------
+def _genblk_cases():
+    sys.path.insert(0, GOLD)
+    from make_golden_genblk import CASES
+    return list(CASES)
+
+
+@pytest.mark.parametrize("name", _genblk_cases())
+def test_blocks_match_the_executed_genblkposix(tmp_path, name):
+    """tests/golden/f77_genblk.npz holds lcblk and every mien(iblk)%p as the UNMODIFIED common/genblkPosix.f +
+    gensav.f (run by f77np over this repo's geombc file) leave them; the mesh generator's own blocking
+    (mesh._blocks) and the file reader (phio.read_geombc) must give the same integers, block for block."""
+    from make_golden_genblk import build_case
+    z = np.load(os.path.join(GOLD, "f77_genblk.npz"))
+    (params, tables, parts, states), ibksz = build_case(name)
+    p = parts[0]
+    q = phio.read_geombc(os.path.dirname(os.path.dirname(phio.write_geombc(p, str(tmp_path)))), 0, 1, ibksz)
+    nelblk = int(z["%s_nelblk" % name])
+    for mp in (p, q):
+        assert mp.nelblk == nelblk
+        assert np.array_equal(mp.lcblk, z["%s_lcblk" % name])
+        for i in range(nelblk):
+            assert np.array_equal(mp.mien[i], z["%s_mien_%d" % (name, i)])
+    if name == "mixed":      # tets first, then wedges: lcsyst 1 ... 3, a ragged last block per topology
+        assert list(np.unique(z["mixed_lcblk"][2, :-1])) == [1, 3]
+
+
+def test_genblk_fixture_reproduces_from_the_reference():
+    if not os.path.isdir("/root/reference/phSolver/common"):
+        pytest.skip("reference sources not present")
+    from make_golden_genblk import generate
+    z = np.load(os.path.join(GOLD, "f77_genblk.npz"))
+    new = generate()
+    assert set(new) == set(z.files)
+    assert all(np.array_equal(new[k], z[k]) for k in new)
