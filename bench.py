@@ -711,6 +711,23 @@ def side_workload(env, args, name, params, tables, init_comm, steps):
         except Exception as e:
             par = {"ok": False, "error": repr(e)[:200]}
     r = time_workload(env, g, part, steps, 3, residual_only=False)
+    if isinstance(par, dict) and "sparse" in r and "error" not in par:
+        # the block-CSR flavour of the same part: lhsK blocks and CSR rows against the oracle's, and the two solvers
+        # (independent operators on the device) must need the same number of iterations
+        try:
+            from oracle.spot_check import slab_check
+            ny, nz = WORKLOADS[name][1:3]
+            g.dev_elmgmrs(st)
+            s2 = slab_check(g, part, params, tables, y, ac, (ny + 1) * (nz + 1), flavour="csr")
+            par["csr"] = {"res": s2["res"], "BDiag": s2["BDiag"], "lhsK": s2["lhsK"],
+                          "csr_rows_bit_exact": s2["csr_rows_bit_exact"], "blocks_checked": s2["blocks"]}
+            par["ok"] = bool(par["ok"] and s2["csr_rows_bit_exact"] and max(s2["res"], s2["BDiag"], s2["lhsK"]) < 1e-10)
+        except Exception as e:
+            par["csr"] = {"error": repr(e)[:200]}
+            par["ok"] = False
+    if isinstance(par, dict) and "sparse" in r and "solgmre" in r:
+        par["iterations_ebe_csr"] = [r["solgmre"]["gmres_iterations"], r["sparse"]["gmres_iterations"]]
+        par["ok"] = bool(par["ok"] and abs(par["iterations_ebe_csr"][0] - par["iterations_ebe_csr"][1]) <= 1)
     all_tets = len(WORKLOADS[name]) == 3
     tf = part.numel * FLOP_PER_ELEM_KERNEL / (r["kern_ms"] * 1e-3) / 1e12 if all_tets else None
     out = {"workload": name, "elements": part.numel * env.world, "elements_per_gpu": part.numel,

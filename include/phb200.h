@@ -236,6 +236,14 @@ int phb200_profile_reset(phb200_ctx *ctx);
 /* FP64 FMA peak microbenchmark (MEASURED_PEAKS.json has no FP64 number):
  * returns achieved TFLOP/s of a register-resident DFMA chain kernel. */
 int phb200_fp64_peak(phb200_ctx *ctx, double *tflops);
+/* Deterministic assembly option (north_star: 'colored or warp-aggregated scatter-add'; the reference adds element
+ * contributions in element order, local.f:67-74).  on != 0: AsIq and the lhs=1 tet assembly store their per-element
+ * contributions and a node-wise gather sums them in ascending element order, so qres, res and BDiag (and EGmass,
+ * which never used atomics) are bit-for-bit reproducible from run to run; costs one extra pass over 960 B/element.
+ * Default off: FP64 atomics, results equal to round-off.  Parts of linear tets without boundary-element blocks. */
+int phb200_set_deterministic(phb200_ctx *ctx, int on);
+/* FP64 tensor-core peak (mma.sync.m8n8k4.f64 chains): the evidence for keeping 5x5 blocks on the FMA pipe */
+int phb200_dmma_peak(phb200_ctx *ctx, double *tflops);
 /* FP64 scatter-add microbenchmark: warp-wide red.global.add.f64 on the 25 contiguous doubles of pseudo-random
  * 200-byte blocks out of nblk (the address pattern of fillsparseC into lhsK): G doubles added per second. */
 int phb200_red_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s);

@@ -269,7 +269,7 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
                   ctx->d_rmass, ctx->d_res, ctx->d_rmes, ctx->d_Dy, ctx->d_temp, ctx->d_BDiag, ctx->d_BDtmp,
                   ctx->d_EG, ctx->d_uBrg, ctx->d_dots, ctx->d_scratch, ctx->d_ienb, ctx->d_iBCB,
                   ctx->d_BCB, ctx->d_aerfrc, ctx->d_colm, ctx->d_rowp, ctx->d_rowofblk, ctx->d_eloc, ctx->d_lhsK,
-                  ctx->d_nodeaos, ctx->d_yold, ctx->d_acold, ctx->d_mfg, ctx->d_ptmp, ctx->d_kry, ctx->d_kflag, ctx->d_apchunk};
+                  ctx->d_nodeaos, ctx->d_yold, ctx->d_acold, ctx->d_mfg, ctx->d_ptmp, ctx->d_kry, ctx->d_kflag, ctx->d_apchunk, ctx->d_elc, ctx->d_inc, ctx->d_inc_ptr};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (ctx->d_refel_tet) cudaFree(ctx->d_refel_tet);
@@ -898,9 +898,18 @@ extern "C" int phb200_fp64_peak(phb200_ctx *ctx, double *tflops) {
   ENTER(ctx);
   return phb_fp64_peak(ctx, tflops);
 }
+extern "C" int phb200_set_deterministic(phb200_ctx *ctx, int on) {
+  ENTER(ctx);
+  return phb_set_deterministic(ctx, on);
+}
+extern "C" int phb200_dmma_peak(phb200_ctx *ctx, double *tflops) {
+  ENTER(ctx);
+  return phb_dmma_peak(ctx, tflops);
+}
 extern "C" int phb200_red_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s) {
   ENTER(ctx);
   if (!gadds_per_s) return fail("red_peak", "null argument");
+  if (nblk < 0) return phb_bulkred_peak(ctx, -nblk, gadds_per_s);  // negative: the bulk-copy-engine variant
   return phb_red_peak(ctx, nblk, gadds_per_s);
 }
 extern "C" int phb200_flush_l2(phb200_ctx *ctx) {

@@ -25,6 +25,7 @@
 // code and the kernel with inline PTX are left out of that build.  The product build never defines it.
 #ifndef PHB_HOST_EMUL
 #include "ctx.h"
+#include "mbar.cuh"
 #endif
 #include <cstring>
 #include "bnd_pack.h"
@@ -54,6 +55,14 @@ __constant__ TetTables c_tet;
 __constant__ TriTables c_tri;
 __constant__ PhysParams c_ph;
 __constant__ BndTables c_bnd[3];
+// Deterministic assembly option: when elc is set, the tet kernels STORE their per-element contributions
+// (row (a,c) of elc[row][stride], lane = element, coalesced) instead of atomically adding them to the node arrays, and
+// k_node_gather sums every node's contributions in ascending element order (the order of local.f:67-74).
+struct DetParams {
+  double *elc;
+  size_t stride;
+};
+__constant__ DetParams c_det;
 #include "boundary.cuh"
 
 #ifndef PHB_HOST_EMUL  // host: table / parameter upload
@@ -144,6 +153,50 @@ static int upload_phys(phb200_ctx *ctx, const phb200_step *st) {
   p.iremove = c.iremoveStabTimeTerm; p.ipord = c.ipord;
   p.lhs = st->lhs; p.iprec = st->iprec; p.iDC = c.iDC; p.epsM = c.epsM;
   PHB_CHECK(cudaMemcpyToSymbolAsync(c_ph, &p, sizeof p, 0, cudaMemcpyHostToDevice, ctx->stream));
+  DetParams d;
+  d.elc = ctx->deterministic ? ctx->d_elc : nullptr;
+  d.stride = ctx->numel_pad;
+  PHB_CHECK(cudaMemcpyToSymbolAsync(c_det, &d, sizeof d, 0, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int phb_set_deterministic(phb200_ctx *ctx, int on) {
+  if (!on) {
+    ctx->deterministic = false;
+    return 0;
+  }
+  if (!ctx->gen.empty() || ctx->numelb > 0 || !ctx->bgen.empty()) {
+    fprintf(stderr, "phb200: deterministic: supported for parts of linear tets without boundary-element blocks\n");
+    return 1;
+  }
+  PHB_TRY(phb_build_incidence(ctx));
+  if (!ctx->d_elc) PHB_CHECK(cudaMalloc(&ctx->d_elc, sizeof(double) * 120 * ctx->numel_pad));
+  ctx->deterministic = true;
+  return 0;
+}
+
+// Sums the stored element contributions of every node in incidence order: one warp per node, lane = component.
+// Components c < nfirst go to out_a[c][nshg], the rest to out_b[c - nfirst][nshg] (null = skipped).
+__global__ void __launch_bounds__(256) k_node_gather(int nshg, const int *__restrict__ inc_ptr, const int *__restrict__ inc,
+                                                      size_t stride, const double *__restrict__ elc, int NC, int nfirst,
+                                                      double *__restrict__ out_a, double *__restrict__ out_b) {
+  const int node = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5), c = threadIdx.x & 31;
+  if (node >= nshg || c >= NC) return;
+  double s = 0.0;
+  const int k1 = inc_ptr[node + 1];
+  for (int k = inc_ptr[node]; k < k1; k++) {
+    const int ea = __ldg(inc + k);
+    s += __ldcs(elc + (size_t)((ea & 3) * NC + c) * stride + (size_t)(ea >> 2));
+  }
+  if (c < nfirst) out_a[(size_t)nshg * c + node] = s;
+  else if (out_b) out_b[(size_t)nshg * (c - nfirst) + node] = s;
+}
+static int node_gather(phb200_ctx *ctx, int NC, int nfirst, double *out_a, double *out_b) {
+  KScope ks(ctx, KC_NODE);
+  const size_t threads = (size_t)ctx->c.nshg * 32;
+  k_node_gather<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->c.nshg, ctx->d_inc_ptr, ctx->d_inc,
+                                                                            ctx->numel_pad, ctx->d_elc, NC, nfirst, out_a, out_b);
+  PHB_CHECK(cudaGetLastError());
   return 0;
 }
 
@@ -281,6 +334,15 @@ __global__ void __launch_bounds__(128) k_asiq_tet(int numel, size_t numel_pad, i
         for (int m = 0; m < 4; m++) ql[a][4 * i + m] += nw * f[i][m];
       rm[a] += nw;
     }
+  }
+  if (c_det.elc) {  // deterministic option: rows (a,k) of the element buffer, gathered per node afterwards
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+#pragma unroll
+      for (int k = 0; k < 12; k++) c_det.elc[(size_t)(a * 13 + k) * c_det.stride + e] = ql[a][k];
+      c_det.elc[(size_t)(a * 13 + 12) * c_det.stride + e] = rm[a];
+    }
+    return;
   }
 #pragma unroll
   for (int a = 0; a < 4; a++) {
@@ -423,6 +485,13 @@ __device__ __forceinline__ int bc_elim_mask(int ibc) {
   return m;
 }
 
+// One slot of the asynchronous CSR scatter of the warp-specialised kernel: the 32 blocks of a warp-task, entry-major
+// (padded so that both the element-wise writes and the entry-wise reads are conflict-free), and their CSR indices
+struct ScatSlot {
+  double v[25][33];
+  int k[32];
+};
+
 // Tail of AsIGMR for one (a,b) block of one element: BDiag extraction before the BCs (asigmr.f:92-102, SURVEY
 // B3), bc3LHS on the block in registers (bc3lhs.f:1-290; rows by node a's code, columns by node b's), then the
 // coalesced store into the element tile (LHS==1) or the fillsparseC scatter into lhsK (LHS==2).
@@ -435,10 +504,17 @@ __device__ __forceinline__ void finish_block(double (&acc)[5][5], int a, int b, 
   constexpr int ND = 5 * NSHL;
   if (ge < numel) {
     if (a == b && c_ph.iprec != 0) {
+      if (NSHL == 4 && c_det.elc) {
 #pragma unroll
-      for (int m = 0; m < 5; m++)
+        for (int m = 0; m < 5; m++)
 #pragma unroll
-        for (int n = 0; n < 5; n++) atomicAdd(BDiag + (size_t)nshg * (m + 5 * n) + na, acc[m][n]);
+          for (int n = 0; n < 5; n++) c_det.elc[(size_t)(a * 30 + 5 + m + 5 * n) * c_det.stride + ge] = acc[m][n];
+      } else {
+#pragma unroll
+        for (int m = 0; m < 5; m++)
+#pragma unroll
+          for (int n = 0; n < 5; n++) atomicAdd(BDiag + (size_t)nshg * (m + 5 * n) + na, acc[m][n]);
+      }
     }
     if (LHS == 3) return;  // e3bdg (e3.f:258-285): only the block diagonal is wanted, nothing is stored
     if (ibca | ibcb) {
@@ -469,6 +545,45 @@ __device__ __forceinline__ void finish_block(double (&acc)[5][5], int a, int b, 
     }
   }
   if (LHS == 3) return;
+  if (LHS == 4) {
+    // fillsparseC handed to the scatter warps (k_asigmr_tet_ws2): park the block and its CSR index in the ring slot
+    ScatSlot *sl = reinterpret_cast<ScatSlot *>(stage);
+    const int lane = threadIdx.x & 31;
+    sl->k[lane] = (ge < numel) ? eloc[(size_t)(NSHL * a + b) * numel_pad + ge] : -1;
+#pragma unroll
+    for (int n = 0; n < 5; n++)
+#pragma unroll
+      for (int m = 0; m < 5; m++) sl->v[m + 5 * n][lane] = acc[m][n];
+    return;
+  }
+  if (LHS == 5) {
+#if !defined(PHB_HOST_EMUL) && !defined(PHB_HOST_FULL)
+    // fillsparseC through the bulk-copy engine (k_asigmr_tet_ws2): every lane parks its block in its own 208-byte
+    // slice of the warp's stage and hands 24 of the 25 doubles to ONE cp.reduce.async.bulk ... .add.f64 (192 bytes,
+    // 16-byte aligned at both ends: for an odd block index lhsK + 25 k sits 8 bytes off, so the block is parked one
+    // double further in and entries 1..24 go in bulk); the 25th double is a plain red.f64.  The warp does not wait
+    // for the reductions -- only, before it overwrites the stage one task later, for the engine to have READ it.
+    const int lane = threadIdx.x & 31;
+    const int k = (ge < numel) ? eloc[(size_t)(NSHL * a + b) * numel_pad + ge] : -1;
+    double *reg = stage + lane * 26;
+    const int sh = k & 1;
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+#pragma unroll
+    for (int n = 0; n < 5; n++)
+#pragma unroll
+      for (int m = 0; m < 5; m++) reg[sh + m + 5 * n] = acc[m][n];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (k >= 0) {
+      double *dst = lhsK + (size_t)25 * k;
+      const unsigned src = (unsigned)__cvta_generic_to_shared(reg + 2 * sh);
+      asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 192;" ::"l"(dst + sh), "r"(src)
+                   : "memory");
+      atomicAdd(dst + (sh ? 0 : 24), sh ? acc[0][0] : acc[4][4]);
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+#endif
+    return;
+  }
   if (LHS == 2) {
     // fillsparseC (fillsparse.f:66-126): lhsK(f+5g, k) += EGmass(e, r+f, s+g); the block index k
     // comes from the precomputed sparseloc map.  The 32 blocks of the warp are transposed through a
@@ -528,17 +643,14 @@ __device__ __forceinline__ void phase_bprime(const SM &sm, int el, int sub, bool
       }
 }
 
-// phase B: the 5x5 blocks of EGmass; one warp-task per (a,b) pair and 32-element half tile
-template <int TILE_E, int NQ, int LHS, int NWARP, bool DCON = false, class SM>
-__device__ __forceinline__ void phase_b(const SM &sm, int warp, int lane, int tile, int numel,
-                                        size_t numel_pad, int nshg, const int *__restrict__ iBC,
-                                        const double *__restrict__ BC, double *__restrict__ BDiag,
-                                        double *__restrict__ EG, const int *__restrict__ eloc,
-                                        double *__restrict__ lhsK, double *__restrict__ stage) {
-      constexpr int NHALF = TILE_E / 32;
-      constexpr int NPAIR = (LHS == 3) ? 4 : 16;  // LHS==3: the four (a,a) blocks only (e3bdg.f)
-      for (int task = warp; task < NPAIR * NHALF; task += NWARP) {
-        const int pair = (LHS == 3) ? 5 * (task / NHALF) : task / NHALF, half = task % NHALF;
+// phase B, one warp-task: the 5x5 block (a,b) = pair of EGmass for the 32 elements of one half tile
+template <int TILE_E, int NQ, int LHS, bool DCON = false, class SM>
+__device__ __forceinline__ void phase_b_task(const SM &sm, int pair, int half, int lane, int tile, int numel,
+                                             size_t numel_pad, int nshg, const double *__restrict__ BC,
+                                             double *__restrict__ BDiag, double *__restrict__ EG,
+                                             const int *__restrict__ eloc, double *__restrict__ lhsK,
+                                             double *__restrict__ stage) {
+      {
         const int a = pair >> 2, b = pair & 3;
         const int le = half * 32 + lane;
         const int ge = tile * TILE_E + le;
@@ -692,6 +804,22 @@ __device__ __forceinline__ void phase_b(const SM &sm, int warp, int lane, int ti
         }
         finish_block<LHS, 4>(acc, a, b, ge, numel, numel_pad, nshg, sm.nd[a][le], sm.nd[b][le], sm.ibc[a][le],
                              sm.ibc[b][le], BC, BDiag, EG, eloc, lhsK, stage);
+      }
+}
+
+// phase B: one warp-task per (a,b) pair and 32-element half tile, dealt round-robin to the NWARP warps of the CTA
+template <int TILE_E, int NQ, int LHS, int NWARP, bool DCON = false, class SM>
+__device__ __forceinline__ void phase_b(const SM &sm, int warp, int lane, int tile, int numel,
+                                        size_t numel_pad, int nshg, const int *__restrict__ iBC,
+                                        const double *__restrict__ BC, double *__restrict__ BDiag,
+                                        double *__restrict__ EG, const int *__restrict__ eloc,
+                                        double *__restrict__ lhsK, double *__restrict__ stage) {
+      constexpr int NHALF = TILE_E / 32;
+      constexpr int NPAIR = (LHS == 3) ? 4 : 16;  // LHS==3: the four (a,a) blocks only (e3bdg.f)
+      for (int task = warp; task < NPAIR * NHALF; task += NWARP) {
+        const int pair = (LHS == 3) ? 5 * (task / NHALF) : task / NHALF, half = task % NHALF;
+        phase_b_task<TILE_E, NQ, LHS, DCON>(sm, pair, half, lane, tile, numel, numel_pad, nshg, BC, BDiag, EG, eloc, lhsK,
+                                            stage);
       }
 }
 
@@ -1031,6 +1159,235 @@ __global__ void __launch_bounds__(192, 2) k_asigmr_tet_ws(
       if (LHS) phase_b<TILE_E, NQ, LHS, 4>(sm, warp, lane, tile, numel, numel_pad, nshg, iBC, BC, BDiag, EG, eloc, lhsK, stage);
       if (tile + 2 * (int)gridDim.x < ntiles) bar_arrive_named(3 + buf, NTHR);
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// Second generation of the warp-specialised kernel (the one that runs): CTA = 1 producer warp + 5 consumer warps
+// over a ring of WS_NBUF 32-element tiles, shared-memory mbarriers instead of named barriers.
+//  * The producer does everything that is per element or per quadrature point: gathers, metric, gradients, div q,
+//    the point state of all four points -- and the residual (e3wmlt.f:74-145, the old phase B'): it holds ri of
+//    every point in registers anyway, so rl never travels through shared memory and the consumers do nothing but
+//    5x5 block products.
+//  * The 16 (a,b) tasks of a tile are dealt round-robin to the five consumers ACROSS tile boundaries (task number
+//    tile*16 + pair, consumer = task mod 5), so every consumer gets 16 tasks per 5 tiles and none waits for the
+//    slowest one at a tile boundary; a consumer only waits on the `full` barrier of the tile it enters and tells
+//    the `empty` barrier when it has left it.
+// Ten consumer warps per SM instead of eight on the same register file (2 CTAs of 192 threads x 168 registers).
+// ---------------------------------------------------------------------------
+#define WS_NBUF 5
+template <int TILE_E, int NQ>
+struct WsTile {
+  double st[NQ][S_NVAR][TILE_E];
+  double shg[12][TILE_E];
+  double W[TILE_E];
+  int nd[4][TILE_E];
+  int ibc[4][TILE_E];
+};
+#define WS_NSLOT 12
+#define STAGE_BULK_DBL (32 * 26)  // per-consumer stage of the bulk-engine CSR scatter: 32 blocks of 208 bytes
+template <int LHS, int WS_NPROD, int WS_NCONS, int WS_NSCAT = 0>
+__global__ void __launch_bounds__(32 * (WS_NCONS + WS_NPROD + WS_NSCAT), 1) k_asigmr_tet_ws2(
+    int numel, size_t numel_pad, int nshg, int numnp, int ntiles, const int *__restrict__ ien,
+    const double *__restrict__ aos, const int *__restrict__ iBC, const double *__restrict__ BC,
+    double *__restrict__ res, double *__restrict__ BDiag, double *__restrict__ EG, const int *__restrict__ eloc,
+    double *__restrict__ lhsK) {
+  constexpr int NQ = 4, TILE_E = 32;
+  using Tile = WsTile<TILE_E, NQ>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Tile *tiles = reinterpret_cast<Tile *>(smem_raw);
+  unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + WS_NBUF * sizeof(Tile));
+  unsigned long long *empty = full + WS_NBUF;
+  // LHS==2 with scatter warps: ring of WS_NSLOT block slots between the consumers and the scatter warps
+  unsigned long long *sfull = empty + WS_NBUF, *sempty = sfull + WS_NSLOT;
+  ScatSlot *slots = reinterpret_cast<ScatSlot *>(smem_raw + WS_NBUF * sizeof(Tile) +
+                                                 (2 * WS_NBUF + 2 * WS_NSLOT) * sizeof(unsigned long long));
+  constexpr bool ASYNC = (LHS == 2 && WS_NSCAT > 0);
+  constexpr int LHS_B = ASYNC ? 4 : (LHS == 2 ? 5 : LHS);  // CSR: scatter warps (4) or the bulk-copy engine (5)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < WS_NBUF; i++) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], WS_NCONS);
+    }
+    for (int i = 0; i < WS_NSLOT; i++) {
+      mbar_init(&sfull[i], 1);
+      mbar_init(&sempty[i], 1);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (ASYNC && warp >= WS_NCONS + WS_NPROD) {
+    // ------------------------------ scatter warps: fillsparseC (fillsparse.f:66-126) ------------------------------
+    // lane l < 25 adds entry l of every parked block: one warp-wide red.f64 covers the 25 contiguous doubles of a block
+    const int mytiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const long long ntask = (long long)mytiles * 16;
+    for (long long T = warp - (WS_NCONS + WS_NPROD); T < ntask; T += WS_NSCAT) {
+      const int slot = (int)(T % WS_NSLOT);
+      const ScatSlot &sl = slots[slot];
+      mbar_wait(&sfull[slot], (unsigned)((T / WS_NSLOT) & 1));
+      // all 32 values of this lane's entry first (one round trip to shared memory), then 32 reductions back to back
+      const int kk = sl.k[lane];
+      const int l25 = lane < 25 ? lane : 0;
+      double v[32];
+#pragma unroll
+      for (int e = 0; e < 32; e++) v[e] = sl.v[l25][e];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sempty[slot]);  // the slot is in registers: the consumers may refill it
+#pragma unroll
+      for (int e = 0; e < 32; e++) {
+        const int ke = __shfl_sync(0xffffffffu, kk, e);
+        if (ke >= 0 && lane < 25) atomicAdd(lhsK + (size_t)25 * ke + lane, v[e]);
+      }
+    }
+  } else if (warp >= WS_NCONS) {
+    // ------------------------------ producers: whole tiles, dealt round-robin ------------------------------
+    for (int it = warp - WS_NCONS;; it += WS_NPROD) {
+      const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (tile_ll >= ntiles) break;
+      const int tile = (int)tile_ll;
+      const int buf = it % WS_NBUF;
+      Tile &sm = tiles[buf];
+      const int e = tile * TILE_E + lane;
+      const bool live = e < numel;
+      int nd[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) nd[a] = live ? ien[(size_t)a * numel_pad + e] : 0;
+      const double2 *rec[4];
+      double xl[4][3];
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        rec[a] = reinterpret_cast<const double2 *>(aos + (size_t)nd[a] * NREC);
+        const double2 v0 = __ldg(rec[a]), v1 = __ldg(rec[a] + 1);
+        xl[a][0] = v0.x; xl[a][1] = v0.y; xl[a][2] = v1.x;
+      }
+      int ibcn[4];
+#pragma unroll
+      for (int a = 0; a < 4; a++) ibcn[a] = __ldg(iBC + nd[a]);
+      Metric g;
+      tet_metric(xl, c_tet.dN[0], c_tet.Qwt[0], g);
+      double gij[6];
+      tet_gij(g.dxidx, gij);
+      // gradients and div q are constant on the element (e3ivar.f:259-395)
+      double gr[3][5], divq[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int m = 0; m < 5; m++) gr[i][m] = 0.0;
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        const double2 v1 = __ldg(rec[a] + 1), v2 = __ldg(rec[a] + 2), v3 = __ldg(rec[a] + 3);
+        const double yl[5] = {v1.y, v2.x, v2.y, v3.x, v3.y};
+#pragma unroll
+        for (int m = 0; m < 5; m++)
+#pragma unroll
+          for (int i = 0; i < 3; i++) gr[i][m] += g.shg[a][i] * yl[m];
+        if (c_ph.idiff >= 1) {
+          const double2 v6 = __ldg(rec[a] + 6), v7 = __ldg(rec[a] + 7), v8 = __ldg(rec[a] + 8),
+                        v9 = __ldg(rec[a] + 9), v10 = __ldg(rec[a] + 10), v11 = __ldg(rec[a] + 11),
+                        v12 = __ldg(rec[a] + 12);
+          const double ql[12] = {v6.y, v7.x, v7.y, v8.x, v8.y, v9.x, v9.y, v10.x, v10.y, v11.x, v11.y, v12.x};
+#pragma unroll
+          for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int m = 0; m < 4; m++) divq[m] += g.shg[a][i] * ql[4 * i + m];
+        }
+      }
+      if (it >= WS_NBUF) mbar_wait(&empty[buf], ((it / WS_NBUF) - 1) & 1);  // the consumers have left this buffer
+#pragma unroll
+      for (int a = 0; a < 4; a++) {
+        sm.nd[a][lane] = nd[a];
+        sm.ibc[a][lane] = ibcn[a];
+#pragma unroll
+        for (int i = 0; i < 3; i++) sm.shg[3 * a + i][lane] = g.shg[a][i];
+      }
+      sm.W[lane] = g.W;
+      double rl[4][5];
+#pragma unroll
+      for (int a = 0; a < 4; a++)
+#pragma unroll
+        for (int m = 0; m < 5; m++) rl[a][m] = 0.0;
+#pragma unroll 1
+      for (int q = 0; q < NQ; q++) {
+        double Y[5] = {0, 0, 0, 0, 0}, At[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          const double2 v1 = __ldg(rec[a] + 1), v2 = __ldg(rec[a] + 2), v3 = __ldg(rec[a] + 3),
+                        v4 = __ldg(rec[a] + 4), v5 = __ldg(rec[a] + 5), v6 = __ldg(rec[a] + 6);
+          const double yl[5] = {v1.y, v2.x, v2.y, v3.x, v3.y};
+          const double al[5] = {v4.x, v4.y, v5.x, v5.y, v6.x};
+          const double Na = c_tet.N[q][a];
+#pragma unroll
+          for (int m = 0; m < 5; m++) {
+            Y[m] += Na * yl[m];
+            At[m] += Na * al[m];
+          }
+        }
+        double ri[20], st[S_NVAR];
+        point_math(Y, At, gr, divq, gij, ri, st);
+        // e3wmlt.f:74-145: rl = W (N_a,i ri_i) + N_a W ri(16:20), summed over the points in their order
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+          const double Na = c_tet.N[q][a];
+#pragma unroll
+          for (int m = 0; m < 5; m++) {
+            rl[a][m] += g.W * (g.shg[a][0] * ri[m] + g.shg[a][1] * ri[5 + m] + g.shg[a][2] * ri[10 + m]);
+            rl[a][m] += Na * g.W * ri[15 + m];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < S_NVAR; k++) sm.st[q][k][lane] = st[k];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[buf]);
+      if (live) {
+        if (c_det.elc) {
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int m = 0; m < 5; m++) c_det.elc[(size_t)(a * 30 + m) * c_det.stride + e] = rl[a][m];
+        } else {
+#pragma unroll
+          for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int m = 0; m < 5; m++) atomicAdd(res + (size_t)nshg * m + nd[a], rl[a][m]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------ consumers -----------------------------
+    // LHS==2: per-consumer-warp staging tile for the CSR scatter (see finish_block)
+    double *stage = (LHS == 2 && !ASYNC)
+                        ? reinterpret_cast<double *>(smem_raw + WS_NBUF * sizeof(Tile) +
+                                                     (2 * WS_NBUF + 2 * WS_NSLOT) * sizeof(unsigned long long)) +
+                              warp * STAGE_BULK_DBL
+                        : nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+      const int buf = it % WS_NBUF;
+      const Tile &sm = tiles[buf];
+      mbar_wait(&full[buf], (it / WS_NBUF) & 1);
+      // tasks it*16 + pair with (it*16 + pair) % WS_NCONS == warp
+      int pair = (warp - (it * 16) % WS_NCONS + WS_NCONS) % WS_NCONS;
+      for (; pair < 16; pair += WS_NCONS) {
+        if (ASYNC) {
+          const long long T = (long long)it * 16 + pair;
+          const int slot = (int)(T % WS_NSLOT);
+          const long long use = T / WS_NSLOT;
+          if (use > 0) mbar_wait(&sempty[slot], (unsigned)((use - 1) & 1));  // the previous block of this slot is in lhsK
+          phase_b_task<TILE_E, NQ, LHS_B>(sm, pair, 0, lane, tile, numel, numel_pad, nshg, BC, BDiag, EG, eloc, lhsK,
+                                          reinterpret_cast<double *>(slots + slot));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sfull[slot]);
+        } else {
+          phase_b_task<TILE_E, NQ, LHS_B>(sm, pair, 0, lane, tile, numel, numel_pad, nshg, BC, BDiag, EG, eloc, lhsK, stage);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[buf]);
+    }
+    if (LHS_B == 5) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the stage must outlive its readers
   }
 }
 
@@ -2076,9 +2433,52 @@ static int launch_asigmr(phb200_ctx *ctx) {
 template <int LHS>
 static int launch_asigmr_ws(phb200_ctx *ctx) { return launch_asigmr<32, 4, LHS>(ctx); }
 #else
+template <int LHS, int NP, int NC, int NS = 0>
+static int launch_asigmr_ws2(phb200_ctx *ctx) {
+  const phb200_common &c = ctx->c;
+  const size_t smem = WS_NBUF * sizeof(WsTile<32, 4>) + (2 * WS_NBUF + 2 * WS_NSLOT) * sizeof(unsigned long long) +
+                      (LHS == 2 ? (NS > 0 ? WS_NSLOT * sizeof(ScatSlot) : NC * STAGE_BULK_DBL * sizeof(double)) : 0);
+  auto kern = k_asigmr_tet_ws2<LHS, NP, NC, NS>;
+  static bool configured = false;
+  if (!configured) {
+    PHB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int ntiles = (ctx->numel_tet + 31) / 32;
+  int nsm = 148;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+  int grid = nsm;  // one CTA of NP + NC warps per SM (12 warps x 168 registers fill the register file)
+  if (grid > ntiles) grid = ntiles;
+  if (grid < 1) grid = 1;
+  KScope ks(ctx, KC_ASM);
+  kern<<<grid, 32 * (NP + NC + NS), smem, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, c.nshg, c.numnp, ntiles, ctx->d_ien,
+                                                    ctx->d_nodeaos, ctx->d_iBC, ctx->d_BC, ctx->d_res, ctx->d_BDiag,
+                                                    ctx->d_EG, ctx->d_eloc, ctx->d_lhsK);
+  PHB_CHECK(cudaGetLastError());
+  return 0;
+}
 template <int LHS>
 static int launch_asigmr_ws(phb200_ctx *ctx) {
   const phb200_common &c = ctx->c;
+  // PHB200_ASM_WS=1 selects the first generation (2 producer + 4 consumer warps, named barriers) for A/B runs;
+  // PHB200_WS_PROD = producer warps of the second generation (2, 3 or 4 of the 12 warps of a CTA)
+  static const bool gen1 = getenv("PHB200_ASM_WS") && atoi(getenv("PHB200_ASM_WS")) == 1;
+  if (!gen1) {
+    // measured on 4.03 M tets (profiles/r02j): EBE tiles 6.17 / 6.33 / 5.97 ms with 2 / 3 / 4 producers;
+    // CSR scatter by the consumers themselves 8.15 / 8.97 / 9.31 ms.  Defaults: 4 + 8 for the EBE tiles; for the CSR
+    // flavour 2 producers + 8 consumers + 2 scatter warps (PHB200_WS_SCAT=0: consumers scatter, 2 + 10)
+    static const int np = getenv("PHB200_WS_PROD") ? atoi(getenv("PHB200_WS_PROD")) : (LHS == 2 ? 2 : 4);
+    static const int ns = getenv("PHB200_WS_SCAT") ? atoi(getenv("PHB200_WS_SCAT")) : 0;
+    if constexpr (LHS == 2) {
+      if (ns > 0) {
+        if (ns == 3) return launch_asigmr_ws2<LHS, 2, 7, 3>(ctx);
+        return launch_asigmr_ws2<LHS, 2, 8, 2>(ctx);
+      }
+    }
+    if (np == 2) return launch_asigmr_ws2<LHS, 2, 10>(ctx);
+    if (np == 3) return launch_asigmr_ws2<LHS, 3, 9>(ctx);
+    return launch_asigmr_ws2<LHS, 4, 8>(ctx);
+  }
   size_t smem = 2 * sizeof(AsmSmem<32, 4>) + (LHS == 2 ? 4 * STAGE_DBL * sizeof(double) : 0);
   auto kern = k_asigmr_tet_ws<LHS>;
   static bool configured = false;
@@ -2410,6 +2810,7 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
                                         ctx->d_qres, ctx->d_rmass);
       PHB_CHECK(cudaGetLastError());
     }
+    if (ctx->deterministic) PHB_TRY(node_gather(ctx, 13, 12, ctx->d_qres, ctx->d_rmass));
     PHB_TRY(phb_qpbc(ctx));
   } else if (c.idiff != 0) {
     fprintf(stderr, "phb200: elmgmre: idiff=%d not supported (0 or 1)\n", c.idiff);
@@ -2439,6 +2840,13 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
   // mode 3 (matrix-free flavour, itrdrv.f:496-498: lhs=0, iprec per LHSupd): the block diagonal is built
   // directly (e3bdg, e3.f:258-285) = the (a,a) blocks of what EGmass would hold
   const int mode = (st->lhs == 1) ? (sparse ? 2 : 1) : ((st->iprec != 0) ? 3 : 0);
+  if (ctx->deterministic) {
+    const bool gen1 = getenv("PHB200_ASM_WS") && atoi(getenv("PHB200_ASM_WS")) != 2;
+    if (!(mode == 1 || mode == 2) || c.iDC != 0 || nq != 4 || !ctx->tet_uniform_rule || gen1) {
+      fprintf(stderr, "phb200: elmgmr: the deterministic option covers lhs=1 assemblies of 4-point linear tets (iDC=0)\n");
+      return 1;
+    }
+  }
   if (c.iDC != 0) {
     // discontinuity capturing (e3dc.f): built into the phase A/B tet kernel (not the warp-specialised one) and into
     // the hex / wedge kernel
@@ -2480,6 +2888,8 @@ int phb_elmgmre(phb200_ctx *ctx, const phb200_step *st, int sparse) {
     if (g.nshl == 8) PHB_TRY((launch_asigmr_gen_mode<8, 8>(ctx, g, mode)));
     else PHB_TRY((launch_asigmr_gen_mode<6, 6>(ctx, g, mode)));
   }
+  if (ctx->deterministic)  // res / BDiag = the stored element contributions, summed per node in element order
+    PHB_TRY(node_gather(ctx, 30, 5, ctx->d_res, st->iprec != 0 ? ctx->d_BDiag : nullptr));
   if (st->lhs == 1) {
     if (sparse) ctx->have_lhs_sparse = true; else ctx->have_lhs = true;
   }

@@ -179,6 +179,10 @@ struct phb200_ctx {
   std::vector<const int *> h_mien;
   // host-side Hessenberg work (solgmr.f:46-49)
   std::vector<double> HBrg, eBrg, yBrg, Rcos, Rsin;
+  // ---- deterministic assembly option (assembly.cu: per-element contributions + ordered node gather)
+  bool deterministic;
+  double *d_elc;                 // [120][numel_pad]
+  int *d_inc_ptr, *d_inc;        // node -> (element*4 + local node), ascending in the element id
   // ---- instrumentation
   long long launches;
   cudaEvent_t ev[16];
@@ -227,6 +231,8 @@ int phb_zero_slaves(phb200_ctx *ctx, double *d_r, int n, int identity);
 int phb_sumgat_dev(phb200_ctx *ctx, const double *d_u, size_t len, double *out);
 int phb_solve(phb200_ctx *ctx, const phb200_step *st, int sparse, int *iKs, int *lGMRES, int *ntotGM);
 int phb_fp64_peak(phb200_ctx *ctx, double *tflops);
+int phb_dmma_peak(phb200_ctx *ctx, double *tflops);
+int phb_bulkred_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s);
 int phb_red_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s);
 // timestep.cu
 int phb_itrpredict(phb200_ctx *ctx, const phb200_step *st, int ipred);
@@ -251,6 +257,8 @@ void phb_inc_free(phb200_ctx *ctx);
 // sparse.cu
 int phb_set_sparse(phb200_ctx *ctx, const int *colm, const int *rowp, int nnz_tot);
 int phb_genadj(phb200_ctx *ctx, int nnz, int *colm, int *rowp, int *nnz_tot);
+int phb_build_incidence(phb200_ctx *ctx);  // genadj.cu
+int phb_set_deterministic(phb200_ctx *ctx, int on);  // assembly.cu
 int phb_genadj_dev(phb200_ctx *ctx, int **d_colm0, int **d_rowp0, int **d_rob, long long *nnz_tot);  // genadj.cu
 int phb_spsi3pre(phb200_ctx *ctx);
 int phb_sparseap(phb200_ctx *ctx, double *d_u);

@@ -129,3 +129,72 @@ done:
   }
   return rc;
 }
+
+// ---------------------------------------------------------------------------
+// node -> incident (tet, local node) lists, ascending in the element id (the order in which local.f:67-74 adds
+// the element contributions of a block sequence): the deterministic assembly option gathers along them
+// ---------------------------------------------------------------------------
+__global__ void k_inc_keys(int numel, size_t numel_pad, const int *__restrict__ ien, unsigned long long *__restrict__ keys) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)numel * 4) return;
+  const size_t e = t % numel;
+  const int a = (int)(t / numel);
+  keys[t] = ((unsigned long long)ien[(size_t)a * numel_pad + e] << 34) | ((unsigned long long)e << 2) | (unsigned long long)a;
+}
+__global__ void k_inc_split(size_t n, const unsigned long long *__restrict__ keys, int *__restrict__ inc, int *__restrict__ count) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const unsigned long long key = keys[k];
+  inc[k] = (int)(key & ((1ull << 34) - 1ull));
+  atomicAdd(count + (int)(key >> 34), 1);
+}
+int phb_build_incidence(phb200_ctx *ctx) {
+  if (ctx->d_inc) return 0;
+  const int nshg = ctx->c.nshg, numel = ctx->numel_tet;
+  cudaStream_t s = ctx->stream;
+  int rc = 0;
+  if ((size_t)numel * 4 > 2147483647ull || numel >= (1 << 30)) {
+    fprintf(stderr, "phb200: deterministic: more than 2^29 tets per part\n");
+    return 1;
+  }
+  const size_t n = (size_t)numel * 4;
+  int bits = 1;
+  while ((1ll << bits) < (long long)nshg) bits++;
+  unsigned long long *d_keys = nullptr, *d_alt = nullptr;
+  void *d_tmp = nullptr;
+  int *d_cnt = nullptr;
+  size_t tmp_bytes = 0, need = 0;
+  CUB_TRY(cudaMalloc(&d_keys, sizeof(unsigned long long) * (n + 1)));
+  CUB_TRY(cudaMalloc(&d_alt, sizeof(unsigned long long) * (n + 1)));
+  CUB_TRY(cudaMalloc(&ctx->d_inc, sizeof(int) * (n + 1)));
+  CUB_TRY(cudaMalloc(&ctx->d_inc_ptr, sizeof(int) * ((size_t)nshg + 1)));
+  CUB_TRY(cudaMalloc(&d_cnt, sizeof(int) * ((size_t)nshg + 1)));
+  CUB_TRY(cudaMemsetAsync(d_cnt, 0, sizeof(int) * ((size_t)nshg + 1), s));
+  if (n > 0) k_inc_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(numel, ctx->numel_pad, ctx->d_ien, d_keys);
+  {
+    cub::DoubleBuffer<unsigned long long> buf(d_keys, d_alt);
+    CUB_TRY(cub::DeviceRadixSort::SortKeys(nullptr, need, buf, n, 0, 34 + bits, s));
+    tmp_bytes = need;
+    CUB_TRY(cub::DeviceScan::ExclusiveSum(nullptr, need, (int *)nullptr, (int *)nullptr, nshg + 1, s));
+    if (need > tmp_bytes) tmp_bytes = need;
+    CUB_TRY(cudaMalloc(&d_tmp, tmp_bytes));
+    need = tmp_bytes;
+    CUB_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, need, buf, n, 0, 34 + bits, s));
+    if (n > 0) k_inc_split<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, buf.Current(), ctx->d_inc, d_cnt);
+    need = tmp_bytes;
+    CUB_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, need, d_cnt, ctx->d_inc_ptr, nshg + 1, s));
+    ctx->launches += 6;
+  }
+  CUB_TRY(cudaStreamSynchronize(s));
+done:
+  if (d_keys) cudaFree(d_keys);
+  if (d_alt) cudaFree(d_alt);
+  if (d_tmp) cudaFree(d_tmp);
+  if (d_cnt) cudaFree(d_cnt);
+  if (rc) {
+    if (ctx->d_inc) cudaFree(ctx->d_inc);
+    if (ctx->d_inc_ptr) cudaFree(ctx->d_inc_ptr);
+    ctx->d_inc = ctx->d_inc_ptr = nullptr;
+  }
+  return rc;
+}

@@ -856,6 +856,62 @@ __global__ void k_red_peak(double *buf, unsigned nblk, int iters, double v) {
     if (lane < 25) atomicAdd(buf + (size_t)25 * k + lane, v);
   }
 }
+#if !defined(PHB_HOST_EMUL) && !defined(PHB_HOST_FULL)
+// the same scatter through the bulk-copy engine: every lane hands one 208-byte block (26 doubles) of shared memory to
+// cp.reduce.async.bulk ... .add.f64; blocks are 26 doubles apart in the target so that they stay 16-byte aligned
+__global__ void k_bulkred_peak(double *buf, unsigned nblk, int iters, double v) {
+  __shared__ __align__(16) double sh[4][32][26];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int m = 0; m < 26; m++) sh[w][lane][m] = (m < 25) ? v : 0.0;
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  unsigned h = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+  const unsigned src = (unsigned)__cvta_generic_to_shared(&sh[w][lane][0]);
+  for (int i = 0; i < iters; i++) {
+    h = h * 1664525u + 1013904223u;
+    const unsigned k = (h >> 4) % nblk;
+    double *dst = buf + (size_t)26 * k;
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], 208;" ::"l"(dst), "r"(src) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if ((i & 7) == 7) asm volatile("cp.async.bulk.wait_group.read 4;" ::: "memory");
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+#endif
+// mode 1: the bulk-copy engine variant (one 208-byte reduction per lane and iteration)
+int phb_bulkred_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s) {
+#if !defined(PHB_HOST_EMUL) && !defined(PHB_HOST_FULL)
+  if (nblk < 1) return 1;
+  double *buf = nullptr;
+  PHB_CHECK(cudaMalloc(&buf, sizeof(double) * 26 * (size_t)nblk));
+  PHB_CHECK(cudaMemsetAsync(buf, 0, sizeof(double) * 26 * (size_t)nblk, ctx->stream));
+  const int blocks = 148 * 8, threads = 128, iters = 400;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_bulkred_peak<<<blocks, threads, 0, ctx->stream>>>(buf, (unsigned)nblk, 16, 1.0);
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  float best = 1e30f;
+  for (int r = 0; r < 3; r++) {
+    cudaEventRecord(e0, ctx->stream);
+    k_bulkred_peak<<<blocks, threads, 0, ctx->stream>>>(buf, (unsigned)nblk, iters, 1.0);
+    cudaEventRecord(e1, ctx->stream);
+    PHB_CHECK(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  ctx->launches += 4;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  *gadds_per_s = 25.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e9;
+  return 0;
+#else
+  *gadds_per_s = 0.0;
+  return 0;
+#endif
+}
 int phb_red_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s) {
   if (nblk < 1) return 1;
   double *buf = nullptr;
@@ -882,4 +938,53 @@ int phb_red_peak(phb200_ctx *ctx, long long nblk, double *gadds_per_s) {
   cudaFree(buf);
   *gadds_per_s = 25.0 * (double)iters * blocks * (threads / 32) / (best * 1e-3) / 1e9;
   return 0;
+}
+
+// ---------------------------------------------------------------------------
+// FP64 tensor-core (DMMA) peak: mma.sync.m8n8k4.f64, four independent accumulator chains per warp.  The evidence
+// behind the decision to keep the 5x5x5 block products on the FMA pipe: on B200 the DMMA rate is
+// not above the DFMA rate, and a 5-wide operand fills 5/8 of a tile side.
+// ---------------------------------------------------------------------------
+#if !defined(PHB_HOST_EMUL) && !defined(PHB_HOST_FULL)
+__global__ void k_dmma_peak(double *out, int iters, double a, double b) {
+  double c0[2] = {0, 0}, c1[2] = {1, 1}, c2[2] = {2, 2}, c3[2] = {3, 3};
+  const double av = a + threadIdx.x * 1e-9, bv = b;
+  for (int i = 0; i < iters; i++) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0[0]), "+d"(c0[1]) : "d"(av), "d"(bv));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c1[0]), "+d"(c1[1]) : "d"(av), "d"(bv));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c2[0]), "+d"(c2[1]) : "d"(av), "d"(bv));
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c3[0]), "+d"(c3[1]) : "d"(av), "d"(bv));
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0[0] + c0[1] + c1[0] + c1[1] + c2[0] + c2[1] + c3[0] + c3[1];
+}
+#endif
+int phb_dmma_peak(phb200_ctx *ctx, double *tflops) {
+#if !defined(PHB_HOST_EMUL) && !defined(PHB_HOST_FULL)
+  const int blocks = 148 * 8, threads = 256, iters = 20000;
+  if (ctx->scratch_bytes < sizeof(double) * blocks * threads) return 1;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  k_dmma_peak<<<blocks, threads, 0, ctx->stream>>>(ctx->d_scratch, 1000, 0.999999, 1e-7);
+  float best = 1e30f;
+  for (int r = 0; r < 3; r++) {
+    cudaEventRecord(e0, ctx->stream);
+    k_dmma_peak<<<blocks, threads, 0, ctx->stream>>>(ctx->d_scratch, iters, 0.999999, 1e-7);
+    cudaEventRecord(e1, ctx->stream);
+    PHB_CHECK(cudaEventSynchronize(e1));
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (ms < best) best = ms;
+  }
+  ctx->launches += 4;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  // one m8n8k4 = 8*8*4 multiply-adds per warp
+  const double flops = 2.0 * 256.0 * 4.0 * (double)iters * blocks * (threads / 32);
+  *tflops = flops / (best * 1e-3) / 1e12;
+  return 0;
+#else
+  *tflops = 0.0;
+  return 0;
+#endif
 }

@@ -6,6 +6,7 @@
 // common/fillsparse.f:66-126,236-271, compressible/spsi3pre.f:41-221,
 // compressible/sparseap.f:26-135.
 #include "ctx.h"
+#include "mbar.cuh"
 #include <algorithm>
 #include <cstring>
 
@@ -97,6 +98,10 @@ int phb_genadj_dev(phb200_ctx *ctx, int **d_colm0, int **d_rowp0, int **d_rob, l
     }
   *nnz_tot = ntot;
   return 0;
+}
+int phb_build_incidence(phb200_ctx *) {
+  fprintf(stderr, "phb200: deterministic: not available under host emulation\n");
+  return 1;
 }
 #endif
 
@@ -390,40 +395,6 @@ __global__ void __launch_bounds__(256) k_sparseap(int nshg, const int *__restric
 // finds its stage empty moves on to the next one, so there is no tail at chunk boundaries.
 // Copies start / end on multiples of 4 CSR entries (16-byte rule of the bulk copy; the arrays are padded).
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-  // bounded: a protocol error becomes a launch failure (reported by the next CUDA call), not a hung GPU
-  for (long long spins = 0;; spins++) {
-    unsigned ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, P1;\n"
-        "}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (spins > (1ll << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
 struct ApStage {
   double a[25 * (AP_CB + 16)];   // + alignment slack (3 + 3) and the over-read of the last 16-wide batch
   int col[AP_CB + 16];

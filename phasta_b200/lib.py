@@ -71,7 +71,7 @@ SYMBOLS = [
     "phb200_dev_solve", "phb200_dev_ap", "phb200_get_res", "phb200_get_dy", "phb200_get_bdiag",
     "phb200_get_egmass", "phb200_get_egmass_range", "phb200_get_lhsk_range", "phb200_get_aerfrc", "phb200_event_record", "phb200_event_elapsed_ms", "phb200_sync",
     "phb200_launch_count", "phb200_profile", "phb200_profile_get", "phb200_profile_reset",
-    "phb200_fp64_peak", "phb200_red_peak", "phb200_flush_l2", "phb200_version", "phb200_sizeof_common",
+    "phb200_set_deterministic", "phb200_fp64_peak", "phb200_dmma_peak", "phb200_red_peak", "phb200_flush_l2", "phb200_version", "phb200_sizeof_common",
     "phb200_sizeof_step", "phb200_local_group_join", "phb200_genadj", "phb200_set_sparse",
     "phb200_elmgmrs", "phb200_spsi3pre", "phb200_sparseap", "phb200_solgmrs", "phb200_dev_elmgmrs",
     "phb200_dev_solve_sparse", "phb200_dev_sparseap",

@@ -493,6 +493,15 @@ class PhastaGPU:
         _chk(self.L.phb200_fp64_peak(self.ctx, C.byref(t)), "fp64_peak")
         return t.value
 
+    def set_deterministic(self, on=True):
+        """ordered gather instead of FP64 atomics for qres / res / BDiag (lhs=1 assemblies of linear tets)"""
+        _chk(self.L.phb200_set_deterministic(self.ctx, int(bool(on))), "set_deterministic")
+
+    def dmma_peak(self):
+        t = C.c_double(0)
+        _chk(self.L.phb200_dmma_peak(self.ctx, C.byref(t)), "dmma_peak")
+        return t.value
+
     def red_peak(self, nblk):
         """G FP64 scatter-adds per second into nblk random 25-double blocks (microbenchmark)"""
         t = C.c_double(0)
