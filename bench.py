@@ -878,7 +878,7 @@ def main():
         all_tets = len(WORKLOADS[args.workload]) == 3
         # reference-equivalent flops of the dominant kernel alone (the AsIq pre-pass runs in k_asiq_tet)
         tf = elem_per_launch * FLOP_PER_ELEM_KERNEL / (kern_ms * 1e-3) / 1e12 if all_tets else None
-        roof = {"bound": "fp64", "kernel": "k_asigmr_tet_ws<1> (FP64 FMA pipe, not tensor cores; DESIGN 4.1d)",
+        roof = {"bound": "fp64", "kernel": "k_asigmr_tet_ws2<1,4,8> (FP64 FMA pipe, not tensor cores; DESIGN 4.1f)",
                 "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": (tf / fp64_peak) if (fp64_peak and all_tets) else None,
                 "traffic": tr_asm and tr_asm["bytes_per_launch"], "traffic_source": tr_asm and tr_asm["source"],

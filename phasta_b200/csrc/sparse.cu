@@ -395,28 +395,36 @@ __global__ void __launch_bounds__(256) k_sparseap(int nshg, const int *__restric
 // finds its stage empty moves on to the next one, so there is no tail at chunk boundaries.
 // Copies start / end on multiples of 4 CSR entries (16-byte rule of the bulk copy; the arrays are padded).
 // ---------------------------------------------------------------------------
+// STAGEA = true: blocks, column ids and row pointers are staged; false: only the indices (4 bytes per block) are, and
+// the consumers stream the blocks themselves -- their addresses come from shared memory, so the loads of a whole
+// batch of blocks and of the matching entries of p leave together, and the L1 sees every matrix byte once, not twice.
+template <bool STAGEA>
 struct ApStage {
-  double a[25 * (AP_CB + 16)];   // + alignment slack (3 + 3) and the over-read of the last 16-wide batch
+  double a[STAGEA ? 25 * (AP_CB + 16) : 2];   // + alignment slack (3 + 3) and the over-read of the last batch
   int col[AP_CB + 16];
   int rowptr[AP_CR + 8];
 };
+template <bool STAGEA>
 struct ApSmem {
-  ApStage st[AP_STAGES];
-  unsigned long long full[AP_STAGES], empty[AP_STAGES];
-  int next_row[AP_STAGES];
-  int r0[AP_STAGES], r1[AP_STAGES], direct[AP_STAGES];  // the chunk a stage holds (written by the producer)
+  static constexpr int NST = STAGEA ? AP_STAGES : 6;
+  ApStage<STAGEA> st[NST];
+  unsigned long long full[NST], empty[NST];
+  int next_row[NST];
+  int r0[NST], r1[NST], direct[NST];  // the chunk a stage holds (written by the producer)
 };
 
+template <bool STAGEA>
 __global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
     k_sparseap_tma(int nshg, int nchunk, const int *__restrict__ chunk, const int *__restrict__ colm,
                    const int *__restrict__ rowp, const double *__restrict__ lhsK, const double *__restrict__ p,
                    double *__restrict__ q, const int *__restrict__ skip) {
   extern __shared__ __align__(128) unsigned char ap_smem_raw[];
-  ApSmem &S = *reinterpret_cast<ApSmem *>(ap_smem_raw);
+  ApSmem<STAGEA> &S = *reinterpret_cast<ApSmem<STAGEA> *>(ap_smem_raw);
+  constexpr int AP_STAGES_ = ApSmem<STAGEA>::NST;
   if (skip && *skip) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < AP_STAGES; i++) {
+    for (int i = 0; i < AP_STAGES_; i++) {
       mbar_init(&S.full[i], 1);
       mbar_init(&S.empty[i], AP_WARPS);
       S.next_row[i] = 0;
@@ -429,8 +437,8 @@ __global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
     if (lane == 0) {
       int it = 0;
       for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
-        const int stg = it % AP_STAGES;
-        if (it >= AP_STAGES) mbar_wait(&S.empty[stg], ((it / AP_STAGES) - 1) & 1);
+        const int stg = it % AP_STAGES_;
+        if (it >= AP_STAGES_) mbar_wait(&S.empty[stg], ((it / AP_STAGES_) - 1) & 1);
         const int r0 = chunk[c], r1 = chunk[c + 1];
         const int k0 = colm[r0], k1 = colm[r1];
         S.next_row[stg] = 0;
@@ -443,8 +451,8 @@ __global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
         }
         const int ka = k0 & ~3, kb = (k1 + 3) & ~3, ra = r0 & ~3, rb = (r1 + 1 + 3) & ~3;
         const unsigned ba = (unsigned)(kb - ka) * 200u, bc = (unsigned)(kb - ka) * 4u, br = (unsigned)(rb - ra) * 4u;
-        mbar_expect_tx(&S.full[stg], ba + bc + br);
-        bulk_g2s(S.st[stg].a, lhsK + (size_t)25 * ka, ba, &S.full[stg]);
+        mbar_expect_tx(&S.full[stg], (STAGEA ? ba : 0u) + bc + br);
+        if (STAGEA) bulk_g2s(S.st[stg].a, lhsK + (size_t)25 * ka, ba, &S.full[stg]);
         bulk_g2s(S.st[stg].col, rowp + ka, bc, &S.full[stg]);
         bulk_g2s(S.st[stg].rowptr, colm + ra, br, &S.full[stg]);
       }
@@ -457,9 +465,9 @@ __global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
   const double *__restrict__ pg = p + (size_t)nshg * (l / 5);
   int it = 0;
   for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
-    const int stg = it % AP_STAGES;
-    const ApStage &T = S.st[stg];
-    mbar_wait(&S.full[stg], (it / AP_STAGES) & 1);
+    const int stg = it % AP_STAGES_;
+    const ApStage<STAGEA> &T = S.st[stg];
+    mbar_wait(&S.full[stg], (it / AP_STAGES_) & 1);
     const int r0 = S.r0[stg], r1 = S.r1[stg];
     const int ra = r0 & ~3;
     const bool direct = S.direct[stg] != 0;
@@ -476,17 +484,36 @@ __global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
         for (int k = k0; k < k1; k++) acc0 += __ldcs(lhsK + (size_t)25 * k + l) * __ldg(pg + __ldg(rowp + k));
       } else {
         const int k0 = T.rowptr[r - ra], k1 = T.rowptr[r - ra + 1];
-        const double *a = T.a + 25 * (k0 - ka) + l;
         const int *cj = T.col + (k0 - ka);
-        // sixteen gathers of p in flight per lane: a typical row (15 blocks) is one round trip to L2
-        for (int k = k0; k < k1; k += 16, a += 400, cj += 16) {
-          double pv[16];
+        if (STAGEA) {
+          const double *a = T.a + 25 * (k0 - ka) + l;
+          // sixteen gathers of p in flight per lane: a typical row (15 blocks) is one round trip to L2
+          for (int k = k0; k < k1; k += 16, a += 400, cj += 16) {
+            double pv[16];
 #pragma unroll
-          for (int i = 0; i < 16; i++) pv[i] = __ldg(pg + ((k + i < k1) ? cj[i] : r));
+            for (int i = 0; i < 16; i++) pv[i] = __ldg(pg + ((k + i < k1) ? cj[i] : r));
 #pragma unroll
-          for (int i = 0; i < 16; i += 2) {
-            acc0 += ((k + i < k1) ? a[25 * i] : 0.0) * pv[i];
-            acc1 += ((k + i + 1 < k1) ? a[25 * (i + 1)] : 0.0) * pv[i + 1];
+            for (int i = 0; i < 16; i += 2) {
+              acc0 += ((k + i < k1) ? a[25 * i] : 0.0) * pv[i];
+              acc1 += ((k + i + 1 < k1) ? a[25 * (i + 1)] : 0.0) * pv[i + 1];
+            }
+          }
+        } else {
+          const double *a = lhsK + (size_t)25 * k0 + l;
+          // eight blocks and their entries of p in flight per lane, no load waits for another one
+          for (int k = k0; k < k1; k += 8, a += 200, cj += 8) {
+            double av[8], pv[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+              const bool ok = k + i < k1;
+              av[i] = ok ? __ldcs(a + 25 * i) : 0.0;
+              pv[i] = __ldg(pg + (ok ? cj[i] : r));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              acc0 += av[i] * pv[i];
+              acc1 += av[i + 1] * pv[i + 1];
+            }
           }
         }
       }
@@ -530,15 +557,24 @@ int phb_sparseap2(phb200_ctx *ctx, double *d_p, double *d_out, const int *d_skip
     KScope ks(ctx, KC_AP);
 #if !defined(PHB_HOST_EMUL) && !defined(PHB_HOST_FULL)
     static bool attr_set = false;
+    // PHB200_AP_STAGEA=1: also the blocks go through shared memory (A/B runs; measured equal within 2 %)
+    static const bool stage_a = getenv("PHB200_AP_STAGEA") && atoi(getenv("PHB200_AP_STAGEA")) == 1;
     if (!attr_set) {
-      PHB_CHECK(cudaFuncSetAttribute(k_sparseap_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ApSmem)));
+      PHB_CHECK(cudaFuncSetAttribute(k_sparseap_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(ApSmem<true>)));
+      PHB_CHECK(cudaFuncSetAttribute(k_sparseap_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(ApSmem<false>)));
       attr_set = true;
     }
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     const int grid = std::min(ctx->n_apchunk, nsm * AP_CTAS);
-    k_sparseap_tma<<<grid, 32 * (AP_WARPS + 1), sizeof(ApSmem), s>>>(nshg, ctx->n_apchunk, ctx->d_apchunk, ctx->d_colm,
-                                                                     ctx->d_rowp, ctx->d_lhsK, d_p, d_out, d_skip);
+    if (stage_a)
+      k_sparseap_tma<true><<<grid, 32 * (AP_WARPS + 1), sizeof(ApSmem<true>), s>>>(
+          nshg, ctx->n_apchunk, ctx->d_apchunk, ctx->d_colm, ctx->d_rowp, ctx->d_lhsK, d_p, d_out, d_skip);
+    else
+      k_sparseap_tma<false><<<grid, 32 * (AP_WARPS + 1), sizeof(ApSmem<false>), s>>>(
+          nshg, ctx->n_apchunk, ctx->d_apchunk, ctx->d_colm, ctx->d_rowp, ctx->d_lhsK, d_p, d_out, d_skip);
 #else
     size_t threads = (size_t)nshg * 32;
     k_sparseap<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(nshg, ctx->d_colm, ctx->d_rowp, ctx->d_lhsK, d_p,
