@@ -212,7 +212,7 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   ctx->d_yold = ctx->d_acold = nullptr;
   ctx->d_mfg = nullptr;
   ctx->d_mail = nullptr; ctx->d_peer_mail = nullptr; ctx->d_ticket = nullptr; ctx->d_p2p_err = nullptr;
-  ctx->p2p = false; ctx->p2p_seq = 0; ctx->p2p_halo = false; ctx->d_halo_tickets = nullptr;
+  ctx->p2p = false; ctx->p2p_seq = 0;
   for (int r = 0; r < 64; r++) ctx->peer_mapped[r] = nullptr;
   ctx->d_res4 = ctx->d_lhsK9 = ctx->d_lhsP4 = ctx->d_lesp = ctx->d_lesq = ctx->d_lesp4 = nullptr;
   ctx->d_tpos = nullptr;

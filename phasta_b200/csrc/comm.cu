@@ -180,33 +180,6 @@ __global__ void k_halo_unpack(int count, const int *__restrict__ nodes, int nshg
   *p = add ? (*p + buf[t]) : buf[t];
 }
 
-#include "halo_p2p.cuh"  // k_halo_send / k_halo_recv: halo exchange by direct peer stores over NVLink
-
-static int commu_p2p(phb200_ctx *ctx, double *g, int n, int code) {
-  cudaStream_t s = ctx->stream;
-  const int nshg = ctx->c.nshg, me = ctx->c.myrank;
-  const int send_role = (code == 0) ? 0 : 1;
-  auto arena = [&](int r) { return r == me ? ctx->d_mail : (double *)ctx->peer_mapped[r]; };
-  const PhbArena A = phb_arena_layout(ctx->halo_cap);
-  KScope ks(ctx, KC_HALO);
-  for (size_t ti = 0; ti < ctx->tasks.size(); ti++) {
-    HaloTask &h = ctx->tasks[ti];
-    if (h.iacc != send_role || h.count * n == 0) continue;
-    const PhbHaloMsg m = phb_p2p_send_msg(h, ti, n, ctx->d_mail, arena(h.peer), A);
-    k_halo_send<<<(m.tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g, m.data, m.flag,
-                                                    m.ack, m.msg, ctx->d_halo_tickets + ti, ctx->d_p2p_err);
-  }
-  for (size_t ti = 0; ti < ctx->tasks.size(); ti++) {
-    HaloTask &h = ctx->tasks[ti];
-    if (h.iacc == send_role || h.count * n == 0) continue;
-    const PhbHaloMsg m = phb_p2p_recv_msg(h, ti, n, ctx->d_mail, arena(h.peer), A, ctx->halo_cap);
-    k_halo_recv<<<(m.tot + 255) / 256, 256, 0, s>>>(h.count, ctx->d_halo_nodes + h.offset, nshg, n, g, m.data, m.flag,
-                                                    m.ack, m.msg, code == 0, ctx->d_halo_tickets + ti, ctx->d_p2p_err);
-  }
-  PHB_CHECK(cudaGetLastError());
-  return 0;
-}
-
 int phb_commu(phb200_ctx *ctx, double *g, int n, int code) {
   if (ctx->c.numpe <= 1 || ctx->tasks.empty()) return 0;
   if (!ctx->nccl && !ctx->local_group) {
@@ -217,7 +190,6 @@ int phb_commu(phb200_ctx *ctx, double *g, int n, int code) {
     fprintf(stderr, "phb200: commu: n=%d > 25 unsupported\n", n);
     return 1;
   }
-  if (ctx->p2p_halo) return commu_p2p(ctx, g, n, code);
   cudaStream_t s = ctx->stream;
   const int nshg = ctx->c.nshg;
   // sender role: iacc==0 on 'in', iacc==1 on 'out'
@@ -301,14 +273,7 @@ int phb_p2p_check(phb200_ctx *ctx) {
   PHB_CHECK(cudaMemcpyAsync(&e, ctx->d_p2p_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PHB_CHECK(cudaStreamSynchronize(ctx->stream));
   if (e) {
-    // codes written by the device: 1..PHB_MAXR = all-reduce lane waiting for rank e-1; 100 = a halo sender
-    // waiting for the receiver's acknowledgement; 200 = a halo receiver waiting for the sender's flag
-    if (e == 200)
-      fprintf(stderr, "phb200: peer halo receive timed out waiting for a sender's flag\n");
-    else if (e == 100)
-      fprintf(stderr, "phb200: peer halo send timed out waiting for a receiver's acknowledgement\n");
-    else
-      fprintf(stderr, "phb200: peer all-reduce timed out waiting for rank %d\n", e - 1);
+    fprintf(stderr, "phb200: peer all-reduce timed out waiting for rank %d\n", e - 1);
     return 1;
   }
   return 0;
@@ -345,38 +310,40 @@ int phb_allreduce_sum(phb200_ctx *ctx, double *d_vals, int n) {
   return 1;
 }
 
-// map every rank's mailbox into this process (handles travel through one ncclAllGather)
+// map every rank's mailbox into this process (handles travel through one ncclAllGather).
+// Every rank takes part in the same collectives whatever happens locally: a failure (no IPC handle, a mapping that
+// does not open) only lowers this rank's vote, and the unanimous all-reduce at the end decides for everybody, so no
+// rank is left waiting in a collective another one has skipped.  On "no" everything allocated here is released and
+// the small all-reduces stay on NCCL.
 static int p2p_setup(phb200_ctx *ctx) {
   const int world = ctx->c.numpe, me = ctx->c.myrank;
   ctx->p2p = false;
   const char *env = getenv("PHB200_P2P");
   if (env && atoi(env) == 0) return 0;
   if (world > PHB_MAXR) return 0;
-  // one peer-visible arena: all-reduce mailbox | halo flags [64][2] | halo acks [64] | halo data [2][halo_cap].
-  // The offsets are the same on every rank (a rank addresses its PEERS' arenas with them); only the data slot
-  // stride (the peer's halo_cap) differs per rank and travels in the task table.
-  const size_t ntask = ctx->tasks.size();
-  const PhbArena A = phb_arena_layout(ctx->halo_cap);
-  ctx->arena_flag_off = A.flag_off;
-  ctx->arena_ack_off = A.ack_off;
-  ctx->arena_data_off = A.data_off;
-  const size_t mail_dbl = A.total;
-  PHB_CHECK(cudaMalloc(&ctx->d_mail, sizeof(double) * mail_dbl));
-  PHB_CHECK(cudaMemset(ctx->d_mail, 0, sizeof(double) * mail_dbl));
-  PHB_CHECK(cudaMalloc(&ctx->d_halo_tickets, sizeof(unsigned int) * (ntask + 1)));
-  PHB_CHECK(cudaMemset(ctx->d_halo_tickets, 0, sizeof(unsigned int) * (ntask + 1)));
-  PHB_CHECK(cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)));
-  PHB_CHECK(cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int)));
-  PHB_CHECK(cudaMalloc(&ctx->d_p2p_err, sizeof(int)));
-  PHB_CHECK(cudaMemset(ctx->d_p2p_err, 0, sizeof(int)));
+  const size_t mail_dbl = phb_mailbox_doubles();
+  int ok = 1;
   cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  unsigned char *d_h = nullptr;
+  double *d_ok = nullptr;
+  ok &= cudaMalloc(&ctx->d_mail, sizeof(double) * mail_dbl) == cudaSuccess;
+  ok &= cudaMalloc(&ctx->d_ticket, sizeof(unsigned int)) == cudaSuccess;
+  ok &= cudaMalloc(&ctx->d_p2p_err, sizeof(int)) == cudaSuccess;
+  ok &= cudaMalloc(&d_h, (size_t)(world + 1) * sizeof(mine)) == cudaSuccess;
+  ok &= cudaMalloc(&d_ok, sizeof(double)) == cudaSuccess;
+  if (!ok) {  // out of device memory: nothing collective can be attempted at all
+    cudaGetLastError();
+    fprintf(stderr, "phb200: comm_init: cannot allocate the peer mailbox\n");
+    return 1;
+  }
+  cudaMemset(ctx->d_mail, 0, sizeof(double) * mail_dbl);
+  cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int));
+  cudaMemset(ctx->d_p2p_err, 0, sizeof(int));
   if (cudaIpcGetMemHandle(&mine, ctx->d_mail) != cudaSuccess) {
     cudaGetLastError();
-    fprintf(stderr, "phb200: comm_init: cudaIpcGetMemHandle failed; small all-reduces stay on NCCL\n");
-    return 0;
+    ok = 0;
   }
-  unsigned char *d_h;
-  PHB_CHECK(cudaMalloc(&d_h, (size_t)(world + 1) * sizeof(mine)));
   PHB_CHECK(cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice));
   NCCL_CHECK(N.AllGather(d_h, d_h + sizeof(mine), sizeof(mine), /*ncclInt8*/ 0, (ncclComm_t)ctx->nccl, ctx->stream));
   std::vector<cudaIpcMemHandle_t> all(world);
@@ -384,24 +351,31 @@ static int p2p_setup(phb200_ctx *ctx) {
                             ctx->stream));
   PHB_CHECK(cudaStreamSynchronize(ctx->stream));
   cudaFree(d_h);
-  std::vector<double *> ptrs(world, nullptr);
-  int ok = 1;
-  for (int r = 0; r < world; r++) {
-    ctx->peer_mapped[r] = nullptr;
-    if (r == me) { ptrs[r] = ctx->d_mail; continue; }
-    void *p = nullptr;
-    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-      cudaGetLastError();
-      ok = 0;
-      break;
-    }
-    ctx->peer_mapped[r] = p;
-    ptrs[r] = (double *)p;
-  }
-  // every rank must take the same decision: agree through one NCCL all-reduce (min)
-  double *d_ok;
-  PHB_CHECK(cudaMalloc(&d_ok, sizeof(double)));
+  // a rank that got no handle votes "no" first, so that nobody tries to open its (zeroed) handle
   double okd = ok ? 0.0 : 1.0;
+  PHB_CHECK(cudaMemcpy(d_ok, &okd, sizeof(double), cudaMemcpyHostToDevice));
+  NCCL_CHECK(N.AllReduce(d_ok, d_ok, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
+  PHB_CHECK(cudaMemcpyAsync(&okd, d_ok, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
+  std::vector<double *> ptrs(world, nullptr);
+  if (okd == 0.0) {
+    for (int r = 0; r < world; r++) {
+      ctx->peer_mapped[r] = nullptr;
+      if (r == me) { ptrs[r] = ctx->d_mail; continue; }
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        break;
+      }
+      ctx->peer_mapped[r] = p;
+      ptrs[r] = (double *)p;
+    }
+  } else {
+    ok = 0;
+  }
+  // every rank must take the same decision: agree through one NCCL all-reduce
+  okd = ok ? 0.0 : 1.0;
   PHB_CHECK(cudaMemcpy(d_ok, &okd, sizeof(double), cudaMemcpyHostToDevice));
   NCCL_CHECK(N.AllReduce(d_ok, d_ok, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
   PHB_CHECK(cudaMemcpyAsync(&okd, d_ok, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -409,42 +383,16 @@ static int p2p_setup(phb200_ctx *ctx) {
   cudaFree(d_ok);
   if (okd != 0.0) {
     if (me == 0) fprintf(stderr, "phb200: comm_init: peer mapping unavailable on %d rank(s); small all-reduces stay on NCCL\n", (int)okd);
+    for (int r = 0; r < world && r < 64; r++)
+      if (ctx->peer_mapped[r]) { cudaIpcCloseMemHandle(ctx->peer_mapped[r]); ctx->peer_mapped[r] = nullptr; }
+    cudaFree(ctx->d_mail); cudaFree(ctx->d_ticket); cudaFree(ctx->d_p2p_err);
+    ctx->d_mail = nullptr; ctx->d_ticket = nullptr; ctx->d_p2p_err = nullptr;
     return 0;
   }
   PHB_CHECK(cudaMalloc(&ctx->d_peer_mail, sizeof(double *) * world));
   PHB_CHECK(cudaMemcpy(ctx->d_peer_mail, ptrs.data(), sizeof(double *) * world, cudaMemcpyHostToDevice));
   ctx->p2p_seq = 0;
   ctx->p2p = true;
-  // ---- halo over peer memory: every rank publishes its task table (tag, iacc, peer, offset, count) ----
-  ctx->p2p_halo = false;
-  // Opt-in (PHB200_P2P_HALO=1): validated on 2 GPUs (r01h); the first 8-GPU attempt addressed peers' arenas with
-  // this rank's own task count (fixed above) and could not be re-measured within the round's GPU budget.
-  const char *envh = getenv("PHB200_P2P_HALO");
-  if (!envh || atoi(envh) == 0) return 0;
-  const int W = PHB_P2P_W;
-  std::vector<int> mytab(W, 0), alltab((size_t)W * world, 0);
-  phb_p2p_mytab(ctx->tasks, ctx->halo_cap, mytab.data());
-  int *d_tab;
-  PHB_CHECK(cudaMalloc(&d_tab, sizeof(int) * (size_t)W * (world + 1)));
-  PHB_CHECK(cudaMemcpy(d_tab, mytab.data(), sizeof(int) * W, cudaMemcpyHostToDevice));
-  NCCL_CHECK(N.AllGather(d_tab, d_tab + W, sizeof(int) * W, /*ncclInt8*/ 0, (ncclComm_t)ctx->nccl, ctx->stream));
-  PHB_CHECK(cudaMemcpyAsync(alltab.data(), d_tab + W, sizeof(int) * (size_t)W * world, cudaMemcpyDeviceToHost,
-                            ctx->stream));
-  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_tab);
-  const bool good = phb_p2p_pair(me, world, alltab.data(), ctx->tasks);
-  // unanimous decision (a rank whose table does not match would otherwise wait forever)
-  double *d_g;
-  PHB_CHECK(cudaMalloc(&d_g, sizeof(double)));
-  double bad = good ? 0.0 : 1.0;
-  PHB_CHECK(cudaMemcpy(d_g, &bad, sizeof(double), cudaMemcpyHostToDevice));
-  NCCL_CHECK(N.AllReduce(d_g, d_g, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream));
-  PHB_CHECK(cudaMemcpyAsync(&bad, d_g, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  PHB_CHECK(cudaStreamSynchronize(ctx->stream));
-  cudaFree(d_g);
-  ctx->p2p_halo = (bad == 0.0);
-  if (!ctx->p2p_halo && me == 0)
-    fprintf(stderr, "phb200: comm_init: halo task tables do not pair up on %d rank(s); halos stay on NCCL\n", (int)bad);
   return 0;
 }
 
@@ -471,17 +419,8 @@ int phb_comm_init(phb200_ctx *ctx, const void *id128) {
 
 void phb_comm_free(phb200_ctx *ctx) {
   if (ctx->p2p) {
-    // peers may still be storing acknowledgements into this rank's arena: everybody drains, then everybody frees
+    // drain this rank.s stream before the peers. mappings of its mailbox go away
     cudaStreamSynchronize(ctx->stream);
-    if (ctx->p2p_halo && ctx->nccl && N.AllReduce && ctx->d_p2p_err) {
-      double *d_b = nullptr;
-      if (cudaMalloc(&d_b, sizeof(double)) == cudaSuccess) {
-        cudaMemsetAsync(d_b, 0, sizeof(double), ctx->stream);
-        N.AllReduce(d_b, d_b, 1, ncclFloat64, ncclSum, (ncclComm_t)ctx->nccl, ctx->stream);
-        cudaStreamSynchronize(ctx->stream);
-        cudaFree(d_b);
-      }
-    }
     for (int r = 0; r < ctx->c.numpe && r < 64; r++)
       if (ctx->peer_mapped[r]) cudaIpcCloseMemHandle(ctx->peer_mapped[r]);
     ctx->p2p = false;
@@ -489,9 +428,6 @@ void phb_comm_free(phb200_ctx *ctx) {
   if (ctx->d_mail) cudaFree(ctx->d_mail);
   if (ctx->d_peer_mail) cudaFree(ctx->d_peer_mail);
   if (ctx->d_ticket) cudaFree(ctx->d_ticket);
-  if (ctx->d_halo_tickets) cudaFree(ctx->d_halo_tickets);
-  ctx->d_halo_tickets = nullptr;
-  ctx->p2p_halo = false;
   if (ctx->d_p2p_err) cudaFree(ctx->d_p2p_err);
   ctx->d_mail = nullptr; ctx->d_peer_mail = nullptr; ctx->d_ticket = nullptr; ctx->d_p2p_err = nullptr;
   if (ctx->nccl && N.CommDestroy) N.CommDestroy((ncclComm_t)ctx->nccl);

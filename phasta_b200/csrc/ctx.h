@@ -125,9 +125,6 @@ struct phb200_ctx {
   unsigned int *d_ticket;     // last-block detection for the fused reduction kernels
   int *d_p2p_err;             // set by a kernel whose wait on a peer flag timed out
   bool p2p;
-  bool p2p_halo;              // halo exchange by direct peer stores too (k_halo_send / k_halo_recv)
-  size_t arena_flag_off, arena_ack_off, arena_data_off;  // doubles from the arena base (mailbox first)
-  unsigned int *d_halo_tickets;   // one last-block counter per task
   bool local_group;    // in-process multi-part transport (tests)
   // ---- state / results
   double *d_y, *d_ac;            // [5][nshg] {u,v,w,p,T}
