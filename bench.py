@@ -711,20 +711,22 @@ def side_workload(env, args, name, params, tables, init_comm, steps):
         except Exception as e:
             par = {"ok": False, "error": repr(e)[:200]}
     r = time_workload(env, g, part, steps, 3, residual_only=False)
-    if isinstance(par, dict) and "sparse" in r and "error" not in par:
-        # the block-CSR flavour of the same part: lhsK blocks and CSR rows against the oracle's, and the two solvers
-        # (independent operators on the device) must need the same number of iterations
-        try:
-            from oracle.spot_check import slab_check
-            ny, nz = WORKLOADS[name][1:3]
-            g.dev_elmgmrs(st)
-            s2 = slab_check(g, part, params, tables, y, ac, (ny + 1) * (nz + 1), flavour="csr")
-            par["csr"] = {"res": s2["res"], "BDiag": s2["BDiag"], "lhsK": s2["lhsK"],
-                          "csr_rows_bit_exact": s2["csr_rows_bit_exact"], "blocks_checked": s2["blocks"]}
-            par["ok"] = bool(par["ok"] and s2["csr_rows_bit_exact"] and max(s2["res"], s2["BDiag"], s2["lhsK"]) < 1e-10)
-        except Exception as e:
-            par["csr"] = {"error": repr(e)[:200]}
-            par["ok"] = False
+    if "sparse" in r and not args.no_check:
+        # the block-CSR flavour of the same part: lhsK blocks and CSR rows against the oracle's.  EVERY rank assembles
+        # (the assembly exchanges halos); only rank 0 reads its part back and runs the oracle on slabs of it.
+        g.dev_elmgmrs(st)
+        if isinstance(par, dict) and "error" not in par:
+            try:
+                from oracle.spot_check import slab_check
+                ny, nz = WORKLOADS[name][1:3]
+                s2 = slab_check(g, part, params, tables, y, ac, (ny + 1) * (nz + 1), flavour="csr")
+                par["csr"] = {"res": s2["res"], "BDiag": s2["BDiag"], "lhsK": s2["lhsK"],
+                              "csr_rows_bit_exact": s2["csr_rows_bit_exact"], "blocks_checked": s2["blocks"]}
+                par["ok"] = bool(par["ok"] and s2["csr_rows_bit_exact"]
+                                 and max(s2["res"], s2["BDiag"], s2["lhsK"]) < 1e-10)
+            except Exception as e:
+                par["csr"] = {"error": repr(e)[:200]}
+                par["ok"] = False
     if isinstance(par, dict) and "sparse" in r and "solgmre" in r:
         par["iterations_ebe_csr"] = [r["solgmre"]["gmres_iterations"], r["sparse"]["gmres_iterations"]]
         par["ok"] = bool(par["ok"] and abs(par["iterations_ebe_csr"][0] - par["iterations_ebe_csr"][1]) <= 1)
@@ -736,6 +738,7 @@ def side_workload(env, args, name, params, tables, init_comm, steps):
            "ap": r.get("ap"), "solgmre": r.get("solgmre"), "sparse": r.get("sparse"), "parity": par,
            "egmass_GB_per_gpu": part.numel * (5 * max(int(b.shape[1]) for b in part.mien)) ** 2 * 8 / 1e9,
            "setup_s": setup_s}
+    env.barrier()        # rank 0 has been checking its part: nobody tears its communicator down before that is over
     env.g = None
     g.close()
     return out
@@ -743,6 +746,10 @@ def side_workload(env, args, name, params, tables, init_comm, steps):
 
 def main():
     _quiet_stdout()
+    # a rank that leaves the SPMD sequence early (an exception on one rank only) would leave the others waiting in a
+    # collective for ever: after 15 minutes every rank dumps its Python stack and exits instead
+    import faulthandler
+    faulthandler.dump_traceback_later(900, exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
