@@ -638,7 +638,7 @@ def time_workload(env, g, part, steps, warmup, *, solve=True, sparse=True, resid
             "sparseap_per_s": 1e3 / sap_ms, "sparseap_ms": sap_ms, "sparseap_kernel_ms": sap_k_ms,
             "solve_ms": ssm, "gmres_iterations": int(s_its[-1]), "ms_per_iteration": ssm / max(1, s_its[-1]),
             "implicit_solve_ms": ssm + asm_s_ms,
-            "roofline_sparseap": {"bound": "hbm", "kernel": "k_sparseap", "unit": "GB/s",
+            "roofline_sparseap": {"bound": "hbm", "kernel": "k_sparseap_tma<false>", "unit": "GB/s",
                                   "achieved": csr_bytes / (sap_k_ms * 1e-3) / 1e9,
                                   "algorithmic_bytes": csr_bytes}}
     return out
