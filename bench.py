@@ -747,9 +747,9 @@ def side_workload(env, args, name, params, tables, init_comm, steps):
 def main():
     _quiet_stdout()
     # a rank that leaves the SPMD sequence early (an exception on one rank only) would leave the others waiting in a
-    # collective for ever: after 15 minutes every rank dumps its Python stack and exits instead
+    # collective for ever: after 10 minutes every rank dumps its Python stack and exits instead
     import faulthandler
-    faulthandler.dump_traceback_later(900, exit=True)
+    faulthandler.dump_traceback_later(600, exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
