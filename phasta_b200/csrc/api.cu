@@ -236,6 +236,7 @@ extern "C" int phb200_init(phb200_ctx **out, const phb200_common *c, const int *
   PHB_TRY(dev_alloc(&ctx->d_dots, (size_t)c->Kspace + 8));
   PHB_CHECK(cudaMallocHost(&ctx->h_dots, sizeof(double) * ((size_t)c->Kspace + 8)));
   PHB_TRY(dev_alloc(&ctx->d_ptmp, n5));
+  PHB_TRY(dev_alloc(&ctx->d_p5, n5));
   {
     const size_t nk = phb_kry_doubles(c->Kspace), nf = (size_t)c->Kspace + 4;
     PHB_TRY(dev_alloc(&ctx->d_kry, nk));
@@ -269,7 +270,7 @@ extern "C" void phb200_finalize(phb200_ctx *ctx) {
                   ctx->d_rmass, ctx->d_res, ctx->d_rmes, ctx->d_Dy, ctx->d_temp, ctx->d_BDiag, ctx->d_BDtmp,
                   ctx->d_EG, ctx->d_uBrg, ctx->d_dots, ctx->d_scratch, ctx->d_ienb, ctx->d_iBCB,
                   ctx->d_BCB, ctx->d_aerfrc, ctx->d_colm, ctx->d_rowp, ctx->d_rowofblk, ctx->d_eloc, ctx->d_lhsK,
-                  ctx->d_nodeaos, ctx->d_yold, ctx->d_acold, ctx->d_mfg, ctx->d_ptmp, ctx->d_kry, ctx->d_kflag, ctx->d_apchunk, ctx->d_elc, ctx->d_inc, ctx->d_inc_ptr};
+                  ctx->d_nodeaos, ctx->d_yold, ctx->d_acold, ctx->d_mfg, ctx->d_ptmp, ctx->d_p5, ctx->d_kry, ctx->d_kflag, ctx->d_apchunk, ctx->d_elc, ctx->d_inc, ctx->d_inc_ptr};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   if (ctx->d_refel_tet) cudaFree(ctx->d_refel_tet);

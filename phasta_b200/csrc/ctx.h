@@ -150,6 +150,7 @@ struct phb200_ctx {
   // Krylov loop without the host in it (solver.cu): the Ap input with slaves filled, the Hessenberg / Givens state
   // and the per-iteration status words on the device, pinned mirrors, one event per in-flight iteration
   double *d_ptmp;                // [5][nshg]
+  double *d_p5;                  // [nshg][5] node-major copy of the vector SparseAp gathers from
   double *d_kry, *h_kry;         // layout: KryLayout (solver.cu)
   int *d_kflag, *h_kflag;        // [0] done, [1] iKs at convergence, [2 + iK] status of iteration iK (1 run, 2 converged)
   cudaEvent_t kev[4];

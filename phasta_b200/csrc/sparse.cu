@@ -413,7 +413,16 @@ struct ApSmem {
   int r0[NST], r1[NST], direct[NST];  // the chunk a stage holds (written by the producer)
 };
 
-template <bool STAGEA>
+// p <- node-major copy p5[node][5] of the Krylov vector p[5][nshg]: the 25 lanes of a block then gather their five
+// entries of p from ONE 40-byte piece (1-2 sectors) instead of five sectors nshg apart -- ncu showed the L1 91 % busy
+__global__ void k_node_major(int nshg, const double *__restrict__ p, double *__restrict__ p5) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)nshg * 5) return;
+  const int i = (int)(t / 5), g = (int)(t % 5);
+  p5[t] = p[(size_t)nshg * g + i];
+}
+
+template <bool STAGEA, bool PNM = false>
 __global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
     k_sparseap_tma(int nshg, int nchunk, const int *__restrict__ chunk, const int *__restrict__ colm,
                    const int *__restrict__ rowp, const double *__restrict__ lhsK, const double *__restrict__ p,
@@ -462,7 +471,9 @@ __global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
   // -------------------------------------------------------------- consumers
   const bool act = lane < 25;
   const int l = act ? lane : 0;
-  const double *__restrict__ pg = p + (size_t)nshg * (l / 5);
+  // PNM: p is the node-major copy, entry g of node j at p[5 j + g]
+  const double *__restrict__ pg = PNM ? p + (l / 5) : p + (size_t)nshg * (l / 5);
+  constexpr int PS = PNM ? 5 : 1;
   int it = 0;
   for (int c = blockIdx.x; c < nchunk; c += gridDim.x, it++) {
     const int stg = it % AP_STAGES_;
@@ -481,7 +492,7 @@ __global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
       if (direct) {
         // a row that does not fit a stage
         const int k0 = colm[r], k1 = colm[r + 1];
-        for (int k = k0; k < k1; k++) acc0 += __ldcs(lhsK + (size_t)25 * k + l) * __ldg(pg + __ldg(rowp + k));
+        for (int k = k0; k < k1; k++) acc0 += __ldcs(lhsK + (size_t)25 * k + l) * __ldg(pg + (size_t)PS * __ldg(rowp + k));
       } else {
         const int k0 = T.rowptr[r - ra], k1 = T.rowptr[r - ra + 1];
         const int *cj = T.col + (k0 - ka);
@@ -491,7 +502,7 @@ __global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
           for (int k = k0; k < k1; k += 16, a += 400, cj += 16) {
             double pv[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) pv[i] = __ldg(pg + ((k + i < k1) ? cj[i] : r));
+            for (int i = 0; i < 16; i++) pv[i] = __ldg(pg + (size_t)PS * ((k + i < k1) ? cj[i] : r));
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
               acc0 += ((k + i < k1) ? a[25 * i] : 0.0) * pv[i];
@@ -507,7 +518,7 @@ __global__ void __launch_bounds__(32 * (AP_WARPS + 1), AP_CTAS)
             for (int i = 0; i < 8; i++) {
               const bool ok = k + i < k1;
               av[i] = ok ? __ldcs(a + 25 * i) : 0.0;
-              pv[i] = __ldg(pg + (ok ? cj[i] : r));
+              pv[i] = __ldg(pg + (size_t)PS * (ok ? cj[i] : r));
             }
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {
@@ -564,17 +575,28 @@ int phb_sparseap2(phb200_ctx *ctx, double *d_p, double *d_out, const int *d_skip
                                      (int)sizeof(ApSmem<true>)));
       PHB_CHECK(cudaFuncSetAttribute(k_sparseap_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(ApSmem<false>)));
+      PHB_CHECK(cudaFuncSetAttribute(k_sparseap_tma<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(ApSmem<false>)));
       attr_set = true;
     }
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
     const int grid = std::min(ctx->n_apchunk, nsm * AP_CTAS);
-    if (stage_a)
+    // PHB200_AP_NODEMAJOR=0: gather p from the [5][nshg] vector itself (A/B runs)
+    static const bool node_major = !(getenv("PHB200_AP_NODEMAJOR") && atoi(getenv("PHB200_AP_NODEMAJOR")) == 0);
+    if (stage_a) {
       k_sparseap_tma<true><<<grid, 32 * (AP_WARPS + 1), sizeof(ApSmem<true>), s>>>(
           nshg, ctx->n_apchunk, ctx->d_apchunk, ctx->d_colm, ctx->d_rowp, ctx->d_lhsK, d_p, d_out, d_skip);
-    else
+    } else if (node_major) {
+      const size_t n5 = (size_t)nshg * 5;
+      k_node_major<<<(unsigned)((n5 + 255) / 256), 256, 0, s>>>(nshg, d_p, ctx->d_p5);
+      ctx->launches++;
+      k_sparseap_tma<false, true><<<grid, 32 * (AP_WARPS + 1), sizeof(ApSmem<false>), s>>>(
+          nshg, ctx->n_apchunk, ctx->d_apchunk, ctx->d_colm, ctx->d_rowp, ctx->d_lhsK, ctx->d_p5, d_out, d_skip);
+    } else {
       k_sparseap_tma<false><<<grid, 32 * (AP_WARPS + 1), sizeof(ApSmem<false>), s>>>(
           nshg, ctx->n_apchunk, ctx->d_apchunk, ctx->d_colm, ctx->d_rowp, ctx->d_lhsK, d_p, d_out, d_skip);
+    }
 #else
     size_t threads = (size_t)nshg * 32;
     k_sparseap<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(nshg, ctx->d_colm, ctx->d_rowp, ctx->d_lhsK, d_p,
