@@ -485,13 +485,6 @@ __device__ __forceinline__ int bc_elim_mask(int ibc) {
   return m;
 }
 
-// One slot of the asynchronous CSR scatter of the warp-specialised kernel: the 32 blocks of a warp-task, entry-major
-// (padded so that both the element-wise writes and the entry-wise reads are conflict-free), and their CSR indices
-struct ScatSlot {
-  double v[25][33];
-  int k[32];
-};
-
 // Tail of AsIGMR for one (a,b) block of one element: BDiag extraction before the BCs (asigmr.f:92-102, SURVEY
 // B3), bc3LHS on the block in registers (bc3lhs.f:1-290; rows by node a's code, columns by node b's), then the
 // coalesced store into the element tile (LHS==1) or the fillsparseC scatter into lhsK (LHS==2).
@@ -545,17 +538,6 @@ __device__ __forceinline__ void finish_block(double (&acc)[5][5], int a, int b, 
     }
   }
   if (LHS == 3) return;
-  if (LHS == 4) {
-    // fillsparseC handed to the scatter warps (k_asigmr_tet_ws2): park the block and its CSR index in the ring slot
-    ScatSlot *sl = reinterpret_cast<ScatSlot *>(stage);
-    const int lane = threadIdx.x & 31;
-    sl->k[lane] = (ge < numel) ? eloc[(size_t)(NSHL * a + b) * numel_pad + ge] : -1;
-#pragma unroll
-    for (int n = 0; n < 5; n++)
-#pragma unroll
-      for (int m = 0; m < 5; m++) sl->v[m + 5 * n][lane] = acc[m][n];
-    return;
-  }
   if (LHS == 5) {
 #if !defined(PHB_HOST_EMUL) && !defined(PHB_HOST_FULL)
     // fillsparseC through the bulk-copy engine (k_asigmr_tet_ws2): every lane parks its block in its own 208-byte
@@ -1185,10 +1167,9 @@ struct WsTile {
   int nd[4][TILE_E];
   int ibc[4][TILE_E];
 };
-#define WS_NSLOT 12
 #define STAGE_BULK_DBL (32 * 26)  // per-consumer stage of the bulk-engine CSR scatter: 32 blocks of 208 bytes
-template <int LHS, int WS_NPROD, int WS_NCONS, int WS_NSCAT = 0>
-__global__ void __launch_bounds__(32 * (WS_NCONS + WS_NPROD + WS_NSCAT), 1) k_asigmr_tet_ws2(
+template <int LHS, int WS_NPROD, int WS_NCONS>
+__global__ void __launch_bounds__(32 * (WS_NCONS + WS_NPROD), 1) k_asigmr_tet_ws2(
     int numel, size_t numel_pad, int nshg, int numnp, int ntiles, const int *__restrict__ ien,
     const double *__restrict__ aos, const int *__restrict__ iBC, const double *__restrict__ BC,
     double *__restrict__ res, double *__restrict__ BDiag, double *__restrict__ EG, const int *__restrict__ eloc,
@@ -1199,49 +1180,17 @@ __global__ void __launch_bounds__(32 * (WS_NCONS + WS_NPROD + WS_NSCAT), 1) k_as
   Tile *tiles = reinterpret_cast<Tile *>(smem_raw);
   unsigned long long *full = reinterpret_cast<unsigned long long *>(smem_raw + WS_NBUF * sizeof(Tile));
   unsigned long long *empty = full + WS_NBUF;
-  // LHS==2 with scatter warps: ring of WS_NSLOT block slots between the consumers and the scatter warps
-  unsigned long long *sfull = empty + WS_NBUF, *sempty = sfull + WS_NSLOT;
-  ScatSlot *slots = reinterpret_cast<ScatSlot *>(smem_raw + WS_NBUF * sizeof(Tile) +
-                                                 (2 * WS_NBUF + 2 * WS_NSLOT) * sizeof(unsigned long long));
-  constexpr bool ASYNC = (LHS == 2 && WS_NSCAT > 0);
-  constexpr int LHS_B = ASYNC ? 4 : (LHS == 2 ? 5 : LHS);  // CSR: scatter warps (4) or the bulk-copy engine (5)
+  constexpr int LHS_B = (LHS == 2) ? 5 : LHS;  // CSR: scatter through the bulk-copy engine (finish_block<5>)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < WS_NBUF; i++) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], WS_NCONS);
     }
-    for (int i = 0; i < WS_NSLOT; i++) {
-      mbar_init(&sfull[i], 1);
-      mbar_init(&sempty[i], 1);
-    }
     mbar_fence_init();
   }
   __syncthreads();
-  if (ASYNC && warp >= WS_NCONS + WS_NPROD) {
-    // ------------------------------ scatter warps: fillsparseC (fillsparse.f:66-126) ------------------------------
-    // lane l < 25 adds entry l of every parked block: one warp-wide red.f64 covers the 25 contiguous doubles of a block
-    const int mytiles = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const long long ntask = (long long)mytiles * 16;
-    for (long long T = warp - (WS_NCONS + WS_NPROD); T < ntask; T += WS_NSCAT) {
-      const int slot = (int)(T % WS_NSLOT);
-      const ScatSlot &sl = slots[slot];
-      mbar_wait(&sfull[slot], (unsigned)((T / WS_NSLOT) & 1));
-      // all 32 values of this lane's entry first (one round trip to shared memory), then 32 reductions back to back
-      const int kk = sl.k[lane];
-      const int l25 = lane < 25 ? lane : 0;
-      double v[32];
-#pragma unroll
-      for (int e = 0; e < 32; e++) v[e] = sl.v[l25][e];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sempty[slot]);  // the slot is in registers: the consumers may refill it
-#pragma unroll
-      for (int e = 0; e < 32; e++) {
-        const int ke = __shfl_sync(0xffffffffu, kk, e);
-        if (ke >= 0 && lane < 25) atomicAdd(lhsK + (size_t)25 * ke + lane, v[e]);
-      }
-    }
-  } else if (warp >= WS_NCONS) {
+  if (warp >= WS_NCONS) {
     // ------------------------------ producers: whole tiles, dealt round-robin ------------------------------
     for (int it = warp - WS_NCONS;; it += WS_NPROD) {
       const long long tile_ll = (long long)blockIdx.x + (long long)it * gridDim.x;
@@ -1358,11 +1307,10 @@ __global__ void __launch_bounds__(32 * (WS_NCONS + WS_NPROD + WS_NSCAT), 1) k_as
   } else {
     // ------------------------------ consumers -----------------------------
     // LHS==2: per-consumer-warp staging tile for the CSR scatter (see finish_block)
-    double *stage = (LHS == 2 && !ASYNC)
-                        ? reinterpret_cast<double *>(smem_raw + WS_NBUF * sizeof(Tile) +
-                                                     (2 * WS_NBUF + 2 * WS_NSLOT) * sizeof(unsigned long long)) +
-                              warp * STAGE_BULK_DBL
-                        : nullptr;
+    double *stage = (LHS == 2) ? reinterpret_cast<double *>(smem_raw + WS_NBUF * sizeof(Tile) +
+                                                            2 * WS_NBUF * sizeof(unsigned long long)) +
+                                     warp * STAGE_BULK_DBL
+                               : nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
       const int buf = it % WS_NBUF;
@@ -1370,20 +1318,8 @@ __global__ void __launch_bounds__(32 * (WS_NCONS + WS_NPROD + WS_NSCAT), 1) k_as
       mbar_wait(&full[buf], (it / WS_NBUF) & 1);
       // tasks it*16 + pair with (it*16 + pair) % WS_NCONS == warp
       int pair = (warp - (it * 16) % WS_NCONS + WS_NCONS) % WS_NCONS;
-      for (; pair < 16; pair += WS_NCONS) {
-        if (ASYNC) {
-          const long long T = (long long)it * 16 + pair;
-          const int slot = (int)(T % WS_NSLOT);
-          const long long use = T / WS_NSLOT;
-          if (use > 0) mbar_wait(&sempty[slot], (unsigned)((use - 1) & 1));  // the previous block of this slot is in lhsK
-          phase_b_task<TILE_E, NQ, LHS_B>(sm, pair, 0, lane, tile, numel, numel_pad, nshg, BC, BDiag, EG, eloc, lhsK,
-                                          reinterpret_cast<double *>(slots + slot));
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sfull[slot]);
-        } else {
-          phase_b_task<TILE_E, NQ, LHS_B>(sm, pair, 0, lane, tile, numel, numel_pad, nshg, BC, BDiag, EG, eloc, lhsK, stage);
-        }
-      }
+      for (; pair < 16; pair += WS_NCONS)
+        phase_b_task<TILE_E, NQ, LHS_B>(sm, pair, 0, lane, tile, numel, numel_pad, nshg, BC, BDiag, EG, eloc, lhsK, stage);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[buf]);
     }
@@ -2433,12 +2369,12 @@ static int launch_asigmr(phb200_ctx *ctx) {
 template <int LHS>
 static int launch_asigmr_ws(phb200_ctx *ctx) { return launch_asigmr<32, 4, LHS>(ctx); }
 #else
-template <int LHS, int NP, int NC, int NS = 0>
+template <int LHS, int NP, int NC>
 static int launch_asigmr_ws2(phb200_ctx *ctx) {
   const phb200_common &c = ctx->c;
-  const size_t smem = WS_NBUF * sizeof(WsTile<32, 4>) + (2 * WS_NBUF + 2 * WS_NSLOT) * sizeof(unsigned long long) +
-                      (LHS == 2 ? (NS > 0 ? WS_NSLOT * sizeof(ScatSlot) : NC * STAGE_BULK_DBL * sizeof(double)) : 0);
-  auto kern = k_asigmr_tet_ws2<LHS, NP, NC, NS>;
+  const size_t smem = WS_NBUF * sizeof(WsTile<32, 4>) + 2 * WS_NBUF * sizeof(unsigned long long) +
+                      (LHS == 2 ? NC * STAGE_BULK_DBL * sizeof(double) : 0);
+  auto kern = k_asigmr_tet_ws2<LHS, NP, NC>;
   static bool configured = false;
   if (!configured) {
     PHB_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -2451,7 +2387,7 @@ static int launch_asigmr_ws2(phb200_ctx *ctx) {
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
   KScope ks(ctx, KC_ASM);
-  kern<<<grid, 32 * (NP + NC + NS), smem, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, c.nshg, c.numnp, ntiles, ctx->d_ien,
+  kern<<<grid, 32 * (NP + NC), smem, ctx->stream>>>(ctx->numel_tet, ctx->numel_pad, c.nshg, c.numnp, ntiles, ctx->d_ien,
                                                     ctx->d_nodeaos, ctx->d_iBC, ctx->d_BC, ctx->d_res, ctx->d_BDiag,
                                                     ctx->d_EG, ctx->d_eloc, ctx->d_lhsK);
   PHB_CHECK(cudaGetLastError());
@@ -2464,17 +2400,10 @@ static int launch_asigmr_ws(phb200_ctx *ctx) {
   // PHB200_WS_PROD = producer warps of the second generation (2, 3 or 4 of the 12 warps of a CTA)
   static const bool gen1 = getenv("PHB200_ASM_WS") && atoi(getenv("PHB200_ASM_WS")) == 1;
   if (!gen1) {
-    // measured on 4.03 M tets (profiles/r02j): EBE tiles 6.17 / 6.33 / 5.97 ms with 2 / 3 / 4 producers;
-    // CSR scatter by the consumers themselves 8.15 / 8.97 / 9.31 ms.  Defaults: 4 + 8 for the EBE tiles; for the CSR
-    // flavour 2 producers + 8 consumers + 2 scatter warps (PHB200_WS_SCAT=0: consumers scatter, 2 + 10)
+    // measured on 4.03 M tets (profiles/r02jk_ws2_split_sweep.txt): EBE tiles 6.17 / 6.33 / 5.97 ms with 2 / 3 / 4
+    // producers; the CSR flavour (scatter through the bulk-copy engine) 6.74 / 7.41 / 7.21 ms.  Two or three dedicated
+    // scatter warps were tried and lost (12.9 / 9.3 ms: a warp issues one 25-lane red.f64 per ~112 cycles).
     static const int np = getenv("PHB200_WS_PROD") ? atoi(getenv("PHB200_WS_PROD")) : (LHS == 2 ? 2 : 4);
-    static const int ns = getenv("PHB200_WS_SCAT") ? atoi(getenv("PHB200_WS_SCAT")) : 0;
-    if constexpr (LHS == 2) {
-      if (ns > 0) {
-        if (ns == 3) return launch_asigmr_ws2<LHS, 2, 7, 3>(ctx);
-        return launch_asigmr_ws2<LHS, 2, 8, 2>(ctx);
-      }
-    }
     if (np == 2) return launch_asigmr_ws2<LHS, 2, 10>(ctx);
     if (np == 3) return launch_asigmr_ws2<LHS, 3, 9>(ctx);
     return launch_asigmr_ws2<LHS, 4, 8>(ctx);

@@ -541,20 +541,6 @@ __global__ void k_backsolve(KryLayout L, double *kry, int iKs) {
   }
 }
 
-// v <- v / sqrt(*nrm2) (solgmr.f:251-256) or v <- v * alpha
-__global__ void k_scale_dev(size_t n, double *v, const double *nrm2) {
-  const double f = sqrt(*nrm2);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    v[i] = v[i] / f;
-}
-__global__ void k_scale(size_t n, double *v, double divisor) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    v[i] = v[i] / divisor;
-}
-__global__ void k_axpy(size_t n, double *y, double a, const double *__restrict__ x) {
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-    y[i] = y[i] + a * x[i];
-}
 // Dy += sum_j yBrg(j) uBrg(:,:,j) in one pass (solgmr.f:315-317)
 __global__ void k_update(size_t n, double *Dy, const double *__restrict__ U, int nvec, const double *__restrict__ yb) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
