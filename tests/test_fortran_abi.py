@@ -31,6 +31,10 @@ ARGS = {
 }
 
 
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
 def _c_args(name):
     src = open(SRC).read()
     m = re.search(r"void %s_\((.*?)\)\s*\{" % name, src, re.S)
@@ -62,6 +66,91 @@ def test_common_blocks_stay_undefined_in_the_drop_in():
         assert re.search(r"^\s+U %s_$" % blk, out, re.M), blk
 
 
+# ------------------------------------------------- the host side of the boundary, against a recording stub of the C-ABI
+def test_common_blocks_reach_the_c_abi_and_itrpar_comes_back(tmp_path):
+    """fortran_abi.c compiled together with a stub of libphb200.so that records its arguments: every COMMON scalar the
+    path reads must arrive in phb200_common / phb200_step, the registered block pointers and the call's own array
+    arguments must be the ones handed to phb200_init / phb200_set_sparse, and iKs / lGMRES / ntotGM (iKss ... for
+    SolGMRs, eGMRES for SolMFG) must come back in COMMON /itrpar/."""
+    from phasta_b200.lib import PhbCommon, PhbStep
+    so = str(tmp_path / "libfabi_stub.so")
+    subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", "-o", so, SRC, os.path.join(HERE, "fortran_abi", "commons.c"),
+                           os.path.join(HERE, "fortran_abi", "stub_phb200.c")])
+    L = C.CDLL(so)
+    case = make_case(6, 4, 3, bc="channel", ibksiz=50, etol=3e-5, Kspace=37)
+    params, tables, parts, states = case
+    mp = parts[0]
+    # the two structs exactly as the ctypes binding of the product fills them (without creating a device context)
+    c = PhbCommon()
+    c.nshg, c.numnp, c.numel, c.numelb = mp.nshg, mp.numnp, mp.numel, 0
+    c.nflow, c.ndof, c.ndofBC, c.nshape, c.nedof = 5, 5, 6, 4, 20
+    c.nelblk, c.nelblb, c.nlwork, c.numpe, c.myrank = mp.nelblk, 0, mp.nlwork, 1, 0
+    for nm in ("ipord", "idiff", "itau", "iremoveStabTimeTerm", "EntropyPressure", "iDC", "Navier", "Kspace", "nGMRES",
+               "minIters", "matflg2", "matflg3"):
+        setattr(c, nm, int(getattr(params, nm)))
+    for nm in ("Rgas", "gamma", "gamma1", "pr", "datmat121", "datmat221", "datmat321", "datmat131", "epsM", "dtsfct",
+               "taucfct", "temper"):
+        setattr(c, nm, float(getattr(params, nm)))
+    for i in range(6):
+        c.nint[i], c.nintb[i] = int(tables["nint"][i]), int(tables["nintb"][i])
+    q = np.asfortranarray(tables["Qwt"]).ravel(order="F")
+    C.memmove(c.Qwt, q.ctypes.data, q.nbytes)
+    st = PhbStep()
+    st.lhs, st.iprec, st.iter, st.nitr, st.lstep, st.istep = 1, 1, 2, 3, 120, 7
+    st.Dtgl, st.almi, st.alfi, st.gami, st.etol = 1.0e3, 0.9, 0.8, 0.7, 3e-5
+    lcblk = np.asfortranarray(mp.lcblk, dtype=np.int32)
+    L.drv_fill_commons(C.byref(c), C.byref(st), _p(lcblk), None, 4321)
+    mien = [np.asfortranarray(b, dtype=np.int32) for b in mp.mien]
+    for b, ien in enumerate(mien):
+        L.phb200_register_block_(C.byref(C.c_int(b + 1)), _p(ien))
+    nshg = mp.nshg
+    arr = {k: np.zeros(8) for k in ("yold", "acold", "EG", "BD", "H", "e", "yb", "rc", "rs", "rerr", "lhsk")}
+    y, ac, res, Dy = (np.zeros((nshg, 5), order="F") for _ in range(4))
+    x, iBC, BC = np.asfortranarray(mp.x), np.ascontiguousarray(mp.iBC, dtype=np.int32), np.asfortranarray(mp.BC)
+    iper, il = np.ascontiguousarray(mp.iper, dtype=np.int32), np.ascontiguousarray(mp.ilwork, dtype=np.int32)
+    tabs = [np.asfortranarray(tables[k], dtype=np.float64) for k in ("shp", "shgl", "shpb", "shglb")]
+    L.solgmre_(_p(y), _p(ac), _p(arr["yold"]), _p(arr["acold"]), _p(x), _p(iBC), _p(BC), _p(arr["EG"]), _p(res),
+               _p(arr["BD"]), _p(arr["H"]), _p(arr["e"]), _p(arr["yb"]), _p(arr["rc"]), _p(arr["rs"]), _p(iper), _p(il),
+               *[_p(t) for t in tabs], _p(Dy), _p(arr["rerr"]))
+    got = PhbCommon.in_dll(L, "stub_common")
+    for name, _ in PhbCommon._fields_:
+        a, b = getattr(got, name), getattr(c, name)
+        if hasattr(a, "__len__"):
+            if name in ("Qwtb",):
+                continue                                    # not set above
+            assert list(a) == list(b), name
+        else:
+            assert a == b, name
+    gst = PhbStep.in_dll(L, "stub_step")
+    for name, _ in PhbStep._fields_:
+        assert getattr(gst, name) == getattr(st, name), name
+    ptrs = (C.c_void_p * 16).in_dll(L, "stub_ptrs")
+    want = [lcblk, mien[0], mien[-1], x, iBC, BC, iper, il] + tabs
+    # lcblk is the COMMON block's own storage (filled from `lcblk` by the stand-in), the rest are the caller's arrays
+    assert [ptrs[i] for i in range(1, 12)] == [w.ctypes.data for w in want[1:]]
+    itr, eg = (C.c_int * 6)(), C.c_double(0)
+    L.drv_get_itrpar(itr, C.byref(eg))
+    assert (res[0, 0], Dy[0, 0]) == (11.0, 12.0) and list(itr)[:3] == [17, 0, 17]
+    # SolGMRs: colm / rowp go to phb200_set_sparse once, with COMMON nnz_tot; counters land in iKss / lGMRESs / ntotGMs
+    colm, rowp = np.arange(5, dtype=np.int32), np.arange(7, dtype=np.int32)
+    for _ in range(2):
+        L.solgmrs_(_p(y), _p(ac), _p(arr["yold"]), _p(arr["acold"]), _p(x), _p(iBC), _p(BC), _p(colm), _p(rowp),
+                   _p(arr["lhsk"]), _p(res), _p(arr["BD"]), _p(arr["H"]), _p(arr["e"]), _p(arr["yb"]), _p(arr["rc"]),
+                   _p(arr["rs"]), _p(iper), _p(il), *[_p(t) for t in tabs], _p(Dy), _p(arr["rerr"]))
+    calls = (C.c_int * 8).in_dll(L, "stub_calls")
+    assert list(calls)[:6] == [1, 1, 2, 0, 1, 0]            # one context, one set_sparse, two sparse solves
+    assert (ptrs[12], ptrs[13], C.c_int.in_dll(L, "stub_nnz_tot").value) == (colm.ctypes.data, rowp.ctypes.data, 4321)
+    L.drv_get_itrpar(itr, C.byref(eg))
+    assert list(itr) == [17, 0, 17, 9, 1, 18]
+    L.solmfg_(_p(y), _p(ac), _p(arr["yold"]), _p(arr["acold"]), _p(x), _p(iBC), _p(BC), _p(res), _p(arr["BD"]),
+              _p(arr["H"]), _p(arr["e"]), _p(arr["yb"]), _p(arr["rc"]), _p(arr["rs"]), _p(iper), _p(il),
+              *[_p(t) for t in tabs], _p(Dy), _p(arr["rerr"]))
+    L.drv_get_itrpar(itr, C.byref(eg))
+    assert list(itr)[:3] == [5, 0, 22] and (res[0, 0], Dy[0, 0]) == (31.0, 32.0)
+    L.phb200_fortran_finalize_()
+    assert list(calls)[5] == 1
+
+
 # ---------------------------------------------------------------------------------------------------- GPU
 def _stand_in():
     bdir = os.path.join(HERE, "fortran_abi", "_build")
@@ -73,10 +162,6 @@ def _stand_in():
         subprocess.check_call(["gcc", "-O1", "-fPIC", "-shared", "-o", so, src])
     com = C.CDLL(so, mode=C.RTLD_GLOBAL)        # the COMMON blocks must be visible when the drop-in is loaded
     return com, C.CDLL(LIBF)
-
-
-def _p(a):
-    return a.ctypes.data_as(C.c_void_p)
 
 
 @pytest.mark.gpu
