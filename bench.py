@@ -10,10 +10,17 @@ bc3BDg, lhs=1, iprec=1) over the whole synthetic mesh, state resident in HBM.
 At N=1 the workload is BASELINE.json configs[1]: compressible channel,
 128x64x82 hexes x 6 = 4 030 464 linear tets; at N>1 each GPU
 gets a slab of the same per-GPU size (weak scaling, ilwork halo over NCCL).
-The same JSON line carries Ap/s (EBE Au1GMR + bc3per) and the whole SolGMRe
-(assembly + BDiag-preconditioned GMRES), the roofline of the dominant kernel,
-the end-to-end number through the C-ABI with host buffers, and the CPU
-baseline (oracle port, -O3 -march=native, one replica per host core).
+Before anything is timed the line checks itself: a small partitioned SolGMRe
+against the oracle through the communicator that is timed next, and rank 0's
+full-size part against the oracle on slabs (oracle/spot_check.py); a mismatch
+ends the run with exit code 1.  The same JSON line carries Ap/s (EBE Au1GMR +
+bc3per), the whole SolGMRe and SolGMRs, the roofline of the dominant kernel,
+the end-to-end numbers through the C-ABI with host buffers (phb200_elmgmre and
+the whole phb200_solgmrs call), the CPU baseline (oracle port, -O3
+-march=native, one replica per host core) and a second BASELINE.json
+configuration in its own context: c5_tet_32M (32 M tets, north_star's
+single-GPU target) at N=1, c3_plate_mixed_4M per GPU (tets + wedges) at N>1.
+DESIGN.md section 6 explains every key.
 """
 from __future__ import annotations
 
