@@ -1,4 +1,5 @@
-"""Pins SURVEY row a28 (genblk / gensav / lcblk / mien) to the reference: common/genblkPosix.f and common/gensav.f are
+"""Pins SURVEY row a28 (genblk / gensav / lcblk / mien) to the reference: common/genblkPosix.f and common/gensav.f --
+and the boundary variant common/genbkbPosix.f + gensvb.f (lcblkb, mienb, miBCB, mBCB) -- are
 executed UNMODIFIED by f77np; the two phio calls they make (phio_readheader / phio_readdatablock, the `use phio`
 interface of common/phio.f90) are bound to phasta_b200.phio.PhioFile reading a geombc file written by
 phasta_b200.phio.write_geombc.  So the chain checked is: the file this repo writes -> the reference's own block
@@ -23,6 +24,12 @@ sys.path.insert(0, HERE)
 from f77np import Program, scan_functions  # noqa: E402
 
 REF = "/root/reference/phSolver/common"
+# boundary blocks (genbkbPosix.f + gensvb.f): name -> (make_case arguments, IBKSZ)
+BCASES = {
+    "tet_bnd": (dict(nx=5, ny=4, nz=3, topo="tet", boundary=True, natural="mixed"), 32),
+    "mixed_bnd": (dict(nx=6, ny=6, nz=4, topo="mixed", boundary=True, natural="mixed"), 20),   # tets, wedge tri + quad faces
+    "hex_bnd": (dict(nx=4, ny=3, nz=3, topo="hex", boundary=True, natural="mixed"), 4096),
+}
 # name -> (make_case arguments, IBKSZ)
 CASES = {
     "tet": (dict(nx=5, ny=4, nz=3, topo="tet"), 64),             # 360 tets: five full blocks and a ragged one
@@ -33,7 +40,7 @@ CASES = {
 
 def build_case(name):
     from common import make_case
-    kw, ibksz = CASES[name]
+    kw, ibksz = (CASES[name] if name in CASES else BCASES[name])
     kw = dict(kw)
     nx, ny, nz = kw.pop("nx"), kw.pop("ny"), kw.pop("nz")
     return make_case(nx, ny, nz, bc="channel", ibksiz=ibksz, **kw), ibksz
@@ -76,9 +83,65 @@ def run_genblk(path, ntopo, ibksz):
         [np.array(p.p, dtype=np.int32) for p in prog.M["mmat"][:nelblk]]
 
 
+def run_genbkb(path, ntopo, ibksz):
+    """genbkbPosix.f + gensvb.f on the geombc file `path`: lcblkb(10,nelblb+1), mienb, miBCB, mBCB per block"""
+    from phasta_b200 import phio
+
+    f = phio.PhioFile(path, "r")
+
+    def readheader(prog, fh, phrase, ints, n, dtype, iotype):
+        h = f.readheader(phrase.rstrip("\0").strip(), int(n), "integer")
+        ints[:len(h)] = h
+
+    def readdatablock(prog, fh, phrase, arr, n, dtype, iotype):
+        data = f.readdatablock(phrase.rstrip("\0").strip(), int(n), dtype.rstrip("\0").strip())
+        arr.reshape(-1, order="F")[:int(n)] = data
+
+    readheader.array_args = (2,)
+    readdatablock.array_args = (2,)
+    prog = Program([REF], modules={"fhandle": 0, "iotype": "binary", "c_null_char": "\0", "nsynciofieldsreadgeombc": 0,
+                                   "mienb": [], "mibcb": [], "mbcb": [], "mmatb": [],
+                                   "_comp_dtype": {"mienb": np.int64, "mibcb": np.int64, "mmatb": np.int64,
+                                                   "mbcb": np.float64}},
+                   stubs={"phio_readheader": readheader, "phio_readdatablock": readdatablock})
+    for fn in ("gensvb.f", "genbkbPosix.f"):
+        scan_functions(os.path.join(REF, fn))
+        prog.load(os.path.join(REF, fn))
+    G = prog.G
+    # what readnblk.f has set before genbkb: nelblb = boundary topology blocks in the file, ndof, ndiBCB, ndBCB
+    G.update(nelblb=ntopo, ndof=5, ndibcb=2, ndbcb=6, numpe=1, myrank=0, npro=0, nshl=0, nshlb=0, nenbl=0, mattyp=0,
+             ndofl=0, lcsyst=0, nenl=0, zero=0.0)
+    G["lcblkb"] = np.zeros((10, 50001), dtype=np.int64, order="F")
+    prog.call("genbkbposix", ibksz)
+    f.close()
+    n = int(G["nelblb"])
+    M = prog.M
+    return (np.array(G["lcblkb"][:, :n + 1], dtype=np.int32, order="F"),
+            [np.array(p.p, dtype=np.int32, order="F") for p in M["mienb"][:n]],
+            [np.array(p.p, dtype=np.int32, order="F") for p in M["mibcb"][:n]],
+            [np.array(p.p, dtype=np.float64, order="F") for p in M["mbcb"][:n]])
+
+
 def generate():
     from phasta_b200 import phio
     out = {}
+    for name in BCASES:
+        (params, tables, parts, states), ibksz = build_case(name)
+        with tempfile.TemporaryDirectory() as d:
+            path = phio.write_geombc(parts[0], d)
+            # one 'connectivity boundary' block per boundary kind in the file (genbkbPosix.f loops nelblb times)
+            kinds = []
+            for b in range(parts[0].nelblb):
+                k = (int(parts[0].lcblkb[2, b]), int(parts[0].lcblkb[5, b]))
+                if k not in kinds:
+                    kinds.append(k)
+            lcblkb, mienb, mibcb, mbcb = run_genbkb(path, len(kinds), ibksz)
+        out["%s_lcblkb" % name] = lcblkb
+        out["%s_nelblb" % name] = np.int32(len(mienb))
+        for i in range(len(mienb)):
+            out["%s_mienb_%d" % (name, i)] = mienb[i]
+            out["%s_mibcb_%d" % (name, i)] = mibcb[i]
+            out["%s_mbcb_%d" % (name, i)] = mbcb[i]
     for name in CASES:
         (params, tables, parts, states), ibksz = build_case(name)
         with tempfile.TemporaryDirectory() as d:

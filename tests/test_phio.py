@@ -218,6 +218,33 @@ def test_blocks_match_the_executed_genblkposix(tmp_path, name):
         assert list(np.unique(z["mixed_lcblk"][2, :-1])) == [1, 3]
 
 
+def _genbkb_cases():
+    sys.path.insert(0, GOLD)
+    from make_golden_genblk import BCASES
+    return list(BCASES)
+
+
+@pytest.mark.parametrize("name", _genbkb_cases())
+def test_boundary_blocks_match_the_executed_genbkbposix(tmp_path, name):
+    """the boundary-element variant: common/genbkbPosix.f + gensvb.f (connectivity boundary / nbc codes / nbc values,
+    the zeroing of unset flux values, blocking by IBKSZ) executed by f77np over this repo's geombc file -> lcblkb and
+    every mienb / miBCB / mBCB block; mesh._boundary_elements and phio.read_geombc must give the same"""
+    from make_golden_genblk import build_case
+    z = np.load(os.path.join(GOLD, "f77_genblk.npz"))
+    (params, tables, parts, states), ibksz = build_case(name)
+    p = parts[0]
+    q = phio.read_geombc(os.path.dirname(os.path.dirname(phio.write_geombc(p, str(tmp_path)))), 0, 1, ibksz)
+    n = int(z["%s_nelblb" % name])
+    assert n > 0
+    for mp in (p, q):
+        assert mp.nelblb == n
+        assert np.array_equal(mp.lcblkb, z["%s_lcblkb" % name])
+        for i in range(n):
+            assert np.array_equal(mp.mienb[i], z["%s_mienb_%d" % (name, i)])
+            assert np.array_equal(mp.miBCB[i], z["%s_mibcb_%d" % (name, i)])
+            assert np.array_equal(mp.mBCB[i], z["%s_mbcb_%d" % (name, i)])
+
+
 def test_genblk_fixture_reproduces_from_the_reference():
     if not os.path.isdir("/root/reference/phSolver/common"):
         pytest.skip("reference sources not present")
