@@ -62,3 +62,24 @@ def test_solmfg_parity(topo):
     res2, Dy2 = g.SolGMRe(y, ac, step=g.step(lhs=1, iprec=1, etol=1e-6))
     assert rel_l2(Dy, Dy2) < 5e-3
     g.close()
+
+
+def test_solmfg_partitioned():
+    """two parts over the in-process transport: the halo exchanges inside Au1MFG / ItrRes and the (lag-one) device-side
+    Krylov loop of the matrix-free flavour against the oracle's in-process two-part run"""
+    from test_gpu_multipart import run_parts
+    case, o = prepared(8, 4, 3, nparts=2)
+    params, tables, parts, states = case
+    o.set_flags(lhs=0, iprec=1)
+    iKs, lG, eG = o.SolMFG(eGMRES=0.0, iter=1, istep=0)
+
+    def fn(g, y, ac):
+        return g.SolMFG(y, ac, step=g.step(lhs=0, iprec=1, iter=1, istep=0), eGMRES=0.0)
+
+    gs, out = run_parts(case, fn)
+    for g, op, (res, Dy) in zip(gs, o.parts, out):
+        assert abs(g.eGMRES - eG) < 1e-3 * eG
+        assert abs(g.iKs - iKs) <= 1
+        assert rel_l2(res, op.res) < 1e-10
+        assert rel_l2(Dy, op.Dy) < 1e-4
+    [g.close() for g in gs]
