@@ -58,6 +58,20 @@ def test_exported_with_the_reference_argument_list(name):
         assert [a.lower() for a in _fortran_args(os.path.join(REF, f[0]), f[1])] == [a.lower() for a in ARGS[name]]
 
 
+def test_library_exports_every_symbol_the_header_declares():
+    txt = open(os.path.join(ROOT, "include", "phb200_fortran.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    syms = sorted(set(re.findall(r"\bvoid\s+([a-z0-9_]+_)\s*\(", txt)))
+    assert syms == sorted(["solgmre_", "solgmrs_", "solmfg_", "phb200_register_block_", "phb200_register_blockb_",
+                           "phb200_fortran_unique_id_", "phb200_fortran_comm_id_", "phb200_fortran_finalize_"])
+    out = subprocess.run(["nm", "-D", "--defined-only", LIBF], capture_output=True, text=True, check=True).stdout
+    for s_ in syms:
+        assert re.search(r" T %s$" % s_, out, re.M), "libphb200_f.so does not export %s" % s_
+    # and the definitions compile against the declarations (same argument types)
+    subprocess.check_call(["gcc", "-fsyntax-only", "-Wall", "-Werror", "-include",
+                           os.path.join(ROOT, "include", "phb200_fortran.h"), SRC])
+
+
 def test_common_blocks_stay_undefined_in_the_drop_in():
     """the Fortran executable owns the COMMON storage: the library must only reference it"""
     out = subprocess.run(["nm", "-D", LIBF], capture_output=True, text=True, check=True).stdout
