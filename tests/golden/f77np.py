@@ -334,6 +334,11 @@ class ExprParser:
             return "(-%s)" % self.primary()
         if kind == "id" and val.endswith("_") and self.peek() is not None and self.peek()[0] == "str":
             return repr(self.next()[1])          # kind-prefixed character literal: c_char_'integer'
+        if kind == "id" and val == "c_loc" and self.peek() == ("op", "(") and self.p + 2 < len(self.t) \
+                and self.t[self.p + 1][0] == "id" and self.t[self.p + 2] == ("op", ")"):
+            name = self.t[self.p + 1][1]             # c_loc(name): the array itself, or a reference to the scalar
+            self.p += 3
+            return "_cloc(_E,%r)" % name
         if kind == "id":
             src = val
             if self.accept("("):
@@ -579,6 +584,24 @@ def _ref(E, name, args):
     raise TypeError("f77np: %r is a scalar (%r) but is referenced with arguments" % (name, obj))
 
 
+class ScalarRef:
+    """c_loc(scalar): a reference a python stub can store through (phio_readheader writing a COMMON scalar)"""
+
+    def __init__(self, E, name):
+        self.E, self.name = E, name
+
+    def set(self, v):
+        self.E.prog._assign(self.E, self.name, None, v)
+
+    def get(self):
+        return self.E[self.name]
+
+
+def _cloc(E, name):
+    obj = E[name]
+    return obj if isinstance(obj, np.ndarray) else ScalarRef(E, name)
+
+
 def _elemview(E, name, args):
     try:
         obj = E[name]
@@ -602,7 +625,7 @@ def scan_functions(path):
             FUNCTION_UNITS.add(m.group(1).lower())
 
 
-HELPERS = dict(_elemview=_elemview, _ref=_ref, _idx=_idx, _sl=_sl, _div=_div, _pow=_pow, _eq=_eq, _ne=_ne, _and=_and,
+HELPERS = dict(_cloc=_cloc, _elemview=_elemview, _ref=_ref, _idx=_idx, _sl=_sl, _div=_div, _pow=_pow, _eq=_eq, _ne=_ne, _and=_and,
                _or=_or, _not=_not, _eqv=_eqv, _neqv=_neqv, np=np, math=math)
 
 
@@ -650,7 +673,7 @@ class _Goto(Exception):
 
 _TYPES = ("real", "integer", "logical", "character", "double", "complex")
 _IGNORED = ("write", "print", "read", "open", "close", "format", "implicit", "external", "save",
-            "intrinsic", "data", "use", "rewind", "flush", "equivalence", "nullify", "interface")
+            "intrinsic", "data", "use", "rewind", "flush", "equivalence", "nullify", "interface", "type")
 
 
 def _split_top(toks, sep=","):
@@ -1198,6 +1221,11 @@ class Program:
         for dname in unit.order:
             d = unit.decls[dname]
             if d.dims is None:
+                # a character scalar starts out blank (its content is undefined in Fortran; file names built by
+                # formatted internal writes, which are not interpreted, only ever reach python stubs)
+                if d.typ == "character" and dname not in unit.args and dname not in L \
+                        and dname not in self.M and not (unit.uses_common and dname in self.G):
+                    L[dname] = ""
                 continue
             if d.alloc:
                 continue

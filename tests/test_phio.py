@@ -253,3 +253,71 @@ def test_genblk_fixture_reproduces_from_the_reference():
     new = generate()
     assert set(new) == set(z.files)
     assert all(np.array_equal(new[k], z[k]) for k in new)
+
+
+# ---- f-2: the file format against the reference's own reader, readnblk.f (executed by f77np over this repo's files) --
+def _readnblk_cases():
+    sys.path.insert(0, GOLD)
+    from make_golden_readnblk import CASES
+    return list(CASES)
+
+
+@pytest.mark.parametrize("name", _readnblk_cases())
+def test_files_read_by_the_executed_readnblk_give_what_the_repo_reader_gives(tmp_path, name):
+    """tests/golden/f77_readnblk.npz: what the UNMODIFIED common/readnblk.f (+ genblkPosix / gensav / genbkbPosix /
+    gensvb) holds after reading the geombc and restart files phio.write_geombc / write_restart produce -- the
+    /conpar/ scalars and derived constants, x, the raw BC arrays, iper, every interior and boundary block, qold, acold,
+    lstep.  phio.read_geombc / read_restart must return the same from the same files (the BC arrays after geniBC /
+    genBC1, which tests/golden/f77_genbc1.npz pins separately)."""
+    from make_golden_readnblk import build_case
+    z = np.load(os.path.join(GOLD, "f77_readnblk.npz"))
+    Z = lambda k: z["%s_%s" % (name, k)]  # noqa: E731
+    (params, tables, parts, states), ibksz, lstep = build_case(name)
+    p = parts[0]
+    y, ac = states[0]
+    d = str(tmp_path)
+    phio.write_geombc(p, d)
+    phio.write_restart(d, 0, 1, lstep, y, ac)
+    q = phio.read_geombc(d, 0, 1, ibksz)
+    sc = dict(zip(("numnp", "nshg", "numel", "numelb", "nen", "nelblk", "nelblb", "numpbc", "nflow", "ndof", "ndofBC", "ndiBCB",
+                   "ndBCB", "nsymdf", "nenb", "lstep", "nlwork", "nshg0"), (int(v) for v in Z("scalars"))))
+    assert (sc["numnp"], sc["nshg"], sc["numel"]) == (q.numnp, q.nshg, q.numel)
+    assert sc["numelb"] == sum(b.shape[0] for b in q.mienb) and sc["nen"] == max(b.shape[1] for b in q.mien)
+    assert (sc["nelblk"], sc["nelblb"]) == (q.nelblk, q.nelblb)            # after genblk / genbkb: blocks, not topologies
+    assert (sc["nflow"], sc["ndof"], sc["ndofBC"], sc["ndiBCB"], sc["ndBCB"], sc["nsymdf"]) == (5, 5, 6, 2, 6, 15)
+    assert (sc["lstep"], sc["nlwork"], sc["nshg0"]) == (lstep, 1, q.nshg)
+    assert np.array_equal(Z("x"), q.x)
+    assert np.array_equal(Z("lcblk"), q.lcblk) and np.array_equal(Z("lcblkb"), q.lcblkb)
+    for i in range(q.nelblk):
+        assert np.array_equal(Z("mien_%d" % i), q.mien[i])
+    for i in range(q.nelblb):
+        assert np.array_equal(Z("mienb_%d" % i), q.mienb[i]) and np.array_equal(Z("mibcb_%d" % i), q.miBCB[i])
+        assert np.array_equal(Z("mbcb_%d" % i), q.mBCB[i])
+    # periodic masters: 0 in the file = the node itself
+    raw = Z("iper")
+    assert np.array_equal(np.where(raw == 0, np.arange(1, q.nshg + 1), raw), q.iper)
+    # essential BCs: geniBC (genibc.f:17-19) and genBC (genbc.f:20-25) + genBC1 on the arrays the Fortran read
+    nBC, iBCtmp, BCinp = Z("nBC"), Z("iBCtmp"), Z("BCinp")
+    assert sc["numpbc"] == iBCtmp.size == BCinp.shape[0] and BCinp.shape[1] == 12
+    iBC = np.zeros(q.nshg, dtype=np.int32)
+    sel = nBC != 0
+    iBC[sel] = iBCtmp[nBC[sel] - 1]
+    assert np.array_equal(iBC, q.iBC)
+    BCtmp = np.zeros((q.nshg, 12), order="F")
+    BCtmp[sel] = BCinp[nBC[sel] - 1]
+    assert np.array_equal(phio.genBC1(BCtmp, iBC), q.BC)
+    # restart: the reference keeps the file's column order {p,u,v,w,T}; restar('in') permutes to {u,v,w,p,T}
+    y2, ac2, lstep2 = phio.read_restart(d, 0, 1, q.nshg)
+    inv = [1, 2, 3, 0, 4]
+    assert lstep2 == lstep and np.array_equal(Z("qold")[:, inv], y2) and np.array_equal(Z("acold")[:, inv], ac2)
+    assert np.array_equal(y2, y) and not Z("uold").any()
+
+
+def test_readnblk_fixture_reproduces_from_the_reference():
+    if not os.path.isdir("/root/reference/phSolver/common"):
+        pytest.skip("reference sources not present")
+    from make_golden_readnblk import generate
+    z = np.load(os.path.join(GOLD, "f77_readnblk.npz"))
+    new = generate()
+    assert set(new) == set(z.files)
+    assert all(np.array_equal(new[k], z[k]) for k in new)
