@@ -25,26 +25,32 @@ sys.path.insert(0, HERE)
 from f77np import Program, ScalarRef, scan_functions  # noqa: E402
 
 REF = "/root/reference/phSolver/common"
+# name -> (make_case arguments, IBKSZ, lstep, rank read)
 CASES = {
-    "tet_bnd": (dict(nx=5, ny=4, nz=3, topo="tet", boundary=True, natural="mixed", bc="channel"), 32, 120),
-    "mixed_allcodes": (dict(nx=6, ny=6, nz=4, topo="mixed", boundary=True, natural="mixed", bc="allcodes"), 20, 7),
+    "tet_bnd": (dict(nx=5, ny=4, nz=3, topo="tet", boundary=True, natural="mixed", bc="channel"), 32, 120, 0),
+    "mixed_allcodes": (dict(nx=6, ny=6, nz=4, topo="mixed", boundary=True, natural="mixed", bc="allcodes"), 20, 7, 0),
+    # the middle part of three: the numpe > 1 branch ('size of ilwork array', 'ilwork', ctypes), split segments
+    "tet_part2of3": (dict(nx=6, ny=3, nz=3, topo="tet", boundary=True, natural="mixed", bc="channel", nparts=3, max_seg=7),
+                     32, 40, 1),
 }
 
 
 def build_case(name):
     from common import make_case
-    kw, ibksz, lstep = CASES[name]
+    kw, ibksz, lstep, rank = CASES[name]
     kw = dict(kw)
     nx, ny, nz = kw.pop("nx"), kw.pop("ny"), kw.pop("nz")
-    return make_case(nx, ny, nz, ibksiz=ibksz, **kw), ibksz, lstep
+    return make_case(nx, ny, nz, ibksiz=ibksz, **kw), ibksz, lstep, rank
 
 
-def run_readnblk(root, ibksz, lstep):
-    """readnblk.f on <root>/1-procs_case/{geombc.dat.1, restart.<lstep>.1}: returns a dict of what it read"""
+def run_readnblk(root, ibksz, lstep, rank=0, numpe=1):
+    """readnblk.f as rank `rank` of `numpe` on <root>/<numpe>-procs_case/{geombc.dat.<rank+1>, restart.<lstep>.<rank+1>}:
+    returns a dict of what it read"""
     from phasta_b200 import phio
 
-    d = phio.case_dir(root, 1)
-    files = {"geombc": os.path.join(d, "geombc.dat.1"), "restart": os.path.join(d, "restart.%d.1" % lstep)}
+    d = phio.case_dir(root, numpe)
+    files = {"geombc": os.path.join(d, "geombc.dat.%d" % (rank + 1)),
+             "restart": os.path.join(d, "restart.%d.%d" % (lstep, rank + 1))}
     state = {"next": None, "f": None, "opened": []}
 
     def construct(prog, fh, kind, fname):
@@ -74,6 +80,14 @@ def run_readnblk(root, ibksz, lstep):
     def error(prog, *a):
         raise RuntimeError("reference called error(%r)" % (a,))
 
+    def ctypes_stub(prog, il):
+        # ctypes.f:36-47 (executed for real by make_golden_commu.py): iother becomes 0-based; the MPI datatypes it
+        # also builds do not exist outside an MPI run
+        pos = 1
+        for _ in range(int(il[0])):
+            il[pos + 2] -= 1
+            pos += 4 + 2 * int(il[pos + 3])
+
     noop = lambda prog, *a: None  # noqa: E731
     mods = {"fhandle": 0, "iotype": "binary", "c_null_char": "\0", "nsynciofieldsreadgeombc": 0,
             "geomrestartstream": 0, "geombc_read": 1, "restart_read": 2, "cname2": lambda i: ".%d" % int(i),
@@ -84,14 +98,14 @@ def run_readnblk(root, ibksz, lstep):
                    stubs={"phio_readheader": readheader, "phio_readdatablock": readdatablock, "phio_openfile": openfile,
                           "phio_closefile": closefile, "phio_constructname": construct, "phastaio_setfile": noop,
                           "posixio_setup": noop, "streamio_setup_read": noop, "syncio_setup_read": noop,
-                          "phstr_appendint": noop, "phstr_appendstr": noop, "error": error,
+                          "phstr_appendint": noop, "phstr_appendstr": noop, "error": error, "ctypes": ctypes_stub,
                           "drvallreducemaxint": lambda prog, a, b: {1: lstep}})
     for fn in ("gensav.f", "genblkPosix.f", "gensvb.f", "genbkbPosix.f", "readnblk.f"):
         scan_functions(os.path.join(REF, fn))
         prog.load(os.path.join(REF, fn))
     G = prog.G
     # what input.f / the input.config plumbing has set before readnblk is called (compressible, no scalars, posix)
-    G.update(myrank=0, master=0, numpe=1, input_mode=0, ibksiz=ibksz, usingpetsc=0, svlsflag=0, istretchoutlet=0,
+    G.update(myrank=rank, master=0, numpe=numpe, input_mode=0, ibksiz=ibksz, usingpetsc=0, svlsflag=0, istretchoutlet=0,
              iles=0, itwmod=0, nohomog=0, ideformwall=0, nsynciofiles=1, melcat=8, nsd=3, zero=0.0, one=1.0,
              npro=0, nshl=0, nshlb=0, nenbl=0, mattyp=0, ndofl=0, nsymdl=0, lcsyst=0, nenl=0, nfacel=0, maxsh=32,
              numnp=0, nshg=0, numel=0, numelb=0, nen=0, nelblk=0, nelblb=0, numpbc=0, ntopsh=0, nlwork=0, nshg0=0,
@@ -116,7 +130,8 @@ def run_readnblk(root, ibksz, lstep):
            "iper": np.array(L["point2iper"], dtype=np.int32), "qold": np.array(L["qold"]),
            "acold": np.array(L["acold"]), "uold": np.array(L["uold"]),
            "lcblk": np.array(G["lcblk"][:, :nelblk + 1], dtype=np.int32),
-           "lcblkb": np.array(G["lcblkb"][:, :nelblb + 1], dtype=np.int32)}
+           "lcblkb": np.array(G["lcblkb"][:, :nelblb + 1], dtype=np.int32),
+           "ilwork": np.array(L["point2ilwork"], dtype=np.int32) if numpe > 1 else np.zeros(1, dtype=np.int32)}
     M = prog.M
     for i in range(nelblk):
         out["mien_%d" % i] = np.array(M["mien"][i].p, dtype=np.int32)
@@ -132,12 +147,12 @@ def generate():
     from phasta_b200 import phio
     out = {}
     for name in CASES:
-        (params, tables, parts, states), ibksz, lstep = build_case(name)
-        y, ac = states[0]
+        (params, tables, parts, states), ibksz, lstep, rank = build_case(name)
+        y, ac = states[rank]
         with tempfile.TemporaryDirectory() as d:
-            phio.write_geombc(parts[0], d)
-            phio.write_restart(d, 0, 1, lstep, y, ac)
-            r = run_readnblk(d, ibksz, lstep)
+            phio.write_geombc(parts[rank], d)
+            phio.write_restart(d, rank, len(parts), lstep, y, ac)
+            r = run_readnblk(d, ibksz, lstep, rank, len(parts))
         for k, v in r.items():
             out["%s_%s" % (name, k)] = v
     return out

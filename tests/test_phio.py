@@ -272,20 +272,26 @@ def test_files_read_by_the_executed_readnblk_give_what_the_repo_reader_gives(tmp
     from make_golden_readnblk import build_case
     z = np.load(os.path.join(GOLD, "f77_readnblk.npz"))
     Z = lambda k: z["%s_%s" % (name, k)]  # noqa: E731
-    (params, tables, parts, states), ibksz, lstep = build_case(name)
-    p = parts[0]
-    y, ac = states[0]
+    (params, tables, parts, states), ibksz, lstep, rank = build_case(name)
+    p = parts[rank]
+    y, ac = states[rank]
+    numpe = len(parts)
     d = str(tmp_path)
     phio.write_geombc(p, d)
-    phio.write_restart(d, 0, 1, lstep, y, ac)
-    q = phio.read_geombc(d, 0, 1, ibksz)
+    for r in sorted({0, rank}):                            # (rank 0 writes numstart.dat)
+        phio.write_restart(d, r, numpe, lstep, *states[r])
+    q = phio.read_geombc(d, rank, numpe, ibksz)
     sc = dict(zip(("numnp", "nshg", "numel", "numelb", "nen", "nelblk", "nelblb", "numpbc", "nflow", "ndof", "ndofBC", "ndiBCB",
                    "ndBCB", "nsymdf", "nenb", "lstep", "nlwork", "nshg0"), (int(v) for v in Z("scalars"))))
     assert (sc["numnp"], sc["nshg"], sc["numel"]) == (q.numnp, q.nshg, q.numel)
     assert sc["numelb"] == sum(b.shape[0] for b in q.mienb) and sc["nen"] == max(b.shape[1] for b in q.mien)
     assert (sc["nelblk"], sc["nelblb"]) == (q.nelblk, q.nelblb)            # after genblk / genbkb: blocks, not topologies
     assert (sc["nflow"], sc["ndof"], sc["ndofBC"], sc["ndiBCB"], sc["ndBCB"], sc["nsymdf"]) == (5, 5, 6, 2, 6, 15)
-    assert (sc["lstep"], sc["nlwork"], sc["nshg0"]) == (lstep, 1, q.nshg)
+    if numpe == 1:
+        assert (sc["lstep"], sc["nlwork"], sc["nshg0"]) == (lstep, 1, q.nshg)
+    else:       # 'size of ilwork array' / 'ilwork', then ctypes: iother 0-based, segments as written
+        assert (sc["lstep"], sc["nlwork"]) == (lstep, q.nlwork) and np.array_equal(Z("ilwork"), q.ilwork)
+        assert int(q.ilwork[0]) == 2                      # the middle part talks to both neighbours
     assert np.array_equal(Z("x"), q.x)
     assert np.array_equal(Z("lcblk"), q.lcblk) and np.array_equal(Z("lcblkb"), q.lcblkb)
     for i in range(q.nelblk):
@@ -307,7 +313,7 @@ def test_files_read_by_the_executed_readnblk_give_what_the_repo_reader_gives(tmp
     BCtmp[sel] = BCinp[nBC[sel] - 1]
     assert np.array_equal(phio.genBC1(BCtmp, iBC), q.BC)
     # restart: the reference keeps the file's column order {p,u,v,w,T}; restar('in') permutes to {u,v,w,p,T}
-    y2, ac2, lstep2 = phio.read_restart(d, 0, 1, q.nshg)
+    y2, ac2, lstep2 = phio.read_restart(d, rank, numpe, q.nshg)
     inv = [1, 2, 3, 0, 4]
     assert lstep2 == lstep and np.array_equal(Z("qold")[:, inv], y2) and np.array_equal(Z("acold")[:, inv], ac2)
     assert np.array_equal(y2, y) and not Z("uold").any()
