@@ -61,3 +61,51 @@ def test_ours_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                        timeout=300)
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
+def _rank_dependent_collectives(path):
+    """(if-line, call-line, name) of every communicating call inside an `if` whose test depends on the rank: it mentions
+    `rank` itself or a variable that is assigned (as a plain name) inside a rank-conditioned block"""
+    import ast
+    collective = {"dev_elmgmre", "dev_elmgmrs", "dev_solve", "dev_solve_sparse", "dev_solve_mfg", "dev_ap", "dev_sparseap",
+                  "dev_au1mfg", "dev_elmmfg", "dev_inc_elmgmr", "dev_inc_apfull", "comm_init", "barrier", "all_reduce",
+                  "broadcast", "SolGMRe", "SolGMRs", "SolMFG", "ElmGMRe", "ElmGMRs", "commu", "sumgat", "TimeStep",
+                  "time_workload", "side_workload", "e2e_legs", "bench_mfg", "bench_incomp", "parity_small", "init_comm"}
+    tree = ast.parse(open(path).read())
+
+    def names(test):
+        return {getattr(n, "id", None) or getattr(n, "attr", None) for n in ast.walk(test)
+                if isinstance(n, (ast.Name, ast.Attribute))}
+
+    tainted = {"rank"}
+    for _ in range(3):                       # propagate: assigned under a tainted condition -> tainted
+        for node in ast.walk(tree):
+            if isinstance(node, ast.If) and names(node.test) & tainted:
+                for sub in node.body + node.orelse:
+                    for n in ast.walk(sub):
+                        if isinstance(n, ast.Assign):
+                            tainted |= {t.id for t in n.targets if isinstance(t, ast.Name)}
+    bad = []
+    for node in ast.walk(tree):
+        if isinstance(node, ast.If) and names(node.test) & tainted:
+            for sub in node.body + node.orelse:
+                for n in ast.walk(sub):
+                    if isinstance(n, ast.Call):
+                        f = n.func
+                        name = f.attr if isinstance(f, ast.Attribute) else getattr(f, "id", None)
+                        if name in collective:
+                            bad.append((node.lineno, n.lineno, name))
+    return bad
+
+
+def test_no_collective_call_under_a_rank_condition(tmp_path):
+    """bench.py is SPMD: anything that exchanges halos or reduces across ranks must be called by EVERY rank.  Round 2
+    lost an 8-GPU run to `g.dev_elmgmrs(st)` under `if isinstance(par, dict)` -- and `par` is a dict on rank 0 only:
+    rank 0 waited for a halo nobody sent.  Static check with one level of data flow; the version that hung must be
+    flagged when the history is at hand."""
+    assert not _rank_dependent_collectives(os.path.join(ROOT, "bench.py"))
+    r = subprocess.run(["git", "-C", ROOT, "show", "5c46fed:bench.py"], capture_output=True, text=True)
+    if r.returncode == 0 and "def side_workload" in r.stdout:
+        old = tmp_path / "bench_that_hung.py"
+        old.write_text(r.stdout)
+        assert any(name == "dev_elmgmrs" for _, _, name in _rank_dependent_collectives(str(old)))
